@@ -1,0 +1,66 @@
+"""Builds libdpe_b200.so in-tree with nvcc for sm_100a (no torch dependency in the library)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent / "csrc"
+LIB = CSRC / "libdpe_b200.so"
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "streams.cu", "orbitals_det.cu", "mcmc.cu"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: libdpe_b200.so cannot be built (there is no CPU fallback)")
+    return nvcc
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) + [CSRC.parent.parent / "include" / "dpe_b200.h"]
+    return any(p.stat().st_mtime > t for p in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    nvcc = _nvcc()
+    objdir = CSRC / "build"
+    objdir.mkdir(exist_ok=True)
+
+    def compile_one(src):
+        obj = objdir / (src[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, p
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    log = []
+    for src, obj, p in results:
+        log.append(f"==== {src}\n{p.stderr}")
+        if p.returncode != 0:
+            sys.stderr.write(p.stdout + p.stderr)
+            raise RuntimeError(f"nvcc failed on {src}")
+    (objdir / "ptxas.log").write_text("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    cmd = [nvcc, "-shared", "-o", str(LIB), *[str(o) for _, o, _ in results], "-lcudart"]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stdout + p.stderr)
+        raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,447 @@
+// C ABI of libdpe_b200.so (include/dpe_b200.h): handle, parameter layout, workspace planning and the
+// kernel sequences of log psi^2, E_loc and the Metropolis step.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+#include "dpe_internal.cuh"
+
+namespace dpe {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return DPE_OK;
+    return set_error(DPE_ERR_CUDA, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+}
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---- dims helpers ---------------------------------------------------------------------------------
+static int d_one_in(const dpe_dims &d, int it) { return it == 0 ? 4 * d.n_ion : d.n_hidden_one_el[it - 1]; }
+static int d_pair_in(const dpe_dims &d, int it) { return it == 0 ? 1 : d.n_hidden_two_el[it - 1]; }
+static int d_eion_in(const dpe_dims &d, int it) { return it == 0 ? 4 : d.n_hidden_two_el[it - 1]; }
+
+static int validate_dims(const dpe_dims &d) {
+    if (d.n_el < 2 || d.n_el > 64) return set_error(DPE_ERR_UNSUPPORTED, "n_el=%d outside [2, 64]", d.n_el);
+    if (d.n_up < 1 || d.n_up >= d.n_el) return set_error(DPE_ERR_UNSUPPORTED, "need at least one electron of each spin (n_up=%d)", d.n_up);
+    if (d.n_ion < 1 || d.n_ion > 256) return set_error(DPE_ERR_UNSUPPORTED, "n_ion=%d outside [1, 256]", d.n_ion);
+    if (d.n_iterations < 1 || d.n_iterations > DPE_MAX_ITER) return set_error(DPE_ERR_UNSUPPORTED, "n_iterations=%d", d.n_iterations);
+    if (d.emb_dim < 4 || d.emb_dim > 32 || (d.emb_dim & 3)) return set_error(DPE_ERR_UNSUPPORTED, "emb_dim=%d must be a multiple of 4 in [4, 32]", d.emb_dim);
+    if (d.n_ion_features < 1 || d.n_dets < 1) return set_error(DPE_ERR_UNSUPPORTED, "n_ion_features / n_dets must be positive");
+    if (d.z_max < d.z_min) return set_error(DPE_ERR_ARG, "z_max < z_min");
+    for (int it = 0; it < d.n_iterations; ++it) {
+        if (d.n_hidden_one_el[it] < 4 || (d.n_hidden_one_el[it] & 3)) return set_error(DPE_ERR_UNSUPPORTED, "n_hidden_one_el[%d]=%d must be a multiple of 4", it, d.n_hidden_one_el[it]);
+        if (it + 1 < d.n_iterations && (d.n_hidden_two_el[it] < 4 || d.n_hidden_two_el[it] > 32 || (d.n_hidden_two_el[it] & 3)))
+            return set_error(DPE_ERR_UNSUPPORTED, "n_hidden_two_el[%d]=%d must be a multiple of 4 in [4, 32]", it, d.n_hidden_two_el[it]);
+        int din = d_one_in(d, it);
+        if (3 * din + d.emb_dim + d_eion_in(d, it) == d.n_hidden_one_el[it])
+            return set_error(DPE_ERR_UNSUPPORTED, "h_el_%d would take the residual branch (mlp.py:13-16); not implemented", it);
+    }
+    return DPE_OK;
+}
+
+static void add_leaf(dpe_model *m, int rows, int cols) {
+    Leaf &l = m->leaves[m->n_leaves++];
+    l.off = m->n_params; l.rows = rows; l.cols = cols; l.size = (int64_t)rows * cols;
+    m->n_params += l.size;
+}
+
+static void build_leaves(dpe_model *m) {
+    const dpe_dims &d = m->dims;
+    m->n_leaves = 0; m->n_params = 0;
+    add_leaf(m, d.z_max - d.z_min + 1, d.n_ion_features);
+    for (int it = 0; it < d.n_iterations; ++it) {
+        int din = d_one_in(d, it), dP = d_pair_in(d, it), dE = d_eion_in(d, it), dout = d.n_hidden_one_el[it];
+        add_leaf(m, dP, d.emb_dim); add_leaf(m, 1, d.emb_dim);      // w_same
+        add_leaf(m, dP, d.emb_dim); add_leaf(m, 1, d.emb_dim);      // w_diff
+        add_leaf(m, din, d.emb_dim); add_leaf(m, 1, d.emb_dim);     // h_map
+        add_leaf(m, d.n_ion_features, dE); add_leaf(m, 1, dE);      // h_ion_map
+        add_leaf(m, 3 * din + d.emb_dim + dE, dout); add_leaf(m, 1, dout);   // h_el
+        if (it + 1 < d.n_iterations) {
+            int d2 = d.n_hidden_two_el[it];
+            add_leaf(m, dP, d2); add_leaf(m, 1, d2);                // h_same
+            add_leaf(m, dP, d2); add_leaf(m, 1, d2);                // h_diff
+            add_leaf(m, dE, d2); add_leaf(m, 1, d2);                // h_el_ion
+        }
+    }
+    int cols = d.n_dets * d.n_el, dl = d.n_hidden_one_el[d.n_iterations - 1];
+    add_leaf(m, dl, cols); add_leaf(m, dl, cols);                   // bf_up, bf_dn
+    for (int q = 0; q < 4; ++q) add_leaf(m, d.n_ion, cols);         // alpha_up, alpha_dn, weights_up, weights_dn
+}
+
+static void bind_views(dpe_model *m) {
+    const dpe_dims &d = m->dims;
+    int li = 0;
+    auto next = [&]() { return m->params + m->leaves[li++].off; };
+    auto dense = [&](Dense &L, int din, int dout) { L.w = next(); L.b = next(); L.din = din; L.dout = dout; };
+    m->h_ion_emb = next();
+    float *dv = m->derived;
+    for (int it = 0; it < d.n_iterations; ++it) {
+        IterParams &p = m->it[it];
+        p.d_in = d_one_in(d, it); p.dP = d_pair_in(d, it); p.dE = d_eion_in(d, it); p.d_out = d.n_hidden_one_el[it];
+        p.k_main = p.d_in + d.emb_dim + p.dE;
+        dense(p.w_same, p.dP, d.emb_dim);
+        dense(p.w_diff, p.dP, d.emb_dim);
+        dense(p.h_map, p.d_in, d.emb_dim);
+        dense(p.h_ion_map, d.n_ion_features, p.dE);
+        dense(p.h_el, 3 * p.d_in + d.emb_dim + p.dE, p.d_out);
+        if (it + 1 < d.n_iterations) {
+            int d2 = d.n_hidden_two_el[it];
+            dense(p.h_same, p.dP, d2);
+            dense(p.h_diff, p.dP, d2);
+            dense(p.h_el_ion, p.dE, d2);
+            p.pair_next = d2; p.eion_next = d2;
+        }
+        p.w_main = dv; dv += (size_t)p.k_main * p.d_out;
+        p.w_mean = dv; dv += (size_t)2 * p.d_in * p.d_out;
+        p.him = dv; dv += (size_t)d.n_ion * p.dE;
+        dv = m->derived + align_up((dv - m->derived) * sizeof(float)) / sizeof(float);
+    }
+    m->bf_w[0] = next(); m->bf_w[1] = next();
+    m->alpha[0] = next(); m->alpha[1] = next();
+    m->env_w[0] = next(); m->env_w[1] = next();
+    size_t nsp = (size_t)d.n_ion * d.n_dets * d.n_el;
+    m->sp_alpha[0] = dv; dv += nsp;
+    m->sp_alpha[1] = dv; dv += nsp;
+}
+
+static size_t derived_floats(const dpe_dims &d) {
+    size_t n = 0;
+    for (int it = 0; it < d.n_iterations; ++it) {
+        int din = d_one_in(d, it), dE = d_eion_in(d, it), dout = d.n_hidden_one_el[it];
+        n += (size_t)(din + d.emb_dim + dE) * dout + (size_t)2 * din * dout + (size_t)d.n_ion * dE;
+        n = align_up(n * sizeof(float)) / sizeof(float);
+    }
+    n += 2 * (size_t)d.n_ion * d.n_dets * d.n_el;
+    return n + 64;
+}
+
+// ---- workspace ------------------------------------------------------------------------------------
+static void plan(const dpe_dims &d, int Bc, int C, WsLayout &L) {
+    const int N = d.n_el, CP = C > 1 ? 3 : 1, CE = C > 1 ? 5 : 1;
+    int ldx = 0, max_din = 0, max_dout = 0;
+    for (int it = 0; it < d.n_iterations; ++it) {
+        int din = d_one_in(d, it), km = din + d.emb_dim + d_eion_in(d, it);
+        if (km > ldx) ldx = km;
+        if (din > max_din) max_din = din;
+        if (d.n_hidden_one_el[it] > max_dout) max_dout = d.n_hidden_one_el[it];
+    }
+    if (max_dout > ldx) ldx = max_dout;
+    L.ldx = ldx;
+    size_t off = 0;
+    auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float)); return o; };
+    const size_t rows = (size_t)Bc * N * C;
+    L.x[0] = take(rows * ldx);
+    L.x[1] = take(rows * ldx);
+    L.hm = take(rows * d.emb_dim);
+    L.mean = take((size_t)Bc * C * 2 * max_din);
+    L.add = take((size_t)Bc * C * max_dout);
+    L.pw = off;
+    for (int it = 0; it < d.n_iterations; ++it) L.pw_it[it] = take((size_t)Bc * N * N * CP * d.emb_dim);
+    L.ei = off;
+    for (int it = 0; it < d.n_iterations; ++it) L.ei_it[it] = take((size_t)Bc * N * CE * d_eion_in(d, it));
+    L.mo = take(rows * d.n_dets * N);
+    L.det = take((size_t)Bc * d.n_dets * (C > 1 ? 3 * N + 3 : 2));
+    L.epot = take(Bc);
+    L.lp = take(Bc);
+    L.total_chunk = off;
+}
+
+static void plan_mcmc(const dpe_dims &d, int B, WsLayout &L) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    L.r_prop = take((size_t)B * d.n_el * 3 * sizeof(float));
+    L.lp_prop = take((size_t)B * sizeof(float));
+    L.thr = take((size_t)B * sizeof(float));
+    L.new_keys = take((size_t)B * 2 * sizeof(uint32_t));
+    L.total_mcmc = off;
+}
+
+static int max_chunk(const dpe_dims &d, int C, size_t avail, int B) {
+    WsLayout L;
+    plan(d, B, C, L);
+    if (L.total_chunk <= avail) return B;
+    int lo = 0, hi = B;       // invariant: plan(lo) fits (lo = 0 trivially), plan(hi) does not
+    while (hi - lo > 1) {
+        int mid = lo + (hi - lo) / 2;
+        plan(d, mid, C, L);
+        if (L.total_chunk <= avail) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- kernel sequences -------------------------------------------------------------------------------
+static int gemm(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
+    if (m->gemm_path == 1) {
+        int e = launch_gemm_tc(m, g, s);
+        if (e != DPE_ERR_UNSUPPORTED) return e;
+    }
+    return launch_gemm_simt(m, g, s);
+}
+
+static GemmArgs plain_gemm(const float *A, int lda, const float *W, int ldw, float *Cc, int ldc, int M, int N, int K) {
+    GemmArgs g;
+    g.A = A; g.lda = lda; g.a_seg_len = M > 0 ? M : 1; g.a_seg_stride = 0; g.a_seg_off = 0;
+    g.W = W; g.ldw = ldw;
+    g.C = Cc; g.ldc = ldc; g.c_seg_len = M > 0 ? M : 1; g.c_seg_stride = 0; g.c_seg_off = 0; g.c_col_off = 0;
+    g.M = M; g.N = N; g.K = K;
+    return g;
+}
+
+// One chunk of Bc walkers through the whole network. C = 1 (forward) or 3N+2 (forward Laplacian).
+static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, const WsLayout &L, float *phase, float *logpsi2,
+                     float *grad, float *ekin, float *eloc, float *epot_out, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    const int N = d.n_el, U = d.n_up, D = N - U;
+    const int CP = C > 1 ? 3 : 1, CE = C > 1 ? 5 : 1;
+    (void)CP;
+    float *x[2] = {(float *)(ws + L.x[0]), (float *)(ws + L.x[1])};
+    float *hm = (float *)(ws + L.hm), *mean = (float *)(ws + L.mean), *add = (float *)(ws + L.add);
+    float *mo = (float *)(ws + L.mo), *det = (float *)(ws + L.det), *epot = (float *)(ws + L.epot);
+    size_t pw_off[DPE_MAX_ITER], ei_off[DPE_MAX_ITER];
+    for (int it = 0; it < d.n_iterations; ++it) {
+        pw_off[it] = (L.pw_it[it] - L.pw) / sizeof(float);
+        ei_off[it] = (L.ei_it[it] - L.ei) / sizeof(float);
+    }
+    float *pw = (float *)(ws + L.pw), *ei = (float *)(ws + L.ei);
+    const int ldx = L.ldx;
+    const int rows = Bc * N * C;
+    int e;
+    if ((e = launch_features(m, r, Bc, C, x[0], ldx, C > 1 ? epot : nullptr, s))) return e;
+    if ((e = launch_eion_stream(m, r, Bc, CE, ei, ei_off, s))) return e;
+    if ((e = launch_pair_stream(m, r, Bc, C > 1 ? 3 : 1, pw, pw_off, s))) return e;
+    int cur = 0;
+    for (int it = 0; it < d.n_iterations; ++it) {
+        const IterParams &p = m->it[it];
+        // h_map: [rows, d_in] x [d_in, emb] -> hm, tanh rule
+        if ((e = gemm(m, plain_gemm(x[cur], ldx, p.h_map.w, d.emb_dim, hm, d.emb_dim, rows, d.emb_dim, p.d_in), s))) return e;
+        if ((e = launch_act(m, hm, d.emb_dim, Bc * N, C, d.emb_dim, p.h_map.b, nullptr, 1, s))) return e;
+        // SchNet convolutions fill columns [d_in, k_main)
+        if ((e = launch_conv(m, it, r, Bc, C, hm, pw + pw_off[it], ei + ei_off[it], x[cur], ldx, s))) return e;
+        // spin means and their contribution (shared by all electrons of a walker)
+        if ((e = launch_mean(m, x[cur], ldx, Bc, C, p.d_in, mean, s))) return e;
+        if ((e = gemm(m, plain_gemm(mean, 2 * p.d_in, p.w_mean, p.d_out, add, p.d_out, Bc * C, p.d_out, 2 * p.d_in), s))) return e;
+        // main layer
+        if ((e = gemm(m, plain_gemm(x[cur], ldx, p.w_main, p.d_out, x[cur ^ 1], ldx, rows, p.d_out, p.k_main), s))) return e;
+        if ((e = launch_act(m, x[cur ^ 1], ldx, Bc * N, C, p.d_out, p.h_el.b, add, N, s))) return e;
+        cur ^= 1;
+    }
+    // backflow factors (envelope_orbitals.py:46-75): spin-up / spin-down electrons use different matrices
+    const int cols = d.n_dets * N, dl = d.n_hidden_one_el[d.n_iterations - 1];
+    for (int sp = 0; sp < 2; ++sp) {
+        GemmArgs g = plain_gemm(x[cur], ldx, m->bf_w[sp], cols, mo, cols, Bc * (sp ? D : U) * C, cols, dl);
+        g.a_seg_len = g.c_seg_len = (sp ? D : U) * C;
+        g.a_seg_stride = g.c_seg_stride = N * C;
+        g.a_seg_off = g.c_seg_off = sp ? U * C : 0;
+        if ((e = gemm(m, g, s))) return e;
+    }
+    if ((e = launch_envelope(m, r, Bc, C, mo, s))) return e;
+    if ((e = launch_det(m, Bc, C, mo, det, s))) return e;
+    if ((e = launch_combine(m, Bc, C, det, epot, phase, logpsi2, grad, ekin, eloc, epot_out, s))) return e;
+    return DPE_OK;
+}
+
+static int run_batched(dpe_model *m, const float *r, int B, int C, char *ws, size_t ws_bytes, float *phase, float *logpsi2,
+                       float *grad, float *ekin, float *eloc, float *epot_out, cudaStream_t s) {
+    if (!m->params_set || !m->geom_set) return set_error(DPE_ERR_STATE, "set_params and set_geometry must be called first");
+    const dpe_dims &d = m->dims;
+    int chunk = max_chunk(d, C, ws_bytes, B);
+    if (chunk < 1) return set_error(DPE_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one walker", ws_bytes);
+    const int K = 3 * d.n_el;
+    for (int off = 0; off < B; off += chunk) {
+        int Bc = B - off < chunk ? B - off : chunk;
+        WsLayout L;
+        plan(d, Bc, C, L);
+        float *lp = logpsi2 ? logpsi2 + off : (float *)(ws + L.lp);
+        int e = run_chunk(m, r + (size_t)off * d.n_el * 3, Bc, C, ws, L, phase ? phase + off : nullptr, lp,
+                          grad ? grad + (size_t)off * K : nullptr, ekin ? ekin + off : nullptr, eloc ? eloc + off : nullptr,
+                          epot_out ? epot_out + off : nullptr, s);
+        if (e) return e;
+    }
+    return DPE_OK;
+}
+
+}  // namespace dpe
+
+using namespace dpe;
+
+extern "C" {
+
+const char *dpe_version(void) { return "deeperwin_b200 0.1 (sm_100a)"; }
+const char *dpe_last_error(void) { return g_err; }
+
+int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
+    if (!dims || !out) return set_error(DPE_ERR_ARG, "model_create: null argument");
+    int e = validate_dims(*dims);
+    if (e) return e;
+    dpe_model *m = new (std::nothrow) dpe_model();
+    if (!m) return set_error(DPE_ERR_ARG, "out of host memory");
+    memset(m, 0, sizeof(*m));
+    m->dims = *dims;
+    build_leaves(m);
+    m->derived_floats = derived_floats(*dims);
+    cudaError_t ce = cudaMalloc(&m->params, (size_t)m->n_params * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&m->derived, m->derived_floats * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&m->R_dev, (size_t)dims->n_ion * 3 * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&m->Z_dev, (size_t)dims->n_ion * sizeof(float));
+    if (ce != cudaSuccess) {
+        int rc = check_cuda(ce, "cudaMalloc(model)");
+        dpe_model_destroy(m);
+        return rc;
+    }
+    bind_views(m);
+    *out = m;
+    return DPE_OK;
+}
+
+void dpe_model_destroy(dpe_model *m) {
+    if (!m) return;
+    cudaFree(m->params); cudaFree(m->derived); cudaFree(m->R_dev); cudaFree(m->Z_dev);
+    delete m;
+}
+
+int64_t dpe_param_count(const dpe_model *m) { return m ? m->n_params : 0; }
+int32_t dpe_param_leaf_count(const dpe_model *m) { return m ? m->n_leaves : 0; }
+
+int dpe_param_leaf(const dpe_model *m, int32_t leaf, int64_t *offset, int64_t *size, int32_t *rows, int32_t *cols) {
+    if (!m || leaf < 0 || leaf >= m->n_leaves) return set_error(DPE_ERR_ARG, "param_leaf: bad index");
+    if (offset) *offset = m->leaves[leaf].off;
+    if (size) *size = m->leaves[leaf].size;
+    if (rows) *rows = m->leaves[leaf].rows;
+    if (cols) *cols = m->leaves[leaf].cols;
+    return DPE_OK;
+}
+
+int dpe_model_set_params(dpe_model *m, const float *params_dev, int64_t n, void *stream) {
+    if (!m || !params_dev) return set_error(DPE_ERR_ARG, "set_params: null argument");
+    if (n != m->n_params) return set_error(DPE_ERR_ARG, "set_params: got %lld values, model has %lld", (long long)n, (long long)m->n_params);
+    cudaStream_t s = (cudaStream_t)stream;
+    DPE_CUDA(cudaMemcpyAsync(m->params, params_dev, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    int e = launch_prepare_params(m, s);
+    if (e) return e;
+    m->params_set = true;
+    if (m->geom_set) return launch_prepare_geometry(m, s);   // him depends on the weights too
+    return DPE_OK;
+}
+
+int dpe_model_set_geometry(dpe_model *m, const float *R_host, const int32_t *Z_host, void *stream) {
+    if (!m || !R_host || !Z_host) return set_error(DPE_ERR_ARG, "set_geometry: null argument");
+    const dpe_dims &d = m->dims;
+    cudaStream_t s = (cudaStream_t)stream;
+    float Zf[256];
+    for (int J = 0; J < d.n_ion; ++J) {
+        if (Z_host[J] < d.z_min || Z_host[J] > d.z_max) return set_error(DPE_ERR_ARG, "Z[%d]=%d outside [z_min, z_max]", J, Z_host[J]);
+        Zf[J] = (float)Z_host[J];
+        m->Z_host[J] = Z_host[J];
+    }
+    // ion-ion repulsion (hamiltonian.py:25-31), float32 like the reference
+    float eii = 0.f;
+    for (int I = 0; I < d.n_ion; ++I)
+        for (int J = I + 1; J < d.n_ion; ++J) {
+            float dx = R_host[I * 3] - R_host[J * 3], dy = R_host[I * 3 + 1] - R_host[J * 3 + 1], dz = R_host[I * 3 + 2] - R_host[J * 3 + 2];
+            eii += Zf[I] * Zf[J] / sqrtf(dx * dx + dy * dy + dz * dz);
+        }
+    m->e_ion_ion = eii;
+    // synchronous small copies: the host arrays may be temporaries
+    DPE_CUDA(cudaStreamSynchronize(s));
+    DPE_CUDA(cudaMemcpy(m->R_dev, R_host, (size_t)d.n_ion * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    DPE_CUDA(cudaMemcpy(m->Z_dev, Zf, (size_t)d.n_ion * sizeof(float), cudaMemcpyHostToDevice));
+    m->geom_set = true;
+    if (m->params_set) return launch_prepare_geometry(m, s);
+    return DPE_OK;
+}
+
+size_t dpe_workspace_bytes(const dpe_model *m, int32_t n_walkers, int32_t mode) {
+    if (!m || n_walkers <= 0) return 0;
+    WsLayout L;
+    plan(m->dims, n_walkers, mode == DPE_MODE_LAPLACIAN ? 3 * m->dims.n_el + 2 : 1, L);
+    plan_mcmc(m->dims, n_walkers, L);
+    return L.total_chunk + L.total_mcmc + 256;
+}
+
+int dpe_log_psi_sqr(dpe_model *m, const float *r_dev, int32_t n_walkers, float *phase_dev, float *log_psi_sqr_dev,
+                    void *workspace_dev, size_t workspace_bytes, void *stream) {
+    if (!m || !r_dev || !log_psi_sqr_dev || !workspace_dev || n_walkers <= 0) return set_error(DPE_ERR_ARG, "log_psi_sqr: bad argument");
+    return run_batched(m, r_dev, n_walkers, 1, (char *)workspace_dev, workspace_bytes, phase_dev, log_psi_sqr_dev, nullptr, nullptr,
+                       nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int dpe_local_energy(dpe_model *m, const float *r_dev, int32_t n_walkers, float *e_loc_dev, float *log_psi_sqr_dev,
+                     float *grad_dev, float *e_kin_dev, float *e_pot_dev, void *workspace_dev, size_t workspace_bytes,
+                     void *stream) {
+    if (!m || !r_dev || !e_loc_dev || !workspace_dev || n_walkers <= 0) return set_error(DPE_ERR_ARG, "local_energy: bad argument");
+    return run_batched(m, r_dev, n_walkers, 3 * m->dims.n_el + 2, (char *)workspace_dev, workspace_bytes, nullptr, log_psi_sqr_dev,
+                       grad_dev, e_kin_dev, e_loc_dev, e_pot_dev, (cudaStream_t)stream);
+}
+
+int dpe_mcmc_steps(dpe_model *m, const dpe_mcmc_state *st, int32_t B, int32_t n_steps, const dpe_mcmc_config *cfg,
+                   int32_t recompute_log_psi, int32_t run_controller, int32_t *accept_counts_dev, void *workspace_dev,
+                   size_t workspace_bytes, void *stream) {
+    if (!m || !st || !cfg || !workspace_dev || B <= 0 || n_steps < 0) return set_error(DPE_ERR_ARG, "mcmc_steps: bad argument");
+    if (!st->r_dev || !st->log_psi_sqr_dev || !st->walker_age_dev || !st->rng_state_dev || !st->stepsize_dev || !st->step_nr_dev || !st->acc_rate_dev)
+        return set_error(DPE_ERR_ARG, "mcmc_steps: state has null fields");
+    if (n_steps > 0 && !accept_counts_dev) return set_error(DPE_ERR_ARG, "mcmc_steps: accept_counts_dev is null");
+    cudaStream_t s = (cudaStream_t)stream;
+    WsLayout L;
+    plan_mcmc(m->dims, B, L);
+    if (workspace_bytes <= L.total_mcmc) return set_error(DPE_ERR_WORKSPACE, "workspace too small for the Metropolis scratch");
+    char *ws = (char *)workspace_dev;
+    float *r_prop = (float *)(ws + L.r_prop), *lp_prop = (float *)(ws + L.lp_prop), *thr = (float *)(ws + L.thr);
+    uint32_t *new_keys = (uint32_t *)(ws + L.new_keys);
+    char *ws_net = ws + L.total_mcmc;
+    size_t ws_net_bytes = workspace_bytes - L.total_mcmc;
+    int e;
+    if (recompute_log_psi)
+        if ((e = run_batched(m, st->r_dev, B, 1, ws_net, ws_net_bytes, nullptr, st->log_psi_sqr_dev, nullptr, nullptr, nullptr, nullptr, s))) return e;
+    if (n_steps > 0) DPE_CUDA(cudaMemsetAsync(accept_counts_dev, 0, (size_t)n_steps * sizeof(int32_t), s));
+    for (int t = 0; t < n_steps; ++t) {
+        if ((e = launch_propose(st, B, m->dims.n_el, r_prop, thr, new_keys, s))) return e;
+        m->launches++;
+        if ((e = run_batched(m, r_prop, B, 1, ws_net, ws_net_bytes, nullptr, lp_prop, nullptr, nullptr, nullptr, nullptr, s))) return e;
+        if ((e = launch_accept(st, B, m->dims.n_el, r_prop, lp_prop, thr, new_keys, cfg->max_age, nullptr, accept_counts_dev + t, s))) return e;
+        m->launches++;
+        if (run_controller) {
+            if ((e = launch_controller(st, accept_counts_dev + t, 1, B, *cfg, s))) return e;
+            m->launches++;
+        }
+    }
+    return DPE_OK;
+}
+
+int64_t dpe_debug_ws_offset(const dpe_model *m, int32_t n_walkers, int32_t mode, const char *name) {
+    if (!m || !name || n_walkers <= 0) return -1;
+    WsLayout L;
+    plan(m->dims, n_walkers, mode == DPE_MODE_LAPLACIAN ? 3 * m->dims.n_el + 2 : 1, L);
+    if (!strcmp(name, "x0")) return (int64_t)L.x[0];
+    if (!strcmp(name, "x1")) return (int64_t)L.x[1];
+    if (!strcmp(name, "hm")) return (int64_t)L.hm;
+    if (!strcmp(name, "mean")) return (int64_t)L.mean;
+    if (!strcmp(name, "add")) return (int64_t)L.add;
+    if (!strcmp(name, "mo")) return (int64_t)L.mo;
+    if (!strcmp(name, "det")) return (int64_t)L.det;
+    if (!strcmp(name, "epot")) return (int64_t)L.epot;
+    if (!strcmp(name, "ldx")) return (int64_t)L.ldx;
+    if (!strncmp(name, "pw", 2) && name[2] >= '0' && name[2] < '0' + DPE_MAX_ITER) return (int64_t)L.pw_it[name[2] - '0'];
+    if (!strncmp(name, "ei", 2) && name[2] >= '0' && name[2] < '0' + DPE_MAX_ITER) return (int64_t)L.ei_it[name[2] - '0'];
+    return -1;
+}
+
+int dpe_set_gemm_path(dpe_model *m, int32_t path) {
+    if (!m || (path != 0 && path != 1)) return set_error(DPE_ERR_ARG, "set_gemm_path: path must be 0 or 1");
+    m->gemm_path = path;
+    return DPE_OK;
+}
+int dpe_get_gemm_path(const dpe_model *m) { return m ? m->gemm_path : -1; }
+int64_t dpe_launch_count(const dpe_model *m) { return m ? m->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Internal declarations shared by the kernels of libdpe_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/dpe_b200.h"
+
+#define DPE_MAX_LEAVES (1 + DPE_MAX_ITER * 16 + 6)
+
+namespace dpe {
+
+// Channel convention of every "tangent-carrying" tensor: channel 0 = value, channels 1..n_t = d/dx_k,
+// channel n_t+1 = Laplacian.  Forward-only mode has a single channel (n_t = -1 -> C = 1).
+struct Leaf { int64_t off; int64_t size; int32_t rows, cols; };
+
+struct Dense { const float *w, *b; int din, dout; };
+
+struct IterParams {
+    Dense w_same, w_diff, h_map, h_ion_map, h_el, h_same, h_diff, h_el_ion;  // views into the flat params
+    float *w_main;  // [k_main, d_out]  rows: h_one (d_in) | conv_ee (emb) | conv_eI (dE)  of h_el.w
+    float *w_mean;  // [2*d_in, d_out]  rows: mean_up | mean_dn                            of h_el.w
+    float *him;     // [n_ion, dE] = tanh(Lin_h_ion_map(h_ion[Z]))   (geometry-only)
+    int d_in, dP, dE, d_out, k_main;
+    int pair_next, eion_next;  // widths after this iteration's pair / el-ion layers (0 on the last iteration)
+};
+
+struct GemmArgs {
+    const float *A; int lda;
+    int a_seg_len, a_seg_stride, a_seg_off;   // row m -> (m / seg_len) * seg_stride + seg_off + m % seg_len
+    const float *W; int ldw;                  // [K, N] row-major
+    float *C; int ldc;
+    int c_seg_len, c_seg_stride, c_seg_off, c_col_off;
+    int M, N, K;
+};
+
+// Workspace layout for one chunk of Bc walkers with C channels (byte offsets).
+struct WsLayout {
+    size_t x[2], hm, mean, add, pw, ei, mo, det, epot, lp, total_chunk;
+    size_t ei_it[DPE_MAX_ITER];   // offsets (bytes) of the per-iteration el-ion convolution blocks
+    size_t pw_it[DPE_MAX_ITER];
+    // per-call (full batch) scratch for the Metropolis step
+    size_t r_prop, lp_prop, thr, new_keys, mask, ctrl, total_mcmc;
+    int ldx;       // row stride (floats) of the X buffers
+};
+
+}  // namespace dpe
+
+struct dpe_model {
+    dpe_dims dims;
+    int n_leaves;
+    dpe::Leaf leaves[DPE_MAX_LEAVES];
+    int64_t n_params;
+    float *params;      // device copy of the flat vector
+    float *derived;     // device: w_main / w_mean / softplus(alpha) / him blocks
+    size_t derived_floats;
+    dpe::IterParams it[DPE_MAX_ITER];
+    const float *h_ion_emb;                       // [V, F]
+    const float *bf_w[2], *alpha[2], *env_w[2];   // up, dn
+    float *sp_alpha[2];                           // softplus(alpha) [n_ion, n_det*n_el]
+    float *R_dev;  // [n_ion,3]
+    float *Z_dev;  // [n_ion] as float
+    float e_ion_ion;
+    int32_t Z_host[256];
+    bool params_set, geom_set;
+    int gemm_path;
+    int64_t launches;
+};
+
+namespace dpe {
+
+int set_error(int code, const char *fmt, ...);
+int check_cuda(cudaError_t e, const char *what);
+#define DPE_CUDA(x) do { int _e = dpe::check_cuda((x), #x); if (_e) return _e; } while (0)
+#define DPE_LAUNCH_CHECK(m) do { (m)->launches++; int _e = dpe::check_cuda(cudaGetLastError(), __func__); if (_e) return _e; } while (0)
+
+// gemm_simt.cu
+int launch_gemm_simt(dpe_model *m, const GemmArgs &g, cudaStream_t s);
+// gemm_tc.cu (tcgen05 3xTF32); returns DPE_ERR_UNSUPPORTED when the shape does not fit, caller falls back to SIMT
+int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s);
+
+// streams.cu
+int launch_features(dpe_model *m, const float *r, int Bc, int C, float *x0, int ldx, float *epot, cudaStream_t s);
+int launch_eion_stream(dpe_model *m, const float *r, int Bc, int CE, float *ei_base, const size_t *ei_off_floats, cudaStream_t s);
+int launch_pair_stream(dpe_model *m, const float *r, int Bc, int CP, float *pw_base, const size_t *pw_off_floats, cudaStream_t s);
+int launch_act(dpe_model *m, float *z, int ld, int n_groups, int C, int width, const float *bias, const float *add,
+               int groups_per_add, cudaStream_t s);
+int launch_mean(dpe_model *m, const float *x, int ldx, int Bc, int C, int d_in, float *mean, cudaStream_t s);
+int launch_conv(dpe_model *m, int it, const float *r, int Bc, int C, const float *hm, const float *pw, const float *ei,
+                float *x, int ldx, cudaStream_t s);
+int launch_prepare_params(dpe_model *m, cudaStream_t s);
+int launch_prepare_geometry(dpe_model *m, cudaStream_t s);
+
+// orbitals_det.cu
+int launch_envelope(dpe_model *m, const float *r, int Bc, int C, float *mo, cudaStream_t s);
+int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStream_t s);
+int launch_combine(dpe_model *m, int Bc, int C, const float *det, const float *epot, float *phase, float *logpsi2,
+                   float *grad, float *ekin, float *eloc, float *epot_out, cudaStream_t s);
+
+// mcmc.cu
+int launch_propose(const dpe_mcmc_state *st, int B, int n_el, float *r_prop, float *thr, uint32_t *new_keys, cudaStream_t s);
+int launch_accept(const dpe_mcmc_state *st, int B, int n_el, const float *r_prop, const float *lp_prop, const float *thr,
+                  const uint32_t *new_keys, int max_age, int32_t *mask, int32_t *count, cudaStream_t s);
+int launch_controller(const dpe_mcmc_state *st, const int32_t *counts, int n_steps, int64_t n_total,
+                      const dpe_mcmc_config &cfg, cudaStream_t s);
+
+}  // namespace dpe

@@ -1,0 +1,302 @@
+// Metropolis-Hastings walker update with a jax-compatible threefry2x32 counter RNG.
+// Reference: mcmc.py:175-180 (_propose_normal), :345-387 (make_mcmc_step, _adjust_stepsize),
+// utils/utils.py:115 (batch_rng_split); RNG = jax 0.4.23 threefry (un-vendored; restated in
+// oracle/threefry.py and pinned by its known-answer tests).  Also the E_loc statistics of
+// optimization/loss_function.py:19-30, 62-72, 89-109.
+#include "dpe_internal.cuh"
+
+namespace dpe {
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int d) { return (x << d) | (x >> (32 - d)); }
+
+__device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t &x0, uint32_t &x1) {
+    const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+    x0 += ks[0]; x1 += ks[1];
+#pragma unroll
+    for (int g = 0; g < 5; ++g) {
+        if ((g & 1) == 0) {
+            x0 += x1; x1 = rotl32(x1, 13); x1 ^= x0;
+            x0 += x1; x1 = rotl32(x1, 15); x1 ^= x0;
+            x0 += x1; x1 = rotl32(x1, 26); x1 ^= x0;
+            x0 += x1; x1 = rotl32(x1, 6);  x1 ^= x0;
+        } else {
+            x0 += x1; x1 = rotl32(x1, 17); x1 ^= x0;
+            x0 += x1; x1 = rotl32(x1, 29); x1 ^= x0;
+            x0 += x1; x1 = rotl32(x1, 16); x1 ^= x0;
+            x0 += x1; x1 = rotl32(x1, 24); x1 ^= x0;
+        }
+        x0 += ks[(g + 1) % 3];
+        x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+    }
+}
+
+// jax.random.split(key, 2): bits(key, 4) with counters (0,2) and (1,3) -> new_key = (y0a, y0b), sub = (y1a, y1b)
+__device__ __forceinline__ void split2(uint32_t k0, uint32_t k1, uint32_t (&nk)[2], uint32_t (&sub)[2]) {
+    uint32_t a0 = 0u, a1 = 2u, b0 = 1u, b1 = 3u;
+    threefry2x32(k0, k1, a0, a1);
+    threefry2x32(k0, k1, b0, b1);
+    nk[0] = a0; nk[1] = b0;
+    sub[0] = a1; sub[1] = b1;
+}
+
+__device__ __forceinline__ float bits_to_unit(uint32_t bits) { return __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f; }
+
+// XLA's f32 erf_inv (Giles), evaluated without fused contractions to stay close to the CPU restatement
+__device__ __forceinline__ float erf_inv_f32(float x) {
+    float w = -log1pf(__fmul_rn(-x, x));
+    float p;
+    if (w < 5.0f) {
+        w = __fsub_rn(w, 2.5f);
+        p = 2.81022636e-08f;
+        p = __fadd_rn(3.43273939e-07f, __fmul_rn(p, w));
+        p = __fadd_rn(-3.5233877e-06f, __fmul_rn(p, w));
+        p = __fadd_rn(-4.39150654e-06f, __fmul_rn(p, w));
+        p = __fadd_rn(0.00021858087f, __fmul_rn(p, w));
+        p = __fadd_rn(-0.00125372503f, __fmul_rn(p, w));
+        p = __fadd_rn(-0.00417768164f, __fmul_rn(p, w));
+        p = __fadd_rn(0.246640727f, __fmul_rn(p, w));
+        p = __fadd_rn(1.50140941f, __fmul_rn(p, w));
+    } else {
+        w = __fsub_rn(sqrtf(w), 3.0f);
+        p = -0.000200214257f;
+        p = __fadd_rn(0.000100950558f, __fmul_rn(p, w));
+        p = __fadd_rn(0.00134934322f, __fmul_rn(p, w));
+        p = __fadd_rn(-0.00367342844f, __fmul_rn(p, w));
+        p = __fadd_rn(0.00573950773f, __fmul_rn(p, w));
+        p = __fadd_rn(-0.0076224613f, __fmul_rn(p, w));
+        p = __fadd_rn(0.00943887047f, __fmul_rn(p, w));
+        p = __fadd_rn(1.00167406f, __fmul_rn(p, w));
+        p = __fadd_rn(2.83297682f, __fmul_rn(p, w));
+    }
+    return __fmul_rn(p, x);
+}
+
+__device__ __forceinline__ float bits_to_normal(uint32_t bits) {
+    const float lo = -0.99999994f;                       // nextafter(-1, 0)
+    float u = __fadd_rn(__fmul_rn(bits_to_unit(bits), 2.0f), lo);   // (hi - lo) rounds to 2.0f
+    u = fmaxf(lo, u);
+    return __fmul_rn(1.41421356237309515f, erf_inv_f32(u));
+}
+
+// One thread per (walker, counter pair p): noise element p from y0, element h+p from y1 (jax bits layout).
+__global__ void __launch_bounds__(256) k_propose(const float *__restrict__ r, const uint32_t *__restrict__ keys,
+                                                  const float *__restrict__ stepsize, int B, int n, float *__restrict__ r_prop,
+                                                  float *__restrict__ noise_out, float *__restrict__ thr,
+                                                  uint32_t *__restrict__ new_keys) {
+    const int h = (n + 1) / 2;
+    const long total = (long)B * h;
+    long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long b = idx / h;
+    const int p = (int)(idx - b * h);
+    uint32_t nk[2], sub[2];
+    split2(keys[2 * b], keys[2 * b + 1], nk, sub);
+    uint32_t x0 = (uint32_t)p, x1 = (h + p < n) ? (uint32_t)(h + p) : 0u;   // odd n: padded counter is 0
+    threefry2x32(sub[0], sub[1], x0, x1);
+    const float ss = stepsize ? stepsize[0] : 1.f;
+    float n0 = bits_to_normal(x0);
+    if (noise_out) noise_out[b * n + p] = n0;
+    if (r_prop) r_prop[b * n + p] = __fadd_rn(r[b * n + p], __fmul_rn(n0, ss));
+    if (h + p < n) {
+        float n1 = bits_to_normal(x1);
+        if (noise_out) noise_out[b * n + h + p] = n1;
+        if (r_prop) r_prop[b * n + h + p] = __fadd_rn(r[b * n + h + p], __fmul_rn(n1, ss));
+    }
+    if (p == 0) {
+        uint32_t t0 = 0u, t1 = 0u;                    // uniform(sub, ()) = bits(sub, 1)[0]: counters (0, 0)
+        threefry2x32(sub[0], sub[1], t0, t1);
+        thr[b] = fmaxf(0.f, bits_to_unit(t0));
+        new_keys[2 * b] = nk[0];
+        new_keys[2 * b + 1] = nk[1];
+    }
+}
+
+int launch_propose(const dpe_mcmc_state *st, int B, int n_el, float *r_prop, float *thr, uint32_t *new_keys, cudaStream_t s) {
+    int n = 3 * n_el, h = (n + 1) / 2;
+    long total = (long)B * h;
+    k_propose<<<(int)((total + 255) / 256), 256, 0, s>>>(st->r_dev, st->rng_state_dev, st->stepsize_dev, B, n, r_prop, nullptr,
+                                                         thr, new_keys);
+    return check_cuda(cudaGetLastError(), "k_propose");
+}
+
+// accept/reject (mcmc.py:358-366): one thread per walker decides, then the block copies positions.
+__global__ void __launch_bounds__(256) k_accept(float *__restrict__ r, float *__restrict__ lp, int32_t *__restrict__ age,
+                                                 uint32_t *__restrict__ keys, const float *__restrict__ r_prop,
+                                                 const float *__restrict__ lp_prop, const float *__restrict__ thr,
+                                                 const uint32_t *__restrict__ new_keys, int B, int n, int max_age,
+                                                 int32_t *__restrict__ mask, int32_t *__restrict__ count) {
+    __shared__ int s_acc[256];
+    __shared__ int s_cnt;
+    const int b0 = blockIdx.x * blockDim.x;
+    const int b = b0 + threadIdx.x;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    int acc = 0;
+    if (b < B) {
+        float lo = lp[b], ln = lp_prop[b];
+        float p_acc = expf(ln - lo);                      // log_q_ratio = 0 for the normal proposal
+        int a = age[b];
+        acc = (p_acc > thr[b]) || (a >= max_age);
+        age[b] = acc ? 0 : a + 1;
+        if (acc) lp[b] = ln;
+        keys[2 * b] = new_keys[2 * b];
+        keys[2 * b + 1] = new_keys[2 * b + 1];
+        if (mask) mask[b] = acc;
+        if (acc) atomicAdd(&s_cnt, 1);
+    }
+    s_acc[threadIdx.x] = acc;
+    __syncthreads();
+    const int nb = min((int)blockDim.x, B - b0);
+    for (int e = threadIdx.x; e < nb * n; e += blockDim.x) {
+        int w = e / n;
+        if (s_acc[w]) r[(long)b0 * n + e] = r_prop[(long)b0 * n + e];
+    }
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(count, s_cnt);
+}
+
+int launch_accept(const dpe_mcmc_state *st, int B, int n_el, const float *r_prop, const float *lp_prop, const float *thr,
+                  const uint32_t *new_keys, int max_age, int32_t *mask, int32_t *count, cudaStream_t s) {
+    k_accept<<<(B + 255) / 256, 256, 0, s>>>(st->r_dev, st->log_psi_sqr_dev, st->walker_age_dev, st->rng_state_dev, r_prop,
+                                             lp_prop, thr, new_keys, B, 3 * n_el, max_age, mask, count);
+    return check_cuda(cudaGetLastError(), "k_accept");
+}
+
+// scalar tail of make_mcmc_step (mcmc.py:367-377), replayed over n_steps accept counts
+__global__ void k_controller(float *stepsize, int32_t *step_nr, float *acc_rate, const int32_t *counts, int n_steps,
+                             float total, dpe_mcmc_config cfg) {
+    if (threadIdx.x || blockIdx.x) return;
+    float ss = stepsize[0], ar = acc_rate[0];
+    int sn = step_nr[0];
+    for (int t = 0; t < n_steps; ++t) {
+        float rate = __fdiv_rn((float)counts[t], total);   // jnp.mean(do_accept)
+        sn += 1;
+        float ar_new = __fadd_rn(__fmul_rn(0.9f, ar), __fmul_rn(0.1f, rate));
+        if (sn % cfg.stepsize_update_interval == 0) {   // decided with the PRE-update acc_rate
+            ss = (ar < cfg.target_acceptance_rate) ? __fdiv_rn(ss, 1.05f) : __fmul_rn(ss, 1.05f);
+            ss = fminf(fmaxf(ss, cfg.min_stepsize_scale), cfg.max_stepsize_scale);
+        }
+        ar = ar_new;
+    }
+    stepsize[0] = ss; acc_rate[0] = ar; step_nr[0] = sn;
+}
+
+int launch_controller(const dpe_mcmc_state *st, const int32_t *counts, int n_steps, int64_t n_total,
+                      const dpe_mcmc_config &cfg, cudaStream_t s) {
+    k_controller<<<1, 32, 0, s>>>(st->stepsize_dev, st->step_nr_dev, st->acc_rate_dev, counts, n_steps, (float)n_total, cfg);
+    return check_cuda(cudaGetLastError(), "k_controller");
+}
+
+// ------------------------------------------------------------------------------------------------
+// E_loc statistics (loss_function.py): single block reductions, NaN-tolerant (jnp.nanmean)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float *red) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    return s;
+}
+
+__global__ void __launch_bounds__(1024) k_moments1(const float *__restrict__ e, int n, const float *__restrict__ cw,
+                                                    int clip_mode, float *__restrict__ ec, float *__restrict__ out) {
+    __shared__ float red[32];
+    const float c = cw[0], w = cw[1];
+    float s = 0.f, sc = 0.f, cnt = 0.f, cntc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = e[i];
+        float vc = clip_mode == 1 ? fminf(fmaxf(v, c - w), c + w) : c + tanhf((v - c) / w) * w;
+        if (v != v) vc = v;
+        ec[i] = vc;
+        if (v == v) { s += v; cnt += 1.f; }
+        if (vc == vc) { sc += vc; cntc += 1.f; }
+    }
+    s = block_sum(s, red); cnt = block_sum(cnt, red); sc = block_sum(sc, red); cntc = block_sum(cntc, red);
+    if (threadIdx.x == 0) { out[0] = s / cnt; out[1] = sc / cntc; }
+}
+
+__global__ void __launch_bounds__(1024) k_moments2(const float *__restrict__ e, const float *__restrict__ ec, int n,
+                                                    const float *__restrict__ means, float *__restrict__ out) {
+    __shared__ float red[32];
+    const float m0 = means[0], m1 = means[1];
+    float s = 0.f, sc = 0.f, cnt = 0.f, cntc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = e[i] - m0, vc = ec[i] - m1;
+        if (v == v) { s = fmaf(v, v, s); cnt += 1.f; }
+        if (vc == vc) { sc = fmaf(vc, vc, sc); cntc += 1.f; }
+    }
+    s = block_sum(s, red); cnt = block_sum(cnt, red); sc = block_sum(sc, red); cntc = block_sum(cntc, red);
+    if (threadIdx.x == 0) { out[0] = s / cnt; out[1] = sc / cntc; }
+}
+
+__global__ void k_bits(uint32_t k0, uint32_t k1, int n, uint32_t *__restrict__ bits) {
+    const int h = (n + 1) / 2;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= h) return;
+    uint32_t x0 = (uint32_t)p, x1 = (h + p < n) ? (uint32_t)(h + p) : 0u;
+    threefry2x32(k0, k1, x0, x1);
+    bits[p] = x0;
+    if (h + p < n) bits[h + p] = x1;
+}
+
+__global__ void k_normal(uint32_t k0, uint32_t k1, int n, float *__restrict__ out) {
+    const int h = (n + 1) / 2;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= h) return;
+    uint32_t x0 = (uint32_t)p, x1 = (h + p < n) ? (uint32_t)(h + p) : 0u;
+    threefry2x32(k0, k1, x0, x1);
+    out[p] = bits_to_normal(x0);
+    if (h + p < n) out[h + p] = bits_to_normal(x1);
+}
+
+}  // namespace dpe
+
+extern "C" {
+
+int dpe_energy_moments1(const float *e_loc_dev, int32_t n, const float *clip_center_width_dev, int32_t clip_mode,
+                        float *e_clipped_dev, float *out2_dev, void *stream) {
+    if (!e_loc_dev || !clip_center_width_dev || !e_clipped_dev || !out2_dev || n <= 0) return dpe::set_error(DPE_ERR_ARG, "energy_moments1: bad argument");
+    dpe::k_moments1<<<1, 1024, 0, (cudaStream_t)stream>>>(e_loc_dev, n, clip_center_width_dev, clip_mode, e_clipped_dev, out2_dev);
+    return dpe::check_cuda(cudaGetLastError(), "k_moments1");
+}
+
+int dpe_energy_moments2(const float *e_loc_dev, const float *e_clipped_dev, int32_t n, const float *means_dev,
+                        float *out2_dev, void *stream) {
+    if (!e_loc_dev || !e_clipped_dev || !means_dev || !out2_dev || n <= 0) return dpe::set_error(DPE_ERR_ARG, "energy_moments2: bad argument");
+    dpe::k_moments2<<<1, 1024, 0, (cudaStream_t)stream>>>(e_loc_dev, e_clipped_dev, n, means_dev, out2_dev);
+    return dpe::check_cuda(cudaGetLastError(), "k_moments2");
+}
+
+int dpe_threefry_mcmc_randoms(const uint32_t *keys_dev, int32_t n_walkers, int32_t n_el, uint32_t *new_keys_dev,
+                              float *noise_dev, float *thr_dev, void *stream) {
+    if (!keys_dev || !new_keys_dev || !noise_dev || !thr_dev || n_walkers <= 0 || n_el <= 0) return dpe::set_error(DPE_ERR_ARG, "threefry_mcmc_randoms: bad argument");
+    int n = 3 * n_el, h = (n + 1) / 2;
+    long total = (long)n_walkers * h;
+    dpe::k_propose<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nullptr, keys_dev, nullptr, n_walkers, n, nullptr,
+                                                                                 noise_dev, thr_dev, new_keys_dev);
+    return dpe::check_cuda(cudaGetLastError(), "k_propose(randoms)");
+}
+
+int dpe_threefry_bits(const uint32_t *key_host, int32_t n, uint32_t *bits_dev, void *stream) {
+    if (!key_host || !bits_dev || n <= 0) return dpe::set_error(DPE_ERR_ARG, "threefry_bits: bad argument");
+    int h = (n + 1) / 2;
+    dpe::k_bits<<<(h + 255) / 256, 256, 0, (cudaStream_t)stream>>>(key_host[0], key_host[1], n, bits_dev);
+    return dpe::check_cuda(cudaGetLastError(), "k_bits");
+}
+
+int dpe_threefry_normal(const uint32_t *key_host, int32_t n, float *out_dev, void *stream) {
+    if (!key_host || !out_dev || n <= 0) return dpe::set_error(DPE_ERR_ARG, "threefry_normal: bad argument");
+    int h = (n + 1) / 2;
+    dpe::k_normal<<<(h + 255) / 256, 256, 0, (cudaStream_t)stream>>>(key_host[0], key_host[1], n, out_dev);
+    return dpe::check_cuda(cudaGetLastError(), "k_normal");
+}
+
+int dpe_mcmc_controller(const dpe_mcmc_state *state, const int32_t *accept_counts_dev, int32_t n_steps,
+                        int64_t n_walkers_total, const dpe_mcmc_config *cfg, void *stream) {
+    if (!state || !accept_counts_dev || !cfg || n_steps < 0 || n_walkers_total <= 0) return dpe::set_error(DPE_ERR_ARG, "mcmc_controller: bad argument");
+    if (n_steps == 0) return DPE_OK;
+    return dpe::launch_controller(state, accept_counts_dev, n_steps, n_walkers_total, *cfg, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,309 @@
+// Envelope multiply, batched determinants (LU / Gauss-Jordan with partial pivoting, inverse-trace
+// Laplacian contraction) and the signed log-sum-exp that ends in log psi^2 and E_loc.
+// Reference: model/orbitals/envelope_orbitals.py:39-127, model/wavefunction.py:63-83,
+// hamiltonian.py:206-216 (forward-Laplacian kinetic energy), :34-39 (potential).
+#include "dpe_internal.cuh"
+
+namespace dpe {
+
+// ------------------------------------------------------------------------------------------------
+// mo[b,i,c,col] = env[b,i,col] (x) bf[b,i,c,col]  in place (product rule; env depends on r_i only)
+// env = sum_J w[J,col] exp(-softplus(alpha[J,col]) |r_i - R_J|)      col = det*N + orb
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_envelope(const float *__restrict__ r, const float *__restrict__ R, int Bc, int N,
+                                                   int U, int I, int C, int cols, const float *__restrict__ spa_up,
+                                                   const float *__restrict__ spa_dn, const float *__restrict__ w_up,
+                                                   const float *__restrict__ w_dn, float *__restrict__ mo) {
+    const long total = (long)Bc * N * cols;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int col = idx % cols;
+        long bi = idx / cols;
+        int i = bi % N;
+        const float *spa = i < U ? spa_up : spa_dn;
+        const float *wt = i < U ? w_up : w_dn;
+        const float *ri = r + bi * 3;
+        float env = 0.f, e1[3] = {0.f, 0.f, 0.f}, el = 0.f;
+        for (int J = 0; J < I; ++J) {
+            float dx = ri[0] - R[J * 3], dy = ri[1] - R[J * 3 + 1], dz = ri[2] - R[J * 3 + 2];
+            float d = sqrtf(dx * dx + dy * dy + dz * dz);
+            float a = spa[(long)J * cols + col];
+            float e = wt[(long)J * cols + col] * expf(-a * d);
+            env += e;
+            if (C > 1) {
+                float inv = 1.f / d;
+                float g = -a * e * inv;
+                e1[0] = fmaf(g, dx, e1[0]); e1[1] = fmaf(g, dy, e1[1]); e1[2] = fmaf(g, dz, e1[2]);
+                el = fmaf(e, a * a - 2.f * a * inv, el);
+            }
+        }
+        float *p = mo + bi * (long)C * cols + col;
+        if (C == 1) {
+            p[0] *= env;
+        } else {
+            float bf0 = p[0];
+            float t0 = p[(long)(1 + 3 * i) * cols], t1 = p[(long)(2 + 3 * i) * cols], t2 = p[(long)(3 + 3 * i) * cols];
+            for (int c = 0; c < C; ++c) p[(long)c * cols] *= env;
+            p[(long)(1 + 3 * i) * cols] += e1[0] * bf0;
+            p[(long)(2 + 3 * i) * cols] += e1[1] * bf0;
+            p[(long)(3 + 3 * i) * cols] += e1[2] * bf0;
+            p[(long)(C - 1) * cols] += el * bf0 + 2.f * (e1[0] * t0 + e1[1] * t1 + e1[2] * t2);
+        }
+    }
+}
+
+int launch_envelope(dpe_model *m, const float *r, int Bc, int C, float *mo, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    int cols = d.n_dets * d.n_el;
+    long total = (long)Bc * d.n_el * cols;
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 32) blocks = 148L * 32;
+    k_envelope<<<(int)blocks, 256, 0, s>>>(r, m->R_dev, Bc, d.n_el, d.n_up, d.n_ion, C, cols, m->sp_alpha[0], m->sp_alpha[1],
+                                           m->env_w[0], m->env_w[1], mo);
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// determinants: one group of T threads per (walker, determinant)
+//   forward:    sign, log|det|                                 (jnp.linalg.slogdet, wavefunction.py:69)
+//   Laplacian:  A^-1, g_k = tr(A^-1 dA_k), lap = tr(A^-1 lapA) - sum_k tr((A^-1 dA_k)^2)
+// det record: [logdet, sign, lap, g_0 .. g_{K-1}]
+// ------------------------------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ float group_sum(float v, float *red, int tid) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (T == 32) return v;
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int w = 0; w < T / 32; ++w) s += red[w];
+    return s;
+}
+
+template <int T, bool LAP>
+__global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float *__restrict__ mo, float *__restrict__ det) {
+    extern __shared__ float sm[];
+    const int W = LAP ? 2 * N : N;       // augmented width
+    const int S = W + 1;                 // padded row stride
+    float *aug = sm;                     // [N][S]
+    float *dA = aug + N * S;             // [N][N+1]   (LAP only)
+    float *P = dA + (LAP ? N * (N + 1) : 0);   // [N][N+1]
+    float *red = P + (LAP ? N * (N + 1) : 0);  // [T/32 + 2]
+    __shared__ int piv_row;
+    const int tid = threadIdx.x;
+    const long bd = blockIdx.x;
+    const long b = bd / n_det;
+    const int dt = (int)(bd - b * n_det);
+    const int cols = n_det * N;
+    const float *mob = mo + b * (long)N * C * cols + (long)dt * N;     // element (i, c, o): mob[(i*C + c)*cols + o]
+    const int K = C - 2;
+
+    for (int e = tid; e < N * W; e += T) {
+        int i = e / W, o = e - i * W;
+        aug[i * S + o] = o < N ? mob[((long)i * C) * cols + o] : ((o - N == i) ? 1.f : 0.f);
+    }
+    __syncthreads();
+    float logdet = 0.f, sign = 1.f;
+    for (int p = 0; p < N; ++p) {
+        // pivot search (first maximum, as LAPACK's isamax)
+        if (tid < 32) {
+            float best = -1.f; int bi = p;
+            for (int i = p + tid; i < N; i += 32) {
+                float v = fabsf(aug[i * S + p]);
+                if (v > best) { best = v; bi = i; }
+            }
+            for (int o = 16; o; o >>= 1) {
+                float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (tid == 0) piv_row = bi;
+        }
+        __syncthreads();
+        const int pr = piv_row;
+        if (pr != p) {
+            for (int o = tid; o < W; o += T) {
+                float t = aug[p * S + o]; aug[p * S + o] = aug[pr * S + o]; aug[pr * S + o] = t;
+            }
+            sign = -sign;
+            __syncthreads();
+        }
+        const float piv = aug[p * S + p];
+        logdet += logf(fabsf(piv));
+        if (piv < 0.f) sign = -sign;
+        const float inv = 1.f / piv;
+        __syncthreads();
+        if (LAP) {
+            // Gauss-Jordan: scale the pivot row, eliminate the column from every other row
+            for (int o = tid; o < W; o += T) aug[p * S + o] *= inv;
+            __syncthreads();
+            for (int e = tid; e < N * W; e += T) {
+                int i = e / W, o = e - i * W;
+                if (i != p && o != p) aug[i * S + o] = fmaf(-aug[i * S + p], aug[p * S + o], aug[i * S + o]);
+            }
+            __syncthreads();
+            for (int i = tid; i < N; i += T)
+                if (i != p) aug[i * S + p] = 0.f;
+            __syncthreads();
+        } else {
+            const int rem = N - p - 1;
+            for (int e = tid; e < rem * rem; e += T) {
+                int i = p + 1 + e / rem, o = p + 1 + e % rem;
+                aug[i * S + o] = fmaf(-aug[i * S + p] * inv, aug[p * S + o], aug[i * S + o]);
+            }
+            __syncthreads();
+        }
+    }
+    float *out = det + bd * (long)(LAP ? K + 3 : 2);
+    if (tid == 0) { out[0] = logdet; out[1] = sign; }
+    if (!LAP) return;
+
+    // Ainv[o][i] = aug[o*S + N + i]
+    // Laplacian term tr(Ainv lapA)
+    float part = 0.f;
+    for (int e = tid; e < N * N; e += T) {
+        int i = e / N, o = e - i * N;
+        part = fmaf(aug[o * S + N + i], mob[((long)i * C + C - 1) * cols + o], part);
+    }
+    float lap = group_sum<T>(part, red, tid);
+    float tr2_total = 0.f;
+    for (int k = 0; k < K; ++k) {
+        __syncthreads();
+        for (int e = tid; e < N * N; e += T) {
+            int i = e / N, o = e - i * N;
+            dA[i * (N + 1) + o] = mob[((long)i * C + 1 + k) * cols + o];
+        }
+        __syncthreads();
+        float gk = 0.f;
+        for (int e = tid; e < N * N; e += T) {
+            int o = e / N, q = e - o * N;      // P[o][q] = sum_i Ainv[o][i] dA[i][q]
+            float acc = 0.f;
+            for (int i = 0; i < N; ++i) acc = fmaf(aug[o * S + N + i], dA[i * (N + 1) + q], acc);
+            P[o * (N + 1) + q] = acc;
+            if (o == q) gk += acc;
+        }
+        __syncthreads();
+        float t2 = 0.f;
+        for (int e = tid; e < N * N; e += T) {
+            int o = e / N, q = e - o * N;
+            t2 = fmaf(P[o * (N + 1) + q], P[q * (N + 1) + o], t2);
+        }
+        gk = group_sum<T>(gk, red, tid);
+        t2 = group_sum<T>(t2, red, tid);
+        tr2_total += t2;
+        if (tid == 0) out[3 + k] = gk;
+    }
+    if (tid == 0) out[2] = lap - tr2_total;
+}
+
+int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    const int N = d.n_el;
+    const bool lap = C > 1;
+    size_t fl = (size_t)N * ((lap ? 2 * N : N) + 1) + (lap ? 2 * (size_t)N * (N + 1) : 0) + 16;
+    size_t smem = fl * sizeof(float);
+    int blocks = Bc * d.n_dets;
+    if (N <= 16) {
+        if (lap) k_det<32, true><<<blocks, 32, smem, s>>>(N, C, d.n_dets, mo, det);
+        else k_det<32, false><<<blocks, 32, smem, s>>>(N, C, d.n_dets, mo, det);
+    } else {
+        if (smem > 48 * 1024) {
+            DPE_CUDA(cudaFuncSetAttribute(k_det<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DPE_CUDA(cudaFuncSetAttribute(k_det<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        if (lap) k_det<128, true><<<blocks, 128, smem, s>>>(N, C, d.n_dets, mo, det);
+        else k_det<128, false><<<blocks, 128, smem, s>>>(N, C, d.n_dets, mo, det);
+    }
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// signed log-sum-exp over determinants (wavefunction.py:77-83) with gradient / Laplacian, then
+// E_kin = -1/2 (1/2 lap L + 1/4 |grad L|^2), L = log psi^2 (hamiltonian.py:216). One warp per walker.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_combine(int Bc, int n_det, int K, bool lap_mode, const float *__restrict__ det,
+                                                  const float *__restrict__ epot, float *__restrict__ phase,
+                                                  float *__restrict__ logpsi2, float *__restrict__ grad,
+                                                  float *__restrict__ ekin, float *__restrict__ eloc,
+                                                  float *__restrict__ epot_out) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= Bc) return;
+    const int rec = lap_mode ? K + 3 : 2;
+    const float *db = det + (long)b * n_det * rec;
+    // shift = max_d logdet, first arg-max
+    float best = -INFINITY; int bi = 0;
+    for (int d = lane; d < n_det; d += 32) {
+        float v = db[(long)d * rec];
+        if (v > best) { best = v; bi = d; }
+    }
+    for (int o = 16; o; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    const float shift = best; const int md = bi;
+    float psi = 0.f;
+    for (int d = lane; d < n_det; d += 32) psi += db[(long)d * rec + 1] * expf(db[(long)d * rec] - shift);
+    for (int o = 16; o; o >>= 1) psi += __shfl_xor_sync(0xffffffffu, psi, o);
+    const float apsi = fabsf(psi);
+    const float lp2 = 2.f * (logf(apsi + 1e-8f) + shift);
+    if (lane == 0) {
+        logpsi2[b] = lp2;
+        if (phase) phase[b] = psi < 0.f ? 3.14159265358979323846f : 0.f;
+    }
+    if (!lap_mode) return;
+    const float inv_psi = 1.f / psi;
+    const float rho = apsi / (apsi + 1e-8f);
+    // sum_d w_d lap_d
+    float wl = 0.f;
+    for (int d = lane; d < n_det; d += 32) {
+        float w = db[(long)d * rec + 1] * expf(db[(long)d * rec] - shift) * inv_psi;
+        wl = fmaf(w, db[(long)d * rec + 2], wl);
+    }
+    for (int o = 16; o; o >>= 1) wl += __shfl_xor_sync(0xffffffffu, wl, o);
+    const float l_m = db[(long)md * rec + 2];
+    float sum_gkk = 0.f, sum_dev2 = 0.f, sum_f2 = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        float G = 0.f, S2 = 0.f;
+        for (int d = 0; d < n_det; ++d) {
+            float w = db[(long)d * rec + 1] * expf(db[(long)d * rec] - shift) * inv_psi;
+            float g = db[(long)d * rec + 3 + k];
+            G = fmaf(w, g, G);
+            S2 = fmaf(w * g, g, S2);
+        }
+        float gm = db[(long)md * rec + 3 + k];
+        float Fk = rho * (G - gm) + gm;
+        sum_gkk += S2 - G * G;
+        sum_dev2 += (G - gm) * (G - gm);
+        float gr = 2.f * Fk;
+        sum_f2 = fmaf(gr, gr, sum_f2);
+        if (grad) grad[(long)b * K + k] = gr;
+    }
+    for (int o = 16; o; o >>= 1) {
+        sum_gkk += __shfl_xor_sync(0xffffffffu, sum_gkk, o);
+        sum_dev2 += __shfl_xor_sync(0xffffffffu, sum_dev2, o);
+        sum_f2 += __shfl_xor_sync(0xffffffffu, sum_f2, o);
+    }
+    if (lane == 0) {
+        float Gkk = sum_gkk + wl;
+        float F_lap = rho * (1.f - rho) * sum_dev2 + rho * (Gkk - l_m) + l_m;
+        float lapL = 2.f * F_lap;
+        float ek = -0.5f * (0.5f * lapL + 0.25f * sum_f2);
+        if (ekin) ekin[b] = ek;
+        if (epot_out) epot_out[b] = epot[b];
+        if (eloc) eloc[b] = ek + epot[b];
+    }
+}
+
+int launch_combine(dpe_model *m, int Bc, int C, const float *det, const float *epot, float *phase, float *logpsi2,
+                   float *grad, float *ekin, float *eloc, float *epot_out, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    k_combine<<<(Bc * 32 + 127) / 128, 128, 0, s>>>(Bc, d.n_dets, 3 * d.n_el, C > 1, det, epot, phase, logpsi2, grad, ekin,
+                                                    eloc, epot_out);
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
+}  // namespace dpe

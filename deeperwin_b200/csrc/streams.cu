@@ -1,0 +1,541 @@
+// Feature construction, el-ion stream, el-el pair stream, SchNet convolution, spin means and the
+// tanh value/tangent/Laplacian rule of the dpe4 embedding (reference: model/input_features.py:112-303,
+// model/embeddings/ferminet_embedding.py:45-267, model/mlp.py:45-69, utils/utils.py:262-305).
+//
+// Layout (walker-major, feature-minor so that warps read/write 128-byte rows):
+//   one-electron stream  X[b][i][c][ld]   columns: h_one (d_in) | conv_ee (emb) | conv_eI (dE)
+//   channels c: 0 = value, 1+3e+a = d/d r_{e,a}, 3N+1 = Laplacian   (C = 3N+2; C = 1 forward-only)
+//   el-ion stream        5 channels (value, d/d r_i{x,y,z}, Laplacian): depends on r_i only
+//   pair stream          3 channels (f, f', f'') as a function of the scalar distance d_ij
+#include "dpe_internal.cuh"
+
+namespace dpe {
+
+__device__ __forceinline__ float tanh_f32(float x) { return tanhf(x); }
+
+// ------------------------------------------------------------------------------------------------
+// features: h_one^0 = reshape([dist_eI, diff_eI]) with tangents, plus E_pot
+// ------------------------------------------------------------------------------------------------
+__global__ void k_features(const float *__restrict__ r, const float *__restrict__ R, int Bc, int N, int I, int C,
+                           float *__restrict__ x0, int ldx) {
+    const int d0 = 4 * I;
+    const long total = (long)Bc * N * C * d0;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int col = idx % d0;
+        long row = idx / d0;            // (b*N + i)*C + c
+        int c = row % C;
+        long bi = row / C;
+        int i = bi % N;
+        int J = col >> 2, q = col & 3;
+        const float *ri = r + bi * 3;
+        float dx = ri[0] - R[J * 3 + 0], dy = ri[1] - R[J * 3 + 1], dz = ri[2] - R[J * 3 + 2];
+        float d = sqrtf(dx * dx + dy * dy + dz * dz);
+        float diff[3] = {dx, dy, dz};
+        float v = 0.f;
+        if (c == 0) {
+            v = (q == 0) ? d : diff[q - 1];
+        } else if (c == C - 1) {
+            v = (q == 0) ? 2.0f / d : 0.f;
+        } else {
+            int k = c - 1, e = k / 3, a = k - 3 * e;
+            if (e == i) v = (q == 0) ? diff[a] / d : ((q - 1 == a) ? 1.f : 0.f);
+        }
+        x0[row * ldx + col] = v;
+    }
+}
+
+// E_pot (hamiltonian.py:17-39): one warp per walker.
+__global__ void k_epot(const float *__restrict__ r, const float *__restrict__ R, const float *__restrict__ Zf, int Bc,
+                       int N, int I, float e_ion_ion, float *__restrict__ epot) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= Bc) return;
+    const float *rb = r + (long)warp * N * 3;
+    float e_ei = 0.f, e_ee = 0.f;
+    for (int t = lane; t < N * I; t += 32) {
+        int i = t / I, J = t - i * I;
+        float dx = rb[i * 3] - R[J * 3], dy = rb[i * 3 + 1] - R[J * 3 + 1], dz = rb[i * 3 + 2] - R[J * 3 + 2];
+        e_ei += Zf[J] / sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+    for (int t = lane; t < N * N; t += 32) {
+        int i = t / N, j = t - i * N;
+        if (j > i) {
+            float dx = rb[i * 3] - rb[j * 3], dy = rb[i * 3 + 1] - rb[j * 3 + 1], dz = rb[i * 3 + 2] - rb[j * 3 + 2];
+            e_ee += 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        e_ei += __shfl_xor_sync(0xffffffffu, e_ei, o);
+        e_ee += __shfl_xor_sync(0xffffffffu, e_ee, o);
+    }
+    if (lane == 0) epot[warp] = e_ee - e_ei + e_ion_ion;
+}
+
+int launch_features(dpe_model *m, const float *r, int Bc, int C, float *x0, int ldx, float *epot, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    long total = (long)Bc * d.n_el * C * 4 * d.n_ion;
+    int blocks = (int)((total + 255) / 256 < 148L * 64 ? (total + 255) / 256 : 148L * 64);
+    k_features<<<blocks, 256, 0, s>>>(r, m->R_dev, Bc, d.n_el, d.n_ion, C, x0, ldx);
+    DPE_LAUNCH_CHECK(m);
+    if (epot) {
+        k_epot<<<(Bc * 32 + 255) / 256, 256, 0, s>>>(r, m->R_dev, m->Z_dev, Bc, d.n_el, d.n_ion, m->e_ion_ion, epot);
+        DPE_LAUNCH_CHECK(m);
+    }
+    return DPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp-wide tiny dense layer: lane = output feature; x[c] holds input feature `lane` of channel c
+// ------------------------------------------------------------------------------------------------
+template <int CH>
+__device__ __forceinline__ void warp_dense_tanh(const float *__restrict__ W, const float *__restrict__ bias, int din,
+                                                int dout, const float (&x)[CH], float (&y)[CH], int lane) {
+    float z[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) z[c] = 0.f;
+    const bool act = lane < dout;
+    for (int k = 0; k < din; ++k) {
+        float w = act ? W[k * dout + lane] : 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) z[c] = fmaf(__shfl_sync(0xffffffffu, x[c], k), w, z[c]);
+    }
+    if (act) z[0] += bias[lane];
+    // tanh rule: channels 1..CH-2 tangents, CH-1 Laplacian (CH == 1: value only)
+    float t = tanh_f32(z[0]);
+    float d1 = 1.f - t * t;
+    y[0] = act ? t : 0.f;
+    if (CH > 1) {
+        float ssq = 0.f;
+#pragma unroll
+        for (int c = 1; c < CH - 1; ++c) {
+            ssq = fmaf(z[c], z[c], ssq);
+            y[c] = act ? d1 * z[c] : 0.f;
+        }
+        y[CH - 1] = act ? d1 * z[CH - 1] - 2.f * t * d1 * ssq : 0.f;
+    }
+}
+
+struct SmallNet {         // shared-memory offsets (floats) of the per-iteration tiny layers
+    int w_off[DPE_MAX_ITER][4], b_off[DPE_MAX_ITER][4];
+    int din[DPE_MAX_ITER], dout_w[DPE_MAX_ITER], dout_h[DPE_MAX_ITER];
+    int n_iter, total;
+};
+
+// ------------------------------------------------------------------------------------------------
+// el-ion stream: h_eI^it for all iterations + conv_eI^it[b,i,:] = sum_J h_eI^it[b,i,J,:] * him^it[J,:]
+// ------------------------------------------------------------------------------------------------
+struct EionArgs {
+    const float *r, *R;
+    const float *w[DPE_MAX_ITER], *b[DPE_MAX_ITER], *him[DPE_MAX_ITER];
+    float *out[DPE_MAX_ITER];
+    int dE[DPE_MAX_ITER];
+    int n_iter, N, I, n_rows;  // n_rows = Bc*N
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_eion_stream(EionArgs a) {
+    extern __shared__ float smem[];
+    // stage the (n_iter-1) layer weights: [din*dout] + [dout]
+    int off = 0;
+    int w_off[DPE_MAX_ITER], b_off[DPE_MAX_ITER];
+    for (int it = 0; it + 1 < a.n_iter; ++it) {
+        w_off[it] = off; off += a.dE[it] * a.dE[it + 1];
+        b_off[it] = off; off += a.dE[it + 1];
+    }
+    for (int it = 0; it + 1 < a.n_iter; ++it) {
+        int nw = a.dE[it] * a.dE[it + 1];
+        for (int t = threadIdx.x; t < nw; t += blockDim.x) smem[w_off[it] + t] = a.w[it][t];
+        for (int t = threadIdx.x; t < a.dE[it + 1]; t += blockDim.x) smem[b_off[it] + t] = a.b[it][t];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < a.n_rows; row += gridDim.x * warps_per_block) {
+        const float *ri = a.r + (long)row * 3;
+        float rx = ri[0], ry = ri[1], rz = ri[2];
+        float acc[DPE_MAX_ITER][CH];
+#pragma unroll
+        for (int it = 0; it < DPE_MAX_ITER; ++it)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) acc[it][c] = 0.f;
+        for (int J = 0; J < a.I; ++J) {
+            float dx = rx - a.R[J * 3], dy = ry - a.R[J * 3 + 1], dz = rz - a.R[J * 3 + 2];
+            float d = sqrtf(dx * dx + dy * dy + dz * dz);
+            float x[CH];
+            {   // features [d, dx, dy, dz] on lanes 0..3
+                float diff = lane == 1 ? dx : (lane == 2 ? dy : dz);
+                x[0] = lane == 0 ? d : (lane < 4 ? diff : 0.f);
+                if (CH > 1) {
+                    float inv = 1.f / d;
+                    float u[3] = {dx * inv, dy * inv, dz * inv};
+#pragma unroll
+                    for (int c = 1; c < CH - 1; ++c) x[c] = lane == 0 ? u[c - 1] : ((lane == c) ? 1.f : 0.f);
+                    x[CH - 1] = lane == 0 ? 2.f * inv : 0.f;
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < DPE_MAX_ITER; ++it) {
+                if (it < a.n_iter) {
+                    float hm = lane < a.dE[it] ? a.him[it][J * a.dE[it] + lane] : 0.f;
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) acc[it][c] = fmaf(x[c], hm, acc[it][c]);
+                    if (it + 1 < a.n_iter) {
+                        float y[CH];
+                        warp_dense_tanh<CH>(smem + w_off[it], smem + b_off[it], a.dE[it], a.dE[it + 1], x, y, lane);
+                        const bool res = a.dE[it] == a.dE[it + 1];     // mlp.py:13-16
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) x[c] = res ? (x[c] + y[c]) * 0.70710678118654752f : y[c];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < DPE_MAX_ITER; ++it) {
+            if (it < a.n_iter && lane < a.dE[it]) {
+#pragma unroll
+                for (int c = 0; c < CH; ++c) a.out[it][((long)row * CH + c) * a.dE[it] + lane] = acc[it][c];
+            }
+        }
+    }
+}
+
+int launch_eion_stream(dpe_model *m, const float *r, int Bc, int CE, float *ei_base, const size_t *ei_off, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    EionArgs a;
+    a.r = r; a.R = m->R_dev; a.n_iter = d.n_iterations; a.N = d.n_el; a.I = d.n_ion; a.n_rows = Bc * d.n_el;
+    size_t smem = 0;
+    for (int it = 0; it < d.n_iterations; ++it) {
+        a.dE[it] = m->it[it].dE;
+        a.him[it] = m->it[it].him;
+        a.out[it] = ei_base + ei_off[it];
+        a.w[it] = m->it[it].h_el_ion.w;
+        a.b[it] = m->it[it].h_el_ion.b;
+        if (it + 1 < d.n_iterations) smem += ((size_t)m->it[it].dE * m->it[it + 1].dE + m->it[it + 1].dE) * sizeof(float);
+    }
+    int blocks = (a.n_rows + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (CE == 1) k_eion_stream<1><<<blocks, 256, smem, s>>>(a);
+    else k_eion_stream<5><<<blocks, 256, smem, s>>>(a);
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair stream: w^it[b,i,j,:] (value, d/dd, d2/dd2) for every iteration, one warp per pair
+// ------------------------------------------------------------------------------------------------
+struct PairArgs {
+    const float *r;
+    const float *ww[DPE_MAX_ITER][2], *wb[DPE_MAX_ITER][2];   // w_same / w_diff
+    const float *hw[DPE_MAX_ITER][2], *hb[DPE_MAX_ITER][2];   // h_same / h_diff
+    float *out[DPE_MAX_ITER];
+    int dP[DPE_MAX_ITER];
+    int n_iter, N, U, emb;
+    long n_pairs;  // Bc*N*N
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_pair_stream(PairArgs a) {
+    extern __shared__ float smem[];
+    // per iteration: [same block][diff block], each = w_w | w_b | (h_w | h_b)
+    int base[DPE_MAX_ITER], blk[DPE_MAX_ITER];
+    {
+        int off = 0;
+        for (int it = 0; it < a.n_iter; ++it) {
+            base[it] = off;
+            blk[it] = a.dP[it] * a.emb + a.emb + ((it + 1 < a.n_iter) ? a.dP[it] * a.dP[it + 1] + a.dP[it + 1] : 0);
+            off += 2 * blk[it];
+        }
+    }
+    for (int it = 0; it < a.n_iter; ++it)
+        for (int sd = 0; sd < 2; ++sd) {
+            float *dst = smem + base[it] + sd * blk[it];
+            const int nww = a.dP[it] * a.emb;
+            for (int t = threadIdx.x; t < nww; t += blockDim.x) dst[t] = a.ww[it][sd][t];
+            for (int t = threadIdx.x; t < a.emb; t += blockDim.x) dst[nww + t] = a.wb[it][sd][t];
+            if (it + 1 < a.n_iter) {
+                const int nhw = a.dP[it] * a.dP[it + 1];
+                for (int t = threadIdx.x; t < nhw; t += blockDim.x) dst[nww + a.emb + t] = a.hw[it][sd][t];
+                for (int t = threadIdx.x; t < a.dP[it + 1]; t += blockDim.x) dst[nww + a.emb + nhw + t] = a.hb[it][sd][t];
+            }
+        }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int NN = a.N * a.N;
+    for (long p = blockIdx.x * (long)wpb + (threadIdx.x >> 5); p < a.n_pairs; p += (long)gridDim.x * wpb) {
+        long b = p / NN;
+        int ij = (int)(p - b * NN);
+        int i = ij / a.N, j = ij - i * a.N;
+        const float *ri = a.r + (b * a.N + i) * 3, *rj = a.r + (b * a.N + j) * 3;
+        float dx = rj[0] - ri[0], dy = rj[1] - ri[1], dz = rj[2] - ri[2];
+        float d = (i == j) ? 0.f : sqrtf(dx * dx + dy * dy + dz * dz);   // utils.py:299-300: diagonal exactly 0, zero grads
+        const int sd = ((i < a.U) == (j < a.U)) ? 0 : 1;
+        float x[CH];
+        x[0] = lane == 0 ? d : 0.f;
+        if (CH > 1) {
+            x[1] = (lane == 0 && i != j) ? 1.f : 0.f;
+            x[2] = 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < DPE_MAX_ITER; ++it) {
+            if (it < a.n_iter) {
+                float w[CH];
+                const float *blkp = smem + base[it] + sd * blk[it];
+                const int nww = a.dP[it] * a.emb;
+                warp_dense_tanh<CH>(blkp, blkp + nww, a.dP[it], a.emb, x, w, lane);
+                if (lane < a.emb) {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) a.out[it][(p * CH + c) * a.emb + lane] = w[c];
+                }
+                if (it + 1 < a.n_iter) {
+                    float y[CH];
+                    const float *hwp = blkp + nww + a.emb;
+                    warp_dense_tanh<CH>(hwp, hwp + a.dP[it] * a.dP[it + 1], a.dP[it], a.dP[it + 1], x, y, lane);
+                    const bool res = a.dP[it] == a.dP[it + 1];
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) x[c] = res ? (x[c] + y[c]) * 0.70710678118654752f : y[c];
+                }
+            }
+        }
+    }
+}
+
+int launch_pair_stream(dpe_model *m, const float *r, int Bc, int CP, float *pw_base, const size_t *pw_off, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    PairArgs a;
+    a.r = r; a.n_iter = d.n_iterations; a.N = d.n_el; a.U = d.n_up; a.emb = d.emb_dim;
+    a.n_pairs = (long)Bc * d.n_el * d.n_el;
+    size_t fl = 0;
+    for (int it = 0; it < d.n_iterations; ++it) {
+        const IterParams &p = m->it[it];
+        a.dP[it] = p.dP;
+        a.out[it] = pw_base + pw_off[it];
+        a.ww[it][0] = p.w_same.w; a.wb[it][0] = p.w_same.b;
+        a.ww[it][1] = p.w_diff.w; a.wb[it][1] = p.w_diff.b;
+        a.hw[it][0] = p.h_same.w; a.hb[it][0] = p.h_same.b;
+        a.hw[it][1] = p.h_diff.w; a.hb[it][1] = p.h_diff.b;
+        fl += 2 * ((size_t)p.dP * d.emb_dim + d.emb_dim);
+        if (it + 1 < d.n_iterations) fl += 2 * ((size_t)p.dP * m->it[it + 1].dP + m->it[it + 1].dP);
+    }
+    size_t smem = fl * sizeof(float);
+    long blocks = (a.n_pairs + 7) / 8;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (CP == 1) {
+        DPE_CUDA(cudaFuncSetAttribute(k_pair_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pair_stream<1><<<(int)blocks, 256, smem, s>>>(a);
+    } else {
+        DPE_CUDA(cudaFuncSetAttribute(k_pair_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pair_stream<3><<<(int)blocks, 256, smem, s>>>(a);
+    }
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tanh rule on a GEMM output, in place: z[group][c][0:width] (row stride ld)
+//   z0 += bias + add[.,0]; y = tanh(z0); t_k = (1-y^2) z_k ; lap = (1-y^2) z_lap - 2 y (1-y^2) sum_k z_k^2
+// `add` (may be null) is indexed [group / groups_per_add][c][width]  (the spin-mean addend of h_el).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_act(float *__restrict__ z, int ld, long n_groups, int C, int width,
+                                              const float *__restrict__ bias, const float *__restrict__ add,
+                                              int groups_per_add) {
+    const long total = n_groups * width;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long g = idx / width;
+        int f = (int)(idx - g * width);
+        float *zp = z + g * C * ld + f;
+        const float *ap = add ? add + (g / groups_per_add) * C * width + f : nullptr;
+        float z0 = zp[0] + (bias ? bias[f] : 0.f) + (ap ? ap[0] : 0.f);
+        float y = tanh_f32(z0);
+        zp[0] = y;
+        if (C > 1) {
+            float d1 = 1.f - y * y;
+            float ssq = 0.f;
+            for (int c = 1; c < C - 1; ++c) {
+                float v = zp[(long)c * ld] + (ap ? ap[(long)c * width] : 0.f);
+                ssq = fmaf(v, v, ssq);
+                zp[(long)c * ld] = d1 * v;
+            }
+            float zl = zp[(long)(C - 1) * ld] + (ap ? ap[(long)(C - 1) * width] : 0.f);
+            zp[(long)(C - 1) * ld] = d1 * zl - 2.f * y * d1 * ssq;
+        }
+    }
+}
+
+int launch_act(dpe_model *m, float *z, int ld, int n_groups, int C, int width, const float *bias, const float *add,
+               int groups_per_add, cudaStream_t s) {
+    long total = (long)n_groups * width;
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    k_act<<<(int)blocks, 256, 0, s>>>(z, ld, n_groups, C, width, bias, add, groups_per_add);
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// spin means (ferminet_embedding.py:60-72): mean[b][c][0:d] = mean_{i<U} h, [d:2d] = mean_{i>=U} h
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mean(const float *__restrict__ x, int ldx, int Bc, int N, int U, int C, int d_in, float *__restrict__ mean) {
+    const long total = (long)Bc * C * 2 * d_in;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int f2 = idx % (2 * d_in);
+        long bc = idx / (2 * d_in);
+        int c = bc % C;
+        long b = bc / C;
+        int spin = f2 >= d_in, f = f2 - spin * d_in;
+        int i0 = spin ? U : 0, i1 = spin ? N : U;
+        float acc = 0.f;
+        for (int i = i0; i < i1; ++i) acc += x[((b * N + i) * C + c) * ldx + f];
+        mean[idx] = acc / (float)(i1 - i0);
+    }
+}
+
+int launch_mean(dpe_model *m, const float *x, int ldx, int Bc, int C, int d_in, float *mean, cudaStream_t s) {
+    long total = (long)Bc * C * 2 * d_in;
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    k_mean<<<(int)blocks, 256, 0, s>>>(x, ldx, Bc, m->dims.n_el, m->dims.n_up, C, d_in, mean);
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SchNet convolution (ferminet_embedding.py:159-175) with the product rule:
+//   conv_ee[i] = sum_j w[i,j] * hm[j]   (incl. j == i),   conv_eI[i] = (precomputed by the el-ion stream)
+// One block per (b, i); work items (c, f).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_conv(const float *__restrict__ r, int N, int C, int CP, int CE, int emb, int dE,
+                                               const float *__restrict__ hm, const float *__restrict__ pw,
+                                               const float *__restrict__ ei, float *__restrict__ x, int ldx, int col_ee) {
+    extern __shared__ float sm[];      // u[N][3], invd[N]
+    float *u = sm, *invd = sm + 3 * N;
+    const long bi = blockIdx.x;
+    const long b = bi / N;
+    const int i = (int)(bi - b * N);
+    const float *rb = r + b * N * 3;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        float dx = rb[j * 3] - rb[i * 3], dy = rb[j * 3 + 1] - rb[i * 3 + 1], dz = rb[j * 3 + 2] - rb[i * 3 + 2];
+        float d2 = dx * dx + dy * dy + dz * dz;
+        float inv = (j == i) ? 0.f : 1.0f / sqrtf(d2);
+        u[j * 3] = dx * inv; u[j * 3 + 1] = dy * inv; u[j * 3 + 2] = dz * inv;
+        invd[j] = inv;
+    }
+    __syncthreads();
+    const float *hmb = hm + b * N * C * emb;                 // [j][c][f]
+    const float *pwi = pw + (b * N + i) * (long)N * CP * emb;  // [j][ch][f]
+    float *xrow = x + (b * N + i) * (long)C * ldx;
+    const int n_items = C * emb;
+    for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
+        int c = item / emb, f = item - c * emb;
+        float acc = 0.f;
+        for (int j = 0; j < N; ++j) acc = fmaf(pwi[(long)j * CP * emb + f], hmb[((long)j * C + c) * emb + f], acc);
+        if (C > 1) {
+            if (c == C - 1) {
+                for (int j = 0; j < N; ++j) {
+                    if (j == i) continue;
+                    float w1 = pwi[((long)j * CP + 1) * emb + f], w2 = pwi[((long)j * CP + 2) * emb + f];
+                    float h0 = hmb[((long)j * C) * emb + f];
+                    float cross = 0.f;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+                        cross = fmaf(u[j * 3 + a], hmb[((long)j * C + 1 + 3 * j + a) * emb + f] - hmb[((long)j * C + 1 + 3 * i + a) * emb + f], cross);
+                    acc += (2.f * w2 + 4.f * w1 * invd[j]) * h0 + 2.f * w1 * cross;
+                }
+            } else if (c > 0) {
+                int k = c - 1, e = k / 3, a = k - 3 * e;
+                if (e == i) {
+                    float sacc = 0.f;
+                    for (int j = 0; j < N; ++j) {
+                        if (j == i) continue;
+                        sacc = fmaf(pwi[((long)j * CP + 1) * emb + f] * u[j * 3 + a], hmb[((long)j * C) * emb + f], sacc);
+                    }
+                    acc -= sacc;
+                } else {
+                    acc = fmaf(pwi[((long)e * CP + 1) * emb + f] * u[e * 3 + a], hmb[((long)e * C) * emb + f], acc);
+                }
+            }
+        }
+        xrow[(long)c * ldx + col_ee + f] = acc;
+    }
+    // conv_eI columns: expand the 5-channel el-ion convolution into the C channels of electron i
+    const float *eii = ei + bi * CE * dE;
+    for (int item = threadIdx.x; item < C * dE; item += blockDim.x) {
+        int c = item / dE, f = item - c * dE;
+        float v = 0.f;
+        if (c == 0) v = eii[f];
+        else if (C > 1) {
+            if (c == C - 1) v = eii[4 * dE + f];
+            else {
+                int k = c - 1, e = k / 3, a = k - 3 * e;
+                if (e == i) v = eii[(1 + a) * dE + f];
+            }
+        }
+        xrow[(long)c * ldx + col_ee + emb + f] = v;
+    }
+}
+
+int launch_conv(dpe_model *m, int it, const float *r, int Bc, int C, const float *hm, const float *pw, const float *ei,
+                float *x, int ldx, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    const IterParams &p = m->it[it];
+    int CP = C > 1 ? 3 : 1, CE = C > 1 ? 5 : 1;
+    size_t smem = (size_t)4 * d.n_el * sizeof(float);
+    k_conv<<<Bc * d.n_el, 256, smem, s>>>(r, d.n_el, C, CP, CE, d.emb_dim, p.dE, hm, pw, ei, x, ldx, p.d_in);
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameter / geometry preparation
+// ------------------------------------------------------------------------------------------------
+__global__ void k_softplus(const float *__restrict__ x, float *__restrict__ y, long n) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) {
+        float v = x[i];
+        y[i] = fmaxf(v, 0.f) + log1pf(expf(-fabsf(v)));   // jax.nn.softplus = logaddexp(x, 0)
+    }
+}
+
+int launch_prepare_params(dpe_model *m, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    for (int it = 0; it < d.n_iterations; ++it) {
+        IterParams &p = m->it[it];
+        const float *w = p.h_el.w;   // rows: h_one (d_in) | mean_up (d_in) | mean_dn (d_in) | conv_ee (emb) | conv_eI (dE)
+        size_t row = (size_t)p.d_out * sizeof(float);
+        DPE_CUDA(cudaMemcpyAsync(p.w_main, w, p.d_in * row, cudaMemcpyDeviceToDevice, s));
+        DPE_CUDA(cudaMemcpyAsync(p.w_main + (size_t)p.d_in * p.d_out, w + (size_t)3 * p.d_in * p.d_out,
+                                 (d.emb_dim + p.dE) * row, cudaMemcpyDeviceToDevice, s));
+        DPE_CUDA(cudaMemcpyAsync(p.w_mean, w + (size_t)p.d_in * p.d_out, 2 * p.d_in * row, cudaMemcpyDeviceToDevice, s));
+    }
+    long n = (long)d.n_ion * d.n_dets * d.n_el;
+    for (int sp = 0; sp < 2; ++sp) {
+        k_softplus<<<(int)((n + 255) / 256), 256, 0, s>>>(m->alpha[sp], m->sp_alpha[sp], n);
+        DPE_LAUNCH_CHECK(m);
+    }
+    return DPE_OK;
+}
+
+// him^it[J][f] = tanh(h_ion[Z_J - z_min] @ W + b)   (ferminet_embedding.py:171-174, input_features.py:184-191)
+__global__ void k_him(const float *__restrict__ emb_tab, const float *__restrict__ Zf, int z_min, int F, int I, int dE,
+                      const float *__restrict__ W, const float *__restrict__ b, float *__restrict__ him) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= I * dE) return;
+    int J = idx / dE, f = idx - J * dE;
+    const float *h = emb_tab + (long)((int)Zf[J] - z_min) * F;
+    float acc = 0.f;
+    for (int k = 0; k < F; ++k) acc = fmaf(h[k], W[k * dE + f], acc);
+    him[idx] = tanh_f32(acc + b[f]);
+}
+
+int launch_prepare_geometry(dpe_model *m, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    for (int it = 0; it < d.n_iterations; ++it) {
+        const IterParams &p = m->it[it];
+        int n = d.n_ion * p.dE;
+        k_him<<<(n + 127) / 128, 128, 0, s>>>(m->h_ion_emb, m->Z_dev, d.z_min, d.n_ion_features, d.n_ion, p.dE,
+                                              p.h_ion_map.w, p.h_ion_map.b, p.him);
+        DPE_LAUNCH_CHECK(m);
+    }
+    return DPE_OK;
+}
+
+}  // namespace dpe

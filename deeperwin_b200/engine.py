@@ -1,0 +1,186 @@
+"""Host-side owner of one dpe_model handle: parameter flattening, geometry, workspace, stream plumbing.
+PyTorch is used for device memory and streams only; all arithmetic happens in libdpe_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DpeDims, DpeMcmcConfig, DpeMcmcState, MODE_FORWARD, MODE_LAPLACIAN, check
+
+EMB = "wf/fermi_net_embedding"
+ORB = "wf/~/orbitals/envelope_orbitals"
+
+
+def canonical_leaves(n_iterations: int) -> List[Tuple[str, str]]:
+    """(haiku module path, leaf name) in the flat order documented in include/dpe_b200.h."""
+    leaves = [("wf/~/input/h_ion", "embeddings")]
+    for it in range(n_iterations):
+        cf = f"{EMB}/symm_features_{it}/convolutional_features"
+        for nm in ("w_same", "w_diff", "h_map", "h_ion_map"):
+            leaves += [(f"{cf}/{nm}/linear_0", "w"), (f"{cf}/{nm}/linear_0", "b")]
+        leaves += [(f"{EMB}/h_el_{it}/linear_0", "w"), (f"{EMB}/h_el_{it}/linear_0", "b")]
+        if it < n_iterations - 1:
+            for nm in ("h_same", "h_diff", "h_el_ion"):
+                leaves += [(f"{EMB}/{nm}_{it}/linear_0", "w"), (f"{EMB}/{nm}_{it}/linear_0", "b")]
+    leaves += [(f"{ORB}/bf_up/linear_0", "w"), (f"{ORB}/bf_dn/linear_0", "w")]
+    leaves += [(ORB, k) for k in ("alpha_up", "alpha_dn", "weights_up", "weights_dn")]
+    return leaves
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, *, n_el, n_up, n_ion, n_iterations, n_hidden_one_el, n_hidden_two_el, emb_dim, n_ion_features,
+                 n_dets, z_min, z_max, device="cuda:0", workspace_gb: float = 48.0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("deeperwin_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device)
+        d = DpeDims()
+        d.n_el, d.n_up, d.n_ion, d.n_iterations = n_el, n_up, n_ion, n_iterations
+        for i, v in enumerate(n_hidden_one_el):
+            d.n_hidden_one_el[i] = v
+        for i, v in enumerate(n_hidden_two_el):
+            d.n_hidden_two_el[i] = v
+        d.emb_dim, d.n_ion_features, d.n_dets, d.z_min, d.z_max = emb_dim, n_ion_features, n_dets, z_min, z_max
+        self.dims = d
+        self.n_el, self.n_up, self.n_ion = n_el, n_up, n_ion
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.dpe_model_create(C.byref(d), C.byref(self.handle)), "dpe_model_create")
+        self.n_params = self.lib.dpe_param_count(self.handle)
+        self.leaves = canonical_leaves(n_iterations)
+        assert len(self.leaves) == self.lib.dpe_param_leaf_count(self.handle)
+        self.leaf_shapes = []
+        for i in range(len(self.leaves)):
+            off, size, rows, cols = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+            check(self.lib.dpe_param_leaf(self.handle, i, C.byref(off), C.byref(size), C.byref(rows), C.byref(cols)), "dpe_param_leaf")
+            self.leaf_shapes.append((off.value, size.value, rows.value, cols.value))
+        self._flat = torch.empty(self.n_params, dtype=torch.float32, device=self.device)
+        self._param_sig = None
+        self._geom_sig = None
+        self._ws: Optional[torch.Tensor] = None
+        self.workspace_cap = int(workspace_gb * 2 ** 30)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                self.lib.dpe_model_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_params(self, params: Dict[str, Dict[str, torch.Tensor]]):
+        sig = tuple((params[m][k].data_ptr(), params[m][k]._version) for m, k in self.leaves)
+        if sig == self._param_sig:
+            return
+        with torch.cuda.device(self.device):
+            for (mod, name), (off, size, rows, cols) in zip(self.leaves, self.leaf_shapes):
+                t = params[mod][name]
+                if t.numel() != size:
+                    raise ValueError(f"parameter {mod}/{name} has {t.numel()} values, expected {size} ({rows}x{cols})")
+                self._flat[off:off + size].copy_(t.reshape(-1).to(torch.float32), non_blocking=True)
+            check(self.lib.dpe_model_set_params(self.handle, _ptr(self._flat), self.n_params, self._stream()), "dpe_model_set_params")
+        self._param_sig = sig
+
+    def set_geometry(self, R, Z):
+        Rn = np.ascontiguousarray(np.asarray(R.detach().cpu() if isinstance(R, torch.Tensor) else R, dtype=np.float32))
+        Zn = np.ascontiguousarray(np.asarray(Z.detach().cpu() if isinstance(Z, torch.Tensor) else Z).astype(np.int32))
+        if Rn.ndim == 3:      # tiled over a device/batch axis by the caller: all copies are equal
+            Rn, Zn = Rn[0], Zn[0]
+        sig = (Rn.tobytes(), Zn.tobytes())
+        if sig == self._geom_sig:
+            return
+        if Rn.shape != (self.n_ion, 3) or Zn.shape != (self.n_ion,):
+            raise ValueError(f"R/Z shapes {Rn.shape}/{Zn.shape} do not match n_ion={self.n_ion}")
+        with torch.cuda.device(self.device):
+            check(self.lib.dpe_model_set_geometry(self.handle, Rn.ctypes.data_as(C.POINTER(C.c_float)),
+                                                  Zn.ctypes.data_as(C.POINTER(C.c_int32)), self._stream()), "dpe_model_set_geometry")
+        self._geom_sig = sig
+
+    def workspace(self, n_walkers: int, mode: int) -> torch.Tensor:
+        need = min(self.lib.dpe_workspace_bytes(self.handle, n_walkers, mode), self.workspace_cap)
+        free, _ = torch.cuda.mem_get_info(self.device)
+        have = 0 if self._ws is None else self._ws.numel()
+        if have < need:
+            need = min(need, have + int(free * 0.9))
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _r(self, r: torch.Tensor) -> torch.Tensor:
+        r = r.to(device=self.device, dtype=torch.float32).contiguous()
+        if r.shape[-2:] != (self.n_el, 3):
+            raise ValueError(f"r has shape {tuple(r.shape)}, expected [..., {self.n_el}, 3]")
+        return r
+
+    # ------------------------------------------------------------------ hot path
+    def log_psi_sqr(self, r: torch.Tensor):
+        r = self._r(r)
+        batch = r.shape[:-2]
+        B = int(np.prod(batch)) if len(batch) else 1
+        phase = torch.empty(B, dtype=torch.float32, device=self.device)
+        lp = torch.empty(B, dtype=torch.float32, device=self.device)
+        ws = self.workspace(B, MODE_FORWARD)
+        with torch.cuda.device(self.device):
+            check(self.lib.dpe_log_psi_sqr(self.handle, _ptr(r), B, _ptr(phase), _ptr(lp), _ptr(ws), ws.numel(), self._stream()), "dpe_log_psi_sqr")
+        return phase.reshape(batch), lp.reshape(batch)
+
+    def local_energy(self, r: torch.Tensor, with_aux: bool = False):
+        r = self._r(r)
+        batch = r.shape[:-2]
+        B = int(np.prod(batch)) if len(batch) else 1
+        e_loc = torch.empty(B, dtype=torch.float32, device=self.device)
+        lp = grad = ekin = epot = None
+        if with_aux:
+            lp = torch.empty(B, dtype=torch.float32, device=self.device)
+            grad = torch.empty(B, 3 * self.n_el, dtype=torch.float32, device=self.device)
+            ekin = torch.empty(B, dtype=torch.float32, device=self.device)
+            epot = torch.empty(B, dtype=torch.float32, device=self.device)
+        ws = self.workspace(B, MODE_LAPLACIAN)
+        with torch.cuda.device(self.device):
+            check(self.lib.dpe_local_energy(self.handle, _ptr(r), B, _ptr(e_loc), _ptr(lp), _ptr(grad), _ptr(ekin), _ptr(epot),
+                                            _ptr(ws), ws.numel(), self._stream()), "dpe_local_energy")
+        if with_aux:
+            return e_loc.reshape(batch), dict(log_psi_sqr=lp.reshape(batch), grad=grad.reshape(batch + (-1,)),
+                                              E_kin=ekin.reshape(batch), E_pot=epot.reshape(batch))
+        return e_loc.reshape(batch)
+
+    def mcmc_steps(self, state_struct: DpeMcmcState, n_walkers: int, n_steps: int, cfg: DpeMcmcConfig, recompute: bool,
+                   run_controller: bool, counts: torch.Tensor):
+        ws = self.workspace(n_walkers, MODE_FORWARD)
+        with torch.cuda.device(self.device):
+            check(self.lib.dpe_mcmc_steps(self.handle, C.byref(state_struct), n_walkers, n_steps, C.byref(cfg), int(recompute),
+                                          int(run_controller), _ptr(counts), _ptr(ws), ws.numel(), self._stream()), "dpe_mcmc_steps")
+
+    def mcmc_controller(self, state_struct: DpeMcmcState, counts: torch.Tensor, n_steps: int, n_total: int, cfg: DpeMcmcConfig):
+        with torch.cuda.device(self.device):
+            check(self.lib.dpe_mcmc_controller(C.byref(state_struct), _ptr(counts), n_steps, n_total, C.byref(cfg), self._stream()),
+                  "dpe_mcmc_controller")
+
+    # ------------------------------------------------------------------ debug / accounting
+    def ws_view(self, name: str, n_walkers: int, mode: int, shape: Sequence[int]) -> torch.Tensor:
+        off = self.lib.dpe_debug_ws_offset(self.handle, n_walkers, mode, name.encode())
+        if off < 0:
+            raise KeyError(name)
+        n = int(np.prod(shape))
+        return self._ws[off:off + 4 * n].view(torch.float32).reshape(*shape)
+
+    def ldx(self, n_walkers: int, mode: int) -> int:
+        return int(self.lib.dpe_debug_ws_offset(self.handle, n_walkers, mode, b"ldx"))
+
+    def launch_count(self) -> int:
+        return int(self.lib.dpe_launch_count(self.handle))
+
+    def set_gemm_path(self, path: int):
+        check(self.lib.dpe_set_gemm_path(self.handle, path), "dpe_set_gemm_path")

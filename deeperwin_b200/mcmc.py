@@ -1,0 +1,245 @@
+"""Drop-in for src/deeperwin/mcmc.py: MCMCState (:20-146) and MetropolisHastingsMonteCarlo (:314-412)
+with the default `normal` proposal (:175-180).  Walker state lives in torch CUDA tensors with the
+reference's field names and dtypes; every step runs in libdpe_b200.so (fused threefry proposal,
+forward pass, accept/reject, step-size controller).
+
+One process per GPU: `split_across_devices` keeps this rank's contiguous block of walkers
+(mcmc.py:105-129 with n_local_devices = 1), `merge_devices` all-gathers them (mcmc.py:131-146)."""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from dataclasses import dataclass, field, replace
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, utils
+from ._lib import DpeMcmcConfig, DpeMcmcState
+from .configuration import MCMCConfig, PhysicalConfig
+
+
+def PRNGKey(seed: int) -> torch.Tensor:
+    """jax.random.PRNGKey: uint32[2] = [hi32, lo32] (host tensor)."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return torch.tensor([seed >> 32, seed & 0xFFFFFFFF], dtype=torch.int64).to(torch.uint32)
+
+
+def _key_array(key) -> "C.Array":
+    k = np.asarray(key.cpu() if isinstance(key, torch.Tensor) else key).astype(np.uint32).reshape(2)
+    return (C.c_uint32 * 2)(int(k[0]), int(k[1]))
+
+
+def random_bits(key, n: int, device) -> torch.Tensor:
+    """jax `random_bits(key, 32, (n,))` on the GPU."""
+    lib = _lib.load()
+    out = torch.empty(n, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(lib.dpe_threefry_bits(_key_array(key), n, C.c_void_p(out.data_ptr()),
+                                         C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "dpe_threefry_bits")
+    return out.view(torch.uint32)
+
+
+def split(key, num: int = 2, device="cuda") -> torch.Tensor:
+    """jax.random.split(key, num) -> uint32[num, 2]."""
+    return random_bits(key, 2 * num, device).reshape(num, 2)
+
+
+def normal(key, shape, device="cuda") -> torch.Tensor:
+    """jax.random.normal(key, shape, float32)."""
+    lib = _lib.load()
+    n = int(np.prod(shape))
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(lib.dpe_threefry_normal(_key_array(key), n, C.c_void_p(out.data_ptr()),
+                                           C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "dpe_threefry_normal")
+    return out.reshape(*shape)
+
+
+@dataclass
+class MCMCState:
+    """mcmc.py:20-33."""
+    r: torch.Tensor                      # f32 [B, n_el, 3]
+    R: torch.Tensor                      # f32 [n_ions, 3]
+    Z: torch.Tensor                      # int32 [n_ions]
+    log_psi_sqr: Optional[torch.Tensor] = None   # f32 [B]
+    walker_age: Optional[torch.Tensor] = None    # int32 [B]
+    rng_state: Optional[torch.Tensor] = None     # uint32 [B, 2]
+    stepsize: Optional[torch.Tensor] = None      # f32 scalar (init 1e-2)
+    step_nr: Optional[torch.Tensor] = None       # int32 scalar
+    acc_rate: Optional[torch.Tensor] = None      # f32 scalar
+    _step_nr_host: Optional[int] = field(default=None, repr=False, compare=False)
+
+    def __post_init__(self):
+        dev = self.r.device
+        if self.stepsize is None:
+            self.stepsize = torch.full((), 1e-2, dtype=torch.float32, device=dev)
+        if self.step_nr is None:
+            self.step_nr = torch.zeros((), dtype=torch.int32, device=dev)
+            self._step_nr_host = 0
+        if self.acc_rate is None:
+            self.acc_rate = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def build_batch(self, fixed_params: Dict):
+        """mcmc.py:36-37."""
+        return self.r, self.R, self.Z, fixed_params
+
+    @classmethod
+    def initialize_around_nuclei(cls, n_walkers, physical_config: PhysicalConfig, init_method, spin_initialization, rng,
+                                 device="cuda"):
+        """mcmc.py:39-91 for init_method='gaussian', spin_initialization='el_ion_mapping' (the exponential
+        radial pdf, orbitals.py:894-928, is a 'next' row of the scope table)."""
+        if spin_initialization != "el_ion_mapping":
+            raise NotImplementedError(f"Unknown spin initialization: {spin_initialization}")
+        if init_method != "gaussian":
+            raise NotImplementedError(f"initialization '{init_method}' is not part of the B200 hot path; use 'gaussian'")
+        device = torch.device(device)
+        keys = split(rng, 3, device).cpu()
+        rng_r, rng = keys[0], keys[2]
+        n_el = physical_config.n_electrons
+        r0 = normal(rng_r, (n_walkers, n_el, 3), device)
+        R = torch.tensor(physical_config.R, dtype=torch.float32, device=device)
+        r0 = r0 + R[torch.tensor(physical_config.el_ion_mapping, dtype=torch.long, device=device)]
+        return cls(r=r0, R=R, Z=torch.tensor(physical_config.Z, dtype=torch.int32, device=device),
+                   log_psi_sqr=-torch.ones(n_walkers, dtype=torch.float32, device=device) * 1000,
+                   walker_age=torch.zeros(n_walkers, dtype=torch.int32, device=device),
+                   rng_state=split(rng, n_walkers, device))
+
+    @classmethod
+    def resize_or_init(cls, mcmc_state, mcmc_config: MCMCConfig, physical_config: PhysicalConfig, rng, device="cuda"):
+        """mcmc.py:93-103."""
+        if mcmc_state:
+            if mcmc_state.r.ndim == 4:
+                mcmc_state = mcmc_state.merge_devices()
+            return resize_nr_of_walkers(mcmc_state, mcmc_config.n_walkers)
+        return cls.initialize_around_nuclei(mcmc_config.n_walkers, physical_config, mcmc_config.initialization,
+                                            mcmc_config.spin_initialization, rng, device)
+
+    def split_across_devices(self):
+        """mcmc.py:105-129: contiguous blocks of B/n_dev walkers; this process keeps block `rank` with a
+        leading local-device axis of size 1, the unbatched fields are tiled to [1, ...]."""
+        assert self.r.ndim == 3, "State is already split across devices"
+        n_dev, rk = utils.world_size(), utils.rank()
+        assert len(self.r) % n_dev == 0, f"Number of samples ({len(self.r)}) is not evenly divisible across devices ({n_dev})"
+        n = len(self.r) // n_dev
+
+        def _split(x):
+            return x[rk * n:(rk + 1) * n][None].contiguous()
+
+        def _tile(x):
+            return x[None].clone()
+
+        return MCMCState(r=_split(self.r), log_psi_sqr=_split(self.log_psi_sqr), walker_age=_split(self.walker_age),
+                         rng_state=_split(self.rng_state), R=_tile(self.R), Z=_tile(self.Z), stepsize=_tile(self.stepsize),
+                         step_nr=_tile(self.step_nr), acc_rate=_tile(self.acc_rate), _step_nr_host=self._step_nr_host)
+
+    def merge_devices(self):
+        """mcmc.py:131-146 (real all-gather instead of the psum-of-padded emulation, utils.py:100-112)."""
+        if self.r.ndim == 3:
+            return self
+        assert self.r.ndim == 4, "State is not split across devices"
+        g = lambda x: utils.all_gather_batch(x[0])
+        return MCMCState(r=g(self.r), log_psi_sqr=g(self.log_psi_sqr), walker_age=g(self.walker_age), rng_state=g(self.rng_state),
+                         R=self.R[0], Z=self.Z[0], stepsize=self.stepsize[0], step_nr=self.step_nr[0], acc_rate=self.acc_rate[0],
+                         _step_nr_host=self._step_nr_host)
+
+
+def _resize_array(x, new_length):
+    """mcmc.py:154-161."""
+    old_length = x.shape[0]
+    if new_length < old_length:
+        return x[:new_length]
+    n_replicas, n_remainder = new_length // old_length, new_length % old_length
+    return torch.cat([x for _ in range(n_replicas)] + [x[:n_remainder]], dim=0)
+
+
+def resize_nr_of_walkers(state: MCMCState, n_walkers_new):
+    """mcmc.py:164-172."""
+    if n_walkers_new == len(state.r):
+        return state
+    return replace(state, r=_resize_array(state.r, n_walkers_new), log_psi_sqr=_resize_array(state.log_psi_sqr, n_walkers_new),
+                   walker_age=_resize_array(state.walker_age, n_walkers_new),
+                   rng_state=split(state.rng_state[0], n_walkers_new, state.r.device))
+
+
+def plan_segments(step_nr: int, n_steps: int, interval: int):
+    """Multi-GPU schedule of one run_mcmc_steps call: the step size only changes when
+    step_nr % stepsize_update_interval == 0 (mcmc.py:372-377), so the per-step scalar all-reduce of the
+    reference (mcmc.py:367) is deferred to the end of each segment that ends on such a boundary (the
+    acceptance-rate EMA is replayed exactly from the all-reduced integer counts)."""
+    segs, done = [], 0
+    while done < n_steps:
+        seg = min(n_steps - done, interval - (step_nr + done) % interval)
+        segs.append(seg)
+        done += seg
+    return segs
+
+
+class MetropolisHastingsMonteCarlo:
+    """mcmc.py:314-412. Holds the MCMC logic and configuration, not the state."""
+
+    def __init__(self, mcmc_config: MCMCConfig):
+        self.config = mcmc_config
+        if self.config.proposal.name != "normal":
+            raise NotImplementedError("Unknown MCMC proposal type")   # mcmc.py:343
+        self._cfg = DpeMcmcConfig(int(mcmc_config.max_age), int(mcmc_config.stepsize_update_interval),
+                                  float(mcmc_config.target_acceptance_rate), float(mcmc_config.min_stepsize_scale),
+                                  float(mcmc_config.max_stepsize_scale))
+        self.last_accept_counts: Optional[torch.Tensor] = None
+
+    def _run_mcmc_steps(self, func, state: MCMCState, params, n_up, n_dn, fixed_params, n_steps) -> MCMCState:
+        """mcmc.py:389-406. `func` must be the log_psi_sqr callable of build_log_psi_squared."""
+        engine = getattr(func, "engine", None)
+        if engine is None:
+            raise TypeError("run_mcmc_steps needs the log_psi_sqr callable returned by deeperwin_b200.build_log_psi_squared")
+        split_axis = state.r.ndim == 4
+        sq = (lambda x: x[0]) if split_axis else (lambda x: x)
+        engine.set_params(params)
+        engine.set_geometry(sq(state.R), sq(state.Z))
+        # functional update: inputs are never mutated (SURVEY.md 8b conventions)
+        r = sq(state.r).to(torch.float32).contiguous().clone()
+        lp = sq(state.log_psi_sqr).to(torch.float32).contiguous().clone()
+        age = sq(state.walker_age).to(torch.int32).contiguous().clone()
+        keys = sq(state.rng_state).contiguous().clone()
+        stepsize = sq(state.stepsize).to(torch.float32).reshape(1).clone()
+        step_nr = sq(state.step_nr).to(torch.int32).reshape(1).clone()
+        acc_rate = sq(state.acc_rate).to(torch.float32).reshape(1).clone()
+        B = r.shape[0]
+        st = DpeMcmcState(r.data_ptr(), lp.data_ptr(), age.data_ptr(), keys.data_ptr(), stepsize.data_ptr(), step_nr.data_ptr(),
+                          acc_rate.data_ptr())
+        counts = torch.zeros(max(n_steps, 1), dtype=torch.int32, device=r.device)
+        ws_n = utils.world_size()
+        step_host = state._step_nr_host
+        if ws_n == 1:
+            engine.mcmc_steps(st, B, n_steps, self._cfg, True, True, counts)
+        else:
+            if step_host is None:
+                step_host = int(step_nr.item())
+            if n_steps == 0:
+                engine.mcmc_steps(st, B, 0, self._cfg, True, False, counts)
+            done = 0
+            for seg in plan_segments(step_host, n_steps, self._cfg.stepsize_update_interval):
+                seg_counts = counts[done:done + seg]
+                engine.mcmc_steps(st, B, seg, self._cfg, done == 0, False, seg_counts)
+                torch.distributed.all_reduce(seg_counts)     # acceptance rate: pmean(mean(do_accept)), mcmc.py:367
+                engine.mcmc_controller(st, seg_counts, seg, B * ws_n, self._cfg)
+                done += seg
+        self.last_accept_counts = counts[:n_steps]
+        known = state._step_nr_host if state._step_nr_host is not None else step_host
+        un = (lambda x: x[None]) if split_axis else (lambda x: x)
+        return MCMCState(r=un(r), R=state.R, Z=state.Z, log_psi_sqr=un(lp), walker_age=un(age), rng_state=un(keys),
+                         stepsize=un(stepsize.reshape(())), step_nr=un(step_nr.reshape(())), acc_rate=un(acc_rate.reshape(())),
+                         _step_nr_host=None if known is None else known + n_steps)
+
+    # the reference wraps _run_mcmc_steps in jax.pmap (mcmc.py:325-327); one process per GPU needs no wrapper
+    def run_mcmc_steps(self, func, state, params, n_up, n_dn, fixed_params, n_steps):
+        return self._run_mcmc_steps(func, state, params, n_up, n_dn, fixed_params, n_steps)
+
+    def run_inter_steps(self, func, state: MCMCState, params, n_up, n_dn, fixed_params):
+        """mcmc.py:408-409."""
+        return self.run_mcmc_steps(func, state, params, n_up, n_dn, fixed_params, self.config.n_inter_steps)
+
+    def run_burn_in(self, func, state: MCMCState, params, n_up, n_dn, fixed_params):
+        """mcmc.py:411-412."""
+        return self.run_mcmc_steps(func, state, params, n_up, n_dn, fixed_params, self.config.n_burn_in)

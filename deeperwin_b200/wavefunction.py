@@ -1,0 +1,75 @@
+"""Drop-in for the model callables of DeepErwin's wavefunction module.
+
+Reference: src/deeperwin/model/wavefunction.py:262-299 (build_log_psi_squared) and :293 (the
+`log_psi_sqr(params, n_up, n_dn, r, R, Z, fixed_params) -> (phase, log_psi_sqr)` callable that
+mcmc.py:391, hamiltonian.py:208 and loss_function.py:144 consume).  Arrays are torch CUDA tensors instead
+of jax arrays; all arithmetic runs in libdpe_b200.so.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .configuration import ModelConfigDeepErwin4, PhysicalConfig
+from .engine import EMB, ORB, Engine, canonical_leaves
+
+
+def construct_wavefunction_definition(config: ModelConfigDeepErwin4, physical_config: PhysicalConfig):
+    """model/wavefunction.py:302-326: (Z_max, Z_min) of the lookup embedding."""
+    Z_max = config.Z_max if config.Z_max is not None else int(max(physical_config.Z))
+    Z_min = config.Z_min if config.Z_min is not None else int(min(physical_config.Z))
+    return Z_max, Z_min
+
+
+def init_params(engine: Engine, rng_seed: int, device) -> Dict[str, Dict[str, torch.Tensor]]:
+    """Random initial weights with the reference's distributions (mlp.py:42-43: VarianceScaling(1.0, fan_avg,
+    uniform) weights, zero biases; envelope_orbitals.py:34-37: alpha = weights = 1; hk.Embed: truncated
+    normal).  The random stream is torch's, not haiku's."""
+    g = torch.Generator().manual_seed(int(rng_seed))
+    params: Dict[str, Dict[str, torch.Tensor]] = {}
+    for (mod, name), (_, _, rows, cols) in zip(engine.leaves, engine.leaf_shapes):
+        if name == "w":
+            lim = math.sqrt(3.0 / (0.5 * (rows + cols)))
+            t = (torch.rand(rows, cols, generator=g) * 2 - 1) * lim
+        elif name == "b":
+            t = torch.zeros(cols)
+        elif name == "embeddings":
+            t = torch.randn(rows, cols, generator=g).clamp(-2, 2)
+        else:
+            t = torch.ones(rows, cols)
+        params.setdefault(mod, {})[name] = t.to(device=device, dtype=torch.float32)
+    return params
+
+
+def build_log_psi_squared(config: ModelConfigDeepErwin4, physical_config: PhysicalConfig, baseline_config=None,
+                          fixed_params: Optional[Dict] = None, rng_seed: int = 0, device=None, workspace_gb: float = 48.0):
+    """Same return tuple as the reference: (log_psi_sqr, get_slater_mat, get_cache, params, fixed_params)."""
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    emb, orb = config.embedding, config.orbitals
+    Z_max, Z_min = construct_wavefunction_definition(config, physical_config)
+    engine = Engine(n_el=physical_config.n_electrons, n_up=physical_config.n_up, n_ion=len(physical_config.Z),
+                    n_iterations=emb.n_iterations, n_hidden_one_el=list(emb.n_hidden_one_el),
+                    n_hidden_two_el=list(emb.n_hidden_two_el), emb_dim=emb.emb_dim,
+                    n_ion_features=config.features.n_ion_features, n_dets=orb.n_determinants, z_min=Z_min, z_max=Z_max,
+                    device=device, workspace_gb=workspace_gb)
+    params = init_params(engine, rng_seed, device)
+    fixed_params = fixed_params if fixed_params is not None else {}
+
+    def log_psi_sqr(params, n_up, n_dn, r, R, Z, fixed_params=None):
+        if (n_up, n_dn) != (engine.n_up, engine.n_el - engine.n_up):
+            raise ValueError(f"model was built for n_up={engine.n_up}, n_dn={engine.n_el - engine.n_up}")
+        engine.set_params(params)
+        engine.set_geometry(R, Z)
+        return engine.log_psi_sqr(r)
+
+    def get_slater_mat(*args, **kwargs):
+        raise NotImplementedError("Slater-matrix output is only used by pre-training (out of the hot-path scope)")
+
+    def get_cache(*args, **kwargs):
+        return {}   # envelope orbitals have no geometry-only cache (wavefunction.py:165-211 caches TAOs only)
+
+    log_psi_sqr.engine = engine
+    return log_psi_sqr, get_slater_mat, get_cache, params, fixed_params

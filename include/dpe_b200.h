@@ -1,0 +1,170 @@
+/*
+ * dpe_b200.h -- C ABI of the B200-native DeepErwin VMC inner loop (libdpe_b200.so).
+ *
+ * The reference (mdsunivie/deeperwin) has no FFI layer: the boundary it exposes is a set of Python
+ * callables.  Each entry point below names the reference callable it replaces
+ * (paths relative to /root/reference/src/deeperwin/).  deeperwin_b200/ re-creates those callables on
+ * top of this ABI with ctypes; INTEGRATION.md shows the jax-side binding.
+ *
+ * Conventions: plain pointers and sizes only; every `*_dev` pointer is a CUDA device pointer,
+ * everything else is host memory; all floating point is float32 (computation.float_precision,
+ * configuration.py:1893), integers int32 / uint32.  Every call is asynchronous on `stream` (a
+ * cudaStream_t passed as void*), returns 0 on success or a negative dpe_status, never throws and never
+ * allocates device memory behind the caller's back: scratch comes from the caller-provided workspace
+ * (size it with dpe_workspace_bytes).  A handle may be used by one host thread at a time.
+ * There is no CPU fallback: without a CUDA device every compute entry point returns DPE_ERR_CUDA.
+ */
+#ifndef DPE_B200_H
+#define DPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPE_MAX_ITER 8
+
+typedef enum dpe_status {
+    DPE_OK = 0,
+    DPE_ERR_ARG = -1,         /* null pointer / inconsistent sizes */
+    DPE_ERR_UNSUPPORTED = -2, /* model shape outside what the kernels implement */
+    DPE_ERR_WORKSPACE = -3,   /* workspace too small for even one walker */
+    DPE_ERR_CUDA = -4,        /* a CUDA runtime call failed; see dpe_last_error() */
+    DPE_ERR_STATE = -5        /* parameters / geometry not set yet */
+} dpe_status;
+
+/* Shape of the default `dpe4` model: ModelConfigDeepErwin4, configuration.py:422-440, 634-674,
+ * 783-806, 875-890 (full_det determinants, isotropic exponential envelopes, tanh MLPs). */
+typedef struct dpe_dims {
+    int32_t n_el, n_up, n_ion;
+    int32_t n_iterations;              /* embedding.n_iterations (4) */
+    int32_t n_hidden_one_el[DPE_MAX_ITER]; /* [n_iterations]  (256) */
+    int32_t n_hidden_two_el[DPE_MAX_ITER]; /* [n_iterations-1] (32); also used by the el-ion stream, ferminet_embedding.py:260 */
+    int32_t emb_dim;                   /* 32 */
+    int32_t n_ion_features;            /* 32 */
+    int32_t n_dets;                    /* 32 */
+    int32_t z_min, z_max;              /* lookup-embedding vocabulary, model/wavefunction.py:310-326 */
+} dpe_dims;
+
+/* MCMCConfig fields the Metropolis step reads (configuration.py:978-1049), `normal` proposal. */
+typedef struct dpe_mcmc_config {
+    int32_t max_age;
+    int32_t stepsize_update_interval;
+    float target_acceptance_rate;
+    float min_stepsize_scale;
+    float max_stepsize_scale;
+} dpe_mcmc_config;
+
+/* Device-resident walker state: the batch-axis fields of MCMCState (mcmc.py:20-33, 149-151). */
+typedef struct dpe_mcmc_state {
+    float *r_dev;            /* [B, n_el, 3] */
+    float *log_psi_sqr_dev;  /* [B] */
+    int32_t *walker_age_dev; /* [B] */
+    uint32_t *rng_state_dev; /* [B, 2] threefry keys */
+    float *stepsize_dev;     /* [1] */
+    int32_t *step_nr_dev;    /* [1] */
+    float *acc_rate_dev;     /* [1] */
+} dpe_mcmc_state;
+
+typedef struct dpe_model dpe_model; /* opaque */
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+const char *dpe_version(void);
+const char *dpe_last_error(void);
+
+/* Replaces hk.multi_transform(Wavefunction(...)) of build_log_psi_squared (model/wavefunction.py:262-299):
+ * fixes the shapes; weights arrive through dpe_model_set_params. */
+int dpe_model_create(const dpe_dims *dims, dpe_model **out);
+void dpe_model_destroy(dpe_model *m);
+
+/* Number of float32 values in the flat parameter vector, and the offset/size of one leaf.
+ * Canonical leaf order (the haiku tree of SURVEY.md 8b, flattened):
+ *   0: wf/~/input/h_ion embeddings [V, n_ion_features]
+ *   per iteration it: w_same.{w,b}, w_diff.{w,b}, h_map.{w,b}, h_ion_map.{w,b}, h_el_it.{w,b},
+ *                     and for it < n_iterations-1: h_same_it.{w,b}, h_diff_it.{w,b}, h_el_ion_it.{w,b}
+ *   then bf_up.w, bf_dn.w, alpha_up, alpha_dn, weights_up, weights_dn.
+ * All `w` are [d_in, d_out] row-major (y = x @ w + b, hk.Linear). */
+int64_t dpe_param_count(const dpe_model *m);
+int32_t dpe_param_leaf_count(const dpe_model *m);
+int dpe_param_leaf(const dpe_model *m, int32_t leaf, int64_t *offset, int64_t *size, int32_t *rows, int32_t *cols);
+
+/* `params` of log_psi_sqr(params, ...) (model/wavefunction.py:293): copies the flat vector (device
+ * memory) and rebuilds the derived kernel-side layouts. */
+int dpe_model_set_params(dpe_model *m, const float *params_dev, int64_t n, void *stream);
+
+/* `R, Z` of log_psi_sqr(params, n_up, n_dn, r, R, Z, fixed_params): host arrays R[n_ion*3], Z[n_ion]. */
+int dpe_model_set_geometry(dpe_model *m, const float *R_host, const int32_t *Z_host, void *stream);
+
+/* ---- workspace ------------------------------------------------------------------------------- */
+/* mode 0: forward only (log psi^2), mode 1: forward-Laplacian (E_loc). Bytes needed to process
+ * `n_walkers` walkers in one pass; calls given less process the batch in chunks. */
+#define DPE_MODE_FORWARD 0
+#define DPE_MODE_LAPLACIAN 1
+size_t dpe_workspace_bytes(const dpe_model *m, int32_t n_walkers, int32_t mode);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* Replaces log_psi_sqr (model/wavefunction.py:118-134, 293): r[B,n_el,3] -> phase[B] (0 or pi),
+ * log_psi_sqr[B]. phase_dev may be NULL. */
+int dpe_log_psi_sqr(dpe_model *m, const float *r_dev, int32_t n_walkers, float *phase_dev, float *log_psi_sqr_dev,
+                    void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Replaces get_local_energy built by build_local_energy(..., forward_lap=True) (hamiltonian.py:272-291,
+ * kinetic part :206-216, potential :34-39). Optional outputs (NULL to skip): log_psi_sqr[B],
+ * grad_log_psi_sqr[B,3*n_el], E_kin[B], E_pot[B]. */
+int dpe_local_energy(dpe_model *m, const float *r_dev, int32_t n_walkers, float *e_loc_dev, float *log_psi_sqr_dev,
+                     float *grad_dev, float *e_kin_dev, float *e_pot_dev, void *workspace_dev, size_t workspace_bytes,
+                     void *stream);
+
+/* Replaces MetropolisHastingsMonteCarlo._run_mcmc_steps (mcmc.py:389-406) with the `normal` proposal
+ * (mcmc.py:175-180) and make_mcmc_step (mcmc.py:345-379) for one device's walkers.
+ *  - recompute_log_psi != 0 re-evaluates state.log_psi_sqr first (mcmc.py:396);
+ *  - accept_counts_dev[n_steps] (int32) receives the number of accepted walkers of each step;
+ *  - run_controller != 0 applies the acceptance-rate EMA / step-size controller (mcmc.py:367-377) after
+ *    every step using this device's counts over n_walkers_total == n_walkers (single GPU). With several
+ *    GPUs pass 0, all-reduce accept_counts_dev and call dpe_mcmc_controller; n_steps must then not cross
+ *    a multiple of stepsize_update_interval (the host shim segments the call). */
+int dpe_mcmc_steps(dpe_model *m, const dpe_mcmc_state *state, int32_t n_walkers, int32_t n_steps,
+                   const dpe_mcmc_config *cfg, int32_t recompute_log_psi, int32_t run_controller,
+                   int32_t *accept_counts_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* The scalar tail of make_mcmc_step (mcmc.py:367-377) replayed for n_steps steps from (all-reduced)
+ * accept counts: acc_rate EMA, step_nr += 1, step-size update with the pre-update acc_rate. */
+int dpe_mcmc_controller(const dpe_mcmc_state *state, const int32_t *accept_counts_dev, int32_t n_steps,
+                        int64_t n_walkers_total, const dpe_mcmc_config *cfg, void *stream);
+
+/* Replaces the statistics of total_energy (optimization/loss_function.py:89-109) on one device.
+ * Pass 1 (dpe_energy_moments1): out[0]=nanmean(E), out[1]=nanmean(E_clipped), writes E_clipped[B]
+ *   using clip center/width (tanh: clip_mode 0, hard: 1).
+ * Pass 2 (dpe_energy_moments2): out[0]=nanmean((E-e_mean)^2), out[1]=nanmean((E_clipped-c_mean)^2),
+ *   reading e_mean / c_mean from means_dev[0..1] (after the caller's all-reduce). */
+int dpe_energy_moments1(const float *e_loc_dev, int32_t n, const float *clip_center_width_dev, int32_t clip_mode,
+                        float *e_clipped_dev, float *out2_dev, void *stream);
+int dpe_energy_moments2(const float *e_loc_dev, const float *e_clipped_dev, int32_t n, const float *means_dev,
+                        float *out2_dev, void *stream);
+
+/* ---- test hooks (jax.random restated; oracle/threefry.py) ------------------------------------ */
+/* keys[B,2] -> new_keys[B,2], noise[B,n,3]=normal(sub,[n,3]), thr[B]=uniform(sub,()), as one Metropolis
+ * step consumes them (mcmc.py:178-179, 360-361). */
+int dpe_threefry_mcmc_randoms(const uint32_t *keys_dev, int32_t n_walkers, int32_t n_el, uint32_t *new_keys_dev,
+                              float *noise_dev, float *thr_dev, void *stream);
+/* bits(key, n): jax _threefry_random_bits for one key (host key[2]) -> bits_dev[n]. */
+int dpe_threefry_bits(const uint32_t *key_host, int32_t n, uint32_t *bits_dev, void *stream);
+
+/* normal(key, [n]) for one key (host key[2]) -> out_dev[n] float32 (walker initialisation, mcmc.py:65). */
+int dpe_threefry_normal(const uint32_t *key_host, int32_t n, float *out_dev, void *stream);
+
+/* Debug: byte offset of a named intermediate inside the workspace for a chunk of n_walkers in `mode`
+ * (names: "x0".."x7","hm","mean","add","pw","ei","mo","det","epot"); -1 if unknown. */
+int64_t dpe_debug_ws_offset(const dpe_model *m, int32_t n_walkers, int32_t mode, const char *name);
+/* Which GEMM path the library was built to use for the dense layers: 0 = FP32 SIMT, 1 = tcgen05 3xTF32. */
+int dpe_set_gemm_path(dpe_model *m, int32_t path);
+int dpe_get_gemm_path(const dpe_model *m);
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+int64_t dpe_launch_count(const dpe_model *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPE_B200_H */
