@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- walker E_loc evaluations / second of the VMC inner loop (BASELINE.json metric).
+
+One *step* = one pass of the hot path over one batch of synthetic walkers: one Metropolis-Hastings step
+(mcmc.py:345-379: threefry proposal + forward pass + accept/reject) followed by one local-energy evaluation
+(hamiltonian.py:272-291, forward Laplacian) and the E_loc statistics (loss_function.py:89-109) -- i.e. one
+"eval" per walker.  Workload at N=1: BASELINE.json configs[1] = N2, 4096 walkers, default dpe4
+model, random-init weights, walkers burnt in for 100 steps; N>1 keeps 4096 walkers per GPU (weak scaling,
+walkers are independent chains; the only collectives are the natural scalar reductions).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--molecule N2] [--walkers 4096]
+  python bench.py --impl reference ...   # the CPU restatement of the reference (oracle/) on the host cores
+
+`value`   : device-timed throughput, inputs resident in HBM (CUDA events around every step, L2 flushed between steps)
+`e2e`     : same metric through the public Python API (MetropolisHastingsMonteCarlo.run_inter_steps + get_local_energy)
+            with HOST buffers: pinned H2D of the walker state and D2H of the new state + E_loc inside the timed region
+`roofline`: the dominant kernel (the dense-layer GEMM), timed live with CUDA events inside the library
+`cpu_baseline`: oracle/ (a port, not the reference binary: jax is not installable here) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# algorithmic FLOP per walker-eval (SURVEY.md 8d / BASELINE.md section 2)
+FLOP_PER_EVAL = {"LiH": 0.0872e9, "HChain10": 0.533e9, "N2": 1.027e9, "Benzene": 12.20e9}
+METRIC = "walker_eloc_evals_per_sec"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--molecule", default="N2")
+    ap.add_argument("--walkers", type=int, default=4096, help="walkers per GPU")
+    ap.add_argument("--burn-in", type=int, default=100)
+    ap.add_argument("--gemm-path", type=int, default=int(os.environ.get("DPE_GEMM_PATH", "-1")),
+                    help="-1 library default, 0 FP32 SIMT, 1 tcgen05 3xTF32")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    hbm_gbs=d["hbm_gbs"], sm_max_mhz=d.get("sm_max_mhz", 1965.0), source="measured")
+    return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_port_throughput(molecule: str, target_seconds: float):
+    """Times oracle/ (torch CPU fp32, all host threads) on a bounded sample: per walker one forward pass
+    (the Metropolis step's log psi^2) + one forward-Laplacian E_loc in chunks of 64 (hamiltonian.py:280)."""
+    import torch
+    from oracle import model as om
+    from deeperwin_b200.configuration import PhysicalConfig
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    phys = PhysicalConfig(name=molecule)
+    d = om.ModelDims(n_el=phys.n_electrons, n_up=phys.n_up, n_ion=len(phys.Z), Z_max=max(phys.Z))
+    p32 = om.init_params(d, seed=1234, dtype=torch.float32)
+    R = torch.tensor(phys.R, dtype=torch.float32)
+    g = torch.Generator().manual_seed(1234)
+
+    def run(n):
+        r = (R[torch.tensor(phys.el_ion_mapping)][None] + torch.randn(n, d.n_el, 3, generator=g)).float()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            om.log_psi_sqr(p32, d, r, R, phys.Z)
+            om.local_energy(p32, d, r, R, phys.Z, max_batch_size=64)
+        return time.perf_counter() - t0
+
+    run(16)                       # warm-up (thread pools, allocator)
+    pilot = run(64)
+    n = int(max(64, min(8192, 64 * target_seconds / max(pilot, 1e-3)) // 64 * 64))
+    t = run(n)
+    return dict(value=n / t, unit=UNIT, cores=cores, kind="port",
+                sample=f"{n} {molecule} walkers (1 forward + 1 forward-Laplacian E_loc each), torch-CPU fp32 oracle, {t:.1f} s")
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  jax/haiku/folx are not installable in
+    this image (no network, not in /opt/wheelhouse), so this arm times the oracle port (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = cpu_port_throughput(args.molecule, min(args.cpu_seconds, 6.0))
+        if i >= args.warmup:
+            vals.append(info["value"])
+    v = sum(vals) / len(vals)
+    info["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * args.walkers / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.molecule}, default dpe4 model, random-init weights; CPU sample per step: {info['sample']}"},
+            "cpu_baseline": info, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if not (t0 <= t <= t1 + 0.1):
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0])); smax = float(parts[1])
+            except Exception:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import deeperwin_b200 as dpe
+    from deeperwin_b200 import mcmc as gm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = dpe.Configuration(physical=dict(name=args.molecule), optimization=dict(mcmc=dict(n_walkers=args.walkers * world, initialization="gaussian")))
+    phys = cfg.physical
+    B = args.walkers
+    n_el, n_up, n_dn = phys.n_electrons, phys.n_up, phys.n_dn
+    log_psi_sqr, _, _, params, fixed = dpe.build_log_psi_squared(cfg.model, phys, None, None, rng_seed=1234, device=dev)
+    engine = log_psi_sqr.engine
+    if args.gemm_path >= 0:
+        engine.set_gemm_path(args.gemm_path)
+    get_local_energy = dpe.build_local_energy(log_psi_sqr, forward_lap=True)
+    total_energy = dpe.build_total_energy(get_local_energy, cfg.optimization.clipping)
+    mcmc_cfg_burn = dpe.MCMCConfigOptimization(n_inter_steps=args.burn_in, initialization="gaussian")
+    mcmc_cfg_one = dpe.MCMCConfigOptimization(n_inter_steps=1, initialization="gaussian")
+    # synthetic walkers: r0 = R[el_ion_mapping] + N(0,1) (mcmc.py:64-67), threefry seed 1234, then burn-in
+    full = dpe.MCMCState.initialize_around_nuclei(B * world, phys, "gaussian", "el_ion_mapping", dpe.PRNGKey(1234), device=dev)
+    state = full.split_across_devices()
+    del full
+    state = dpe.MetropolisHastingsMonteCarlo(mcmc_cfg_burn).run_inter_steps(log_psi_sqr, state, params, n_up, n_dn, fixed)
+    mc = dpe.MetropolisHastingsMonteCarlo(mcmc_cfg_one)
+    clip_state = dpe.init_clipping_state(device=dev)
+    torch.cuda.synchronize()
+
+    # ---- device-resident step through the C ABI (state stays in HBM) ---------------------------------
+    import ctypes as C
+    from deeperwin_b200._lib import DpeMcmcState
+    r = state.r[0].clone(); lp = state.log_psi_sqr[0].clone(); age = state.walker_age[0].clone(); keys = state.rng_state[0].clone()
+    ss = state.stepsize.reshape(1).clone(); sn = state.step_nr.reshape(1).to(torch.int32).clone(); ar = state.acc_rate.reshape(1).clone()
+    st = DpeMcmcState(r.data_ptr(), lp.data_ptr(), age.data_ptr(), keys.data_ptr(), ss.data_ptr(), sn.data_ptr(), ar.data_ptr())
+    counts = torch.zeros(1, dtype=torch.int32, device=dev)
+    R_, Z_ = state.R[0], state.Z[0]
+    flush = torch.empty(512 * 2 ** 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
+
+    def device_step():
+        engine.mcmc_steps(st, B, 1, mc._cfg, False, world == 1, counts)
+        if world > 1:
+            dist.all_reduce(counts)
+            engine.mcmc_controller(st, counts, 1, B * world, mc._cfg)
+        return total_energy(params, clip_state, (n_up, n_dn), (r, R_, Z_, fixed))
+
+    for _ in range(args.warmup):
+        loss, (clip_state, aux) = device_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = engine.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (not timed)
+        ev[k][0].record()
+        loss, (clip_state, aux) = device_step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall1 = time.perf_counter()
+    launches = engine.launch_count() - launches0 + 2 * args.steps      # + the two moment kernels per step
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_ms = tmax.item()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    value = B * world * args.steps / (dev_ms * 1e-3)
+
+    # ---- end-to-end through the public Python API with host buffers ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = {k: getattr(state, k)[0].cpu().pin_memory() for k in ("r", "log_psi_sqr", "walker_age", "rng_state")}
+        out_host = {k: torch.empty_like(v).pin_memory() for k, v in host.items()}
+        e_host = torch.empty(B, dtype=torch.float32).pin_memory()
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = h2d + e_host.numel() * 4
+
+        def api_step():
+            s_dev = dpe.MCMCState(r=host["r"].to(dev, non_blocking=True)[None], R=state.R, Z=state.Z,
+                                  log_psi_sqr=host["log_psi_sqr"].to(dev, non_blocking=True)[None],
+                                  walker_age=host["walker_age"].to(dev, non_blocking=True)[None],
+                                  rng_state=host["rng_state"].to(dev, non_blocking=True)[None],
+                                  stepsize=state.stepsize, step_nr=state.step_nr, acc_rate=state.acc_rate, _step_nr_host=0)
+            s_new = mc.run_inter_steps(log_psi_sqr, s_dev, params, n_up, n_dn, fixed)
+            e = get_local_energy(params, (n_up, n_dn), s_new.r[0], R_, Z_, fixed)
+            for k in out_host:
+                out_host[k].copy_(getattr(s_new, k)[0], non_blocking=True)
+            e_host.copy_(e, non_blocking=True)
+            torch.cuda.synchronize()
+            return float(e_host[0])
+
+        for _ in range(max(1, args.warmup)):
+            api_step()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            api_step()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * world * args.steps / t.item(), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "MetropolisHastingsMonteCarlo.run_inter_steps(n_inter_steps=1) + get_local_energy, pinned host state in/out"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: the dense-layer GEMM, timed live inside the library ----------
+    pk = peaks()
+    prof = engine.profile_gemms(lambda: engine.local_energy(r)) if hasattr(engine, "profile_gemms") else None
+    fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+    tensor_peak = pk["bf16_tflops"] / 6.0          # 3xTF32 = (bf16 / 2) / 3, SURVEY.md 8d
+    roofline = None
+    if prof:
+        ach = prof["flops"] / (prof["ms"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": prof["kernel"], "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": ach / tensor_peak, "traffic": None,
+                    "peak_source": f"{pk['source']}: bf16 {pk['bf16_tflops']} TF/s / 6 (3xTF32 FP32-accurate tensor peak)",
+                    "launches": prof["count"], "avg_launch_ms": prof["ms"] / max(prof["count"], 1),
+                    "algorithmic_flops_per_launch": prof["flops"] / max(prof["count"], 1),
+                    "frac_of_fp32_simt_peak": ach / fp32_peak, "fp32_simt_peak": fp32_peak,
+                    "share_of_eloc_time": prof["ms"] / prof["total_ms"]}
+    flop_eval = FLOP_PER_EVAL.get(args.molecule)
+    cpu = None if args.no_cpu_baseline else cpu_port_throughput(args.molecule, args.cpu_seconds)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.molecule} ({n_el} electrons), {B} walkers per GPU, default dpe4 model (4x256/32, 32 full determinants), "
+                                   "random-init weights, 100 burn-in steps; step = 1 Metropolis step + 1 forward-Laplacian E_loc + E statistics",
+                       "walkers_per_gpu": B, "l2": "512 MiB flush between timed steps", "gemm_path": engine.lib.dpe_get_gemm_path(engine.handle),
+                       "wall_ms_per_step_incl_flush": 1e3 * (t_wall1 - t_wall0) / args.steps},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "algorithmic_tflops": None if flop_eval is None else value * flop_eval / 1e12,
+            "E_mean": float(aux["E_mean"]), "acc_rate": float(ar.item())}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

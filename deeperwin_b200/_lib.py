@@ -53,6 +53,8 @@ SIGNATURES = {
     "dpe_debug_ws_offset": (C.c_int64, [_P, C.c_int32, C.c_int32, C.c_char_p]),
     "dpe_set_gemm_path": (C.c_int, [_P, C.c_int32]),
     "dpe_get_gemm_path": (C.c_int, [_P]),
+    "dpe_profile_enable": (C.c_int, [_P, C.c_int32]),
+    "dpe_profile_collect": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "dpe_launch_count": (C.c_int64, [_P]),
 }
 

@@ -181,12 +181,26 @@ static int max_chunk(const dpe_dims &d, int C, size_t avail, int B) {
 }
 
 // ---- kernel sequences -------------------------------------------------------------------------------
-static int gemm(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
+static int gemm_dispatch(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     if (m->gemm_path == 1) {
         int e = launch_gemm_tc(m, g, s);
         if (e != DPE_ERR_UNSUPPORTED) return e;
     }
     return launch_gemm_simt(m, g, s);
+}
+
+static int gemm(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
+    if (!m->profile) return gemm_dispatch(m, g, s);
+    dpe_model::ProfRec rec;
+    DPE_CUDA(cudaEventCreate(&rec.e0));
+    DPE_CUDA(cudaEventCreate(&rec.e1));
+    DPE_CUDA(cudaEventRecord(rec.e0, s));
+    int e = gemm_dispatch(m, g, s);
+    DPE_CUDA(cudaEventRecord(rec.e1, s));
+    rec.klass = m->last_gemm_class;
+    rec.flops = 2.0 * (double)g.M * (double)g.N * (double)g.K;
+    m->prof->push_back(rec);
+    return e;
 }
 
 static GemmArgs plain_gemm(const float *A, int lda, const float *W, int ldw, float *Cc, int ldc, int M, int N, int K) {
@@ -287,6 +301,7 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
     dpe_model *m = new (std::nothrow) dpe_model();
     if (!m) return set_error(DPE_ERR_ARG, "out of host memory");
     memset(m, 0, sizeof(*m));
+    m->prof = new std::vector<dpe_model::ProfRec>();
     m->dims = *dims;
     build_leaves(m);
     m->derived_floats = derived_floats(*dims);
@@ -307,6 +322,10 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
 void dpe_model_destroy(dpe_model *m) {
     if (!m) return;
     cudaFree(m->params); cudaFree(m->derived); cudaFree(m->R_dev); cudaFree(m->Z_dev);
+    if (m->prof) {
+        for (auto &r : *m->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        delete m->prof;
+    }
     delete m;
 }
 
@@ -442,6 +461,28 @@ int dpe_set_gemm_path(dpe_model *m, int32_t path) {
     return DPE_OK;
 }
 int dpe_get_gemm_path(const dpe_model *m) { return m ? m->gemm_path : -1; }
+int dpe_profile_enable(dpe_model *m, int32_t on) {
+    if (!m) return set_error(DPE_ERR_ARG, "profile_enable: null model");
+    m->profile = on != 0;
+    return DPE_OK;
+}
+
+int dpe_profile_collect(dpe_model *m, int32_t klass, double *ms, int64_t *count, double *flops) {
+    if (!m || !ms || !count || !flops) return set_error(DPE_ERR_ARG, "profile_collect: null argument");
+    DPE_CUDA(cudaDeviceSynchronize());
+    *ms = 0.0; *count = 0; *flops = 0.0;
+    std::vector<dpe_model::ProfRec> keep;
+    for (auto &r : *m->prof) {
+        if (r.klass != klass) { keep.push_back(r); continue; }
+        float t = 0.f;
+        DPE_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        *ms += t; *count += 1; *flops += r.flops;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    m->prof->swap(keep);
+    return DPE_OK;
+}
+
 int64_t dpe_launch_count(const dpe_model *m) { return m ? m->launches : 0; }
 
 }  // extern "C"

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <vector>
 #include "../../include/dpe_b200.h"
 
 #define DPE_MAX_LEAVES (1 + DPE_MAX_ITER * 16 + 6)
@@ -64,6 +65,10 @@ struct dpe_model {
     bool params_set, geom_set;
     int gemm_path;
     int64_t launches;
+    bool profile;
+    struct ProfRec { cudaEvent_t e0, e1; int klass; double flops; };
+    std::vector<ProfRec> *prof;
+    int last_gemm_class;
 };
 
 namespace dpe {

@@ -149,12 +149,15 @@ int launch_gemm_simt(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     if (g.N > 64) {
         dim3 grid((unsigned)(((g.N + 127) / 128) * (long)((g.M + 127) / 128)));
         k_gemm_simt<128, 128, 8, 8><<<grid, 256, 0, s>>>(g);
+        m->last_gemm_class = 0;
     } else if (g.N > 32) {
         dim3 grid((unsigned)(((g.N + 63) / 64) * (long)((g.M + 127) / 128)));
         k_gemm_simt<128, 64, 8, 4><<<grid, 256, 0, s>>>(g);
+        m->last_gemm_class = 1;
     } else {
         dim3 grid((unsigned)(((g.N + 31) / 32) * (long)((g.M + 255) / 256)));
         k_gemm_simt<256, 32, 8, 4><<<grid, 256, 0, s>>>(g);
+        m->last_gemm_class = 2;
     }
     DPE_LAUNCH_CHECK(m);
     return DPE_OK;

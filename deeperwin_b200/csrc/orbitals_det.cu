@@ -83,13 +83,17 @@ __device__ __forceinline__ float group_sum(float v, float *red, int tid) {
 
 template <int T, bool LAP>
 __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float *__restrict__ mo, float *__restrict__ det) {
-    extern __shared__ float sm[];
+    // The factorisation runs in FP64: the Slater matrices of a random-init network reach condition numbers
+    // of 1e5, where an FP32 LU alone costs 1e-3 relative in E_loc.  It is O(N^3) against the O(3N * N^3)
+    // FP32 tangent stage, so the extra cost is negligible.
+    extern __shared__ double smd[];
     const int W = LAP ? 2 * N : N;       // augmented width
     const int S = W + 1;                 // padded row stride
-    float *aug = sm;                     // [N][S]
-    float *dA = aug + N * S;             // [N][N+1]   (LAP only)
-    float *P = dA + (LAP ? N * (N + 1) : 0);   // [N][N+1]
-    float *red = P + (LAP ? N * (N + 1) : 0);  // [T/32 + 2]
+    double *aug = smd;                   // [N][S]
+    float *Ainv = reinterpret_cast<float *>(aug + N * S);   // [N][N+1]  (LAP only) Ainv[o][i]
+    float *dA = Ainv + (LAP ? N * (N + 1) : 0);             // [N][N+1]
+    float *P = dA + (LAP ? N * (N + 1) : 0);                // [N][N+1]
+    float *red = P + (LAP ? N * (N + 1) : 0);               // [T/32 + 2]
     __shared__ int piv_row;
     const int tid = threadIdx.x;
     const long bd = blockIdx.x;
@@ -101,20 +105,21 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
 
     for (int e = tid; e < N * W; e += T) {
         int i = e / W, o = e - i * W;
-        aug[i * S + o] = o < N ? mob[((long)i * C) * cols + o] : ((o - N == i) ? 1.f : 0.f);
+        aug[i * S + o] = o < N ? (double)mob[((long)i * C) * cols + o] : ((o - N == i) ? 1.0 : 0.0);
     }
     __syncthreads();
-    float logdet = 0.f, sign = 1.f;
+    double logdet = 0.0;
+    float sign = 1.f;
     for (int p = 0; p < N; ++p) {
-        // pivot search (first maximum, as LAPACK's isamax)
+        // pivot search (first maximum, as LAPACK's idamax)
         if (tid < 32) {
-            float best = -1.f; int bi = p;
+            double best = -1.0; int bi = p;
             for (int i = p + tid; i < N; i += 32) {
-                float v = fabsf(aug[i * S + p]);
+                double v = fabs(aug[i * S + p]);
                 if (v > best) { best = v; bi = i; }
             }
             for (int o = 16; o; o >>= 1) {
-                float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                double ob = __shfl_xor_sync(0xffffffffu, best, o);
                 int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
@@ -124,15 +129,15 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
         const int pr = piv_row;
         if (pr != p) {
             for (int o = tid; o < W; o += T) {
-                float t = aug[p * S + o]; aug[p * S + o] = aug[pr * S + o]; aug[pr * S + o] = t;
+                double t = aug[p * S + o]; aug[p * S + o] = aug[pr * S + o]; aug[pr * S + o] = t;
             }
             sign = -sign;
             __syncthreads();
         }
-        const float piv = aug[p * S + p];
-        logdet += logf(fabsf(piv));
-        if (piv < 0.f) sign = -sign;
-        const float inv = 1.f / piv;
+        const double piv = aug[p * S + p];
+        logdet += log(fabs(piv));
+        if (piv < 0.0) sign = -sign;
+        const double inv = 1.0 / piv;
         __syncthreads();
         if (LAP) {
             // Gauss-Jordan: scale the pivot row, eliminate the column from every other row
@@ -140,31 +145,35 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
             __syncthreads();
             for (int e = tid; e < N * W; e += T) {
                 int i = e / W, o = e - i * W;
-                if (i != p && o != p) aug[i * S + o] = fmaf(-aug[i * S + p], aug[p * S + o], aug[i * S + o]);
+                if (i != p && o != p) aug[i * S + o] = fma(-aug[i * S + p], aug[p * S + o], aug[i * S + o]);
             }
             __syncthreads();
             for (int i = tid; i < N; i += T)
-                if (i != p) aug[i * S + p] = 0.f;
+                if (i != p) aug[i * S + p] = 0.0;
             __syncthreads();
         } else {
             const int rem = N - p - 1;
             for (int e = tid; e < rem * rem; e += T) {
                 int i = p + 1 + e / rem, o = p + 1 + e % rem;
-                aug[i * S + o] = fmaf(-aug[i * S + p] * inv, aug[p * S + o], aug[i * S + o]);
+                aug[i * S + o] = fma(-aug[i * S + p] * inv, aug[p * S + o], aug[i * S + o]);
             }
             __syncthreads();
         }
     }
     float *out = det + bd * (long)(LAP ? K + 3 : 2);
-    if (tid == 0) { out[0] = logdet; out[1] = sign; }
+    if (tid == 0) { out[0] = (float)logdet; out[1] = sign; }
     if (!LAP) return;
 
-    // Ainv[o][i] = aug[o*S + N + i]
+    for (int e = tid; e < N * N; e += T) {
+        int o = e / N, i = e - o * N;
+        Ainv[o * (N + 1) + i] = (float)aug[o * S + N + i];
+    }
+    __syncthreads();
     // Laplacian term tr(Ainv lapA)
     float part = 0.f;
     for (int e = tid; e < N * N; e += T) {
         int i = e / N, o = e - i * N;
-        part = fmaf(aug[o * S + N + i], mob[((long)i * C + C - 1) * cols + o], part);
+        part = fmaf(Ainv[o * (N + 1) + i], mob[((long)i * C + C - 1) * cols + o], part);
     }
     float lap = group_sum<T>(part, red, tid);
     float tr2_total = 0.f;
@@ -179,7 +188,7 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
         for (int e = tid; e < N * N; e += T) {
             int o = e / N, q = e - o * N;      // P[o][q] = sum_i Ainv[o][i] dA[i][q]
             float acc = 0.f;
-            for (int i = 0; i < N; ++i) acc = fmaf(aug[o * S + N + i], dA[i * (N + 1) + q], acc);
+            for (int i = 0; i < N; ++i) acc = fmaf(Ainv[o * (N + 1) + i], dA[i * (N + 1) + q], acc);
             P[o * (N + 1) + q] = acc;
             if (o == q) gk += acc;
         }
@@ -201,8 +210,7 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStr
     const dpe_dims &d = m->dims;
     const int N = d.n_el;
     const bool lap = C > 1;
-    size_t fl = (size_t)N * ((lap ? 2 * N : N) + 1) + (lap ? 2 * (size_t)N * (N + 1) : 0) + 16;
-    size_t smem = fl * sizeof(float);
+    size_t smem = (size_t)N * ((lap ? 2 * N : N) + 1) * sizeof(double) + ((lap ? 3 * (size_t)N * (N + 1) : 0) + 16) * sizeof(float);
     int blocks = Bc * d.n_dets;
     if (N <= 16) {
         if (lap) k_det<32, true><<<blocks, 32, smem, s>>>(N, C, d.n_dets, mo, det);

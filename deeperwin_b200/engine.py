@@ -184,3 +184,27 @@ class Engine:
 
     def set_gemm_path(self, path: int):
         check(self.lib.dpe_set_gemm_path(self.handle, path), "dpe_set_gemm_path")
+
+    GEMM_CLASSES = {0: "k_gemm_simt<128,128,8,8>", 1: "k_gemm_simt<128,64,8,4>", 2: "k_gemm_simt<256,32,8,4>", 3: "k_gemm_tc_3xtf32"}
+
+    def profile_gemms(self, fn):
+        """Runs fn() once with per-launch CUDA-event timing of the dense-layer GEMMs (bench.py roofline).
+        Returns the kernel class with the largest summed time."""
+        fn()
+        torch.cuda.synchronize(self.device)
+        check(self.lib.dpe_profile_enable(self.handle, 1), "dpe_profile_enable")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize(self.device)
+        check(self.lib.dpe_profile_enable(self.handle, 0), "dpe_profile_enable")
+        best = None
+        for klass, name in self.GEMM_CLASSES.items():
+            ms, cnt, fl = C.c_double(), C.c_int64(), C.c_double()
+            check(self.lib.dpe_profile_collect(self.handle, klass, C.byref(ms), C.byref(cnt), C.byref(fl)), "dpe_profile_collect")
+            if cnt.value and (best is None or ms.value > best["ms"]):
+                best = dict(kernel=name, ms=ms.value, count=cnt.value, flops=fl.value)
+        if best:
+            best["total_ms"] = e0.elapsed_time(e1)
+        return best

@@ -161,6 +161,12 @@ int64_t dpe_debug_ws_offset(const dpe_model *m, int32_t n_walkers, int32_t mode,
 /* Which GEMM path the library was built to use for the dense layers: 0 = FP32 SIMT, 1 = tcgen05 3xTF32. */
 int dpe_set_gemm_path(dpe_model *m, int32_t path);
 int dpe_get_gemm_path(const dpe_model *m);
+/* Live kernel timing for bench.py's roofline: while enabled, every dense-layer GEMM launch is bracketed by
+ * CUDA events on the launching stream. dpe_profile_collect synchronises and returns, for GEMM kernel class
+ * `klass` (0: SIMT 128x128, 1: SIMT 128x64, 2: SIMT 256x32, 3: tcgen05 3xTF32), the summed device time (ms), the
+ * number of launches and their algorithmic FLOPs (2*M*N*K each); it then clears the records. */
+int dpe_profile_enable(dpe_model *m, int32_t on);
+int dpe_profile_collect(dpe_model *m, int32_t klass, double *ms, int64_t *count, double *flops);
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t dpe_launch_count(const dpe_model *m);
 

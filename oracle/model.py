@@ -447,7 +447,7 @@ def forward_laplacian(params, d: ModelDims, r, R, Z, return_intermediates=False)
     lap = 2 * F_lap
     e_kin = -0.5 * (0.5 * lap + 0.25 * (grad * grad).sum(-1))
     e_pot = potential_energy(r, R, Z)
-    out = dict(logpsi2=logpsi2, phase=torch.where(psi < 0, math.pi, 0.0).to(dt), grad=grad, lap=lap,
+    out = dict(logpsi2=logpsi2, phase=torch.where(psi < 0, torch.full_like(psi, math.pi), torch.zeros_like(psi)), grad=grad, lap=lap,
                E_kin=e_kin, E_pot=e_pot, E_loc=e_kin + e_pot, sign_d=sign, logdet_d=logdet)
     if return_intermediates:
         inter.update(mo=mo, g_d=g_d, lap_d=lap_d)

@@ -1,0 +1,67 @@
+"""world_size-2 gloo tests of the N>1 host logic (walker sharding, the natural reductions)."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from deeperwin_b200 import utils
+        from deeperwin_b200.mcmc import MCMCState
+        from oracle import mcmc as omc
+        out = {}
+        x = torch.tensor([1.0 + rank, 10.0 * (rank + 1)])
+        out["pmean"] = utils.pmean(x).tolist()
+        out["psum"] = utils.psum(x).tolist()
+        assert x.tolist() == [1.0 + rank, 10.0 * (rank + 1)]          # functional: input untouched
+        B, N = 8, 3
+        g = torch.Generator().manual_seed(0)
+        full = MCMCState(r=torch.randn(B, N, 3, generator=g), R=torch.zeros(2, 3), Z=torch.tensor([1, 1], dtype=torch.int32),
+                         log_psi_sqr=torch.arange(B, dtype=torch.float32), walker_age=torch.arange(B, dtype=torch.int32),
+                         rng_state=torch.arange(2 * B, dtype=torch.int32).view(torch.uint32).reshape(B, 2))
+        sp = full.split_across_devices()
+        assert sp.r.shape == (1, B // world, N, 3) and sp.R.shape == (1, 2, 3) and sp.stepsize.shape == (1,)
+        assert torch.equal(sp.r[0], full.r[rank * 4:(rank + 1) * 4])      # contiguous blocks (mcmc.py:105-129)
+        merged = sp.merge_devices()
+        for k in ("r", "log_psi_sqr", "walker_age"):
+            assert torch.equal(getattr(merged, k), getattr(full, k)), k
+        assert torch.equal(merged.rng_state.view(torch.int32), full.rng_state.view(torch.int32))
+        # flat all-reduce of "gradients"
+        ts = [torch.full((3,), float(rank)), torch.full((2, 2), 2.0 * rank)]
+        utils.flat_allreduce_mean(ts)
+        out["flat"] = [t.flatten().tolist() for t in ts]
+        # energy statistics with pmean == statistics of the equal-sized shards combined as the reference does
+        rng = np.random.default_rng(1)
+        E = rng.normal(-5, 2, 64).astype(np.float32)
+        shard = E[rank * 32:(rank + 1) * 32]
+        ar = lambda v: float(utils.pmean(torch.tensor([float(v)], dtype=torch.float32))[0])
+        loss, st, aux = omc.energy_statistics(shard, omc.init_clipping_state(), allreduce_mean=ar)
+        out["E_mean"], out["E_var"] = float(aux["E_mean"]), float(aux["E_var"])
+        out["E_ref_mean"], out["E_ref_var"] = float(E.mean()), float(E.var())
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world_size_2():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    for rank in range(world):
+        o = ret[rank]
+        assert o["pmean"] == [1.5, 15.0] and o["psum"] == [3.0, 30.0]
+        assert o["flat"] == [[0.5] * 3, [1.0] * 4]
+        assert abs(o["E_mean"] - o["E_ref_mean"]) < 1e-5 and abs(o["E_var"] - o["E_ref_var"]) < 1e-4

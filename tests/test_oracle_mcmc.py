@@ -1,0 +1,57 @@
+"""Oracle Metropolis step and energy statistics (mcmc.py:345-387, loss_function.py:12-109)."""
+from pathlib import Path
+
+import numpy as np
+
+from oracle import mcmc as omc, threefry
+
+GOLD = Path(__file__).parent / "golden"
+f32 = np.float32
+
+
+def gaussian_logp(r):
+    return (-np.sum(r.astype(f32) ** 2, axis=(1, 2))).astype(f32)
+
+
+def test_golden_chain():
+    g = np.load(GOLD / "mcmc_gaussian.npz")
+    B = g["r0"].shape[0]
+    st = omc.OracleMCMCState(r=g["r0"], R=np.zeros((1, 3), f32), Z=np.array([4]), log_psi_sqr=-np.ones(B, f32) * 1000,
+                             walker_age=np.zeros(B, np.int32), rng_state=g["keys0"], stepsize=f32(0.3))
+    out = omc.run_mcmc_steps(gaussian_logp, st, 7, max_age=2, stepsize_update_interval=3)
+    assert np.array_equal(out.rng_state, g["keys"]) and np.array_equal(out.walker_age, g["age"])
+    assert np.array_equal(out.r, g["r"]) and np.array_equal(out.log_psi_sqr, g["log_psi_sqr"])
+    assert out.stepsize == g["stepsize"] and out.acc_rate == g["acc_rate"] and out.step_nr == 7
+
+
+def test_step_bookkeeping():
+    B, N = 32, 3
+    keys = threefry.split(threefry.prng_key(3), B)
+    r0 = threefry.normal(threefry.prng_key(4), (B, N, 3))
+    st = omc.OracleMCMCState(r=r0, R=np.zeros((1, 3), f32), Z=np.array([3]), log_psi_sqr=gaussian_logp(r0),
+                             walker_age=np.full(B, 1, np.int32), rng_state=keys, stepsize=f32(0.5))
+    new, mask = omc.make_mcmc_step(gaussian_logp, st, max_age=2, stepsize_update_interval=1, return_mask=True)
+    assert np.array_equal(new.rng_state, np.stack([threefry.split(k)[0] for k in keys]))
+    assert np.array_equal(new.walker_age, np.where(mask, 0, 2))
+    assert np.array_equal(new.r[~mask], st.r[~mask]) and not np.array_equal(new.r[mask], st.r[mask])
+    assert new.step_nr == 1 and new.acc_rate == f32(f32(0.1) * f32(mask.mean()))
+    assert new.stepsize == f32(np.clip(f32(0.5) / f32(1.05), 0.01, 1.0))   # pre-update acc_rate 0 < 0.5 -> shrink
+    # forced accept once age >= max_age
+    st2 = omc.OracleMCMCState(**{**st.__dict__, "walker_age": np.full(B, 2, np.int32)})
+    _, mask2 = omc.make_mcmc_step(gaussian_logp, st2, max_age=2, return_mask=True)
+    assert mask2.all()
+
+
+def test_energy_statistics():
+    rng = np.random.default_rng(0)
+    E = rng.normal(-10, 1, 257).astype(f32)
+    E[5] = np.nan
+    loss, (c, w), aux = omc.energy_statistics(E, omc.init_clipping_state())
+    assert np.isclose(aux["E_mean"], np.nanmean(E)) and np.isclose(aux["E_var"], np.nanvar(E), rtol=1e-5)
+    assert np.isclose(loss, aux["E_mean"], rtol=1e-6)          # width 1e12: tanh clipping is the identity
+    assert np.isclose(c, aux["E_mean_clipped"]) and np.isclose(w, 5 * np.sqrt(aux["E_var_clipped"]), rtol=1e-6)
+    E2 = E.copy(); E2[7] = 1e4
+    _, _, aux2 = omc.energy_statistics(E2, (c, w))
+    assert np.nanmax(aux2["E_loc_clipped"]) <= c + w + 1e-3
+    _, _, aux3 = omc.energy_statistics(E2, (c, w), name="hard")
+    assert np.nanmax(aux3["E_loc_clipped"]) == f32(c + w)
