@@ -52,6 +52,7 @@ SIGNATURES = {
     "dpe_threefry_normal": (C.c_int, [C.POINTER(C.c_uint32), C.c_int32, _P, _P]),
     "dpe_debug_ws_offset": (C.c_int64, [_P, C.c_int32, C.c_int32, C.c_char_p]),
     "dpe_set_gemm_path": (C.c_int, [_P, C.c_int32]),
+    "dpe_debug_gemm": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32] + [C.c_int32] * 9 + [_P]),
     "dpe_get_gemm_path": (C.c_int, [_P]),
     "dpe_profile_enable": (C.c_int, [_P, C.c_int32]),
     "dpe_profile_collect": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),

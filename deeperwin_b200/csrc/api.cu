@@ -315,6 +315,20 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
         return rc;
     }
     bind_views(m);
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || m->n_sm <= 0) m->n_sm = 148;
+    }
+    // tensor-core path: the big dense layers (h_el main blocks and the backflow matrices)
+    {
+        int e = DPE_OK;
+        for (int it = 0; it < dims->n_iterations && !e; ++it) e = tc_register_weight(m, m->it[it].w_main, m->it[it].k_main, m->it[it].d_out);
+        const int cols = dims->n_dets * dims->n_el, dl = dims->n_hidden_one_el[dims->n_iterations - 1];
+        for (int sp = 0; sp < 2 && !e; ++sp) e = tc_register_weight(m, m->bf_w[sp], dl, cols);
+        if (e) { tc_destroy(m); cudaGetLastError(); }      // no tensor-core path: dense layers stay on the FP32 SIMT GEMM
+        m->gemm_path = 0;
+    }
     *out = m;
     return DPE_OK;
 }
@@ -322,6 +336,7 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
 void dpe_model_destroy(dpe_model *m) {
     if (!m) return;
     cudaFree(m->params); cudaFree(m->derived); cudaFree(m->R_dev); cudaFree(m->Z_dev);
+    tc_destroy(m);
     if (m->prof) {
         for (auto &r : *m->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
         delete m->prof;
@@ -348,6 +363,7 @@ int dpe_model_set_params(dpe_model *m, const float *params_dev, int64_t n, void 
     DPE_CUDA(cudaMemcpyAsync(m->params, params_dev, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s));
     int e = launch_prepare_params(m, s);
     if (e) return e;
+    if ((e = tc_refresh_weights(m, s))) return e;
     m->params_set = true;
     if (m->geom_set) return launch_prepare_geometry(m, s);   // him depends on the weights too
     return DPE_OK;
@@ -457,8 +473,28 @@ int64_t dpe_debug_ws_offset(const dpe_model *m, int32_t n_walkers, int32_t mode,
 
 int dpe_set_gemm_path(dpe_model *m, int32_t path) {
     if (!m || (path != 0 && path != 1)) return set_error(DPE_ERR_ARG, "set_gemm_path: path must be 0 or 1");
+    if (path == 1 && !m->tc) return set_error(DPE_ERR_UNSUPPORTED, "tensor-core path unavailable (TMA descriptor encode failed)");
     m->gemm_path = path;
     return DPE_OK;
+}
+
+int dpe_debug_gemm(dpe_model *m, int32_t path, const float *a_dev, int32_t lda, const float *w_dev, float *c_dev, int32_t ldc,
+                   int32_t M, int32_t N, int32_t K, int32_t seg_len, int32_t a_seg_stride, int32_t a_seg_off, int32_t c_seg_stride,
+                   int32_t c_seg_off, int32_t c_col_off, void *stream) {
+    if (!m || !a_dev || !w_dev || !c_dev) return set_error(DPE_ERR_ARG, "debug_gemm: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    GemmArgs g;
+    g.A = a_dev; g.lda = lda; g.W = w_dev; g.ldw = N; g.C = c_dev; g.ldc = ldc;
+    g.a_seg_len = g.c_seg_len = seg_len > 0 ? seg_len : M;
+    g.a_seg_stride = a_seg_stride; g.a_seg_off = a_seg_off; g.c_seg_stride = c_seg_stride; g.c_seg_off = c_seg_off; g.c_col_off = c_col_off;
+    g.M = M; g.N = N; g.K = K;
+    if (path == 0) return launch_gemm_simt(m, g, s);
+    int e = tc_register_weight(m, w_dev, K, N);
+    if (e) return e;
+    if ((e = tc_refresh_weights(m, s))) return e;
+    e = launch_gemm_tc(m, g, s);
+    if (e == DPE_ERR_UNSUPPORTED) return set_error(e, "debug_gemm: shape not supported by the tensor-core kernel");
+    return e;
 }
 int dpe_get_gemm_path(const dpe_model *m) { return m ? m->gemm_path : -1; }
 int dpe_profile_enable(dpe_model *m, int32_t on) {

@@ -69,6 +69,8 @@ struct dpe_model {
     struct ProfRec { cudaEvent_t e0, e1; int klass; double flops; };
     std::vector<ProfRec> *prof;
     int last_gemm_class;
+    void *tc;      // dpe::TcState (gemm_tc.cu): tf32-split transposed weights + their TMA descriptors
+    int n_sm;
 };
 
 namespace dpe {
@@ -82,6 +84,9 @@ int check_cuda(cudaError_t e, const char *what);
 int launch_gemm_simt(dpe_model *m, const GemmArgs &g, cudaStream_t s);
 // gemm_tc.cu (tcgen05 3xTF32); returns DPE_ERR_UNSUPPORTED when the shape does not fit, caller falls back to SIMT
 int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s);
+int tc_register_weight(dpe_model *m, const float *W, int K, int N);   // W: [K, N] row-major, device
+int tc_refresh_weights(dpe_model *m, cudaStream_t s);                  // re-split after a parameter update
+void tc_destroy(dpe_model *m);
 
 // streams.cu
 int launch_features(dpe_model *m, const float *r, int Bc, int C, float *x0, int ldx, float *epot, cudaStream_t s);

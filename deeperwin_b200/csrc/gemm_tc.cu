@@ -1,12 +1,406 @@
-// tcgen05 3xTF32 dense layer (placeholder until the tensor-core path lands): reports "unsupported" so that
-// api.cu falls back to the FP32 SIMT GEMM.
+// Dense layers on the 5th-generation tensor cores: FP32-accurate 3xTF32 GEMM with tcgen05.mma, TMEM
+// accumulators and TMA-staged operands (sm_100a).
+//
+//   C[m, n] = sum_k X[m, k] W[k, n]      X: activations (rows = walker x electron x channel), W: layer weights
+//
+// The product is computed transposed, D^T[n, m] = sum_k Wt[n, k] X[m, k]:
+//   * MMA "A" operand (M side, 128 lanes)  = Wt  [N_out, K]  K-major  -> TMEM lane  = output feature
+//   * MMA "B" operand (N side, <=256 cols) = X   [rows,  K]  K-major  -> TMEM column = activation row
+// so that every epilogue thread owns one output feature and walks over rows: a warp stores 32 consecutive
+// features of one row (128 B, coalesced), and a later fusion of the tanh/tangent/Laplacian rule needs no
+// cross-thread reduction (the channels of one electron are consecutive columns).
+//
+// FP32 accuracy (the reference forces true FP32, process_molecule.py:20-29): x = xh + xl, w = wh + wl with
+// xh = rna_tf32(x), xl = rna_tf32(x - xh);  x*w ~= wh*xh + wh*xl + wl*xh   (3 tcgen05.mma.kind::tf32, FP32 accumulate).
+// W is split once per parameter update (k_split_transpose); X is split in shared memory by a splitter warpgroup
+// between the TMA arrival and the MMA issue (an element-wise rewrite, so it is oblivious to the 64B swizzle).
+//
+// CTA = 14 warps, persistent (one per SM), tile = 256 features x NMMA (<=256) rows, K in slabs of 16 floats:
+//   warp 0      TMA producer (Wt_hi, Wt_lo, X slabs -> 3-stage ring, mbarrier complete_tx)
+//   warp 1      TMEM allocation + MMA issuer (12 MMAs per slab: 2 k-steps x 2 feature halves x 3 products)
+//   warps 2-5   splitter (X -> xh in place, xl into its own buffer, fence.proxy.async)
+//   warps 6-13  epilogue (tcgen05.ld 32x32b -> coalesced global stores)
+// TMEM: two accumulators [128 lanes x 256 columns] (features 0-127 / 128-255) = all 512 columns.
+#include <cuda.h>
+#include <vector>
 #include "dpe_internal.cuh"
 
 namespace dpe {
 
+constexpr int TC_BK = 16;                 // floats per K slab = 64 B rows, SWIZZLE_64B
+constexpr int TC_STAGES = 3;
+constexpr int TC_FEAT = 256;              // features per tile (2 x M=128)
+constexpr int TC_ROWB = TC_BK * 4;        // 64 bytes per smem row
+constexpr int TC_W_BYTES = TC_FEAT * TC_ROWB;          // 16 KB per hi / lo
+constexpr int TC_X_BYTES = 256 * TC_ROWB;              // 16 KB (sized for NMMA = 256)
+constexpr int TC_STAGE_BYTES = 2 * TC_W_BYTES + 2 * TC_X_BYTES;   // 64 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int TC_THREADS = 14 * 32;
+
+struct TcArgs {
+    float *C;
+    int ldc, c_seg_stride, c_seg_off, c_col_off;   // row of segment s, local row m -> s * c_seg_stride + c_seg_off + m
+    int n_seg, seg_len;                            // rows per segment
+    int N_out, K;
+    int nmma;                                      // rows per tile (multiple of 16, <= 256)
+    int n_rt, n_ft;                                // row tiles per segment, feature tiles
+};
+
+// ---------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 64-byte rows, 8-row atoms.
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((8 * TC_ROWB) >> 4) << 32;           // stride byte offset: 8 rows x 64 B = 512 B
+    d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+    d |= (uint64_t)4 << 61;                              // layout type: SWIZZLE_64B
+    return d;
+}
+
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
+                 const __grid_constant__ CUtensorMap map_wl, TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t *bar_full = bars;                    // [S] TMA landed
+    uint64_t *bar_split = bars + TC_STAGES;       // [S] splitter done
+    uint64_t *bar_empty = bars + 2 * TC_STAGES;   // [S] MMAs that read the stage retired
+    uint64_t *bar_tfull = bars + 3 * TC_STAGES;   // accumulators complete
+    uint64_t *bar_tempty = bar_tfull + 1;         // accumulators drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_tempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_kb = (a.K + TC_BK - 1) / TC_BK;
+    const long n_tiles = (long)a.n_seg * a.n_rt * a.n_ft;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_split[s], 128);
+            mbar_init(&bar_empty[s], 1);
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 256);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM: all 512 columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t tx = 2 * TC_W_BYTES + a.nmma * TC_ROWB;
+            for (long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int ft = (int)(t % a.n_ft);
+                const long rest = t / a.n_ft;
+                const int rt = (int)(rest % a.n_rt), seg = (int)(rest / a.n_rt);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    uint8_t *st = smem + stage * TC_STAGE_BYTES;
+                    mbar_expect_tx(&bar_full[stage], tx);
+                    tma_load_2d(st, &map_wh, &bar_full[stage], kb * TC_BK, ft * TC_FEAT);
+                    tma_load_2d(st + TC_W_BYTES, &map_wl, &bar_full[stage], kb * TC_BK, ft * TC_FEAT);
+                    tma_load_3d(st + 2 * TC_W_BYTES, &map_x, &bar_full[stage], kb * TC_BK, rt * a.nmma, seg);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.nmma >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0; uint32_t phase = 0, tphase = 0;
+            for (long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(bar_tempty, tphase ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&bar_split[stage], phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * TC_STAGE_BYTES);
+                    const uint32_t wh = st, wl = st + TC_W_BYTES, xh = st + 2 * TC_W_BYTES, xl = st + 2 * TC_W_BYTES + TC_X_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                        const uint32_t ko = kk * 32;               // 8 tf32 = 32 bytes along K inside the swizzle atom
+                        const uint64_t dxh = make_desc_sw64(xh + ko), dxl = make_desc_sw64(xl + ko);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t d = tmem_base + h * 256;
+                            const uint64_t dwh = make_desc_sw64(wh + h * 128 * TC_ROWB + ko);
+                            const uint64_t dwl = make_desc_sw64(wl + h * 128 * TC_ROWB + ko);
+                            tc_mma_tf32(d, dwl, dxh, idesc, (kb | kk) ? 1u : 0u);   // small terms first
+                            tc_mma_tf32(d, dwh, dxl, idesc, 1u);
+                            tc_mma_tf32(d, dwh, dxh, idesc, 1u);
+                        }
+                    }
+                    tc_commit(&bar_empty[stage]);                   // frees the stage once these MMAs retire
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(bar_tfull);
+                tphase ^= 1;
+            }
+        }
+    } else if (warp < 6) {
+        // ================================ splitter ================================
+        const int tid = threadIdx.x - 64;       // 0..127
+        int stage = 0; uint32_t phase = 0;
+        const int n_f4 = a.nmma * (TC_ROWB / 16);
+        for (long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(&bar_full[stage], phase);
+                float4 *xh = reinterpret_cast<float4 *>(smem + stage * TC_STAGE_BYTES + 2 * TC_W_BYTES);
+                float4 *xl = reinterpret_cast<float4 *>(smem + stage * TC_STAGE_BYTES + 2 * TC_W_BYTES + TC_X_BYTES);
+                for (int i = tid; i < n_f4; i += 128) {
+                    float4 v = xh[i], h, l;
+                    h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+                    l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+                    xh[i] = h;
+                    xl[i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&bar_split[stage]);
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int h = (warp - 6) >> 2;           // accumulator (feature half)
+        uint32_t tphase = 0;
+        for (long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int ft = (int)(t % a.n_ft);
+            const long rest = t / a.n_ft;
+            const int rt = (int)(rest % a.n_rt), seg = (int)(rest / a.n_rt);
+            const int f = ft * TC_FEAT + h * 128 + q * 32 + lane;
+            const int m0 = rt * a.nmma;
+            const int rows_valid = min(a.nmma, a.seg_len - m0);
+            float *cbase = a.C + ((long)seg * a.c_seg_stride + a.c_seg_off + m0) * a.ldc + a.c_col_off + f;
+            mbar_wait(bar_tfull, tphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * 256;
+            for (int c0 = 0; c0 < a.nmma; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+                if (c0 + 16 >= a.nmma) {         // last chunk is in registers: the accumulators may be overwritten
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty);
+                }
+                if (f < a.N_out) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < rows_valid) cbase[(long)(c0 + j) * a.ldc] = __uint_as_float(v[j]);
+                }
+            }
+            tphase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// W[K][N] (row-major) -> Wt_hi / Wt_lo [N][K] (K-major), tf32-rounded halves
+__global__ void k_split_transpose(const float *__restrict__ W, int K, int N, float *__restrict__ hi, float *__restrict__ lo) {
+    long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (idx >= (long)K * N) return;
+    int n = idx / K, k = idx - (long)n * K;
+    float w = W[(long)k * N + n];
+    float h = rna_tf32(w);
+    hi[idx] = h;
+    lo[idx] = rna_tf32(w - h);
+}
+
+// ---------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+struct TcWeight {
+    const float *W;      // key: the [K, N] row-major weight the SIMT path would read
+    int K, N;
+    float *hi, *lo;      // [N, K]
+    CUtensorMap map_hi, map_lo;
+    bool fresh;
+};
+
+struct TcState {
+    std::vector<TcWeight> weights;
+};
+
+static int encode_w(CUtensorMap *map, float *ptr, int N, int K) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return set_error(DPE_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    cuuint32_t box[2] = {TC_BK, TC_FEAT};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(DPE_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
+    return DPE_OK;
+}
+
+int tc_register_weight(dpe_model *m, const float *W, int K, int N) {
+    if (!m->tc) m->tc = new TcState();
+    TcState *st = static_cast<TcState *>(m->tc);
+    TcWeight w;
+    w.W = W; w.K = K; w.N = N; w.fresh = false;
+    DPE_CUDA(cudaMalloc(&w.hi, (size_t)K * N * sizeof(float)));
+    DPE_CUDA(cudaMalloc(&w.lo, (size_t)K * N * sizeof(float)));
+    int e;
+    if ((e = encode_w(&w.map_hi, w.hi, N, K))) return e;
+    if ((e = encode_w(&w.map_lo, w.lo, N, K))) return e;
+    st->weights.push_back(w);
+    return DPE_OK;
+}
+
+int tc_refresh_weights(dpe_model *m, cudaStream_t s) {
+    if (!m->tc) return DPE_OK;
+    TcState *st = static_cast<TcState *>(m->tc);
+    for (auto &w : st->weights) {
+        long n = (long)w.K * w.N;
+        k_split_transpose<<<(int)((n + 255) / 256), 256, 0, s>>>(w.W, w.K, w.N, w.hi, w.lo);
+        DPE_LAUNCH_CHECK(m);
+        w.fresh = true;
+    }
+    return DPE_OK;
+}
+
+void tc_destroy(dpe_model *m) {
+    if (!m->tc) return;
+    TcState *st = static_cast<TcState *>(m->tc);
+    for (auto &w : st->weights) { cudaFree(w.hi); cudaFree(w.lo); }
+    delete st;
+    m->tc = nullptr;
+}
+
 int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
-    (void)m; (void)g; (void)s;
-    return DPE_ERR_UNSUPPORTED;
+    if (!m->tc) return DPE_ERR_UNSUPPORTED;
+    TcState *st = static_cast<TcState *>(m->tc);
+    const TcWeight *w = nullptr;
+    for (auto &c : st->weights)
+        if (c.W == g.W && c.K == g.K && c.N == g.N && c.fresh) { w = &c; break; }
+    if (!w) return DPE_ERR_UNSUPPORTED;
+    if ((g.K & 3) || (g.lda & 3) || (reinterpret_cast<size_t>(g.A) & 15) || g.ldw != g.N) return DPE_ERR_UNSUPPORTED;
+    // A and C must use the same segmentation (true for every caller in api.cu)
+    if (g.a_seg_len != g.c_seg_len) return DPE_ERR_UNSUPPORTED;
+    const int seg_len = g.a_seg_len < g.M ? g.a_seg_len : g.M;
+    const int n_seg = g.M / seg_len;
+    if ((long)n_seg * seg_len != g.M) return DPE_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return DPE_ERR_UNSUPPORTED;
+
+    TcArgs a;
+    a.C = g.C; a.ldc = g.ldc; a.c_seg_stride = n_seg > 1 ? g.c_seg_stride : 0; a.c_seg_off = g.c_seg_off; a.c_col_off = g.c_col_off;
+    a.n_seg = n_seg; a.seg_len = seg_len; a.N_out = g.N; a.K = g.K;
+    const int tiles_min = (seg_len + 255) / 256;
+    a.nmma = (((seg_len + tiles_min - 1) / tiles_min) + 15) / 16 * 16;
+    if (a.nmma > 256) a.nmma = 256;
+    a.n_rt = (seg_len + a.nmma - 1) / a.nmma;
+    a.n_ft = (g.N + TC_FEAT - 1) / TC_FEAT;
+
+    CUtensorMap map_x;
+    const long a_stride_rows = n_seg > 1 ? g.a_seg_stride : seg_len;
+    cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)seg_len, (cuuint64_t)n_seg};
+    cuuint64_t strides[2] = {(cuuint64_t)g.lda * sizeof(float), (cuuint64_t)a_stride_rows * g.lda * sizeof(float)};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)a.nmma, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    void *base = const_cast<float *>(g.A + (long)g.a_seg_off * g.lda);
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(DPE_ERR_CUDA, "cuTensorMapEncodeTiled(X) failed: %d", (int)r);
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    long n_tiles = (long)a.n_seg * a.n_rt * a.n_ft;
+    int grid = (int)(n_tiles < m->n_sm ? n_tiles : m->n_sm);
+    k_gemm_tc_3xtf32<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(map_x, w->map_hi, w->map_lo, a);
+    m->last_gemm_class = 3;
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
 }
 
 }  // namespace dpe

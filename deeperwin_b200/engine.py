@@ -3,6 +3,7 @@ PyTorch is used for device memory and streams only; all arithmetic happens in li
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -67,6 +68,8 @@ class Engine:
         self._geom_sig = None
         self._ws: Optional[torch.Tensor] = None
         self.workspace_cap = int(workspace_gb * 2 ** 30)
+        if os.environ.get("DPE_GEMM_PATH", "") != "":       # 0 = FP32 SIMT GEMM, 1 = tcgen05 3xTF32 GEMM
+            self.set_gemm_path(int(os.environ["DPE_GEMM_PATH"]))
 
     def __del__(self):
         try:

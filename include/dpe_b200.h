@@ -160,6 +160,11 @@ int dpe_threefry_normal(const uint32_t *key_host, int32_t n, float *out_dev, voi
 int64_t dpe_debug_ws_offset(const dpe_model *m, int32_t n_walkers, int32_t mode, const char *name);
 /* Which GEMM path the library was built to use for the dense layers: 0 = FP32 SIMT, 1 = tcgen05 3xTF32. */
 int dpe_set_gemm_path(dpe_model *m, int32_t path);
+/* Test hook: C[row(m), c_col_off + n] = sum_k A[row(m), k] W[k, n] through GEMM path 0 / 1 with the library's segmented
+ * row addressing (row m -> (m / seg_len) * seg_stride + seg_off + m % seg_len). W is [K, N] row-major. */
+int dpe_debug_gemm(dpe_model *m, int32_t path, const float *a_dev, int32_t lda, const float *w_dev, float *c_dev, int32_t ldc,
+                   int32_t M, int32_t N, int32_t K, int32_t seg_len, int32_t a_seg_stride, int32_t a_seg_off, int32_t c_seg_stride,
+                   int32_t c_seg_off, int32_t c_col_off, void *stream);
 int dpe_get_gemm_path(const dpe_model *m);
 /* Live kernel timing for bench.py's roofline: while enabled, every dense-layer GEMM launch is bracketed by
  * CUDA events on the launching stream. dpe_profile_collect synchronises and returns, for GEMM kernel class
