@@ -327,7 +327,7 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
         const int cols = dims->n_dets * dims->n_el, dl = dims->n_hidden_one_el[dims->n_iterations - 1];
         for (int sp = 0; sp < 2 && !e; ++sp) e = tc_register_weight(m, m->bf_w[sp], dl, cols);
         if (e) { tc_destroy(m); cudaGetLastError(); }      // no tensor-core path: dense layers stay on the FP32 SIMT GEMM
-        m->gemm_path = 0;
+        m->gemm_path = m->tc ? 1 : 0;
     }
     *out = m;
     return DPE_OK;

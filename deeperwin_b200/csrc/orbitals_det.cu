@@ -70,6 +70,11 @@ int launch_envelope(dpe_model *m, const float *r, int Bc, int C, float *mo, cuda
 // det record: [logdet, sign, lap, g_0 .. g_{K-1}]
 // ------------------------------------------------------------------------------------------------
 template <int T>
+__device__ __forceinline__ void group_sync() {
+    if (T == 32) __syncwarp(); else __syncthreads();
+}
+
+template <int T>
 __device__ __forceinline__ float group_sum(float v, float *red, int tid) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (T == 32) return v;
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
         int i = e / W, o = e - i * W;
         aug[i * S + o] = o < N ? (double)mob[((long)i * C) * cols + o] : ((o - N == i) ? 1.0 : 0.0);
     }
-    __syncthreads();
+    group_sync<T>();
     double logdet = 0.0;
     float sign = 1.f;
     for (int p = 0; p < N; ++p) {
@@ -125,39 +130,39 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
             }
             if (tid == 0) piv_row = bi;
         }
-        __syncthreads();
+        group_sync<T>();
         const int pr = piv_row;
         if (pr != p) {
             for (int o = tid; o < W; o += T) {
                 double t = aug[p * S + o]; aug[p * S + o] = aug[pr * S + o]; aug[pr * S + o] = t;
             }
             sign = -sign;
-            __syncthreads();
+            group_sync<T>();
         }
         const double piv = aug[p * S + p];
         logdet += log(fabs(piv));
         if (piv < 0.0) sign = -sign;
         const double inv = 1.0 / piv;
-        __syncthreads();
+        group_sync<T>();
         if (LAP) {
             // Gauss-Jordan: scale the pivot row, eliminate the column from every other row
             for (int o = tid; o < W; o += T) aug[p * S + o] *= inv;
-            __syncthreads();
+            group_sync<T>();
             for (int e = tid; e < N * W; e += T) {
                 int i = e / W, o = e - i * W;
                 if (i != p && o != p) aug[i * S + o] = fma(-aug[i * S + p], aug[p * S + o], aug[i * S + o]);
             }
-            __syncthreads();
+            group_sync<T>();
             for (int i = tid; i < N; i += T)
                 if (i != p) aug[i * S + p] = 0.0;
-            __syncthreads();
+            group_sync<T>();
         } else {
             const int rem = N - p - 1;
             for (int e = tid; e < rem * rem; e += T) {
                 int i = p + 1 + e / rem, o = p + 1 + e % rem;
                 aug[i * S + o] = fma(-aug[i * S + p] * inv, aug[p * S + o], aug[i * S + o]);
             }
-            __syncthreads();
+            group_sync<T>();
         }
     }
     float *out = det + bd * (long)(LAP ? K + 3 : 2);
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
         int o = e / N, i = e - o * N;
         Ainv[o * (N + 1) + i] = (float)aug[o * S + N + i];
     }
-    __syncthreads();
+    group_sync<T>();
     // Laplacian term tr(Ainv lapA)
     float part = 0.f;
     for (int e = tid; e < N * N; e += T) {
@@ -177,22 +182,37 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
     }
     float lap = group_sum<T>(part, red, tid);
     float tr2_total = 0.f;
+    // P = Ainv dA_k in strips: one strip = row o, TQ consecutive columns (TQ+1 shared loads per TQ FMAs)
+    constexpr int TQ = 8;
+    const int n_qc = (N + TQ - 1) / TQ, n_strips = N * n_qc;
     for (int k = 0; k < K; ++k) {
-        __syncthreads();
+        group_sync<T>();
         for (int e = tid; e < N * N; e += T) {
             int i = e / N, o = e - i * N;
             dA[i * (N + 1) + o] = mob[((long)i * C + 1 + k) * cols + o];
         }
-        __syncthreads();
+        group_sync<T>();
         float gk = 0.f;
-        for (int e = tid; e < N * N; e += T) {
-            int o = e / N, q = e - o * N;      // P[o][q] = sum_i Ainv[o][i] dA[i][q]
-            float acc = 0.f;
-            for (int i = 0; i < N; ++i) acc = fmaf(Ainv[o * (N + 1) + i], dA[i * (N + 1) + q], acc);
-            P[o * (N + 1) + q] = acc;
-            if (o == q) gk += acc;
+        for (int sidx = tid; sidx < n_strips; sidx += T) {
+            const int o = sidx / n_qc, q0 = (sidx - o * n_qc) * TQ;
+            float acc[TQ];
+#pragma unroll
+            for (int t = 0; t < TQ; ++t) acc[t] = 0.f;
+            for (int i = 0; i < N; ++i) {
+                const float av = Ainv[o * (N + 1) + i];
+                const float *drow = dA + i * (N + 1) + q0;
+#pragma unroll
+                for (int t = 0; t < TQ; ++t)
+                    if (q0 + t < N) acc[t] = fmaf(av, drow[t], acc[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < TQ; ++t)
+                if (q0 + t < N) {
+                    P[o * (N + 1) + q0 + t] = acc[t];
+                    if (q0 + t == o) gk += acc[t];
+                }
         }
-        __syncthreads();
+        group_sync<T>();
         float t2 = 0.f;
         for (int e = tid; e < N * N; e += T) {
             int o = e / N, q = e - o * N;

@@ -401,75 +401,112 @@ int launch_mean(dpe_model *m, const float *x, int ldx, int Bc, int C, int d_in, 
 // ------------------------------------------------------------------------------------------------
 // SchNet convolution (ferminet_embedding.py:159-175) with the product rule:
 //   conv_ee[i] = sum_j w[i,j] * hm[j]   (incl. j == i),   conv_eI[i] = (precomputed by the el-ion stream)
-// One block per (b, i); work items (c, f).
+// Laplacian mode: one block per (walker, slab of CS channels); thread = (channel, feature). The channel slab of
+// hm for all electrons stays in shared memory; the pair weights of one electron i are staged per iteration.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_conv(const float *__restrict__ r, int N, int C, int CP, int CE, int emb, int dE,
-                                               const float *__restrict__ hm, const float *__restrict__ pw,
-                                               const float *__restrict__ ei, float *__restrict__ x, int ldx, int col_ee) {
-    extern __shared__ float sm[];      // u[N][3], invd[N]
-    float *u = sm, *invd = sm + 3 * N;
-    const long bi = blockIdx.x;
-    const long b = bi / N;
-    const int i = (int)(bi - b * N);
-    const float *rb = r + b * N * 3;
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        float dx = rb[j * 3] - rb[i * 3], dy = rb[j * 3 + 1] - rb[i * 3 + 1], dz = rb[j * 3 + 2] - rb[i * 3 + 2];
-        float d2 = dx * dx + dy * dy + dz * dz;
-        float inv = (j == i) ? 0.f : 1.0f / sqrtf(d2);
-        u[j * 3] = dx * inv; u[j * 3 + 1] = dy * inv; u[j * 3 + 2] = dz * inv;
-        invd[j] = inv;
+template <int CS>
+__global__ void __launch_bounds__(CS * 32) k_conv_lap(const float *__restrict__ r, int N, int C, int emb, int dE,
+                                                       const float *__restrict__ hm, const float *__restrict__ pw,
+                                                       const float *__restrict__ ei, float *__restrict__ x, int ldx, int col_ee) {
+    extern __shared__ float sm[];
+    float *r_s = sm;                         // [N][3]
+    float *hm0_s = r_s + 3 * N;              // [N][emb]      value channel of hm
+    float *hmd_s = hm0_s + N * emb;          // [N][3][emb]   d hm_j / d r_j
+    float *hm_s = hmd_s + 3 * N * emb;       // [N][CS][emb]  this block's channel slab
+    float *w_s = hm_s + N * CS * emb;        // [N][3][emb]   w, w', w'' of pairs (i, :)
+    const int n_slabs = (C + CS - 1) / CS;
+    const long b = blockIdx.x / n_slabs;
+    const int slab = blockIdx.x - (int)(b * n_slabs);
+    const int cl = threadIdx.x >> 5, f = threadIdx.x & 31;
+    const int c = slab * CS + cl;
+    const bool act = c < C && f < emb;
+    const float *hmb = hm + b * N * C * emb;   // [j][c][f]
+    for (int t = threadIdx.x; t < 3 * N; t += blockDim.x) r_s[t] = r[b * N * 3 + t];
+    for (int t = threadIdx.x; t < N * emb; t += blockDim.x) {
+        int j = t / emb, ff = t - j * emb;
+        hm0_s[t] = hmb[((long)j * C) * emb + ff];
     }
-    __syncthreads();
-    const float *hmb = hm + b * N * C * emb;                 // [j][c][f]
-    const float *pwi = pw + (b * N + i) * (long)N * CP * emb;  // [j][ch][f]
-    float *xrow = x + (b * N + i) * (long)C * ldx;
-    const int n_items = C * emb;
-    for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
-        int c = item / emb, f = item - c * emb;
-        float acc = 0.f;
-        for (int j = 0; j < N; ++j) acc = fmaf(pwi[(long)j * CP * emb + f], hmb[((long)j * C + c) * emb + f], acc);
-        if (C > 1) {
-            if (c == C - 1) {
+    for (int t = threadIdx.x; t < 3 * N * emb; t += blockDim.x) {
+        int j = t / (3 * emb), rem = t - j * 3 * emb, a = rem / emb, ff = rem - a * emb;
+        hmd_s[t] = hmb[((long)j * C + 1 + 3 * j + a) * emb + ff];
+    }
+    for (int t = threadIdx.x; t < N * CS * emb; t += blockDim.x) {
+        int j = t / (CS * emb), rem = t - j * CS * emb, cc = rem / emb, ff = rem - cc * emb;
+        int cg = slab * CS + cc;
+        hm_s[t] = cg < C ? hmb[((long)j * C + cg) * emb + ff] : 0.f;
+    }
+    // channel classification of this thread
+    const bool is_lap = c == C - 1;
+    const int k = c - 1, e = (c > 0 && !is_lap) ? k / 3 : -1, a = k - 3 * (k / 3);
+    const int wrow = 3 * N * emb;
+    for (int i = 0; i < N; ++i) {
+        __syncthreads();
+        const float *pwi = pw + (b * N + i) * (long)wrow;     // [j][ch][f], contiguous
+        for (int t = threadIdx.x; t < wrow; t += blockDim.x) w_s[t] = pwi[t];
+        __syncthreads();
+        float *xrow = x + ((b * N + i) * (long)C + c) * ldx + col_ee;
+        if (act) {
+            float acc = 0.f;
+            for (int j = 0; j < N; ++j) acc = fmaf(w_s[(j * 3) * emb + f], hm_s[(j * CS + cl) * emb + f], acc);
+            const float xi = r_s[3 * i], yi = r_s[3 * i + 1], zi = r_s[3 * i + 2];
+            if (is_lap) {
                 for (int j = 0; j < N; ++j) {
                     if (j == i) continue;
-                    float w1 = pwi[((long)j * CP + 1) * emb + f], w2 = pwi[((long)j * CP + 2) * emb + f];
-                    float h0 = hmb[((long)j * C) * emb + f];
-                    float cross = 0.f;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a)
-                        cross = fmaf(u[j * 3 + a], hmb[((long)j * C + 1 + 3 * j + a) * emb + f] - hmb[((long)j * C + 1 + 3 * i + a) * emb + f], cross);
-                    acc += (2.f * w2 + 4.f * w1 * invd[j]) * h0 + 2.f * w1 * cross;
+                    float dx = r_s[3 * j] - xi, dy = r_s[3 * j + 1] - yi, dz = r_s[3 * j + 2] - zi;
+                    float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+                    float w1 = w_s[(j * 3 + 1) * emb + f], w2 = w_s[(j * 3 + 2) * emb + f];
+                    const float *hji = hmb + ((long)j * C + 1 + 3 * i) * emb + f;      // d hm_j / d r_i
+                    float cross = dx * (hmd_s[(j * 3) * emb + f] - hji[0]) + dy * (hmd_s[(j * 3 + 1) * emb + f] - hji[emb]) +
+                                  dz * (hmd_s[(j * 3 + 2) * emb + f] - hji[2 * emb]);
+                    acc += (2.f * w2 + 4.f * w1 * inv) * hm0_s[j * emb + f] + 2.f * w1 * (cross * inv);
                 }
-            } else if (c > 0) {
-                int k = c - 1, e = k / 3, a = k - 3 * e;
-                if (e == i) {
-                    float sacc = 0.f;
-                    for (int j = 0; j < N; ++j) {
-                        if (j == i) continue;
-                        sacc = fmaf(pwi[((long)j * CP + 1) * emb + f] * u[j * 3 + a], hmb[((long)j * C) * emb + f], sacc);
-                    }
-                    acc -= sacc;
-                } else {
-                    acc = fmaf(pwi[((long)e * CP + 1) * emb + f] * u[e * 3 + a], hmb[((long)e * C) * emb + f], acc);
+            } else if (e == i) {
+                float sacc = 0.f;
+                for (int j = 0; j < N; ++j) {
+                    if (j == i) continue;
+                    float dx = r_s[3 * j] - xi, dy = r_s[3 * j + 1] - yi, dz = r_s[3 * j + 2] - zi;
+                    float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+                    float ua = (a == 0 ? dx : (a == 1 ? dy : dz)) * inv;
+                    sacc = fmaf(w_s[(j * 3 + 1) * emb + f] * ua, hm0_s[j * emb + f], sacc);
                 }
+                acc -= sacc;
+            } else if (e >= 0) {
+                float dx = r_s[3 * e] - xi, dy = r_s[3 * e + 1] - yi, dz = r_s[3 * e + 2] - zi;
+                float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+                float ua = (a == 0 ? dx : (a == 1 ? dy : dz)) * inv;
+                acc = fmaf(w_s[(e * 3 + 1) * emb + f] * ua, hm0_s[e * emb + f], acc);
             }
+            xrow[f] = acc;
         }
-        xrow[(long)c * ldx + col_ee + f] = acc;
+        if (c < C && f < dE) {     // conv_eI: expand the 5-channel el-ion convolution into the C channels of electron i
+            const float *eii = ei + (b * N + i) * 5 * dE;
+            float v = 0.f;
+            if (c == 0) v = eii[f];
+            else if (is_lap) v = eii[4 * dE + f];
+            else if (e == i) v = eii[(1 + a) * dE + f];
+            xrow[emb + f] = v;
+        }
     }
-    // conv_eI columns: expand the 5-channel el-ion convolution into the C channels of electron i
-    const float *eii = ei + bi * CE * dE;
-    for (int item = threadIdx.x; item < C * dE; item += blockDim.x) {
-        int c = item / dE, f = item - c * dE;
-        float v = 0.f;
-        if (c == 0) v = eii[f];
-        else if (C > 1) {
-            if (c == C - 1) v = eii[4 * dE + f];
-            else {
-                int k = c - 1, e = k / 3, a = k - 3 * e;
-                if (e == i) v = eii[(1 + a) * dE + f];
-            }
+}
+
+// forward-only mode: one block per walker, warp per electron
+__global__ void __launch_bounds__(256) k_conv_fwd(int N, int emb, int dE, const float *__restrict__ hm,
+                                                   const float *__restrict__ pw, const float *__restrict__ ei,
+                                                   float *__restrict__ x, int ldx, int col_ee) {
+    extern __shared__ float sm[];            // hm[N][emb]
+    const long b = blockIdx.x;
+    for (int t = threadIdx.x; t < N * emb; t += blockDim.x) sm[t] = hm[b * N * emb + t];
+    __syncthreads();
+    const int f = threadIdx.x & 31;
+    for (int i = threadIdx.x >> 5; i < N; i += blockDim.x >> 5) {
+        float *xrow = x + (b * N + i) * (long)ldx + col_ee;
+        if (f < emb) {
+            const float *pwi = pw + (b * N + i) * (long)N * emb + f;
+            float acc = 0.f;
+            for (int j = 0; j < N; ++j) acc = fmaf(pwi[j * emb], sm[j * emb + f], acc);
+            xrow[f] = acc;
         }
-        xrow[(long)c * ldx + col_ee + emb + f] = v;
+        if (f < dE) xrow[emb + f] = ei[(b * N + i) * dE + f];
     }
 }
 
@@ -477,9 +514,16 @@ int launch_conv(dpe_model *m, int it, const float *r, int Bc, int C, const float
                 float *x, int ldx, cudaStream_t s) {
     const dpe_dims &d = m->dims;
     const IterParams &p = m->it[it];
-    int CP = C > 1 ? 3 : 1, CE = C > 1 ? 5 : 1;
-    size_t smem = (size_t)4 * d.n_el * sizeof(float);
-    k_conv<<<Bc * d.n_el, 256, smem, s>>>(r, d.n_el, C, CP, CE, d.emb_dim, p.dE, hm, pw, ei, x, ldx, p.d_in);
+    const int N = d.n_el, emb = d.emb_dim;
+    if (C == 1) {
+        k_conv_fwd<<<Bc, 256, (size_t)N * emb * sizeof(float), s>>>(N, emb, p.dE, hm, pw, ei, x, ldx, p.d_in);
+    } else {
+        constexpr int CS = 8;
+        size_t smem = ((size_t)3 * N + (size_t)N * emb * (1 + 3 + CS + 3)) * sizeof(float);
+        if (smem > 48 * 1024) DPE_CUDA(cudaFuncSetAttribute(k_conv_lap<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int n_slabs = (C + CS - 1) / CS;
+        k_conv_lap<CS><<<Bc * n_slabs, CS * 32, smem, s>>>(r, N, C, emb, p.dE, hm, pw, ei, x, ldx, p.d_in);
+    }
     DPE_LAUNCH_CHECK(m);
     return DPE_OK;
 }

@@ -92,7 +92,7 @@ def main():
     print(f"  E_loc max rel err {err:.2e}   (E_loc ref {ref['E_loc'][:3].tolist()})")
     ph, lp = eng.log_psi_sqr(r32.cuda())
     print(f"  forward-only: logpsi2 {rel(lp, ref['logpsi2']):.2e}  |dlogpsi2| max {(lp.double().cpu() - ref['logpsi2']).abs().max().item():.2e} "
-          f"phase_eq {bool((ph.cpu().double() == ref['phase']).all())}")
+          f"phase_eq {bool(((ph.cpu() > 1) == (ref['phase'] > 1)).all())}")
     print(f"  launches so far: {eng.launch_count()}")
     mcmc_report(eng, phys, d, params64, r32, R)
 
