@@ -182,14 +182,34 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
     }
     float lap = group_sum<T>(part, red, tid);
     float tr2_total = 0.f;
-    // P = Ainv dA_k in strips: one strip = row o, TQ consecutive columns (TQ+1 shared loads per TQ FMAs)
+    // P = Ainv dA_k in strips: one strip = row o, TQ consecutive columns (TQ+1 shared loads per TQ FMAs).
+    // Element -> (row, column) maps are hoisted out of the k loop (runtime N: integer divisions are expensive).
     constexpr int TQ = 8;
+    constexpr int ME = T == 32 ? 8 : 16;                   // register-cached element slots per thread (covers N*N <= ME*T)
     const int n_qc = (N + TQ - 1) / TQ, n_strips = N * n_qc;
+    int src_off[ME], dst_off[ME], tr_off[ME];
+#pragma unroll
+    for (int sl = 0; sl < ME; ++sl) {
+        int e = tid + sl * T;
+        int i = e / N, o = e - i * N;
+        bool ok = e < N * N;
+        src_off[sl] = ok ? (i * C) * cols + o : -1;
+        dst_off[sl] = i * (N + 1) + o;
+        tr_off[sl] = o * (N + 1) + i;
+    }
+    const bool cached = N * N <= ME * T;
     for (int k = 0; k < K; ++k) {
+        const float *mk = mob + (long)(1 + k) * cols;
         group_sync<T>();
-        for (int e = tid; e < N * N; e += T) {
-            int i = e / N, o = e - i * N;
-            dA[i * (N + 1) + o] = mob[((long)i * C + 1 + k) * cols + o];
+        if (cached) {
+#pragma unroll
+            for (int sl = 0; sl < ME; ++sl)
+                if (src_off[sl] >= 0) dA[dst_off[sl]] = mk[src_off[sl]];
+        } else {
+            for (int e = tid; e < N * N; e += T) {
+                int i = e / N, o = e - i * N;
+                dA[i * (N + 1) + o] = mk[((long)i * C) * cols + o];
+            }
         }
         group_sync<T>();
         float gk = 0.f;
@@ -198,8 +218,9 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
             float acc[TQ];
 #pragma unroll
             for (int t = 0; t < TQ; ++t) acc[t] = 0.f;
+            const float *arow = Ainv + o * (N + 1);
             for (int i = 0; i < N; ++i) {
-                const float av = Ainv[o * (N + 1) + i];
+                const float av = arow[i];
                 const float *drow = dA + i * (N + 1) + q0;
 #pragma unroll
                 for (int t = 0; t < TQ; ++t)
@@ -214,10 +235,17 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
         }
         group_sync<T>();
         float t2 = 0.f;
-        for (int e = tid; e < N * N; e += T) {
-            int o = e / N, q = e - o * N;
-            t2 = fmaf(P[o * (N + 1) + q], P[q * (N + 1) + o], t2);
+        if (cached) {
+#pragma unroll
+            for (int sl = 0; sl < ME; ++sl)
+                if (src_off[sl] >= 0) t2 = fmaf(P[dst_off[sl]], P[tr_off[sl]], t2);
+        } else {
+            for (int e = tid; e < N * N; e += T) {
+                int o = e / N, q = e - o * N;
+                t2 = fmaf(P[o * (N + 1) + q], P[q * (N + 1) + o], t2);
+            }
         }
+        // one reduction for both sums: pack (gk, t2) through the shuffle tree
         gk = group_sum<T>(gk, red, tid);
         t2 = group_sum<T>(t2, red, tid);
         tr2_total += t2;
