@@ -40,13 +40,27 @@ __global__ void __launch_bounds__(256) k_envelope(const float *__restrict__ r, c
         if (C == 1) {
             p[0] *= env;
         } else {
-            float bf0 = p[0];
-            float t0 = p[(long)(1 + 3 * i) * cols], t1 = p[(long)(2 + 3 * i) * cols], t2 = p[(long)(3 + 3 * i) * cols];
-            for (int c = 0; c < C; ++c) p[(long)c * cols] *= env;
-            p[(long)(1 + 3 * i) * cols] += e1[0] * bf0;
-            p[(long)(2 + 3 * i) * cols] += e1[1] * bf0;
-            p[(long)(3 + 3 * i) * cols] += e1[2] * bf0;
-            p[(long)(C - 1) * cols] += el * bf0 + 2.f * (e1[0] * t0 + e1[1] * t1 + e1[2] * t2);
+            const float bf0 = p[0];
+            const int ci = 1 + 3 * i;
+            const float t0 = p[(long)ci * cols], t1 = p[(long)(ci + 1) * cols], t2 = p[(long)(ci + 2) * cols];
+            const float lap_extra = el * bf0 + 2.f * (e1[0] * t0 + e1[1] * t1 + e1[2] * t2);
+            constexpr int UB = 8;      // batch the loads ahead of the in-place stores
+            for (int c0 = 0; c0 < C; c0 += UB) {
+                float v[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u)
+                    if (c0 + u < C) v[u] = p[(long)(c0 + u) * cols];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int c = c0 + u;
+                    if (c < C) {
+                        float o = v[u] * env;
+                        if (c >= ci && c < ci + 3) o += (c == ci ? e1[0] : (c == ci + 1 ? e1[1] : e1[2])) * bf0;
+                        if (c == C - 1) o += lap_extra;
+                        p[(long)c * cols] = o;
+                    }
+                }
+            }
         }
     }
 }
@@ -254,6 +268,150 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
     if (tid == 0) out[2] = lap - tr2_total;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small systems (N <= 16): one warp per (walker, determinant), 4 warps per block. Lane = column of the augmented
+// matrix [A | I] during the FP64 Gauss-Jordan sweep (no index arithmetic, conflict-free rows of 32 doubles);
+// tangent stage in 8-column strips with zero-padded 16-float rows (2 x LDS.128 per 8 FMAs).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <bool LAP>
+__global__ void __launch_bounds__(128, 5) k_det_warp(int N, int C, int n_det, long n_mat, const float *__restrict__ mo,
+                                                   float *__restrict__ det) {
+    extern __shared__ double smd[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long bd = blockIdx.x * 4L + wib;
+    if (bd >= n_mat) return;
+    const int per_warp_doubles = N * 32 + (LAP ? (N * (N + 1) + N * 16 + N * 17 + 1) / 2 + 2 : 0);
+    double *aug = smd + (size_t)wib * per_warp_doubles;      // [N][32]
+    float *Ainv = reinterpret_cast<float *>(aug + N * 32);    // [N][N+1]
+    float *dA = Ainv + N * (N + 1);                           // [N][16]
+    float *P = dA + N * 16;                                   // [N][17]
+    dA = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(dA) + 15) & ~uintptr_t(15));   // float4 loads
+    if (LAP) P = dA + N * 16;
+    const long b = bd / n_det;
+    const int dt = (int)(bd - b * n_det);
+    const int cols = n_det * N, K = C - 2, W = LAP ? 2 * N : N;
+    const float *mob = mo + b * (long)N * C * cols + (long)dt * N;   // element (i, c, o): mob[(i*C + c)*cols + o]
+
+    for (int i = 0; i < N; ++i) {
+        double v = 0.0;
+        if (lane < N) v = (double)mob[((long)i * C) * cols + lane];
+        else if (lane - N == i) v = 1.0;
+        aug[i * 32 + lane] = v;
+    }
+    __syncwarp();
+    double logdet = 0.0;
+    float sign = 1.f;
+    for (int p = 0; p < N; ++p) {
+        float best = (lane >= p && lane < N) ? fabsf((float)aug[lane * 32 + p]) : -1.f;
+        int bi = lane;
+        for (int o = 16; o; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (bi != p) {
+            double t = aug[p * 32 + lane];
+            aug[p * 32 + lane] = aug[bi * 32 + lane];
+            aug[bi * 32 + lane] = t;
+            sign = -sign;
+            __syncwarp();
+        }
+        const double piv = aug[p * 32 + p];
+        logdet += log(fabs(piv));
+        if (piv < 0.0) sign = -sign;
+        __syncwarp();
+        if (LAP) {
+            const double rowp = aug[p * 32 + lane] / piv;
+            if (lane != p) aug[p * 32 + lane] = rowp;          // column p is left as is: it is never read again
+            for (int i = 0; i < N; ++i) {
+                const double fct = aug[i * 32 + p];
+                if (i != p && lane != p && lane < W) aug[i * 32 + lane] = fma(-fct, rowp, aug[i * 32 + lane]);
+            }
+        } else {
+            const double rowp = aug[p * 32 + lane] / piv;
+            for (int i = p + 1; i < N; ++i) {
+                const double fct = aug[i * 32 + p];
+                if (lane > p && lane < N) aug[i * 32 + lane] = fma(-fct, rowp, aug[i * 32 + lane]);
+            }
+        }
+        __syncwarp();
+    }
+    float *out = det + bd * (long)(LAP ? K + 3 : 2);
+    if (lane == 0) { out[0] = (float)logdet; out[1] = sign; }
+    if (!LAP) return;
+
+    for (int o = 0; o < N; ++o)
+        if (lane < N) Ainv[o * (N + 1) + lane] = (float)aug[o * 32 + N + lane];
+    for (int e = lane; e < N * 16; e += 32) dA[e] = 0.f;       // zero padding of the 16-float rows
+    // element slots (hoisted index math): e = lane + 32 s -> (i, o)
+    int src_off[8], d16[8], p17[8], t17[8];
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) {
+        int e = lane + 32 * sl;
+        int i = e / N, o = e - i * N;
+        bool ok = e < N * N;
+        src_off[sl] = ok ? (i * C) * cols + o : -1;
+        d16[sl] = i * 16 + o;
+        p17[sl] = i * 17 + o;
+        t17[sl] = o * 17 + i;
+    }
+    __syncwarp();
+    float part = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl)
+        if (src_off[sl] >= 0) {
+            int e = lane + 32 * sl, i = e / N, o = e - i * N;
+            part = fmaf(Ainv[o * (N + 1) + i], mob[(long)(C - 1) * cols + src_off[sl]], part);
+        }
+    const float lap = warp_sum(part);
+    const int orow = lane >> 1, q0 = (lane & 1) * 8;
+    const bool strip = orow < N;
+    float t2 = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float *mk = mob + (long)(1 + k) * cols;
+        float ld[8];
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) ld[sl] = src_off[sl] >= 0 ? mk[src_off[sl]] : 0.f;
+        __syncwarp();
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl)
+            if (src_off[sl] >= 0) dA[d16[sl]] = ld[sl];
+        __syncwarp();
+        float gk = 0.f;
+        if (strip) {
+            float acc[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+            const float *arow = Ainv + orow * (N + 1);
+            for (int i = 0; i < N; ++i) {
+                const float av = arow[i];
+                const float4 x0 = *reinterpret_cast<const float4 *>(dA + i * 16 + q0);
+                const float4 x1 = *reinterpret_cast<const float4 *>(dA + i * 16 + q0 + 4);
+                acc[0] = fmaf(av, x0.x, acc[0]); acc[1] = fmaf(av, x0.y, acc[1]); acc[2] = fmaf(av, x0.z, acc[2]); acc[3] = fmaf(av, x0.w, acc[3]);
+                acc[4] = fmaf(av, x1.x, acc[4]); acc[5] = fmaf(av, x1.y, acc[5]); acc[6] = fmaf(av, x1.z, acc[6]); acc[7] = fmaf(av, x1.w, acc[7]);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                P[orow * 17 + q0 + t] = acc[t];
+                if (q0 + t == orow) gk = acc[t];
+            }
+        }
+        gk = warp_sum(gk);
+        if (lane == 0) out[3 + k] = gk;
+        __syncwarp();
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl)
+            if (src_off[sl] >= 0) t2 = fmaf(P[p17[sl]], P[t17[sl]], t2);
+    }
+    t2 = warp_sum(t2);
+    if (lane == 0) out[2] = lap - t2;
+}
+
 int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStream_t s) {
     const dpe_dims &d = m->dims;
     const int N = d.n_el;
@@ -261,8 +419,10 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStr
     size_t smem = (size_t)N * ((lap ? 2 * N : N) + 1) * sizeof(double) + ((lap ? 3 * (size_t)N * (N + 1) : 0) + 16) * sizeof(float);
     int blocks = Bc * d.n_dets;
     if (N <= 16) {
-        if (lap) k_det<32, true><<<blocks, 32, smem, s>>>(N, C, d.n_dets, mo, det);
-        else k_det<32, false><<<blocks, 32, smem, s>>>(N, C, d.n_dets, mo, det);
+        const size_t per_warp = ((size_t)N * 32 + (lap ? ((size_t)N * (N + 1) + N * 16 + N * 17 + 1) / 2 + 2 : 0)) * sizeof(double);
+        const long n_mat = (long)blocks;
+        if (lap) k_det_warp<true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det);
+        else k_det_warp<false><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det);
     } else {
         if (smem > 48 * 1024) {
             DPE_CUDA(cudaFuncSetAttribute(k_det<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -232,42 +232,96 @@ struct PairArgs {
     long n_pairs;  // Bc*N*N
 };
 
+// Tiny dense layer for one pair held by a warp: lane = output feature, the input vector x[c][0:din] sits in a
+// per-warp shared buffer (float4 broadcast reads), weights are staged as [k/4][n][4] (one LDS.128 per 4 k).
 template <int CH>
-__global__ void __launch_bounds__(256) k_pair_stream(PairArgs a) {
-    extern __shared__ float smem[];
-    // per iteration: [same block][diff block], each = w_w | w_b | (h_w | h_b)
-    int base[DPE_MAX_ITER], blk[DPE_MAX_ITER];
-    {
-        int off = 0;
-        for (int it = 0; it < a.n_iter; ++it) {
-            base[it] = off;
-            blk[it] = a.dP[it] * a.emb + a.emb + ((it + 1 < a.n_iter) ? a.dP[it] * a.dP[it + 1] + a.dP[it + 1] : 0);
-            off += 2 * blk[it];
+__device__ __forceinline__ void pair_dense_tanh(const float *__restrict__ W4, const float *__restrict__ bias, int din,
+                                                int dout, const float *__restrict__ xs, float (&y)[CH], int lane) {
+    float z[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) z[c] = 0.f;
+    const bool act = lane < dout;
+    if (din == 1) {
+        const float w = act ? W4[lane * 4] : 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) z[c] = xs[c * 32] * w;
+    } else {
+        const int nk4 = din >> 2;
+        for (int k4 = 0; k4 < nk4; ++k4) {
+            const float4 w = act ? *reinterpret_cast<const float4 *>(W4 + (k4 * dout + lane) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const float4 xv = *reinterpret_cast<const float4 *>(xs + c * 32 + k4 * 4);
+                z[c] = fmaf(xv.x, w.x, z[c]); z[c] = fmaf(xv.y, w.y, z[c]); z[c] = fmaf(xv.z, w.z, z[c]); z[c] = fmaf(xv.w, w.w, z[c]);
+            }
         }
     }
+    if (act) z[0] += bias[lane];
+    float t = tanh_f32(z[0]);
+    float d1 = 1.f - t * t;
+    y[0] = act ? t : 0.f;
+    if (CH > 1) {
+        float ssq = 0.f;
+#pragma unroll
+        for (int c = 1; c < CH - 1; ++c) {
+            ssq = fmaf(z[c], z[c], ssq);
+            y[c] = act ? d1 * z[c] : 0.f;
+        }
+        y[CH - 1] = act ? d1 * z[CH - 1] - 2.f * t * d1 * ssq : 0.f;
+    }
+}
+
+// One warp per UNORDERED electron pair (i <= j): w(i,j) = w(j,i) because both orderings see the same distance and the
+// same (same-spin / different-spin) weights (ferminet_embedding.py:197-205: diff = concat(ud, du) through one MLP).
+template <int CH>
+__global__ void __launch_bounds__(256) k_pair_stream(PairArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    // per iteration: [same block][diff block], each = w_w | w_b | (h_w | h_b); weights re-laid out as [k/4][n][4]
+    int base[DPE_MAX_ITER], blk[DPE_MAX_ITER];
+    int off = 0;
+    for (int it = 0; it < a.n_iter; ++it) {
+        base[it] = off;
+        const int kp = a.dP[it] == 1 ? 4 : a.dP[it];        // din = 1 is padded to one k4 group
+        blk[it] = kp * a.emb + a.emb + ((it + 1 < a.n_iter) ? kp * a.dP[it + 1] + a.dP[it + 1] : 0);
+        off += 2 * blk[it];
+    }
+    float *xs_all = smem + off;                               // [8 warps][CH][32]
+    int *pair_tab = reinterpret_cast<int *>(xs_all + 8 * CH * 32);   // [n_up_pairs] packed (i << 8) | j
+    auto stage = [&](float *dst, const float *src, int din, int dout) {
+        const int kp = din == 1 ? 4 : din;
+        for (int t = threadIdx.x; t < kp * dout; t += blockDim.x) {
+            int k4 = t / (dout * 4), rem = t - k4 * dout * 4, n = rem >> 2, kk = rem & 3, k = k4 * 4 + kk;
+            dst[t] = k < din ? src[k * dout + n] : 0.f;
+        }
+    };
     for (int it = 0; it < a.n_iter; ++it)
         for (int sd = 0; sd < 2; ++sd) {
             float *dst = smem + base[it] + sd * blk[it];
-            const int nww = a.dP[it] * a.emb;
-            for (int t = threadIdx.x; t < nww; t += blockDim.x) dst[t] = a.ww[it][sd][t];
-            for (int t = threadIdx.x; t < a.emb; t += blockDim.x) dst[nww + t] = a.wb[it][sd][t];
+            const int kp = a.dP[it] == 1 ? 4 : a.dP[it];
+            stage(dst, a.ww[it][sd], a.dP[it], a.emb);
+            for (int t = threadIdx.x; t < a.emb; t += blockDim.x) dst[kp * a.emb + t] = a.wb[it][sd][t];
             if (it + 1 < a.n_iter) {
-                const int nhw = a.dP[it] * a.dP[it + 1];
-                for (int t = threadIdx.x; t < nhw; t += blockDim.x) dst[nww + a.emb + t] = a.hw[it][sd][t];
-                for (int t = threadIdx.x; t < a.dP[it + 1]; t += blockDim.x) dst[nww + a.emb + nhw + t] = a.hb[it][sd][t];
+                stage(dst + kp * a.emb + a.emb, a.hw[it][sd], a.dP[it], a.dP[it + 1]);
+                for (int t = threadIdx.x; t < a.dP[it + 1]; t += blockDim.x) dst[kp * a.emb + a.emb + kp * a.dP[it + 1] + t] = a.hb[it][sd][t];
             }
         }
+    const int n_up = a.N * (a.N + 1) / 2;
+    for (int t = threadIdx.x; t < n_up; t += blockDim.x) {     // decode t -> (i <= j)
+        int i = 0, rem = t;
+        while (rem >= a.N - i) { rem -= a.N - i; ++i; }
+        pair_tab[t] = (i << 8) | (i + rem);
+    }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
-    const int NN = a.N * a.N;
-    for (long p = blockIdx.x * (long)wpb + (threadIdx.x >> 5); p < a.n_pairs; p += (long)gridDim.x * wpb) {
-        long b = p / NN;
-        int ij = (int)(p - b * NN);
-        int i = ij / a.N, j = ij - i * a.N;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float *xs = xs_all + wib * CH * 32;
+    const long n_units = a.n_pairs / (a.N * a.N) * n_up;       // walkers x unordered pairs
+    for (long p = blockIdx.x * 8L + wib; p < n_units; p += gridDim.x * 8L) {
+        const long b = p / n_up;
+        const int pk = pair_tab[(int)(p - b * n_up)];
+        const int i = pk >> 8, j = pk & 255;
         const float *ri = a.r + (b * a.N + i) * 3, *rj = a.r + (b * a.N + j) * 3;
-        float dx = rj[0] - ri[0], dy = rj[1] - ri[1], dz = rj[2] - ri[2];
-        float d = (i == j) ? 0.f : sqrtf(dx * dx + dy * dy + dz * dz);   // utils.py:299-300: diagonal exactly 0, zero grads
+        const float dx = rj[0] - ri[0], dy = rj[1] - ri[1], dz = rj[2] - ri[2];
+        const float d = (i == j) ? 0.f : sqrtf(dx * dx + dy * dy + dz * dz);   // utils.py:299-300: diagonal exactly 0, zero grads
         const int sd = ((i < a.U) == (j < a.U)) ? 0 : 1;
         float x[CH];
         x[0] = lane == 0 ? d : 0.f;
@@ -275,21 +329,29 @@ __global__ void __launch_bounds__(256) k_pair_stream(PairArgs a) {
             x[1] = (lane == 0 && i != j) ? 1.f : 0.f;
             x[2] = 0.f;
         }
+        const long o_ij = ((b * a.N + i) * a.N + j) * (long)CH * a.emb, o_ji = ((b * a.N + j) * a.N + i) * (long)CH * a.emb;
 #pragma unroll
         for (int it = 0; it < DPE_MAX_ITER; ++it) {
             if (it < a.n_iter) {
-                float w[CH];
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < CH; ++c) xs[c * 32 + lane] = x[c];
+                __syncwarp();
                 const float *blkp = smem + base[it] + sd * blk[it];
-                const int nww = a.dP[it] * a.emb;
-                warp_dense_tanh<CH>(blkp, blkp + nww, a.dP[it], a.emb, x, w, lane);
+                const int kp = a.dP[it] == 1 ? 4 : a.dP[it];
+                float w[CH];
+                pair_dense_tanh<CH>(blkp, blkp + kp * a.emb, a.dP[it], a.emb, xs, w, lane);
                 if (lane < a.emb) {
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) a.out[it][(p * CH + c) * a.emb + lane] = w[c];
+                    for (int c = 0; c < CH; ++c) {
+                        a.out[it][o_ij + c * a.emb + lane] = w[c];
+                        if (i != j) a.out[it][o_ji + c * a.emb + lane] = w[c];
+                    }
                 }
                 if (it + 1 < a.n_iter) {
                     float y[CH];
-                    const float *hwp = blkp + nww + a.emb;
-                    warp_dense_tanh<CH>(hwp, hwp + a.dP[it] * a.dP[it + 1], a.dP[it], a.dP[it + 1], x, y, lane);
+                    const float *hwp = blkp + kp * a.emb + a.emb;
+                    pair_dense_tanh<CH>(hwp, hwp + kp * a.dP[it + 1], a.dP[it], a.dP[it + 1], xs, y, lane);
                     const bool res = a.dP[it] == a.dP[it + 1];
 #pragma unroll
                     for (int c = 0; c < CH; ++c) x[c] = res ? (x[c] + y[c]) * 0.70710678118654752f : y[c];
@@ -313,11 +375,13 @@ int launch_pair_stream(dpe_model *m, const float *r, int Bc, int CP, float *pw_b
         a.ww[it][1] = p.w_diff.w; a.wb[it][1] = p.w_diff.b;
         a.hw[it][0] = p.h_same.w; a.hb[it][0] = p.h_same.b;
         a.hw[it][1] = p.h_diff.w; a.hb[it][1] = p.h_diff.b;
-        fl += 2 * ((size_t)p.dP * d.emb_dim + d.emb_dim);
-        if (it + 1 < d.n_iterations) fl += 2 * ((size_t)p.dP * m->it[it + 1].dP + m->it[it + 1].dP);
+        const size_t kp = p.dP == 1 ? 4 : p.dP;
+        fl += 2 * (kp * d.emb_dim + d.emb_dim);
+        if (it + 1 < d.n_iterations) fl += 2 * (kp * m->it[it + 1].dP + m->it[it + 1].dP);
     }
+    fl += (size_t)8 * CP * 32 + (size_t)d.n_el * (d.n_el + 1) / 2 + 4;
     size_t smem = fl * sizeof(float);
-    long blocks = (a.n_pairs + 7) / 8;
+    long blocks = ((long)Bc * (d.n_el * (d.n_el + 1) / 2) + 7) / 8;
     if (blocks > 148 * 4) blocks = 148 * 4;
     if (CP == 1) {
         DPE_CUDA(cudaFuncSetAttribute(k_pair_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -338,34 +402,58 @@ int launch_pair_stream(dpe_model *m, const float *r, int Bc, int CP, float *pw_b
 __global__ void __launch_bounds__(256) k_act(float *__restrict__ z, int ld, long n_groups, int C, int width,
                                               const float *__restrict__ bias, const float *__restrict__ add,
                                               int groups_per_add) {
-    const long total = n_groups * width;
+    // one thread = 4 consecutive features of one group; channel loads are issued in batches of UB before the
+    // dependent stores (the update is in place, so the compiler cannot reorder them itself)
+    constexpr int UB = 8;
+    const int w4 = width >> 2;
+    const long total = n_groups * w4;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        long g = idx / width;
-        int f = (int)(idx - g * width);
+        const long g = idx / w4;
+        const int f = (int)(idx - g * w4) << 2;
         float *zp = z + g * C * ld + f;
         const float *ap = add ? add + (g / groups_per_add) * C * width + f : nullptr;
-        float z0 = zp[0] + (bias ? bias[f] : 0.f) + (ap ? ap[0] : 0.f);
-        float y = tanh_f32(z0);
-        zp[0] = y;
+        float4 z0 = *reinterpret_cast<const float4 *>(zp);
+        if (bias) { float4 b = *reinterpret_cast<const float4 *>(bias + f); z0.x += b.x; z0.y += b.y; z0.z += b.z; z0.w += b.w; }
+        if (ap) { float4 a = *reinterpret_cast<const float4 *>(ap); z0.x += a.x; z0.y += a.y; z0.z += a.z; z0.w += a.w; }
+        float4 y = make_float4(tanh_f32(z0.x), tanh_f32(z0.y), tanh_f32(z0.z), tanh_f32(z0.w));
+        *reinterpret_cast<float4 *>(zp) = y;
         if (C > 1) {
-            float d1 = 1.f - y * y;
-            float ssq = 0.f;
-            for (int c = 1; c < C - 1; ++c) {
-                float v = zp[(long)c * ld] + (ap ? ap[(long)c * width] : 0.f);
-                ssq = fmaf(v, v, ssq);
-                zp[(long)c * ld] = d1 * v;
+            const float4 d1 = make_float4(1.f - y.x * y.x, 1.f - y.y * y.y, 1.f - y.z * y.z, 1.f - y.w * y.w);
+            float4 ssq = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c0 = 1; c0 < C - 1; c0 += UB) {
+                float4 v[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u)
+                    if (c0 + u < C - 1) {
+                        v[u] = *reinterpret_cast<const float4 *>(zp + (long)(c0 + u) * ld);
+                        if (ap) {
+                            float4 a = *reinterpret_cast<const float4 *>(ap + (long)(c0 + u) * width);
+                            v[u].x += a.x; v[u].y += a.y; v[u].z += a.z; v[u].w += a.w;
+                        }
+                    }
+#pragma unroll
+                for (int u = 0; u < UB; ++u)
+                    if (c0 + u < C - 1) {
+                        ssq.x = fmaf(v[u].x, v[u].x, ssq.x); ssq.y = fmaf(v[u].y, v[u].y, ssq.y);
+                        ssq.z = fmaf(v[u].z, v[u].z, ssq.z); ssq.w = fmaf(v[u].w, v[u].w, ssq.w);
+                        *reinterpret_cast<float4 *>(zp + (long)(c0 + u) * ld) = make_float4(d1.x * v[u].x, d1.y * v[u].y, d1.z * v[u].z, d1.w * v[u].w);
+                    }
             }
-            float zl = zp[(long)(C - 1) * ld] + (ap ? ap[(long)(C - 1) * width] : 0.f);
-            zp[(long)(C - 1) * ld] = d1 * zl - 2.f * y * d1 * ssq;
+            float4 zl = *reinterpret_cast<const float4 *>(zp + (long)(C - 1) * ld);
+            if (ap) { float4 a = *reinterpret_cast<const float4 *>(ap + (long)(C - 1) * width); zl.x += a.x; zl.y += a.y; zl.z += a.z; zl.w += a.w; }
+            *reinterpret_cast<float4 *>(zp + (long)(C - 1) * ld) =
+                make_float4(d1.x * zl.x - 2.f * y.x * d1.x * ssq.x, d1.y * zl.y - 2.f * y.y * d1.y * ssq.y,
+                            d1.z * zl.z - 2.f * y.z * d1.z * ssq.z, d1.w * zl.w - 2.f * y.w * d1.w * ssq.w);
         }
     }
 }
 
 int launch_act(dpe_model *m, float *z, int ld, int n_groups, int C, int width, const float *bias, const float *add,
                int groups_per_add, cudaStream_t s) {
-    long total = (long)n_groups * width;
+    if ((width & 3) || (ld & 3)) return set_error(DPE_ERR_UNSUPPORTED, "act: width=%d / ld=%d must be multiples of 4", width, ld);
+    long total = (long)n_groups * (width >> 2);
     long blocks = (total + 255) / 256;
-    if (blocks > 148L * 16) blocks = 148L * 16;
+    if (blocks > 148L * 32) blocks = 148L * 32;
     k_act<<<(int)blocks, 256, 0, s>>>(z, ld, n_groups, C, width, bias, add, groups_per_add);
     DPE_LAUNCH_CHECK(m);
     return DPE_OK;
@@ -374,25 +462,49 @@ int launch_act(dpe_model *m, float *z, int ld, int n_groups, int C, int width, c
 // ------------------------------------------------------------------------------------------------
 // spin means (ferminet_embedding.py:60-72): mean[b][c][0:d] = mean_{i<U} h, [d:2d] = mean_{i>=U} h
 // ------------------------------------------------------------------------------------------------
-__global__ void k_mean(const float *__restrict__ x, int ldx, int Bc, int N, int U, int C, int d_in, float *__restrict__ mean) {
-    const long total = (long)Bc * C * 2 * d_in;
+__global__ void __launch_bounds__(256) k_mean(const float *__restrict__ x, int ldx, int Bc, int N, int U, int C, int d_in,
+                                               float *__restrict__ mean) {
+    const int d4 = d_in >> 2;
+    const long total = (long)Bc * C * d4;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        int f2 = idx % (2 * d_in);
-        long bc = idx / (2 * d_in);
-        int c = bc % C;
-        long b = bc / C;
-        int spin = f2 >= d_in, f = f2 - spin * d_in;
-        int i0 = spin ? U : 0, i1 = spin ? N : U;
-        float acc = 0.f;
-        for (int i = i0; i < i1; ++i) acc += x[((b * N + i) * C + c) * ldx + f];
-        mean[idx] = acc / (float)(i1 - i0);
+        const int f = (int)(idx % d4) << 2;
+        const long bc = idx / d4;
+        const int c = (int)(bc % C);
+        const long b = bc / C;
+        const float *xp = x + ((b * N) * C + c) * (long)ldx + f;
+        const long stride = (long)C * ldx;
+        float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = up;
+        int i = 0;
+        for (; i + 4 <= U; i += 4) {
+            float4 a0 = *reinterpret_cast<const float4 *>(xp + (i + 0) * stride), a1 = *reinterpret_cast<const float4 *>(xp + (i + 1) * stride);
+            float4 a2 = *reinterpret_cast<const float4 *>(xp + (i + 2) * stride), a3 = *reinterpret_cast<const float4 *>(xp + (i + 3) * stride);
+            up.x += a0.x; up.y += a0.y; up.z += a0.z; up.w += a0.w;
+            up.x += a1.x; up.y += a1.y; up.z += a1.z; up.w += a1.w;
+            up.x += a2.x; up.y += a2.y; up.z += a2.z; up.w += a2.w;
+            up.x += a3.x; up.y += a3.y; up.z += a3.z; up.w += a3.w;
+        }
+        for (; i < U; ++i) { float4 a = *reinterpret_cast<const float4 *>(xp + i * stride); up.x += a.x; up.y += a.y; up.z += a.z; up.w += a.w; }
+        for (; i + 4 <= N; i += 4) {
+            float4 a0 = *reinterpret_cast<const float4 *>(xp + (i + 0) * stride), a1 = *reinterpret_cast<const float4 *>(xp + (i + 1) * stride);
+            float4 a2 = *reinterpret_cast<const float4 *>(xp + (i + 2) * stride), a3 = *reinterpret_cast<const float4 *>(xp + (i + 3) * stride);
+            dn.x += a0.x; dn.y += a0.y; dn.z += a0.z; dn.w += a0.w;
+            dn.x += a1.x; dn.y += a1.y; dn.z += a1.z; dn.w += a1.w;
+            dn.x += a2.x; dn.y += a2.y; dn.z += a2.z; dn.w += a2.w;
+            dn.x += a3.x; dn.y += a3.y; dn.z += a3.z; dn.w += a3.w;
+        }
+        for (; i < N; ++i) { float4 a = *reinterpret_cast<const float4 *>(xp + i * stride); dn.x += a.x; dn.y += a.y; dn.z += a.z; dn.w += a.w; }
+        const float nu = (float)U, nd = (float)(N - U);
+        float *mp = mean + bc * 2 * d_in + f;
+        *reinterpret_cast<float4 *>(mp) = make_float4(up.x / nu, up.y / nu, up.z / nu, up.w / nu);
+        *reinterpret_cast<float4 *>(mp + d_in) = make_float4(dn.x / nd, dn.y / nd, dn.z / nd, dn.w / nd);
     }
 }
 
 int launch_mean(dpe_model *m, const float *x, int ldx, int Bc, int C, int d_in, float *mean, cudaStream_t s) {
-    long total = (long)Bc * C * 2 * d_in;
+    if (d_in & 3) return set_error(DPE_ERR_UNSUPPORTED, "mean: d_in=%d must be a multiple of 4", d_in);
+    long total = (long)Bc * C * (d_in >> 2);
     long blocks = (total + 255) / 256;
-    if (blocks > 148L * 16) blocks = 148L * 16;
+    if (blocks > 148L * 32) blocks = 148L * 32;
     k_mean<<<(int)blocks, 256, 0, s>>>(x, ldx, Bc, m->dims.n_el, m->dims.n_up, C, d_in, mean);
     DPE_LAUNCH_CHECK(m);
     return DPE_OK;
@@ -404,16 +516,17 @@ int launch_mean(dpe_model *m, const float *x, int ldx, int Bc, int C, int d_in, 
 // Laplacian mode: one block per (walker, slab of CS channels); thread = (channel, feature). The channel slab of
 // hm for all electrons stays in shared memory; the pair weights of one electron i are staged per iteration.
 // ------------------------------------------------------------------------------------------------
-template <int CS>
-__global__ void __launch_bounds__(CS * 32) k_conv_lap(const float *__restrict__ r, int N, int C, int emb, int dE,
+template <int CS, int EMB>   // EMB > 0: compile-time embedding width (index math folds to shifts); 0: runtime
+__global__ void __launch_bounds__(CS * 32) k_conv_lap(const float *__restrict__ r, int N, int C, int emb_rt, int dE,
                                                        const float *__restrict__ hm, const float *__restrict__ pw,
                                                        const float *__restrict__ ei, float *__restrict__ x, int ldx, int col_ee) {
-    extern __shared__ float sm[];
-    float *r_s = sm;                         // [N][3]
-    float *hm0_s = r_s + 3 * N;              // [N][emb]      value channel of hm
+    extern __shared__ __align__(16) float sm[];
+    const int emb = EMB > 0 ? EMB : emb_rt;
+    float *hm0_s = sm;                       // [N][emb]      value channel of hm
     float *hmd_s = hm0_s + N * emb;          // [N][3][emb]   d hm_j / d r_j
     float *hm_s = hmd_s + 3 * N * emb;       // [N][CS][emb]  this block's channel slab
     float *w_s = hm_s + N * CS * emb;        // [N][3][emb]   w, w', w'' of pairs (i, :)
+    float *r_s = w_s + 3 * N * emb;          // [N][3]
     const int n_slabs = (C + CS - 1) / CS;
     const long b = blockIdx.x / n_slabs;
     const int slab = blockIdx.x - (int)(b * n_slabs);
@@ -442,7 +555,8 @@ __global__ void __launch_bounds__(CS * 32) k_conv_lap(const float *__restrict__ 
     for (int i = 0; i < N; ++i) {
         __syncthreads();
         const float *pwi = pw + (b * N + i) * (long)wrow;     // [j][ch][f], contiguous
-        for (int t = threadIdx.x; t < wrow; t += blockDim.x) w_s[t] = pwi[t];
+        for (int t = threadIdx.x; t < (wrow >> 2); t += blockDim.x)
+            reinterpret_cast<float4 *>(w_s)[t] = reinterpret_cast<const float4 *>(pwi)[t];
         __syncthreads();
         float *xrow = x + ((b * N + i) * (long)C + c) * ldx + col_ee;
         if (act) {
@@ -520,9 +634,14 @@ int launch_conv(dpe_model *m, int it, const float *r, int Bc, int C, const float
     } else {
         constexpr int CS = 8;
         size_t smem = ((size_t)3 * N + (size_t)N * emb * (1 + 3 + CS + 3)) * sizeof(float);
-        if (smem > 48 * 1024) DPE_CUDA(cudaFuncSetAttribute(k_conv_lap<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n_slabs = (C + CS - 1) / CS;
-        k_conv_lap<CS><<<Bc * n_slabs, CS * 32, smem, s>>>(r, N, C, emb, p.dE, hm, pw, ei, x, ldx, p.d_in);
+        if (emb == 32) {
+            if (smem > 48 * 1024) DPE_CUDA(cudaFuncSetAttribute(k_conv_lap<CS, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_conv_lap<CS, 32><<<Bc * n_slabs, CS * 32, smem, s>>>(r, N, C, emb, p.dE, hm, pw, ei, x, ldx, p.d_in);
+        } else {
+            if (smem > 48 * 1024) DPE_CUDA(cudaFuncSetAttribute(k_conv_lap<CS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_conv_lap<CS, 0><<<Bc * n_slabs, CS * 32, smem, s>>>(r, N, C, emb, p.dE, hm, pw, ei, x, ldx, p.d_in);
+        }
     }
     DPE_LAUNCH_CHECK(m);
     return DPE_OK;
