@@ -2,6 +2,7 @@
 // Laplacian contraction) and the signed log-sum-exp that ends in log psi^2 and E_loc.
 // Reference: model/orbitals/envelope_orbitals.py:39-127, model/wavefunction.py:63-83,
 // hamiltonian.py:206-216 (forward-Laplacian kinetic energy), :34-39 (potential).
+#include <cstdlib>
 #include "dpe_internal.cuh"
 
 namespace dpe {
@@ -83,6 +84,20 @@ int launch_envelope(dpe_model *m, const float *r, int Bc, int C, float *mo, cuda
 //   Laplacian:  A^-1, g_k = tr(A^-1 dA_k), lap = tr(A^-1 lapA) - sum_k tr((A^-1 dA_k)^2)
 // det record: [logdet, sign, lap, g_0 .. g_{K-1}]
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_d(double v);
+
+template <int T>
+__device__ __forceinline__ double group_sum_d(double v, double *red, int tid) {
+    v = warp_sum_d(v);
+    if (T == 32) return v;
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < T / 32; ++w) s += red[w];
+    return s;
+}
+
 template <int T>
 __device__ __forceinline__ void group_sync() {
     if (T == 32) __syncwarp(); else __syncthreads();
@@ -112,7 +127,8 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
     float *Ainv = reinterpret_cast<float *>(aug + N * S);   // [N][N+1]  (LAP only) Ainv[o][i]
     float *dA = Ainv + (LAP ? N * (N + 1) : 0);             // [N][N+1]
     float *P = dA + (LAP ? N * (N + 1) : 0);                // [N][N+1]
-    float *red = P + (LAP ? N * (N + 1) : 0);               // [T/32 + 2]
+    float *red = P + (LAP ? N * (N + 1) : 0);               // [T/32 + 2] floats, then 8 doubles
+    double *redd = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(red + 8) + 7) & ~uintptr_t(7));
     __shared__ int piv_row;
     const int tid = threadIdx.x;
     const long bd = blockIdx.x;
@@ -188,14 +204,14 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
         Ainv[o * (N + 1) + i] = (float)aug[o * S + N + i];
     }
     group_sync<T>();
-    // Laplacian term tr(Ainv lapA)
-    float part = 0.f;
+    // Laplacian term tr(Ainv lapA); record = lap' = tr(Ainv lapA) - sum_k tr(P_k^2) + sum_k tr(P_k)^2 (FP64 sums, see k_det_warp)
+    double part = 0.0;
     for (int e = tid; e < N * N; e += T) {
         int i = e / N, o = e - i * N;
-        part = fmaf(Ainv[o * (N + 1) + i], mob[((long)i * C + C - 1) * cols + o], part);
+        part = fma((double)Ainv[o * (N + 1) + i], (double)mob[((long)i * C + C - 1) * cols + o], part);
     }
-    float lap = group_sum<T>(part, red, tid);
-    float tr2_total = 0.f;
+    const double lap = group_sum_d<T>(part, redd, tid);
+    double tr2_total = 0.0, sum_g2 = 0.0;
     // P = Ainv dA_k in strips: one strip = row o, TQ consecutive columns (TQ+1 shared loads per TQ FMAs).
     // Element -> (row, column) maps are hoisted out of the k loop (runtime N: integer divisions are expensive).
     constexpr int TQ = 8;
@@ -226,7 +242,7 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
             }
         }
         group_sync<T>();
-        float gk = 0.f;
+        double gkd = 0.0;
         for (int sidx = tid; sidx < n_strips; sidx += T) {
             const int o = sidx / n_qc, q0 = (sidx - o * n_qc) * TQ;
             float acc[TQ];
@@ -244,28 +260,26 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
             for (int t = 0; t < TQ; ++t)
                 if (q0 + t < N) {
                     P[o * (N + 1) + q0 + t] = acc[t];
-                    if (q0 + t == o) gk += acc[t];
+                    if (q0 + t == o) gkd += (double)acc[t];
                 }
         }
         group_sync<T>();
-        float t2 = 0.f;
         if (cached) {
 #pragma unroll
             for (int sl = 0; sl < ME; ++sl)
-                if (src_off[sl] >= 0) t2 = fmaf(P[dst_off[sl]], P[tr_off[sl]], t2);
+                if (src_off[sl] >= 0) tr2_total = fma((double)P[dst_off[sl]], (double)P[tr_off[sl]], tr2_total);
         } else {
             for (int e = tid; e < N * N; e += T) {
                 int o = e / N, q = e - o * N;
-                t2 = fmaf(P[o * (N + 1) + q], P[q * (N + 1) + o], t2);
+                tr2_total = fma((double)P[o * (N + 1) + q], (double)P[q * (N + 1) + o], tr2_total);
             }
         }
-        // one reduction for both sums: pack (gk, t2) through the shuffle tree
-        gk = group_sum<T>(gk, red, tid);
-        t2 = group_sum<T>(t2, red, tid);
-        tr2_total += t2;
+        const float gk = (float)group_sum_d<T>(gkd, redd, tid);
+        sum_g2 = fma((double)gk, (double)gk, sum_g2);
         if (tid == 0) out[3 + k] = gk;
     }
-    if (tid == 0) out[2] = lap - tr2_total;
+    tr2_total = group_sum_d<T>(tr2_total, redd, tid);
+    if (tid == 0) out[2] = (float)(lap + (sum_g2 - tr2_total));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -274,6 +288,10 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
 // tangent stage in 8-column strips with zero-padded 16-float rows (2 x LDS.128 per 8 FMAs).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
@@ -361,17 +379,20 @@ __global__ void __launch_bounds__(128, 5) k_det_warp(int N, int C, int n_det, lo
         t17[sl] = o * 17 + i;
     }
     __syncwarp();
-    float part = 0.f;
+    // The record holds lap' = tr(Ainv lapA) - sum_k tr(P_k^2) + sum_k tr(P_k)^2: for an ill-conditioned matrix P_k is
+    // nearly rank one, tr(P_k^2) ~ tr(P_k)^2, and the two sums cancel to many digits -- they are accumulated in FP64
+    // from the same FP32 P entries so that the cancellation is exact with respect to those entries.
+    double part = 0.0;
 #pragma unroll
     for (int sl = 0; sl < 8; ++sl)
         if (src_off[sl] >= 0) {
             int e = lane + 32 * sl, i = e / N, o = e - i * N;
-            part = fmaf(Ainv[o * (N + 1) + i], mob[(long)(C - 1) * cols + src_off[sl]], part);
+            part = fma((double)Ainv[o * (N + 1) + i], (double)mob[(long)(C - 1) * cols + src_off[sl]], part);
         }
-    const float lap = warp_sum(part);
+    const double lap = warp_sum_d(part);
     const int orow = lane >> 1, q0 = (lane & 1) * 8;
     const bool strip = orow < N;
-    float t2 = 0.f;
+    double t2 = 0.0, sum_g2 = 0.0;
     for (int k = 0; k < K; ++k) {
         const float *mk = mob + (long)(1 + k) * cols;
         float ld[8];
@@ -382,7 +403,7 @@ __global__ void __launch_bounds__(128, 5) k_det_warp(int N, int C, int n_det, lo
         for (int sl = 0; sl < 8; ++sl)
             if (src_off[sl] >= 0) dA[d16[sl]] = ld[sl];
         __syncwarp();
-        float gk = 0.f;
+        double gkd = 0.0;
         if (strip) {
             float acc[8];
 #pragma unroll
@@ -398,31 +419,36 @@ __global__ void __launch_bounds__(128, 5) k_det_warp(int N, int C, int n_det, lo
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 P[orow * 17 + q0 + t] = acc[t];
-                if (q0 + t == orow) gk = acc[t];
+                if (q0 + t == orow) gkd = (double)acc[t];
             }
         }
-        gk = warp_sum(gk);
+        const float gk = (float)warp_sum_d(gkd);
+        sum_g2 = fma((double)gk, (double)gk, sum_g2);       // with the rounded value that the record stores
         if (lane == 0) out[3 + k] = gk;
         __syncwarp();
 #pragma unroll
         for (int sl = 0; sl < 8; ++sl)
-            if (src_off[sl] >= 0) t2 = fmaf(P[p17[sl]], P[t17[sl]], t2);
+            if (src_off[sl] >= 0) t2 = fma((double)P[p17[sl]], (double)P[t17[sl]], t2);
     }
-    t2 = warp_sum(t2);
-    if (lane == 0) out[2] = lap - t2;
+    t2 = warp_sum_d(t2);
+    if (lane == 0) out[2] = (float)(lap + (sum_g2 - t2));
 }
 
 int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStream_t s) {
     const dpe_dims &d = m->dims;
     const int N = d.n_el;
     const bool lap = C > 1;
-    size_t smem = (size_t)N * ((lap ? 2 * N : N) + 1) * sizeof(double) + ((lap ? 3 * (size_t)N * (N + 1) : 0) + 16) * sizeof(float);
+    size_t smem = (size_t)N * ((lap ? 2 * N : N) + 1) * sizeof(double) + ((lap ? 3 * (size_t)N * (N + 1) : 0) + 16) * sizeof(float) + 10 * sizeof(double);
     int blocks = Bc * d.n_dets;
-    if (N <= 16) {
+    static const bool force_generic = getenv("DPE_DET_GENERIC") != nullptr;   // debug knob
+    if (N <= 16 && !force_generic) {
         const size_t per_warp = ((size_t)N * 32 + (lap ? ((size_t)N * (N + 1) + N * 16 + N * 17 + 1) / 2 + 2 : 0)) * sizeof(double);
         const long n_mat = (long)blocks;
         if (lap) k_det_warp<true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det);
         else k_det_warp<false><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det);
+    } else if (N <= 16) {
+        if (lap) k_det<32, true><<<blocks, 32, smem, s>>>(N, C, d.n_dets, mo, det);
+        else k_det<32, false><<<blocks, 32, smem, s>>>(N, C, d.n_dets, mo, det);
     } else {
         if (smem > 48 * 1024) {
             DPE_CUDA(cudaFuncSetAttribute(k_det<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -470,43 +496,39 @@ __global__ void __launch_bounds__(128) k_combine(int Bc, int n_det, int K, bool 
         if (phase) phase[b] = psi < 0.f ? 3.14159265358979323846f : 0.f;
     }
     if (!lap_mode) return;
-    const float inv_psi = 1.f / psi;
-    const float rho = apsi / (apsi + 1e-8f);
-    // sum_d w_d lap_d
-    float wl = 0.f;
+    // The determinant record holds lap'_d = lap_d + sum_k g_dk^2; the sums over k and d below cancel to many digits when
+    // one determinant dominates, so they run in FP64 on the FP32 records.
+    const double inv_psi = 1.0 / (double)psi;
+    const double rho = (double)apsi / ((double)apsi + 1e-8);
+    double wl = 0.0;
     for (int d = lane; d < n_det; d += 32) {
-        float w = db[(long)d * rec + 1] * expf(db[(long)d * rec] - shift) * inv_psi;
-        wl = fmaf(w, db[(long)d * rec + 2], wl);
+        double w = (double)(db[(long)d * rec + 1] * expf(db[(long)d * rec] - shift)) * inv_psi;
+        wl = fma(w, (double)db[(long)d * rec + 2], wl);
     }
-    for (int o = 16; o; o >>= 1) wl += __shfl_xor_sync(0xffffffffu, wl, o);
-    const float l_m = db[(long)md * rec + 2];
-    float sum_gkk = 0.f, sum_dev2 = 0.f, sum_f2 = 0.f;
+    wl = warp_sum_d(wl);
+    double sum_G2 = 0.0, sum_dev2 = 0.0, sum_f2 = 0.0, sum_gm2 = 0.0;
     for (int k = lane; k < K; k += 32) {
-        float G = 0.f, S2 = 0.f;
+        double G = 0.0;
         for (int d = 0; d < n_det; ++d) {
-            float w = db[(long)d * rec + 1] * expf(db[(long)d * rec] - shift) * inv_psi;
-            float g = db[(long)d * rec + 3 + k];
-            G = fmaf(w, g, G);
-            S2 = fmaf(w * g, g, S2);
+            double w = (double)(db[(long)d * rec + 1] * expf(db[(long)d * rec] - shift)) * inv_psi;
+            G = fma(w, (double)db[(long)d * rec + 3 + k], G);
         }
-        float gm = db[(long)md * rec + 3 + k];
-        float Fk = rho * (G - gm) + gm;
-        sum_gkk += S2 - G * G;
-        sum_dev2 += (G - gm) * (G - gm);
-        float gr = 2.f * Fk;
-        sum_f2 = fmaf(gr, gr, sum_f2);
+        const double gm = (double)db[(long)md * rec + 3 + k];
+        const double Fk = rho * (G - gm) + gm;
+        sum_G2 = fma(G, G, sum_G2);
+        sum_gm2 = fma(gm, gm, sum_gm2);
+        sum_dev2 = fma(G - gm, G - gm, sum_dev2);
+        const float gr = (float)(2.0 * Fk);
+        sum_f2 = fma((double)gr, (double)gr, sum_f2);
         if (grad) grad[(long)b * K + k] = gr;
     }
-    for (int o = 16; o; o >>= 1) {
-        sum_gkk += __shfl_xor_sync(0xffffffffu, sum_gkk, o);
-        sum_dev2 += __shfl_xor_sync(0xffffffffu, sum_dev2, o);
-        sum_f2 += __shfl_xor_sync(0xffffffffu, sum_f2, o);
-    }
+    sum_G2 = warp_sum_d(sum_G2); sum_gm2 = warp_sum_d(sum_gm2); sum_dev2 = warp_sum_d(sum_dev2); sum_f2 = warp_sum_d(sum_f2);
     if (lane == 0) {
-        float Gkk = sum_gkk + wl;
-        float F_lap = rho * (1.f - rho) * sum_dev2 + rho * (Gkk - l_m) + l_m;
-        float lapL = 2.f * F_lap;
-        float ek = -0.5f * (0.5f * lapL + 0.25f * sum_f2);
+        const double Gkk = wl - sum_G2;                                  // sum_k d_kk log|psi| without the epsilon
+        const double l_m = (double)db[(long)md * rec + 2] - sum_gm2;      // Laplacian of the arg-max determinant alone
+        const double F_lap = rho * (1.0 - rho) * sum_dev2 + rho * (Gkk - l_m) + l_m;
+        const double lapL = 2.0 * F_lap;
+        const float ek = (float)(-0.5 * (0.5 * lapL + 0.25 * sum_f2));
         if (ekin) ekin[b] = ek;
         if (epot_out) epot_out[b] = epot[b];
         if (eloc) eloc[b] = ek + epot[b];

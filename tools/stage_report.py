@@ -85,9 +85,14 @@ def main():
           f"lap {rel(mo[:, :, C - 1], inter['mo'][:, :, C - 1]):.2e}")
     det = eng.ws_view("det", B, MODE_LAPLACIAN, (B, d.n_dets, K + 3))
     print(f"  det: logdet {rel(det[..., 0], ref['logdet_d']):.2e} sign_eq {bool((det[..., 1].cpu().double() == ref['sign_d']).all())} "
-          f"lap_d {rel(det[..., 2], inter['lap_d']):.2e} g_d {rel(det[..., 3:], inter['g_d']):.2e}")
+          f"lap'_d {rel(det[..., 2], inter['lap_d'] + (inter['g_d'] ** 2).sum(-1)):.2e} g_d {rel(det[..., 3:], inter['g_d']):.2e}")
     print(f"  logpsi2 {rel(aux['log_psi_sqr'], ref['logpsi2']):.2e}  grad {rel(aux['grad'], ref['grad']):.2e}  "
           f"E_kin {rel(aux['E_kin'], ref['E_kin']):.2e}  E_pot {rel(aux['E_pot'], ref['E_pot']):.2e}")
+    print("  per-walker E_kin rel err", ((aux["E_kin"].double().cpu() - ref["E_kin"]).abs() / ref["E_kin"].abs()).tolist())
+    dd = det.double().cpu()
+    lp_ref = inter["lap_d"] + (inter["g_d"] ** 2).sum(-1)
+    print("  lap'_d per-element rel err max", ((dd[..., 2] - lp_ref).abs() / lp_ref.abs()).max().item(),
+          " g_d per-det rel err max", ((dd[..., 3:] - inter["g_d"]).abs().amax(-1) / inter["g_d"].abs().amax(-1)).max().item())
     err = ((e_loc.double().cpu() - ref["E_loc"]).abs() / ref["E_loc"].abs()).max().item()
     print(f"  E_loc max rel err {err:.2e}   (E_loc ref {ref['E_loc'][:3].tolist()})")
     ph, lp = eng.log_psi_sqr(r32.cuda())
