@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(256) k_envelope(const float *__restrict__ r, c
             float dx = ri[0] - R[J * 3], dy = ri[1] - R[J * 3 + 1], dz = ri[2] - R[J * 3 + 2];
             float d = sqrtf(dx * dx + dy * dy + dz * dz);
             float a = spa[(long)J * cols + col];
-            float e = wt[(long)J * cols + col] * expf(-a * d);
-            env += e;
+            float e = __fmul_rn(wt[(long)J * cols + col], expf(-a * d));   // no FMA contraction: same bits in both modes
+            env = __fadd_rn(env, e);
             if (C > 1) {
                 float inv = 1.f / d;
                 float g = -a * e * inv;
