@@ -36,7 +36,7 @@ static int validate_dims(const dpe_dims &d) {
     if (d.n_up < 1 || d.n_up >= d.n_el) return set_error(DPE_ERR_UNSUPPORTED, "need at least one electron of each spin (n_up=%d)", d.n_up);
     if (d.n_ion < 1 || d.n_ion > 256) return set_error(DPE_ERR_UNSUPPORTED, "n_ion=%d outside [1, 256]", d.n_ion);
     if (d.n_iterations < 1 || d.n_iterations > DPE_MAX_ITER) return set_error(DPE_ERR_UNSUPPORTED, "n_iterations=%d", d.n_iterations);
-    if (d.emb_dim < 4 || d.emb_dim > 32 || (d.emb_dim & 3)) return set_error(DPE_ERR_UNSUPPORTED, "emb_dim=%d must be a multiple of 4 in [4, 32]", d.emb_dim);
+    if (d.emb_dim < 8 || d.emb_dim > 32 || (d.emb_dim & 7)) return set_error(DPE_ERR_UNSUPPORTED, "emb_dim=%d must be a multiple of 8 in [8, 32]", d.emb_dim);
     if (d.n_ion_features < 1 || d.n_dets < 1) return set_error(DPE_ERR_UNSUPPORTED, "n_ion_features / n_dets must be positive");
     if (d.z_max < d.z_min) return set_error(DPE_ERR_ARG, "z_max < z_min");
     for (int it = 0; it < d.n_iterations; ++it) {
@@ -181,21 +181,23 @@ static int max_chunk(const dpe_dims &d, int C, size_t avail, int B) {
 }
 
 // ---- kernel sequences -------------------------------------------------------------------------------
-static int gemm_dispatch(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
+// *fused is set when the kernel that ran applied the requested fused epilogue
+static int gemm_dispatch(dpe_model *m, const GemmArgs &g, cudaStream_t s, bool *fused) {
+    if (fused) *fused = false;
     if (m->gemm_path == 1) {
         int e = launch_gemm_tc(m, g, s);
-        if (e != DPE_ERR_UNSUPPORTED) return e;
+        if (e != DPE_ERR_UNSUPPORTED) { if (fused) *fused = g.epi != 0; return e; }
     }
     return launch_gemm_simt(m, g, s);
 }
 
-static int gemm(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
-    if (!m->profile) return gemm_dispatch(m, g, s);
+static int gemm(dpe_model *m, const GemmArgs &g, cudaStream_t s, bool *fused = nullptr) {
+    if (!m->profile) return gemm_dispatch(m, g, s, fused);
     dpe_model::ProfRec rec;
     DPE_CUDA(cudaEventCreate(&rec.e0));
     DPE_CUDA(cudaEventCreate(&rec.e1));
     DPE_CUDA(cudaEventRecord(rec.e0, s));
-    int e = gemm_dispatch(m, g, s);
+    int e = gemm_dispatch(m, g, s, fused);
     DPE_CUDA(cudaEventRecord(rec.e1, s));
     rec.klass = m->last_gemm_class;
     rec.flops = 2.0 * (double)g.M * (double)g.N * (double)g.K;
@@ -252,14 +254,19 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
     }
     // backflow factors (envelope_orbitals.py:46-75): spin-up / spin-down electrons use different matrices
     const int cols = d.n_dets * N, dl = d.n_hidden_one_el[d.n_iterations - 1];
+    bool env_fused = true;
     for (int sp = 0; sp < 2; ++sp) {
         GemmArgs g = plain_gemm(x[cur], ldx, m->bf_w[sp], cols, mo, cols, Bc * (sp ? D : U) * C, cols, dl);
         g.a_seg_len = g.c_seg_len = (sp ? D : U) * C;
         g.a_seg_stride = g.c_seg_stride = N * C;
         g.a_seg_off = g.c_seg_off = sp ? U * C : 0;
-        if ((e = gemm(m, g, s))) return e;
+        g.epi = 2; g.n_ch = C; g.r = r; g.R = m->R_dev; g.spa = m->sp_alpha[sp]; g.envw = m->env_w[sp];
+        g.n_el = N; g.n_ion = d.n_ion; g.el_base = sp ? U : 0;
+        bool fused = false;
+        if ((e = gemm(m, g, s, &fused))) return e;
+        env_fused = env_fused && fused;
     }
-    if ((e = launch_envelope(m, r, Bc, C, mo, s))) return e;
+    if (!env_fused && (e = launch_envelope(m, r, Bc, C, mo, s))) return e;
     if ((e = launch_det(m, Bc, C, mo, det, s))) return e;
     if ((e = launch_combine(m, Bc, C, det, epot, phase, logpsi2, grad, ekin, eloc, epot_out, s))) return e;
     return DPE_OK;

@@ -32,6 +32,10 @@ struct GemmArgs {
     float *C; int ldc;
     int c_seg_len, c_seg_stride, c_seg_off, c_col_off;
     int M, N, K;
+    // optional fused epilogue (tensor-core path only; the SIMT path ignores it and the caller runs the separate kernel)
+    int epi = 0, n_ch = 1;
+    const float *r = nullptr, *R = nullptr, *spa = nullptr, *envw = nullptr;
+    int n_el = 0, n_ion = 0, el_base = 0;
 };
 
 // Workspace layout for one chunk of Bc walkers with C channels (byte offsets).

@@ -42,8 +42,13 @@ struct TcArgs {
     int ldc, c_seg_stride, c_seg_off, c_col_off;   // row of segment s, local row m -> s * c_seg_stride + c_seg_off + m
     int n_seg, seg_len;                            // rows per segment
     int N_out, K;
-    int nmma;                                      // rows per tile (multiple of 16, <= 256)
+    int nmma;                                      // MMA N = TMA box rows (multiple of 16, <= 256)
+    int tile_rows;                                 // rows a tile owns (<= nmma; a multiple of the channel count when epi != 0)
     int n_rt, n_ft;                                // row tiles per segment, feature tiles
+    // fused epilogue. 0: plain store. 2: envelope multiply of the backflow GEMM (envelope_orbitals.py:96-127) with the product rule
+    int epi, C;                                    // channels per (walker, electron) group
+    const float *r, *R, *spa, *envw;               // walker positions [n_seg, n_el, 3], ions [I,3], softplus(alpha) / weights [I, N_out]
+    int n_el, n_ion, el_base;                      // electron index of local group 0 of a segment (0 for spin-up, n_up for spin-down)
 };
 
 // ---------------------------------------------------------------------------------------- PTX wrappers
@@ -164,7 +169,7 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     mbar_expect_tx(&bar_full[stage], tx);
                     tma_load_2d(st, &map_wh, &bar_full[stage], kb * TC_BK, ft * TC_FEAT);
                     tma_load_2d(st + TC_W_BYTES, &map_wl, &bar_full[stage], kb * TC_BK, ft * TC_FEAT);
-                    tma_load_3d(st + 2 * TC_W_BYTES, &map_x, &bar_full[stage], kb * TC_BK, rt * a.nmma, seg);
+                    tma_load_3d(st + 2 * TC_W_BYTES, &map_x, &bar_full[stage], kb * TC_BK, rt * a.tile_rows, seg);
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -235,9 +240,14 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const long rest = t / a.n_ft;
             const int rt = (int)(rest % a.n_rt), seg = (int)(rest / a.n_rt);
             const int f = ft * TC_FEAT + h * 128 + q * 32 + lane;
-            const int m0 = rt * a.nmma;
-            const int rows_valid = min(a.nmma, a.seg_len - m0);
+            const int m0 = rt * a.tile_rows;
+            const int rows_valid = min(a.tile_rows, a.seg_len - m0);
             float *cbase = a.C + ((long)seg * a.c_seg_stride + a.c_seg_off + m0) * a.ldc + a.c_col_off + f;
+            const bool f_ok = f < a.N_out;
+            // envelope state (epi == 2): group = (walker seg, electron el_base + (m0 + col) / C), channel cch
+            int cch = 0, grp = a.epi == 2 ? m0 / a.C : 0;
+            float env = 1.f, e1x = 0.f, e1y = 0.f, e1z = 0.f, el = 0.f, bf0 = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
+            int ci = 0;
             mbar_wait(bar_tfull, tphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * 256;
@@ -249,10 +259,50 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     tc_fence_before();
                     mbar_arrive(bar_tempty);
                 }
-                if (f < a.N_out) {
+                if (a.epi == 0) {
+                    if (f_ok) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < rows_valid) cbase[(long)(c0 + j) * a.ldc] = __uint_as_float(v[j]);
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < rows_valid) cbase[(long)(c0 + j) * a.ldc] = __uint_as_float(v[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (c0 + j < rows_valid) {
+                            const float val = __uint_as_float(v[j]);
+                            if (cch == 0) {
+                                const int i = a.el_base + grp;
+                                ci = 1 + 3 * i;
+                                bf0 = val;
+                                env = 0.f; e1x = e1y = e1z = el = 0.f;
+                                if (f_ok) {
+                                    const float *ri = a.r + ((long)seg * a.n_el + i) * 3;
+                                    const float rx = ri[0], ry = ri[1], rz = ri[2];
+                                    for (int J = 0; J < a.n_ion; ++J) {
+                                        const float dx = rx - a.R[J * 3], dy = ry - a.R[J * 3 + 1], dz = rz - a.R[J * 3 + 2];
+                                        const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                                        const float al = a.spa[(long)J * a.N_out + f];
+                                        const float e = __fmul_rn(a.envw[(long)J * a.N_out + f], expf(-al * d));
+                                        env = __fadd_rn(env, e);
+                                        if (a.C > 1) {
+                                            const float inv = 1.f / d, g = -al * e * inv;
+                                            e1x = fmaf(g, dx, e1x); e1y = fmaf(g, dy, e1y); e1z = fmaf(g, dz, e1z);
+                                            el = fmaf(e, al * al - 2.f * al * inv, el);
+                                        }
+                                    }
+                                }
+                            }
+                            float o = val * env;
+                            if (a.C > 1) {
+                                if (cch == ci) { tx = val; o += e1x * bf0; }
+                                else if (cch == ci + 1) { ty = val; o += e1y * bf0; }
+                                else if (cch == ci + 2) { tz = val; o += e1z * bf0; }
+                                else if (cch == a.C - 1) o += el * bf0 + 2.f * (e1x * tx + e1y * ty + e1z * tz);
+                            }
+                            if (f_ok) cbase[(long)(c0 + j) * a.ldc] = o;
+                            if (++cch == a.C) { cch = 0; ++grp; }
+                        }
+                    }
                 }
             }
             tphase ^= 1;
@@ -373,10 +423,23 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     TcArgs a;
     a.C = g.C; a.ldc = g.ldc; a.c_seg_stride = n_seg > 1 ? g.c_seg_stride : 0; a.c_seg_off = g.c_seg_off; a.c_col_off = g.c_col_off;
     a.n_seg = n_seg; a.seg_len = seg_len; a.N_out = g.N; a.K = g.K;
-    const int tiles_min = (seg_len + 255) / 256;
-    a.nmma = (((seg_len + tiles_min - 1) / tiles_min) + 15) / 16 * 16;
-    if (a.nmma > 256) a.nmma = 256;
-    a.n_rt = (seg_len + a.nmma - 1) / a.nmma;
+    a.epi = g.epi; a.C = g.epi ? g.n_ch : 1;
+    a.r = g.r; a.R = g.R; a.spa = g.spa; a.envw = g.envw; a.n_el = g.n_el; a.n_ion = g.n_ion; a.el_base = g.el_base;
+    if (a.epi) {
+        // group-aligned tiles: a tile owns whole (walker, electron) groups of C rows
+        if (a.C > 256 || seg_len % a.C) return DPE_ERR_UNSUPPORTED;
+        const int n_groups = seg_len / a.C, g_max = 256 / a.C;
+        const int n_rt = (n_groups + g_max - 1) / g_max, gpt = (n_groups + n_rt - 1) / n_rt;
+        a.tile_rows = gpt * a.C;
+        a.nmma = (a.tile_rows + 15) / 16 * 16;
+        a.n_rt = n_rt;
+    } else {
+        const int tiles_min = (seg_len + 255) / 256;
+        a.nmma = (((seg_len + tiles_min - 1) / tiles_min) + 15) / 16 * 16;
+        if (a.nmma > 256) a.nmma = 256;
+        a.tile_rows = a.nmma;
+        a.n_rt = (seg_len + a.nmma - 1) / a.nmma;
+    }
     a.n_ft = (g.N + TC_FEAT - 1) / TC_FEAT;
 
     CUtensorMap map_x;

@@ -117,18 +117,18 @@ __device__ __forceinline__ float group_sum(float v, float *red, int tid) {
 
 template <int T, bool LAP>
 __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float *__restrict__ mo, float *__restrict__ det) {
-    // The factorisation runs in FP64: the Slater matrices of a random-init network reach condition numbers
-    // of 1e5, where an FP32 LU alone costs 1e-3 relative in E_loc.  It is O(N^3) against the O(3N * N^3)
-    // FP32 tangent stage, so the extra cost is negligible.
+    // The factorisation runs in FP64 (O(N^3) against the O(3N * N^3) FP32 tangent stage).
     extern __shared__ double smd[];
     const int W = LAP ? 2 * N : N;       // augmented width
     const int S = W + 1;                 // padded row stride
-    double *aug = smd;                   // [N][S]
-    float *Ainv = reinterpret_cast<float *>(aug + N * S);   // [N][N+1]  (LAP only) Ainv[o][i]
-    float *dA = Ainv + (LAP ? N * (N + 1) : 0);             // [N][N+1]
-    float *P = dA + (LAP ? N * (N + 1) : 0);                // [N][N+1]
-    float *red = P + (LAP ? N * (N + 1) : 0);               // [T/32 + 2] floats, then 8 doubles
-    double *redd = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(red + 8) + 7) & ~uintptr_t(7));
+    const int NP2 = (N + 1) & ~1;        // rows of Ainv^T padded to an even count (float2 loads)
+    const int NQ = (N + 7) & ~7;         // tangent-matrix rows padded to 8 floats (float4 loads), zero filled
+    double *aug = smd;                   // [N][S]; after the sweep the same memory holds dA [N][NQ] and P [N][NQ]
+    float *AinvT = reinterpret_cast<float *>(aug + N * S);        // [N][NP2]  AinvT[i][o] = Ainv[o][i]
+    float *red = AinvT + (LAP ? N * NP2 : 0);                     // 8 floats
+    double *redd = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(red + 8) + 7) & ~uintptr_t(7));   // 8 doubles
+    float *dA = reinterpret_cast<float *>(aug);
+    float *P = dA + N * NQ;
     __shared__ int piv_row;
     const int tid = threadIdx.x;
     const long bd = blockIdx.x;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
         int i = e / W, o = e - i * W;
         aug[i * S + o] = o < N ? (double)mob[((long)i * C) * cols + o] : ((o - N == i) ? 1.0 : 0.0);
     }
-    group_sync<T>();
+    __syncthreads();
     double logdet = 0.0;
     float sign = 1.f;
     for (int p = 0; p < N; ++p) {
@@ -160,77 +160,73 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
             }
             if (tid == 0) piv_row = bi;
         }
-        group_sync<T>();
+        __syncthreads();
         const int pr = piv_row;
         if (pr != p) {
             for (int o = tid; o < W; o += T) {
                 double t = aug[p * S + o]; aug[p * S + o] = aug[pr * S + o]; aug[pr * S + o] = t;
             }
             sign = -sign;
-            group_sync<T>();
+            __syncthreads();
         }
         const double piv = aug[p * S + p];
         logdet += log(fabs(piv));
         if (piv < 0.0) sign = -sign;
         const double inv = 1.0 / piv;
-        group_sync<T>();
+        __syncthreads();
         if (LAP) {
-            // Gauss-Jordan: scale the pivot row, eliminate the column from every other row
+            // Gauss-Jordan: scale the pivot row, eliminate the column from every other row (thread = column, no divisions)
             for (int o = tid; o < W; o += T) aug[p * S + o] *= inv;
-            group_sync<T>();
-            for (int e = tid; e < N * W; e += T) {
-                int i = e / W, o = e - i * W;
-                if (i != p && o != p) aug[i * S + o] = fma(-aug[i * S + p], aug[p * S + o], aug[i * S + o]);
+            __syncthreads();
+            for (int o = tid; o < W; o += T) {
+                if (o == p) continue;
+                const double rp = aug[p * S + o];
+                for (int i = 0; i < N; ++i)
+                    if (i != p) aug[i * S + o] = fma(-aug[i * S + p], rp, aug[i * S + o]);
             }
-            group_sync<T>();
-            for (int i = tid; i < N; i += T)
-                if (i != p) aug[i * S + p] = 0.0;
-            group_sync<T>();
+            __syncthreads();
         } else {
-            const int rem = N - p - 1;
-            for (int e = tid; e < rem * rem; e += T) {
-                int i = p + 1 + e / rem, o = p + 1 + e % rem;
-                aug[i * S + o] = fma(-aug[i * S + p] * inv, aug[p * S + o], aug[i * S + o]);
+            for (int o = p + 1 + tid; o < N; o += T) {
+                const double rp = aug[p * S + o] * inv;
+                for (int i = p + 1; i < N; ++i) aug[i * S + o] = fma(-aug[i * S + p], rp, aug[i * S + o]);
             }
-            group_sync<T>();
+            __syncthreads();
         }
     }
     float *out = det + bd * (long)(LAP ? K + 3 : 2);
     if (tid == 0) { out[0] = (float)logdet; out[1] = sign; }
     if (!LAP) return;
 
-    for (int e = tid; e < N * N; e += T) {
-        int o = e / N, i = e - o * N;
-        Ainv[o * (N + 1) + i] = (float)aug[o * S + N + i];
+    for (int e = tid; e < N * NP2; e += T) {
+        int i = e / NP2, o = e - i * NP2;
+        AinvT[e] = o < N ? (float)aug[o * S + N + i] : 0.f;
     }
-    group_sync<T>();
-    // Laplacian term tr(Ainv lapA); record = lap' = tr(Ainv lapA) - sum_k tr(P_k^2) + sum_k tr(P_k)^2 (FP64 sums, see k_det_warp)
-    double part = 0.0;
-    for (int e = tid; e < N * N; e += T) {
-        int i = e / N, o = e - i * N;
-        part = fma((double)Ainv[o * (N + 1) + i], (double)mob[((long)i * C + C - 1) * cols + o], part);
-    }
-    const double lap = group_sum_d<T>(part, redd, tid);
-    double tr2_total = 0.0, sum_g2 = 0.0;
-    // P = Ainv dA_k in strips: one strip = row o, TQ consecutive columns (TQ+1 shared loads per TQ FMAs).
-    // Element -> (row, column) maps are hoisted out of the k loop (runtime N: integer divisions are expensive).
-    constexpr int TQ = 8;
-    constexpr int ME = T == 32 ? 8 : 16;                   // register-cached element slots per thread (covers N*N <= ME*T)
-    const int n_qc = (N + TQ - 1) / TQ, n_strips = N * n_qc;
-    int src_off[ME], dst_off[ME], tr_off[ME];
+    __syncthreads();                       // aug is dead from here on: its memory becomes dA / P
+    for (int e = tid; e < 2 * N * NQ; e += T) dA[e] = 0.f;
+    // element -> (row, column) maps hoisted out of the k loop (runtime N: integer divisions are expensive)
+    constexpr int ME = T == 32 ? 8 : 16;   // register-cached element slots per thread (covers N*N <= ME*T)
+    int src_off[ME], dst_off[ME];
 #pragma unroll
     for (int sl = 0; sl < ME; ++sl) {
         int e = tid + sl * T;
         int i = e / N, o = e - i * N;
-        bool ok = e < N * N;
-        src_off[sl] = ok ? (i * C) * cols + o : -1;
-        dst_off[sl] = i * (N + 1) + o;
-        tr_off[sl] = o * (N + 1) + i;
+        src_off[sl] = e < N * N ? (i * C) * cols + o : -1;
+        dst_off[sl] = i * NQ + o;
     }
     const bool cached = N * N <= ME * T;
+    // record = lap' = tr(Ainv lapA) - sum_k tr(P_k^2) + sum_k tr(P_k)^2 (FP64 sums of FP32 P entries, see k_det_warp)
+    double part = 0.0;
+    for (int e = tid; e < N * N; e += T) {
+        int i = e / N, o = e - i * N;
+        part = fma((double)AinvT[i * NP2 + o], (double)mob[((long)i * C + C - 1) * cols + o], part);
+    }
+    const double lap = group_sum_d<T>(part, redd, tid);
+    // P = Ainv dA_k in 2 x 8 register tiles: per i one float2 (two rows of Ainv) and two float4 (eight columns of dA) for 16 FMAs
+    const int nqc = NQ >> 3, n_items = (NP2 >> 1) * nqc;
+    double tr2 = 0.0, sum_g2 = 0.0;
     for (int k = 0; k < K; ++k) {
         const float *mk = mob + (long)(1 + k) * cols;
-        group_sync<T>();
+        __syncthreads();
         if (cached) {
 #pragma unroll
             for (int sl = 0; sl < ME; ++sl)
@@ -238,48 +234,54 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
         } else {
             for (int e = tid; e < N * N; e += T) {
                 int i = e / N, o = e - i * N;
-                dA[i * (N + 1) + o] = mk[((long)i * C) * cols + o];
+                dA[i * NQ + o] = mk[((long)i * C) * cols + o];
             }
         }
-        group_sync<T>();
+        __syncthreads();
         double gkd = 0.0;
-        for (int sidx = tid; sidx < n_strips; sidx += T) {
-            const int o = sidx / n_qc, q0 = (sidx - o * n_qc) * TQ;
-            float acc[TQ];
+        for (int item = tid; item < n_items; item += T) {
+            const int o0 = (item / nqc) * 2, q0 = (item - (item / nqc) * nqc) * 8;
+            float a0[8], a1[8];
 #pragma unroll
-            for (int t = 0; t < TQ; ++t) acc[t] = 0.f;
-            const float *arow = Ainv + o * (N + 1);
+            for (int t = 0; t < 8; ++t) { a0[t] = 0.f; a1[t] = 0.f; }
             for (int i = 0; i < N; ++i) {
-                const float av = arow[i];
-                const float *drow = dA + i * (N + 1) + q0;
-#pragma unroll
-                for (int t = 0; t < TQ; ++t)
-                    if (q0 + t < N) acc[t] = fmaf(av, drow[t], acc[t]);
+                const float2 av = *reinterpret_cast<const float2 *>(AinvT + i * NP2 + o0);
+                const float4 x0 = *reinterpret_cast<const float4 *>(dA + i * NQ + q0);
+                const float4 x1 = *reinterpret_cast<const float4 *>(dA + i * NQ + q0 + 4);
+                a0[0] = fmaf(av.x, x0.x, a0[0]); a0[1] = fmaf(av.x, x0.y, a0[1]); a0[2] = fmaf(av.x, x0.z, a0[2]); a0[3] = fmaf(av.x, x0.w, a0[3]);
+                a0[4] = fmaf(av.x, x1.x, a0[4]); a0[5] = fmaf(av.x, x1.y, a0[5]); a0[6] = fmaf(av.x, x1.z, a0[6]); a0[7] = fmaf(av.x, x1.w, a0[7]);
+                a1[0] = fmaf(av.y, x0.x, a1[0]); a1[1] = fmaf(av.y, x0.y, a1[1]); a1[2] = fmaf(av.y, x0.z, a1[2]); a1[3] = fmaf(av.y, x0.w, a1[3]);
+                a1[4] = fmaf(av.y, x1.x, a1[4]); a1[5] = fmaf(av.y, x1.y, a1[5]); a1[6] = fmaf(av.y, x1.z, a1[6]); a1[7] = fmaf(av.y, x1.w, a1[7]);
+            }
+            *reinterpret_cast<float4 *>(P + o0 * NQ + q0) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+            *reinterpret_cast<float4 *>(P + o0 * NQ + q0 + 4) = make_float4(a0[4], a0[5], a0[6], a0[7]);
+            if (o0 + 1 < N) {
+                *reinterpret_cast<float4 *>(P + (o0 + 1) * NQ + q0) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+                *reinterpret_cast<float4 *>(P + (o0 + 1) * NQ + q0 + 4) = make_float4(a1[4], a1[5], a1[6], a1[7]);
             }
 #pragma unroll
-            for (int t = 0; t < TQ; ++t)
-                if (q0 + t < N) {
-                    P[o * (N + 1) + q0 + t] = acc[t];
-                    if (q0 + t == o) gkd += (double)acc[t];
-                }
+            for (int t = 0; t < 8; ++t) {
+                if (q0 + t == o0) gkd += (double)a0[t];
+                if (q0 + t == o0 + 1 && o0 + 1 < N) gkd += (double)a1[t];
+            }
         }
-        group_sync<T>();
-        if (cached) {
+        __syncthreads();
+        for (int item = tid; item < n_items; item += T) {     // tr(P^2) = sum_{o,q} P[o][q] P[q][o] over this thread's tile
+            const int o0 = (item / nqc) * 2, q0 = (item - (item / nqc) * nqc) * 8;
+            const bool two = o0 + 1 < N;
 #pragma unroll
-            for (int sl = 0; sl < ME; ++sl)
-                if (src_off[sl] >= 0) tr2_total = fma((double)P[dst_off[sl]], (double)P[tr_off[sl]], tr2_total);
-        } else {
-            for (int e = tid; e < N * N; e += T) {
-                int o = e / N, q = e - o * N;
-                tr2_total = fma((double)P[o * (N + 1) + q], (double)P[q * (N + 1) + o], tr2_total);
-            }
+            for (int t = 0; t < 8; ++t)
+                if (q0 + t < N) {
+                    tr2 = fma((double)P[o0 * NQ + q0 + t], (double)P[(q0 + t) * NQ + o0], tr2);
+                    if (two) tr2 = fma((double)P[(o0 + 1) * NQ + q0 + t], (double)P[(q0 + t) * NQ + o0 + 1], tr2);
+                }
         }
         const float gk = (float)group_sum_d<T>(gkd, redd, tid);
         sum_g2 = fma((double)gk, (double)gk, sum_g2);
         if (tid == 0) out[3 + k] = gk;
     }
-    tr2_total = group_sum_d<T>(tr2_total, redd, tid);
-    if (tid == 0) out[2] = (float)(lap + (sum_g2 - tr2_total));
+    tr2 = group_sum_d<T>(tr2, redd, tid);
+    if (tid == 0) out[2] = (float)(lap + (sum_g2 - tr2));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -438,7 +440,10 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStr
     const dpe_dims &d = m->dims;
     const int N = d.n_el;
     const bool lap = C > 1;
-    size_t smem = (size_t)N * ((lap ? 2 * N : N) + 1) * sizeof(double) + ((lap ? 3 * (size_t)N * (N + 1) : 0) + 16) * sizeof(float) + 10 * sizeof(double);
+    const size_t np2 = (N + 1) & ~1, nq = (N + 7) & ~7;
+    size_t aug_bytes = (size_t)N * ((lap ? 2 * N : N) + 1) * sizeof(double);
+    if (lap && aug_bytes < 2 * N * nq * sizeof(float)) aug_bytes = 2 * N * nq * sizeof(float);
+    size_t smem = aug_bytes + ((lap ? (size_t)N * np2 : 0) + 16) * sizeof(float) + 10 * sizeof(double);
     int blocks = Bc * d.n_dets;
     static const bool force_generic = getenv("DPE_DET_GENERIC") != nullptr;   // debug knob
     if (N <= 16 && !force_generic) {

@@ -516,89 +516,105 @@ int launch_mean(dpe_model *m, const float *x, int ldx, int Bc, int C, int d_in, 
 // Laplacian mode: one block per (walker, slab of CS channels); thread = (channel, feature). The channel slab of
 // hm for all electrons stays in shared memory; the pair weights of one electron i are staged per iteration.
 // ------------------------------------------------------------------------------------------------
-template <int CS, int EMB>   // EMB > 0: compile-time embedding width (index math folds to shifts); 0: runtime
-__global__ void __launch_bounds__(CS * 32) k_conv_lap(const float *__restrict__ r, int N, int C, int emb_rt, int dE,
+// Dense part: conv_ee[b,i,c,f] = sum_j w[b,i,j,f] * hm[b,j,c,f] is, per (walker, feature), an [N x N] x [N x C] product.
+// Block = (walker, 8 features, 32 channels); w and the hm slab are staged once in shared memory; each thread owns one
+// (channel, feature) and register-blocks 4 electrons i (one LDS.128 of w + one LDS of hm per 4 FMAs).
+constexpr int CV_FG = 8, CV_CB = 32;
+__global__ void __launch_bounds__(CV_FG * CV_CB) k_conv_dense(int N, int C, int CP, int emb, const float *__restrict__ hm,
+                                                              const float *__restrict__ pw, float *__restrict__ x, int ldx,
+                                                              int col_ee) {
+    extern __shared__ __align__(16) float sm[];
+    const int NP = (N + 3) & ~3;
+    float *A_s = sm;                              // [j][f][NP]   w(i, j, f), i fastest
+    float *B_s = A_s + N * CV_FG * NP;            // [j][cl][f]
+    const int n_fg = emb / CV_FG, n_cb = (C + CV_CB - 1) / CV_CB;
+    int bid = blockIdx.x;
+    const int cb = bid % n_cb; bid /= n_cb;
+    const int fg = bid % n_fg;
+    const long b = bid / n_fg;
+    const int f0 = fg * CV_FG, c0 = cb * CV_CB;
+    const int tid = threadIdx.x, f = tid & (CV_FG - 1), cl = tid >> 3;
+    for (int t = tid; t < N * N * CV_FG; t += blockDim.x) {
+        const int ff = t & (CV_FG - 1), ij = t >> 3, i = ij / N, j = ij - i * N;
+        A_s[(j * CV_FG + ff) * NP + i] = pw[((b * N + i) * N + j) * (long)CP * emb + f0 + ff];
+    }
+    if (NP > N)
+        for (int t = tid; t < N * CV_FG * (NP - N); t += blockDim.x) {
+            const int jf = t / (NP - N), i = N + (t - jf * (NP - N));
+            A_s[jf * NP + i] = 0.f;
+        }
+    for (int t = tid; t < N * CV_CB * CV_FG; t += blockDim.x) {
+        const int ff = t & (CV_FG - 1), jc = t >> 3, j = jc / CV_CB, cc = jc - j * CV_CB;
+        B_s[t] = (c0 + cc < C) ? hm[((b * N + j) * (long)C + c0 + cc) * emb + f0 + ff] : 0.f;
+    }
+    __syncthreads();
+    const int c = c0 + cl;
+    if (c >= C) return;
+    const float *ap = A_s + f * NP;
+    const float *bp = B_s + cl * CV_FG + f;
+    float *xp = x + ((b * N) * (long)C + c) * ldx + col_ee + f0 + f;
+    const long xstride = (long)C * ldx;
+    for (int ig = 0; ig < NP; ig += 4) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int j = 0; j < N; ++j) {
+            const float4 w = *reinterpret_cast<const float4 *>(ap + j * CV_FG * NP + ig);
+            const float h = bp[j * CV_CB * CV_FG];
+            a0 = fmaf(w.x, h, a0); a1 = fmaf(w.y, h, a1); a2 = fmaf(w.z, h, a2); a3 = fmaf(w.w, h, a3);
+        }
+        xp[(ig + 0) * xstride] = a0;
+        if (ig + 1 < N) xp[(ig + 1) * xstride] = a1;
+        if (ig + 2 < N) xp[(ig + 2) * xstride] = a2;
+        if (ig + 3 < N) xp[(ig + 3) * xstride] = a3;
+    }
+}
+
+// Sparse part of the product rule (w depends on r_i, r_j only) and the expansion of conv_eI: one thread per (walker, i, f).
+//   d/dr_j  (j != i):  + w'_ij u_ij hm_j          d/dr_i:  - sum_j w'_ij u_ij hm_j
+//   Laplacian:  sum_j [ (2 w''_ij + 4 w'_ij / d_ij) hm_j + 2 w'_ij u_ij . (d hm_j/d r_j - d hm_j/d r_i) ]
+__global__ void __launch_bounds__(256) k_conv_special(const float *__restrict__ r, long n_rows, int N, int C, int emb, int dE,
                                                        const float *__restrict__ hm, const float *__restrict__ pw,
                                                        const float *__restrict__ ei, float *__restrict__ x, int ldx, int col_ee) {
-    extern __shared__ __align__(16) float sm[];
-    const int emb = EMB > 0 ? EMB : emb_rt;
-    float *hm0_s = sm;                       // [N][emb]      value channel of hm
-    float *hmd_s = hm0_s + N * emb;          // [N][3][emb]   d hm_j / d r_j
-    float *hm_s = hmd_s + 3 * N * emb;       // [N][CS][emb]  this block's channel slab
-    float *w_s = hm_s + N * CS * emb;        // [N][3][emb]   w, w', w'' of pairs (i, :)
-    float *r_s = w_s + 3 * N * emb;          // [N][3]
-    const int n_slabs = (C + CS - 1) / CS;
-    const long b = blockIdx.x / n_slabs;
-    const int slab = blockIdx.x - (int)(b * n_slabs);
-    const int cl = threadIdx.x >> 5, f = threadIdx.x & 31;
-    const int c = slab * CS + cl;
-    const bool act = c < C && f < emb;
-    const float *hmb = hm + b * N * C * emb;   // [j][c][f]
-    for (int t = threadIdx.x; t < 3 * N; t += blockDim.x) r_s[t] = r[b * N * 3 + t];
-    for (int t = threadIdx.x; t < N * emb; t += blockDim.x) {
-        int j = t / emb, ff = t - j * emb;
-        hm0_s[t] = hmb[((long)j * C) * emb + ff];
-    }
-    for (int t = threadIdx.x; t < 3 * N * emb; t += blockDim.x) {
-        int j = t / (3 * emb), rem = t - j * 3 * emb, a = rem / emb, ff = rem - a * emb;
-        hmd_s[t] = hmb[((long)j * C + 1 + 3 * j + a) * emb + ff];
-    }
-    for (int t = threadIdx.x; t < N * CS * emb; t += blockDim.x) {
-        int j = t / (CS * emb), rem = t - j * CS * emb, cc = rem / emb, ff = rem - cc * emb;
-        int cg = slab * CS + cc;
-        hm_s[t] = cg < C ? hmb[((long)j * C + cg) * emb + ff] : 0.f;
-    }
-    // channel classification of this thread
-    const bool is_lap = c == C - 1;
-    const int k = c - 1, e = (c > 0 && !is_lap) ? k / 3 : -1, a = k - 3 * (k / 3);
-    const int wrow = 3 * N * emb;
-    for (int i = 0; i < N; ++i) {
-        __syncthreads();
-        const float *pwi = pw + (b * N + i) * (long)wrow;     // [j][ch][f], contiguous
-        for (int t = threadIdx.x; t < (wrow >> 2); t += blockDim.x)
-            reinterpret_cast<float4 *>(w_s)[t] = reinterpret_cast<const float4 *>(pwi)[t];
-        __syncthreads();
-        float *xrow = x + ((b * N + i) * (long)C + c) * ldx + col_ee;
-        if (act) {
-            float acc = 0.f;
-            for (int j = 0; j < N; ++j) acc = fmaf(w_s[(j * 3) * emb + f], hm_s[(j * CS + cl) * emb + f], acc);
-            const float xi = r_s[3 * i], yi = r_s[3 * i + 1], zi = r_s[3 * i + 2];
-            if (is_lap) {
-                for (int j = 0; j < N; ++j) {
-                    if (j == i) continue;
-                    float dx = r_s[3 * j] - xi, dy = r_s[3 * j + 1] - yi, dz = r_s[3 * j + 2] - zi;
-                    float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-                    float w1 = w_s[(j * 3 + 1) * emb + f], w2 = w_s[(j * 3 + 2) * emb + f];
-                    const float *hji = hmb + ((long)j * C + 1 + 3 * i) * emb + f;      // d hm_j / d r_i
-                    float cross = dx * (hmd_s[(j * 3) * emb + f] - hji[0]) + dy * (hmd_s[(j * 3 + 1) * emb + f] - hji[emb]) +
-                                  dz * (hmd_s[(j * 3 + 2) * emb + f] - hji[2 * emb]);
-                    acc += (2.f * w2 + 4.f * w1 * inv) * hm0_s[j * emb + f] + 2.f * w1 * (cross * inv);
-                }
-            } else if (e == i) {
-                float sacc = 0.f;
-                for (int j = 0; j < N; ++j) {
-                    if (j == i) continue;
-                    float dx = r_s[3 * j] - xi, dy = r_s[3 * j + 1] - yi, dz = r_s[3 * j + 2] - zi;
-                    float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-                    float ua = (a == 0 ? dx : (a == 1 ? dy : dz)) * inv;
-                    sacc = fmaf(w_s[(j * 3 + 1) * emb + f] * ua, hm0_s[j * emb + f], sacc);
-                }
-                acc -= sacc;
-            } else if (e >= 0) {
-                float dx = r_s[3 * e] - xi, dy = r_s[3 * e + 1] - yi, dz = r_s[3 * e + 2] - zi;
-                float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-                float ua = (a == 0 ? dx : (a == 1 ? dy : dz)) * inv;
-                acc = fmaf(w_s[(e * 3 + 1) * emb + f] * ua, hm0_s[e * emb + f], acc);
-            }
-            xrow[f] = acc;
+    const long row = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);     // (b, i)
+    const int f = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const long b = row / N;
+    const int i = (int)(row - b * N);
+    const float *rb = r + b * N * 3;
+    const float xi = rb[3 * i], yi = rb[3 * i + 1], zi = rb[3 * i + 2];
+    float *xr = x + row * (long)C * ldx + col_ee;            // channel c at xr[c * ldx]
+    if (f < emb) {
+        const float *pwi = pw + row * (long)N * 3 * emb + f;  // [j][ch][f]
+        const float *hmb = hm + b * N * (long)C * emb + f;    // [j][c][f]
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, lap = 0.f;
+        for (int j = 0; j < N; ++j) {
+            if (j == i) continue;
+            const float dx = rb[3 * j] - xi, dy = rb[3 * j + 1] - yi, dz = rb[3 * j + 2] - zi;
+            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            const float ux = dx * inv, uy = dy * inv, uz = dz * inv;
+            const float w1 = pwi[(long)(j * 3 + 1) * emb], w2 = pwi[(long)(j * 3 + 2) * emb];
+            const float *hj = hmb + (long)j * C * emb;
+            const float h0 = hj[0];
+            const float *hjj = hj + (long)(1 + 3 * j) * emb, *hji = hj + (long)(1 + 3 * i) * emb;
+            const float cross = ux * (hjj[0] - hji[0]) + uy * (hjj[emb] - hji[emb]) + uz * (hjj[2 * emb] - hji[2 * emb]);
+            const float t = w1 * h0;
+            float *xt = xr + (long)(1 + 3 * j) * ldx + f;
+            xt[0] += t * ux; xt[ldx] += t * uy; xt[2 * ldx] += t * uz;
+            s0 = fmaf(t, ux, s0); s1 = fmaf(t, uy, s1); s2 = fmaf(t, uz, s2);
+            lap += (2.f * w2 + 4.f * w1 * inv) * h0 + 2.f * w1 * cross;
         }
-        if (c < C && f < dE) {     // conv_eI: expand the 5-channel el-ion convolution into the C channels of electron i
-            const float *eii = ei + (b * N + i) * 5 * dE;
+        float *xs = xr + (long)(1 + 3 * i) * ldx + f;
+        xs[0] -= s0; xs[ldx] -= s1; xs[2 * ldx] -= s2;
+        xr[(long)(C - 1) * ldx + f] += lap;
+    }
+    if (f < dE) {          // conv_eI: the 5-channel el-ion convolution expanded into the C channels of electron i
+        const float *eii = ei + row * 5 * dE + f;
+        float *xe = xr + emb + f;
+        for (int c = 0; c < C; ++c) {
             float v = 0.f;
-            if (c == 0) v = eii[f];
-            else if (is_lap) v = eii[4 * dE + f];
-            else if (e == i) v = eii[(1 + a) * dE + f];
-            xrow[emb + f] = v;
+            if (c == 0) v = eii[0];
+            else if (c == C - 1) v = eii[4 * dE];
+            else if (c >= 1 + 3 * i && c < 4 + 3 * i) v = eii[(c - 3 * i) * dE];
+            xe[(long)c * ldx] = v;
         }
     }
 }
@@ -632,16 +648,15 @@ int launch_conv(dpe_model *m, int it, const float *r, int Bc, int C, const float
     if (C == 1) {
         k_conv_fwd<<<Bc, 256, (size_t)N * emb * sizeof(float), s>>>(N, emb, p.dE, hm, pw, ei, x, ldx, p.d_in);
     } else {
-        constexpr int CS = 8;
-        size_t smem = ((size_t)3 * N + (size_t)N * emb * (1 + 3 + CS + 3)) * sizeof(float);
-        int n_slabs = (C + CS - 1) / CS;
-        if (emb == 32) {
-            if (smem > 48 * 1024) DPE_CUDA(cudaFuncSetAttribute(k_conv_lap<CS, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_conv_lap<CS, 32><<<Bc * n_slabs, CS * 32, smem, s>>>(r, N, C, emb, p.dE, hm, pw, ei, x, ldx, p.d_in);
-        } else {
-            if (smem > 48 * 1024) DPE_CUDA(cudaFuncSetAttribute(k_conv_lap<CS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_conv_lap<CS, 0><<<Bc * n_slabs, CS * 32, smem, s>>>(r, N, C, emb, p.dE, hm, pw, ei, x, ldx, p.d_in);
-        }
+        if (emb % CV_FG) return set_error(DPE_ERR_UNSUPPORTED, "conv: emb_dim=%d must be a multiple of %d", emb, CV_FG);
+        const int NP = (N + 3) & ~3;
+        size_t smem = ((size_t)N * CV_FG * NP + (size_t)N * CV_CB * CV_FG) * sizeof(float);
+        if (smem > 48 * 1024) DPE_CUDA(cudaFuncSetAttribute(k_conv_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int n_cb = (C + CV_CB - 1) / CV_CB;
+        k_conv_dense<<<Bc * (emb / CV_FG) * n_cb, CV_FG * CV_CB, smem, s>>>(N, C, 3, emb, hm, pw, x, ldx, p.d_in);
+        DPE_LAUNCH_CHECK(m);
+        long n_rows = (long)Bc * N;
+        k_conv_special<<<(int)((n_rows + 7) / 8), 256, 0, s>>>(r, n_rows, N, C, emb, p.dE, hm, pw, ei, x, ldx, p.d_in);
     }
     DPE_LAUNCH_CHECK(m);
     return DPE_OK;

@@ -101,7 +101,7 @@ def test_analytic_helium_like():
     from oracle import model as om
     from deeperwin_b200.engine import Engine
     Zc = 2
-    d = om.ModelDims(n_el=2, n_up=1, n_ion=1, Z_max=2, n_iterations=1, n_hidden_one_el=[8], n_hidden_two_el=[], emb_dim=4, n_dets=1)
+    d = om.ModelDims(n_el=2, n_up=1, n_ion=1, Z_max=2, n_iterations=1, n_hidden_one_el=[8], n_hidden_two_el=[], emb_dim=8, n_dets=1)
     params = om.init_params(d, seed=0, dtype=torch.float32)
     for leaves in params.values():
         for k in leaves:
@@ -114,7 +114,7 @@ def test_analytic_helium_like():
     params[f"{om.ORB}/bf_dn/linear_0"]["w"] = w_dn
     for k in ("alpha_up", "alpha_dn"):
         params[om.ORB][k].fill_(math.log(math.expm1(Zc)))
-    eng = Engine(n_el=2, n_up=1, n_ion=1, n_iterations=1, n_hidden_one_el=[8], n_hidden_two_el=[], emb_dim=4, n_ion_features=32,
+    eng = Engine(n_el=2, n_up=1, n_ion=1, n_iterations=1, n_hidden_one_el=[8], n_hidden_two_el=[], emb_dim=8, n_ion_features=32,
                  n_dets=1, z_min=1, z_max=2)
     eng.set_params({m: {k: v.cuda() for k, v in l.items()} for m, l in params.items()})
     eng.set_geometry(np.zeros((1, 3), np.float32), [Zc])
