@@ -46,7 +46,7 @@ struct TcArgs {
     int tile_rows;                                 // rows a tile owns (<= nmma; a multiple of the channel count when epi != 0)
     int n_rt, n_ft;                                // row tiles per segment, feature tiles
     // fused epilogue. 0: plain store. 2: envelope multiply of the backflow GEMM (envelope_orbitals.py:96-127) with the product rule
-    int epi, C;                                    // channels per (walker, electron) group
+    int epi, nch;                                  // channels per (walker, electron) group
     const float *r, *R, *spa, *envw;               // walker positions [n_seg, n_el, 3], ions [I,3], softplus(alpha) / weights [I, N_out]
     int n_el, n_ion, el_base;                      // electron index of local group 0 of a segment (0 for spin-up, n_up for spin-down)
 };
@@ -245,7 +245,7 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             float *cbase = a.C + ((long)seg * a.c_seg_stride + a.c_seg_off + m0) * a.ldc + a.c_col_off + f;
             const bool f_ok = f < a.N_out;
             // envelope state (epi == 2): group = (walker seg, electron el_base + (m0 + col) / C), channel cch
-            int cch = 0, grp = a.epi == 2 ? m0 / a.C : 0;
+            int cch = 0, grp = a.epi == 2 ? m0 / a.nch : 0;
             float env = 1.f, e1x = 0.f, e1y = 0.f, e1z = 0.f, el = 0.f, bf0 = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
             int ci = 0;
             mbar_wait(bar_tfull, tphase);
@@ -284,7 +284,7 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                                         const float al = a.spa[(long)J * a.N_out + f];
                                         const float e = __fmul_rn(a.envw[(long)J * a.N_out + f], expf(-al * d));
                                         env = __fadd_rn(env, e);
-                                        if (a.C > 1) {
+                                        if (a.nch > 1) {
                                             const float inv = 1.f / d, g = -al * e * inv;
                                             e1x = fmaf(g, dx, e1x); e1y = fmaf(g, dy, e1y); e1z = fmaf(g, dz, e1z);
                                             el = fmaf(e, al * al - 2.f * al * inv, el);
@@ -293,14 +293,14 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                                 }
                             }
                             float o = val * env;
-                            if (a.C > 1) {
+                            if (a.nch > 1) {
                                 if (cch == ci) { tx = val; o += e1x * bf0; }
                                 else if (cch == ci + 1) { ty = val; o += e1y * bf0; }
                                 else if (cch == ci + 2) { tz = val; o += e1z * bf0; }
-                                else if (cch == a.C - 1) o += el * bf0 + 2.f * (e1x * tx + e1y * ty + e1z * tz);
+                                else if (cch == a.nch - 1) o += el * bf0 + 2.f * (e1x * tx + e1y * ty + e1z * tz);
                             }
                             if (f_ok) cbase[(long)(c0 + j) * a.ldc] = o;
-                            if (++cch == a.C) { cch = 0; ++grp; }
+                            if (++cch == a.nch) { cch = 0; ++grp; }
                         }
                     }
                 }
@@ -423,14 +423,14 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     TcArgs a;
     a.C = g.C; a.ldc = g.ldc; a.c_seg_stride = n_seg > 1 ? g.c_seg_stride : 0; a.c_seg_off = g.c_seg_off; a.c_col_off = g.c_col_off;
     a.n_seg = n_seg; a.seg_len = seg_len; a.N_out = g.N; a.K = g.K;
-    a.epi = g.epi; a.C = g.epi ? g.n_ch : 1;
+    a.epi = g.epi; a.nch = g.epi ? g.n_ch : 1;
     a.r = g.r; a.R = g.R; a.spa = g.spa; a.envw = g.envw; a.n_el = g.n_el; a.n_ion = g.n_ion; a.el_base = g.el_base;
     if (a.epi) {
         // group-aligned tiles: a tile owns whole (walker, electron) groups of C rows
-        if (a.C > 256 || seg_len % a.C) return DPE_ERR_UNSUPPORTED;
-        const int n_groups = seg_len / a.C, g_max = 256 / a.C;
+        if (a.nch > 256 || seg_len % a.nch) return DPE_ERR_UNSUPPORTED;
+        const int n_groups = seg_len / a.nch, g_max = 256 / a.nch;
         const int n_rt = (n_groups + g_max - 1) / g_max, gpt = (n_groups + n_rt - 1) / n_rt;
-        a.tile_rows = gpt * a.C;
+        a.tile_rows = gpt * a.nch;
         a.nmma = (a.tile_rows + 15) / 16 * 16;
         a.n_rt = n_rt;
     } else {
