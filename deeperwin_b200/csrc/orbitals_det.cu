@@ -116,7 +116,7 @@ __device__ __forceinline__ float group_sum(float v, float *red, int tid) {
 }
 
 template <int T, bool LAP>
-__global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float *__restrict__ mo, float *__restrict__ det) {
+__global__ void __launch_bounds__(T, 3) k_det(int N, int C, int n_det, const float *__restrict__ mo, float *__restrict__ det) {
     // The factorisation runs in FP64 (O(N^3) against the O(3N * N^3) FP32 tangent stage).
     extern __shared__ double smd[];
     const int W = LAP ? 2 * N : N;       // augmented width
@@ -224,13 +224,23 @@ __global__ void __launch_bounds__(T) k_det(int N, int C, int n_det, const float 
     // P = Ainv dA_k in 2 x 8 register tiles: per i one float2 (two rows of Ainv) and two float4 (eight columns of dA) for 16 FMAs
     const int nqc = NQ >> 3, n_items = (NP2 >> 1) * nqc;
     double tr2 = 0.0, sum_g2 = 0.0;
+    float pre[ME];                                   // software pipeline: dA_{k+1} travels while P_k is computed
+    if (cached) {
+#pragma unroll
+        for (int sl = 0; sl < ME; ++sl) pre[sl] = src_off[sl] >= 0 ? mob[(long)cols + src_off[sl]] : 0.f;
+    }
     for (int k = 0; k < K; ++k) {
         const float *mk = mob + (long)(1 + k) * cols;
         __syncthreads();
         if (cached) {
 #pragma unroll
             for (int sl = 0; sl < ME; ++sl)
-                if (src_off[sl] >= 0) dA[dst_off[sl]] = mk[src_off[sl]];
+                if (src_off[sl] >= 0) dA[dst_off[sl]] = pre[sl];
+            if (k + 1 < K) {
+#pragma unroll
+                for (int sl = 0; sl < ME; ++sl)
+                    if (src_off[sl] >= 0) pre[sl] = mk[(long)cols + src_off[sl]];
+            }
         } else {
             for (int e = tid; e < N * N; e += T) {
                 int i = e / N, o = e - i * N;
@@ -299,7 +309,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 template <bool LAP>
-__global__ void __launch_bounds__(128, 5) k_det_warp(int N, int C, int n_det, long n_mat, const float *__restrict__ mo,
+__global__ void __launch_bounds__(128, 4) k_det_warp(int N, int C, int n_det, long n_mat, const float *__restrict__ mo,
                                                    float *__restrict__ det) {
     extern __shared__ double smd[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -395,15 +405,20 @@ __global__ void __launch_bounds__(128, 5) k_det_warp(int N, int C, int n_det, lo
     const int orow = lane >> 1, q0 = (lane & 1) * 8;
     const bool strip = orow < N;
     double t2 = 0.0, sum_g2 = 0.0;
+    float ld[8];                                     // software pipeline: dA_{k+1} travels while P_k is computed
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) ld[sl] = src_off[sl] >= 0 ? mob[(long)cols + src_off[sl]] : 0.f;
     for (int k = 0; k < K; ++k) {
         const float *mk = mob + (long)(1 + k) * cols;
-        float ld[8];
-#pragma unroll
-        for (int sl = 0; sl < 8; ++sl) ld[sl] = src_off[sl] >= 0 ? mk[src_off[sl]] : 0.f;
         __syncwarp();
 #pragma unroll
         for (int sl = 0; sl < 8; ++sl)
             if (src_off[sl] >= 0) dA[d16[sl]] = ld[sl];
+        if (k + 1 < K) {
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl)
+                if (src_off[sl] >= 0) ld[sl] = mk[(long)cols + src_off[sl]];
+        }
         __syncwarp();
         double gkd = 0.0;
         if (strip) {

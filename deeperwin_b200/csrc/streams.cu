@@ -534,19 +534,20 @@ __global__ void __launch_bounds__(CV_FG * CV_CB) k_conv_dense(int N, int C, int 
     const long b = bid / n_fg;
     const int f0 = fg * CV_FG, c0 = cb * CV_CB;
     const int tid = threadIdx.x, f = tid & (CV_FG - 1), cl = tid >> 3;
-    for (int t = tid; t < N * N * CV_FG; t += blockDim.x) {
-        const int ff = t & (CV_FG - 1), ij = t >> 3, i = ij / N, j = ij - i * N;
-        A_s[(j * CV_FG + ff) * NP + i] = pw[((b * N + i) * N + j) * (long)CP * emb + f0 + ff];
+    {   // 32 threads x 8 features walk j for every i: no integer division in the staging loops
+        const int ff = tid & (CV_FG - 1), jl = tid >> 3;
+        for (int i = 0; i < N; ++i) {
+            const float *src = pw + ((b * N + i) * N) * (long)CP * emb + f0 + ff;
+            for (int j = jl; j < N; j += CV_CB) A_s[(j * CV_FG + ff) * NP + i] = src[(long)j * CP * emb];
+        }
     }
     if (NP > N)
         for (int t = tid; t < N * CV_FG * (NP - N); t += blockDim.x) {
             const int jf = t / (NP - N), i = N + (t - jf * (NP - N));
             A_s[jf * NP + i] = 0.f;
         }
-    for (int t = tid; t < N * CV_CB * CV_FG; t += blockDim.x) {
-        const int ff = t & (CV_FG - 1), jc = t >> 3, j = jc / CV_CB, cc = jc - j * CV_CB;
-        B_s[t] = (c0 + cc < C) ? hm[((b * N + j) * (long)C + c0 + cc) * emb + f0 + ff] : 0.f;
-    }
+    for (int j = 0; j < N; ++j)      // thread = (channel cl, feature f) of the slab
+        B_s[(j * CV_CB + cl) * CV_FG + f] = (c0 + cl < C) ? hm[((b * N + j) * (long)C + c0 + cl) * emb + f0 + f] : 0.f;
     __syncthreads();
     const int c = c0 + cl;
     if (c >= C) return;
