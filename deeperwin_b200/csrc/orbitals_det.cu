@@ -116,19 +116,22 @@ __device__ __forceinline__ float group_sum(float v, float *red, int tid) {
 }
 
 template <int T, bool LAP>
-__global__ void __launch_bounds__(T, 3) k_det(int N, int C, int n_det, const float *__restrict__ mo, float *__restrict__ det) {
+__global__ void __launch_bounds__(T, T == 64 ? 6 : 3) k_det(int N, int C, int n_det, const float *__restrict__ mo, float *__restrict__ det) {
     // The factorisation runs in FP64 (O(N^3) against the O(3N * N^3) FP32 tangent stage).
     extern __shared__ double smd[];
     const int W = LAP ? 2 * N : N;       // augmented width
     const int S = W + 1;                 // padded row stride
-    const int NP2 = (N + 1) & ~1;        // rows of Ainv^T padded to an even count (float2 loads)
-    const int NQ = (N + 7) & ~7;         // tangent-matrix rows padded to 8 floats (float4 loads), zero filled
-    double *aug = smd;                   // [N][S]; after the sweep the same memory holds dA [N][NQ] and P [N][NQ]
-    float *AinvT = reinterpret_cast<float *>(aug + N * S);        // [N][NP2]  AinvT[i][o] = Ainv[o][i]
-    float *red = AinvT + (LAP ? N * NP2 : 0);                     // 8 floats
+    const int NQ = (N + 7) & ~7;         // rows padded to 8 floats (float4 loads), zero filled
+    double *aug = smd;                   // [N][S]; after the sweep the same memory holds dA[2][N][NQ] and the tile exchange buffer
+    size_t aug_b = (size_t)N * S * sizeof(double);                // must match launch_det
+    {
+        const size_t nbt = NQ >> 3, alias_b = (2 * (size_t)N * NQ + nbt * nbt * 64) * sizeof(float);
+        if (LAP && alias_b > aug_b) aug_b = alias_b;
+        aug_b = (aug_b + 15) & ~(size_t)15;
+    }
+    float *AinvT = reinterpret_cast<float *>(reinterpret_cast<char *>(smd) + aug_b);   // [N][NQ]  AinvT[i][pos(o)] = Ainv[o][i]
+    float *red = AinvT + (LAP ? N * NQ : 0);                      // 8 floats
     double *redd = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(red + 8) + 7) & ~uintptr_t(7));   // 8 doubles
-    float *dA = reinterpret_cast<float *>(aug);
-    float *P = dA + N * NQ;
     __shared__ int piv_row;
     const int tid = threadIdx.x;
     const long bd = blockIdx.x;
@@ -197,94 +200,94 @@ __global__ void __launch_bounds__(T, 3) k_det(int N, int C, int n_det, const flo
     if (tid == 0) { out[0] = (float)logdet; out[1] = sign; }
     if (!LAP) return;
 
-    for (int e = tid; e < N * NP2; e += T) {
-        int i = e / NP2, o = e - i * NP2;
-        AinvT[e] = o < N ? (float)aug[o * S + N + i] : 0.f;
-    }
-    __syncthreads();                       // aug is dead from here on: its memory becomes dA / P
-    for (int e = tid; e < 2 * N * NQ; e += T) dA[e] = 0.f;
-    // element -> (row, column) maps hoisted out of the k loop (runtime N: integer divisions are expensive)
-    constexpr int ME = T == 32 ? 8 : 16;   // register-cached element slots per thread (covers N*N <= ME*T)
-    int src_off[ME], dst_off[ME];
-#pragma unroll
-    for (int sl = 0; sl < ME; ++sl) {
-        int e = tid + sl * T;
+    // ---- tangent stage: P_k = Ainv dA_k in 8 x 8 register tiles (one tile per thread, nb x nb <= T tiles) -------------
+    // Rows of AinvT / dA are stored permuted, [first halves of the 8-column chunks | second halves], so that the float4
+    // loads of a quarter warp hit distinct banks; padded rows / columns are zero, which zeroes the padding of P.
+    const int nb = (N + 7) >> 3, NPAD = nb * 8;
+    auto pos = [nb](int o) { return ((o & 7) >> 2) * (4 * nb) + (o >> 3) * 4 + (o & 3); };
+    for (int e = tid; e < N * NPAD; e += T) AinvT[e] = 0.f;
+    __syncthreads();
+    for (int e = tid; e < N * N; e += T) {
         int i = e / N, o = e - i * N;
-        src_off[sl] = e < N * N ? (i * C) * cols + o : -1;
-        dst_off[sl] = i * NQ + o;
+        AinvT[i * NPAD + pos(o)] = (float)aug[o * S + N + i];
     }
-    const bool cached = N * N <= ME * T;
+    __syncthreads();                       // aug is dead from here on: its memory becomes dA[2] (double buffer) and Tx
+    float *dAb = reinterpret_cast<float *>(aug);           // [2][N][NPAD]
+    float *Tx = dAb + 2 * N * NPAD;                        // [nb*nb][64] transposed tiles for tr(P^2)
+    for (int e = tid; e < 2 * N * NPAD; e += T) dAb[e] = 0.f;
     // record = lap' = tr(Ainv lapA) - sum_k tr(P_k^2) + sum_k tr(P_k)^2 (FP64 sums of FP32 P entries, see k_det_warp)
     double part = 0.0;
     for (int e = tid; e < N * N; e += T) {
         int i = e / N, o = e - i * N;
-        part = fma((double)AinvT[i * NP2 + o], (double)mob[((long)i * C + C - 1) * cols + o], part);
+        part = fma((double)AinvT[i * NPAD + pos(o)], (double)mob[((long)i * C + C - 1) * cols + o], part);
     }
     const double lap = group_sum_d<T>(part, redd, tid);
-    // P = Ainv dA_k in 2 x 8 register tiles: per i one float2 (two rows of Ainv) and two float4 (eight columns of dA) for 16 FMAs
-    const int nqc = NQ >> 3, n_items = (NP2 >> 1) * nqc;
-    double tr2 = 0.0, sum_g2 = 0.0;
-    float pre[ME];                                   // software pipeline: dA_{k+1} travels while P_k is computed
-    if (cached) {
-#pragma unroll
-        for (int sl = 0; sl < ME; ++sl) pre[sl] = src_off[sl] >= 0 ? mob[(long)cols + src_off[sl]] : 0.f;
-    }
-    for (int k = 0; k < K; ++k) {
-        const float *mk = mob + (long)(1 + k) * cols;
-        __syncthreads();
-        if (cached) {
-#pragma unroll
-            for (int sl = 0; sl < ME; ++sl)
-                if (src_off[sl] >= 0) dA[dst_off[sl]] = pre[sl];
-            if (k + 1 < K) {
-#pragma unroll
-                for (int sl = 0; sl < ME; ++sl)
-                    if (src_off[sl] >= 0) pre[sl] = mk[(long)cols + src_off[sl]];
-            }
-        } else {
-            for (int e = tid; e < N * N; e += T) {
-                int i = e / N, o = e - i * N;
-                dA[i * NQ + o] = mk[((long)i * C) * cols + o];
-            }
-        }
-        __syncthreads();
-        double gkd = 0.0;
-        for (int item = tid; item < n_items; item += T) {
-            const int o0 = (item / nqc) * 2, q0 = (item - (item / nqc) * nqc) * 8;
-            float a0[8], a1[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) { a0[t] = 0.f; a1[t] = 0.f; }
+    // dA_k staging with cp.async: thread -> column o (coalesced rows of mo), all rows i
+    const int o_ld = tid;                                  // T >= N is guaranteed by the launcher
+    const int pos_ld = o_ld < N ? pos(o_ld) : 0;
+    auto stage = [&](int k, int buf) {
+        if (o_ld < N) {
+            const float *src = mob + (long)(1 + k) * cols + o_ld;
+            float *dst = dAb + buf * N * NPAD + pos_ld;
             for (int i = 0; i < N; ++i) {
-                const float2 av = *reinterpret_cast<const float2 *>(AinvT + i * NP2 + o0);
-                const float4 x0 = *reinterpret_cast<const float4 *>(dA + i * NQ + q0);
-                const float4 x1 = *reinterpret_cast<const float4 *>(dA + i * NQ + q0 + 4);
-                a0[0] = fmaf(av.x, x0.x, a0[0]); a0[1] = fmaf(av.x, x0.y, a0[1]); a0[2] = fmaf(av.x, x0.z, a0[2]); a0[3] = fmaf(av.x, x0.w, a0[3]);
-                a0[4] = fmaf(av.x, x1.x, a0[4]); a0[5] = fmaf(av.x, x1.y, a0[5]); a0[6] = fmaf(av.x, x1.z, a0[6]); a0[7] = fmaf(av.x, x1.w, a0[7]);
-                a1[0] = fmaf(av.y, x0.x, a1[0]); a1[1] = fmaf(av.y, x0.y, a1[1]); a1[2] = fmaf(av.y, x0.z, a1[2]); a1[3] = fmaf(av.y, x0.w, a1[3]);
-                a1[4] = fmaf(av.y, x1.x, a1[4]); a1[5] = fmaf(av.y, x1.y, a1[5]); a1[6] = fmaf(av.y, x1.z, a1[6]); a1[7] = fmaf(av.y, x1.w, a1[7]);
+                const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst + i * NPAD);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32), "l"(src + (long)i * C * cols) : "memory");
             }
-            *reinterpret_cast<float4 *>(P + o0 * NQ + q0) = make_float4(a0[0], a0[1], a0[2], a0[3]);
-            *reinterpret_cast<float4 *>(P + o0 * NQ + q0 + 4) = make_float4(a0[4], a0[5], a0[6], a0[7]);
-            if (o0 + 1 < N) {
-                *reinterpret_cast<float4 *>(P + (o0 + 1) * NQ + q0) = make_float4(a1[0], a1[1], a1[2], a1[3]);
-                *reinterpret_cast<float4 *>(P + (o0 + 1) * NQ + q0 + 4) = make_float4(a1[4], a1[5], a1[6], a1[7]);
-            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int n_items = nb * nb;
+    const bool has_item = tid < n_items;
+    const int rb = has_item ? tid / nb : 0, cq = has_item ? tid - rb * nb : 0;
+    const int partner = cq * nb + rb;
+    double tr2 = 0.0, sum_g2 = 0.0;
+    __syncthreads();
+    stage(0, 0);
+    for (int k = 0; k < K; ++k) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();                                   // dA_k visible; Tx of the previous k consumed
+        if (k + 1 < K) stage(k + 1, (k + 1) & 1);
+        const float *dA = dAb + (k & 1) * N * NPAD;
+        double gkd = 0.0;
+        float acc[8][8];
+        if (has_item) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                if (q0 + t == o0) gkd += (double)a0[t];
-                if (q0 + t == o0 + 1 && o0 + 1 < N) gkd += (double)a1[t];
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int c2 = 0; c2 < 8; ++c2) acc[a][c2] = 0.f;
+            const float *ap = AinvT + 4 * rb, *xp = dA + 4 * cq;
+            for (int i = 0; i < N; ++i) {
+                const float4 al = *reinterpret_cast<const float4 *>(ap + i * NPAD), ah = *reinterpret_cast<const float4 *>(ap + i * NPAD + 4 * nb);
+                const float4 xl = *reinterpret_cast<const float4 *>(xp + i * NPAD), xh = *reinterpret_cast<const float4 *>(xp + i * NPAD + 4 * nb);
+                const float av[8] = {al.x, al.y, al.z, al.w, ah.x, ah.y, ah.z, ah.w};
+                const float xv[8] = {xl.x, xl.y, xl.z, xl.w, xh.x, xh.y, xh.z, xh.w};
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int c2 = 0; c2 < 8; ++c2) acc[a][c2] = fmaf(av[a], xv[c2], acc[a][c2]);
+            }
+            if (rb == cq) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) gkd += (double)acc[a][a];
+            }
+            float *tx = Tx + tid * 64;                      // Tx[item][b][a] = acc[a][b]
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2) {
+                *reinterpret_cast<float4 *>(tx + c2 * 8) = make_float4(acc[0][c2], acc[1][c2], acc[2][c2], acc[3][c2]);
+                *reinterpret_cast<float4 *>(tx + c2 * 8 + 4) = make_float4(acc[4][c2], acc[5][c2], acc[6][c2], acc[7][c2]);
             }
         }
         __syncthreads();
-        for (int item = tid; item < n_items; item += T) {     // tr(P^2) = sum_{o,q} P[o][q] P[q][o] over this thread's tile
-            const int o0 = (item / nqc) * 2, q0 = (item - (item / nqc) * nqc) * 8;
-            const bool two = o0 + 1 < N;
+        if (has_item) {                                    // tr(P^2) = sum over tiles <T(rb,cq), T(cq,rb)^T>
+            const float *px = Tx + partner * 64;
 #pragma unroll
-            for (int t = 0; t < 8; ++t)
-                if (q0 + t < N) {
-                    tr2 = fma((double)P[o0 * NQ + q0 + t], (double)P[(q0 + t) * NQ + o0], tr2);
-                    if (two) tr2 = fma((double)P[(o0 + 1) * NQ + q0 + t], (double)P[(q0 + t) * NQ + o0 + 1], tr2);
-                }
+            for (int a = 0; a < 8; ++a) {
+                const float4 p0 = *reinterpret_cast<const float4 *>(px + a * 8), p1 = *reinterpret_cast<const float4 *>(px + a * 8 + 4);
+                tr2 = fma((double)acc[a][0], (double)p0.x, tr2); tr2 = fma((double)acc[a][1], (double)p0.y, tr2);
+                tr2 = fma((double)acc[a][2], (double)p0.z, tr2); tr2 = fma((double)acc[a][3], (double)p0.w, tr2);
+                tr2 = fma((double)acc[a][4], (double)p1.x, tr2); tr2 = fma((double)acc[a][5], (double)p1.y, tr2);
+                tr2 = fma((double)acc[a][6], (double)p1.z, tr2); tr2 = fma((double)acc[a][7], (double)p1.w, tr2);
+            }
         }
         const float gk = (float)group_sum_d<T>(gkd, redd, tid);
         sum_g2 = fma((double)gk, (double)gk, sum_g2);
@@ -455,10 +458,12 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStr
     const dpe_dims &d = m->dims;
     const int N = d.n_el;
     const bool lap = C > 1;
-    const size_t np2 = (N + 1) & ~1, nq = (N + 7) & ~7;
+    const size_t nq = (N + 7) & ~7, nb = nq / 8;
     size_t aug_bytes = (size_t)N * ((lap ? 2 * N : N) + 1) * sizeof(double);
-    if (lap && aug_bytes < 2 * N * nq * sizeof(float)) aug_bytes = 2 * N * nq * sizeof(float);
-    size_t smem = aug_bytes + ((lap ? (size_t)N * np2 : 0) + 16) * sizeof(float) + 10 * sizeof(double);
+    const size_t alias_bytes = (2 * (size_t)N * nq + nb * nb * 64) * sizeof(float);
+    if (lap && aug_bytes < alias_bytes) aug_bytes = alias_bytes;
+    aug_bytes = (aug_bytes + 15) & ~(size_t)15;
+    size_t smem = aug_bytes + ((lap ? (size_t)N * nq : 0) + 16) * sizeof(float) + 10 * sizeof(double);
     int blocks = Bc * d.n_dets;
     static const bool force_generic = getenv("DPE_DET_GENERIC") != nullptr;   // debug knob
     if (N <= 16 && !force_generic) {
@@ -466,15 +471,13 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStr
         const long n_mat = (long)blocks;
         if (lap) k_det_warp<true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det);
         else k_det_warp<false><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det);
-    } else if (N <= 16) {
-        if (lap) k_det<32, true><<<blocks, 32, smem, s>>>(N, C, d.n_dets, mo, det);
-        else k_det<32, false><<<blocks, 32, smem, s>>>(N, C, d.n_dets, mo, det);
     } else {
+        // 64 threads: one 8 x 8 tile of P per thread (N <= 64 -> at most 64 tiles) and one column of mo per thread
         if (smem > 48 * 1024) {
-            DPE_CUDA(cudaFuncSetAttribute(k_det<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DPE_CUDA(cudaFuncSetAttribute(k_det<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             DPE_CUDA(cudaFuncSetAttribute(k_det<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
-        if (lap) k_det<128, true><<<blocks, 128, smem, s>>>(N, C, d.n_dets, mo, det);
+        if (lap) k_det<64, true><<<blocks, 64, smem, s>>>(N, C, d.n_dets, mo, det);
         else k_det<128, false><<<blocks, 128, smem, s>>>(N, C, d.n_dets, mo, det);
     }
     DPE_LAUNCH_CHECK(m);
