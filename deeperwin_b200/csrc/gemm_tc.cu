@@ -22,6 +22,7 @@
 //   warps 6-13  epilogue (tcgen05.ld 32x32b -> coalesced global stores)
 // TMEM: two accumulators [128 lanes x 256 columns] (features 0-127 / 128-255) = all 512 columns.
 #include <cuda.h>
+#include <cstdlib>
 #include <vector>
 #include "dpe_internal.cuh"
 
@@ -49,6 +50,7 @@ struct TcArgs {
     int epi, nch;                                  // channels per (walker, electron) group
     const float *r, *R, *spa, *envw;               // walker positions [n_seg, n_el, 3], ions [I,3], softplus(alpha) / weights [I, N_out]
     int n_el, n_ion, el_base;                      // electron index of local group 0 of a segment (0 for spin-up, n_up for spin-down)
+    int pipe;                                      // software-pipelined TMEM loads in the epilogue
 };
 
 // ---------------------------------------------------------------------------------------- PTX wrappers
@@ -251,14 +253,8 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             mbar_wait(bar_tfull, tphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * 256;
-            for (int c0 = 0; c0 < a.nmma; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c0, v);
-                tmem_ld_wait();
-                if (c0 + 16 >= a.nmma) {         // last chunk is in registers: the accumulators may be overwritten
-                    tc_fence_before();
-                    mbar_arrive(bar_tempty);
-                }
+            // one 16-column chunk of this thread's feature: plain store or fused envelope (epi == 2)
+            auto process = [&](const uint32_t (&v)[16], int c0) {
                 if (a.epi == 0) {
                     if (f_ok) {
 #pragma unroll
@@ -304,6 +300,30 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                         }
                     }
                 }
+            };
+            // TMEM -> registers is software pipelined: the next chunk travels while the current one is stored
+            uint32_t v0[16], v1[16];
+            if (!a.pipe) {
+                for (int c0 = 0; c0 < a.nmma; c0 += 16) {
+                    tmem_ld16(taddr + c0, v0);
+                    tmem_ld_wait();
+                    if (c0 + 16 >= a.nmma) { tc_fence_before(); mbar_arrive(bar_tempty); }
+                    process(v0, c0);
+                }
+            } else {
+            tmem_ld16(taddr, v0);
+            for (int c0 = 0; c0 < a.nmma; c0 += 32) {
+                tmem_ld_wait();
+                if (c0 + 16 < a.nmma) tmem_ld16(taddr + c0 + 16, v1);
+                else { tc_fence_before(); mbar_arrive(bar_tempty); }   // everything is in registers: accumulators are free
+                process(v0, c0);
+                if (c0 + 16 < a.nmma) {
+                    tmem_ld_wait();
+                    if (c0 + 32 < a.nmma) tmem_ld16(taddr + c0 + 32, v0);
+                    else { tc_fence_before(); mbar_arrive(bar_tempty); }
+                    process(v1, c0 + 16);
+                }
+            }
             }
             tphase ^= 1;
         }
@@ -423,6 +443,8 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     TcArgs a;
     a.C = g.C; a.ldc = g.ldc; a.c_seg_stride = n_seg > 1 ? g.c_seg_stride : 0; a.c_seg_off = g.c_seg_off; a.c_col_off = g.c_col_off;
     a.n_seg = n_seg; a.seg_len = seg_len; a.N_out = g.N; a.K = g.K;
+    static const bool pipe = getenv("DPE_TC_EPI_PIPE") != nullptr;
+    a.pipe = pipe;
     a.epi = g.epi; a.nch = g.epi ? g.n_ch : 1;
     a.r = g.r; a.R = g.R; a.spa = g.spa; a.envw = g.envw; a.n_el = g.n_el; a.n_ion = g.n_ion; a.el_base = g.el_base;
     if (a.epi) {
