@@ -318,13 +318,11 @@ __global__ void __launch_bounds__(128, 4) k_det_warp(int N, int C, int n_det, lo
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long bd = blockIdx.x * 4L + wib;
     if (bd >= n_mat) return;
-    const int per_warp_doubles = N * 32 + (LAP ? (N * (N + 1) + N * 16 + N * 17 + 1) / 2 + 2 : 0);
+    const int per_warp_doubles = N * 32 + (LAP ? (N * 16 + 2 * (N * 16 + 16) + 2 * 272 + 8) / 2 + 2 : 0);
     double *aug = smd + (size_t)wib * per_warp_doubles;      // [N][32]
-    float *Ainv = reinterpret_cast<float *>(aug + N * 32);    // [N][N+1]
-    float *dA = Ainv + N * (N + 1);                           // [N][16]
-    float *P = dA + N * 16;                                   // [N][17]
-    dA = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(dA) + 15) & ~uintptr_t(15));   // float4 loads
-    if (LAP) P = dA + N * 16;
+    float *Ainv = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(aug + N * 32) + 15) & ~uintptr_t(15));   // [N][16], float4 loads
+    float *dA = Ainv + N * 16;                                // [2][N*16 + 16]
+    float *P = dA + 2 * (N * 16 + 16);                        // [2][16][17]
     const long b = bd / n_det;
     const int dt = (int)(bd - b * n_det);
     const int cols = n_det * N, K = C - 2, W = LAP ? 2 * N : N;
@@ -378,79 +376,97 @@ __global__ void __launch_bounds__(128, 4) k_det_warp(int N, int C, int n_det, lo
     if (lane == 0) { out[0] = (float)logdet; out[1] = sign; }
     if (!LAP) return;
 
-    for (int o = 0; o < N; ++o)
-        if (lane < N) Ainv[o * (N + 1) + lane] = (float)aug[o * 32 + N + lane];
-    for (int e = lane; e < N * 16; e += 32) dA[e] = 0.f;       // zero padding of the 16-float rows
-    // element slots (hoisted index math): e = lane + 32 s -> (i, o)
-    int src_off[8], d16[8], p17[8], t17[8];
-#pragma unroll
-    for (int sl = 0; sl < 8; ++sl) {
-        int e = lane + 32 * sl;
-        int i = e / N, o = e - i * N;
-        bool ok = e < N * N;
-        src_off[sl] = ok ? (i * C) * cols + o : -1;
-        d16[sl] = i * 16 + o;
-        p17[sl] = i * 17 + o;
-        t17[sl] = o * 17 + i;
-    }
+    // ---- tangent stage: two tangent directions per warp (half-warps), lane = column q of P_k -------------------------
+    // P_k[o][q] = sum_i Ainv[o][i] dA_k[i][q]: per i one conflict-free LDS of dA_k[i][q] and four broadcast LDS.128 of the
+    // row Ainv[:, i] feed 16 FMAs (the earlier row-strip version was shared-memory-bandwidth bound, ncu 84 %).
+    float *AinvT = Ainv;                       // [N][16]: AinvT[i][o] = Ainv[o][i], zero padded to 16 columns
+    const int HS = N * 16 + 16;                // half-warp stride of the dA staging buffers (keeps the halves on distinct banks)
+    float *dAh = dA;                           // [2][N][16] (+16)
+    float *Ps = P;                             // [2][16][17]
+    for (int e = lane; e < N * 16; e += 32) AinvT[e] = 0.f;
+    for (int e = lane; e < 2 * HS; e += 32) dAh[e] = 0.f;
     __syncwarp();
-    // The record holds lap' = tr(Ainv lapA) - sum_k tr(P_k^2) + sum_k tr(P_k)^2: for an ill-conditioned matrix P_k is
-    // nearly rank one, tr(P_k^2) ~ tr(P_k)^2, and the two sums cancel to many digits -- they are accumulated in FP64
-    // from the same FP32 P entries so that the cancellation is exact with respect to those entries.
+    for (int i = 0; i < N; ++i)
+        if (lane < N) AinvT[i * 16 + lane] = (float)aug[lane * 32 + N + i];
+    __syncwarp();
+    const int half = lane >> 4, q = lane & 15;
+    // element slots of this half-warp's matrix: e = q + 16 s -> (i, o)
+    constexpr int NS = 16;                     // 16 * 16 >= N * N for N <= 16
+    int src_off[NS], dst_off[NS];
+#pragma unroll
+    for (int sl = 0; sl < NS; ++sl) {
+        int e = q + 16 * sl;
+        int i = e / N, o = e - i * N;
+        src_off[sl] = e < N * N ? (i * C) * cols + o : -1;
+        dst_off[sl] = half * HS + i * 16 + o;
+    }
+    // lap' = tr(Ainv lapA) - sum_k tr(P_k^2) + sum_k tr(P_k)^2: for an ill-conditioned matrix P_k is nearly rank one,
+    // tr(P_k^2) ~ tr(P_k)^2, and the two sums cancel to many digits -- they are accumulated in FP64 from the same FP32 P
+    // entries so that the cancellation is exact with respect to those entries.
     double part = 0.0;
-#pragma unroll
-    for (int sl = 0; sl < 8; ++sl)
-        if (src_off[sl] >= 0) {
-            int e = lane + 32 * sl, i = e / N, o = e - i * N;
-            part = fma((double)Ainv[o * (N + 1) + i], (double)mob[(long)(C - 1) * cols + src_off[sl]], part);
-        }
+    for (int e = lane; e < N * N; e += 32) {
+        int i = e / N, o = e - i * N;
+        part = fma((double)AinvT[i * 16 + o], (double)mob[((long)i * C + C - 1) * cols + o], part);
+    }
     const double lap = warp_sum_d(part);
-    const int orow = lane >> 1, q0 = (lane & 1) * 8;
-    const bool strip = orow < N;
     double t2 = 0.0, sum_g2 = 0.0;
-    float ld[8];                                     // software pipeline: dA_{k+1} travels while P_k is computed
-#pragma unroll
-    for (int sl = 0; sl < 8; ++sl) ld[sl] = src_off[sl] >= 0 ? mob[(long)cols + src_off[sl]] : 0.f;
-    for (int k = 0; k < K; ++k) {
+    const int n_it = (K + 1) >> 1;
+    float ld[NS];                              // software pipeline: the next pair of tangent matrices travels during the FMAs
+    {
+        const int k = half;
         const float *mk = mob + (long)(1 + k) * cols;
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) ld[sl] = (src_off[sl] >= 0 && k < K) ? mk[src_off[sl]] : 0.f;
+    }
+    for (int it = 0; it < n_it; ++it) {
+        const int k = 2 * it + half;
+        const bool kv = k < K;
         __syncwarp();
 #pragma unroll
-        for (int sl = 0; sl < 8; ++sl)
-            if (src_off[sl] >= 0) dA[d16[sl]] = ld[sl];
-        if (k + 1 < K) {
+        for (int sl = 0; sl < NS; ++sl)
+            if (src_off[sl] >= 0) dAh[dst_off[sl]] = ld[sl];
+        if (it + 1 < n_it) {
+            const int kn = k + 2;
+            const float *mk = mob + (long)(1 + kn) * cols;
 #pragma unroll
-            for (int sl = 0; sl < 8; ++sl)
-                if (src_off[sl] >= 0) ld[sl] = mk[(long)cols + src_off[sl]];
+            for (int sl = 0; sl < NS; ++sl) ld[sl] = (src_off[sl] >= 0 && kn < K) ? mk[src_off[sl]] : 0.f;
         }
         __syncwarp();
-        double gkd = 0.0;
-        if (strip) {
-            float acc[8];
+        float acc[16];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) acc[t] = 0.f;
-            const float *arow = Ainv + orow * (N + 1);
-            for (int i = 0; i < N; ++i) {
-                const float av = arow[i];
-                const float4 x0 = *reinterpret_cast<const float4 *>(dA + i * 16 + q0);
-                const float4 x1 = *reinterpret_cast<const float4 *>(dA + i * 16 + q0 + 4);
-                acc[0] = fmaf(av, x0.x, acc[0]); acc[1] = fmaf(av, x0.y, acc[1]); acc[2] = fmaf(av, x0.z, acc[2]); acc[3] = fmaf(av, x0.w, acc[3]);
-                acc[4] = fmaf(av, x1.x, acc[4]); acc[5] = fmaf(av, x1.y, acc[5]); acc[6] = fmaf(av, x1.z, acc[6]); acc[7] = fmaf(av, x1.w, acc[7]);
-            }
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                P[orow * 17 + q0 + t] = acc[t];
-                if (q0 + t == orow) gkd = (double)acc[t];
-            }
+        for (int o = 0; o < 16; ++o) acc[o] = 0.f;
+        const float *dcol = dAh + half * HS + q;
+        for (int i = 0; i < N; ++i) {
+            const float x = dcol[i * 16];
+            const float4 a0 = *reinterpret_cast<const float4 *>(AinvT + i * 16), a1 = *reinterpret_cast<const float4 *>(AinvT + i * 16 + 4);
+            const float4 a2 = *reinterpret_cast<const float4 *>(AinvT + i * 16 + 8), a3 = *reinterpret_cast<const float4 *>(AinvT + i * 16 + 12);
+            acc[0] = fmaf(a0.x, x, acc[0]); acc[1] = fmaf(a0.y, x, acc[1]); acc[2] = fmaf(a0.z, x, acc[2]); acc[3] = fmaf(a0.w, x, acc[3]);
+            acc[4] = fmaf(a1.x, x, acc[4]); acc[5] = fmaf(a1.y, x, acc[5]); acc[6] = fmaf(a1.z, x, acc[6]); acc[7] = fmaf(a1.w, x, acc[7]);
+            acc[8] = fmaf(a2.x, x, acc[8]); acc[9] = fmaf(a2.y, x, acc[9]); acc[10] = fmaf(a2.z, x, acc[10]); acc[11] = fmaf(a2.w, x, acc[11]);
+            acc[12] = fmaf(a3.x, x, acc[12]); acc[13] = fmaf(a3.y, x, acc[13]); acc[14] = fmaf(a3.z, x, acc[14]); acc[15] = fmaf(a3.w, x, acc[15]);
         }
-        const float gk = (float)warp_sum_d(gkd);
-        sum_g2 = fma((double)gk, (double)gk, sum_g2);       // with the rounded value that the record stores
-        if (lane == 0) out[3 + k] = gk;
-        __syncwarp();
+        // column q of P_k sits in acc[0..N): publish it, then read row q for tr(P^2) = sum_{o,q} P[o][q] P[q][o]
+        float diag = 0.f;
+        float *pcol = Ps + half * 272 + q;
 #pragma unroll
-        for (int sl = 0; sl < 8; ++sl)
-            if (src_off[sl] >= 0) t2 = fma((double)P[p17[sl]], (double)P[t17[sl]], t2);
+        for (int o = 0; o < 16; ++o) {
+            pcol[o * 17] = acc[o];
+            if (o == q) diag = acc[o];
+        }
+        double gkd = (q < N && kv) ? (double)diag : 0.0;
+        for (int sh = 8; sh; sh >>= 1) gkd += __shfl_xor_sync(0xffffffffu, gkd, sh);    // within the half-warp
+        const float gk = (float)gkd;
+        if (kv) sum_g2 = (q == 0) ? fma((double)gk, (double)gk, sum_g2) : sum_g2;
+        if (q == 0 && kv) out[3 + k] = gk;
+        __syncwarp();
+        if (q < N && kv) {
+            const float *prow = Ps + half * 272 + q * 17;
+#pragma unroll
+            for (int o = 0; o < 16; ++o) t2 = fma((double)acc[o], (double)prow[o], t2);
+        }
     }
     t2 = warp_sum_d(t2);
+    sum_g2 = warp_sum_d(sum_g2);
     if (lane == 0) out[2] = (float)(lap + (sum_g2 - t2));
 }
 
@@ -467,7 +483,7 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStr
     int blocks = Bc * d.n_dets;
     static const bool force_generic = getenv("DPE_DET_GENERIC") != nullptr;   // debug knob
     if (N <= 16 && !force_generic) {
-        const size_t per_warp = ((size_t)N * 32 + (lap ? ((size_t)N * (N + 1) + N * 16 + N * 17 + 1) / 2 + 2 : 0)) * sizeof(double);
+        const size_t per_warp = ((size_t)N * 32 + (lap ? ((size_t)N * 16 + 2 * ((size_t)N * 16 + 16) + 2 * 272 + 8) / 2 + 2 : 0)) * sizeof(double);
         const long n_mat = (long)blocks;
         if (lap) k_det_warp<true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det);
         else k_det_warp<false><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det);

@@ -524,7 +524,8 @@ __global__ void __launch_bounds__(CV_FG * CV_CB) k_conv_dense(int N, int C, int 
                                                               const float *__restrict__ pw, float *__restrict__ x, int ldx,
                                                               int col_ee) {
     extern __shared__ __align__(16) float sm[];
-    const int NP = (N + 3) & ~3;
+    int NP = (N + 3) & ~3;
+    if ((NP & 7) == 0) NP += 4;                   // row stride = 4 (mod 8) floats: the 8 features of a quarter warp hit distinct banks
     float *A_s = sm;                              // [j][f][NP]   w(i, j, f), i fastest
     float *B_s = A_s + N * CV_FG * NP;            // [j][cl][f]
     const int n_fg = emb / CV_FG, n_cb = (C + CV_CB - 1) / CV_CB;
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(CV_FG * CV_CB) k_conv_dense(int N, int C, int 
     const float *bp = B_s + cl * CV_FG + f;
     float *xp = x + ((b * N) * (long)C + c) * ldx + col_ee + f0 + f;
     const long xstride = (long)C * ldx;
-    for (int ig = 0; ig < NP; ig += 4) {
+    for (int ig = 0; ig < N; ig += 4) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         for (int j = 0; j < N; ++j) {
             const float4 w = *reinterpret_cast<const float4 *>(ap + j * CV_FG * NP + ig);
@@ -650,7 +651,8 @@ int launch_conv(dpe_model *m, int it, const float *r, int Bc, int C, const float
         k_conv_fwd<<<Bc, 256, (size_t)N * emb * sizeof(float), s>>>(N, emb, p.dE, hm, pw, ei, x, ldx, p.d_in);
     } else {
         if (emb % CV_FG) return set_error(DPE_ERR_UNSUPPORTED, "conv: emb_dim=%d must be a multiple of %d", emb, CV_FG);
-        const int NP = (N + 3) & ~3;
+        int NP = (N + 3) & ~3;
+        if ((NP & 7) == 0) NP += 4;
         size_t smem = ((size_t)N * CV_FG * NP + (size_t)N * CV_CB * CV_FG) * sizeof(float);
         if (smem > 48 * 1024) DPE_CUDA(cudaFuncSetAttribute(k_conv_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n_cb = (C + CV_CB - 1) / CV_CB;
