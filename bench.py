@@ -307,13 +307,20 @@ def run_ours(args):
     roofline = None
     if prof:
         ach = prof["flops"] / (prof["ms"] * 1e-3) / 1e12
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"       # dram__bytes_read.sum + dram__bytes_write.sum of the same launch shape (ncu --set full)
+        if tf.exists():
+            t = json.loads(tf.read_text()).get(f"{args.molecule}:{B}:{prof['kernel']}")
+            traffic = t["dram_bytes_per_launch"] if t else None
         roofline = {"bound": "tensor", "kernel": prof["kernel"], "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
-                    "frac": ach / tensor_peak, "traffic": None,
+                    "frac": ach / tensor_peak, "traffic": traffic,
+                    "launch_shape": "largest-FLOP launches of the class (main embedding layers: rows = walkers x electrons x (3N+2), K = 320, N_out = 256)",
+                    "class_achieved": prof["class_flops"] / (prof["class_ms"] * 1e-3) / 1e12, "class_launches": prof["class_count"],
                     "peak_source": f"{pk['source']}: bf16 {pk['bf16_tflops']} TF/s / 6 (3xTF32 FP32-accurate tensor peak)",
                     "launches": prof["count"], "avg_launch_ms": prof["ms"] / max(prof["count"], 1),
                     "algorithmic_flops_per_launch": prof["flops"] / max(prof["count"], 1),
                     "frac_of_fp32_simt_peak": ach / fp32_peak, "fp32_simt_peak": fp32_peak,
-                    "share_of_eloc_time": prof["ms"] / prof["total_ms"]}
+                    "share_of_eloc_time": prof["class_ms"] / prof["total_ms"]}
     flop_eval = FLOP_PER_EVAL.get(args.molecule)
     cpu = None if args.no_cpu_baseline else cpu_port_throughput(args.molecule, args.cpu_seconds)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

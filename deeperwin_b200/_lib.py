@@ -56,6 +56,7 @@ SIGNATURES = {
     "dpe_get_gemm_path": (C.c_int, [_P]),
     "dpe_profile_enable": (C.c_int, [_P, C.c_int32]),
     "dpe_profile_collect": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "dpe_profile_launches": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_int32)]),
     "dpe_launch_count": (C.c_int64, [_P]),
 }
 

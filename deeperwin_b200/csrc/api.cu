@@ -535,6 +535,19 @@ int dpe_profile_collect(dpe_model *m, int32_t klass, double *ms, int64_t *count,
     return DPE_OK;
 }
 
+int dpe_profile_launches(dpe_model *m, int32_t klass, double *ms_arr, double *flops_arr, int32_t cap, int32_t *n) {
+    if (!m || !ms_arr || !flops_arr || !n) return set_error(DPE_ERR_ARG, "profile_launches: null argument");
+    DPE_CUDA(cudaDeviceSynchronize());
+    *n = 0;
+    for (auto &r : *m->prof) {
+        if (r.klass != klass || *n >= cap) continue;
+        float t = 0.f;
+        DPE_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms_arr[*n] = t; flops_arr[*n] = r.flops; ++*n;
+    }
+    return DPE_OK;
+}
+
 int64_t dpe_launch_count(const dpe_model *m) { return m ? m->launches : 0; }
 
 }  // extern "C"

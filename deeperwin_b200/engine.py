@@ -205,6 +205,12 @@ class Engine:
         torch.cuda.synchronize(self.device)
         check(self.lib.dpe_profile_enable(self.handle, 0), "dpe_profile_enable")
         best = None
+        launches = {}
+        for klass, name in self.GEMM_CLASSES.items():
+            cap = 256
+            ms_arr, fl_arr, n = (C.c_double * cap)(), (C.c_double * cap)(), C.c_int32()
+            check(self.lib.dpe_profile_launches(self.handle, klass, ms_arr, fl_arr, cap, C.byref(n)), "dpe_profile_launches")
+            launches[name] = [(ms_arr[i], fl_arr[i]) for i in range(n.value)]
         for klass, name in self.GEMM_CLASSES.items():
             ms, cnt, fl = C.c_double(), C.c_int64(), C.c_double()
             check(self.lib.dpe_profile_collect(self.handle, klass, C.byref(ms), C.byref(cnt), C.byref(fl)), "dpe_profile_collect")
@@ -212,4 +218,10 @@ class Engine:
                 best = dict(kernel=name, ms=ms.value, count=cnt.value, flops=fl.value)
         if best:
             best["total_ms"] = e0.elapsed_time(e1)
+            best["class_ms"], best["class_count"], best["class_flops"] = best["ms"], best["count"], best["flops"]
+            # the dominant launch SHAPE of that class: the launches with the largest algorithmic FLOP count
+            per = launches[best["kernel"]]
+            fmax = max(f for _, f in per)
+            top = [(t, f) for t, f in per if f >= 0.999 * fmax]
+            best.update(ms=sum(t for t, _ in top), count=len(top), flops=sum(f for _, f in top))
         return best

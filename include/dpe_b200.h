@@ -172,6 +172,8 @@ int dpe_get_gemm_path(const dpe_model *m);
  * number of launches and their algorithmic FLOPs (2*M*N*K each); it then clears the records. */
 int dpe_profile_enable(dpe_model *m, int32_t on);
 int dpe_profile_collect(dpe_model *m, int32_t klass, double *ms, int64_t *count, double *flops);
+/* Same, but per launch: fills ms_arr / flops_arr (capacity cap) in launch order and sets *n; does not clear the records. */
+int dpe_profile_launches(dpe_model *m, int32_t klass, double *ms_arr, double *flops_arr, int32_t cap, int32_t *n);
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t dpe_launch_count(const dpe_model *m);
 
