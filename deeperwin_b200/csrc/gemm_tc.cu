@@ -51,6 +51,7 @@ struct TcArgs {
     const float *r, *R, *spa, *envw;               // walker positions [n_seg, n_el, 3], ions [I,3], softplus(alpha) / weights [I, N_out]
     int n_el, n_ion, el_base;                      // electron index of local group 0 of a segment (0 for spin-up, n_up for spin-down)
     int pipe;                                      // software-pipelined TMEM loads in the epilogue
+    int spt;                                       // segments per tile (> 1: short segments, e.g. the spin blocks of a forward pass, are packed into one tile)
 };
 
 // ---------------------------------------------------------------------------------------- PTX wrappers
@@ -135,7 +136,7 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = (a.K + TC_BK - 1) / TC_BK;
-    const long n_tiles = (long)a.n_seg * a.n_rt * a.n_ft;
+    const long n_tiles = (long)((a.n_seg + a.spt - 1) / a.spt) * a.n_rt * a.n_ft;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -160,7 +161,7 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         // ================================ TMA producer ================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t tx = 2 * TC_W_BYTES + a.nmma * TC_ROWB;
+            const uint32_t tx = 2 * TC_W_BYTES + (a.spt > 1 ? a.tile_rows : a.nmma) * TC_ROWB;
             for (long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int ft = (int)(t % a.n_ft);
                 const long rest = t / a.n_ft;
@@ -171,7 +172,7 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     mbar_expect_tx(&bar_full[stage], tx);
                     tma_load_2d(st, &map_wh, &bar_full[stage], kb * TC_BK, ft * TC_FEAT);
                     tma_load_2d(st + TC_W_BYTES, &map_wl, &bar_full[stage], kb * TC_BK, ft * TC_FEAT);
-                    tma_load_3d(st + 2 * TC_W_BYTES, &map_x, &bar_full[stage], kb * TC_BK, rt * a.tile_rows, seg);
+                    tma_load_3d(st + 2 * TC_W_BYTES, &map_x, &bar_full[stage], kb * TC_BK, a.spt > 1 ? 0 : rt * a.tile_rows, seg * a.spt);
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -255,7 +256,17 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * 256;
             // one 16-column chunk of this thread's feature: plain store or fused envelope (epi == 2)
             auto process = [&](const uint32_t (&v)[16], int c0) {
-                if (a.epi == 0) {
+                if (a.epi == 0 && a.spt > 1) {
+                    if (f_ok) {       // packed short segments: column -> (segment, row in segment)
+                        int sl = c0 / a.seg_len, mm = c0 - sl * a.seg_len;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (c0 + j < a.tile_rows && seg * a.spt + sl < a.n_seg)
+                                a.C[((long)(seg * a.spt + sl) * a.c_seg_stride + a.c_seg_off + mm) * a.ldc + a.c_col_off + f] = __uint_as_float(v[j]);
+                            if (++mm == a.seg_len) { mm = 0; ++sl; }
+                        }
+                    }
+                } else if (a.epi == 0) {
                     if (f_ok) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
@@ -445,6 +456,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     a.n_seg = n_seg; a.seg_len = seg_len; a.N_out = g.N; a.K = g.K;
     static const bool pipe = getenv("DPE_TC_EPI_PIPE") != nullptr;
     a.pipe = pipe;
+    a.spt = 1;
     a.epi = g.epi; a.nch = g.epi ? g.n_ch : 1;
     a.r = g.r; a.R = g.R; a.spa = g.spa; a.envw = g.envw; a.n_el = g.n_el; a.n_ion = g.n_ion; a.el_base = g.el_base;
     if (a.epi) {
@@ -455,6 +467,13 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
         a.tile_rows = gpt * a.nch;
         a.nmma = (a.tile_rows + 15) / 16 * 16;
         a.n_rt = n_rt;
+    } else if (n_seg > 1 && 2 * seg_len <= 256) {
+        // short segments (forward pass: the spin block of one walker): pack several per tile with a 3-D TMA box
+        a.spt = 256 / seg_len;
+        if (a.spt > n_seg) a.spt = n_seg;
+        a.tile_rows = seg_len * a.spt;
+        a.nmma = (a.tile_rows + 15) / 16 * 16;
+        a.n_rt = 1;
     } else {
         const int tiles_min = (seg_len + 255) / 256;
         a.nmma = (((seg_len + tiles_min - 1) / tiles_min) + 15) / 16 * 16;
@@ -468,7 +487,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     const long a_stride_rows = n_seg > 1 ? g.a_seg_stride : seg_len;
     cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)seg_len, (cuuint64_t)n_seg};
     cuuint64_t strides[2] = {(cuuint64_t)g.lda * sizeof(float), (cuuint64_t)a_stride_rows * g.lda * sizeof(float)};
-    cuuint32_t box[3] = {TC_BK, (cuuint32_t)a.nmma, 1};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)(a.spt > 1 ? seg_len : a.nmma), (cuuint32_t)a.spt};
     cuuint32_t es[3] = {1, 1, 1};
     void *base = const_cast<float *>(g.A + (long)g.a_seg_off * g.lda);
     CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -480,7 +499,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
         DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_set = true;
     }
-    long n_tiles = (long)a.n_seg * a.n_rt * a.n_ft;
+    long n_tiles = (long)((a.n_seg + a.spt - 1) / a.spt) * a.n_rt * a.n_ft;
     int grid = (int)(n_tiles < m->n_sm ? n_tiles : m->n_sm);
     k_gemm_tc_3xtf32<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(map_x, w->map_hi, w->map_lo, a);
     m->last_gemm_class = 3;

@@ -57,6 +57,10 @@ check("narrow N=64", 700, 64, 256, 256)
 check("bf-like N=448", 3000, 448, 256, 320)
 check("segmented up (308 of 616)", 0, 448, 256, 320, seg=(9, 308, 616, 0))
 check("segmented dn (308 of 616)", 0, 448, 256, 320, seg=(9, 308, 616, 308))
+check("packed segs 7 of 14", 0, 448, 256, 320, seg=(1000, 7, 14, 0))
+check("packed segs 7 of 14 (dn)", 0, 448, 256, 320, seg=(1000, 7, 14, 7))
+check("packed segs 21 of 42", 0, 1344, 256, 320, seg=(333, 21, 42, 21))
+check("packed segs 2 of 4", 0, 12, 16, 28, seg=(5, 2, 4, 2))
 check("many tiles", 200000, 256, 320, 320)
 
 # timing
