@@ -1,0 +1,57 @@
+"""BASELINE.json configs[2] in miniature: one set of weights shared by several H-chain geometries (weight sharing,
+variational_optimization.py:210-442 picks ONE geometry per step): the same handle must switch geometry per call and
+reproduce the oracle for each; and the segmented / packed GEMM paths of the forward pass agree with the SIMT path."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_shared_weights_over_hchain_geometries():
+    import deeperwin_b200 as dpe
+    from oracle import model as om
+    n_at = 6
+    phys = [dpe.PhysicalConfig(name=f"HChain{n_at}_{a:.2f}", R=[[a * k, 0.0, 0.0] for k in range(n_at)], Z=[1] * n_at,
+                               n_electrons=n_at, n_up=n_at // 2, el_ion_mapping=[0, 2, 4, 1, 3, 5]) for a in np.linspace(1.6, 2.6, 4)]
+    cfg = dpe.Configuration(physical=phys[0].model_dump())
+    f, _, _, params, fixed = dpe.build_log_psi_squared(cfg.model, phys[0], None, None, rng_seed=3, device="cuda:0")
+    gle = dpe.build_local_energy(f, forward_lap=True)
+    d = om.ModelDims(n_el=n_at, n_up=n_at // 2, n_ion=n_at, Z_max=1)
+    p64 = {m: {k: v.double().cpu() for k, v in l.items()} for m, l in params.items()}
+    mc = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=5, initialization="gaussian"))
+    states = [dpe.MCMCState.initialize_around_nuclei(48, p, "gaussian", "el_ion_mapping", dpe.PRNGKey(10 + g), device="cuda:0")
+              for g, p in enumerate(phys)]
+    for epoch in range(2):                                   # round-robin over geometries, as the shared optimisation does
+        for g, p in enumerate(phys):
+            states[g] = mc.run_inter_steps(f, states[g], params, p.n_up, p.n_dn, fixed)
+            st = states[g]
+            e = gle(params, (p.n_up, p.n_dn), st.r, st.R, st.Z, fixed).double().cpu()
+            ref = om.forward_laplacian(p64, d, st.r.double().cpu(), st.R.double().cpu(), p.Z)
+            lp = f(params, p.n_up, p.n_dn, st.r, st.R, st.Z, fixed)[1].double().cpu()
+            assert ((lp - ref["logpsi2"]).abs() / ref["logpsi2"].abs()).median() < 1e-5
+            rel = (e - ref["E_loc"]).abs() / ref["E_loc"].abs().clamp_min(1.0)
+            assert rel.median() < 1e-4, (g, rel.median())
+            assert torch.equal(lp.float(), st.log_psi_sqr.cpu())          # state carries the log psi^2 of ITS geometry
+    assert int(states[0].step_nr) == 10
+
+
+@pytest.mark.parametrize("name", ["LiH", "N2"])
+def test_tensor_core_and_simt_paths_agree(name):
+    """gemm_path 1 (tcgen05 3xTF32) vs gemm_path 0 (FP32 SIMT) on the same walkers: both are FP32-accurate."""
+    import deeperwin_b200 as dpe
+    cfg = dpe.Configuration(physical=dict(name=name))
+    phys = cfg.physical
+    f, _, _, params, fixed = dpe.build_log_psi_squared(cfg.model, phys, None, None, rng_seed=5, device="cuda:0")
+    st = dpe.MCMCState.initialize_around_nuclei(256, phys, "gaussian", "el_ion_mapping", dpe.PRNGKey(1), device="cuda:0")
+    eng = f.engine
+    if eng.lib.dpe_get_gemm_path(eng.handle) != 1:
+        pytest.skip("tensor-core path unavailable")
+    lp1 = f(params, phys.n_up, phys.n_dn, st.r, st.R, st.Z, fixed)[1]      # sets the parameters and the geometry
+    e1 = eng.local_energy(st.r)
+    eng.set_gemm_path(0)
+    lp0 = eng.log_psi_sqr(st.r)[1]
+    e0 = eng.local_energy(st.r)
+    eng.set_gemm_path(1)
+    assert ((lp1 - lp0).abs() / lp0.abs()).median() < 2e-6
+    assert ((e1 - e0).abs() / e0.abs().clamp_min(1.0)).median() < 1e-4
