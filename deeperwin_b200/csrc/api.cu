@@ -339,6 +339,7 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
         for (int it = 0; it < dims->n_iterations && !e; ++it) {
             e = tc_register_weight(m, m->it[it].w_main, m->it[it].k_main, m->it[it].d_out);
             if (!e) e = tc_register_weight(m, m->it[it].w_mean, 2 * m->it[it].d_in, m->it[it].d_out);
+            if (!e && m->it[it].d_in <= 320) e = tc_register_weight(m, m->it[it].h_map.w, m->it[it].d_in, dims->emb_dim);
         }
         const int cols = dims->n_dets * dims->n_el, dl = dims->n_hidden_one_el[dims->n_iterations - 1];
         for (int sp = 0; sp < 2 && !e; ++sp) e = tc_register_weight(m, m->bf_w[sp], dl, cols);

@@ -347,6 +347,178 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Narrow layers (N_out <= 32: the h_map layer of the SchNet convolution, ferminet_embedding.py:156-158).
+// Here the roles are the natural ones, D[m, n] = sum_k X[m, k] Wt[n, k]: MMA M side = 128 activation rows (TMEM lanes),
+// N side = 32 output features, so no tensor lane is wasted on padding features.  Wt_hi / Wt_lo (<= 2 x 40 KB) stay resident
+// in shared memory for the whole kernel; X streams through a 3-stage ring exactly as in the wide kernel (TMA -> splitter
+// -> 12 MMAs of M128 x N32 x K8 per slab); accumulators are double buffered in TMEM (2 x 64 columns), so the epilogue
+// (one thread = one output row = 128 contiguous bytes) overlaps the MMAs of the next tile.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int TR_ROWS = 256;                       // rows per tile (2 x M=128)
+constexpr int TR_N = 32;                           // MMA N
+constexpr int TR_STAGES = 3;
+constexpr int TR_X_BYTES = TR_ROWS * TC_ROWB;      // 16 KB
+constexpr int TR_STAGE_BYTES = 2 * TR_X_BYTES;     // raw->hi, lo
+constexpr int TR_WSLAB = TR_N * TC_ROWB;           // 2 KB per K slab per hi / lo
+constexpr int TR_MAX_KB = 20;                      // K <= 320
+constexpr int TR_SMEM_BYTES = TR_STAGES * TR_STAGE_BYTES + 2 * TR_MAX_KB * TR_WSLAB + 1024 + 1024;
+constexpr int TR_THREADS = 10 * 32;
+
+struct TrArgs {
+    float *C; int ldc, c_col_off;
+    int M, N_out, K;
+};
+
+__global__ void __launch_bounds__(TR_THREADS, 1)
+k_gemm_tc_rows_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
+                      const __grid_constant__ CUtensorMap map_wl, TrArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *w_hi = smem + TR_STAGES * TR_STAGE_BYTES;          // [n_kb][32 rows x 64 B]
+    uint8_t *w_lo = w_hi + TR_MAX_KB * TR_WSLAB;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(w_lo + TR_MAX_KB * TR_WSLAB);
+    uint64_t *bar_full = bars, *bar_split = bars + TR_STAGES, *bar_empty = bars + 2 * TR_STAGES;
+    uint64_t *bar_tfull = bars + 3 * TR_STAGES;                 // [2]
+    uint64_t *bar_tempty = bar_tfull + 2;                       // [2]
+    uint64_t *bar_w = bar_tempty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_w + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_kb = (a.K + TC_BK - 1) / TC_BK;
+    const long n_tiles = ((long)a.M + TR_ROWS - 1) / TR_ROWS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TR_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_split[s], 128); mbar_init(&bar_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], 128); }
+        mbar_init(bar_w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_w, 2 * n_kb * TR_WSLAB);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                tma_load_2d(w_hi + kb * TR_WSLAB, &map_wh, bar_w, kb * TC_BK, 0);
+                tma_load_2d(w_lo + kb * TR_WSLAB, &map_wl, bar_w, kb * TC_BK, 0);
+            }
+            int stage = 0; uint32_t phase = 0;
+            for (long t = blockIdx.x; t < n_tiles; t += gridDim.x)
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    mbar_expect_tx(&bar_full[stage], TR_X_BYTES);
+                    tma_load_3d(smem + stage * TR_STAGE_BYTES, &map_x, &bar_full[stage], kb * TC_BK, (int)(t * TR_ROWS), 0);
+                    if (++stage == TR_STAGES) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TR_N >> 3) << 17) | ((128u >> 4) << 24);
+            mbar_wait(bar_w, 0);
+            int stage = 0; uint32_t phase = 0, tph0 = 0, tph1 = 0;
+            int buf = 0;
+            for (long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(&bar_tempty[buf], (buf ? tph1 : tph0) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&bar_split[stage], phase);
+                    tc_fence_after();
+                    const uint32_t xh = smem_u32(smem + stage * TR_STAGE_BYTES), xl = xh + TR_X_BYTES;
+                    const uint32_t wh = smem_u32(w_hi + kb * TR_WSLAB), wl = smem_u32(w_lo + kb * TR_WSLAB);
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                        const uint32_t ko = kk * 32;
+                        const uint64_t dwh = make_desc_sw64(wh + ko), dwl = make_desc_sw64(wl + ko);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t d = tmem_base + buf * 64 + h * TR_N;
+                            const uint64_t dxh = make_desc_sw64(xh + h * 128 * TC_ROWB + ko), dxl = make_desc_sw64(xl + h * 128 * TC_ROWB + ko);
+                            tc_mma_tf32(d, dxh, dwl, idesc, (kb | kk) ? 1u : 0u);
+                            tc_mma_tf32(d, dxl, dwh, idesc, 1u);
+                            tc_mma_tf32(d, dxh, dwh, idesc, 1u);
+                        }
+                    }
+                    tc_commit(&bar_empty[stage]);
+                    if (++stage == TR_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&bar_tfull[buf]);
+                if (buf) tph1 ^= 1; else tph0 ^= 1;
+                buf ^= 1;
+            }
+        }
+    } else if (warp < 6) {
+        const int tid = threadIdx.x - 64;
+        int stage = 0; uint32_t phase = 0;
+        for (long t = blockIdx.x; t < n_tiles; t += gridDim.x)
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(&bar_full[stage], phase);
+                float4 *xh = reinterpret_cast<float4 *>(smem + stage * TR_STAGE_BYTES);
+                float4 *xl = reinterpret_cast<float4 *>(smem + stage * TR_STAGE_BYTES + TR_X_BYTES);
+#pragma unroll
+                for (int i = tid; i < TR_X_BYTES / 16; i += 128) {
+                    float4 v = xh[i], h, l;
+                    h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+                    l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+                    xh[i] = h;
+                    xl[i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&bar_split[stage]);
+                if (++stage == TR_STAGES) { stage = 0; phase ^= 1; }
+            }
+    } else {
+        const int q = warp & 3;
+        uint32_t tph0 = 0, tph1 = 0;
+        int buf = 0;
+        for (long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            mbar_wait(&bar_tfull[buf], buf ? tph1 : tph0);
+            tc_fence_after();
+            uint32_t v0[16], v1[16], v2[16], v3[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64;
+            tmem_ld16(taddr, v0); tmem_ld16(taddr + 16, v1); tmem_ld16(taddr + 32, v2); tmem_ld16(taddr + 48, v3);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bar_tempty[buf]);
+            auto store_row = [&](long row, const uint32_t (&lo)[16], const uint32_t (&hi)[16]) {
+                if (row >= a.M) return;
+                float *dst = a.C + row * a.ldc + a.c_col_off;
+                if (a.N_out == 32 && ((a.ldc | a.c_col_off) & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(__uint_as_float(lo[4 * j]), __uint_as_float(lo[4 * j + 1]), __uint_as_float(lo[4 * j + 2]), __uint_as_float(lo[4 * j + 3]));
+                        *reinterpret_cast<float4 *>(dst + 16 + 4 * j) = make_float4(__uint_as_float(hi[4 * j]), __uint_as_float(hi[4 * j + 1]), __uint_as_float(hi[4 * j + 2]), __uint_as_float(hi[4 * j + 3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j < a.N_out) dst[j] = __uint_as_float(lo[j]);
+                        if (16 + j < a.N_out) dst[16 + j] = __uint_as_float(hi[j]);
+                    }
+                }
+            };
+            const long r0 = t * TR_ROWS + q * 32 + lane;
+            store_row(r0, v0, v1);            // rows 0..127 of the tile (accumulator columns 0..31)
+            store_row(r0 + 128, v2, v3);      // rows 128..255 (columns 32..63)
+            if (buf) tph1 ^= 1; else tph0 ^= 1;
+            buf ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    }
+}
+
 // W[K][N] (row-major) -> Wt_hi / Wt_lo [N][K] (K-major), tf32-rounded halves
 __global__ void k_split_transpose(const float *__restrict__ W, int K, int N, float *__restrict__ hi, float *__restrict__ lo) {
     long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -388,12 +560,15 @@ struct TcState {
     std::vector<TcWeight> weights;
 };
 
-static int encode_w(CUtensorMap *map, float *ptr, int N, int K) {
+static int encode_w(CUtensorMap *map, float *ptr, int N, int K, int box_rows = TC_FEAT);
+static int launch_gemm_tc_rows(dpe_model *m, const GemmArgs &g, const struct TcWeight *w, cudaStream_t s);
+
+static int encode_w(CUtensorMap *map, float *ptr, int N, int K, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return set_error(DPE_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
-    cuuint32_t box[2] = {TC_BK, TC_FEAT};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -409,8 +584,9 @@ int tc_register_weight(dpe_model *m, const float *W, int K, int N) {
     DPE_CUDA(cudaMalloc(&w.hi, (size_t)K * N * sizeof(float)));
     DPE_CUDA(cudaMalloc(&w.lo, (size_t)K * N * sizeof(float)));
     int e;
-    if ((e = encode_w(&w.map_hi, w.hi, N, K))) return e;
-    if ((e = encode_w(&w.map_lo, w.lo, N, K))) return e;
+    const int box_rows = N <= TR_N ? TR_N : TC_FEAT;      // narrow layers use the rows kernel (Wt resident in shared memory)
+    if ((e = encode_w(&w.map_hi, w.hi, N, K, box_rows))) return e;
+    if ((e = encode_w(&w.map_lo, w.lo, N, K, box_rows))) return e;
     st->weights.push_back(w);
     return DPE_OK;
 }
@@ -443,6 +619,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
         if (c.W == g.W && c.K == g.K && c.N == g.N && c.fresh) { w = &c; break; }
     if (!w) return DPE_ERR_UNSUPPORTED;
     if ((g.K & 3) || (g.lda & 3) || (reinterpret_cast<size_t>(g.A) & 15) || g.ldw != g.N) return DPE_ERR_UNSUPPORTED;
+    if (g.N <= TR_N) return launch_gemm_tc_rows(m, g, w, s);
     // A and C must use the same segmentation (true for every caller in api.cu)
     if (g.a_seg_len != g.c_seg_len) return DPE_ERR_UNSUPPORTED;
     const int seg_len = g.a_seg_len < g.M ? g.a_seg_len : g.M;
@@ -502,6 +679,34 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     long n_tiles = (long)((a.n_seg + a.spt - 1) / a.spt) * a.n_rt * a.n_ft;
     int grid = (int)(n_tiles < m->n_sm ? n_tiles : m->n_sm);
     k_gemm_tc_3xtf32<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(map_x, w->map_hi, w->map_lo, a);
+    m->last_gemm_class = 3;
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
+static int launch_gemm_tc_rows(dpe_model *m, const GemmArgs &g, const TcWeight *w, cudaStream_t s) {
+    if (g.a_seg_len < g.M || g.c_seg_len < g.M || g.a_seg_off || g.c_seg_off) return DPE_ERR_UNSUPPORTED;   // plain rows only
+    if (g.K > TR_MAX_KB * TC_BK || g.epi) return DPE_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return DPE_ERR_UNSUPPORTED;
+    CUtensorMap map_x;
+    cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.M, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)g.lda * sizeof(float), (cuuint64_t)g.M * g.lda * sizeof(float)};
+    cuuint32_t box[3] = {TC_BK, TR_ROWS, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(g.A), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(DPE_ERR_CUDA, "cuTensorMapEncodeTiled(X rows) failed: %d", (int)r);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc_rows_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM_BYTES));
+        attr_set = true;
+    }
+    TrArgs a;
+    a.C = g.C; a.ldc = g.ldc; a.c_col_off = g.c_col_off; a.M = g.M; a.N_out = g.N; a.K = g.K;
+    long n_tiles = ((long)g.M + TR_ROWS - 1) / TR_ROWS;
+    int grid = (int)(n_tiles < m->n_sm ? n_tiles : m->n_sm);
+    k_gemm_tc_rows_3xtf32<<<grid, TR_THREADS, TR_SMEM_BYTES, s>>>(map_x, w->map_hi, w->map_lo, a);
     m->last_gemm_class = 3;
     DPE_LAUNCH_CHECK(m);
     return DPE_OK;

@@ -57,14 +57,17 @@ check("narrow N=64", 700, 64, 256, 256)
 check("bf-like N=448", 3000, 448, 256, 320)
 check("segmented up (308 of 616)", 0, 448, 256, 320, seg=(9, 308, 616, 0))
 check("segmented dn (308 of 616)", 0, 448, 256, 320, seg=(9, 308, 616, 308))
+check("narrow N=32 K=256", 100000, 32, 256, 320)
+check("narrow N=32 K=8", 3000, 32, 8, 44)
+check("narrow N=8 K=16", 777, 8, 16, 28)
+check("narrow N=32 K=320 ragged", 1001, 32, 320, 320)
 check("packed segs 7 of 14", 0, 448, 256, 320, seg=(1000, 7, 14, 0))
 check("packed segs 7 of 14 (dn)", 0, 448, 256, 320, seg=(1000, 7, 14, 7))
 check("packed segs 21 of 42", 0, 1344, 256, 320, seg=(333, 21, 42, 21))
-check("packed segs 2 of 4", 0, 12, 16, 28, seg=(5, 2, 4, 2))
 check("many tiles", 200000, 256, 320, 320)
 
 # timing
-for M, N, K, lda in ((2_523_136, 256, 320, 320), (1_261_568, 448, 256, 320)):
+for M, N, K, lda in ((2_523_136, 256, 320, 320), (1_261_568, 448, 256, 320), (2_523_136, 32, 256, 320)):
     A = torch.randn(M, lda, device="cuda")
     W = torch.randn(K, N, device="cuda") * 0.05
     for pth in (0, 1):
