@@ -153,6 +153,10 @@ static void plan(const dpe_dims &d, int Bc, int C, WsLayout &L) {
     for (int it = 0; it < d.n_iterations; ++it) L.ei_it[it] = take((size_t)Bc * N * CE * d_eion_in(d, it));
     L.mo = take(rows * d.n_dets * N);
     L.det = take((size_t)Bc * d.n_dets * (C > 1 ? 3 * N + 3 : 2));
+    {   // tf32-split Ainv^T tiles for the tensor-core determinant stage (Laplacian mode)
+        const size_t NP = det_tc_pad(N, d.n_dets);
+        L.ainv = take(C > 1 && NP <= 64 ? (size_t)Bc * d.n_dets * NP * NP * 2 : 0);
+    }
     L.epot = take(Bc);
     L.lp = take(Bc);
     L.total_chunk = off;
@@ -273,7 +277,7 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
         env_fused = env_fused && fused;
     }
     if (!env_fused && (e = launch_envelope(m, r, Bc, C, mo, s))) return e;
-    if ((e = launch_det(m, Bc, C, mo, det, s))) return e;
+    if ((e = launch_det(m, Bc, C, mo, det, C > 1 ? (float *)(ws + L.ainv) : nullptr, s))) return e;
     if ((e = launch_combine(m, Bc, C, det, epot, phase, logpsi2, grad, ekin, eloc, epot_out, s))) return e;
     return DPE_OK;
 }

@@ -40,7 +40,7 @@ struct GemmArgs {
 
 // Workspace layout for one chunk of Bc walkers with C channels (byte offsets).
 struct WsLayout {
-    size_t x[2], hm, mean, add, pw, ei, mo, det, epot, lp, total_chunk;
+    size_t x[2], hm, mean, add, pw, ei, mo, det, ainv, epot, lp, total_chunk;
     size_t ei_it[DPE_MAX_ITER];   // offsets (bytes) of the per-iteration el-ion convolution blocks
     size_t pw_it[DPE_MAX_ITER];
     // per-call (full batch) scratch for the Metropolis step
@@ -106,7 +106,16 @@ int launch_prepare_geometry(dpe_model *m, cudaStream_t s);
 
 // orbitals_det.cu
 int launch_envelope(dpe_model *m, const float *r, int Bc, int C, float *mo, cudaStream_t s);
-int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStream_t s);
+int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *ainv, cudaStream_t s);
+// padded size of the Ainv^T tiles of the tensor-core determinant stage: room for the (det * N) mod 4 column shift that
+// keeps the TMA box start 16-byte aligned, rounded up to the 16-float K slab
+inline int det_tc_pad(int N, int n_det) {
+    int omax = 0;
+    for (int dt = 0; dt < n_det && dt < 4; ++dt) omax = ((dt * N) & 3) > omax ? ((dt * N) & 3) : omax;
+    return (N + omax + 15) & ~15;
+}
+// det_tc.cu: traces of (dA_k Ainv) and (dA_k Ainv)^2 on the tensor cores; DPE_ERR_UNSUPPORTED if the shape does not fit
+int launch_det_trace_tc(dpe_model *m, int Bc, int C, const float *mo, const float *ainv_hi, const float *ainv_lo, int NP, float *det, cudaStream_t s);
 int launch_combine(dpe_model *m, int Bc, int C, const float *det, const float *epot, float *phase, float *logpsi2,
                    float *grad, float *ekin, float *eloc, float *epot_out, cudaStream_t s);
 

@@ -98,6 +98,12 @@ __device__ __forceinline__ double group_sum_d(double v, double *red, int tid) {
     return s;
 }
 
+__device__ __forceinline__ float det_rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 template <int T>
 __device__ __forceinline__ void group_sync() {
     if (T == 32) __syncwarp(); else __syncthreads();
@@ -116,7 +122,8 @@ __device__ __forceinline__ float group_sum(float v, float *red, int tid) {
 }
 
 template <int T, bool LAP>
-__global__ void __launch_bounds__(T, T == 64 ? 6 : 3) k_det(int N, int C, int n_det, const float *__restrict__ mo, float *__restrict__ det) {
+__global__ void __launch_bounds__(T, T == 64 ? 6 : 3) k_det(int N, int C, int n_det, const float *__restrict__ mo, float *__restrict__ det,
+                                                                  float *__restrict__ ainv_hi, float *__restrict__ ainv_lo, int NP) {
     // The factorisation runs in FP64 (O(N^3) against the O(3N * N^3) FP32 tangent stage).
     extern __shared__ double smd[];
     const int W = LAP ? 2 * N : N;       // augmented width
@@ -200,6 +207,18 @@ __global__ void __launch_bounds__(T, T == 64 ? 6 : 3) k_det(int N, int C, int n_
     if (tid == 0) { out[0] = (float)logdet; out[1] = sign; }
     if (!LAP) return;
 
+    if (ainv_hi) {     // factor-only mode: the tensor-core trace kernel (det_tc.cu) consumes AinvT[i][sh + q] = Ainv[q][i], tf32-split, zero padded
+        float *oh = ainv_hi + bd * (long)NP * NP, *ol = ainv_lo + bd * (long)NP * NP;
+        const int sh = (dt * N) & 3;     // the TMA box starts at the 16-byte aligned column below det * N
+        for (int e = tid; e < NP * NP; e += T) {
+            const int i = e / NP, q = e - i * NP - sh;
+            const float v = (i < N && q >= 0 && q < N) ? (float)aug[q * S + N + i] : 0.f;
+            const float hi = det_rna_tf32(v);
+            oh[e] = hi;
+            ol[e] = det_rna_tf32(v - hi);
+        }
+        return;
+    }
     // ---- tangent stage: P_k = Ainv dA_k in 8 x 8 register tiles (one tile per thread, nb x nb <= T tiles) -------------
     // Rows of AinvT / dA are stored permuted, [first halves of the 8-column chunks | second halves], so that the float4
     // loads of a quarter warp hit distinct banks; padded rows / columns are zero, which zeroes the padding of P.
@@ -313,12 +332,13 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 template <bool LAP>
 __global__ void __launch_bounds__(128, 4) k_det_warp(int N, int C, int n_det, long n_mat, const float *__restrict__ mo,
-                                                   float *__restrict__ det) {
+                                                   float *__restrict__ det, float *__restrict__ ainv_hi,
+                                                   float *__restrict__ ainv_lo, int NP) {
     extern __shared__ double smd[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long bd = blockIdx.x * 4L + wib;
     if (bd >= n_mat) return;
-    const int per_warp_doubles = N * 32 + (LAP ? (N * 16 + 2 * (N * 16 + 16) + 2 * 272 + 8) / 2 + 2 : 0);
+    const int per_warp_doubles = N * 32 + ((LAP && !ainv_hi) ? (N * 16 + 2 * (N * 16 + 16) + 2 * 272 + 8) / 2 + 2 : 0);
     double *aug = smd + (size_t)wib * per_warp_doubles;      // [N][32]
     float *Ainv = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(aug + N * 32) + 15) & ~uintptr_t(15));   // [N][16], float4 loads
     float *dA = Ainv + N * 16;                                // [2][N*16 + 16]
@@ -376,6 +396,18 @@ __global__ void __launch_bounds__(128, 4) k_det_warp(int N, int C, int n_det, lo
     if (lane == 0) { out[0] = (float)logdet; out[1] = sign; }
     if (!LAP) return;
 
+    if (ainv_hi) {     // factor-only mode (see k_det)
+        float *oh = ainv_hi + bd * (long)NP * NP, *ol = ainv_lo + bd * (long)NP * NP;
+        const int sh = (dt * N) & 3;     // the TMA box starts at the 16-byte aligned column below det * N
+        for (int e = lane; e < NP * NP; e += 32) {
+            const int i = e / NP, q = e - i * NP - sh;
+            const float v = (i < N && q >= 0 && q < N) ? (float)aug[q * 32 + N + i] : 0.f;
+            const float hi = det_rna_tf32(v);
+            oh[e] = hi;
+            ol[e] = det_rna_tf32(v - hi);
+        }
+        return;
+    }
     // ---- tangent stage: two tangent directions per warp (half-warps), lane = column q of P_k -------------------------
     // P_k[o][q] = sum_i Ainv[o][i] dA_k[i][q]: per i one conflict-free LDS of dA_k[i][q] and four broadcast LDS.128 of the
     // row Ainv[:, i] feed 16 FMAs (the earlier row-strip version was shared-memory-bandwidth bound, ncu 84 %).
@@ -470,10 +502,16 @@ __global__ void __launch_bounds__(128, 4) k_det_warp(int N, int C, int n_det, lo
     if (lane == 0) out[2] = (float)(lap + (sum_g2 - t2));
 }
 
-int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStream_t s) {
+int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *ainv, cudaStream_t s) {
     const dpe_dims &d = m->dims;
     const int N = d.n_el;
     const bool lap = C > 1;
+    const int NP = det_tc_pad(N, d.n_dets);
+    static const bool force_generic = getenv("DPE_DET_GENERIC") != nullptr;   // debug knobs
+    static const bool force_simt = getenv("DPE_DET_SIMT") != nullptr;
+    // Laplacian mode on the tensor-core path: FP64 factorisation here, traces of (dA_k Ainv) and (dA_k Ainv)^2 in det_tc.cu
+    const bool tc = lap && ainv && NP <= 64 && m->gemm_path == 1 && !force_simt;
+    float *ah = tc ? ainv : nullptr, *al = tc ? ainv + (size_t)Bc * d.n_dets * NP * NP : nullptr;
     const size_t nq = (N + 7) & ~7, nb = nq / 8;
     size_t aug_bytes = (size_t)N * ((lap ? 2 * N : N) + 1) * sizeof(double);
     const size_t alias_bytes = (2 * (size_t)N * nq + nb * nb * 64) * sizeof(float);
@@ -481,22 +519,35 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, cudaStr
     aug_bytes = (aug_bytes + 15) & ~(size_t)15;
     size_t smem = aug_bytes + ((lap ? (size_t)N * nq : 0) + 16) * sizeof(float) + 10 * sizeof(double);
     int blocks = Bc * d.n_dets;
-    static const bool force_generic = getenv("DPE_DET_GENERIC") != nullptr;   // debug knob
     if (N <= 16 && !force_generic) {
-        const size_t per_warp = ((size_t)N * 32 + (lap ? ((size_t)N * 16 + 2 * ((size_t)N * 16 + 16) + 2 * 272 + 8) / 2 + 2 : 0)) * sizeof(double);
+        const size_t per_warp = ((size_t)N * 32 + ((lap && !tc) ? ((size_t)N * 16 + 2 * ((size_t)N * 16 + 16) + 2 * 272 + 8) / 2 + 2 : 0)) * sizeof(double);
         const long n_mat = (long)blocks;
-        if (lap) k_det_warp<true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det);
-        else k_det_warp<false><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det);
+        if (lap) k_det_warp<true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, ah, al, NP);
+        else k_det_warp<false><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, nullptr, nullptr, NP);
     } else {
         // 64 threads: one 8 x 8 tile of P per thread (N <= 64 -> at most 64 tiles) and one column of mo per thread
         if (smem > 48 * 1024) {
             DPE_CUDA(cudaFuncSetAttribute(k_det<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             DPE_CUDA(cudaFuncSetAttribute(k_det<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
-        if (lap) k_det<64, true><<<blocks, 64, smem, s>>>(N, C, d.n_dets, mo, det);
-        else k_det<128, false><<<blocks, 128, smem, s>>>(N, C, d.n_dets, mo, det);
+        if (lap) k_det<64, true><<<blocks, 64, smem, s>>>(N, C, d.n_dets, mo, det, ah, al, NP);
+        else k_det<128, false><<<blocks, 128, smem, s>>>(N, C, d.n_dets, mo, det, nullptr, nullptr, NP);
     }
     DPE_LAUNCH_CHECK(m);
+    if (tc) {
+        int e = launch_det_trace_tc(m, Bc, C, mo, ah, al, NP, det, s);
+        if (e == DPE_ERR_UNSUPPORTED) {      // shape outside the tensor-core kernel: redo the whole stage on CUDA cores
+            if (N <= 16 && !force_generic) {
+                const size_t per_warp = ((size_t)N * 32 + ((size_t)N * 16 + 2 * ((size_t)N * 16 + 16) + 2 * 272 + 8) / 2 + 2) * sizeof(double);
+                k_det_warp<true><<<(int)((blocks + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, (long)blocks, mo, det, nullptr, nullptr, NP);
+            } else {
+                k_det<64, true><<<blocks, 64, smem, s>>>(N, C, d.n_dets, mo, det, nullptr, nullptr, NP);
+            }
+            DPE_LAUNCH_CHECK(m);
+        } else if (e) {
+            return e;
+        }
+    }
     return DPE_OK;
 }
 
