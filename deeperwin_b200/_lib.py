@@ -14,7 +14,7 @@ class DpeDims(C.Structure):
     _fields_ = [("n_el", C.c_int32), ("n_up", C.c_int32), ("n_ion", C.c_int32), ("n_iterations", C.c_int32),
                 ("n_hidden_one_el", C.c_int32 * DPE_MAX_ITER), ("n_hidden_two_el", C.c_int32 * DPE_MAX_ITER),
                 ("emb_dim", C.c_int32), ("n_ion_features", C.c_int32), ("n_dets", C.c_int32),
-                ("z_min", C.c_int32), ("z_max", C.c_int32)]
+                ("z_min", C.c_int32), ("z_max", C.c_int32), ("use_taos", C.c_int32)]
 
 
 class DpeMcmcConfig(C.Structure):
@@ -40,6 +40,7 @@ SIGNATURES = {
     "dpe_param_leaf": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dpe_model_set_params": (C.c_int, [_P, _P, C.c_int64, _P]),
     "dpe_model_set_geometry": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32), _P]),
+    "dpe_model_set_tao_cache": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "dpe_workspace_bytes": (C.c_size_t, [_P, C.c_int32, C.c_int32]),
     "dpe_log_psi_sqr": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "dpe_local_energy": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),

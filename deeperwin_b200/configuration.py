@@ -134,10 +134,42 @@ class EnvelopeOrbitalsConfig(ConfigBaseclass):
         return self
 
 
+class TransferableAtomicOrbitalsConfig(ConfigBaseclass):
+    """configuration.py:732-775 of the reference.  The hot path evaluates the orbitals from the per-geometry cache
+    (backflows, exponents); the widths / depths of the geometry-only nets are accepted and unused here."""
+    name: Literal["taos"] = "taos"
+    envelope_width: int = 64
+    envelope_depth: int = 2
+    backflow_width: int = 256
+    backflow_depth: int = 2
+    symmetrize_exponent_mlp: bool = False
+    antisymmetrize_backflow_mlp: bool = False
+    use_prefactors: bool = False
+    use_exponentials: bool = True
+    use_el_ion_embedding: bool = False
+    use_squared_envelope_input: bool = False
+    use_separate_ion_sum_for_envelopes: bool = False
+
+    @model_validator(mode="after")
+    def _supported(self):
+        _only(self.use_exponentials, True, "orbitals.transferable_atomic_orbitals.use_exponentials")
+        _only(self.use_el_ion_embedding, False, "orbitals.transferable_atomic_orbitals.use_el_ion_embedding")
+        _only(self.use_separate_ion_sum_for_envelopes, False, "orbitals.transferable_atomic_orbitals.use_separate_ion_sum_for_envelopes")
+        _only(self.use_prefactors, False, "orbitals.transferable_atomic_orbitals.use_prefactors")
+        return self
+
+
 class OrbitalsConfigFermiNet(ConfigBaseclass):
     envelope_orbitals: Optional[EnvelopeOrbitalsConfig] = EnvelopeOrbitalsConfig()
-    transferable_atomic_orbitals: None = None
+    transferable_atomic_orbitals: Optional[TransferableAtomicOrbitalsConfig] = None
     n_determinants: int = 32
+
+    @model_validator(mode="after")
+    def _one_head(self):
+        # orbital_net.py:69-96 multiplies the enabled heads; the path implements one at a time
+        if (self.envelope_orbitals is None) == (self.transferable_atomic_orbitals is None):
+            raise NotImplementedError("exactly one of orbitals.envelope_orbitals / orbitals.transferable_atomic_orbitals must be set")
+        return self
     determinant_schema: Literal["full_det"] = "full_det"
 
 

@@ -40,6 +40,7 @@ static int validate_dims(const dpe_dims &d) {
     if (d.emb_dim < 8 || d.emb_dim > 32 || (d.emb_dim & 7)) return set_error(DPE_ERR_UNSUPPORTED, "emb_dim=%d must be a multiple of 8 in [8, 32]", d.emb_dim);
     if (d.n_ion_features < 1 || d.n_dets < 1) return set_error(DPE_ERR_UNSUPPORTED, "n_ion_features / n_dets must be positive");
     if (d.z_max < d.z_min) return set_error(DPE_ERR_ARG, "z_max < z_min");
+    if (d.use_taos != 0 && d.use_taos != 1) return set_error(DPE_ERR_ARG, "use_taos must be 0 or 1");
     for (int it = 0; it < d.n_iterations; ++it) {
         if (d.n_hidden_one_el[it] < 4 || (d.n_hidden_one_el[it] & 3)) return set_error(DPE_ERR_UNSUPPORTED, "n_hidden_one_el[%d]=%d must be a multiple of 4", it, d.n_hidden_one_el[it]);
         if (it + 1 < d.n_iterations && (d.n_hidden_two_el[it] < 4 || d.n_hidden_two_el[it] > 32 || (d.n_hidden_two_el[it] & 3)))
@@ -75,6 +76,7 @@ static void build_leaves(dpe_model *m) {
             add_leaf(m, dE, d2); add_leaf(m, 1, d2);                // h_el_ion
         }
     }
+    if (d.use_taos) return;       // TAO heads: backflows / exponents come from the geometry cache (dpe_model_set_tao_cache)
     int cols = d.n_dets * d.n_el, dl = d.n_hidden_one_el[d.n_iterations - 1];
     add_leaf(m, dl, cols); add_leaf(m, dl, cols);                   // bf_up, bf_dn
     for (int q = 0; q < 4; ++q) add_leaf(m, d.n_ion, cols);         // alpha_up, alpha_dn, weights_up, weights_dn
@@ -108,6 +110,7 @@ static void bind_views(dpe_model *m) {
         p.him = dv; dv += (size_t)d.n_ion * p.dE;
         dv = m->derived + align_up((dv - m->derived) * sizeof(float)) / sizeof(float);
     }
+    if (d.use_taos) return;
     m->bf_w[0] = next(); m->bf_w[1] = next();
     m->alpha[0] = next(); m->alpha[1] = next();
     m->env_w[0] = next(); m->env_w[1] = next();
@@ -157,6 +160,7 @@ static void plan(const dpe_dims &d, int Bc, int C, WsLayout &L) {
         const size_t NP = det_tc_pad(N, d.n_dets);
         L.ainv = take(C > 1 && NP <= 64 ? (size_t)Bc * d.n_dets * NP * NP * 2 : 0);
     }
+    L.tao_g = take(d.use_taos ? rows * d.n_ion * d.n_dets * N : 0);      // per-ion orbital pre-factors h_i . b[ion, orb, det]
     L.epot = take(Bc);
     L.lp = take(Bc);
     L.total_chunk = off;
@@ -257,8 +261,16 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
         if ((e = launch_act(m, x[cur ^ 1], ldx, Bc * N, C, p.d_out, p.h_el.b, add, N, s))) return e;
         cur ^= 1;
     }
-    // backflow factors (envelope_orbitals.py:46-75): spin-up / spin-down electrons use different matrices
     const int cols = d.n_dets * N, dl = d.n_hidden_one_el[d.n_iterations - 1];
+    if (d.use_taos) {
+        // transferable atomic orbitals (transferable_atomic_orbitals.py:287-349): one GEMM against the cached backflow matrix
+        // for all electrons (both spin types use slice 0, :255-260), then the exponential envelopes and the sum over ions
+        float *tg = (float *)(ws + L.tao_g);
+        const int gc = d.n_ion * cols;
+        if ((e = gemm(m, plain_gemm(x[cur], ldx, m->tao_w, gc, tg, gc, rows, gc, dl), s))) return e;
+        if ((e = launch_tao_orbitals(m, r, Bc, C, tg, mo, s))) return e;
+    } else {
+    // backflow factors (envelope_orbitals.py:46-75): spin-up / spin-down electrons use different matrices
     bool env_fused = true;
     for (int sp = 0; sp < 2; ++sp) {
         GemmArgs g = plain_gemm(x[cur], ldx, m->bf_w[sp], cols, mo, cols, Bc * (sp ? D : U) * C, cols, dl);
@@ -277,6 +289,7 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
         env_fused = env_fused && fused;
     }
     if (!env_fused && (e = launch_envelope(m, r, Bc, C, mo, s))) return e;
+    }
     if ((e = launch_det(m, Bc, C, mo, det, C > 1 ? (float *)(ws + L.ainv) : nullptr, s))) return e;
     if ((e = launch_combine(m, Bc, C, det, epot, phase, logpsi2, grad, ekin, eloc, epot_out, s))) return e;
     return DPE_OK;
@@ -285,6 +298,7 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
 static int run_batched(dpe_model *m, const float *r, int B, int C, char *ws, size_t ws_bytes, float *phase, float *logpsi2,
                        float *grad, float *ekin, float *eloc, float *epot_out, cudaStream_t s) {
     if (!m->params_set || !m->geom_set) return set_error(DPE_ERR_STATE, "set_params and set_geometry must be called first");
+    if (m->dims.use_taos && !m->tao_set) return set_error(DPE_ERR_STATE, "this model uses transferable atomic orbitals: set_tao_cache must be called first");
     const dpe_dims &d = m->dims;
     int chunk = max_chunk(d, C, ws_bytes, B);
     if (chunk < 1) return set_error(DPE_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one walker", ws_bytes);
@@ -326,6 +340,12 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
     if (ce == cudaSuccess) ce = cudaMalloc(&m->derived, m->derived_floats * sizeof(float));
     if (ce == cudaSuccess) ce = cudaMalloc(&m->R_dev, (size_t)dims->n_ion * 3 * sizeof(float));
     if (ce == cudaSuccess) ce = cudaMalloc(&m->Z_dev, (size_t)dims->n_ion * sizeof(float));
+    if (dims->use_taos) {
+        const size_t gc = (size_t)dims->n_ion * dims->n_dets * dims->n_el;
+        if (ce == cudaSuccess) ce = cudaMalloc(&m->tao_w, (size_t)dims->n_hidden_one_el[dims->n_iterations - 1] * gc * sizeof(float));
+        if (ce == cudaSuccess) ce = cudaMalloc(&m->tao_ex[0], 2 * gc * sizeof(float));
+        if (ce == cudaSuccess) m->tao_ex[1] = m->tao_ex[0] + gc;
+    }
     if (ce != cudaSuccess) {
         int rc = check_cuda(ce, "cudaMalloc(model)");
         dpe_model_destroy(m);
@@ -346,7 +366,8 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
             if (!e && m->it[it].d_in <= 320) e = tc_register_weight(m, m->it[it].h_map.w, m->it[it].d_in, dims->emb_dim);
         }
         const int cols = dims->n_dets * dims->n_el, dl = dims->n_hidden_one_el[dims->n_iterations - 1];
-        for (int sp = 0; sp < 2 && !e; ++sp) e = tc_register_weight(m, m->bf_w[sp], dl, cols);
+        if (dims->use_taos) { if (!e) e = tc_register_weight(m, m->tao_w, dl, dims->n_ion * cols); }
+        else for (int sp = 0; sp < 2 && !e; ++sp) e = tc_register_weight(m, m->bf_w[sp], dl, cols);
         if (e) { tc_destroy(m); cudaGetLastError(); }      // no tensor-core path: dense layers stay on the FP32 SIMT GEMM
         m->gemm_path = m->tc ? 1 : 0;
     }
@@ -357,6 +378,7 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
 void dpe_model_destroy(dpe_model *m) {
     if (!m) return;
     cudaFree(m->params); cudaFree(m->derived); cudaFree(m->R_dev); cudaFree(m->Z_dev);
+    cudaFree(m->tao_w); cudaFree(m->tao_ex[0]);
     tc_destroy(m);
     if (m->prof) {
         for (auto &r : *m->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -414,6 +436,19 @@ int dpe_model_set_geometry(dpe_model *m, const float *R_host, const int32_t *Z_h
     DPE_CUDA(cudaMemcpy(m->Z_dev, Zf, (size_t)d.n_ion * sizeof(float), cudaMemcpyHostToDevice));
     m->geom_set = true;
     if (m->params_set) return launch_prepare_geometry(m, s);
+    return DPE_OK;
+}
+
+int dpe_model_set_tao_cache(dpe_model *m, const float *backflows_up_dev, const float *backflows_dn_dev,
+                            const float *exponents_up_dev, const float *exponents_dn_dev, void *stream) {
+    if (!m || !backflows_up_dev || !backflows_dn_dev || !exponents_up_dev || !exponents_dn_dev)
+        return set_error(DPE_ERR_ARG, "set_tao_cache: null argument");
+    if (!m->dims.use_taos) return set_error(DPE_ERR_STATE, "set_tao_cache: the model was created with envelope orbitals (use_taos = 0)");
+    cudaStream_t s = (cudaStream_t)stream;
+    int e = launch_tao_pack(m, backflows_up_dev, backflows_dn_dev, exponents_up_dev, exponents_dn_dev, s);
+    if (e) return e;
+    if ((e = tc_refresh_weights(m, s))) return e;
+    m->tao_set = true;
     return DPE_OK;
 }
 

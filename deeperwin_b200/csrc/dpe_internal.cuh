@@ -40,7 +40,7 @@ struct GemmArgs {
 
 // Workspace layout for one chunk of Bc walkers with C channels (byte offsets).
 struct WsLayout {
-    size_t x[2], hm, mean, add, pw, ei, mo, det, ainv, epot, lp, total_chunk;
+    size_t x[2], hm, mean, add, pw, ei, mo, det, ainv, tao_g, epot, lp, total_chunk;
     size_t ei_it[DPE_MAX_ITER];   // offsets (bytes) of the per-iteration el-ion convolution blocks
     size_t pw_it[DPE_MAX_ITER];
     // per-call (full batch) scratch for the Metropolis step
@@ -62,6 +62,9 @@ struct dpe_model {
     const float *h_ion_emb;                       // [V, F]
     const float *bf_w[2], *alpha[2], *env_w[2];   // up, dn
     float *sp_alpha[2];                           // softplus(alpha) [n_ion, n_det*n_el]
+    float *tao_w;                                 // TAO: [d_last, n_ion * n_det * n_el] backflow matrix, column = (ion, det, orbital)
+    float *tao_ex[2];                             // TAO: exponents [n_ion, n_det * n_el] for same-spin / different-spin (electron, orbital)
+    bool tao_set;
     float *R_dev;  // [n_ion,3]
     float *Z_dev;  // [n_ion] as float
     float e_ion_ion;
@@ -106,6 +109,9 @@ int launch_prepare_geometry(dpe_model *m, cudaStream_t s);
 
 // orbitals_det.cu
 int launch_envelope(dpe_model *m, const float *r, int Bc, int C, float *mo, cudaStream_t s);
+// TAO orbitals (transferable_atomic_orbitals.py:287-349): mo = sum_ion g[ion] * exp(-exponent * |r_i - R_ion|) with the product rule
+int launch_tao_pack(dpe_model *m, const float *bf_up, const float *bf_dn, const float *ex_up, const float *ex_dn, cudaStream_t s);
+int launch_tao_orbitals(dpe_model *m, const float *r, int Bc, int C, const float *g, float *mo, cudaStream_t s);
 int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *ainv, cudaStream_t s);
 // padded size of the Ainv^T tiles of the tensor-core determinant stage: room for the (det * N) mod 4 column shift that
 // keeps the TMA box start 16-byte aligned, rounded up to the 16-float K slab

@@ -79,6 +79,113 @@ int launch_envelope(dpe_model *m, const float *r, int Bc, int C, float *mo, cuda
 }
 
 // ------------------------------------------------------------------------------------------------
+// transferable atomic orbitals (orbitals/transferable_atomic_orbitals.py:287-349, cache branch; defaults
+// use_el_ion_embedding = False, use_separate_ion_sum_for_envelopes = False, use_exponentials = True, full_det):
+//   mo[i, d, k] = sum_J (h_i . b[J, k, d]) exp(-x[J, k, s(i, k), d] |r_i - R_J|)        k over [up orbitals | dn orbitals],
+//   s = 0 if electron i and orbital k have the same spin, else 1 (:316-345)
+// k_tao_pack lays the cache out for the kernels: tao_w[a][J*cols + d*N + k] = backflows_spin(k)[J, k_s, 0, d, a] (slice 0 for both
+// spin types, :255-260), tao_ex[s][J*cols + d*N + k] = exponents_spin(k)[J, k_s, s, d].
+// ------------------------------------------------------------------------------------------------
+__global__ void k_tao_pack(const float *__restrict__ bf_up, const float *__restrict__ bf_dn, const float *__restrict__ ex_up,
+                           const float *__restrict__ ex_dn, int I, int N, int U, int nd, int dl, float *__restrict__ w,
+                           float *__restrict__ ex_same, float *__restrict__ ex_diff) {
+    const int cols = nd * N;
+    const long gc = (long)I * cols, total = (long)(dl + 1) * gc;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long a = idx / gc;                 // embedding feature, or dl for the exponent rows
+        const long c = idx - a * gc;
+        const int J = (int)(c / cols), dk = (int)(c - (long)J * cols), d = dk / N, k = dk - d * N;
+        const bool up = k < U;
+        const int ks = up ? k : k - U, n_orb = up ? U : N - U;
+        const long base = (((long)J * n_orb + ks) * 2) * nd;          // [J][ks][spin type 0][d = 0]
+        if (a < dl) {
+            w[a * gc + c] = (up ? bf_up : bf_dn)[(base + d) * dl + a];
+        } else {
+            const float *ex = up ? ex_up : ex_dn;
+            ex_same[c] = ex[base + d];
+            ex_diff[c] = ex[base + nd + d];
+        }
+    }
+}
+
+int launch_tao_pack(dpe_model *m, const float *bf_up, const float *bf_dn, const float *ex_up, const float *ex_dn, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    const int dl = d.n_hidden_one_el[d.n_iterations - 1];
+    long total = (long)(dl + 1) * d.n_ion * d.n_dets * d.n_el;
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    k_tao_pack<<<(int)blocks, 256, 0, s>>>(bf_up, bf_dn, ex_up, ex_dn, d.n_ion, d.n_el, d.n_up, d.n_dets, dl, m->tao_w, m->tao_ex[0], m->tao_ex[1]);
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
+// One thread per (walker, electron, det*N + orbital); ions outer (the envelope of an ion is computed once), channels inner;
+// the sum over ions accumulates in `mo` (first ion writes).  Product rule with e = exp(-x d): grad_i e = -x e (r_i - R_J)/d,
+// lap e = e (x^2 - 2 x / d); only the three own-electron tangent channels and the Laplacian channel get extra terms.
+__global__ void __launch_bounds__(256) k_tao_orbitals(const float *__restrict__ r, const float *__restrict__ R, int Bc, int N, int U,
+                                                       int I, int C, int cols, const float *__restrict__ ex_same,
+                                                       const float *__restrict__ ex_diff, const float *__restrict__ g,
+                                                       float *__restrict__ mo) {
+    const long total = (long)Bc * N * cols;
+    const long ldg = (long)I * cols;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int col = idx % cols;
+        const long bi = idx / cols;
+        const int i = bi % N, k = col % N;
+        const float *ex = ((i < U) == (k < U)) ? ex_same : ex_diff;
+        const float *ri = r + bi * 3;
+        float *p = mo + bi * (long)C * cols + col;
+        const int ci = 1 + 3 * i;
+        for (int J = 0; J < I; ++J) {
+            const float dx = ri[0] - R[J * 3], dy = ri[1] - R[J * 3 + 1], dz = ri[2] - R[J * 3 + 2];
+            const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+            const float x = ex[(long)J * cols + col];
+            const float e = expf(-x * d);
+            const float *gp = g + bi * (long)C * ldg + (long)J * cols + col;
+            if (C == 1) {
+                const float o = __fmul_rn(gp[0], e);              // no FMA contraction: same bits as the value channel below
+                p[0] = J ? __fadd_rn(p[0], o) : o;
+                continue;
+            }
+            const float inv = 1.f / d, ge = -x * e * inv;
+            const float e1x = ge * dx, e1y = ge * dy, e1z = ge * dz;
+            const float el = e * (x * x - 2.f * x * inv);
+            const float bf0 = gp[0];
+            const float t0 = gp[(long)ci * ldg], t1 = gp[(long)(ci + 1) * ldg], t2 = gp[(long)(ci + 2) * ldg];
+            const float lap_extra = el * bf0 + 2.f * (e1x * t0 + e1y * t1 + e1z * t2);
+            constexpr int UB = 8;
+            for (int c0 = 0; c0 < C; c0 += UB) {
+                float v[UB], acc[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u)
+                    if (c0 + u < C) { v[u] = gp[(long)(c0 + u) * ldg]; acc[u] = J ? p[(long)(c0 + u) * cols] : 0.f; }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int c = c0 + u;
+                    if (c < C) {
+                        float o = __fmul_rn(v[u], e);
+                        if (c >= ci && c < ci + 3) o += (c == ci ? e1x : (c == ci + 1 ? e1y : e1z)) * bf0;
+                        if (c == C - 1) o += lap_extra;
+                        p[(long)c * cols] = __fadd_rn(acc[u], o);
+                    }
+                }
+            }
+        }
+    }
+}
+
+int launch_tao_orbitals(dpe_model *m, const float *r, int Bc, int C, const float *g, float *mo, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    int cols = d.n_dets * d.n_el;
+    long total = (long)Bc * d.n_el * cols;
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 32) blocks = 148L * 32;
+    k_tao_orbitals<<<(int)blocks, 256, 0, s>>>(r, m->R_dev, Bc, d.n_el, d.n_up, d.n_ion, C, cols, m->tao_ex[0], m->tao_ex[1], g, mo);
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // determinants: one group of T threads per (walker, determinant)
 //   forward:    sign, log|det|                                 (jnp.linalg.slogdet, wavefunction.py:69)
 //   Laplacian:  A^-1, g_k = tr(A^-1 dA_k), lap = tr(A^-1 lapA) - sum_k tr((A^-1 dA_k)^2)

@@ -688,7 +688,7 @@ int launch_prepare_params(dpe_model *m, cudaStream_t s) {
         DPE_CUDA(cudaMemcpyAsync(p.w_mean, w + (size_t)p.d_in * p.d_out, 2 * p.d_in * row, cudaMemcpyDeviceToDevice, s));
     }
     long n = (long)d.n_ion * d.n_dets * d.n_el;
-    for (int sp = 0; sp < 2; ++sp) {
+    for (int sp = 0; sp < 2 && !d.use_taos; ++sp) {
         k_softplus<<<(int)((n + 255) / 256), 256, 0, s>>>(m->alpha[sp], m->sp_alpha[sp], n);
         DPE_LAUNCH_CHECK(m);
     }

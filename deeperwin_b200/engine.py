@@ -16,7 +16,7 @@ EMB = "wf/fermi_net_embedding"
 ORB = "wf/~/orbitals/envelope_orbitals"
 
 
-def canonical_leaves(n_iterations: int) -> List[Tuple[str, str]]:
+def canonical_leaves(n_iterations: int, use_taos: bool = False) -> List[Tuple[str, str]]:
     """(haiku module path, leaf name) in the flat order documented in include/dpe_b200.h."""
     leaves = [("wf/~/input/h_ion", "embeddings")]
     for it in range(n_iterations):
@@ -27,6 +27,8 @@ def canonical_leaves(n_iterations: int) -> List[Tuple[str, str]]:
         if it < n_iterations - 1:
             for nm in ("h_same", "h_diff", "h_el_ion"):
                 leaves += [(f"{EMB}/{nm}_{it}/linear_0", "w"), (f"{EMB}/{nm}_{it}/linear_0", "b")]
+    if use_taos:      # TAO heads: nothing per walker is trainable here, the cache carries backflows / exponents
+        return leaves
     leaves += [(f"{ORB}/bf_up/linear_0", "w"), (f"{ORB}/bf_dn/linear_0", "w")]
     leaves += [(ORB, k) for k in ("alpha_up", "alpha_dn", "weights_up", "weights_dn")]
     return leaves
@@ -38,7 +40,7 @@ def _ptr(t: Optional[torch.Tensor]):
 
 class Engine:
     def __init__(self, *, n_el, n_up, n_ion, n_iterations, n_hidden_one_el, n_hidden_two_el, emb_dim, n_ion_features,
-                 n_dets, z_min, z_max, device="cuda:0", workspace_gb: float = 48.0):
+                 n_dets, z_min, z_max, use_taos: bool = False, device="cuda:0", workspace_gb: float = 48.0):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("deeperwin_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -50,13 +52,18 @@ class Engine:
         for i, v in enumerate(n_hidden_two_el):
             d.n_hidden_two_el[i] = v
         d.emb_dim, d.n_ion_features, d.n_dets, d.z_min, d.z_max = emb_dim, n_ion_features, n_dets, z_min, z_max
+        d.use_taos = int(bool(use_taos))
+        self.use_taos = bool(use_taos)
+        self.n_dets, self.d_last = n_dets, list(n_hidden_one_el)[n_iterations - 1]
+        self._tao_sig = None
+        self._tao_keep = None
         self.dims = d
         self.n_el, self.n_up, self.n_ion = n_el, n_up, n_ion
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):
             check(self.lib.dpe_model_create(C.byref(d), C.byref(self.handle)), "dpe_model_create")
         self.n_params = self.lib.dpe_param_count(self.handle)
-        self.leaves = canonical_leaves(n_iterations)
+        self.leaves = canonical_leaves(n_iterations, self.use_taos)
         assert len(self.leaves) == self.lib.dpe_param_leaf_count(self.handle)
         self.leaf_shapes = []
         for i in range(len(self.leaves)):
@@ -110,6 +117,32 @@ class Engine:
             check(self.lib.dpe_model_set_geometry(self.handle, Rn.ctypes.data_as(C.POINTER(C.c_float)),
                                                   Zn.ctypes.data_as(C.POINTER(C.c_int32)), self._stream()), "dpe_model_set_geometry")
         self._geom_sig = sig
+
+    def set_tao_cache(self, cache: Optional[Dict]):
+        """fixed_params["cache"]["taos"] of the reference (wavefunction.py:164-209, orbital_net.py:84-95):
+        {"backflows": [up, dn], "exponents": [up, dn]} with shapes [I, n_orb, 2, n_det, emb] / [I, n_orb, 2, n_det]."""
+        if not self.use_taos:
+            return
+        if not cache or "backflows" not in cache or "exponents" not in cache:
+            raise NotImplementedError('this model evaluates transferable atomic orbitals from fixed_params["cache"]["taos"] '
+                                      "(backflows, exponents); the geometry-only nets that fill the cache are not part of the hot path")
+        bfs, exs = list(cache["backflows"]), list(cache["exponents"])
+        sig = tuple((t.data_ptr(), t._version) for t in bfs + exs)
+        if sig == self._tao_sig:
+            return
+        n_dn = self.n_el - self.n_up
+        dev = []
+        for t, n_orb, tail in ((bfs[0], self.n_up, (self.n_dets, self.d_last)), (bfs[1], n_dn, (self.n_dets, self.d_last)),
+                               (exs[0], self.n_up, (self.n_dets,)), (exs[1], n_dn, (self.n_dets,))):
+            want = (self.n_ion, n_orb, 2) + tail
+            if tuple(t.shape) != want:
+                raise ValueError(f"TAO cache entry has shape {tuple(t.shape)}, expected {want}")
+            dev.append(t.to(device=self.device, dtype=torch.float32).contiguous())
+        with torch.cuda.device(self.device):
+            check(self.lib.dpe_model_set_tao_cache(self.handle, _ptr(dev[0]), _ptr(dev[1]), _ptr(dev[2]), _ptr(dev[3]), self._stream()),
+                  "dpe_model_set_tao_cache")
+        self._tao_keep = dev       # the pack kernel runs asynchronously on the stream
+        self._tao_sig = sig
 
     def workspace(self, n_walkers: int, mode: int) -> torch.Tensor:
         need = min(self.lib.dpe_workspace_bytes(self.handle, n_walkers, mode), self.workspace_cap)

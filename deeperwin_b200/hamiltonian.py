@@ -23,6 +23,7 @@ def build_local_energy(log_psi_squared, is_complex=False, is_periodic=False, inc
             raise ValueError(f"model was built for n_up={engine.n_up}, n_dn={engine.n_el - engine.n_up}")
         engine.set_params(trainable_params)
         engine.set_geometry(R, Z)
+        engine.set_tao_cache(((fixed_params or {}).get("cache") or {}).get("taos"))
         return engine.local_energy(r, with_aux=with_aux)
 
     get_local_energy.engine = engine

@@ -197,6 +197,7 @@ class MetropolisHastingsMonteCarlo:
         sq = (lambda x: x[0]) if split_axis else (lambda x: x)
         engine.set_params(params)
         engine.set_geometry(sq(state.R), sq(state.Z))
+        engine.set_tao_cache(((fixed_params or {}).get("cache") or {}).get("taos"))
         # functional update: inputs are never mutated (SURVEY.md 8b conventions)
         r = sq(state.r).to(torch.float32).contiguous().clone()
         lp = sq(state.log_psi_sqr).to(torch.float32).contiguous().clone()

@@ -54,7 +54,7 @@ def build_log_psi_squared(config: ModelConfigDeepErwin4, physical_config: Physic
                     n_iterations=emb.n_iterations, n_hidden_one_el=list(emb.n_hidden_one_el),
                     n_hidden_two_el=list(emb.n_hidden_two_el), emb_dim=emb.emb_dim,
                     n_ion_features=config.features.n_ion_features, n_dets=orb.n_determinants, z_min=Z_min, z_max=Z_max,
-                    device=device, workspace_gb=workspace_gb)
+                    use_taos=orb.transferable_atomic_orbitals is not None, device=device, workspace_gb=workspace_gb)
     params = init_params(engine, rng_seed, device)
     fixed_params = fixed_params if fixed_params is not None else {}
 
@@ -63,12 +63,17 @@ def build_log_psi_squared(config: ModelConfigDeepErwin4, physical_config: Physic
             raise ValueError(f"model was built for n_up={engine.n_up}, n_dn={engine.n_el - engine.n_up}")
         engine.set_params(params)
         engine.set_geometry(R, Z)
+        # TAO models read the geometry cache exactly where the reference does (orbital_net.py:84-95)
+        engine.set_tao_cache(((fixed_params or {}).get("cache") or {}).get("taos"))
         return engine.log_psi_sqr(r)
 
     def get_slater_mat(*args, **kwargs):
         raise NotImplementedError("Slater-matrix output is only used by pre-training (out of the hot-path scope)")
 
     def get_cache(*args, **kwargs):
+        if engine.use_taos:
+            raise NotImplementedError("the geometry-only TAO nets (TAOBackflow / TAOExponents, wavefunction.py:164-209) are a 'next' row; "
+                                      'pass the cache in fixed_params["cache"]["taos"]')
         return {}   # envelope orbitals have no geometry-only cache (wavefunction.py:165-211 caches TAOs only)
 
     log_psi_sqr.engine = engine

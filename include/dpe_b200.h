@@ -46,6 +46,9 @@ typedef struct dpe_dims {
     int32_t n_ion_features;            /* 32 */
     int32_t n_dets;                    /* 32 */
     int32_t z_min, z_max;              /* lookup-embedding vocabulary, model/wavefunction.py:310-326 */
+    int32_t use_taos;                  /* 0: envelope orbitals (orbitals/envelope_orbitals.py:39-127, dpe4 default);
+                                          1: transferable atomic orbitals from a per-geometry cache
+                                             (orbitals/transferable_atomic_orbitals.py:287-349, orbitals.envelope_orbitals = null) */
 } dpe_dims;
 
 /* MCMCConfig fields the Metropolis step reads (configuration.py:978-1049), `normal` proposal. */
@@ -96,6 +99,16 @@ int dpe_model_set_params(dpe_model *m, const float *params_dev, int64_t n, void 
 
 /* `R, Z` of log_psi_sqr(params, n_up, n_dn, r, R, Z, fixed_params): host arrays R[n_ion*3], Z[n_ion]. */
 int dpe_model_set_geometry(dpe_model *m, const float *R_host, const int32_t *Z_host, void *stream);
+
+/* `fixed_params["cache"]["taos"]` of log_psi_sqr(...) for models built with use_taos = 1 (orbital_net.py:84-95,
+ * model/wavefunction.py:164-209): the geometry-only outputs of TAOBackflow / TAOExponents, device arrays,
+ *   backflows_{up,dn}  [n_ion, n_orb, 2, n_dets, n_hidden_one_el[last]]   (n_orb = n_up / n_dn orbitals of that spin)
+ *   exponents_{up,dn}  [n_ion, n_orb, 2, n_dets]
+ * axis 2 = (same spin, different spin) of electron vs orbital.  As in the reference with use_el_ion_embedding = False,
+ * the backflow of BOTH spin types is slice 0 (transferable_atomic_orbitals.py:255-260); the exponents use both slices.
+ * With use_taos = 1 the flat parameter vector ends after the embedding leaves (no bf_ / alpha_ / weights_ leaves). */
+int dpe_model_set_tao_cache(dpe_model *m, const float *backflows_up_dev, const float *backflows_dn_dev,
+                            const float *exponents_up_dev, const float *exponents_dn_dev, void *stream);
 
 /* ---- workspace ------------------------------------------------------------------------------- */
 /* mode 0: forward only (log psi^2), mode 1: forward-Laplacian (E_loc). Bytes needed to process

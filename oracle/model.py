@@ -43,6 +43,9 @@ class ModelDims:
     emb_dim: int = 32
     n_ion_features: int = 32
     n_dets: int = 32
+    # orbitals: False = envelope orbitals (dpe4 default); True = transferable atomic orbitals evaluated from a per-geometry
+    # cache (sample_configs/pre_training_basemodel/config_bm_hfcoeff.yml:45-77: n_determinants 4, envelope_orbitals null)
+    use_taos: bool = False
 
     def __post_init__(self):
         if isinstance(self.n_hidden_one_el, int):
@@ -86,6 +89,8 @@ def param_shapes(d: ModelDims) -> Dict[str, Dict[str, Tuple[int, ...]]]:
         if it < d.n_iterations - 1:
             for nm, din in (("h_same", d.d_pair_in(it)), ("h_diff", d.d_pair_in(it)), ("h_el_ion", d.d_eion_in(it))):
                 shapes[f"{EMB}/{nm}_{it}/linear_0"] = {"w": (din, d.n_hidden_two_el[it]), "b": (d.n_hidden_two_el[it],)}
+    if d.use_taos:   # the TAO heads have no per-walker parameters: backflows / exponents come from the geometry cache
+        return shapes
     n_orb_tot = d.n_dets * d.n_el  # full_det: every spin block has n_el orbitals
     d_emb = d.n_hidden_one_el[-1]
     shapes[f"{ORB}/bf_up/linear_0"] = {"w": (d_emb, n_orb_tot)}
@@ -209,6 +214,45 @@ def orbitals(params, d: ModelDims, h_el, dist_eI):
     return torch.cat([mo_up, mo_dn], -2)                                # wavefunction.py:68
 
 
+def make_tao_cache(d: ModelDims, seed: int = 11, dtype=torch.float64):
+    """Synthetic stand-in for Wavefunction._calculate_cache (wavefunction.py:164-209): per spin
+    backflows [I, n_orb, 2, n_det, emb] and exponents [I, n_orb, 2, n_det] (transferable_atomic_orbitals.py:142, 159 comments).
+    The geometry-only nets that produce them (TAOBackflow / TAOExponents on orbital descriptors) are outside the hot path;
+    values here are random with the scale of their outputs (exponents positive so that the orbitals decay)."""
+    g = torch.Generator().manual_seed(seed)
+    emb = d.n_hidden_one_el[-1]
+    bfs, exs = [], []
+    for n_orb in (d.n_up, d.n_dn):
+        bfs.append((torch.randn(d.n_ion, n_orb, 2, d.n_dets, emb, generator=g, dtype=torch.float64) / math.sqrt(emb)).to(dtype))
+        exs.append((0.5 + torch.rand(d.n_ion, n_orb, 2, d.n_dets, generator=g, dtype=torch.float64)).to(dtype))
+    return {"backflows": bfs, "exponents": exs}
+
+
+def cast_tao_cache(tao, dtype):
+    return {k: [t.to(dtype) for t in v] for k, v in tao.items()}
+
+
+def orbitals_tao(tao, d: ModelDims, h_el, dist_eI):
+    """TransferableAtomicOrbitals.__call__ with a cache (transferable_atomic_orbitals.py:287-349), defaults
+    use_el_ion_embedding=False, use_separate_ion_sum_for_envelopes=False, use_exponentials=True, full_det.
+    Returns A [..., n_det, N, N] (rows = electrons; columns = [spin-up orbitals | spin-down orbitals])."""
+    U, N = d.n_up, d.n_el
+    mos = []
+    for spin, (ex, bf) in enumerate(zip(tao["exponents"], tao["backflows"])):
+        sl_same, sl_diff = (slice(None, U), slice(U, None)) if spin == 0 else (slice(U, None), slice(None, U))   # :316-319
+        b_same = bf[..., :, :, 0, :, :]                                              # :234
+        # :255-260 -- without el-ion embedding BOTH products use b_same (b_diff, :235, stays unused)
+        mo_same = torch.einsum("Ikda,...ia->...diIk", b_same, h_el[..., sl_same, :])
+        mo_diff = torch.einsum("Ikda,...ia->...diIk", b_same, h_el[..., sl_diff, :])
+        # :271-284: exponent[..., spin-type, det] * dist -> [el, ion, orb, det] -> moveaxis(-1, -4) -> [det, el, ion, orb]
+        e_same = torch.exp(-ex[None, :, :, 0, :] * dist_eI[..., sl_same, :, None, None]).movedim(-1, -4)
+        e_diff = torch.exp(-ex[None, :, :, 1, :] * dist_eI[..., sl_diff, :, None, None]).movedim(-1, -4)
+        mos.append(((mo_same * e_same).sum(-2), (mo_diff * e_diff).sum(-2)))          # :322-329 (sum over ions)
+    mo_up = torch.cat([mos[0][0], mos[1][1]], -1)                                     # :342-345
+    mo_dn = torch.cat([mos[0][1], mos[1][0]], -1)
+    return torch.cat([mo_up, mo_dn], -2)                                              # wavefunction.py:68
+
+
 def sum_of_determinants(A):
     """model/wavefunction.py:63-83. Returns (phase, log_psi_sqr, sign_total)."""
     sign, logdet = torch.linalg.slogdet(A)
@@ -219,10 +263,11 @@ def sum_of_determinants(A):
     return phase, log_psi_sqr
 
 
-def log_psi_sqr(params, d: ModelDims, r, R, Z):
-    """model/wavefunction.py:118-134, 293: (phase, log psi^2) for r [...,N,3]."""
+def log_psi_sqr(params, d: ModelDims, r, R, Z, tao=None):
+    """model/wavefunction.py:118-134, 293: (phase, log psi^2) for r [...,N,3].  `tao` = fixed_params["cache"]["taos"]
+    (orbital_net.py:84-95) when the model uses transferable atomic orbitals."""
     h_el, dist_eI = embedding(params, d, r, R, Z)
-    A = orbitals(params, d, h_el, dist_eI)
+    A = orbitals_tao(tao, d, h_el, dist_eI) if d.use_taos else orbitals(params, d, h_el, dist_eI)
     return sum_of_determinants(A)
 
 
@@ -245,13 +290,13 @@ def potential_energy(r, R, Z):
     return e_ee + e_ei + e_ii
 
 
-def kinetic_energy_hessian(params, d, r, R, Z):
+def kinetic_energy_hessian(params, d, r, R, Z, tao=None):
     """Definition: E_kin = -1/2 (1/2 lap L + 1/4 |grad L|^2), L = log psi^2 (hamiltonian.py:216),
     with lap/grad from torch.func (exact autodiff). r [B,N,3]. Returns (E_kin, grad[B,3N], lap[B])."""
     from torch.func import grad, hessian, vmap
 
     def f(x):
-        return log_psi_sqr(params, d, x.reshape(d.n_el, 3), R, Z)[1]
+        return log_psi_sqr(params, d, x.reshape(d.n_el, 3), R, Z, tao)[1]
 
     x = r.reshape(r.shape[0], -1)
     g = vmap(grad(f))(x)
@@ -280,9 +325,9 @@ def kinetic_energy_jvp_loop(params, d, r, R, Z):
     return torch.stack(out)
 
 
-def local_energy_hessian(params, d, r, R, Z):
+def local_energy_hessian(params, d, r, R, Z, tao=None):
     """hamiltonian.py:281-289 with the autodiff-definition kinetic energy."""
-    ek, _, _ = kinetic_energy_hessian(params, d, r, R, Z)
+    ek, _, _ = kinetic_energy_hessian(params, d, r, R, Z, tao)
     return ek + potential_energy(r, R, Z)
 
 
@@ -315,7 +360,7 @@ def _lin_rule(params, name, x):
     return y
 
 
-def forward_laplacian(params, d: ModelDims, r, R, Z, return_intermediates=False):
+def forward_laplacian(params, d: ModelDims, r, R, Z, return_intermediates=False, tao=None):
     """Returns dict(logpsi2[B], phase[B], grad[B,3N], lap[B], E_kin[B], E_pot[B], E_loc[B])."""
     U, D, N, I = d.n_up, d.n_dn, d.n_el, d.n_ion
     B = r.shape[0]
@@ -406,9 +451,28 @@ def forward_laplacian(params, d: ModelDims, r, R, Z, return_intermediates=False)
 
     # ---- orbitals
     nd = d.n_dets
-    p = params[ORB]
     mo = torch.empty(B, N, C, nd * N, dtype=dt)
-    for sl, wname, an, wn in ((slice(0, U), "bf_up", "alpha_up", "weights_up"), (slice(U, N), "bf_dn", "alpha_dn", "weights_dn")):
+    if d.use_taos:
+        # TAOs (transferable_atomic_orbitals.py:287-349): mo[i, d, k] = sum_I (h_i . b[I, k, d]) exp(-x[I, k, s(i,k), d] |r_i - R_I|);
+        # product rule with e = exp(-x dist): grad_i e = -x e (r_i - R_I)/dist, lap e = e (x^2 - 2 x / dist)
+        for spin, (ex, bf) in enumerate(zip(tao["exponents"], tao["backflows"])):
+            k0, n_orb = (0, U) if spin == 0 else (U, D)
+            for sl, st in ((slice(0, U), 0 if spin == 0 else 1), (slice(U, N), 1 if spin == 0 else 0)):   # st: 0 same / 1 diff
+                g = torch.einsum("Ikda,bnca->bncIdk", bf[:, :, 0], h_one[:, sl])                # [B,n,C,I,nd,n_orb]
+                x = ex[:, :, st, :].permute(0, 2, 1)                                             # [I,nd,n_orb]
+                dist = dist_eI[:, sl]                                                            # [B,n,I]
+                e = torch.exp(-x * dist[..., None, None])                                        # [B,n,I,nd,n_orb]
+                unit = diff_eI[:, sl] / dist[..., None]                                          # [B,n,I,3]
+                e_t = torch.einsum("bnIx,bnIdk->bnxIdk", unit, -x * e)                           # [B,n,3,I,nd,n_orb]
+                e_l = e * (x * x - 2 * x / dist[..., None, None])
+                m = (g * e[:, :, None]).sum(3)                                                   # [B,n,C,nd,n_orb]
+                for n_loc, i in enumerate(range(N)[sl]):
+                    m[:, n_loc, 1 + 3 * i:4 + 3 * i] += (e_t[:, n_loc] * g[:, n_loc, 0:1]).sum(2)
+                    m[:, n_loc, C - 1] += (e_l[:, n_loc] * g[:, n_loc, 0]).sum(1) + 2 * (e_t[:, n_loc] * g[:, n_loc, 1 + 3 * i:4 + 3 * i]).sum((1, 2))
+                mo.view(B, N, C, nd, N)[:, sl, :, :, k0:k0 + n_orb] = m
+    else:
+      p = params[ORB]
+      for sl, wname, an, wn in ((slice(0, U), "bf_up", "alpha_up", "weights_up"), (slice(U, N), "bf_dn", "alpha_dn", "weights_dn")):
         bf = h_one[:, sl] @ params[f"{ORB}/{wname}/linear_0"]["w"]                    # [B,n,C,nd*N]
         a = torch.nn.functional.softplus(p[an])                                        # [I,cols]
         dist = dist_eI[:, sl]                                                          # [B,n,I]
@@ -455,8 +519,8 @@ def forward_laplacian(params, d: ModelDims, r, R, Z, return_intermediates=False)
     return out
 
 
-def local_energy(params, d, r, R, Z, max_batch_size=64):
+def local_energy(params, d, r, R, Z, max_batch_size=64, tao=None):
     """build_local_energy(..., forward_lap=True, max_batch_size) (hamiltonian.py:272-291): sequential
     chunks of <= max_batch_size walkers, as folx.batched_vmap does."""
-    outs = [forward_laplacian(params, d, r[s:s + max_batch_size], R, Z)["E_loc"] for s in range(0, r.shape[0], max_batch_size)]
+    outs = [forward_laplacian(params, d, r[s:s + max_batch_size], R, Z, tao=tao)["E_loc"] for s in range(0, r.shape[0], max_batch_size)]
     return torch.cat(outs)

@@ -35,6 +35,8 @@ CASES = {
     "LiH_small": dict(R=[[0, 0, 0], [3.015, 0, 0]], Z=[3, 1], n_up=2, mapping=[0, 1, 0, 0],
                       dims=dict(n_iterations=2, n_hidden_one_el=[16, 16], n_hidden_two_el=[4], emb_dim=8, n_dets=3)),
     "LiH": dict(R=[[0, 0, 0], [3.015, 0, 0]], Z=[3, 1], n_up=2, mapping=[0, 1, 0, 0], dims={}),
+    # transferable atomic orbitals from a synthetic geometry cache (config_bm_hfcoeff.yml: 4 determinants)
+    "LiH_tao": dict(R=[[0, 0, 0], [3.015, 0, 0]], Z=[3, 1], n_up=2, mapping=[0, 1, 0, 0], dims=dict(n_dets=4, use_taos=True)),
 }
 
 
@@ -44,7 +46,8 @@ def make_model_fixture(name, spec, B=8):
     g = torch.Generator().manual_seed(5)
     R = torch.tensor(spec["R"], dtype=torch.float32)
     r = (R[torch.tensor(spec["mapping"])][None] + torch.randn(B, d.n_el, 3, generator=g)).float()
-    out = om.forward_laplacian(params, d, r.double(), R.double(), spec["Z"])
+    tao = om.cast_tao_cache(om.cast_tao_cache(om.make_tao_cache(d, seed=11), torch.float32), torch.float64) if d.use_taos else None
+    out = om.forward_laplacian(params, d, r.double(), R.double(), spec["Z"], tao=tao)
     np.savez_compressed(OUT / f"model_{name}.npz", r=r.numpy(), R=R.numpy(), Z=np.array(spec["Z"]), n_up=spec["n_up"],
                         seed=11, bias_scale=0.1, envelope_jitter=0.5,
                         logpsi2=out["logpsi2"].numpy(), phase=out["phase"].numpy(), grad=out["grad"].numpy(),

@@ -36,7 +36,7 @@ def test_shared_weights_over_hchain_geometries():
     assert int(states[0].step_nr) == 10
 
 
-@pytest.mark.parametrize("name", ["LiH", "N2"])
+@pytest.mark.parametrize("name", ["LiH", "N2", "N"])
 def test_tensor_core_and_simt_paths_agree(name):
     """gemm_path 1 (tcgen05 3xTF32) vs gemm_path 0 (FP32 SIMT) on the same walkers.  The tensor-core accumulator rounds
     towards zero, which makes a 3xTF32 dense layer 2-4x noisier than an FP32 FMA chain (2e-6 vs 7e-7 of max|C|); through the

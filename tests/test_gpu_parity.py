@@ -20,12 +20,12 @@ GOLD = Path(__file__).parent / "golden"
 SMALL = dict(n_iterations=2, n_hidden_one_el=[16, 16], n_hidden_two_el=[4], emb_dim=8, n_dets=3)
 
 
-def make(name, B, seed=3, bias_scale=0.1, envelope_jitter=0.5, small=False, device="cuda:0"):
+def make(name, B, seed=3, bias_scale=0.1, envelope_jitter=0.5, small=False, device="cuda:0", **dims_kw):
     import deeperwin_b200 as dpe
     from deeperwin_b200.engine import Engine
     from oracle import model as om
     phys = dpe.PhysicalConfig(name=name)
-    d = om.ModelDims(n_el=phys.n_electrons, n_up=phys.n_up, n_ion=len(phys.Z), Z_max=max(phys.Z), **(SMALL if small else {}))
+    d = om.ModelDims(n_el=phys.n_electrons, n_up=phys.n_up, n_ion=len(phys.Z), Z_max=max(phys.Z), **{**(SMALL if small else {}), **dims_kw})
     p32 = om.cast_params(om.init_params(d, seed=seed, bias_scale=bias_scale, envelope_jitter=envelope_jitter), torch.float32)
     p64 = om.cast_params(p32, torch.float64)
     g = torch.Generator().manual_seed(seed + 100)
@@ -33,13 +33,16 @@ def make(name, B, seed=3, bias_scale=0.1, envelope_jitter=0.5, small=False, devi
     r = (R[torch.tensor(phys.el_ion_mapping)][None] + torch.randn(B, d.n_el, 3, generator=g)).float()
     eng = Engine(n_el=d.n_el, n_up=d.n_up, n_ion=d.n_ion, n_iterations=d.n_iterations, n_hidden_one_el=d.n_hidden_one_el,
                  n_hidden_two_el=d.n_hidden_two_el, emb_dim=d.emb_dim, n_ion_features=d.n_ion_features, n_dets=d.n_dets,
-                 z_min=d.Z_min, z_max=d.Z_max, device=device)
+                 z_min=d.Z_min, z_max=d.Z_max, use_taos=d.use_taos, device=device)
     eng.set_params({m: {k: v.to(device) for k, v in l.items()} for m, l in p32.items()})
     eng.set_geometry(R, phys.Z)
     return phys, d, p32, p64, R, r, eng
 
 
-@pytest.mark.parametrize("name,small,B", [("LiH", True, 32), ("LiH", False, 32), ("N2", False, 24), ("HChain10", False, 8)])
+# B / N atoms: odd electron counts -- the tensor-core determinant stage then runs with shifted TMA boxes ((det * N) mod 4 != 0)
+# and the odd-N minor pairing; ("B", small): n_dets * N = 15 is not a TMA-legal stride, the stage falls back to CUDA cores
+@pytest.mark.parametrize("name,small,B", [("LiH", True, 32), ("LiH", False, 32), ("N2", False, 24), ("HChain10", False, 8),
+                                          ("B", False, 16), ("N", False, 12), ("B", True, 16)])
 def test_logpsi_and_eloc_match_oracle(name, small, B):
     from oracle import model as om
     phys, d, p32, p64, R, r, eng = make(name, B, small=small)
@@ -72,23 +75,84 @@ def test_logpsi_and_eloc_match_oracle(name, small, B):
     assert gerr.max() <= max(1e-4, 8 * gfloor.max().item()), (gerr.max(), gfloor.max())
 
 
-@pytest.mark.parametrize("name", ["LiH_small", "LiH"])
+@pytest.mark.parametrize("name,B,nd", [("LiH", 32, 4), ("N2", 16, 4), ("B", 16, 3)])
+def test_tao_orbitals_match_oracle(name, B, nd):
+    """transferable atomic orbitals evaluated from the per-geometry cache (transferable_atomic_orbitals.py:287-349),
+    CUDA path (one GEMM against the cached backflows + k_tao_orbitals) vs the fp64 oracle; same tolerances as the default model."""
+    from oracle import model as om
+    phys, d, p32, p64, R, r, eng = make(name, B, n_dets=nd, use_taos=True)
+    tao32 = om.cast_tao_cache(om.make_tao_cache(d, seed=9), torch.float32)
+    tao64 = om.cast_tao_cache(tao32, torch.float64)
+    with pytest.raises(RuntimeError, match="set_tao_cache"):        # the cache is part of the inputs: no silent default
+        eng.log_psi_sqr(r.cuda())
+    eng.set_tao_cache({k: [t.cuda() for t in v] for k, v in tao32.items()})
+    ref = om.forward_laplacian(p64, d, r.double(), R.double(), phys.Z, tao=tao64)
+    f32 = om.forward_laplacian(p32, d, r, R, phys.Z, tao=tao32)
+    e_loc, aux = eng.local_energy(r.cuda(), with_aux=True)
+    phase, lp = eng.log_psi_sqr(r.cuda())
+    lp, e_loc = lp.double().cpu(), e_loc.double().cpu()
+    rel_lp = (lp - ref["logpsi2"]).abs() / ref["logpsi2"].abs()
+    floor_lp = (f32["logpsi2"].double() - ref["logpsi2"]).abs() / ref["logpsi2"].abs()
+    assert rel_lp.median() < 1e-5, rel_lp.median()
+    assert rel_lp.max() <= max(1e-5, 8 * floor_lp.max().item()), (rel_lp.max(), floor_lp.max())
+    assert torch.allclose(aux["log_psi_sqr"].cpu(), lp.float(), rtol=2e-6, atol=0)
+    assert torch.equal(phase.cpu() > 1.0, ref["phase"] > 1.0)
+    scale = ref["E_loc"].abs().clamp_min(1.0)
+    err = (e_loc - ref["E_loc"]).abs() / scale
+    floor = (f32["E_loc"].double() - ref["E_loc"]).abs() / scale
+    assert err.median() < 1e-4, err.median()
+    assert err.max() <= max(1e-4, 8 * floor.max().item()), (err.max(), floor.max())
+    gerr = (aux["grad"].double().cpu() - ref["grad"]).abs().amax(-1) / ref["grad"].abs().amax(-1)
+    assert gerr.median() < 1e-4, gerr.median()
+
+
+def test_tao_model_through_the_reference_callables():
+    """The cache travels in fixed_params["cache"]["taos"] exactly as in the reference (orbital_net.py:84-95, opt_utils.py:26-27)."""
+    import deeperwin_b200 as dpe
+    from oracle import model as om
+    cfg = dpe.Configuration(physical=dict(name="LiH"),
+                            model=dict(orbitals=dict(envelope_orbitals=None, transferable_atomic_orbitals=dict(name="taos"), n_determinants=4)))
+    phys = cfg.physical
+    f, _, get_cache, params, fixed = dpe.build_log_psi_squared(cfg.model, phys, None, None, rng_seed=3, device="cuda:0")
+    assert not any("orbitals" in k for k in params)
+    d = om.ModelDims(n_el=4, n_up=2, n_ion=2, Z_max=3, n_dets=4, use_taos=True)
+    tao = om.cast_tao_cache(om.make_tao_cache(d, seed=2), torch.float32)
+    st = dpe.MCMCState.initialize_around_nuclei(64, phys, "gaussian", "el_ion_mapping", dpe.PRNGKey(4), device="cuda:0")
+    with pytest.raises(NotImplementedError):
+        f(params, 2, 2, st.r, st.R, st.Z, {})
+    fixed = {"cache": {"taos": {k: [t.cuda() for t in v] for k, v in tao.items()}}}
+    phase, lp = f(params, 2, 2, st.r, st.R, st.Z, fixed)
+    p64 = {m: {k: v.double().cpu() for k, v in l.items()} for m, l in params.items()}
+    ref = om.log_psi_sqr(p64, d, st.r.double().cpu(), torch.tensor(phys.R, dtype=torch.float64), phys.Z, om.cast_tao_cache(tao, torch.float64))[1]
+    assert ((lp.double().cpu() - ref).abs() / ref.abs()).median() < 1e-5
+    mc = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=5, initialization="gaussian"))
+    st2 = mc.run_inter_steps(f, st, params, 2, 2, fixed)
+    assert int(st2.step_nr) == 5 and torch.isfinite(st2.log_psi_sqr).all()
+    e = dpe.build_local_energy(f, forward_lap=True)(params, (2, 2), st2.r, st2.R, st2.Z, fixed)
+    assert torch.isfinite(e).all()
+
+
+@pytest.mark.parametrize("name", ["LiH_small", "LiH", "LiH_tao"])
 def test_golden_fixtures(name):
     from oracle import model as om
     from deeperwin_b200.engine import Engine
     g = np.load(GOLD / f"model_{name}.npz")
-    kw = SMALL if name.endswith("small") else {}
+    kw = SMALL if name.endswith("small") else (dict(n_dets=4, use_taos=True) if name.endswith("tao") else {})
     d = om.ModelDims(n_el=g["r"].shape[1], n_up=int(g["n_up"]), n_ion=len(g["Z"]), Z_max=int(g["Z"].max()), **kw)
     p32 = om.cast_params(om.init_params(d, seed=int(g["seed"]), bias_scale=float(g["bias_scale"]), envelope_jitter=float(g["envelope_jitter"])), torch.float32)
     eng = Engine(n_el=d.n_el, n_up=d.n_up, n_ion=d.n_ion, n_iterations=d.n_iterations, n_hidden_one_el=d.n_hidden_one_el,
-                 n_hidden_two_el=d.n_hidden_two_el, emb_dim=d.emb_dim, n_ion_features=d.n_ion_features, n_dets=d.n_dets, z_min=1, z_max=d.Z_max)
+                 n_hidden_two_el=d.n_hidden_two_el, emb_dim=d.emb_dim, n_ion_features=d.n_ion_features, n_dets=d.n_dets, z_min=1, z_max=d.Z_max,
+                 use_taos=d.use_taos)
     eng.set_params({m: {k: v.cuda() for k, v in l.items()} for m, l in p32.items()})
     eng.set_geometry(g["R"], g["Z"])
+    tao32 = om.cast_tao_cache(om.make_tao_cache(d, seed=int(g["seed"])), torch.float32) if d.use_taos else None
+    if tao32:
+        eng.set_tao_cache({k: [t.cuda() for t in v] for k, v in tao32.items()})
     e, aux = eng.local_energy(torch.from_numpy(g["r"]).cuda(), with_aux=True)
     rel_lp = np.abs(aux["log_psi_sqr"].cpu().numpy() - g["logpsi2"]) / np.abs(g["logpsi2"])
     rel_e = np.abs(e.cpu().numpy() - g["E_loc"]) / np.maximum(np.abs(g["E_loc"]), 1.0)
     # fp32 CPU restatement on the same fixture = what any fp32 evaluation loses to the conditioning of these walkers
-    f32 = om.forward_laplacian(p32, d, torch.from_numpy(g["r"]), torch.from_numpy(g["R"]), g["Z"].tolist())
+    f32 = om.forward_laplacian(p32, d, torch.from_numpy(g["r"]), torch.from_numpy(g["R"]), g["Z"].tolist(), tao=tao32)
     fl_lp = np.abs(f32["logpsi2"].numpy() - g["logpsi2"]) / np.abs(g["logpsi2"])
     fl_e = np.abs(f32["E_loc"].numpy() - g["E_loc"]) / np.maximum(np.abs(g["E_loc"]), 1.0)
     assert np.median(rel_lp) < 1e-5 and rel_lp.max() <= max(1e-5, 8 * fl_lp.max()), (rel_lp, fl_lp)

@@ -100,14 +100,49 @@ def test_analytic_helium_like_wavefunction():
     assert torch.allclose(out["logpsi2"], 2 * (-Zc * r.norm(dim=-1).sum(-1)) + out["logpsi2"][0] + 2 * Zc * r[0].norm(dim=-1).sum(), rtol=1e-9)
 
 
-@pytest.mark.parametrize("name", ["LiH_small", "LiH"])
+def test_tao_orbitals_three_definitions_and_antisymmetry():
+    """SURVEY.md 8 a18 (transferable_atomic_orbitals.py:287-349, cache branch): the explicit forward-Laplacian through the TAO
+    orbitals equals the autodiff Hessian of the literal einsum restatement, for even and odd spin blocks."""
+    for n_el, n_up, n_ion, zs in ((4, 2, 2, [3, 1]), (5, 3, 1, [5])):
+        d = om.ModelDims(n_el=n_el, n_up=n_up, n_ion=n_ion, Z_max=max(zs), use_taos=True, **{**SMALL, "n_dets": 2})
+        params = om.init_params(d, seed=3, bias_scale=0.1)
+        assert not any("orbitals" in k for k in params)           # no per-walker orbital parameters
+        tao = om.make_tao_cache(d, seed=5)
+        assert tao["backflows"][0].shape == (n_ion, n_up, 2, 2, 16) and tao["exponents"][1].shape == (n_ion, n_el - n_up, 2, 2)
+        R = torch.zeros(n_ion, 3, dtype=torch.float64)
+        R[-1, 0] = 3.015 if n_ion > 1 else 0.0
+        g = torch.Generator().manual_seed(n_el)
+        r = torch.randn(3, n_el, 3, generator=g, dtype=torch.float64)
+        fl = om.forward_laplacian(params, d, r, R, zs, tao=tao)
+        ek, grad, lap = om.kinetic_energy_hessian(params, d, r, R, zs, tao)
+        assert torch.allclose(fl["logpsi2"], om.log_psi_sqr(params, d, r, R, zs, tao)[1], rtol=1e-12)
+        assert torch.allclose(fl["grad"], grad, rtol=1e-9, atol=1e-10)
+        assert torch.allclose(fl["lap"], lap, rtol=1e-9, atol=1e-8)
+        assert torch.allclose(fl["E_kin"], ek, rtol=1e-9, atol=1e-9)
+        r_sw = r.clone()
+        r_sw[:, [0, 1]] = r[:, [1, 0]]                            # two spin-up electrons
+        sw = om.forward_laplacian(params, d, r_sw, R, zs, tao=tao)
+        assert torch.allclose(sw["logpsi2"], fl["logpsi2"], rtol=1e-10) and torch.allclose(sw["E_loc"], fl["E_loc"], rtol=1e-8, atol=1e-8)
+        assert torch.all((sw["phase"] - fl["phase"]).abs() > 3.0)
+        # the different-spin exponent slice is really used: changing it moves the result (guards the same/diff bookkeeping)
+        tao2 = {"backflows": tao["backflows"], "exponents": [t.clone() for t in tao["exponents"]]}
+        tao2["exponents"][0][:, :, 1] *= 1.1
+        assert not torch.allclose(om.log_psi_sqr(params, d, r, R, zs, tao2)[1], fl["logpsi2"], rtol=1e-6)
+        # ... while the different-spin BACKFLOW slice is not (transferable_atomic_orbitals.py:255-260 uses b_same twice)
+        tao3 = {"backflows": [t.clone() for t in tao["backflows"]], "exponents": tao["exponents"]}
+        tao3["backflows"][0][:, :, 1] += 1.0
+        assert torch.allclose(om.log_psi_sqr(params, d, r, R, zs, tao3)[1], fl["logpsi2"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["LiH_small", "LiH", "LiH_tao"])
 def test_golden_fixture_regression(name):
     g = np.load(GOLD / f"model_{name}.npz")
-    kw = SMALL if name.endswith("small") else {}
+    kw = SMALL if name.endswith("small") else (dict(n_dets=4, use_taos=True) if name.endswith("tao") else {})
     d = om.ModelDims(n_el=g["r"].shape[1], n_up=int(g["n_up"]), n_ion=len(g["Z"]), Z_max=int(g["Z"].max()), **kw)
     params = om.cast_params(om.cast_params(om.init_params(d, seed=int(g["seed"]), bias_scale=float(g["bias_scale"]),
                                                           envelope_jitter=float(g["envelope_jitter"])), torch.float32), torch.float64)
-    out = om.forward_laplacian(params, d, torch.from_numpy(g["r"]).double(), torch.from_numpy(g["R"]).double(), g["Z"].tolist())
+    tao = om.cast_tao_cache(om.cast_tao_cache(om.make_tao_cache(d, seed=int(g["seed"])), torch.float32), torch.float64) if d.use_taos else None
+    out = om.forward_laplacian(params, d, torch.from_numpy(g["r"]).double(), torch.from_numpy(g["R"]).double(), g["Z"].tolist(), tao=tao)
     for k in ("logpsi2", "grad", "E_kin", "E_pot", "E_loc"):
         assert np.allclose(out[k].numpy(), g[k], rtol=1e-9, atol=1e-9), k
     assert np.array_equal(out["phase"].numpy(), g["phase"])
