@@ -48,6 +48,8 @@ SIGNATURES = {
     "dpe_mcmc_controller": (C.c_int, [C.POINTER(DpeMcmcState), _P, C.c_int32, C.c_int64, C.POINTER(DpeMcmcConfig), _P]),
     "dpe_energy_moments1": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "dpe_energy_moments2": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
+    "dpe_energy_median": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "dpe_energy_width": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P]),
     "dpe_threefry_mcmc_randoms": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "dpe_threefry_bits": (C.c_int, [C.POINTER(C.c_uint32), C.c_int32, _P, _P]),
     "dpe_threefry_normal": (C.c_int, [C.POINTER(C.c_uint32), C.c_int32, _P, _P]),

@@ -246,13 +246,7 @@ class ClippingConfig(ConfigBaseclass):
     center: Literal["mean", "median"] = "mean"
     from_previous_step: bool = True
     clip_by: float = 5.0
-    clip_imag_around_0: bool = False
-
-    @model_validator(mode="after")
-    def _check(self):
-        _only(self.center, "mean", "clipping.center")
-        _only(self.width_metric, "std", "clipping.width_metric")
-        return self
+    clip_imag_around_0: bool = False      # complex wavefunctions only (loss_function.py:37-38); unused on the real path
 
 
 class OptimizationConfig(ConfigBaseclass):

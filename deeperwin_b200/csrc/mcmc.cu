@@ -230,6 +230,66 @@ __global__ void __launch_bounds__(1024) k_moments2(const float *__restrict__ e, 
     if (threadIdx.x == 0) { out[0] = s / cnt; out[1] = sc / cntc; }
 }
 
+// jnp.nanmedian (loss_function.py:20, clipping.center = "median"): radix select on the order-preserving integer image of the
+// floats, one block; an even count averages the two middle values.
+__device__ __forceinline__ uint32_t f2key(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+__global__ void __launch_bounds__(1024) k_median(const float *__restrict__ e, int n, float *__restrict__ out) {
+    __shared__ float red[32];
+    __shared__ unsigned hist[256];
+    __shared__ uint32_t sel_prefix;
+    __shared__ unsigned sel_rank;
+    float c = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) c += (e[i] == e[i]) ? 1.f : 0.f;
+    const int cnt = (int)block_sum(c, red);
+    if (cnt == 0) { if (threadIdx.x == 0) out[0] = __uint_as_float(0x7fc00000u); return; }
+    float vals[2];
+    for (int which = 0; which < 2; ++which) {
+        if (threadIdx.x == 0) { sel_prefix = 0u; sel_rank = (unsigned)(which ? cnt / 2 : (cnt - 1) / 2); }
+        for (int pass = 3; pass >= 0; --pass) {
+            for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0u;
+            __syncthreads();
+            const uint32_t prefix = sel_prefix;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const float v = e[i];
+                if (v == v) {
+                    const uint32_t k = f2key(v);
+                    if (pass == 3 || (k >> (8 * (pass + 1))) == prefix) atomicAdd(&hist[(k >> (8 * pass)) & 255u], 1u);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned r = sel_rank, b = 0;
+                while (r >= hist[b]) { r -= hist[b]; ++b; }
+                sel_rank = r;
+                sel_prefix = (prefix << 8) | b;
+            }
+            __syncthreads();
+        }
+        vals[which] = key2f(sel_prefix);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = vals[0] + (vals[1] - vals[0]) * 0.5f;      // linear interpolation, as jnp.nanquantile does
+}
+
+// width of the clipping window (loss_function.py:22-27): nanmean((E - center)^2) (metric 0, "std") or nanmean(|E - center|) (1, "mae")
+__global__ void __launch_bounds__(1024) k_width(const float *__restrict__ e, int n, const float *__restrict__ center, int metric,
+                                                 float *__restrict__ out) {
+    __shared__ float red[32];
+    const float c = center[0];
+    float s = 0.f, cnt = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = e[i] - c;
+        if (v == v) { s = metric ? s + fabsf(v) : fmaf(v, v, s); cnt += 1.f; }
+    }
+    s = block_sum(s, red); cnt = block_sum(cnt, red);
+    if (threadIdx.x == 0) out[0] = s / cnt;
+}
+
 __global__ void k_bits(uint32_t k0, uint32_t k1, int n, uint32_t *__restrict__ bits) {
     const int h = (n + 1) / 2;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,6 +326,18 @@ int dpe_energy_moments2(const float *e_loc_dev, const float *e_clipped_dev, int3
     if (!e_loc_dev || !e_clipped_dev || !means_dev || !out2_dev || n <= 0) return dpe::set_error(DPE_ERR_ARG, "energy_moments2: bad argument");
     dpe::k_moments2<<<1, 1024, 0, (cudaStream_t)stream>>>(e_loc_dev, e_clipped_dev, n, means_dev, out2_dev);
     return dpe::check_cuda(cudaGetLastError(), "k_moments2");
+}
+
+int dpe_energy_median(const float *e_dev, int32_t n, float *out_dev, void *stream) {
+    if (!e_dev || !out_dev || n <= 0) return dpe::set_error(DPE_ERR_ARG, "energy_median: bad argument");
+    dpe::k_median<<<1, 1024, 0, (cudaStream_t)stream>>>(e_dev, n, out_dev);
+    return dpe::check_cuda(cudaGetLastError(), "k_median");
+}
+
+int dpe_energy_width(const float *e_dev, int32_t n, const float *center_dev, int32_t metric, float *out_dev, void *stream) {
+    if (!e_dev || !center_dev || !out_dev || n <= 0 || metric < 0 || metric > 1) return dpe::set_error(DPE_ERR_ARG, "energy_width: bad argument");
+    dpe::k_width<<<1, 1024, 0, (cudaStream_t)stream>>>(e_dev, n, center_dev, metric, out_dev);
+    return dpe::check_cuda(cudaGetLastError(), "k_width");
 }
 
 int dpe_threefry_mcmc_randoms(const uint32_t *keys_dev, int32_t n_walkers, int32_t n_el, uint32_t *new_keys_dev,

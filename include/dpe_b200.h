@@ -156,6 +156,13 @@ int dpe_energy_moments1(const float *e_loc_dev, int32_t n, const float *clip_cen
                         float *e_clipped_dev, float *out2_dev, void *stream);
 int dpe_energy_moments2(const float *e_loc_dev, const float *e_clipped_dev, int32_t n, const float *means_dev,
                         float *out2_dev, void *stream);
+/* The other clipping-window statistics of _get_clipping_center_and_width (loss_function.py:19-30), per device:
+ * dpe_energy_median: out[0] = nanmedian(E) (clipping.center = "median"; the caller all-reduces the per-device medians
+ *   exactly as the reference's pmean(nanmedian) does);
+ * dpe_energy_width: out[0] = nanmean((E - center)^2) (metric 0, "std": the caller all-reduces, then sqrt) or
+ *   nanmean(|E - center|) (metric 1, "mae"), center read from center_dev[0]. */
+int dpe_energy_median(const float *e_dev, int32_t n, float *out_dev, void *stream);
+int dpe_energy_width(const float *e_dev, int32_t n, const float *center_dev, int32_t metric, float *out_dev, void *stream);
 
 /* ---- test hooks (jax.random restated; oracle/threefry.py) ------------------------------------ */
 /* keys[B,2] -> new_keys[B,2], noise[B,n,3]=normal(sub,[n,3]), thr[B]=uniform(sub,()), as one Metropolis

@@ -310,3 +310,32 @@ def test_energy_statistics_match_oracle():
     _, _, ref2 = omc.energy_statistics(E2.cpu().numpy(), ref_state)
     assert abs(float(aux2["E_mean_clipped"]) - float(ref2["E_mean_clipped"])) < 1e-4 * abs(float(ref2["E_mean_clipped"]))
     assert torch.isfinite(aux2["E_mean"]) and torch.isnan(aux2["E_loc_clipped"][9])
+
+
+@pytest.mark.parametrize("name,center,width_metric,from_prev", [("tanh", "median", "mae", True), ("hard", "median", "std", True),
+                                                                 ("tanh", "mean", "mae", True), ("hard", "mean", "std", False),
+                                                                 ("tanh", "median", "mae", False)])
+def test_clipping_variants_match_oracle(name, center, width_metric, from_prev):
+    """All windows of loss_function.py:19-72 (sample configs use median / mae): synthetic energies with outliers, NaNs, an even
+    and an odd number of valid entries (the median then averages two middle values or not)."""
+    import deeperwin_b200 as dpe
+    from oracle import mcmc as omc
+    cfg = dpe.ClippingConfig(name=name, center=center, width_metric=width_metric, from_previous_step=from_prev, clip_by=3.0)
+    g = torch.Generator().manual_seed(7)
+    for n, n_nan in ((257, 0), (256, 0), (1000, 3), (4096, 1)):
+        E = (-10 + 2 * torch.randn(n, generator=g)).float()
+        E[5], E[11] = 400.0, -300.0
+        if n_nan:
+            E[torch.arange(n_nan) * 17 + 1] = float("nan")
+        Ed = E.cuda()
+        te = dpe.build_total_energy(lambda *a, **k: Ed, cfg)
+        state = (torch.tensor(-9.5, device="cuda"), torch.tensor(4.0, device="cuda"))
+        loss, (new_state, aux) = te(None, state, (1, 1), (None, None, None, None))
+        rl, rs, ra = omc.energy_statistics(E.numpy(), (np.float32(-9.5), np.float32(4.0)), name=name, clip_by=3.0, center=center,
+                                            width_metric=width_metric, from_previous_step=from_prev)
+        for k in ("E_mean", "E_var", "E_mean_clipped", "E_var_clipped"):
+            assert abs(float(aux[k]) - float(ra[k])) <= 3e-5 * max(1.0, abs(float(ra[k]))), (k, n)
+        assert abs(float(new_state[0]) - float(rs[0])) <= 2e-6 * max(1.0, abs(float(rs[0]))), (n, float(new_state[0]), float(rs[0]))
+        assert abs(float(new_state[1]) - float(rs[1])) <= 3e-5 * float(rs[1]), (n, float(new_state[1]), float(rs[1]))
+        ok = ~torch.isnan(E)
+        assert np.allclose(aux["E_loc_clipped"].cpu().numpy()[ok.numpy()], ra["E_loc_clipped"][ok.numpy()], rtol=2e-6, atol=2e-5)
