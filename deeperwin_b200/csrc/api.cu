@@ -196,6 +196,12 @@ static int gemm_dispatch(dpe_model *m, const GemmArgs &g, cudaStream_t s, bool *
     if (m->gemm_path == 1) {
         int e = launch_gemm_tc(m, g, s);
         if (e != DPE_ERR_UNSUPPORTED) { if (fused) *fused = g.epi != 0; return e; }
+        if (g.epi) {                 // shape without a fused epilogue (e.g. the narrow rows kernel): plain tensor-core GEMM
+            GemmArgs g0 = g;
+            g0.epi = 0;
+            e = launch_gemm_tc(m, g0, s);
+            if (e != DPE_ERR_UNSUPPORTED) return e;
+        }
     }
     return launch_gemm_simt(m, g, s);
 }
@@ -257,8 +263,17 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
         if ((e = launch_mean(m, x[cur], ldx, Bc, C, p.d_in, mean, s))) return e;
         if ((e = gemm(m, plain_gemm(mean, 2 * p.d_in, p.w_mean, p.d_out, add, p.d_out, Bc * C, p.d_out, 2 * p.d_in), s))) return e;
         // main layer
-        if ((e = gemm(m, plain_gemm(x[cur], ldx, p.w_main, p.d_out, x[cur ^ 1], ldx, rows, p.d_out, p.k_main), s))) return e;
-        if ((e = launch_act(m, x[cur ^ 1], ldx, Bc * N, C, p.d_out, p.h_el.b, add, N, s))) return e;
+        {
+            // A fused bias + addend + tanh-rule epilogue exists in the tensor-core kernel (DPE_FUSE_ACT=1) but is off: the tile
+            // uses all 512 TMEM columns, so the epilogue cannot overlap the next tile's MMAs and every extra load in it is
+            // exposed -- measured N2 58.8 vs 42.0 ms/step on the same box.  k_act streams at 5.6 TB/s instead.
+            GemmArgs g = plain_gemm(x[cur], ldx, p.w_main, p.d_out, x[cur ^ 1], ldx, rows, p.d_out, p.k_main);
+            static const bool fuse_act = getenv("DPE_FUSE_ACT") != nullptr;
+            if (fuse_act) { g.epi = 1; g.n_ch = C; g.bias = p.h_el.b; g.add = add; g.groups_per_add = N; }
+            bool fused = false;
+            if ((e = gemm(m, g, s, &fused))) return e;
+            if (!fused && (e = launch_act(m, x[cur ^ 1], ldx, Bc * N, C, p.d_out, p.h_el.b, add, N, s))) return e;
+        }
         cur ^= 1;
     }
     const int cols = d.n_dets * N, dl = d.n_hidden_one_el[d.n_iterations - 1];

@@ -36,6 +36,9 @@ struct GemmArgs {
     int epi = 0, n_ch = 1;
     const float *r = nullptr, *R = nullptr, *spa = nullptr, *envw = nullptr;
     int n_el = 0, n_ion = 0, el_base = 0;
+    // epi == 1: tanh rule of the dense layer (mlp.py:45-69) on bias + per-walker addend, see k_act
+    const float *bias = nullptr, *add = nullptr;
+    int groups_per_add = 1;
 };
 
 // Workspace layout for one chunk of Bc walkers with C channels (byte offsets).

@@ -45,10 +45,12 @@ struct TcArgs {
     int nmma;                                      // MMA N = TMA box rows (multiple of 16, <= 256)
     int tile_rows;                                 // rows a tile owns (<= nmma; a multiple of the channel count when epi != 0)
     int n_rt, n_ft;                                // row tiles per segment, feature tiles
-    // fused epilogue. 0: plain store. 2: envelope multiply of the backflow GEMM (envelope_orbitals.py:96-127) with the product rule
+    // fused epilogue. 0: plain store. 1: bias + spin-mean addend + tanh rule of the layer (what k_act does in a second pass).
+    // 2: envelope multiply of the backflow GEMM (envelope_orbitals.py:96-127) with the product rule
     int epi, nch;                                  // channels per (walker, electron) group
     const float *r, *R, *spa, *envw;               // walker positions [n_seg, n_el, 3], ions [I,3], softplus(alpha) / weights [I, N_out]
     int n_el, n_ion, el_base;                      // electron index of local group 0 of a segment (0 for spin-up, n_up for spin-down)
+    const float *bias, *add; int gpa;              // epi == 1: bias [N_out], addend [(group / gpa)][nch][N_out]
     int pipe;                                      // software-pipelined TMEM loads in the epilogue
     int spt;                                       // segments per tile (> 1: short segments, e.g. the spin blocks of a forward pass, are packed into one tile)
 };
@@ -184,6 +186,10 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             int cch = 0, grp = a.epi == 2 ? m0 / a.nch : 0;
             float env = 1.f, e1x = 0.f, e1y = 0.f, e1z = 0.f, el = 0.f, bf0 = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
             int ci = 0;
+            // activation state (epi == 1): tanh value, 1 - tanh^2, running sum of squared tangents of the current group
+            float act_y = 0.f, act_d1 = 0.f, act_ssq = 0.f;
+            const float act_b = (a.epi == 1 && f_ok && a.bias) ? a.bias[f] : 0.f;
+            long agrp = a.epi == 1 ? ((long)seg * a.seg_len + m0) / a.nch : 0;     // global (walker, electron) group of column 0
             mbar_wait(bar_tfull, tphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * 256;
@@ -204,6 +210,42 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (c0 + j < rows_valid) cbase[(long)(c0 + j) * a.ldc] = __uint_as_float(v[j]);
+                    }
+                } else if (a.epi == 1) {
+                    // z = x W + bias + addend;  y = tanh(z_0), t_k = (1 - y^2) z_k, lap = (1 - y^2) z_lap - 2 y (1 - y^2) sum_k z_k^2
+                    // (same arithmetic and order as k_act).  The addends of the chunk are fetched ahead of the dependent chain.
+                    float ad[16];
+                    {
+                        int cc = cch; long gg = agrp;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            ad[j] = (a.add && f_ok && c0 + j < rows_valid) ? a.add[((gg / a.gpa) * a.nch + cc) * (long)a.N_out + f] : 0.f;
+                            if (++cc == a.nch) { cc = 0; ++gg; }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (c0 + j < rows_valid) {
+                            float z = __uint_as_float(v[j]);
+                            float o;
+                            if (cch == 0) {
+                                z += act_b;
+                                z += ad[j];
+                                act_y = tanhf(z);
+                                act_d1 = 1.f - act_y * act_y;
+                                act_ssq = 0.f;
+                                o = act_y;
+                            } else if (cch < a.nch - 1) {
+                                z += ad[j];
+                                act_ssq = fmaf(z, z, act_ssq);
+                                o = act_d1 * z;
+                            } else {
+                                z += ad[j];
+                                o = act_d1 * z - 2.f * act_y * act_d1 * act_ssq;
+                            }
+                            if (f_ok) cbase[(long)(c0 + j) * a.ldc] = o;
+                            if (++cch == a.nch) { cch = 0; ++agrp; }
+                        }
                     }
                 } else {
 #pragma unroll
@@ -552,6 +594,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     a.spt = 1;
     a.epi = g.epi; a.nch = g.epi ? g.n_ch : 1;
     a.r = g.r; a.R = g.R; a.spa = g.spa; a.envw = g.envw; a.n_el = g.n_el; a.n_ion = g.n_ion; a.el_base = g.el_base;
+    a.bias = g.bias; a.add = g.add; a.gpa = g.groups_per_add > 0 ? g.groups_per_add : 1;
     if (a.epi) {
         // group-aligned tiles: a tile owns whole (walker, electron) groups of C rows
         if (a.nch > 256 || seg_len % a.nch) return DPE_ERR_UNSUPPORTED;
