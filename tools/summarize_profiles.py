@@ -17,7 +17,7 @@ def launch_table(path, tag):
             if r.get("Metric Name") == "gpu__time_duration.sum"]
     idx = [i for i, r in enumerate(rows) if "k_features" in r[1]]
     out = [f"# ncu launch list `{Path(path).name}` ({tag})\n",
-           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 600 --csv "
+           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 330 --csv "
            "python bench.py --steps 1 --warmup 1 --burn-in 2 --no-cpu-baseline --no-e2e` (N2, 4096 walkers, 1 B200).",
            "Per-launch times under ncu are serialised: compare SHARES, not absolutes.\n"]
 
@@ -33,8 +33,11 @@ def launch_table(path, tag):
             out.append(f"| `{n}` | {c} | {t / 1e6:.3f} | {100 * t / tot:.1f}% |")
         out.append("")
 
-    agg(rows[idx[-1]:], "forward-Laplacian E_loc pass (last in the run)")
-    agg(rows[idx[2]:idx[3]], "one Metropolis step (forward pass + propose/accept)")
+    segs = [rows[a:b] for a, b in zip(idx, idx[1:] + [len(rows)])]
+    eloc = [sg for sg in segs if any("k_pair_stream<3>" in n for _, n, _ in sg) and any("k_combine" in n for _, n, _ in sg)]
+    step = [sg for sg in segs if any("k_accept" in n for _, n, _ in sg) and any("k_pair_stream<1>" in n for _, n, _ in sg)]
+    agg(eloc[-1], "forward-Laplacian E_loc pass")
+    agg(step[-1], "one Metropolis step (forward pass + propose/accept)")
     (OUT / f"{tag}_launches.md").write_text("\n".join(out))
 
 
