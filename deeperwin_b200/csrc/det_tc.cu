@@ -201,7 +201,8 @@ k_det_trace_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int q = warp & 3, hh = (warp - 6) >> 2;       // TMEM lane quarter (= warp % 4) and accumulator half of this warp
         const int mrow = hh * 128 + q * 32 + lane;          // the tile row this thread owns
         const int cl = mrow / N, i = mrow - cl * N;         // (channel within the tile, electron) of that row
-        const int n_cyc = (N - 1) >> 1;                     // cyclic partners (i + 1 .. i + n_cyc) mod N: every unordered pair once
+        // cyclic partners (i + 1 .. i + n_pairs) mod N: every unordered pair once; for even N the antipodal pair goes to the lower index
+        const int n_pairs = ((N - 1) >> 1) + ((!(N & 1) && 2 * i < N) ? 1 : 0);
         uint32_t tph0 = 0, tph1 = 0;
         int buf = 0, ui = 0, tcount = 0;
         float *pend = nullptr;                              // record whose lap' still waits for the block-wide sum (thread 0)
@@ -249,32 +250,40 @@ k_det_trace_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     pend = nullptr;
                 }
                 if (mrow == N - 1) DT_TL(9, tcount);
-                if (mrow < rows) {
+                if (mrow < rows && c0 + cl < C - 1) {          // tangent channel: this row's share of the 2 x 2 principal minors of Q_c
                     const float *__restrict__ row = Q + mrow * QS;
                     const float *__restrict__ blk = Q + cl * N * QS;
-                    const bool tangent = c0 + cl < C - 1;
-                    if (tangent) {               // this row's share of the 2 x 2 principal minors of Q_c
-                        const float qii = row[i];
-                        int o = i;
-#pragma unroll 4
-                        for (int dd = 1; dd <= n_cyc; ++dd) {
-                            o = o + 1 == N ? 0 : o + 1;
-                            e2 = __fadd_rn(e2, minor2(qii, blk[o * QS + o], row[o], blk[o * QS + i]));
-                        }
-                        if (!(N & 1) && 2 * i < N) {           // even N: the antipodal pair is taken by the lower index
-                            o = i + (N >> 1);
-                            e2 = __fadd_rn(e2, minor2(qii, blk[o * QS + o], row[o], blk[o * QS + i]));
-                        }
+                    const float qii = row[i];
+                    for (int d0 = 1; d0 <= n_pairs; d0 += 8) {         // operands of up to 8 pairs are fetched ahead of the arithmetic
+                        float pd[8], pb[8], pc[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (d0 + u <= n_pairs) {
+                                int o = i + d0 + u;
+                                o = o >= N ? o - N : o;
+                                pd[u] = blk[o * QS + o]; pb[u] = row[o]; pc[u] = blk[o * QS + i];
+                            }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (d0 + u <= n_pairs) e2 = __fadd_rn(e2, minor2(qii, pd[u], pb[u], pc[u]));
                     }
-                    if (mrow == N - 1) DT_TL(10, tcount);
-                    if (i == N - 1) {            // the last row of the block also sums its diagonal: g_c = tr(dA_c Ainv)
+                }
+                if (mrow == N - 1) DT_TL(10, tcount);
+                {
+                    // g_c = tr(dA_c Ainv): one thread per channel sums the diagonal of its block -- in a warp whose rows the tile does
+                    // not use, when there is one (it then runs beside the minors instead of after them), else the block's last row
+                    const int spare_base = (rows + 31) & ~31;
+                    const bool spare = spare_base + nc <= DT_ROWS;
+                    const int cd = spare ? mrow - spare_base : cl;
+                    if (spare ? (cd >= 0 && cd < nc) : (mrow < rows && i == N - 1)) {
+                        const float *__restrict__ blk = Q + cd * N * QS;
                         float g0 = 0.f, g1 = 0.f;
                         int o = 0;
 #pragma unroll 4
                         for (; o + 1 < N; o += 2) { g0 = __fadd_rn(g0, blk[o * QS + o]); g1 = __fadd_rn(g1, blk[(o + 1) * QS + o + 1]); }
                         if (o < N) g0 = __fadd_rn(g0, blk[o * QS + o]);
                         const float gk = __fadd_rn(g0, g1);
-                        if (tangent) out[3 + c0 + cl - 1] = gk;
+                        if (c0 + cd < C - 1) out[3 + c0 + cd - 1] = gk;
                         else lap_tr = gk;                      // tr(Ainv lapA)
                     }
                 }
