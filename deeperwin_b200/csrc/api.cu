@@ -268,7 +268,7 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
             // uses all 512 TMEM columns, so the epilogue cannot overlap the next tile's MMAs and every extra load in it is
             // exposed -- measured N2 58.8 vs 42.0 ms/step on the same box.  k_act streams at 5.6 TB/s instead.
             GemmArgs g = plain_gemm(x[cur], ldx, p.w_main, p.d_out, x[cur ^ 1], ldx, rows, p.d_out, p.k_main);
-            static const bool fuse_act = getenv("DPE_FUSE_ACT") != nullptr;
+            static const bool fuse_act = getenv("DPE_FUSE_ACT") != nullptr || (getenv("DPE_TC_2CTA") && atoi(getenv("DPE_TC_2CTA")) > 1);
             if (fuse_act) { g.epi = 1; g.n_ch = C; g.bias = p.h_el.b; g.add = add; g.groups_per_add = N; }
             bool fused = false;
             if ((e = gemm(m, g, s, &fused))) return e;

@@ -61,7 +61,7 @@ struct TcArgs {
 };
 
 constexpr int TC_TL_TILES = 64;
-#define TC_TL(role, idx) do { if (a.tl && blockIdx.x == 0 && (idx) < TC_TL_TILES) a.tl[(idx) * 4 + (role)] = clock64(); } while (0)
+#define TC_TL(role, idx) do { if (a.tl && blockIdx.x == 0 && (idx) < TC_TL_TILES) a.tl[(idx) * 8 + (role)] = clock64(); } while (0)
 
 // ---------------------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -167,12 +167,20 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 mbar_wait(&bar_full[stage], phase);
                 float4 *xh = reinterpret_cast<float4 *>(smem + stage * TC_STAGE_BYTES + 2 * TC_W_BYTES);
                 float4 *xl = reinterpret_cast<float4 *>(smem + stage * TC_STAGE_BYTES + 2 * TC_W_BYTES + TC_X_BYTES);
-                for (int i = tid; i < n_f4; i += 128) {
-                    float4 v = xh[i], h, l;
-                    h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-                    l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-                    xh[i] = h;
-                    xl[i] = l;
+                for (int base = tid; base < n_f4; base += 4 * 128) {      // loads batched ahead of the stores (they may alias for the compiler)
+                    float4 v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (base + k * 128 < n_f4) v[k] = xh[base + k * 128];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (base + k * 128 < n_f4) {
+                            float4 h, l;
+                            h.x = rna_tf32(v[k].x); h.y = rna_tf32(v[k].y); h.z = rna_tf32(v[k].z); h.w = rna_tf32(v[k].w);
+                            l.x = rna_tf32(v[k].x - h.x); l.y = rna_tf32(v[k].y - h.y); l.z = rna_tf32(v[k].z - h.z); l.w = rna_tf32(v[k].w - h.w);
+                            xh[base + k * 128] = h;
+                            xl[base + k * 128] = l;
+                        }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&bar_split[stage]);
@@ -538,6 +546,306 @@ k_gemm_tc_rows_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_co
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// CTA-pair variant of the wide kernel (tcgen05 cta_group::2): two SMs of a TPC share one 256-feature x nmma-row tile.
+// CTA r of the pair holds features [128 r, 128 r + 128) of Wt_hi / Wt_lo and rows [r nmma/2, (r+1) nmma/2) of X in its own
+// shared memory; the leader (rank 0) issues M256 x N(nmma) x K8 MMAs that read both halves, and every SM accumulates ITS 128
+// features x nmma rows in its own TMEM.  That is 256 TMEM columns per tile instead of 512, so the accumulators are double
+// buffered and the epilogue (TMEM -> staging -> TMA stores) runs under the next tile's MMAs; per SM the X operand traffic
+// (TMA writes, splitter passes, MMA operand reads) is halved.
+//   warp 0      TMA producer (own halves)            warp 1      TMEM allocation; in the leader: MMA issuer
+//   warps 2-5   splitter (own X half)                warps 6-13  epilogue (own accumulator)
+// Cross-CTA signalling: splitters and epilogues of both CTAs arrive on the LEADER's mbarriers (mapa + .shared::cluster);
+// tcgen05.commit multicasts "stage free" / "accumulator full" to both CTAs.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int T2_STAGES = 4;
+constexpr int T2_W_BYTES = 128 * TC_ROWB;                         // 8 KB per hi / lo (128 features)
+constexpr int T2_X_BYTES = 128 * TC_ROWB;                         // 8 KB (128 rows)
+constexpr int T2_STAGE_BYTES = 2 * T2_W_BYTES + 2 * T2_X_BYTES;   // 32 KB
+constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 4 * TC_OUT_BYTES + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
+                  const __grid_constant__ CUtensorMap map_wl, const __grid_constant__ CUtensorMap map_c,
+                  const __grid_constant__ CUtensorMap map_add, TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int n_st = a.epi == 1 ? 3 : T2_STAGES;       // the fused epilogue trades one stage for its addend buffers
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + n_st * T2_STAGE_BYTES);
+    uint64_t *bar_full = bars;                      // [S] own TMA landed
+    uint64_t *bar_split = bars + T2_STAGES;         // [S] leader only: both splitter groups done (one elected arrival per CTA:
+                                                    //     128 remote arrivals per stage serialise on the DSMEM path)
+    uint64_t *bar_empty = bars + 2 * T2_STAGES;     // [S] MMAs that read the stage retired (multicast commit)
+    uint64_t *bar_tfull = bars + 3 * T2_STAGES;     // [2] accumulator complete (multicast commit)
+    uint64_t *bar_tempty = bar_tfull + 2;           // [2] leader only: the four epilogue groups of the pair drained the buffer
+    uint64_t *bar_afull = bar_tempty + 2;           // [2] addend tile of the fused epilogue landed (TMA)
+    uint64_t *bar_aempty = bar_afull + 2;           // [2] ... and has been consumed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_aempty + 2);
+    uint8_t *out_stage = smem + n_st * T2_STAGE_BYTES + 1024;
+    float *addbuf = reinterpret_cast<float *>(out_stage + 4 * TC_OUT_BYTES);      // [2 tiles][2 walkers][nch][128 features]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_kb = (a.K + TC_BK - 1) / TC_BK;
+    const long n_tiles = (long)a.n_seg * a.n_rt * a.n_ft;
+    const int half_rows = a.nmma >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_split[s], 2); mbar_init(&bar_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], a.epi == 1 ? 2 : 4);
+            mbar_init(&bar_afull[b], 1); mbar_init(&bar_aempty[b], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                             // barriers of both CTAs initialised, TMEM allocated on both SMs
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t tx = 2 * T2_W_BYTES + half_rows * TC_ROWB;
+            int tcount = 0;
+            for (long t = pair; t < n_tiles; t += n_pairs, ++tcount) {
+                const int ft = (int)(t % a.n_ft);
+                const long rest = t / a.n_ft;
+                const int rt = (int)(rest % a.n_rt), seg = (int)(rest / a.n_rt);
+                if (a.epi == 1 && a.add) {
+                    // addends of this tile: one box of nch rows x 128 features per walker the tile touches (at most two)
+                    const int slot = tcount & 1, m0 = rt * a.tile_rows;
+                    const int rows_valid = min(a.tile_rows, a.seg_len - m0);
+                    const long g_first = ((long)seg * a.seg_len + m0) / a.nch, g_last = g_first + (rows_valid + a.nch - 1) / a.nch - 1;
+                    const long w_first = g_first / a.gpa;
+                    const int n_w = (int)(g_last / a.gpa - w_first) + 1;
+                    mbar_wait(&bar_aempty[slot], (((uint32_t)tcount >> 1) & 1u) ^ 1u);
+                    mbar_expect_tx(&bar_afull[slot], (uint32_t)(n_w * a.nch * 512));
+                    for (int w = 0; w < n_w; ++w)
+                        tma_load_2d(addbuf + (size_t)(slot * 2 + w) * a.nch * 128, &map_add, &bar_afull[slot], ft * TC_FEAT + (int)rank * 128,
+                                    (int)((w_first + w) * a.nch));
+                }
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    uint8_t *st = smem + stage * T2_STAGE_BYTES;
+                    mbar_expect_tx(&bar_full[stage], tx);
+                    tma_load_2d(st, &map_wh, &bar_full[stage], kb * TC_BK, ft * TC_FEAT + (int)rank * 128);
+                    tma_load_2d(st + T2_W_BYTES, &map_wl, &bar_full[stage], kb * TC_BK, ft * TC_FEAT + (int)rank * 128);
+                    tma_load_3d(st + 2 * T2_W_BYTES, &map_x, &bar_full[stage], kb * TC_BK, rt * a.tile_rows + (int)rank * half_rows, seg);
+                    if (++stage == n_st) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.nmma >> 3) << 17) | ((256u >> 4) << 24);
+            int stage = 0; uint32_t phase = 0, tph0 = 0, tph1 = 0;
+            int buf = 0, tcount = 0;
+            for (long t = pair; t < n_tiles; t += n_pairs, ++tcount) {
+                mbar_wait_cluster(&bar_tempty[buf], (buf ? tph1 : tph0) ^ 1);
+                tc_fence_after();
+                TC_TL(0, tcount);
+                const uint32_t d = tmem_base + buf * 256;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait_cluster(&bar_split[stage], phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * T2_STAGE_BYTES);
+                    const uint32_t wh = st, wl = st + T2_W_BYTES, xh = st + 2 * T2_W_BYTES, xl = xh + T2_X_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                        const uint32_t ko = kk * 32;
+                        const uint64_t dxh = make_desc_sw64(xh + ko), dxl = make_desc_sw64(xl + ko);
+                        const uint64_t dwh = make_desc_sw64(wh + ko), dwl = make_desc_sw64(wl + ko);
+                        tc_mma2_tf32(d, dwl, dxh, idesc, (kb | kk) ? 1u : 0u);   // small terms first
+                        tc_mma2_tf32(d, dwh, dxl, idesc, 1u);
+                        tc_mma2_tf32(d, dwh, dxh, idesc, 1u);
+                    }
+                    tc_commit2(&bar_empty[stage], 3);          // frees the stage in both CTAs once these MMAs retire
+                    if (++stage == n_st) { stage = 0; phase ^= 1; }
+                }
+                tc_commit2(&bar_tfull[buf], 3);
+                TC_TL(1, tcount);
+                if (buf) tph1 ^= 1; else tph0 ^= 1;
+                buf ^= 1;
+            }
+        }
+    } else if (warp < 6) {
+        const int tid = threadIdx.x - 64;
+        int stage = 0; uint32_t phase = 0;
+        const int n_f4 = half_rows * (TC_ROWB / 16);
+        int tcount = 0;
+        for (long t = pair; t < n_tiles; t += n_pairs, ++tcount) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(&bar_full[stage], phase);
+                float4 *xh = reinterpret_cast<float4 *>(smem + stage * T2_STAGE_BYTES + 2 * T2_W_BYTES);
+                float4 *xl = reinterpret_cast<float4 *>(smem + stage * T2_STAGE_BYTES + 2 * T2_W_BYTES + T2_X_BYTES);
+                for (int base = tid; base < n_f4; base += 4 * 128) {      // loads batched ahead of the stores (they may alias for the compiler)
+                    float4 v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (base + k * 128 < n_f4) v[k] = xh[base + k * 128];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (base + k * 128 < n_f4) {
+                            float4 h, l;
+                            h.x = rna_tf32(v[k].x); h.y = rna_tf32(v[k].y); h.z = rna_tf32(v[k].z); h.w = rna_tf32(v[k].w);
+                            l.x = rna_tf32(v[k].x - h.x); l.y = rna_tf32(v[k].y - h.y); l.z = rna_tf32(v[k].z - h.z); l.w = rna_tf32(v[k].w - h.w);
+                            xh[base + k * 128] = h;
+                            xl[base + k * 128] = l;
+                        }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 4, 128;" ::: "memory");
+                if (tid == 0) mbar_arrive_cluster_relaxed(mapa_u32(&bar_split[stage], 0));     // the leader's barrier collects both CTAs
+                if (++stage == n_st) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;                  // TMEM lane quarter = 32 features of this CTA's 128
+        const int g = (warp - 6) >> 2;           // the two epilogue groups take alternate 16-row chunks
+        float *stage_base = reinterpret_cast<float *>(out_stage + g * 2 * TC_OUT_BYTES);
+        const bool elected = (q == 0 && lane == 0);
+        const int bar_id = 2 + g;
+        uint32_t tph0 = 0, tph1 = 0;
+        int buf = 0, chunk = 0, tcount = 0;
+        if (a.epi == 1) {
+            // Fused dense-layer epilogue (mlp.py:45-69 under the forward Laplacian; what k_act does in a separate pass):
+            //   z = x W + bias + addend;  y = tanh(z_0), t_k = (1 - y^2) z_k, lap = (1 - y^2) z_lap - 2 y (1 - y^2) sum_k z_k^2.
+            // With the accumulators double buffered this runs under the next tile's MMAs.  One thread = one output feature,
+            // walking the rows of the tile in order (tiles hold whole (walker, electron) groups of nch rows), so the tanh state
+            // of a group lives in registers; group 0 of the epilogue warps does all of it, group 1 has nothing to do.
+            if (g == 0) {
+                float act_y = 0.f, act_d1 = 0.f, act_ssq = 0.f;
+                for (long t = pair; t < n_tiles; t += n_pairs, ++tcount) {
+                    const int ft = (int)(t % a.n_ft);
+                    const long rest = t / a.n_ft;
+                    const int rt = (int)(rest % a.n_rt), seg = (int)(rest / a.n_rt);
+                    const int m0 = rt * a.tile_rows;
+                    const int rows_valid = min(a.tile_rows, a.seg_len - m0);
+                    const int f = ft * TC_FEAT + (int)rank * 128 + q * 32 + lane;
+                    const bool f_ok = f < a.N_out;
+                    const float act_b = (f_ok && a.bias) ? a.bias[f] : 0.f;
+                    float *cbase = a.C + ((long)seg * a.c_seg_stride + a.c_seg_off + m0) * a.ldc + a.c_col_off + f;
+                    int cch = 0;                                              // channel of the current column
+                    long agrp = ((long)seg * a.seg_len + m0) / a.nch;         // global (walker, electron) group of the current column
+                    // addends: staged by the producer's TMA into addbuf[slot][walker in tile][channel][feature]
+                    const int slot = tcount & 1;
+                    int pe = (int)(agrp % a.gpa);                             // electron of the current group within its walker
+                    const float *arow = addbuf + (size_t)slot * 2 * a.nch * 128 + q * 32 + lane;
+                    if (a.add) mbar_wait(&bar_afull[slot], ((uint32_t)tcount >> 1) & 1u);
+                    mbar_wait(&bar_tfull[buf], buf ? tph1 : tph0);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+                    uint32_t v[16];
+                    for (int c0 = 0; c0 < a.nmma; c0 += 16, ++chunk) {
+                        tmem_ld16(taddr + c0, v);
+                        tmem_ld_wait();
+                        if (c0 + 16 >= a.nmma) tc_fence_before();
+                        float o[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            o[j] = 0.f;
+                            if (c0 + j < rows_valid) {
+                                float z = __uint_as_float(v[j]);
+                                const float adv = a.add ? arow[cch * 128] : 0.f;
+                                if (cch == 0) {
+                                    z += act_b;
+                                    z += adv;
+                                    act_y = tanhf(z);
+                                    act_d1 = 1.f - act_y * act_y;
+                                    act_ssq = 0.f;
+                                    o[j] = act_y;
+                                } else if (cch < a.nch - 1) {
+                                    z += adv;
+                                    act_ssq = fmaf(z, z, act_ssq);
+                                    o[j] = act_d1 * z;
+                                } else {
+                                    z += adv;
+                                    o[j] = act_d1 * z - 2.f * act_y * act_d1 * act_ssq;
+                                }
+                                if (++cch == a.nch) {
+                                    cch = 0;
+                                    if (++pe == a.gpa) { pe = 0; arow += (size_t)a.nch * 128; }      // next walker of the tile
+                                }
+                            }
+                        }
+                        if (elected) tma_store_wait_read<1>();
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                        if (elected && c0 + 16 >= a.nmma) mbar_arrive_cluster_relaxed(mapa_u32(&bar_tempty[buf], 0));
+                        const bool full_chunk = c0 + 16 <= rows_valid;       // a chunk that crosses the end of the tile must not touch
+                        if (full_chunk) {                                     // the rows after it (they belong to the next tile)
+                            float *st = stage_base + (chunk & 1) * (TC_OUT_BYTES / 4) + q * 32 + lane;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) st[j * 128] = o[j];
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        } else if (f_ok) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < rows_valid) cbase[(long)(c0 + j) * a.ldc] = o[j];
+                        }
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                        if (elected) {
+                            if (full_chunk) tma_store_3d(&map_c, stage_base + (chunk & 1) * (TC_OUT_BYTES / 4), ft * TC_FEAT + (int)rank * 128, m0 + c0, seg);
+                            tma_store_commit();
+                        }
+                    }
+                    if (elected && a.add) mbar_arrive(&bar_aempty[slot]);      // every thread passed the last chunk's barriers: addends consumed
+                    if (buf) tph1 ^= 1; else tph0 ^= 1;
+                    buf ^= 1;
+                }
+                if (elected) tma_store_wait_all();
+            }
+        } else {
+        for (long t = pair; t < n_tiles; t += n_pairs, ++tcount) {
+            const int ft = (int)(t % a.n_ft);
+            const long rest = t / a.n_ft;
+            const int rt = (int)(rest % a.n_rt), seg = (int)(rest / a.n_rt);
+            const int m0 = rt * a.tile_rows;
+            const int rows_valid = min(a.tile_rows, a.seg_len - m0);
+            mbar_wait(&bar_tfull[buf], buf ? tph1 : tph0);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+            uint32_t v[16];
+            for (int c0 = g * 16; c0 < a.nmma; c0 += 32, ++chunk) {
+                tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+                if (c0 + 32 >= a.nmma) tc_fence_before();
+                if (elected) tma_store_wait_read<1>();
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (elected && c0 + 32 >= a.nmma) mbar_arrive_cluster_relaxed(mapa_u32(&bar_tempty[buf], 0));    // the group's last chunk is in registers
+                float *st = stage_base + (chunk & 1) * (TC_OUT_BYTES / 4) + q * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) st[j * 128] = __uint_as_float(v[j]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (elected) {
+                    if (c0 < rows_valid) tma_store_3d(&map_c, stage_base + (chunk & 1) * (TC_OUT_BYTES / 4), ft * TC_FEAT + (int)rank * 128, m0 + c0, seg);
+                    tma_store_commit();
+                }
+            }
+            if (threadIdx.x == 6 * 32) TC_TL(3, tcount);
+            if (buf) tph1 ^= 1; else tph0 ^= 1;
+            buf ^= 1;
+        }
+        if (elected) tma_store_wait_all();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                            // nobody frees TMEM while the peer's MMAs / loads may still touch it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 // W[K][N] (row-major) -> Wt_hi / Wt_lo [N][K] (K-major), tf32-rounded halves
 __global__ void k_split_transpose(const float *__restrict__ W, int K, int N, float *__restrict__ hi, float *__restrict__ lo) {
     long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -555,6 +863,7 @@ struct TcWeight {
     int K, N;
     float *hi, *lo;      // [N, K]
     CUtensorMap map_hi, map_lo;
+    CUtensorMap map_hi128, map_lo128;   // 128-row boxes for the CTA-pair kernel
     bool fresh;
 };
 
@@ -589,6 +898,10 @@ int tc_register_weight(dpe_model *m, const float *W, int K, int N) {
     const int box_rows = N <= TR_N ? TR_N : TC_FEAT;      // narrow layers use the rows kernel (Wt resident in shared memory)
     if ((e = encode_w(&w.map_hi, w.hi, N, K, box_rows))) return e;
     if ((e = encode_w(&w.map_lo, w.lo, N, K, box_rows))) return e;
+    if (N > TR_N) {
+        if ((e = encode_w(&w.map_hi128, w.hi, N, K, 128))) return e;
+        if ((e = encode_w(&w.map_lo128, w.lo, N, K, 128))) return e;
+    }
     st->weights.push_back(w);
     return DPE_OK;
 }
@@ -678,7 +991,8 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     CUtensorMap map_c = map_x;
     static const bool no_tma_store = getenv("DPE_TC_NO_TMA_STORE") != nullptr;
     a.tma_store = 0;
-    if (!no_tma_store && a.epi == 0 && a.spt == 1 && !(g.ldc & 3) && !(g.c_col_off & 3) && !(reinterpret_cast<size_t>(g.C) & 15)) {
+    bool have_map_c = false;
+    if (!no_tma_store && a.epi <= 1 && a.spt == 1 && !(g.ldc & 3) && !(g.c_col_off & 3) && !(reinterpret_cast<size_t>(g.C) & 15)) {
         const long c_stride_rows = n_seg > 1 ? g.c_seg_stride : seg_len;
         cuuint64_t cdims[3] = {(cuuint64_t)g.N, (cuuint64_t)seg_len, (cuuint64_t)n_seg};
         cuuint64_t cstr[2] = {(cuuint64_t)g.ldc * sizeof(float), (cuuint64_t)c_stride_rows * g.ldc * sizeof(float)};
@@ -687,7 +1001,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
         void *cbase = g.C + (long)g.c_seg_off * g.ldc + g.c_col_off;
         CUresult rc = enc(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, cbase, cdims, cstr, cbox, ces, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (rc == CUDA_SUCCESS) a.tma_store = 1;
+        if (rc == CUDA_SUCCESS) { have_map_c = true; a.tma_store = a.epi == 0; }
     }
 
     static bool attr_set = false;
@@ -701,21 +1015,66 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     const char *tl_path = getenv("DPE_GEMM_TIMELINE");        // debug: role timeline of CTA 0 for launches with K >= 256 and M >= 1e6
     const bool tl_on = tl_path && g.K >= 256 && g.M >= 1000000;
     if (tl_on) {
-        DPE_CUDA(cudaMalloc(&a.tl, TC_TL_TILES * 4 * sizeof(long long)));
-        DPE_CUDA(cudaMemsetAsync(a.tl, 0, TC_TL_TILES * 4 * sizeof(long long), s));
+        DPE_CUDA(cudaMalloc(&a.tl, TC_TL_TILES * 8 * sizeof(long long)));
+        DPE_CUDA(cudaMemsetAsync(a.tl, 0, TC_TL_TILES * 8 * sizeof(long long), s));
     }
-    k_gemm_tc_3xtf32<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(map_x, w->map_hi, w->map_lo, map_c, a);
+    bool launched_pair = false;
+    static const int use_pair = getenv("DPE_TC_2CTA") ? atoi(getenv("DPE_TC_2CTA")) : 0;
+    bool pair_ok = use_pair && have_map_c && n_tiles >= m->n_sm && ((a.nmma + 31) & ~31) <= 256;
+    size_t smem2 = T2_SMEM_BYTES;
+    CUtensorMap map_add = map_c;
+    if (pair_ok && a.epi == 1) {
+        // fused tanh-rule epilogue: addend tiles ([2 tiles][2 walkers][nch][128 features]) live in shared memory next to 3 stages;
+        // a tile must not touch more than two walkers
+        const int gpt = a.tile_rows / a.nch;
+        smem2 = 3 * T2_STAGE_BYTES + 1024 + 4 * TC_OUT_BYTES + (size_t)4 * a.nch * 512 + 1024;
+        if (gpt > a.gpa || smem2 > 227 * 1024 || (g.N & 3)) pair_ok = false;
+        if (pair_ok && g.add) {
+            const long n_walkers = ((long)n_seg * seg_len / a.nch) / a.gpa;
+            cuuint64_t adims[2] = {(cuuint64_t)g.N, (cuuint64_t)(n_walkers * a.nch)};
+            cuuint64_t astr[1] = {(cuuint64_t)g.N * sizeof(float)};
+            cuuint32_t abox[2] = {128, (cuuint32_t)a.nch};
+            cuuint32_t aes[2] = {1, 1};
+            CUresult ra = enc(&map_add, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(g.add), adims, astr, abox, aes,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (ra != CUDA_SUCCESS) pair_ok = false;
+        }
+    }
+    // the fused tanh-rule epilogue is only worth running where it overlaps the MMAs (double-buffered accumulators of the pair kernel)
+    static const bool force_fuse = getenv("DPE_FUSE_ACT") != nullptr;
+    if (a.epi == 1 && !pair_ok && !force_fuse) return DPE_ERR_UNSUPPORTED;
+    if (pair_ok) {
+        if (a.nmma & 31) a.nmma = (a.nmma + 31) & ~31;            // each CTA of the pair loads half of the MMA N rows
+        CUtensorMap map_x2;
+        cuuint32_t box2[3] = {TC_BK, (cuuint32_t)(a.nmma / 2), 1};
+        CUresult r2 = enc(&map_x2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box2, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r2 == CUDA_SUCCESS) {
+            static size_t attr2 = 0;
+            if (smem2 > attr2) {
+                DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc2_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                attr2 = smem2;
+            }
+            const int grid2 = (m->n_sm / 2) * 2;
+            k_gemm_tc2_3xtf32<<<grid2, TC_THREADS, smem2, s>>>(map_x2, w->map_hi128, w->map_lo128, map_c, map_add, a);
+            launched_pair = true;
+        } else if (a.epi == 1 && !force_fuse) {
+            return DPE_ERR_UNSUPPORTED;
+        }
+    }
+    if (!launched_pair) k_gemm_tc_3xtf32<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(map_x, w->map_hi, w->map_lo, map_c, a);
     m->last_gemm_class = 3;
     DPE_LAUNCH_CHECK(m);
     if (tl_on) {
-        std::vector<long long> h(TC_TL_TILES * 4);
+        std::vector<long long> h(TC_TL_TILES * 8);
         DPE_CUDA(cudaStreamSynchronize(s));
         DPE_CUDA(cudaMemcpy(h.data(), a.tl, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(a.tl);
         if (FILE *f = fopen(tl_path, "a")) {
             fprintf(f, "# M=%d N=%d K=%d nmma=%d: tile mma_start mma_issued epi_start epi_end (clocks)\n", g.M, g.N, g.K, a.nmma);
             for (int t = 0; t < TC_TL_TILES; ++t)
-                fprintf(f, "%d %lld %lld %lld %lld\n", t, h[t * 4] - h[0], h[t * 4 + 1] - h[0], h[t * 4 + 2] - h[0], h[t * 4 + 3] - h[0]);
+                fprintf(f, "%d %lld %lld %lld %lld | %lld %lld %lld %lld\n", t, h[t * 8] - h[0], h[t * 8 + 1] - h[0], h[t * 8 + 2] - h[0], h[t * 8 + 3] - h[0], h[t * 8 + 4], h[t * 8 + 5], h[t * 8 + 6], h[t * 8 + 7]);
             fclose(f);
         }
     }
