@@ -264,11 +264,11 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
         if ((e = gemm(m, plain_gemm(mean, 2 * p.d_in, p.w_mean, p.d_out, add, p.d_out, Bc * C, p.d_out, 2 * p.d_in), s))) return e;
         // main layer
         {
-            // A fused bias + addend + tanh-rule epilogue exists in the tensor-core kernel (DPE_FUSE_ACT=1) but is off: the tile
-            // uses all 512 TMEM columns, so the epilogue cannot overlap the next tile's MMAs and every extra load in it is
-            // exposed -- measured N2 58.8 vs 42.0 ms/step on the same box.  k_act streams at 5.6 TB/s instead.
+            // bias + spin-mean addend + tanh rule are applied in the epilogue of the CTA-pair tensor-core kernel, where the double
+            // buffered accumulators let it run under the next tile's MMAs (gemm_tc.cu); every other kernel leaves `fused`
+            // false and k_act does it as a separate HBM-bound pass.
             GemmArgs g = plain_gemm(x[cur], ldx, p.w_main, p.d_out, x[cur ^ 1], ldx, rows, p.d_out, p.k_main);
-            static const bool fuse_act = getenv("DPE_FUSE_ACT") != nullptr || (getenv("DPE_TC_2CTA") && atoi(getenv("DPE_TC_2CTA")) > 1);
+            static const bool fuse_act = getenv("DPE_FUSE_ACT") != nullptr || tc_pair_mode() > 1;
             if (fuse_act) { g.epi = 1; g.n_ch = C; g.bias = p.h_el.b; g.add = add; g.groups_per_add = N; }
             bool fused = false;
             if ((e = gemm(m, g, s, &fused))) return e;

@@ -1,5 +1,6 @@
 // Internal declarations shared by the kernels of libdpe_b200.so (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -116,6 +117,11 @@ int launch_envelope(dpe_model *m, const float *r, int Bc, int C, float *mo, cuda
 int launch_tao_pack(dpe_model *m, const float *bf_up, const float *bf_dn, const float *ex_up, const float *ex_dn, cudaStream_t s);
 int launch_tao_orbitals(dpe_model *m, const float *r, int Bc, int C, const float *g, float *mo, cudaStream_t s);
 int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *ainv, cudaStream_t s);
+// CTA-pair (cta_group::2) dense-layer kernel: 0 = off, 1 = plain launches only, 2 (default) = also the fused bias + tanh-rule epilogue
+inline int tc_pair_mode() {
+    static const int mode = getenv("DPE_TC_2CTA") ? atoi(getenv("DPE_TC_2CTA")) : 2;
+    return mode;
+}
 // padded size of the Ainv^T tiles of the tensor-core determinant stage: room for the (det * N) mod 4 column shift that
 // keeps the TMA box start 16-byte aligned, rounded up to the 16-float K slab
 inline int det_tc_pad(int N, int n_det) {

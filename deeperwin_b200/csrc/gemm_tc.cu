@@ -57,6 +57,7 @@ struct TcArgs {
     int pipe;                                      // software-pipelined TMEM loads in the epilogue
     int spt;                                       // segments per tile (> 1: short segments, e.g. the spin blocks of a forward pass, are packed into one tile)
     int tma_store;                                 // plain epilogue through shared-memory staging + TMA tensor stores
+    int n_st;                                      // pipeline stages of the CTA-pair kernel
     long long *tl;                                 // debug timeline (DPE_GEMM_TIMELINE): [tile][4] clock64 stamps of CTA 0, or nullptr
 };
 
@@ -565,13 +566,15 @@ constexpr int T2_X_BYTES = 128 * TC_ROWB;                         // 8 KB (128 r
 constexpr int T2_STAGE_BYTES = 2 * T2_W_BYTES + 2 * T2_X_BYTES;   // 32 KB
 constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 4 * TC_OUT_BYTES + 1024;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+constexpr int T2_FUSED_EPI_WARPS = 16;             // fused epilogue: four warps per TMEM lane quarter, one (walker, electron) group each
+template <bool FUSED>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSED ? (6 + T2_FUSED_EPI_WARPS) * 32 : TC_THREADS, 1)
 k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
                   const __grid_constant__ CUtensorMap map_wl, const __grid_constant__ CUtensorMap map_c,
                   const __grid_constant__ CUtensorMap map_add, TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int n_st = a.epi == 1 ? 3 : T2_STAGES;       // the fused epilogue trades one stage for its addend buffers
+    const int n_st = a.n_st;                           // the fused epilogue may trade a stage for its addend buffers
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + n_st * T2_STAGE_BYTES);
     uint64_t *bar_full = bars;                      // [S] own TMA landed
     uint64_t *bar_split = bars + T2_STAGES;         // [S] leader only: both splitter groups done (one elected arrival per CTA:
@@ -582,8 +585,8 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint64_t *bar_afull = bar_tempty + 2;           // [2] addend tile of the fused epilogue landed (TMA)
     uint64_t *bar_aempty = bar_afull + 2;           // [2] ... and has been consumed
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_aempty + 2);
-    uint8_t *out_stage = smem + n_st * T2_STAGE_BYTES + 1024;
-    float *addbuf = reinterpret_cast<float *>(out_stage + 4 * TC_OUT_BYTES);      // [2 tiles][2 walkers][nch][128 features]
+    uint8_t *out_stage = smem + n_st * T2_STAGE_BYTES + 1024;                      // plain epilogue: TMA-store staging
+    float *addbuf = reinterpret_cast<float *>(smem + n_st * T2_STAGE_BYTES + 1024); // fused epilogue: [2 tiles][2 walkers][nch][128 features]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -595,8 +598,8 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_split[s], 2); mbar_init(&bar_empty[s], 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], a.epi == 1 ? 2 : 4);
-            mbar_init(&bar_afull[b], 1); mbar_init(&bar_aempty[b], 1);
+            mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], FUSED ? 2 * T2_FUSED_EPI_WARPS : 4);
+            mbar_init(&bar_afull[b], 1); mbar_init(&bar_aempty[b], T2_FUSED_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -619,7 +622,7 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 const int ft = (int)(t % a.n_ft);
                 const long rest = t / a.n_ft;
                 const int rt = (int)(rest % a.n_rt), seg = (int)(rest / a.n_rt);
-                if (a.epi == 1 && a.add) {
+                if (FUSED && a.add) {
                     // addends of this tile: one box of nch rows x 128 features per walker the tile touches (at most two)
                     const int slot = tcount & 1, m0 = rt * a.tile_rows;
                     const int rows_valid = min(a.tile_rows, a.seg_len - m0);
@@ -715,92 +718,92 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const int bar_id = 2 + g;
         uint32_t tph0 = 0, tph1 = 0;
         int buf = 0, chunk = 0, tcount = 0;
-        if (a.epi == 1) {
+        if constexpr (FUSED) {
             // Fused dense-layer epilogue (mlp.py:45-69 under the forward Laplacian; what k_act does in a separate pass):
             //   z = x W + bias + addend;  y = tanh(z_0), t_k = (1 - y^2) z_k, lap = (1 - y^2) z_lap - 2 y (1 - y^2) sum_k z_k^2.
-            // With the accumulators double buffered this runs under the next tile's MMAs.  One thread = one output feature,
-            // walking the rows of the tile in order (tiles hold whole (walker, electron) groups of nch rows), so the tanh state
-            // of a group lives in registers; group 0 of the epilogue warps does all of it, group 1 has nothing to do.
-            if (g == 0) {
-                float act_y = 0.f, act_d1 = 0.f, act_ssq = 0.f;
-                for (long t = pair; t < n_tiles; t += n_pairs, ++tcount) {
-                    const int ft = (int)(t % a.n_ft);
-                    const long rest = t / a.n_ft;
-                    const int rt = (int)(rest % a.n_rt), seg = (int)(rest / a.n_rt);
-                    const int m0 = rt * a.tile_rows;
-                    const int rows_valid = min(a.tile_rows, a.seg_len - m0);
-                    const int f = ft * TC_FEAT + (int)rank * 128 + q * 32 + lane;
-                    const bool f_ok = f < a.N_out;
-                    const float act_b = (f_ok && a.bias) ? a.bias[f] : 0.f;
-                    float *cbase = a.C + ((long)seg * a.c_seg_stride + a.c_seg_off + m0) * a.ldc + a.c_col_off + f;
-                    int cch = 0;                                              // channel of the current column
-                    long agrp = ((long)seg * a.seg_len + m0) / a.nch;         // global (walker, electron) group of the current column
-                    // addends: staged by the producer's TMA into addbuf[slot][walker in tile][channel][feature]
-                    const int slot = tcount & 1;
-                    int pe = (int)(agrp % a.gpa);                             // electron of the current group within its walker
-                    const float *arow = addbuf + (size_t)slot * 2 * a.nch * 128 + q * 32 + lane;
-                    if (a.add) mbar_wait(&bar_afull[slot], ((uint32_t)tcount >> 1) & 1u);
-                    mbar_wait(&bar_tfull[buf], buf ? tph1 : tph0);
-                    tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
-                    uint32_t v[16];
-                    for (int c0 = 0; c0 < a.nmma; c0 += 16, ++chunk) {
-                        tmem_ld16(taddr + c0, v);
+            // With the accumulators double buffered it runs under the next tile's MMAs.  One thread = one output feature and one
+            // (walker, electron) group of nch rows at a time: the tanh state of a group lives in registers.  The walk over a
+            // group is a dependent chain (~180 clocks per row for a lone warp), so each TMEM lane quarter gets four warps that
+            // take the groups of a tile round robin; results go straight to global memory (coalesced 128 B per warp and row).
+            const int k4 = (warp - 6) >> 2;                            // which of the four warps of this lane quarter
+            const bool has_add = a.add != nullptr;
+            for (long t = pair; t < n_tiles; t += n_pairs, ++tcount) {
+                const int ft = (int)(t % a.n_ft);
+                const long rest = t / a.n_ft;
+                const int rt = (int)(rest % a.n_rt), seg = (int)(rest / a.n_rt);
+                const int m0 = rt * a.tile_rows;
+                const int rows_valid = min(a.tile_rows, a.seg_len - m0);
+                const int n_grp = (rows_valid + a.nch - 1) / a.nch;
+                const int f = ft * TC_FEAT + (int)rank * 128 + q * 32 + lane;
+                const bool f_ok = f < a.N_out;
+                const float act_b = (f_ok && a.bias) ? a.bias[f] : 0.f;
+                float *cbase = a.C + ((long)seg * a.c_seg_stride + a.c_seg_off + m0) * a.ldc + a.c_col_off + f;
+                const long agrp = ((long)seg * a.seg_len + m0) / a.nch;    // global (walker, electron) group of column 0
+                const int e0 = (int)(agrp % a.gpa);                        // its electron index within the walker
+                const int slot = tcount & 1;
+                if (a.add) mbar_wait(&bar_afull[slot], ((uint32_t)tcount >> 1) & 1u);
+                mbar_wait(&bar_tfull[buf], buf ? tph1 : tph0);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+                for (int gi = k4; gi < n_grp; gi += 4) {
+                    // the 16-column TMEM loads start at the group's first row, so the channel of register j of chunk c is 16 c + j:
+                    // the value column is (0, 0), everything else is a tangent except channel nch - 1 (the Laplacian)
+                    const int col0 = gi * a.nch;
+                    const int n_valid = min(a.nch, rows_valid - col0);         // rows of this group inside the segment (all of them, normally)
+                    const float *arow = addbuf + ((size_t)(slot * 2 + (e0 + gi) / a.gpa) * a.nch) * 128 + q * 32 + lane;
+                    float *crow = cbase + (long)col0 * a.ldc;
+                    float act_y = 0.f, act_d1 = 0.f, act_ssq = 0.f;
+                    for (int cc = 0; cc < a.nch; cc += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(taddr + col0 + cc, v);
                         tmem_ld_wait();
-                        if (c0 + 16 >= a.nmma) tc_fence_before();
-                        float o[16];
+                        if (cc == 0) {
+                            const float z0 = (__uint_as_float(v[0]) + act_b) + (has_add ? arow[0] : 0.f);   // k_act's order: bias, then addend
+                            act_y = tanhf(z0);
+                            act_d1 = 1.f - act_y * act_y;
+                        }
+                        if (cc + 16 < a.nch && cc + 16 <= n_valid && has_add && f_ok) {
+                            // interior chunk: 16 tangent channels (or the value + 15 tangents), no bounds, no Laplacian column
+                            {
+                                const float z = __uint_as_float(v[0]) + arow[0];
+                                float o = act_d1 * z;
+                                if (cc == 0) o = act_y; else act_ssq = fmaf(z, z, act_ssq);
+                                *crow = o;
+                                crow += a.ldc;
+                            }
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            o[j] = 0.f;
-                            if (c0 + j < rows_valid) {
-                                float z = __uint_as_float(v[j]);
-                                const float adv = a.add ? arow[cch * 128] : 0.f;
-                                if (cch == 0) {
-                                    z += act_b;
-                                    z += adv;
-                                    act_y = tanhf(z);
-                                    act_d1 = 1.f - act_y * act_y;
-                                    act_ssq = 0.f;
-                                    o[j] = act_y;
-                                } else if (cch < a.nch - 1) {
-                                    z += adv;
-                                    act_ssq = fmaf(z, z, act_ssq);
-                                    o[j] = act_d1 * z;
-                                } else {
-                                    z += adv;
-                                    o[j] = act_d1 * z - 2.f * act_y * act_d1 * act_ssq;
+                            for (int j = 1; j < 16; ++j) {
+                                const float z = __uint_as_float(v[j]) + arow[j * 128];
+                                act_ssq = fmaf(z, z, act_ssq);
+                                *crow = act_d1 * z;
+                                crow += a.ldc;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int cch = cc + j;
+                                if (cch < n_valid) {
+                                    const float z = __uint_as_float(v[j]) + (has_add ? arow[j * 128] : 0.f);
+                                    float o = act_d1 * z;
+                                    if (cch == a.nch - 1) o = o - 2.f * act_y * act_d1 * act_ssq;
+                                    else act_ssq = fmaf(z, z, act_ssq);
+                                    if (j == 0 && cc == 0) { o = act_y; act_ssq = 0.f; }
+                                    if (f_ok) *crow = o;
                                 }
-                                if (++cch == a.nch) {
-                                    cch = 0;
-                                    if (++pe == a.gpa) { pe = 0; arow += (size_t)a.nch * 128; }      // next walker of the tile
-                                }
+                                crow += a.ldc;
                             }
                         }
-                        if (elected) tma_store_wait_read<1>();
-                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                        if (elected && c0 + 16 >= a.nmma) mbar_arrive_cluster_relaxed(mapa_u32(&bar_tempty[buf], 0));
-                        const bool full_chunk = c0 + 16 <= rows_valid;       // a chunk that crosses the end of the tile must not touch
-                        if (full_chunk) {                                     // the rows after it (they belong to the next tile)
-                            float *st = stage_base + (chunk & 1) * (TC_OUT_BYTES / 4) + q * 32 + lane;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) st[j * 128] = o[j];
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        } else if (f_ok) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (c0 + j < rows_valid) cbase[(long)(c0 + j) * a.ldc] = o[j];
-                        }
-                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                        if (elected) {
-                            if (full_chunk) tma_store_3d(&map_c, stage_base + (chunk & 1) * (TC_OUT_BYTES / 4), ft * TC_FEAT + (int)rank * 128, m0 + c0, seg);
-                            tma_store_commit();
-                        }
+                        arow += 16 * 128;
                     }
-                    if (elected && a.add) mbar_arrive(&bar_aempty[slot]);      // every thread passed the last chunk's barriers: addends consumed
-                    if (buf) tph1 ^= 1; else tph0 ^= 1;
-                    buf ^= 1;
                 }
-                if (elected) tma_store_wait_all();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_cluster_relaxed(mapa_u32(&bar_tempty[buf], 0));      // this warp's share of the accumulator is drained
+                    if (a.add) mbar_arrive(&bar_aempty[slot]);
+                }
+                if (buf) tph1 ^= 1; else tph0 ^= 1;
+                buf ^= 1;
             }
         } else {
         for (long t = pair; t < n_tiles; t += n_pairs, ++tcount) {
@@ -955,8 +958,10 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     if (a.epi) {
         // group-aligned tiles: a tile owns whole (walker, electron) groups of C rows
         if (a.nch > 256 || seg_len % a.nch) return DPE_ERR_UNSUPPORTED;
-        const int n_groups = seg_len / a.nch, g_max = 256 / a.nch;
-        const int n_rt = (n_groups + g_max - 1) / g_max, gpt = (n_groups + n_rt - 1) / n_rt;
+        const int n_groups = seg_len / a.nch;
+        int g_max = 256 / a.nch;
+        const int pair_mode = tc_pair_mode();
+        const int n_rt = (n_groups + g_max - 1) / g_max, gpt = (pair_mode > 1 && a.epi == 1) ? g_max : (n_groups + n_rt - 1) / n_rt;
         a.tile_rows = gpt * a.nch;
         a.nmma = (a.tile_rows + 15) / 16 * 16;
         a.n_rt = n_rt;
@@ -1019,16 +1024,20 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
         DPE_CUDA(cudaMemsetAsync(a.tl, 0, TC_TL_TILES * 8 * sizeof(long long), s));
     }
     bool launched_pair = false;
-    static const int use_pair = getenv("DPE_TC_2CTA") ? atoi(getenv("DPE_TC_2CTA")) : 0;
-    bool pair_ok = use_pair && have_map_c && n_tiles >= m->n_sm && ((a.nmma + 31) & ~31) <= 256;
+    const int use_pair = tc_pair_mode();
+    // (the fused path must not depend on the batch size: chunked and single-pass evaluation have to agree bit for bit)
+    bool pair_ok = use_pair && ((a.nmma + 31) & ~31) <= 256 && a.spt == 1 && (a.epi == 1 || (a.epi == 0 && have_map_c && n_tiles >= m->n_sm));
     size_t smem2 = T2_SMEM_BYTES;
-    CUtensorMap map_add = map_c;
+    a.n_st = T2_STAGES;
+    CUtensorMap map_add = map_x;
     if (pair_ok && a.epi == 1) {
-        // fused tanh-rule epilogue: addend tiles ([2 tiles][2 walkers][nch][128 features]) live in shared memory next to 3 stages;
+        // fused tanh-rule epilogue: addend tiles ([2 tiles][2 walkers][nch][128 features]) live in shared memory;
         // a tile must not touch more than two walkers
         const int gpt = a.tile_rows / a.nch;
-        smem2 = 3 * T2_STAGE_BYTES + 1024 + 4 * TC_OUT_BYTES + (size_t)4 * a.nch * 512 + 1024;
-        if (gpt > a.gpa || smem2 > 227 * 1024 || (g.N & 3)) pair_ok = false;
+        const size_t add_bytes = (size_t)4 * a.nch * 512;
+        a.n_st = (T2_STAGES * T2_STAGE_BYTES + 1024 + add_bytes + 1024 <= 227 * 1024) ? T2_STAGES : 3;
+        smem2 = (size_t)a.n_st * T2_STAGE_BYTES + 1024 + add_bytes + 1024;
+        if (gpt > a.gpa || smem2 > 227 * 1024 || (g.N & 3) || use_pair < 2) pair_ok = false;
         if (pair_ok && g.add) {
             const long n_walkers = ((long)n_seg * seg_len / a.nch) / a.gpa;
             cuuint64_t adims[2] = {(cuuint64_t)g.N, (cuuint64_t)(n_walkers * a.nch)};
@@ -1051,13 +1060,22 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
         CUresult r2 = enc(&map_x2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box2, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r2 == CUDA_SUCCESS) {
-            static size_t attr2 = 0;
-            if (smem2 > attr2) {
-                DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc2_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                attr2 = smem2;
+            static size_t attr_plain = 0, attr_fused = 0;
+            const long pairs_wanted = n_tiles < m->n_sm / 2 ? n_tiles : m->n_sm / 2;
+            const int grid2 = (int)pairs_wanted * 2;
+            if (a.epi == 1) {
+                if (smem2 > attr_fused) {
+                    DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc2_3xtf32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                    attr_fused = smem2;
+                }
+                k_gemm_tc2_3xtf32<true><<<grid2, (6 + T2_FUSED_EPI_WARPS) * 32, smem2, s>>>(map_x2, w->map_hi128, w->map_lo128, map_c, map_add, a);
+            } else {
+                if (smem2 > attr_plain) {
+                    DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc2_3xtf32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                    attr_plain = smem2;
+                }
+                k_gemm_tc2_3xtf32<false><<<grid2, TC_THREADS, smem2, s>>>(map_x2, w->map_hi128, w->map_lo128, map_c, map_add, a);
             }
-            const int grid2 = (m->n_sm / 2) * 2;
-            k_gemm_tc2_3xtf32<<<grid2, TC_THREADS, smem2, s>>>(map_x2, w->map_hi128, w->map_lo128, map_c, map_add, a);
             launched_pair = true;
         } else if (a.epi == 1 && !force_fuse) {
             return DPE_ERR_UNSUPPORTED;
