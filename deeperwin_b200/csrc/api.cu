@@ -286,22 +286,30 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
         if ((e = launch_tao_orbitals(m, r, Bc, C, tg, mo, s))) return e;
     } else {
     // backflow factors (envelope_orbitals.py:46-75): spin-up / spin-down electrons use different matrices
-    bool env_fused = true;
-    for (int sp = 0; sp < 2; ++sp) {
-        GemmArgs g = plain_gemm(x[cur], ldx, m->bf_w[sp], cols, mo, cols, Bc * (sp ? D : U) * C, cols, dl);
-        g.a_seg_len = g.c_seg_len = (sp ? D : U) * C;
-        g.a_seg_stride = g.c_seg_stride = N * C;
-        g.a_seg_off = g.c_seg_off = sp ? U * C : 0;
-        // The fused envelope epilogue is correct but slower than the separate k_envelope pass as long as the GEMM epilogue
-        // cannot overlap the next tile's MMAs (both TMEM accumulators are in use): measured N2 45.3 vs 41.5 ms/step.
-        static const bool fuse_env = getenv("DPE_FUSE_ENVELOPE") != nullptr;
-        if (fuse_env) {
-            g.epi = 2; g.n_ch = C; g.r = r; g.R = m->R_dev; g.spa = m->sp_alpha[sp]; g.envw = m->env_w[sp];
-            g.n_el = N; g.n_ion = d.n_ion; g.el_base = sp ? U : 0;
+    // The envelope is applied in the epilogue of the CTA-pair kernel (double-buffered accumulators: it overlaps the next tile's
+    // MMAs); in the single-CTA kernel the same fusion is exposed and slower (measured N2 45.3 vs 41.5 ms/step), there, on the
+    // SIMT path and in the forward pass (short packed segments) k_envelope runs as a separate pass.
+    static const bool fuse_env_on = getenv("DPE_FUSE_ENVELOPE") != nullptr || (tc_pair_mode() > 1 && !getenv("DPE_NO_FUSE_ENVELOPE"));
+    bool want_fused = fuse_env_on && C > 1, env_fused = false;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        bool all_fused = true;
+        for (int sp = 0; sp < 2; ++sp) {
+            GemmArgs g = plain_gemm(x[cur], ldx, m->bf_w[sp], cols, mo, cols, Bc * (sp ? D : U) * C, cols, dl);
+            g.a_seg_len = g.c_seg_len = (sp ? D : U) * C;
+            g.a_seg_stride = g.c_seg_stride = N * C;
+            g.a_seg_off = g.c_seg_off = sp ? U * C : 0;
+            if (want_fused) {
+                g.epi = 2; g.n_ch = C; g.r = r; g.R = m->R_dev; g.spa = m->sp_alpha[sp]; g.envw = m->env_w[sp];
+                g.n_el = N; g.n_ion = d.n_ion; g.el_base = sp ? U : 0;
+            }
+            bool fused = false;
+            if ((e = gemm(m, g, s, &fused))) return e;
+            all_fused = all_fused && fused;
+            if (want_fused && !fused) break;        // this shape has no fused kernel: redo both spin blocks plainly
         }
-        bool fused = false;
-        if ((e = gemm(m, g, s, &fused))) return e;
-        env_fused = env_fused && fused;
+        env_fused = want_fused && all_fused;
+        if (env_fused || !want_fused) break;
+        want_fused = false;
     }
     if (!env_fused && (e = launch_envelope(m, r, Bc, C, mo, s))) return e;
     }

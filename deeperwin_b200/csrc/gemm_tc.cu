@@ -750,6 +750,55 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     // the value column is (0, 0), everything else is a tangent except channel nch - 1 (the Laplacian)
                     const int col0 = gi * a.nch;
                     const int n_valid = min(a.nch, rows_valid - col0);         // rows of this group inside the segment (all of them, normally)
+                    if (a.epi == 2) {
+                        // envelope multiply of the backflow GEMM (envelope_orbitals.py:96-127) with the product rule -- what k_envelope does
+                        // in a separate in-place pass.  env = sum_J w_J exp(-alpha_J |r_i - R_J|) for this (electron, orbital column); only
+                        // the electron's own three tangent channels and the Laplacian channel get extra terms.
+                        const int i = a.el_base + m0 / a.nch + gi;
+                        const int ci = 1 + 3 * i;
+                        float env = 0.f, e1x = 0.f, e1y = 0.f, e1z = 0.f, el = 0.f;
+                        if (f_ok) {
+                            const float *ri = a.r + ((long)seg * a.n_el + i) * 3;
+                            const float rx = ri[0], ry = ri[1], rz = ri[2];
+                            for (int J = 0; J < a.n_ion; ++J) {
+                                const float dx = rx - a.R[J * 3], dy = ry - a.R[J * 3 + 1], dz = rz - a.R[J * 3 + 2];
+                                const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                                const float al = a.spa[(long)J * a.N_out + f];
+                                const float e = __fmul_rn(a.envw[(long)J * a.N_out + f], expf(-al * d));
+                                env = __fadd_rn(env, e);
+                                if (a.nch > 1) {
+                                    const float inv = 1.f / d, ge = -al * e * inv;
+                                    e1x = fmaf(ge, dx, e1x); e1y = fmaf(ge, dy, e1y); e1z = fmaf(ge, dz, e1z);
+                                    el = fmaf(e, al * al - 2.f * al * inv, el);
+                                }
+                            }
+                        }
+                        float bf0 = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
+                        float *crow = cbase + (long)col0 * a.ldc;
+                        for (int cc = 0; cc < a.nch; cc += 16) {
+                            uint32_t v[16];
+                            tmem_ld16(taddr + col0 + cc, v);
+                            tmem_ld_wait();
+                            if (cc == 0) bf0 = __uint_as_float(v[0]);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int cch = cc + j;
+                                if (cch < n_valid) {
+                                    const float val = __uint_as_float(v[j]);
+                                    float o = val * env;
+                                    if (a.nch > 1) {
+                                        if (cch == ci) { tx = val; o += e1x * bf0; }
+                                        else if (cch == ci + 1) { ty = val; o += e1y * bf0; }
+                                        else if (cch == ci + 2) { tz = val; o += e1z * bf0; }
+                                        else if (cch == a.nch - 1) o += el * bf0 + 2.f * (e1x * tx + e1y * ty + e1z * tz);
+                                    }
+                                    if (f_ok) *crow = o;
+                                }
+                                crow += a.ldc;
+                            }
+                        }
+                        continue;
+                    }
                     const float *arow = addbuf + ((size_t)(slot * 2 + (e0 + gi) / a.gpa) * a.nch) * 128 + q * 32 + lane;
                     float *crow = cbase + (long)col0 * a.ldc;
                     float act_y = 0.f, act_d1 = 0.f, act_ssq = 0.f;
@@ -1026,7 +1075,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     bool launched_pair = false;
     const int use_pair = tc_pair_mode();
     // (the fused path must not depend on the batch size: chunked and single-pass evaluation have to agree bit for bit)
-    bool pair_ok = use_pair && ((a.nmma + 31) & ~31) <= 256 && a.spt == 1 && (a.epi == 1 || (a.epi == 0 && have_map_c && n_tiles >= m->n_sm));
+    bool pair_ok = use_pair && ((a.nmma + 31) & ~31) <= 256 && a.spt == 1 && (a.epi >= 1 || (a.epi == 0 && have_map_c && n_tiles >= m->n_sm));
     size_t smem2 = T2_SMEM_BYTES;
     a.n_st = T2_STAGES;
     CUtensorMap map_add = map_x;
@@ -1050,9 +1099,14 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
             if (ra != CUDA_SUCCESS) pair_ok = false;
         }
     }
-    // the fused tanh-rule epilogue is only worth running where it overlaps the MMAs (double-buffered accumulators of the pair kernel)
-    static const bool force_fuse = getenv("DPE_FUSE_ACT") != nullptr;
-    if (a.epi == 1 && !pair_ok && !force_fuse) return DPE_ERR_UNSUPPORTED;
+    if (pair_ok && a.epi == 2) {
+        smem2 = (size_t)T2_STAGES * T2_STAGE_BYTES + 1024 + 1024;
+        if (use_pair < 2) pair_ok = false;
+    }
+    // the fused epilogues are only worth running where they overlap the MMAs (double-buffered accumulators of the pair kernel)
+    static const bool force_act = getenv("DPE_FUSE_ACT") != nullptr, force_env = getenv("DPE_FUSE_ENVELOPE") != nullptr;
+    const bool force_fuse = a.epi == 1 ? force_act : force_env;
+    if (a.epi && !pair_ok && !force_fuse) return DPE_ERR_UNSUPPORTED;
     if (pair_ok) {
         if (a.nmma & 31) a.nmma = (a.nmma + 31) & ~31;            // each CTA of the pair loads half of the MMA N rows
         CUtensorMap map_x2;
@@ -1063,7 +1117,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
             static size_t attr_plain = 0, attr_fused = 0;
             const long pairs_wanted = n_tiles < m->n_sm / 2 ? n_tiles : m->n_sm / 2;
             const int grid2 = (int)pairs_wanted * 2;
-            if (a.epi == 1) {
+            if (a.epi) {
                 if (smem2 > attr_fused) {
                     DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc2_3xtf32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
                     attr_fused = smem2;
@@ -1077,7 +1131,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
                 k_gemm_tc2_3xtf32<false><<<grid2, TC_THREADS, smem2, s>>>(map_x2, w->map_hi128, w->map_lo128, map_c, map_add, a);
             }
             launched_pair = true;
-        } else if (a.epi == 1 && !force_fuse) {
+        } else if (a.epi && !force_fuse) {
             return DPE_ERR_UNSUPPORTED;
         }
     }
