@@ -314,7 +314,9 @@ def run_ours(args):
             traffic = t["dram_bytes_per_launch"] if t else None
         roofline = {"bound": "tensor", "kernel": prof["kernel"], "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
                     "frac": ach / tensor_peak, "traffic": traffic,
-                    "launch_shape": "largest-FLOP launches of the class (main embedding layers: rows = walkers x electrons x (3N+2), K = 320, N_out = 256)",
+                    "launch_shape": "largest-FLOP launches of the class (main embedding layers: rows = walkers x electrons x (3N+2), K = 320, N_out = 256)"
+                                    + ("; the CTA-pair kernel's launch also applies bias + spin-mean addend + tanh rule in its epilogue "
+                                       "(the separate k_act pass it replaces is not counted as FLOPs)" if prof["kernel"] == "k_gemm_tc2_3xtf32" else ""),
                     "class_achieved": prof["class_flops"] / (prof["class_ms"] * 1e-3) / 1e12, "class_launches": prof["class_count"],
                     "peak_source": f"{pk['source']}: bf16 {pk['bf16_tflops']} TF/s / 6 (3xTF32 FP32-accurate tensor peak)",
                     "launches": prof["count"], "avg_launch_ms": prof["ms"] / max(prof["count"], 1),

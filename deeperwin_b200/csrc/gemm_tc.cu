@@ -1136,7 +1136,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
         }
     }
     if (!launched_pair) k_gemm_tc_3xtf32<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(map_x, w->map_hi, w->map_lo, map_c, a);
-    m->last_gemm_class = 3;
+    m->last_gemm_class = launched_pair ? 4 : 3;
     DPE_LAUNCH_CHECK(m);
     if (tl_on) {
         std::vector<long long> h(TC_TL_TILES * 8);

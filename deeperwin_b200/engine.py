@@ -221,7 +221,8 @@ class Engine:
     def set_gemm_path(self, path: int):
         check(self.lib.dpe_set_gemm_path(self.handle, path), "dpe_set_gemm_path")
 
-    GEMM_CLASSES = {0: "k_gemm_simt<128,128,8,8>", 1: "k_gemm_simt<128,64,8,4>", 2: "k_gemm_simt<256,32,8,4>", 3: "k_gemm_tc_3xtf32"}
+    GEMM_CLASSES = {0: "k_gemm_simt<128,128,8,8>", 1: "k_gemm_simt<128,64,8,4>", 2: "k_gemm_simt<256,32,8,4>", 3: "k_gemm_tc_3xtf32",
+                    4: "k_gemm_tc2_3xtf32"}
 
     def profile_gemms(self, fn):
         """Runs fn() once with per-launch CUDA-event timing of the dense-layer GEMMs (bench.py roofline).
