@@ -88,19 +88,24 @@ class MCMCState:
     @classmethod
     def initialize_around_nuclei(cls, n_walkers, physical_config: PhysicalConfig, init_method, spin_initialization, rng,
                                  device="cuda"):
-        """mcmc.py:39-91 for init_method='gaussian', spin_initialization='el_ion_mapping' (the exponential
-        radial pdf, orbitals.py:894-928, is a 'next' row of the scope table)."""
+        """mcmc.py:39-91 for spin_initialization='el_ion_mapping': init_method 'gaussian' (unit normal around the mapped nucleus)
+        or 'exponential' (the reference's default: per-shell exponential radial pdf with Slater-rule exponents,
+        orbitals.py:854-928, utils/utils.py:387-506).  Setup-time host logic on top of the library's threefry streams."""
         if spin_initialization != "el_ion_mapping":
             raise NotImplementedError(f"Unknown spin initialization: {spin_initialization}")
-        if init_method != "gaussian":
-            raise NotImplementedError(f"initialization '{init_method}' is not part of the B200 hot path; use 'gaussian'")
+        if init_method not in ("gaussian", "exponential"):
+            raise NotImplementedError(f"Unknown initialization: {init_method}")
         device = torch.device(device)
         keys = split(rng, 3, device).cpu()
         rng_r, rng = keys[0], keys[2]
         n_el = physical_config.n_electrons
-        r0 = normal(rng_r, (n_walkers, n_el, 3), device)
         R = torch.tensor(physical_config.R, dtype=torch.float32, device=device)
-        r0 = r0 + R[torch.tensor(physical_config.el_ion_mapping, dtype=torch.long, device=device)]
+        if init_method == "gaussian":
+            r0 = normal(rng_r, (n_walkers, n_el, 3), device)
+            r0 = r0 + R[torch.tensor(physical_config.el_ion_mapping, dtype=torch.long, device=device)]
+        else:
+            r0 = initialize_walkers_with_exponential_radial_pdf(rng_r, physical_config.R, physical_config.Z, n_walkers, n_el,
+                                                                 physical_config.n_up, physical_config.el_ion_mapping, device)
         return cls(r=r0, R=R, Z=torch.tensor(physical_config.Z, dtype=torch.int32, device=device),
                    log_psi_sqr=-torch.ones(n_walkers, dtype=torch.float32, device=device) * 1000,
                    walker_age=torch.zeros(n_walkers, dtype=torch.int32, device=device),
@@ -143,6 +148,90 @@ class MCMCState:
         return MCMCState(r=g(self.r), log_psi_sqr=g(self.log_psi_sqr), walker_age=g(self.walker_age), rng_state=g(self.rng_state),
                          R=self.R[0], Z=self.Z[0], stepsize=self.stepsize[0], step_nr=self.step_nr[0], acc_rate=self.acc_rate[0],
                          _step_nr_host=self._step_nr_host)
+
+
+# ---- exponential radial initialisation (setup time; orbitals.py:854-928, utils/utils.py:387-506) ---------------------------
+def uniform(key, shape, device="cuda") -> torch.Tensor:
+    """jax.random.uniform(key, shape) in [0, 1): ((bits >> 9) | 0x3F800000).view(f32) - 1 on the library's threefry bits."""
+    n = int(np.prod(shape)) if len(shape) else 1
+    bits = random_bits(key, n, device).cpu().numpy().astype(np.uint32)
+    u = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+    return torch.from_numpy(np.maximum(np.float32(0.0), u).reshape(shape)).to(device)
+
+
+def generate_exp_distributed(rng, batch_shape, k=1.0, device="cuda") -> torch.Tensor:
+    """utils/utils.py:387-506: radial pdf r^2 exp(-k r); radius by the tabulated inverse CDF (jnp.interp), direction from a
+    normalised Gaussian.  The table ordinates are the closed-form CDF (see _exp_radial_grid.py)."""
+    from ._exp_radial_grid import EXP_RADIAL_XP
+    xp = np.asarray(EXP_RADIAL_XP, np.float64)
+    Fp = 1.0 - np.exp(-xp) * (1.0 + xp + 0.5 * xp * xp)
+    keys = split(rng, 2, device).cpu()
+    key_uniform, key_gaussian = keys[0], keys[1]
+    r = normal(key_gaussian, tuple(batch_shape) + (3,), device)
+    u = uniform(key_uniform, tuple(batch_shape), device).cpu().numpy()
+    x = torch.from_numpy(np.interp(u, Fp, xp).astype(np.float32)).to(device)
+    return r / r.norm(dim=-1, keepdim=True) * (x / np.float32(k))[..., None]
+
+
+def _get_effective_charge(Z: int, n: int, s_lower_shell=0.85, s_same_shell=0.35):
+    """orbitals.py:854-877: Slater's rules."""
+    shielding = 0
+    for n_shell in range(1, n + 1):
+        n_in_shell = 2 * n_shell ** 2
+        if n_shell == n:
+            n_in_shell = min(Z - sum(2 * k ** 2 for k in range(1, n_shell)), n_in_shell) - 1
+            shielding += n_in_shell * s_same_shell
+        elif n_shell == n - 1:
+            shielding += n_in_shell * s_lower_shell
+        else:
+            shielding += n_in_shell
+    return max(Z - shielding, 1)
+
+
+def _get_electron_configuration(n_el: int):
+    """orbitals.py:880-891: electrons per principal quantum number, shells filled in Madelung order."""
+    order = "1s,2s,2p,3s,3p,4s,3d,4p,5s,4d,5p,6s,4f,5d,6p,5f,6d".split(",")
+    capacity = dict(s=2, p=6, d=10, f=14)
+    config: Dict[int, int] = {}
+    for shell in order:
+        if n_el <= 0:
+            break
+        n_here = min(n_el, capacity[shell[1]])
+        config[int(shell[0])] = config.get(int(shell[0]), 0) + n_here
+        n_el -= n_here
+    return config
+
+
+def initialize_walkers_with_exponential_radial_pdf(rng, R, Z, n_walkers, n_el, n_up, el_ion_mapping, device="cuda"):
+    """orbitals.py:894-928: per ion (one subkey each), per shell (one subkey each) exponential clouds with exponent 2 Z_eff / n;
+    spin-up electrons of all ions first, then spin-down."""
+    if n_el != len(el_ion_mapping):
+        raise ValueError("Number of electrons does not match the number of indices in el_ion_mapping")
+    mapping = np.asarray(el_ion_mapping)
+    r_up, r_dn = [], []
+    for ind_ion, (R_, Z_) in enumerate(zip(R, Z)):
+        ks = split(rng, 2, device).cpu()
+        subkey, rng = ks[0], ks[1]
+        n_up_ion = int((mapping[:n_up] == ind_ion).sum())
+        n_el_ion = int((mapping[n_up:] == ind_ion).sum()) + n_up_ion
+        if n_el_ion == 0:
+            continue
+        clouds, spin = [], []
+        n_el_left, n_up_left = n_el_ion, n_up_ion
+        for n, n_in_shell in _get_electron_configuration(n_el_ion).items():
+            ks = split(subkey, 2, device).cpu()
+            shell_key, subkey = ks[0], ks[1]
+            exponent = 2 * _get_effective_charge(int(Z_), n, 1.0, 0.7) / n
+            clouds.append(generate_exp_distributed(shell_key, [n_walkers, n_in_shell], exponent, device))
+            n_up_in_shell = max(min(n_in_shell // 2, n_up_left), n_in_shell - n_el_left + n_up_left)
+            spin += [0] * n_up_in_shell + [1] * (n_in_shell - n_up_in_shell)
+            n_up_left -= n_up_in_shell
+            n_el_left -= n_in_shell
+        r_atom = torch.cat(clouds, dim=1) + torch.tensor(R_, dtype=torch.float32, device=device)
+        is_up = torch.tensor(spin, device=device) == 0
+        r_up.append(r_atom[:, is_up, :])
+        r_dn.append(r_atom[:, ~is_up, :])
+    return torch.cat(r_up + r_dn, dim=1).contiguous()
 
 
 def _resize_array(x, new_length):

@@ -32,12 +32,97 @@ class OracleMCMCState:
     acc_rate: np.float32 = f32(0.0)
 
 
-def initialize_around_nuclei(n_walkers, R, Z, el_ion_mapping, seed) -> OracleMCMCState:
-    """mcmc.py:39-91 with init_method='gaussian', spin_initialization='el_ion_mapping'."""
+# ---- exponential radial initialisation (the reference's default `initialization: exponential`, configuration.py:1013) ----
+def _exp_radial_tables():
+    from ._exp_radial_grid import EXP_RADIAL_XP
+    xp = np.asarray(EXP_RADIAL_XP, np.float64)
+    return xp, 1.0 - np.exp(-xp) * (1.0 + xp + 0.5 * xp * xp)
+
+
+def generate_exp_distributed(rng, batch_shape, k=1.0):
+    """utils/utils.py:387-506: points with radial pdf r^2 exp(-k r): direction from a normalised Gaussian, radius from the tabulated
+    inverse CDF (jnp.interp) of a uniform sample."""
+    xp, Fp = _exp_radial_tables()
+    key_uniform, key_gaussian = threefry.split(rng)
+    r = threefry.normal(key_gaussian, tuple(batch_shape) + (3,))
+    u = threefry.uniform(key_uniform, tuple(batch_shape))
+    x = np.interp(u, Fp, xp).astype(f32)
+    return (r / np.linalg.norm(r, axis=-1, keepdims=True)).astype(f32) * (x / f32(k))[..., None]
+
+
+def get_effective_charge(Z, n, s_lower_shell=0.85, s_same_shell=0.35):
+    """orbitals.py:854-877 (Slater's rules)."""
+    shielding = 0
+    for n_shell in range(1, n + 1):
+        n_electrons_in_shell = 2 * n_shell ** 2
+        if n_shell == n:
+            n_el_in_lower_shells = sum(2 * k ** 2 for k in range(1, n_shell))
+            n_electrons_in_shell = min(Z - n_el_in_lower_shells, n_electrons_in_shell) - 1
+        if n_shell == n:
+            shielding += n_electrons_in_shell * s_same_shell
+        elif n_shell == n - 1:
+            shielding += n_electrons_in_shell * s_lower_shell
+        else:
+            shielding += n_electrons_in_shell
+    return max(Z - shielding, 1)
+
+
+def get_electron_configuration(n_el):
+    """orbitals.py:880-891: electrons per principal quantum number in Madelung order."""
+    shells = "1s,2s,2p,3s,3p,4s,3d,4p,5s,4d,5p,6s,4f,5d,6p,5f,6d".split(",")
+    cap = dict(s=2, p=6, d=10, f=14)
+    cfg = {}
+    while n_el > 0:
+        shell = shells.pop(0)
+        n_in = min(n_el, cap[shell[1]])
+        cfg[int(shell[0])] = cfg.get(int(shell[0]), 0) + n_in
+        n_el -= n_in
+    return cfg
+
+
+def _initialize_walkers_around_atom(rng, R, Z, n_walkers, n_el, n_up):
+    """orbitals.py:894-910."""
+    r, spin = [], []
+    for n, n_in_shell in get_electron_configuration(n_el).items():
+        subkey, rng = threefry.split(rng)
+        exponent = 2 * get_effective_charge(Z, n, 1.0, 0.7) / n
+        r.append(generate_exp_distributed(subkey, [n_walkers, n_in_shell], exponent))
+        n_up_in_shell = max(min(n_in_shell // 2, n_up), n_in_shell - n_el + n_up)
+        n_dn_in_shell = n_in_shell - n_up_in_shell
+        n_up -= n_up_in_shell
+        n_el -= n_in_shell
+        spin += [0] * n_up_in_shell + [1] * n_dn_in_shell
+    r = np.concatenate(r, axis=1) + np.asarray(R, f32)
+    is_up = np.array(spin) == 0
+    return r[:, is_up, :], r[:, ~is_up, :]
+
+
+def initialize_walkers_with_exponential_radial_pdf(rng, R, Z, n_walkers, n_el, n_up, el_ion_mapping):
+    """orbitals.py:913-928."""
+    assert n_el == len(el_ion_mapping)
+    up_map, dn_map = np.array(el_ion_mapping)[:n_up], np.array(el_ion_mapping)[n_up:]
+    r_up, r_dn = [], []
+    for ind_ion, (R_, Z_) in enumerate(zip(R, Z)):
+        subkey, rng = threefry.split(rng)
+        n_up_ion = int(sum(up_map == ind_ion))
+        n_el_ion = int(sum(dn_map == ind_ion)) + n_up_ion
+        if n_el_ion == 0:
+            continue
+        a_up, a_dn = _initialize_walkers_around_atom(subkey, R_, int(Z_), n_walkers, n_el_ion, n_up_ion)
+        r_up.append(a_up)
+        r_dn.append(a_dn)
+    return np.concatenate(r_up + r_dn, axis=1).astype(f32)
+
+
+def initialize_around_nuclei(n_walkers, R, Z, el_ion_mapping, seed, init_method="gaussian", n_up=None) -> OracleMCMCState:
+    """mcmc.py:39-91 with spin_initialization='el_ion_mapping'."""
     rng = threefry.prng_key(seed)
     rng_r, _rng_spin, rng = threefry.split(rng, 3)
     n_el = len(el_ion_mapping)
-    r0 = threefry.normal(rng_r, (n_walkers, n_el, 3)) + np.asarray(R, f32)[np.asarray(el_ion_mapping)]
+    if init_method == "gaussian":
+        r0 = threefry.normal(rng_r, (n_walkers, n_el, 3)) + np.asarray(R, f32)[np.asarray(el_ion_mapping)]
+    else:
+        r0 = initialize_walkers_with_exponential_radial_pdf(rng_r, R, Z, n_walkers, n_el, n_up, el_ion_mapping)
     return OracleMCMCState(
         r=r0.astype(f32), R=np.asarray(R, f32), Z=np.asarray(Z, np.int32),
         log_psi_sqr=-np.ones(n_walkers, f32) * f32(1000), walker_age=np.zeros(n_walkers, np.int32),

@@ -339,3 +339,22 @@ def test_clipping_variants_match_oracle(name, center, width_metric, from_prev):
         assert abs(float(new_state[1]) - float(rs[1])) <= 3e-5 * float(rs[1]), (n, float(new_state[1]), float(rs[1]))
         ok = ~torch.isnan(E)
         assert np.allclose(aux["E_loc_clipped"].cpu().numpy()[ok.numpy()], ra["E_loc_clipped"][ok.numpy()], rtol=2e-6, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["N2", "LiH", "Benzene"])
+def test_exponential_initialisation_matches_oracle(name):
+    """`initialization: exponential` (the reference's default, configuration.py:1013; orbitals.py:854-928): same threefry streams,
+    same Slater-rule shells -> the same walkers as the oracle (float32 interpolation differences only)."""
+    import deeperwin_b200 as dpe
+    from oracle import mcmc as omc
+    phys = dpe.PhysicalConfig(name=name)
+    st = dpe.MCMCState.initialize_around_nuclei(256, phys, "exponential", "el_ion_mapping", dpe.PRNGKey(77), device="cuda:0")
+    ref = omc.initialize_around_nuclei(256, phys.R, phys.Z, phys.el_ion_mapping, 77, "exponential", n_up=phys.n_up)
+    assert st.r.shape == (256, phys.n_electrons, 3) and st.r.dtype == torch.float32
+    assert np.allclose(st.r.cpu().numpy(), ref.r, rtol=2e-6, atol=2e-6)
+    assert np.array_equal(st.rng_state.cpu().numpy(), ref.rng_state)
+    # and the default MCMC configuration (initialization = exponential) now goes through resize_or_init
+    cfg = dpe.Configuration(physical=dict(name=name))
+    assert cfg.optimization.mcmc.initialization == "exponential"
+    st2 = dpe.MCMCState.resize_or_init(None, cfg.optimization.mcmc, phys, dpe.PRNGKey(77), device="cuda:0")
+    assert st2.r.shape == (cfg.optimization.mcmc.n_walkers, phys.n_electrons, 3) and torch.isfinite(st2.r).all()

@@ -55,3 +55,29 @@ def test_energy_statistics():
     assert np.nanmax(aux2["E_loc_clipped"]) <= c + w + 1e-3
     _, _, aux3 = omc.energy_statistics(E2, (c, w), name="hard")
     assert np.nanmax(aux3["E_loc_clipped"]) == f32(c + w)
+
+
+def test_exponential_radial_initialisation():
+    """The reference's default walker initialisation (orbitals.py:854-928, utils/utils.py:387-506), restated."""
+    # Slater-rule helpers on hand-checked cases
+    assert omc.get_electron_configuration(7) == {1: 2, 2: 5}
+    assert omc.get_electron_configuration(21) == {1: 2, 2: 8, 3: 9, 4: 2}            # 4s fills before 3d
+    assert abs(omc.get_effective_charge(7, 1, 1.0, 0.7) - 6.3) < 1e-12
+    assert abs(omc.get_effective_charge(7, 2, 1.0, 0.7) - 2.2) < 1e-12
+    assert omc.get_effective_charge(1, 1) == 1
+    # radial pdf r^2 exp(-k r): mean radius 3 / k, isotropic directions
+    r = omc.generate_exp_distributed(threefry.prng_key(3), [40000], k=2.0)
+    rad = np.linalg.norm(r, axis=-1)
+    assert abs(rad.mean() - 1.5) < 0.02 and abs((rad ** 2).mean() - 12 / 4.0) < 0.08
+    assert np.abs(r.mean(0)).max() < 0.02
+    # electrons end up around their mapped nucleus, spin-up block first
+    R, Z, mapping = [[0, 0, 0], [2.068, 0, 0]], [7, 7], [0, 0, 0, 0, 1, 1, 1, 0, 0, 0, 1, 1, 1, 1]
+    st = omc.initialize_around_nuclei(512, R, Z, mapping, 1234, "exponential", n_up=7)
+    assert st.r.shape == (512, 14, 3) and st.r.dtype == np.float32
+    d = np.stack([np.linalg.norm(st.r - np.asarray(Rk, np.float32), axis=-1).mean(0) for Rk in R])    # [ion, electron]
+    assert (d.argmin(0) == np.asarray(mapping)).all()
+    # the 1s electrons sit much closer than the n = 2 shell (exponents 2 * 6.3 vs 2.2)
+    assert d[0, 0] < 0.4 < d[0, 2]
+    # same seed -> same walkers; keys / ages as for the gaussian initialisation
+    st2 = omc.initialize_around_nuclei(512, R, Z, mapping, 1234, "exponential", n_up=7)
+    assert np.array_equal(st.r, st2.r) and np.array_equal(st.rng_state, omc.initialize_around_nuclei(512, R, Z, mapping, 1234).rng_state)
