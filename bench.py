@@ -124,7 +124,7 @@ class ClockSampler:
     inside 40 ms steps; the in-process queries do not.  Falls back to one-shot nvidia-smi samples if pynvml is missing."""
     REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=float(os.environ.get("DPE_BENCH_CLOCK_PERIOD", "0.05"))):
         self.rows, self.stop_flag, self.h = [], False, None
         self.period = period
         try:
