@@ -560,11 +560,12 @@ k_gemm_tc_rows_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_co
 // Cross-CTA signalling: splitters and epilogues of both CTAs arrive on the LEADER's mbarriers (mapa + .shared::cluster);
 // tcgen05.commit multicasts "stage free" / "accumulator full" to both CTAs.
 // ----------------------------------------------------------------------------------------------------------------
-constexpr int T2_STAGES = 4;
+constexpr int T2_STAGES = 6;                                     // upper bound; the launcher picks a.n_st <= T2_STAGES that fits
 constexpr int T2_W_BYTES = 128 * TC_ROWB;                         // 8 KB per hi / lo (128 features)
 constexpr int T2_X_BYTES = 128 * TC_ROWB;                         // 8 KB (128 rows)
 constexpr int T2_STAGE_BYTES = 2 * T2_W_BYTES + 2 * T2_X_BYTES;   // 32 KB
-constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 4 * TC_OUT_BYTES + 1024;
+constexpr int T2_PLAIN_STAGES = 6;
+constexpr int T2_SMEM_BYTES = T2_PLAIN_STAGES * T2_STAGE_BYTES + 1024 + 4 * TC_OUT_BYTES + 1024;
 
 constexpr int T2_FUSED_EPI_WARPS = 16;             // fused epilogue: four warps per TMEM lane quarter, one (walker, electron) group each
 template <bool FUSED>
@@ -1077,14 +1078,15 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     // (the fused path must not depend on the batch size: chunked and single-pass evaluation have to agree bit for bit)
     bool pair_ok = use_pair && ((a.nmma + 31) & ~31) <= 256 && a.spt == 1 && (a.epi >= 1 || (a.epi == 0 && have_map_c && n_tiles >= m->n_sm));
     size_t smem2 = T2_SMEM_BYTES;
-    a.n_st = T2_STAGES;
+    a.n_st = T2_PLAIN_STAGES;
     CUtensorMap map_add = map_x;
     if (pair_ok && a.epi == 1) {
         // fused tanh-rule epilogue: addend tiles ([2 tiles][2 walkers][nch][128 features]) live in shared memory;
         // a tile must not touch more than two walkers
         const int gpt = a.tile_rows / a.nch;
         const size_t add_bytes = (size_t)4 * a.nch * 512;
-        a.n_st = (T2_STAGES * T2_STAGE_BYTES + 1024 + add_bytes + 1024 <= 227 * 1024) ? T2_STAGES : 3;
+        a.n_st = T2_STAGES;
+        while (a.n_st > 3 && (size_t)a.n_st * T2_STAGE_BYTES + 1024 + add_bytes + 1024 > 227 * 1024) --a.n_st;
         smem2 = (size_t)a.n_st * T2_STAGE_BYTES + 1024 + add_bytes + 1024;
         if (gpt > a.gpa || smem2 > 227 * 1024 || (g.N & 3) || use_pair < 2) pair_ok = false;
         if (pair_ok && g.add) {
@@ -1100,7 +1102,8 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
         }
     }
     if (pair_ok && a.epi == 2) {
-        smem2 = (size_t)T2_STAGES * T2_STAGE_BYTES + 1024 + 1024;
+        a.n_st = T2_STAGES;
+        smem2 = (size_t)a.n_st * T2_STAGE_BYTES + 1024 + 1024;
         if (use_pair < 2) pair_ok = false;
     }
     // the fused epilogues are only worth running where they overlap the MMAs (double-buffered accumulators of the pair kernel)
