@@ -570,6 +570,56 @@ __global__ void __launch_bounds__(CV_FG * CV_CB) k_conv_dense(int N, int C, int 
     }
 }
 
+// Second version of the dense part.  The first one (k_conv_dense) walks j once per block of four electrons i and stages its
+// operands twice (two channel blocks): ncu counted 11 instructions per useful FMA.  Here a block = (walker, 8 features) covers ALL
+// channels, a thread = (channel, feature) keeps up to 16 electrons i in registers and walks j once: per j one LDS of hm and four
+// LDS.128 of w feed 16 FMAs.  Shared memory: w as [j][f][NP] (i fastest, NP = 20: the 8 features of a quarter warp hit distinct
+// banks), the hm slab as [j][c][f].
+constexpr int CV2_NP = 20;
+__global__ void __launch_bounds__(1024) k_conv_dense2(int N, int C, int CP, int emb, const float *__restrict__ hm,
+                                                      const float *__restrict__ pw, float *__restrict__ x, int ldx, int col_ee) {
+    extern __shared__ __align__(16) float sm[];
+    float *A_s = sm;                               // [j][f][NP]  (one block of <= 16 electrons i at a time)
+    float *B_s = A_s + N * CV_FG * CV2_NP;         // [j][c][f]
+    const int n_fg = emb / CV_FG;
+    const int fg = blockIdx.x % n_fg;
+    const long b = blockIdx.x / n_fg;
+    const int f0 = fg * CV_FG;
+    const int tid = threadIdx.x, f = tid & (CV_FG - 1), c = tid >> 3;       // blockDim.x = 8 * C
+    for (int j = 0; j < N; ++j)
+        B_s[(j * C + c) * CV_FG + f] = hm[((b * N + j) * (long)C + c) * emb + f0 + f];
+    for (int i0 = 0; i0 < N; i0 += 16) {
+        const int ni = min(16, N - i0);
+        __syncthreads();                           // previous i block consumed (and, first time, nothing)
+        for (int t = tid; t < N * CV2_NP * CV_FG; t += blockDim.x) {      // ff fastest: 8 threads share one 32-byte sector of pw
+            const int ff = t & (CV_FG - 1), ji = t >> 3, i = ji % CV2_NP, j = ji / CV2_NP;
+            A_s[(j * CV_FG + ff) * CV2_NP + i] = i < ni ? pw[(((b * N + i0 + i) * N) + j) * (long)CP * emb + f0 + ff] : 0.f;
+        }
+        __syncthreads();
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+        const float *ap = A_s + f * CV2_NP;
+        const float *bp = B_s + c * CV_FG + f;
+        for (int j = 0; j < N; ++j) {
+            const float h = bp[j * C * CV_FG];
+            const float4 w0 = *reinterpret_cast<const float4 *>(ap + j * CV_FG * CV2_NP);
+            const float4 w1 = *reinterpret_cast<const float4 *>(ap + j * CV_FG * CV2_NP + 4);
+            const float4 w2 = *reinterpret_cast<const float4 *>(ap + j * CV_FG * CV2_NP + 8);
+            const float4 w3 = *reinterpret_cast<const float4 *>(ap + j * CV_FG * CV2_NP + 12);
+            acc[0] = fmaf(w0.x, h, acc[0]); acc[1] = fmaf(w0.y, h, acc[1]); acc[2] = fmaf(w0.z, h, acc[2]); acc[3] = fmaf(w0.w, h, acc[3]);
+            acc[4] = fmaf(w1.x, h, acc[4]); acc[5] = fmaf(w1.y, h, acc[5]); acc[6] = fmaf(w1.z, h, acc[6]); acc[7] = fmaf(w1.w, h, acc[7]);
+            acc[8] = fmaf(w2.x, h, acc[8]); acc[9] = fmaf(w2.y, h, acc[9]); acc[10] = fmaf(w2.z, h, acc[10]); acc[11] = fmaf(w2.w, h, acc[11]);
+            acc[12] = fmaf(w3.x, h, acc[12]); acc[13] = fmaf(w3.y, h, acc[13]); acc[14] = fmaf(w3.z, h, acc[14]); acc[15] = fmaf(w3.w, h, acc[15]);
+        }
+        float *xp = x + (((b * N + i0) * (long)C) + c) * ldx + col_ee + f0 + f;
+        const long xstride = (long)C * ldx;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < ni) xp[i * xstride] = acc[i];
+    }
+}
+
 // Sparse part of the product rule (w depends on r_i, r_j only) and the expansion of conv_eI: one thread per (walker, i, f).
 //   d/dr_j  (j != i):  + w'_ij u_ij hm_j          d/dr_i:  - sum_j w'_ij u_ij hm_j
 //   Laplacian:  sum_j [ (2 w''_ij + 4 w'_ij / d_ij) hm_j + 2 w'_ij u_ij . (d hm_j/d r_j - d hm_j/d r_i) ]
@@ -651,12 +701,23 @@ int launch_conv(dpe_model *m, int it, const float *r, int Bc, int C, const float
         k_conv_fwd<<<Bc, 256, (size_t)N * emb * sizeof(float), s>>>(N, emb, p.dE, hm, pw, ei, x, ldx, p.d_in);
     } else {
         if (emb % CV_FG) return set_error(DPE_ERR_UNSUPPORTED, "conv: emb_dim=%d must be a multiple of %d", emb, CV_FG);
-        int NP = (N + 3) & ~3;
-        if ((NP & 7) == 0) NP += 4;
-        size_t smem = ((size_t)N * CV_FG * NP + (size_t)N * CV_CB * CV_FG) * sizeof(float);
-        if (smem > 48 * 1024) DPE_CUDA(cudaFuncSetAttribute(k_conv_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int n_cb = (C + CV_CB - 1) / CV_CB;
-        k_conv_dense<<<Bc * (emb / CV_FG) * n_cb, CV_FG * CV_CB, smem, s>>>(N, C, 3, emb, hm, pw, x, ldx, p.d_in);
+        static const bool old_dense = getenv("DPE_CONV_V1") != nullptr;
+        const size_t smem2 = ((size_t)N * CV_FG * CV2_NP + (size_t)N * C * CV_FG) * sizeof(float);
+        if (!old_dense && C * CV_FG <= 1024 && smem2 <= 200 * 1024) {
+            static size_t attr2 = 0;
+            if (smem2 > 48 * 1024 && smem2 > attr2) {
+                DPE_CUDA(cudaFuncSetAttribute(k_conv_dense2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                attr2 = smem2;
+            }
+            k_conv_dense2<<<Bc * (emb / CV_FG), C * CV_FG, smem2, s>>>(N, C, 3, emb, hm, pw, x, ldx, p.d_in);
+        } else {
+            int NP = (N + 3) & ~3;
+            if ((NP & 7) == 0) NP += 4;
+            size_t smem = ((size_t)N * CV_FG * NP + (size_t)N * CV_CB * CV_FG) * sizeof(float);
+            if (smem > 48 * 1024) DPE_CUDA(cudaFuncSetAttribute(k_conv_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int n_cb = (C + CV_CB - 1) / CV_CB;
+            k_conv_dense<<<Bc * (emb / CV_FG) * n_cb, CV_FG * CV_CB, smem, s>>>(N, C, 3, emb, hm, pw, x, ldx, p.d_in);
+        }
         DPE_LAUNCH_CHECK(m);
         long n_rows = (long)Bc * N;
         k_conv_special<<<(int)((n_rows + 7) / 8), 256, 0, s>>>(r, n_rows, N, C, emb, p.dE, hm, pw, ei, x, ldx, p.d_in);
