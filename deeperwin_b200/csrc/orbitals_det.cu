@@ -437,8 +437,10 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-template <bool LAP>
-__global__ void __launch_bounds__(128, 4) k_det_warp(int N, int C, int n_det, long n_mat, const float *__restrict__ mo,
+// FACTOR = the factor-only instantiation used with the tensor-core trace kernel: the SIMT tangent stage is compiled out, which halves
+// the registers; the Gauss-Jordan sweep is a latency-bound chain per warp, so the extra resident warps translate into throughput.
+template <bool LAP, bool FACTOR = false>
+__global__ void __launch_bounds__(128, (LAP && !FACTOR) ? 4 : 8) k_det_warp(int N, int C, int n_det, long n_mat, const float *__restrict__ mo,
                                                    float *__restrict__ det, float *__restrict__ ainv_hi,
                                                    float *__restrict__ ainv_lo, int NP) {
     extern __shared__ double smd[];
@@ -503,7 +505,7 @@ __global__ void __launch_bounds__(128, 4) k_det_warp(int N, int C, int n_det, lo
     if (lane == 0) { out[0] = (float)logdet; out[1] = sign; }
     if (!LAP) return;
 
-    if (ainv_hi) {     // factor-only mode (see k_det)
+    if (FACTOR || ainv_hi) {     // factor-only mode (see k_det)
         float *oh = ainv_hi + bd * (long)NP * NP, *ol = ainv_lo + bd * (long)NP * NP;
         const int sh = (dt * N) & 3;     // the TMA box starts at the 16-byte aligned column below det * N
         for (int e = lane; e < NP * NP; e += 32) {
@@ -515,6 +517,7 @@ __global__ void __launch_bounds__(128, 4) k_det_warp(int N, int C, int n_det, lo
         }
         return;
     }
+    if constexpr (!FACTOR) {
     // ---- tangent stage: two tangent directions per warp (half-warps), lane = column q of P_k -------------------------
     // P_k[o][q] = sum_i Ainv[o][i] dA_k[i][q]: per i one conflict-free LDS of dA_k[i][q] and four broadcast LDS.128 of the
     // row Ainv[:, i] feed 16 FMAs (the earlier row-strip version was shared-memory-bandwidth bound, ncu 84 %).
@@ -607,6 +610,7 @@ __global__ void __launch_bounds__(128, 4) k_det_warp(int N, int C, int n_det, lo
     t2 = warp_sum_d(t2);
     sum_g2 = warp_sum_d(sum_g2);
     if (lane == 0) out[2] = (float)(lap + (sum_g2 - t2));
+    }
 }
 
 int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *ainv, cudaStream_t s) {
@@ -629,7 +633,8 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *
     if (N <= 16 && !force_generic) {
         const size_t per_warp = ((size_t)N * 32 + ((lap && !tc) ? ((size_t)N * 16 + 2 * ((size_t)N * 16 + 16) + 2 * 272 + 8) / 2 + 2 : 0)) * sizeof(double);
         const long n_mat = (long)blocks;
-        if (lap) k_det_warp<true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, ah, al, NP);
+        if (lap && tc) k_det_warp<true, true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, ah, al, NP);
+        else if (lap) k_det_warp<true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, ah, al, NP);
         else k_det_warp<false><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, nullptr, nullptr, NP);
     } else {
         // 64 threads: one 8 x 8 tile of P per thread (N <= 64 -> at most 64 tiles) and one column of mo per thread

@@ -576,7 +576,8 @@ __global__ void __launch_bounds__(CV_FG * CV_CB) k_conv_dense(int N, int C, int 
 // LDS.128 of w feed 16 FMAs.  Shared memory: w as [j][f][NP] (i fastest, NP = 20: the 8 features of a quarter warp hit distinct
 // banks), the hm slab as [j][c][f].
 constexpr int CV2_NP = 20;
-__global__ void __launch_bounds__(1024) k_conv_dense2(int N, int C, int CP, int emb, const float *__restrict__ hm,
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_conv_dense2(int N, int C, int CP, int emb, const float *__restrict__ hm,
                                                       const float *__restrict__ pw, float *__restrict__ x, int ldx, int col_ee) {
     extern __shared__ __align__(16) float sm[];
     float *A_s = sm;                               // [j][f][NP]  (one block of <= 16 electrons i at a time)
@@ -623,7 +624,7 @@ __global__ void __launch_bounds__(1024) k_conv_dense2(int N, int C, int CP, int 
 // Sparse part of the product rule (w depends on r_i, r_j only) and the expansion of conv_eI: one thread per (walker, i, f).
 //   d/dr_j  (j != i):  + w'_ij u_ij hm_j          d/dr_i:  - sum_j w'_ij u_ij hm_j
 //   Laplacian:  sum_j [ (2 w''_ij + 4 w'_ij / d_ij) hm_j + 2 w'_ij u_ij . (d hm_j/d r_j - d hm_j/d r_i) ]
-__global__ void __launch_bounds__(256) k_conv_special(const float *__restrict__ r, long n_rows, int N, int C, int emb, int dE,
+__global__ void __launch_bounds__(256, 6) k_conv_special(const float *__restrict__ r, long n_rows, int N, int C, int emb, int dE,
                                                        const float *__restrict__ hm, const float *__restrict__ pw,
                                                        const float *__restrict__ ei, float *__restrict__ x, int ldx, int col_ee) {
     const long row = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);     // (b, i)
@@ -704,12 +705,17 @@ int launch_conv(dpe_model *m, int it, const float *r, int Bc, int C, const float
         static const bool old_dense = getenv("DPE_CONV_V1") != nullptr;
         const size_t smem2 = ((size_t)N * CV_FG * CV2_NP + (size_t)N * C * CV_FG) * sizeof(float);
         if (!old_dense && C * CV_FG <= 1024 && smem2 <= 200 * 1024) {
-            static size_t attr2 = 0;
-            if (smem2 > 48 * 1024 && smem2 > attr2) {
-                DPE_CUDA(cudaFuncSetAttribute(k_conv_dense2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                attr2 = smem2;
+            // small systems: 384-thread blocks at 3 blocks per SM (the kernel is latency bound: occupancy matters more than registers)
+            if (C * CV_FG <= 384 && smem2 <= 48 * 1024) {
+                k_conv_dense2<384, 4><<<Bc * (emb / CV_FG), C * CV_FG, smem2, s>>>(N, C, 3, emb, hm, pw, x, ldx, p.d_in);
+            } else {
+                static size_t attr2 = 0;
+                if (smem2 > 48 * 1024 && smem2 > attr2) {
+                    DPE_CUDA(cudaFuncSetAttribute(k_conv_dense2<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                    attr2 = smem2;
+                }
+                k_conv_dense2<1024, 1><<<Bc * (emb / CV_FG), C * CV_FG, smem2, s>>>(N, C, 3, emb, hm, pw, x, ldx, p.d_in);
             }
-            k_conv_dense2<<<Bc * (emb / CV_FG), C * CV_FG, smem2, s>>>(N, C, 3, emb, hm, pw, x, ldx, p.d_in);
         } else {
             int NP = (N + 3) & ~3;
             if ((NP & 7) == 0) NP += 4;
