@@ -228,8 +228,8 @@ __device__ __forceinline__ float group_sum(float v, float *red, int tid) {
     return s;
 }
 
-template <int T, bool LAP>
-__global__ void __launch_bounds__(T, T == 64 ? 6 : 3) k_det(int N, int C, int n_det, const float *__restrict__ mo, float *__restrict__ det,
+template <int T, bool LAP, bool FACTOR = false>      // FACTOR: factor-only instantiation (tangent stage compiled out), see k_det_warp
+__global__ void __launch_bounds__(T, FACTOR ? 12 : (T == 64 ? 6 : 3)) k_det(int N, int C, int n_det, const float *__restrict__ mo, float *__restrict__ det,
                                                                   float *__restrict__ ainv_hi, float *__restrict__ ainv_lo, int NP) {
     // The factorisation runs in FP64 (O(N^3) against the O(3N * N^3) FP32 tangent stage).
     extern __shared__ double smd[];
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(T, T == 64 ? 6 : 3) k_det(int N, int C, int n_
     if (tid == 0) { out[0] = (float)logdet; out[1] = sign; }
     if (!LAP) return;
 
-    if (ainv_hi) {     // factor-only mode: the tensor-core trace kernel (det_tc.cu) consumes AinvT[i][sh + q] = Ainv[q][i], tf32-split, zero padded
+    if (FACTOR || ainv_hi) {     // factor-only mode: the tensor-core trace kernel (det_tc.cu) consumes AinvT[i][sh + q] = Ainv[q][i], tf32-split, zero padded
         float *oh = ainv_hi + bd * (long)NP * NP, *ol = ainv_lo + bd * (long)NP * NP;
         const int sh = (dt * N) & 3;     // the TMA box starts at the 16-byte aligned column below det * N
         for (int e = tid; e < NP * NP; e += T) {
@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(T, T == 64 ? 6 : 3) k_det(int N, int C, int n_
         }
         return;
     }
+    if constexpr (!FACTOR) {
     // ---- tangent stage: P_k = Ainv dA_k in 8 x 8 register tiles (one tile per thread, nb x nb <= T tiles) -------------
     // Rows of AinvT / dA are stored permuted, [first halves of the 8-column chunks | second halves], so that the float4
     // loads of a quarter warp hit distinct banks; padded rows / columns are zero, which zeroes the padding of P.
@@ -421,6 +422,7 @@ __global__ void __launch_bounds__(T, T == 64 ? 6 : 3) k_det(int N, int C, int n_
     }
     tr2 = group_sum_d<T>(tr2, redd, tid);
     if (tid == 0) out[2] = (float)(lap + (sum_g2 - tr2));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -640,9 +642,11 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *
         // 64 threads: one 8 x 8 tile of P per thread (N <= 64 -> at most 64 tiles) and one column of mo per thread
         if (smem > 48 * 1024) {
             DPE_CUDA(cudaFuncSetAttribute(k_det<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DPE_CUDA(cudaFuncSetAttribute(k_det<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             DPE_CUDA(cudaFuncSetAttribute(k_det<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
-        if (lap) k_det<64, true><<<blocks, 64, smem, s>>>(N, C, d.n_dets, mo, det, ah, al, NP);
+        if (lap && tc) k_det<64, true, true><<<blocks, 64, smem, s>>>(N, C, d.n_dets, mo, det, ah, al, NP);
+        else if (lap) k_det<64, true><<<blocks, 64, smem, s>>>(N, C, d.n_dets, mo, det, ah, al, NP);
         else k_det<128, false><<<blocks, 128, smem, s>>>(N, C, d.n_dets, mo, det, nullptr, nullptr, NP);
     }
     DPE_LAUNCH_CHECK(m);
