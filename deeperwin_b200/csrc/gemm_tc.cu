@@ -1104,7 +1104,9 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     if (pair_ok && a.epi == 2) {
         a.n_st = T2_STAGES;
         smem2 = (size_t)a.n_st * T2_STAGE_BYTES + 1024 + 1024;
-        if (use_pair < 2) pair_ok = false;
+        // each lane quarter has four epilogue warps that take one (walker, electron) group each: with fewer than four groups per
+        // tile (3N+2 > 64) half of them idle and the walk over 100+ rows outlasts the MMAs (benzene: 44 ms fused vs 25 ms unfused)
+        if (use_pair < 2 || a.tile_rows / a.nch < 4) pair_ok = false;
     }
     // the fused epilogues are only worth running where they overlap the MMAs (double-buffered accumulators of the pair kernel)
     static const bool force_act = getenv("DPE_FUSE_ACT") != nullptr, force_env = getenv("DPE_FUSE_ENVELOPE") != nullptr;
