@@ -385,7 +385,7 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 // ----------------------------------------------------------------------------------------------------------------
 constexpr int TR_ROWS = 256;                       // rows per tile (2 x M=128)
 constexpr int TR_N = 32;                           // MMA N
-constexpr int TR_STAGES = 3;
+constexpr int TR_STAGES = 6;                       // upper bound; the launcher picks a.n_st so that stages + resident W fit
 constexpr int TR_X_BYTES = TR_ROWS * TC_ROWB;      // 16 KB
 constexpr int TR_STAGE_BYTES = 2 * TR_X_BYTES;     // raw->hi, lo
 constexpr int TR_WSLAB = TR_N * TC_ROWB;           // 2 KB per K slab per hi / lo
@@ -396,6 +396,7 @@ constexpr int TR_THREADS = 10 * 32;
 struct TrArgs {
     float *C; int ldc, c_col_off;
     int M, N_out, K;
+    int n_st;          // X stages (the kernel is HBM-latency bound: as many as fit next to the resident weights)
 };
 
 __global__ void __launch_bounds__(TR_THREADS, 1)
@@ -403,9 +404,10 @@ k_gemm_tc_rows_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_co
                       const __grid_constant__ CUtensorMap map_wl, TrArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
-    uint8_t *w_hi = smem + TR_STAGES * TR_STAGE_BYTES;          // [n_kb][32 rows x 64 B]
-    uint8_t *w_lo = w_hi + TR_MAX_KB * TR_WSLAB;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(w_lo + TR_MAX_KB * TR_WSLAB);
+    const int n_st = a.n_st, n_kbw = (a.K + TC_BK - 1) / TC_BK;
+    uint8_t *w_hi = smem + n_st * TR_STAGE_BYTES;               // [n_kb][32 rows x 64 B]
+    uint8_t *w_lo = w_hi + n_kbw * TR_WSLAB;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(w_lo + n_kbw * TR_WSLAB);
     uint64_t *bar_full = bars, *bar_split = bars + TR_STAGES, *bar_empty = bars + 2 * TR_STAGES;
     uint64_t *bar_tfull = bars + 3 * TR_STAGES;                 // [2]
     uint64_t *bar_tempty = bar_tfull + 2;                       // [2]
@@ -444,7 +446,7 @@ k_gemm_tc_rows_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_co
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     mbar_expect_tx(&bar_full[stage], TR_X_BYTES);
                     tma_load_3d(smem + stage * TR_STAGE_BYTES, &map_x, &bar_full[stage], kb * TC_BK, (int)(t * TR_ROWS), 0);
-                    if (++stage == TR_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == n_st) { stage = 0; phase ^= 1; }
                 }
         }
     } else if (warp == 1) {
@@ -475,7 +477,7 @@ k_gemm_tc_rows_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_co
                         }
                     }
                     tc_commit(&bar_empty[stage]);
-                    if (++stage == TR_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == n_st) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&bar_tfull[buf]);
                 if (buf) tph1 ^= 1; else tph0 ^= 1;
@@ -500,7 +502,7 @@ k_gemm_tc_rows_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_co
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&bar_split[stage]);
-                if (++stage == TR_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == n_st) { stage = 0; phase ^= 1; }
             }
     } else {
         const int q = warp & 3;
@@ -1171,16 +1173,21 @@ static int launch_gemm_tc_rows(dpe_model *m, const GemmArgs &g, const TcWeight *
     CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(g.A), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(DPE_ERR_CUDA, "cuTensorMapEncodeTiled(X rows) failed: %d", (int)r);
-    static bool attr_set = false;
-    if (!attr_set) {
-        DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc_rows_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM_BYTES));
-        attr_set = true;
-    }
     TrArgs a;
     a.C = g.C; a.ldc = g.ldc; a.c_col_off = g.c_col_off; a.M = g.M; a.N_out = g.N; a.K = g.K;
+    const int n_kb = (g.K + TC_BK - 1) / TC_BK;
+    const size_t fixed = 2 * (size_t)n_kb * TR_WSLAB + 1024 + 1024;
+    a.n_st = TR_STAGES;
+    while (a.n_st > 2 && (size_t)a.n_st * TR_STAGE_BYTES + fixed > 227 * 1024) --a.n_st;
+    const size_t smem_rows = (size_t)a.n_st * TR_STAGE_BYTES + fixed;
+    static size_t attr_rows = 0;
+    if (smem_rows > attr_rows) {
+        DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc_rows_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        attr_rows = smem_rows;
+    }
     long n_tiles = ((long)g.M + TR_ROWS - 1) / TR_ROWS;
     int grid = (int)(n_tiles < m->n_sm ? n_tiles : m->n_sm);
-    k_gemm_tc_rows_3xtf32<<<grid, TR_THREADS, TR_SMEM_BYTES, s>>>(map_x, w->map_hi, w->map_lo, a);
+    k_gemm_tc_rows_3xtf32<<<grid, TR_THREADS, smem_rows, s>>>(map_x, w->map_hi, w->map_lo, a);
     m->last_gemm_class = 3;
     DPE_LAUNCH_CHECK(m);
     return DPE_OK;
