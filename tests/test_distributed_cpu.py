@@ -49,6 +49,15 @@ def _worker(rank, world, port, ret):
         loss, st, aux = omc.energy_statistics(shard, omc.init_clipping_state(), allreduce_mean=ar)
         out["E_mean"], out["E_var"] = float(aux["E_mean"]), float(aux["E_var"])
         out["E_ref_mean"], out["E_ref_var"] = float(E.mean()), float(E.var())
+        # median-centred / MAE window (the sample configs): centre = all-reduced mean of the per-rank medians, exactly the
+        # reference's pmean(nanmedian(E)) (loss_function.py:20-21) -- not the median of the union
+        _, st_med, _ = omc.energy_statistics(shard, (np.float32(-5.0), np.float32(6.0)), center="median", width_metric="mae",
+                                             clip_by=3.0, allreduce_mean=ar)
+        out["med_center"], out["med_width"] = float(st_med[0]), float(st_med[1])
+        clipped = [(-5.0 + np.tanh((E[k * 32:(k + 1) * 32] + 5.0) / 6.0) * 6.0).astype(np.float32) for k in range(world)]
+        c_ref = np.float32(np.mean([np.float32(np.median(c)) for c in clipped]))
+        out["med_center_ref"] = float(c_ref)
+        out["med_width_ref"] = float(3.0 * np.mean([np.mean(np.abs(c - c_ref)) for c in clipped]))
         ret[rank] = out
     finally:
         dist.destroy_process_group()
@@ -65,3 +74,4 @@ def test_gloo_world_size_2():
         assert o["pmean"] == [1.5, 15.0] and o["psum"] == [3.0, 30.0]
         assert o["flat"] == [[0.5] * 3, [1.0] * 4]
         assert abs(o["E_mean"] - o["E_ref_mean"]) < 1e-5 and abs(o["E_var"] - o["E_ref_var"]) < 1e-4
+        assert abs(o["med_center"] - o["med_center_ref"]) < 1e-5 and abs(o["med_width"] - o["med_width_ref"]) < 1e-4
