@@ -254,18 +254,20 @@ k_det_trace_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const float *__restrict__ row = Q + mrow * QS;
                     const float *__restrict__ blk = Q + cl * N * QS;
                     const float qii = row[i];
-                    for (int d0 = 1; d0 <= n_pairs; d0 += 8) {         // operands of up to 8 pairs are fetched ahead of the arithmetic
-                        float pd[8], pb[8], pc[8];
+                    for (int d0 = 1; d0 <= n_pairs; d0 += 8) {         // operands of up to 8 pairs are fetched ahead of the arithmetic;
+                        float pd[8], pb[8], pc[8];                     // no branches: pairs past the end read row i itself and add 0
 #pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (d0 + u <= n_pairs) {
-                                int o = i + d0 + u;
-                                o = o >= N ? o - N : o;
-                                pd[u] = blk[o * QS + o]; pb[u] = row[o]; pc[u] = blk[o * QS + i];
-                            }
+                        for (int u = 0; u < 8; ++u) {
+                            int o = i + d0 + u;
+                            o = o >= N ? o - N : o;
+                            o = d0 + u <= n_pairs ? o : i;
+                            pd[u] = blk[o * QS + o]; pb[u] = row[o]; pc[u] = blk[o * QS + i];
+                        }
 #pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (d0 + u <= n_pairs) e2 = __fadd_rn(e2, minor2(qii, pd[u], pb[u], pc[u]));
+                        for (int u = 0; u < 8; ++u) {
+                            const float mm = minor2(qii, pd[u], pb[u], pc[u]);
+                            e2 = __fadd_rn(e2, d0 + u <= n_pairs ? mm : 0.f);
+                        }
                     }
                 }
                 if (mrow == N - 1) DT_TL(10, tcount);
