@@ -19,7 +19,7 @@ class DpeDims(C.Structure):
 
 class DpeMcmcConfig(C.Structure):
     _fields_ = [("max_age", C.c_int32), ("stepsize_update_interval", C.c_int32), ("target_acceptance_rate", C.c_float),
-                ("min_stepsize_scale", C.c_float), ("max_stepsize_scale", C.c_float)]
+                ("min_stepsize_scale", C.c_float), ("max_stepsize_scale", C.c_float), ("proposal", C.c_int32)]
 
 
 class DpeMcmcState(C.Structure):

@@ -194,7 +194,7 @@ class ModelConfigDeepErwin4(ConfigBaseclass):
 
 
 class MCMCSimpleProposalConfig(ConfigBaseclass):
-    name: Literal["normal"] = "normal"
+    name: Literal["normal", "cauchy", "normal_one_el"] = "normal"     # configuration.py:952-953
 
 
 class MCMCConfig(ConfigBaseclass):

@@ -505,6 +505,7 @@ int dpe_mcmc_steps(dpe_model *m, const dpe_mcmc_state *st, int32_t B, int32_t n_
     if (!st->r_dev || !st->log_psi_sqr_dev || !st->walker_age_dev || !st->rng_state_dev || !st->stepsize_dev || !st->step_nr_dev || !st->acc_rate_dev)
         return set_error(DPE_ERR_ARG, "mcmc_steps: state has null fields");
     if (n_steps > 0 && !accept_counts_dev) return set_error(DPE_ERR_ARG, "mcmc_steps: accept_counts_dev is null");
+    if (cfg->proposal < 0 || cfg->proposal > 2) return set_error(DPE_ERR_UNSUPPORTED, "mcmc_steps: proposal %d (0 normal, 1 cauchy, 2 normal_one_el)", cfg->proposal);
     cudaStream_t s = (cudaStream_t)stream;
     WsLayout L;
     plan_mcmc(m->dims, B, L);
@@ -519,7 +520,8 @@ int dpe_mcmc_steps(dpe_model *m, const dpe_mcmc_state *st, int32_t B, int32_t n_
         if ((e = run_batched(m, st->r_dev, B, 1, ws_net, ws_net_bytes, nullptr, st->log_psi_sqr_dev, nullptr, nullptr, nullptr, nullptr, s))) return e;
     if (n_steps > 0) DPE_CUDA(cudaMemsetAsync(accept_counts_dev, 0, (size_t)n_steps * sizeof(int32_t), s));
     for (int t = 0; t < n_steps; ++t) {
-        if ((e = launch_propose(st, B, m->dims.n_el, r_prop, thr, new_keys, s))) return e;
+        // without the in-call controller step_nr is advanced afterwards (dpe_mcmc_controller): offset the moved electron by t
+        if ((e = launch_propose(st, B, m->dims.n_el, cfg->proposal, run_controller ? 0 : t, r_prop, thr, new_keys, s))) return e;
         m->launches++;
         if ((e = run_batched(m, r_prop, B, 1, ws_net, ws_net_bytes, nullptr, lp_prop, nullptr, nullptr, nullptr, nullptr, s))) return e;
         if ((e = launch_accept(st, B, m->dims.n_el, r_prop, lp_prop, thr, new_keys, cfg->max_age, nullptr, accept_counts_dev + t, s))) return e;

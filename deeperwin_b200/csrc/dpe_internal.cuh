@@ -135,7 +135,7 @@ int launch_combine(dpe_model *m, int Bc, int C, const float *det, const float *e
                    float *grad, float *ekin, float *eloc, float *epot_out, cudaStream_t s);
 
 // mcmc.cu
-int launch_propose(const dpe_mcmc_state *st, int B, int n_el, float *r_prop, float *thr, uint32_t *new_keys, cudaStream_t s);
+int launch_propose(const dpe_mcmc_state *st, int B, int n_el, int proposal, int step_offset, float *r_prop, float *thr, uint32_t *new_keys, cudaStream_t s);
 int launch_accept(const dpe_mcmc_state *st, int B, int n_el, const float *r_prop, const float *lp_prop, const float *thr,
                   const uint32_t *new_keys, int max_age, int32_t *mask, int32_t *count, cudaStream_t s);
 int launch_controller(const dpe_mcmc_state *st, const int32_t *counts, int n_steps, int64_t n_total,

@@ -78,11 +78,51 @@ __device__ __forceinline__ float bits_to_normal(uint32_t bits) {
     return __fmul_rn(1.41421356237309515f, erf_inv_f32(u));
 }
 
+// jax.random.cauchy (jax 0.4.23): tan(pi * (uniform(minval = eps, maxval = 1) - 0.5)), all float32
+__device__ __forceinline__ float bits_to_cauchy(uint32_t bits) {
+    const float eps = 1.1920929e-07f;
+    float u = __fadd_rn(__fmul_rn(bits_to_unit(bits), __fsub_rn(1.0f, eps)), eps);
+    u = fmaxf(eps, u);
+    return tanf(__fmul_rn(3.14159274f, __fsub_rn(u, 0.5f)));
+}
+
+// "normal_one_el" (mcmc.py:183-193): only electron step_nr % n_el moves, by normal(sub, [3]) * stepsize.  jax lays the three
+// values out as bits(sub, 3): counters (0, 2) -> elements 0 and 2, counters (1, pad 0) -> element 1.  One thread per coordinate.
+__global__ void __launch_bounds__(256) k_propose_one_el(const float *__restrict__ r, const uint32_t *__restrict__ keys,
+                                                         const float *__restrict__ stepsize, const int32_t *__restrict__ step_nr,
+                                                         int step_offset, int B, int n_el, float *__restrict__ r_prop, float *__restrict__ thr,
+                                                         uint32_t *__restrict__ new_keys) {
+    const int n = 3 * n_el;
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (idx >= (long)B * n) return;
+    const long b = idx / n;
+    const int e = (int)(idx - b * n), el = e / 3, k = e - 3 * el;
+    const int moved = (step_nr[0] + step_offset) % n_el;
+    float v = r[idx];
+    if (el == moved || e == 0) {
+        uint32_t nk[2], sub[2];
+        split2(keys[2 * b], keys[2 * b + 1], nk, sub);
+        if (el == moved) {
+            uint32_t x0 = (k == 1) ? 1u : 0u, x1 = (k == 1) ? 0u : 2u;
+            threefry2x32(sub[0], sub[1], x0, x1);
+            v = __fadd_rn(v, __fmul_rn(bits_to_normal(k == 2 ? x1 : x0), stepsize[0]));
+        }
+        if (e == 0) {
+            uint32_t t0 = 0u, t1 = 0u;
+            threefry2x32(sub[0], sub[1], t0, t1);
+            thr[b] = fmaxf(0.f, bits_to_unit(t0));
+            new_keys[2 * b] = nk[0];
+            new_keys[2 * b + 1] = nk[1];
+        }
+    }
+    r_prop[idx] = v;
+}
+
 // One thread per (walker, counter pair p): noise element p from y0, element h+p from y1 (jax bits layout).
 __global__ void __launch_bounds__(256) k_propose(const float *__restrict__ r, const uint32_t *__restrict__ keys,
                                                   const float *__restrict__ stepsize, int B, int n, float *__restrict__ r_prop,
                                                   float *__restrict__ noise_out, float *__restrict__ thr,
-                                                  uint32_t *__restrict__ new_keys) {
+                                                  uint32_t *__restrict__ new_keys, int cauchy) {
     const int h = (n + 1) / 2;
     const long total = (long)B * h;
     long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -94,11 +134,11 @@ __global__ void __launch_bounds__(256) k_propose(const float *__restrict__ r, co
     uint32_t x0 = (uint32_t)p, x1 = (h + p < n) ? (uint32_t)(h + p) : 0u;   // odd n: padded counter is 0
     threefry2x32(sub[0], sub[1], x0, x1);
     const float ss = stepsize ? stepsize[0] : 1.f;
-    float n0 = bits_to_normal(x0);
+    float n0 = cauchy ? bits_to_cauchy(x0) : bits_to_normal(x0);
     if (noise_out) noise_out[b * n + p] = n0;
     if (r_prop) r_prop[b * n + p] = __fadd_rn(r[b * n + p], __fmul_rn(n0, ss));
     if (h + p < n) {
-        float n1 = bits_to_normal(x1);
+        float n1 = cauchy ? bits_to_cauchy(x1) : bits_to_normal(x1);
         if (noise_out) noise_out[b * n + h + p] = n1;
         if (r_prop) r_prop[b * n + h + p] = __fadd_rn(r[b * n + h + p], __fmul_rn(n1, ss));
     }
@@ -111,11 +151,17 @@ __global__ void __launch_bounds__(256) k_propose(const float *__restrict__ r, co
     }
 }
 
-int launch_propose(const dpe_mcmc_state *st, int B, int n_el, float *r_prop, float *thr, uint32_t *new_keys, cudaStream_t s) {
+int launch_propose(const dpe_mcmc_state *st, int B, int n_el, int proposal, int step_offset, float *r_prop, float *thr, uint32_t *new_keys, cudaStream_t s) {
     int n = 3 * n_el, h = (n + 1) / 2;
+    if (proposal == 2) {
+        long total = (long)B * n;
+        k_propose_one_el<<<(int)((total + 255) / 256), 256, 0, s>>>(st->r_dev, st->rng_state_dev, st->stepsize_dev, st->step_nr_dev, step_offset,
+                                                                    B, n_el, r_prop, thr, new_keys);
+        return check_cuda(cudaGetLastError(), "k_propose_one_el");
+    }
     long total = (long)B * h;
     k_propose<<<(int)((total + 255) / 256), 256, 0, s>>>(st->r_dev, st->rng_state_dev, st->stepsize_dev, B, n, r_prop, nullptr,
-                                                         thr, new_keys);
+                                                         thr, new_keys, proposal == 1);
     return check_cuda(cudaGetLastError(), "k_propose");
 }
 
@@ -346,7 +392,7 @@ int dpe_threefry_mcmc_randoms(const uint32_t *keys_dev, int32_t n_walkers, int32
     int n = 3 * n_el, h = (n + 1) / 2;
     long total = (long)n_walkers * h;
     dpe::k_propose<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nullptr, keys_dev, nullptr, n_walkers, n, nullptr,
-                                                                                 noise_dev, thr_dev, new_keys_dev);
+                                                                                 noise_dev, thr_dev, new_keys_dev, 0);
     return dpe::check_cuda(cudaGetLastError(), "k_propose(randoms)");
 }
 

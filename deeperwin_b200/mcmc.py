@@ -270,11 +270,12 @@ class MetropolisHastingsMonteCarlo:
 
     def __init__(self, mcmc_config: MCMCConfig):
         self.config = mcmc_config
-        if self.config.proposal.name != "normal":
+        proposals = {"normal": 0, "cauchy": 1, "normal_one_el": 2}       # mcmc.py:330-343; all three have log_q_ratio = 0
+        if self.config.proposal.name not in proposals:
             raise NotImplementedError("Unknown MCMC proposal type")   # mcmc.py:343
         self._cfg = DpeMcmcConfig(int(mcmc_config.max_age), int(mcmc_config.stepsize_update_interval),
                                   float(mcmc_config.target_acceptance_rate), float(mcmc_config.min_stepsize_scale),
-                                  float(mcmc_config.max_stepsize_scale))
+                                  float(mcmc_config.max_stepsize_scale), proposals[self.config.proposal.name])
         self.last_accept_counts: Optional[torch.Tensor] = None
 
     def _run_mcmc_steps(self, func, state: MCMCState, params, n_up, n_dn, fixed_params, n_steps) -> MCMCState:

@@ -58,6 +58,8 @@ typedef struct dpe_mcmc_config {
     float target_acceptance_rate;
     float min_stepsize_scale;
     float max_stepsize_scale;
+    int32_t proposal;        /* MCMCSimpleProposalConfig.name (configuration.py:952-953): 0 "normal" (mcmc.py:175-180),
+                                1 "cauchy" (:196-201), 2 "normal_one_el" (:183-193: electron step_nr % n_el moves); log_q_ratio = 0 */
 } dpe_mcmc_config;
 
 /* Device-resident walker state: the batch-axis fields of MCMCState (mcmc.py:20-33, 149-151). */

@@ -131,12 +131,17 @@ def initialize_around_nuclei(n_walkers, R, Z, el_ion_mapping, seed, init_method=
 
 def make_mcmc_step(func: Callable[[np.ndarray], np.ndarray], state: OracleMCMCState, *, max_age=20,
                    stepsize_update_interval=100, target_acceptance_rate=0.5, min_stepsize_scale=1e-2,
-                   max_stepsize_scale=1.0, allreduce_mean=lambda x: x, return_mask=False):
+                   max_stepsize_scale=1.0, allreduce_mean=lambda x: x, return_mask=False, proposal="normal"):
     """mcmc.py:345-387 with the `normal` proposal (mcmc.py:175-180).
     func(r[B,N,3] f32) -> log_psi_sqr[B] f32."""
     B, N, _ = state.r.shape
-    new_keys, noise, thr = threefry.mcmc_step_randoms(state.rng_state, N)   # same subkey for noise and threshold
-    r_new = (state.r + noise * f32(state.stepsize)).astype(f32)
+    new_keys, noise, thr = threefry.mcmc_step_randoms(state.rng_state, N, proposal)   # same subkey for noise and threshold
+    if proposal == "normal_one_el":          # mcmc.py:183-193: only electron step_nr % n_el moves
+        r_new = state.r.copy()
+        idx = int(state.step_nr) % N
+        r_new[:, idx, :] = (state.r[:, idx, :] + noise * f32(state.stepsize)).astype(f32)
+    else:                                    # normal (mcmc.py:175-180) / cauchy (:196-201); log_q_ratio = 0 for all three
+        r_new = (state.r + noise * f32(state.stepsize)).astype(f32)
     lp_new = np.asarray(func(r_new), f32)
     with np.errstate(over="ignore"):
         p_accept = np.exp((lp_new - state.log_psi_sqr).astype(f32)).astype(f32)

@@ -105,20 +105,29 @@ def normal(key, shape=()):
     return (np.float32(np.sqrt(2.0)) * erf_inv_f32(u)).astype(np.float32)
 
 
-def mcmc_step_randoms(keys, n_el):
+def cauchy(key, shape=()):
+    """jax.random.cauchy(key, shape, float32) (jax 0.4.23 `_cauchy`): tan(pi * (uniform(minval=eps, maxval=1) - 0.5)), float32."""
+    eps = np.finfo(np.float32).eps
+    u = uniform(key, shape, eps, 1.0)
+    return np.tan((np.float32(np.pi) * (u - np.float32(0.5))).astype(np.float32)).astype(np.float32)
+
+
+def mcmc_step_randoms(keys, n_el, proposal="normal"):
     """Per-walker randoms of one Metropolis step, exactly as mcmc.py:175-180 + :360-361 consume them.
 
     keys: uint32[B, 2].  Returns (new_keys[B,2], noise[B,n_el,3] f32, thr[B] f32).
     `split(key)` -> (new_key, sub); noise = normal(sub,[n_el,3]); thr = uniform(sub,()) -- the SAME subkey.
+    proposal "cauchy" (mcmc.py:196-201): cauchy noise of the same shape; "normal_one_el" (mcmc.py:183-193): noise[B, 3] only.
     """
     keys = np.asarray(keys, dtype=np.uint32)
     B = keys.shape[0]
     new_keys = np.empty((B, 2), np.uint32)
-    noise = np.empty((B, n_el, 3), np.float32)
+    shape = (3,) if proposal == "normal_one_el" else (n_el, 3)
+    noise = np.empty((B,) + shape, np.float32)
     thr = np.empty((B,), np.float32)
     for b in range(B):
         ks = split(keys[b], 2)
         new_keys[b] = ks[0]
-        noise[b] = normal(ks[1], (n_el, 3))
+        noise[b] = cauchy(ks[1], shape) if proposal == "cauchy" else normal(ks[1], shape)
         thr[b] = uniform(ks[1], ())
     return new_keys, noise, thr

@@ -73,7 +73,8 @@ def test_configuration_mirror(tmp_path):
     with pytest.raises(NotImplementedError):              # options the CUDA path does not implement raise loudly
         dpe.Configuration(model=dict(embedding=dict(use_h_two_same_diff=False)))
     with pytest.raises(Exception):
-        dpe.Configuration(optimization=dict(mcmc=dict(proposal=dict(name="cauchy"))))
+        dpe.Configuration(optimization=dict(mcmc=dict(proposal=dict(name="langevin"))))       # not among the simple proposals
+    assert dpe.Configuration(optimization=dict(mcmc=dict(proposal=dict(name="cauchy")))).optimization.mcmc.proposal.name == "cauchy"
     p = tmp_path / "config.yml"
     cfg.save(p)
     assert dpe.Configuration.load_configuration_file(p).model_dump() == cfg.model_dump()

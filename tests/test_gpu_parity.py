@@ -358,3 +358,31 @@ def test_exponential_initialisation_matches_oracle(name):
     assert cfg.optimization.mcmc.initialization == "exponential"
     st2 = dpe.MCMCState.resize_or_init(None, cfg.optimization.mcmc, phys, dpe.PRNGKey(77), device="cuda:0")
     assert st2.r.shape == (cfg.optimization.mcmc.n_walkers, phys.n_electrons, 3) and torch.isfinite(st2.r).all()
+
+
+@pytest.mark.parametrize("proposal", ["normal_one_el", "cauchy"])
+def test_proposal_variants_match_oracle_chain(proposal):
+    """mcmc.py:183-201 through the public MetropolisHastingsMonteCarlo: keys and ages bit-exact, positions to float tolerance
+    (normal_one_el: electron step_nr % n_el moves, jax's halves layout of normal(sub, [3]); cauchy: tan(pi (u - 1/2)), where
+    tanf vs XLA's tan may differ in the last bits)."""
+    import deeperwin_b200 as dpe
+    from oracle import mcmc as omc, model as om
+    _, phys, f, params, fixed, state = _mcmc_setup(B=32)
+    d = om.ModelDims(n_el=phys.n_electrons, n_up=phys.n_up, n_ion=len(phys.Z), Z_max=max(phys.Z))
+    p64 = {m: {k: v.double().cpu() for k, v in l.items()} for m, l in params.items()}
+    R64 = state.R.double().cpu()
+    func = lambda r: om.log_psi_sqr(p64, d, torch.from_numpy(r).double(), R64, phys.Z)[1].float().numpy()
+    st = omc.OracleMCMCState(r=state.r.cpu().numpy(), R=state.R.cpu().numpy(), Z=np.array(phys.Z), log_psi_sqr=state.log_psi_sqr.cpu().numpy(),
+                             walker_age=state.walker_age.cpu().numpy(), rng_state=state.rng_state.cpu().numpy().view(np.uint32))
+    n_steps = 9 if proposal == "normal_one_el" else 4
+    ref = omc.run_mcmc_steps(func, st, n_steps, max_age=20, stepsize_update_interval=5, proposal=proposal)
+    cfg = dpe.MCMCConfigOptimization(n_inter_steps=n_steps, stepsize_update_interval=5, initialization="gaussian", proposal=dict(name=proposal))
+    new = dpe.MetropolisHastingsMonteCarlo(cfg).run_inter_steps(f, state, params, phys.n_up, phys.n_dn, fixed)
+    assert np.array_equal(new.rng_state.cpu().numpy().view(np.uint32), ref.rng_state)
+    assert int(new.step_nr) == ref.step_nr == n_steps
+    same_age = new.walker_age.cpu().numpy() == ref.walker_age
+    assert same_age.mean() >= (1.0 if proposal == "normal_one_el" else 0.9)        # cauchy: a knife-edge walker may flip
+    dr = np.abs(new.r.cpu().numpy() - ref.r).max(axis=(1, 2))
+    assert dr[same_age].max() < (1e-5 if proposal == "normal_one_el" else 1e-3)
+    with pytest.raises(Exception):
+        dpe.MCMCConfigOptimization(proposal=dict(name="langevin"))

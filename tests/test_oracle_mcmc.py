@@ -81,3 +81,28 @@ def test_exponential_radial_initialisation():
     # same seed -> same walkers; keys / ages as for the gaussian initialisation
     st2 = omc.initialize_around_nuclei(512, R, Z, mapping, 1234, "exponential", n_up=7)
     assert np.array_equal(st.r, st2.r) and np.array_equal(st.rng_state, omc.initialize_around_nuclei(512, R, Z, mapping, 1234).rng_state)
+
+
+def test_proposal_variants():
+    """mcmc.py:183-201: cauchy (heavy tails, same shapes / key usage) and normal_one_el (only electron step_nr % n_el moves)."""
+    B, N = 64, 4
+    keys = threefry.split(threefry.prng_key(5), B)
+    nk0, noise0, thr0 = threefry.mcmc_step_randoms(keys, N)
+    nk1, noise1, thr1 = threefry.mcmc_step_randoms(keys, N, "cauchy")
+    nk2, noise2, thr2 = threefry.mcmc_step_randoms(keys, N, "normal_one_el")
+    assert np.array_equal(nk0, nk1) and np.array_equal(nk0, nk2) and np.array_equal(thr0, thr1) and np.array_equal(thr0, thr2)
+    assert noise1.shape == (B, N, 3) and noise2.shape == (B, 3)
+    # cauchy = tan(pi (u - 1/2)) of the same uniforms that feed the normal's erf_inv: same sign, median |x| = 1
+    assert (np.sign(noise1) == np.sign(noise0)).mean() > 0.99
+    big = threefry.cauchy(threefry.prng_key(1), (20000,))
+    assert abs(np.median(np.abs(big)) - 1.0) < 0.03 and np.abs(big).max() > 100
+    # normal(sub, [3]) is NOT a prefix of normal(sub, [N, 3]): jax lays bits out in halves
+    assert np.array_equal(noise2[0], threefry.normal(threefry.split(keys[0], 2)[1], (3,)))
+    func = lambda r: (-np.sum(r.astype(np.float32) ** 2, axis=(1, 2))).astype(np.float32)
+    r0 = threefry.normal(threefry.prng_key(7), (B, N, 3))
+    st = omc.OracleMCMCState(r=r0, R=np.zeros((1, 3), np.float32), Z=np.array([4]), log_psi_sqr=func(r0), walker_age=np.zeros(B, np.int32),
+                             rng_state=keys, stepsize=np.float32(0.3), step_nr=6)
+    out = omc.make_mcmc_step(func, st, proposal="normal_one_el")
+    moved = np.abs(out.r - st.r).max(axis=(0, 2)) > 0
+    assert moved.tolist() == [False, False, True, False]          # 6 % 4 == 2
+    assert out.step_nr == 7
