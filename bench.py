@@ -16,6 +16,8 @@ walkers are independent chains; the only collectives are the natural scalar redu
             with HOST buffers: pinned H2D of the walker state and D2H of the new state + E_loc inside the timed region
 `roofline`: the dominant kernel (the dense-layer GEMM), timed live with CUDA events inside the library
 `cpu_baseline`: oracle/ (a port, not the reference binary: jax is not installable here) on a bounded sample
+`secondary`: the other half of BASELINE.json's metric, Benzene (42 electrons) x 4096 walkers per GPU (configs[3]), fewer steps
+`cadence`  : the reference's optimisation cadence -- n_inter_steps = 20 Metropolis steps per E_loc evaluation (configuration.py:1039)
 """
 from __future__ import annotations
 
@@ -51,7 +53,15 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--secondary", default="Benzene", help="molecule of the secondary block ('' to skip)")
+    ap.add_argument("--secondary-steps", type=int, default=3)
+    ap.add_argument("--no-cadence", action="store_true")
     return ap.parse_args()
+
+
+def workload_string(molecule, n_el, walkers):
+    return (f"{molecule} ({n_el} electrons), {walkers} walkers per GPU, default dpe4 model (4x256/32, 32 full determinants), "
+            "random-init weights, 100 burn-in steps; step = 1 Metropolis step + 1 forward-Laplacian E_loc + E statistics")
 
 
 def peaks():
@@ -64,9 +74,7 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_port_throughput(molecule: str, target_seconds: float):
-    """Times oracle/ (torch CPU fp32, all host threads) on a bounded sample: per walker one forward pass
-    (the Metropolis step's log psi^2) + one forward-Laplacian E_loc in chunks of 64 (hamiltonian.py:280)."""
+def _cpu_port(molecule: str):
     import torch
     from oracle import model as om
     from deeperwin_b200.configuration import PhysicalConfig
@@ -79,6 +87,7 @@ def cpu_port_throughput(molecule: str, target_seconds: float):
     g = torch.Generator().manual_seed(1234)
 
     def run(n):
+        """n walkers: one forward pass (the Metropolis step's log psi^2) + one forward-Laplacian E_loc in chunks of 64 (hamiltonian.py:280)."""
         r = (R[torch.tensor(phys.el_ion_mapping)][None] + torch.randn(n, d.n_el, 3, generator=g)).float()
         t0 = time.perf_counter()
         with torch.no_grad():
@@ -86,6 +95,12 @@ def cpu_port_throughput(molecule: str, target_seconds: float):
             om.local_energy(p32, d, r, R, phys.Z, max_batch_size=64)
         return time.perf_counter() - t0
 
+    return run, cores, phys
+
+
+def cpu_port_throughput(molecule: str, target_seconds: float):
+    """Times oracle/ (torch CPU fp32, all host threads) on a bounded sample of the workload."""
+    run, cores, _ = _cpu_port(molecule)
     run(16)                       # warm-up (thread pools, allocator)
     pilot = run(64)
     n = int(max(64, min(8192, 64 * target_seconds / max(pilot, 1e-3)) // 64 * 64))
@@ -95,23 +110,29 @@ def cpu_port_throughput(molecule: str, target_seconds: float):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  jax/haiku/folx are not installable in
-    this image (no network, not in /opt/wheelhouse), so this arm times the oracle port (kind = "port")."""
+    """--impl reference: the reference's CPU implementation of the path.  jax/haiku/folx are not installable in this image (no
+    network, not in /opt/wheelhouse), so this arm times the oracle port (kind = "port": same algorithm, torch-CPU fp32, all host
+    threads).  One step = the hot path over a bounded SAMPLE of the workload's walkers (the full 4096 would take minutes per
+    step); `ms_per_step` is the measured time of that sample, `value` = sample walkers / that time.  With --gpus N > 1 the arm
+    is still ONE host (rank 0 runs, the other ranks exit): only the N = 1 ratio compares like with like."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    info = None
-    for i in range(args.warmup + args.steps):
-        info = cpu_port_throughput(args.molecule, min(args.cpu_seconds, 6.0))
-        if i >= args.warmup:
-            vals.append(info["value"])
-    v = sum(vals) / len(vals)
-    info["value"] = v
+    run, cores, phys = _cpu_port(args.molecule)
+    run(16)
+    pilot = run(64)
+    n = int(max(64, min(4096, 64 * min(args.cpu_seconds, 6.0) / max(pilot, 1e-3)) // 64 * 64))
+    times = [run(n) for _ in range(args.warmup + args.steps)][args.warmup:]
+    t = sum(times) / len(times)
+    v = n / t
+    info = dict(value=v, unit=UNIT, cores=cores, kind="port",
+                sample=f"{n} of the {args.walkers} {args.molecule} walkers per step (1 forward + 1 forward-Laplacian E_loc each), torch-CPU fp32 oracle, "
+                       f"{t:.1f} s per step; one host regardless of --gpus")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * args.walkers / v, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.molecule}, default dpe4 model, random-init weights; CPU sample per step: {info['sample']}"},
+            "config": {"workload": workload_string(args.molecule, phys.n_electrons, args.walkers), "walkers_per_gpu": args.walkers,
+                       "sample_walkers_per_step": n},
             "cpu_baseline": info, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -153,22 +174,141 @@ class ClockSampler:
                 pass
             time.sleep(self.period)
 
-    def stop(self, t0, t1):
-        self.stop_flag = True
-        self.thread.join(timeout=1.0)
+    def window(self, t0, t1):
         if not self.nv:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["pynvml unavailable"]}
-        sel = [(c, m) for t, c, m in self.rows if t0 <= t <= t1]
+        sel = [(c, m) for t, c, m in list(self.rows) if t0 <= t <= t1]
         sm = sorted(c for c, _ in sel)
         reasons = sorted(n for n, bit in self.REASONS.items() if any(m & bit for _, m in sel))
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": reasons, "samples": len(sm)}
+
+    def stop(self):
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+
+
+class Workload:
+    """One molecule x walkers-per-GPU on this rank: model, burnt-in walker state resident in HBM, and the timed step."""
+
+    def __init__(self, args, molecule, walkers, burn_in, world, rank, dev):
+        import torch
+        import deeperwin_b200 as dpe
+        from deeperwin_b200._lib import DpeMcmcState
+        self.torch, self.dpe, self.world, self.dev, self.B = torch, dpe, world, dev, walkers
+        cfg = dpe.Configuration(physical=dict(name=molecule), optimization=dict(mcmc=dict(n_walkers=walkers * world, initialization="gaussian")))
+        self.phys = phys = cfg.physical
+        self.spin = (phys.n_up, phys.n_dn)
+        self.log_psi_sqr, _, _, self.params, self.fixed = dpe.build_log_psi_squared(cfg.model, phys, None, None, rng_seed=1234, device=dev)
+        self.engine = self.log_psi_sqr.engine
+        if args.gemm_path >= 0:
+            self.engine.set_gemm_path(args.gemm_path)
+        self.get_local_energy = dpe.build_local_energy(self.log_psi_sqr, forward_lap=True)
+        self.total_energy = dpe.build_total_energy(self.get_local_energy, cfg.optimization.clipping)
+        # synthetic walkers: r0 = R[el_ion_mapping] + N(0,1) (mcmc.py:64-67), threefry seed 1234, then burn-in
+        full = dpe.MCMCState.initialize_around_nuclei(walkers * world, phys, "gaussian", "el_ion_mapping", dpe.PRNGKey(1234), device=dev)
+        state = full.split_across_devices()
+        del full
+        burn = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=burn_in, initialization="gaussian"))
+        self.state = state = burn.run_inter_steps(self.log_psi_sqr, state, self.params, *self.spin, self.fixed)
+        self.mc = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=1, initialization="gaussian"))
+        self.clip_state = dpe.init_clipping_state(device=dev)
+        # device-resident walker state driven through the C ABI
+        self.r = state.r[0].clone(); self.lp = state.log_psi_sqr[0].clone(); self.age = state.walker_age[0].clone()
+        self.keys = state.rng_state[0].clone()
+        self.ss = state.stepsize.reshape(1).clone(); self.sn = state.step_nr.reshape(1).to(torch.int32).clone()
+        self.ar = state.acc_rate.reshape(1).clone()
+        self.st = DpeMcmcState(self.r.data_ptr(), self.lp.data_ptr(), self.age.data_ptr(), self.keys.data_ptr(), self.ss.data_ptr(),
+                               self.sn.data_ptr(), self.ar.data_ptr())
+        self.counts = torch.zeros(32, dtype=torch.int32, device=dev)
+        self.R_, self.Z_ = state.R[0], state.Z[0]
+        self.aux = None
+        torch.cuda.synchronize()
+
+    def device_step(self, n_mcmc=1):
+        """n_mcmc Metropolis steps + one forward-Laplacian E_loc + statistics, state resident in HBM."""
+        import torch.distributed as dist
+        counts = self.counts[:n_mcmc]
+        self.engine.mcmc_steps(self.st, self.B, n_mcmc, self.mc._cfg, False, self.world == 1, counts)
+        if self.world > 1:
+            dist.all_reduce(counts)
+            self.engine.mcmc_controller(self.st, counts, n_mcmc, self.B * self.world, self.mc._cfg)
+        loss, (self.clip_state, self.aux) = self.total_energy(self.params, self.clip_state, self.spin, (self.r, self.R_, self.Z_, self.fixed))
+        return loss
+
+    def timed(self, steps, warmup, flush, n_mcmc=1, settle=True):
+        """W warm-up steps (+ a bounded settle loop), then exactly `steps` steps timed with CUDA events, L2 flushed (untimed)
+        between them; returns (device ms summed over the steps = max over ranks, per-step ms of this rank, launches, wall window)."""
+        torch = self.torch
+        import torch.distributed as dist
+        for _ in range(warmup):
+            self.device_step(n_mcmc)
+        torch.cuda.synchronize()
+        # settle: a fresh process sees 20-100 % slower steps for its first ~0.5 s on these boxes (power / clock ramp);
+        # keep warming up (bounded) until three consecutive steps agree with the fastest one seen to 3 %
+        extra, best = [], float("inf")
+        for _ in range(24 if settle else 0):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(); self.device_step(n_mcmc); a1.record()
+            torch.cuda.synchronize()
+            extra.append(a0.elapsed_time(a1)); best = min(best, extra[-1])
+            if len(extra) >= 3 and all(t <= 1.03 * best for t in extra[-3:]):
+                break
+        if self.world > 1:
+            dist.barrier()
+        launches0 = self.engine.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0 = time.perf_counter()
+        for k in range(steps):
+            flush.zero_()                                   # L2 flush between timed iterations (not timed)
+            ev[k][0].record()
+            self.device_step(n_mcmc)
+            ev[k][1].record()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        t1 = time.perf_counter()
+        launches = self.engine.launch_count() - launches0 + 2 * steps       # + the two moment kernels per step
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        tmax = torch.tensor([sum(step_ms)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        return tmax.item(), step_ms, launches, (t0, t1), len(extra)
+
+    def roofline(self, pk):
+        """The dominant kernel class (the dense-layer GEMM), timed live with CUDA events inside the library."""
+        engine, B = self.engine, self.B
+        prof = engine.profile_gemms(lambda: engine.local_energy(self.r))
+        if not prof:
+            return None
+        fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+        tensor_peak = pk["bf16_tflops"] / 6.0          # 3xTF32 = (bf16 / 2) / 3, SURVEY.md 8d
+        ach = prof["flops"] / (prof["ms"] * 1e-3) / 1e12
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"       # dram__bytes_read.sum + dram__bytes_write.sum of the same launch shape (ncu --set full)
+        if tf.exists():
+            t = json.loads(tf.read_text()).get(f"{self.phys.name}:{B}:{prof['kernel']}")
+            traffic = t["dram_bytes_per_launch"] if t else None
+        flop_eval = FLOP_PER_EVAL.get(self.phys.name)
+        return {"bound": "tensor", "kernel": prof["kernel"], "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": ach / tensor_peak, "traffic": traffic,
+                "launch_shape": "largest-FLOP launches of the class (main embedding layers: rows = walkers x electrons x (3N+2), K = 320, N_out = 256)"
+                                + ("; the CTA-pair kernel's launch also applies bias + spin-mean addend + tanh rule in its epilogue "
+                                   "(the separate k_act pass it replaces is not counted as FLOPs)" if prof["kernel"] == "k_gemm_tc2_3xtf32" else ""),
+                "class_achieved": prof["class_flops"] / (prof["class_ms"] * 1e-3) / 1e12, "class_launches": prof["class_count"],
+                "class_frac": prof["class_flops"] / (prof["class_ms"] * 1e-3) / 1e12 / tensor_peak,
+                "peak_source": f"{pk['source']}: bf16 {pk['bf16_tflops']} TF/s / 6 (3xTF32 FP32-accurate tensor peak)",
+                "launches": prof["count"], "avg_launch_ms": prof["ms"] / max(prof["count"], 1),
+                "algorithmic_flops_per_launch": prof["flops"] / max(prof["count"], 1),
+                "frac_of_fp32_simt_peak": ach / fp32_peak, "fp32_simt_peak": fp32_peak,
+                "share_of_eloc_time": prof["class_ms"] / prof["total_ms"],
+                "eloc_pass_ms": prof["total_ms"],
+                "eloc_pass_frac": None if flop_eval is None else B * flop_eval / (prof["total_ms"] * 1e-3) / 1e12 / tensor_peak}
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import deeperwin_b200 as dpe
-    from deeperwin_b200 import mcmc as gm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -179,86 +319,31 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    # nvidia-smi is started before the warm-up: its NVML start-up stalls the GPU for tens of ms and must not land in the timed region
+    # the clock sampler is started before the warm-up: NVML start-up stalls the GPU for tens of ms and must not land in the timed region
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    cfg = dpe.Configuration(physical=dict(name=args.molecule), optimization=dict(mcmc=dict(n_walkers=args.walkers * world, initialization="gaussian")))
-    phys = cfg.physical
-    B = args.walkers
-    n_el, n_up, n_dn = phys.n_electrons, phys.n_up, phys.n_dn
-    log_psi_sqr, _, _, params, fixed = dpe.build_log_psi_squared(cfg.model, phys, None, None, rng_seed=1234, device=dev)
-    engine = log_psi_sqr.engine
-    if args.gemm_path >= 0:
-        engine.set_gemm_path(args.gemm_path)
-    get_local_energy = dpe.build_local_energy(log_psi_sqr, forward_lap=True)
-    total_energy = dpe.build_total_energy(get_local_energy, cfg.optimization.clipping)
-    mcmc_cfg_burn = dpe.MCMCConfigOptimization(n_inter_steps=args.burn_in, initialization="gaussian")
-    mcmc_cfg_one = dpe.MCMCConfigOptimization(n_inter_steps=1, initialization="gaussian")
-    # synthetic walkers: r0 = R[el_ion_mapping] + N(0,1) (mcmc.py:64-67), threefry seed 1234, then burn-in
-    full = dpe.MCMCState.initialize_around_nuclei(B * world, phys, "gaussian", "el_ion_mapping", dpe.PRNGKey(1234), device=dev)
-    state = full.split_across_devices()
-    del full
-    state = dpe.MetropolisHastingsMonteCarlo(mcmc_cfg_burn).run_inter_steps(log_psi_sqr, state, params, n_up, n_dn, fixed)
-    mc = dpe.MetropolisHastingsMonteCarlo(mcmc_cfg_one)
-    clip_state = dpe.init_clipping_state(device=dev)
-    torch.cuda.synchronize()
-
-    # ---- device-resident step through the C ABI (state stays in HBM) ---------------------------------
-    import ctypes as C
-    from deeperwin_b200._lib import DpeMcmcState
-    r = state.r[0].clone(); lp = state.log_psi_sqr[0].clone(); age = state.walker_age[0].clone(); keys = state.rng_state[0].clone()
-    ss = state.stepsize.reshape(1).clone(); sn = state.step_nr.reshape(1).to(torch.int32).clone(); ar = state.acc_rate.reshape(1).clone()
-    st = DpeMcmcState(r.data_ptr(), lp.data_ptr(), age.data_ptr(), keys.data_ptr(), ss.data_ptr(), sn.data_ptr(), ar.data_ptr())
-    counts = torch.zeros(1, dtype=torch.int32, device=dev)
-    R_, Z_ = state.R[0], state.Z[0]
     flush = torch.empty(512 * 2 ** 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
-
-    def device_step():
-        engine.mcmc_steps(st, B, 1, mc._cfg, False, world == 1, counts)
-        if world > 1:
-            dist.all_reduce(counts)
-            engine.mcmc_controller(st, counts, 1, B * world, mc._cfg)
-        return total_energy(params, clip_state, (n_up, n_dn), (r, R_, Z_, fixed))
-
-    for _ in range(args.warmup):
-        loss, (clip_state, aux) = device_step()
-    torch.cuda.synchronize()
-    # settle: a fresh process sees 20-100 % slower steps for its first ~0.5 s on these boxes (power / clock ramp);
-    # keep warming up (bounded) until three consecutive steps agree with the fastest one seen to 3 %
-    settle, best = [], float("inf")
-    for _ in range(24):
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(); loss, (clip_state, aux) = device_step(); a1.record()
-        torch.cuda.synchronize()
-        settle.append(a0.elapsed_time(a1)); best = min(best, settle[-1])
-        if len(settle) >= 3 and all(t <= 1.03 * best for t in settle[-3:]):
-            break
-    if world > 1:
-        dist.barrier()
-    launches0 = engine.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()                                   # L2 flush between timed iterations (not timed)
-        ev[k][0].record()
-        loss, (clip_state, aux) = device_step()
-        ev[k][1].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t_wall1 = time.perf_counter()
-    launches = engine.launch_count() - launches0 + 2 * args.steps      # + the two moment kernels per step
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    dev_ms = sum(step_ms)
-    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dev_ms = tmax.item()
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    pk = peaks()
+    B = args.walkers
+    w = Workload(args, args.molecule, B, args.burn_in, world, rank, dev)
+    n_el = w.phys.n_electrons
+    dev_ms, step_ms, launches, (t_wall0, t_wall1), n_settle = w.timed(args.steps, args.warmup, flush)
+    clocks = sampler.window(t_wall0, t_wall1) if sampler else None
     value = B * world * args.steps / (dev_ms * 1e-3)
+
+    # ---- the reference's cadence: n_inter_steps = 20 Metropolis steps per E_loc evaluation --------------------------------
+    cadence = None
+    if not args.no_cadence:
+        n_inter = 20
+        c_ms, c_steps, c_launches, _, _ = w.timed(3, 1, flush, n_mcmc=n_inter, settle=False)
+        cadence = {"n_inter_steps": n_inter, "value": B * world * 3 / (c_ms * 1e-3), "unit": UNIT, "ms_per_epoch": c_ms / 3,
+                   "metropolis_ms_per_step": (c_ms / 3 - dev_ms / args.steps) / (n_inter - 1), "gpu_launches": c_launches,
+                   "what": "20 Metropolis steps + 1 forward-Laplacian E_loc + statistics per epoch (configuration.py:1039); evals/s = walkers / epoch time"}
 
     # ---- end-to-end through the public Python API with host buffers ---------------------------------
     e2e = None
     if not args.no_e2e:
+        state, mc, log_psi_sqr, params, fixed = w.state, w.mc, w.log_psi_sqr, w.params, w.fixed
+        n_up, n_dn = w.spin
         host = {k: getattr(state, k)[0].cpu().pin_memory() for k in ("r", "log_psi_sqr", "walker_age", "rng_state")}
         out_host = {k: torch.empty_like(v).pin_memory() for k, v in host.items()}
         e_host = torch.empty(B, dtype=torch.float32).pin_memory()
@@ -272,7 +357,7 @@ def run_ours(args):
                                   rng_state=host["rng_state"].to(dev, non_blocking=True)[None],
                                   stepsize=state.stepsize, step_nr=state.step_nr, acc_rate=state.acc_rate, _step_nr_host=0)
             s_new = mc.run_inter_steps(log_psi_sqr, s_dev, params, n_up, n_dn, fixed)
-            e = get_local_energy(params, (n_up, n_dn), s_new.r[0], R_, Z_, fixed)
+            e = w.get_local_energy(params, (n_up, n_dn), s_new.r[0], w.R_, w.Z_, fixed)
             for k in out_host:
                 out_host[k].copy_(getattr(s_new, k)[0], non_blocking=True)
             e_host.copy_(e, non_blocking=True)
@@ -294,48 +379,50 @@ def run_ours(args):
         e2e = {"value": B * world * args.steps / t.item(), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "api": "MetropolisHastingsMonteCarlo.run_inter_steps(n_inter_steps=1) + get_local_energy, pinned host state in/out"}
 
+    roofline = w.roofline(pk) if rank == 0 else None
+    E_mean, acc_rate = float(w.aux["E_mean"]), float(w.ar.item())
+    gemm_path = w.engine.lib.dpe_get_gemm_path(w.engine.handle)
+
+    # ---- secondary block: the other molecule of BASELINE.json's metric (Benzene x 4096 walkers per GPU, configs[3]) ---------
+    secondary = None
+    if args.secondary and args.secondary != args.molecule:
+        del w
+        torch.cuda.empty_cache()
+        w2 = Workload(args, args.secondary, B, min(args.burn_in, 20), world, rank, dev)
+        s_ms, s_steps, s_launches, (s0, s1), _ = w2.timed(args.secondary_steps, 1, flush, settle=False)
+        flop2 = FLOP_PER_EVAL.get(args.secondary)
+        v2 = B * world * args.secondary_steps / (s_ms * 1e-3)
+        secondary = {"metric": METRIC, "value": v2, "unit": UNIT, "n_gpus": world, "steps": args.secondary_steps, "warmup": 1,
+                     "ms_per_step": s_ms / args.secondary_steps, "step_ms": [round(t, 2) for t in s_steps],
+                     "config": {"workload": workload_string(args.secondary, w2.phys.n_electrons, B).replace("100 burn-in", f"{min(args.burn_in, 20)} burn-in"),
+                                "walkers_per_gpu": B, "l2": "512 MiB flush between timed steps",
+                                "chunks": "E_loc pass in workspace-sized chunks (computation.workspace_gb = 48)"},
+                     "gpu_launches": s_launches, "clocks": sampler.window(s0, s1) if sampler else None,
+                     "roofline": w2.roofline(pk) if rank == 0 else None,
+                     "algorithmic_tflops": None if flop2 is None else v2 * flop2 / 1e12,
+                     "E_mean": float(w2.aux["E_mean"]), "acc_rate": float(w2.ar.item())}
+        del w2
+    if sampler:
+        sampler.stop()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: the dense-layer GEMM, timed live inside the library ----------
-    pk = peaks()
-    prof = engine.profile_gemms(lambda: engine.local_energy(r)) if hasattr(engine, "profile_gemms") else None
-    fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
-    tensor_peak = pk["bf16_tflops"] / 6.0          # 3xTF32 = (bf16 / 2) / 3, SURVEY.md 8d
-    roofline = None
-    if prof:
-        ach = prof["flops"] / (prof["ms"] * 1e-3) / 1e12
-        traffic = None
-        tf = ROOT / "profiles" / "traffic.json"       # dram__bytes_read.sum + dram__bytes_write.sum of the same launch shape (ncu --set full)
-        if tf.exists():
-            t = json.loads(tf.read_text()).get(f"{args.molecule}:{B}:{prof['kernel']}")
-            traffic = t["dram_bytes_per_launch"] if t else None
-        roofline = {"bound": "tensor", "kernel": prof["kernel"], "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
-                    "frac": ach / tensor_peak, "traffic": traffic,
-                    "launch_shape": "largest-FLOP launches of the class (main embedding layers: rows = walkers x electrons x (3N+2), K = 320, N_out = 256)"
-                                    + ("; the CTA-pair kernel's launch also applies bias + spin-mean addend + tanh rule in its epilogue "
-                                       "(the separate k_act pass it replaces is not counted as FLOPs)" if prof["kernel"] == "k_gemm_tc2_3xtf32" else ""),
-                    "class_achieved": prof["class_flops"] / (prof["class_ms"] * 1e-3) / 1e12, "class_launches": prof["class_count"],
-                    "peak_source": f"{pk['source']}: bf16 {pk['bf16_tflops']} TF/s / 6 (3xTF32 FP32-accurate tensor peak)",
-                    "launches": prof["count"], "avg_launch_ms": prof["ms"] / max(prof["count"], 1),
-                    "algorithmic_flops_per_launch": prof["flops"] / max(prof["count"], 1),
-                    "frac_of_fp32_simt_peak": ach / fp32_peak, "fp32_simt_peak": fp32_peak,
-                    "share_of_eloc_time": prof["class_ms"] / prof["total_ms"]}
     flop_eval = FLOP_PER_EVAL.get(args.molecule)
     cpu = None if args.no_cpu_baseline else cpu_port_throughput(args.molecule, args.cpu_seconds)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.molecule} ({n_el} electrons), {B} walkers per GPU, default dpe4 model (4x256/32, 32 full determinants), "
-                                   "random-init weights, 100 burn-in steps; step = 1 Metropolis step + 1 forward-Laplacian E_loc + E statistics",
-                       "walkers_per_gpu": B, "l2": "512 MiB flush between timed steps", "gemm_path": engine.lib.dpe_get_gemm_path(engine.handle),
+            "config": {"workload": workload_string(args.molecule, n_el, B),
+                       "walkers_per_gpu": B, "l2": "512 MiB flush between timed steps", "gemm_path": gemm_path,
                        "wall_ms_per_step_incl_flush": 1e3 * (t_wall1 - t_wall0) / args.steps},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "algorithmic_tflops": None if flop_eval is None else value * flop_eval / 1e12,
-            "E_mean": float(aux["E_mean"]), "acc_rate": float(ar.item()), "step_ms": [round(t, 2) for t in step_ms],
-            "extra_warmup_steps": len(settle)}
+            "step_frac_of_tensor_peak": None if flop_eval is None else value / world * flop_eval / 1e12 / (pk["bf16_tflops"] / 6.0),
+            "cadence": cadence, "secondary": secondary,
+            "E_mean": E_mean, "acc_rate": acc_rate, "step_ms": [round(t, 2) for t in step_ms],
+            "extra_warmup_steps": n_settle}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -40,6 +40,8 @@ SIGNATURES = {
     "dpe_param_leaf": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dpe_model_set_params": (C.c_int, [_P, _P, C.c_int64, _P]),
     "dpe_model_set_geometry": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32), _P]),
+    "dpe_model_set_geometry_dev": (C.c_int, [_P, _P, _P, _P]),
+    "dpe_model_geometry_status": (C.c_int, [_P, _P]),
     "dpe_model_set_tao_cache": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "dpe_workspace_bytes": (C.c_size_t, [_P, C.c_int32, C.c_int32]),
     "dpe_log_psi_sqr": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
@@ -57,6 +59,8 @@ SIGNATURES = {
     "dpe_set_gemm_path": (C.c_int, [_P, C.c_int32]),
     "dpe_debug_gemm": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32] + [C.c_int32] * 9 + [_P]),
     "dpe_get_gemm_path": (C.c_int, [_P]),
+    "dpe_set_det_path": (C.c_int, [_P, C.c_int32]),
+    "dpe_get_det_path": (C.c_int, [_P]),
     "dpe_profile_enable": (C.c_int, [_P, C.c_int32]),
     "dpe_profile_collect": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "dpe_profile_launches": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_int32)]),

@@ -10,7 +10,7 @@ different architecture are accepted only at the value the CUDA path implements; 
 from __future__ import annotations
 
 import pathlib
-from typing import List, Literal, Optional, Union
+from typing import Any, Dict, List, Literal, Optional, Union
 
 import numpy as np
 import yaml
@@ -45,7 +45,17 @@ class MLPConfig(ConfigBaseclass):
     @model_validator(mode="after")
     def _check(self):
         _only(self.use_layer_norm, False, "mlp.use_layer_norm")
+        # mlp.py:39: the MLPs that do not pass `residual=` explicitly (w_same, w_diff, h_map, h_ion_map, bf_up, bf_dn) take this
+        # switch, and with equal in/out widths (32 -> 32 from the second iteration on) it changes the wavefunction
+        _only(self.use_residual, False, "mlp.use_residual")
         return self
+
+
+class InitializationConfig(ConfigBaseclass):
+    """configuration.py (embedding.initialization): kept for YAML round trips, the dpe4 layers initialise from `mlp`."""
+    bias_scale: float = 0.0
+    weight_scale: str = "glorot"
+    weight_distribution: str = "uniform"
 
 
 class InputFeatureConfigDPE4(ConfigBaseclass):
@@ -63,9 +73,32 @@ class InputFeatureConfigDPE4(ConfigBaseclass):
     n_ion_features: int = 32
     log_scale_distances: bool = False
     use_el_spin: bool = False
+    # the remaining fields of InputFeatureConfig (configuration.py:557-627); they only matter for other feature variants
+    r_cut_bessel: float = 5.0
+    n_ion_ion_mlp_features: int = 0
+    use_el_ion_convolution: bool = False
+    init_as_zeros: bool = False
+    n_el_el_features: int = 32
+    n_el_el_layers: int = 2
+    el_el_gating_operation: Literal["rbf", "gauss", "none"] = "none"
+    exp_decay_el_el_edge: bool = False
+    init_with_el_el_feat: bool = False
+    n_el_ion_features: int = 32
+    n_el_ion_layers: int = 2
+    el_ion_gating_operation: Literal["rbf", "gauss", "none"] = "none"
+    exp_decay_el_ion_edge: bool = False
+    init_with_el_ion_feat: bool = False
+    rmax: int = 5
+    max_scale_gauss: float = 8.0
+    include_twist: Optional[List[str]] = None
+    use_el_el_spin: bool = False
 
     @model_validator(mode="after")
     def _check(self):
+        for k in ("use_el_ion_convolution", "exp_decay_el_el_edge", "init_with_el_el_feat", "exp_decay_el_ion_edge",
+                  "init_with_el_ion_feat", "use_el_el_spin"):
+            _only(getattr(self, k), False, f"features.{k}")
+        _only(self.include_twist, None, "features.include_twist")
         _only(self.use_rbf_features, False, "features.use_rbf_features")
         _only(self.use_distance_features, True, "features.use_distance_features")
         _only(self.use_el_ion_differences, True, "features.use_el_ion_differences")
@@ -101,10 +134,16 @@ class EmbeddingConfigDeepErwin4(ConfigBaseclass):
     use_deep_schnet_feat: bool = False
     use_ln_aft_act: bool = False
     use_ln_bef_act: bool = False
+    initialization: InitializationConfig = InitializationConfig()
+    use_layer_norm: bool = False
+    use_symmetric_product: bool = True      # these three only act when h_one_correlation > 0 (ferminet_embedding.py:228-236)
+    downmap_during_product: bool = True
+    one_el_skip_conn: bool = True
 
     @model_validator(mode="after")
     def _set_n_hidden(self):
-        # configuration.py:352-364
+        # configuration.py:352-364.  As in the reference the lists may be longer than n_iterations (tests/test_training.yaml has
+        # four widths and n_iterations = 1): the embedding loop reads entry i of each list (ferminet_embedding.py:217-262).
         if isinstance(self.n_hidden_one_el, int):
             self.n_hidden_one_el = [self.n_hidden_one_el] * self.n_iterations
         if isinstance(self.n_hidden_two_el, int):
@@ -113,6 +152,9 @@ class EmbeddingConfigDeepErwin4(ConfigBaseclass):
             self.n_hidden_el_ions = [self.n_hidden_el_ions] * (self.n_iterations - 1)
         if len(self.n_hidden_one_el) != len(self.n_hidden_two_el) + 1:
             raise ValueError("Number of layers for 1-el-stream must be one more than nr of layers in 2-el-stream")
+        if len(self.n_hidden_one_el) < self.n_iterations:
+            raise ValueError("n_hidden_one_el has fewer entries than n_iterations")
+        _only(self.use_layer_norm, False, "embedding.use_layer_norm")
         for k, v in dict(use_el_ion_stream=True, use_h_two_same_diff=True, use_w_mapping=True, use_schnet_features=True,
                          use_average_h_one=True, use_average_h_two=False, use_h_one=True, use_h_one_same_diff=False,
                          use_linear_out=False, use_schnet_bias_feat=True, use_h_one_mlp=True, h_one_correlation=0,
@@ -131,6 +173,8 @@ class EnvelopeOrbitalsConfig(ConfigBaseclass):
     def _check(self):
         _only(list(self.n_hidden), [], "orbitals.envelope_orbitals.n_hidden")
         _only(self.use_bias, False, "orbitals.envelope_orbitals.use_bias")
+        # 'analytical' fits the exponents to a PySCF baseline at set-up time (wavefunction.py:329-360): out of the hot-path scope
+        _only(self.initialization, "constant", "orbitals.envelope_orbitals.initialization")
         return self
 
 
@@ -171,6 +215,8 @@ class OrbitalsConfigFermiNet(ConfigBaseclass):
             raise NotImplementedError("exactly one of orbitals.envelope_orbitals / orbitals.transferable_atomic_orbitals must be set")
         return self
     determinant_schema: Literal["full_det"] = "full_det"
+    periodic_orbitals: None = None
+    use_bloch_envelopes: bool = False
 
 
 class ModelConfigDeepErwin4(ConfigBaseclass):
@@ -185,11 +231,17 @@ class ModelConfigDeepErwin4(ConfigBaseclass):
     Z_min: Optional[int] = 1
     use_cache: bool = True
     complex_wf: bool = False
+    disable_determinant: bool = False
+    max_n_up_orbitals: Optional[int] = None
+    max_n_dn_orbitals: Optional[int] = None
+    max_n_ions: Optional[int] = None
+    kfac_register_complex: bool = False
 
     @model_validator(mode="after")
     def _check(self):
         _only(self.use_el_el_cusp_correction, False, "model.use_el_el_cusp_correction")
         _only(self.complex_wf, False, "model.complex_wf")
+        _only(self.disable_determinant, False, "model.disable_determinant")
         return self
 
 
@@ -250,12 +302,20 @@ class ClippingConfig(ConfigBaseclass):
 
 
 class OptimizationConfig(ConfigBaseclass):
+    """configuration.py:1262-1330.  `optimizer`, `checkpoints`, `shared_optimization` belong to the control plane around the hot
+    path: they are carried through YAML round trips untouched and never read here."""
     mcmc: MCMCConfigOptimization = MCMCConfigOptimization()
     clipping: ClippingConfig = ClippingConfig()
     n_epochs: int = 60_000
     forward_lap: bool = True
     max_batch_size: int = 64
     stop_on_nan: bool = True
+    optimizer: Optional[Dict[str, Any]] = None
+    n_epochs_prev: int = 0
+    use_batch_reweighting: bool = False
+    checkpoints: Optional[Dict[str, Any]] = None
+    shared_optimization: Optional[Dict[str, Any]] = None
+    params_ema_factor: Optional[float] = None
 
 
 class EvaluationConfig(ConfigBaseclass):
@@ -263,6 +323,13 @@ class EvaluationConfig(ConfigBaseclass):
     n_epochs: int = 0
     forward_lap: bool = True
     max_batch_size: int = 64
+    opt_epochs: List[int] = []
+    evaluate_final: bool = True
+    calculate_energies: bool = True
+    forces: Optional[Dict[str, Any]] = None
+    localization_metric: Optional[str] = None
+    structure_factor_grid: Optional[Any] = None
+    density: Optional[Any] = None
 
 
 class ComputationConfig(ConfigBaseclass):
@@ -271,6 +338,13 @@ class ComputationConfig(ConfigBaseclass):
     n_local_devices: Optional[int] = None
     n_nodes: int = 1
     disable_jit: bool = False
+    use_gpu: bool = True
+    require_gpu: bool = False
+    force_device_count: bool = False
+    disable_tensor_cores: bool = True
+    """The reference forces true-FP32 matmuls (process_molecule.py:20-29); here the dense layers run FP32-accurate 3xTF32 on the
+    tensor cores (three tf32 products per FP32 product), which honours that contract; `dpe_set_gemm_path(0)` selects FP32 SIMT."""
+    use_profiler: bool = False
     workspace_gb: float = 48.0
     """(B200 addition) upper bound of the scratch workspace per GPU; batches that need more run in chunks."""
 
@@ -294,6 +368,32 @@ def _spin_from_hunds_rule(Z):
     return n_up - n_dn
 
 
+def generate_el_ion_mapping(R, Z, n_el, n_up):
+    """The reference's default electron -> ion assignment (PhysicalConfig._generate_el_ion_mapping, configuration.py:1571-1615):
+    electrons are placed one at a time; every (spin, ion) candidate is scored by the largest |local spin| it would leave, where
+    the local spin of an ion is the exp(-distance)-weighted sum of (n_up - n_dn) over all ions; the best-scoring candidate whose
+    ion is not full and whose spin is not exhausted wins.  Output: spin-up electrons ion by ion, then spin-down.  Setup-time
+    host code; the same numpy calls on the same arrays, so ties (symmetric molecules) break as in the reference."""
+    R = np.array(R)
+    n_ions = len(Z)
+    weights = np.exp(-np.linalg.norm(R[:, None, :] - R[None, :, :], axis=-1))
+    occupation = np.zeros([n_ions, 2], int)          # [ion, spin]
+    left = [n_up, n_el - n_up]
+    sign = np.array([1.0, -1.0])
+    for _ in range(n_el):
+        local_spin = weights @ (occupation[:, 0] - occupation[:, 1])
+        # candidate c = spin * n_ions + ion adds sign[spin] * weights[:, ion] to the local spins
+        outcome = [local_spin + weights @ (sign[c // n_ions] * np.eye(n_ions)[c % n_ions]) for c in range(2 * n_ions)]
+        for c in np.argsort(np.max(np.abs(outcome), axis=-1)):
+            spin, ion = divmod(int(c), n_ions)
+            if occupation[ion].sum() == Z[ion] or left[spin] == 0:
+                continue
+            occupation[ion, spin] += 1
+            left[spin] -= 1
+            break
+    return [ion for spin in range(2) for ion in range(n_ions) for _ in range(occupation[ion, spin])]
+
+
 class PhysicalConfig(ConfigBaseclass):
     name: Optional[str] = None
     R: Optional[List[List[float]]] = None
@@ -305,6 +405,8 @@ class PhysicalConfig(ConfigBaseclass):
     E_ref_source: Optional[str] = None
     comment: Optional[str] = None
     periodic: None = None
+    changes: Optional[Any] = None
+    weight_for_shared: Optional[float] = None
 
     @model_validator(mode="after")
     def populate_physical_config_from_name(self):
@@ -327,11 +429,8 @@ class PhysicalConfig(ConfigBaseclass):
         if self.el_ion_mapping is None:
             if "el_ion_mapping" in mol:
                 self.el_ion_mapping = list(mol["el_ion_mapping"])
-            elif self.Z is not None and self.n_electrons == sum(self.Z):
-                # neutral default: fill ions in order, spin-up block first (the reference's greedy
-                # local-spin balancing, configuration.py:1571-1615, is setup-time host code)
-                per_ion = [[(z + 1) // 2, z // 2] for z in self.Z]
-                self.el_ion_mapping = [i for s in range(2) for i, n in enumerate(per_ion) for _ in range(n[s])]
+            elif self.Z is not None and self.R is not None and self.n_electrons is not None:
+                self.el_ion_mapping = generate_el_ion_mapping(self.R, self.Z, self.n_electrons, self.n_up)
         if self.E_ref is None:
             self.E_ref = mol.get("E_ref")
         if self.E_ref_source is None:
@@ -359,6 +458,13 @@ class Configuration(ConfigBaseclass):
     computation: ComputationConfig = ComputationConfig()
     experiment_name: Optional[str] = "deeperwin_experiment"
     comment: Optional[str] = None
+    # sections of the reference's root config (configuration.py:1934-1986) that configure the control plane around the hot path
+    # (pre-training, PySCF baseline, loggers, SLURM dispatch, checkpoint reuse): accepted, kept verbatim, never read here
+    pre_training: Optional[Dict[str, Any]] = None
+    baseline: Optional[Dict[str, Any]] = None
+    logging: Optional[Dict[str, Any]] = None
+    dispatch: Optional[Dict[str, Any]] = None
+    reuse: Optional[Dict[str, Any]] = None
 
     @classmethod
     def load_configuration_file(cls, config_file):

@@ -363,6 +363,12 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
     if (ce == cudaSuccess) ce = cudaMalloc(&m->derived, m->derived_floats * sizeof(float));
     if (ce == cudaSuccess) ce = cudaMalloc(&m->R_dev, (size_t)dims->n_ion * 3 * sizeof(float));
     if (ce == cudaSuccess) ce = cudaMalloc(&m->Z_dev, (size_t)dims->n_ion * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&m->eii_dev, sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&m->geom_flag_dev, sizeof(int32_t));
+    if (ce == cudaSuccess) ce = cudaMemset(m->geom_flag_dev, 0, sizeof(int32_t));
+    if (ce == cudaSuccess) ce = cudaMallocHost(&m->geom_pin, (size_t)DPE_GEOM_SLOTS * (4 * dims->n_ion + 1) * sizeof(float));
+    for (int k = 0; k < DPE_GEOM_SLOTS && ce == cudaSuccess; ++k) ce = cudaEventCreateWithFlags(&m->geom_ev[k], cudaEventDisableTiming);
+    m->det_flags = (getenv("DPE_DET_GENERIC") ? 1 : 0) | (getenv("DPE_DET_SIMT") ? 2 : 0);      // debug defaults; dpe_set_det_path overrides
     if (dims->use_taos) {
         const size_t gc = (size_t)dims->n_ion * dims->n_dets * dims->n_el;
         if (ce == cudaSuccess) ce = cudaMalloc(&m->tao_w, (size_t)dims->n_hidden_one_el[dims->n_iterations - 1] * gc * sizeof(float));
@@ -401,6 +407,10 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
 void dpe_model_destroy(dpe_model *m) {
     if (!m) return;
     cudaFree(m->params); cudaFree(m->derived); cudaFree(m->R_dev); cudaFree(m->Z_dev);
+    cudaFree(m->eii_dev); cudaFree(m->geom_flag_dev);
+    if (m->geom_pin) cudaFreeHost(m->geom_pin);
+    for (int k = 0; k < DPE_GEOM_SLOTS; ++k)
+        if (m->geom_ev[k]) cudaEventDestroy(m->geom_ev[k]);
     cudaFree(m->tao_w); cudaFree(m->tao_ex[0]);
     tc_destroy(m);
     if (m->prof) {
@@ -439,12 +449,20 @@ int dpe_model_set_geometry(dpe_model *m, const float *R_host, const int32_t *Z_h
     if (!m || !R_host || !Z_host) return set_error(DPE_ERR_ARG, "set_geometry: null argument");
     const dpe_dims &d = m->dims;
     cudaStream_t s = (cudaStream_t)stream;
-    float Zf[256];
+    // The host arrays may be temporaries: they are copied into a slot of a pinned staging ring and travel from there with
+    // asynchronous copies, so the call neither synchronises the stream nor blocks on the transfer (the weight-sharing loop
+    // changes the geometry every step, variational_optimization.py:356-387).  A slot is reused after DPE_GEOM_SLOTS calls; its
+    // event tells whether the copy that last read it has finished.
+    const int slot = m->geom_slot;
+    m->geom_slot = (slot + 1) % DPE_GEOM_SLOTS;
+    DPE_CUDA(cudaEventSynchronize(m->geom_ev[slot]));
+    float *pin = m->geom_pin + (size_t)slot * (4 * d.n_ion + 1);
+    float *Rp = pin, *Zf = pin + 3 * d.n_ion, *eiip = pin + 4 * d.n_ion;
     for (int J = 0; J < d.n_ion; ++J) {
         if (Z_host[J] < d.z_min || Z_host[J] > d.z_max) return set_error(DPE_ERR_ARG, "Z[%d]=%d outside [z_min, z_max]", J, Z_host[J]);
         Zf[J] = (float)Z_host[J];
-        m->Z_host[J] = Z_host[J];
     }
+    memcpy(Rp, R_host, (size_t)d.n_ion * 3 * sizeof(float));
     // ion-ion repulsion (hamiltonian.py:25-31), float32 like the reference
     float eii = 0.f;
     for (int I = 0; I < d.n_ion; ++I)
@@ -452,13 +470,32 @@ int dpe_model_set_geometry(dpe_model *m, const float *R_host, const int32_t *Z_h
             float dx = R_host[I * 3] - R_host[J * 3], dy = R_host[I * 3 + 1] - R_host[J * 3 + 1], dz = R_host[I * 3 + 2] - R_host[J * 3 + 2];
             eii += Zf[I] * Zf[J] / sqrtf(dx * dx + dy * dy + dz * dz);
         }
-    m->e_ion_ion = eii;
-    // synchronous small copies: the host arrays may be temporaries
-    DPE_CUDA(cudaStreamSynchronize(s));
-    DPE_CUDA(cudaMemcpy(m->R_dev, R_host, (size_t)d.n_ion * 3 * sizeof(float), cudaMemcpyHostToDevice));
-    DPE_CUDA(cudaMemcpy(m->Z_dev, Zf, (size_t)d.n_ion * sizeof(float), cudaMemcpyHostToDevice));
+    *eiip = eii;
+    DPE_CUDA(cudaMemcpyAsync(m->R_dev, Rp, (size_t)d.n_ion * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    DPE_CUDA(cudaMemcpyAsync(m->Z_dev, Zf, (size_t)d.n_ion * sizeof(float), cudaMemcpyHostToDevice, s));
+    DPE_CUDA(cudaMemcpyAsync(m->eii_dev, eiip, sizeof(float), cudaMemcpyHostToDevice, s));
+    DPE_CUDA(cudaEventRecord(m->geom_ev[slot], s));
     m->geom_set = true;
     if (m->params_set) return launch_prepare_geometry(m, s);
+    return DPE_OK;
+}
+
+int dpe_model_set_geometry_dev(dpe_model *m, const float *R_dev, const int32_t *Z_dev, void *stream) {
+    if (!m || !R_dev || !Z_dev) return set_error(DPE_ERR_ARG, "set_geometry_dev: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    int e = launch_geometry_from_device(m, R_dev, Z_dev, s);
+    if (e) return e;
+    m->geom_set = true;
+    if (m->params_set) return launch_prepare_geometry(m, s);
+    return DPE_OK;
+}
+
+int dpe_model_geometry_status(dpe_model *m, void *stream) {
+    if (!m) return set_error(DPE_ERR_ARG, "geometry_status: null model");
+    int32_t flag = 0;
+    DPE_CUDA(cudaMemcpyAsync(&flag, m->geom_flag_dev, sizeof(flag), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    DPE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flag) return set_error(DPE_ERR_ARG, "set_geometry_dev: a nuclear charge was outside [z_min, z_max] (clamped)");
     return DPE_OK;
 }
 
@@ -578,6 +615,12 @@ int dpe_debug_gemm(dpe_model *m, int32_t path, const float *a_dev, int32_t lda, 
     return e;
 }
 int dpe_get_gemm_path(const dpe_model *m) { return m ? m->gemm_path : -1; }
+int dpe_set_det_path(dpe_model *m, int32_t flags) {
+    if (!m || flags < 0 || flags > 3) return set_error(DPE_ERR_ARG, "set_det_path: flags must be in [0, 3]");
+    m->det_flags = flags;
+    return DPE_OK;
+}
+int dpe_get_det_path(const dpe_model *m) { return m ? m->det_flags : -1; }
 int dpe_profile_enable(dpe_model *m, int32_t on) {
     if (!m) return set_error(DPE_ERR_ARG, "profile_enable: null model");
     m->profile = on != 0;

@@ -364,11 +364,7 @@ int launch_det_trace_tc(dpe_model *m, int Bc, int C, const float *mo, const floa
         if (smem <= 227 * 1024) break;
     }
     if (smem > 227 * 1024) return DPE_ERR_UNSUPPORTED;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        DPE_CUDA(cudaFuncSetAttribute(k_det_trace_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    if (int e = opt_in_smem(m, KID_DET_TRACE, k_det_trace_tc)) return e;
     const int grid = (int)(a.n_units < m->n_sm ? a.n_units : m->n_sm);
     a.tl = nullptr;
     const char *tl_path = getenv("DPE_DET_TIMELINE");          // debug: dump the role timeline of CTA 0 (clock64 stamps)

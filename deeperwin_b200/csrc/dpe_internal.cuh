@@ -8,6 +8,7 @@
 #include "../../include/dpe_b200.h"
 
 #define DPE_MAX_LEAVES (1 + DPE_MAX_ITER * 16 + 6)
+#define DPE_GEOM_SLOTS 8
 
 namespace dpe {
 
@@ -71,8 +72,14 @@ struct dpe_model {
     bool tao_set;
     float *R_dev;  // [n_ion,3]
     float *Z_dev;  // [n_ion] as float
-    float e_ion_ion;
-    int32_t Z_host[256];
+    float *eii_dev;                               // [1] ion-ion repulsion (hamiltonian.py:25-31), float32 like the reference
+    int32_t *geom_flag_dev;                       // [1] != 0 after a device-side set_geometry saw a Z outside [z_min, z_max]
+    // pinned staging ring of the host-array set_geometry (asynchronous H2D without a stream synchronisation)
+    float *geom_pin;                              // [DPE_GEOM_SLOTS][4 * n_ion + 1]
+    cudaEvent_t geom_ev[DPE_GEOM_SLOTS];
+    int geom_slot;
+    int det_flags;                                // dpe_set_det_path: bit 0 generic kernel also for N <= 16, bit 1 SIMT tangent stage
+    unsigned long long smem_opted;                // bit k: kernel k of this device was opted in to the full dynamic shared memory
     bool params_set, geom_set;
     int gemm_path;
     int64_t launches;
@@ -90,6 +97,21 @@ int set_error(int code, const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
 #define DPE_CUDA(x) do { int _e = dpe::check_cuda((x), #x); if (_e) return _e; } while (0)
 #define DPE_LAUNCH_CHECK(m) do { (m)->launches++; int _e = dpe::check_cuda(cudaGetLastError(), __func__); if (_e) return _e; } while (0)
+
+// Kernels that need more than 48 KB of dynamic shared memory are opted in once per model (function attributes are per device /
+// context, and a model lives on one device): always to the full 227 KB, so that two models with different needs cannot undercut
+// each other.
+enum KernelId { KID_PAIR1 = 0, KID_PAIR3, KID_CONV2_BIG, KID_CONV1, KID_DET64, KID_DET64F, KID_DET128, KID_GEMM_TC, KID_GEMM_TC2F,
+                KID_GEMM_TC2P, KID_GEMM_ROWS, KID_DET_TRACE, KID_MCMC_FUSED, KID_GRAD_A, KID_GRAD_B, KID_COUNT };
+constexpr int DPE_SMEM_OPTIN = 227 * 1024;
+template <typename F>
+inline int opt_in_smem(dpe_model *m, int kid, F *fn) {
+    if (m->smem_opted & (1ull << kid)) return DPE_OK;
+    int e = check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, DPE_SMEM_OPTIN), "cudaFuncSetAttribute(smem)");
+    if (e) return e;
+    m->smem_opted |= 1ull << kid;
+    return DPE_OK;
+}
 
 // gemm_simt.cu
 int launch_gemm_simt(dpe_model *m, const GemmArgs &g, cudaStream_t s);
@@ -110,6 +132,7 @@ int launch_conv(dpe_model *m, int it, const float *r, int Bc, int C, const float
                 float *x, int ldx, cudaStream_t s);
 int launch_prepare_params(dpe_model *m, cudaStream_t s);
 int launch_prepare_geometry(dpe_model *m, cudaStream_t s);
+int launch_geometry_from_device(dpe_model *m, const float *R_dev, const int32_t *Z_dev, cudaStream_t s);
 
 // orbitals_det.cu
 int launch_envelope(dpe_model *m, const float *r, int Bc, int C, float *mo, cudaStream_t s);

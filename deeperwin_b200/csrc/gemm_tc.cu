@@ -945,6 +945,8 @@ static int encode_w(CUtensorMap *map, float *ptr, int N, int K, int box_rows) {
 int tc_register_weight(dpe_model *m, const float *W, int K, int N) {
     if (!m->tc) m->tc = new TcState();
     TcState *st = static_cast<TcState *>(m->tc);
+    for (auto &c : st->weights)
+        if (c.W == W && c.K == K && c.N == N) { c.fresh = false; return DPE_OK; }     // already registered (dpe_debug_gemm re-registers)
     TcWeight w;
     w.W = W; w.K = K; w.N = N; w.fresh = false;
     DPE_CUDA(cudaMalloc(&w.hi, (size_t)K * N * sizeof(float)));
@@ -1061,11 +1063,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
         if (rc == CUDA_SUCCESS) { have_map_c = true; a.tma_store = a.epi == 0; }
     }
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        attr_set = true;
-    }
+    if (int e = opt_in_smem(m, KID_GEMM_TC, k_gemm_tc_3xtf32)) return e;
     long n_tiles = (long)((a.n_seg + a.spt - 1) / a.spt) * a.n_rt * a.n_ft;
     int grid = (int)(n_tiles < m->n_sm ? n_tiles : m->n_sm);
     a.tl = nullptr;
@@ -1121,20 +1119,13 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
         CUresult r2 = enc(&map_x2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box2, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r2 == CUDA_SUCCESS) {
-            static size_t attr_plain = 0, attr_fused = 0;
             const long pairs_wanted = n_tiles < m->n_sm / 2 ? n_tiles : m->n_sm / 2;
             const int grid2 = (int)pairs_wanted * 2;
             if (a.epi) {
-                if (smem2 > attr_fused) {
-                    DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc2_3xtf32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                    attr_fused = smem2;
-                }
+                if (int e = opt_in_smem(m, KID_GEMM_TC2F, k_gemm_tc2_3xtf32<true>)) return e;
                 k_gemm_tc2_3xtf32<true><<<grid2, (6 + T2_FUSED_EPI_WARPS) * 32, smem2, s>>>(map_x2, w->map_hi128, w->map_lo128, map_c, map_add, a);
             } else {
-                if (smem2 > attr_plain) {
-                    DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc2_3xtf32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                    attr_plain = smem2;
-                }
+                if (int e = opt_in_smem(m, KID_GEMM_TC2P, k_gemm_tc2_3xtf32<false>)) return e;
                 k_gemm_tc2_3xtf32<false><<<grid2, TC_THREADS, smem2, s>>>(map_x2, w->map_hi128, w->map_lo128, map_c, map_add, a);
             }
             launched_pair = true;
@@ -1180,11 +1171,7 @@ static int launch_gemm_tc_rows(dpe_model *m, const GemmArgs &g, const TcWeight *
     a.n_st = TR_STAGES;
     while (a.n_st > 2 && (size_t)a.n_st * TR_STAGE_BYTES + fixed > 227 * 1024) --a.n_st;
     const size_t smem_rows = (size_t)a.n_st * TR_STAGE_BYTES + fixed;
-    static size_t attr_rows = 0;
-    if (smem_rows > attr_rows) {
-        DPE_CUDA(cudaFuncSetAttribute(k_gemm_tc_rows_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
-        attr_rows = smem_rows;
-    }
+    if (int e = opt_in_smem(m, KID_GEMM_ROWS, k_gemm_tc_rows_3xtf32)) return e;
     long n_tiles = ((long)g.M + TR_ROWS - 1) / TR_ROWS;
     int grid = (int)(n_tiles < m->n_sm ? n_tiles : m->n_sm);
     k_gemm_tc_rows_3xtf32<<<grid, TR_THREADS, smem_rows, s>>>(map_x, w->map_hi, w->map_lo, a);

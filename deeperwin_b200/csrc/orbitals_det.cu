@@ -620,8 +620,7 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *
     const int N = d.n_el;
     const bool lap = C > 1;
     const int NP = det_tc_pad(N, d.n_dets);
-    static const bool force_generic = getenv("DPE_DET_GENERIC") != nullptr;   // debug knobs
-    static const bool force_simt = getenv("DPE_DET_SIMT") != nullptr;
+    const bool force_generic = m->det_flags & 1, force_simt = m->det_flags & 2;   // dpe_set_det_path
     // Laplacian mode on the tensor-core path: FP64 factorisation here, traces of (dA_k Ainv) and (dA_k Ainv)^2 in det_tc.cu
     const bool tc = lap && ainv && NP <= 64 && m->gemm_path == 1 && !force_simt;
     float *ah = tc ? ainv : nullptr, *al = tc ? ainv + (size_t)Bc * d.n_dets * NP * NP : nullptr;
@@ -640,10 +639,12 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *
         else k_det_warp<false><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, nullptr, nullptr, NP);
     } else {
         // 64 threads: one 8 x 8 tile of P per thread (N <= 64 -> at most 64 tiles) and one column of mo per thread
-        if (smem > 48 * 1024) {
-            DPE_CUDA(cudaFuncSetAttribute(k_det<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DPE_CUDA(cudaFuncSetAttribute(k_det<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DPE_CUDA(cudaFuncSetAttribute(k_det<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > DPE_SMEM_OPTIN) return set_error(DPE_ERR_UNSUPPORTED, "det: %zu bytes of shared memory", smem);
+        {
+            int e;
+            if ((e = opt_in_smem(m, KID_DET64, k_det<64, true>))) return e;
+            if ((e = opt_in_smem(m, KID_DET64F, k_det<64, true, true>))) return e;
+            if ((e = opt_in_smem(m, KID_DET128, k_det<128, false>))) return e;
         }
         if (lap && tc) k_det<64, true, true><<<blocks, 64, smem, s>>>(N, C, d.n_dets, mo, det, ah, al, NP);
         else if (lap) k_det<64, true><<<blocks, 64, smem, s>>>(N, C, d.n_dets, mo, det, ah, al, NP);

@@ -46,7 +46,7 @@ __global__ void k_features(const float *__restrict__ r, const float *__restrict_
 
 // E_pot (hamiltonian.py:17-39): one warp per walker.
 __global__ void k_epot(const float *__restrict__ r, const float *__restrict__ R, const float *__restrict__ Zf, int Bc,
-                       int N, int I, float e_ion_ion, float *__restrict__ epot) {
+                       int N, int I, const float *__restrict__ e_ion_ion, float *__restrict__ epot) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= Bc) return;
     const float *rb = r + (long)warp * N * 3;
@@ -67,7 +67,7 @@ __global__ void k_epot(const float *__restrict__ r, const float *__restrict__ R,
         e_ei += __shfl_xor_sync(0xffffffffu, e_ei, o);
         e_ee += __shfl_xor_sync(0xffffffffu, e_ee, o);
     }
-    if (lane == 0) epot[warp] = e_ee - e_ei + e_ion_ion;
+    if (lane == 0) epot[warp] = e_ee - e_ei + e_ion_ion[0];
 }
 
 int launch_features(dpe_model *m, const float *r, int Bc, int C, float *x0, int ldx, float *epot, cudaStream_t s) {
@@ -77,7 +77,7 @@ int launch_features(dpe_model *m, const float *r, int Bc, int C, float *x0, int 
     k_features<<<blocks, 256, 0, s>>>(r, m->R_dev, Bc, d.n_el, d.n_ion, C, x0, ldx);
     DPE_LAUNCH_CHECK(m);
     if (epot) {
-        k_epot<<<(Bc * 32 + 255) / 256, 256, 0, s>>>(r, m->R_dev, m->Z_dev, Bc, d.n_el, d.n_ion, m->e_ion_ion, epot);
+        k_epot<<<(Bc * 32 + 255) / 256, 256, 0, s>>>(r, m->R_dev, m->Z_dev, Bc, d.n_el, d.n_ion, m->eii_dev, epot);
         DPE_LAUNCH_CHECK(m);
     }
     return DPE_OK;
@@ -383,11 +383,12 @@ int launch_pair_stream(dpe_model *m, const float *r, int Bc, int CP, float *pw_b
     size_t smem = fl * sizeof(float);
     long blocks = ((long)Bc * (d.n_el * (d.n_el + 1) / 2) + 7) / 8;
     if (blocks > 148 * 4) blocks = 148 * 4;
+    int e;
     if (CP == 1) {
-        DPE_CUDA(cudaFuncSetAttribute(k_pair_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if ((e = opt_in_smem(m, KID_PAIR1, k_pair_stream<1>))) return e;
         k_pair_stream<1><<<(int)blocks, 256, smem, s>>>(a);
     } else {
-        DPE_CUDA(cudaFuncSetAttribute(k_pair_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if ((e = opt_in_smem(m, KID_PAIR3, k_pair_stream<3>))) return e;
         k_pair_stream<3><<<(int)blocks, 256, smem, s>>>(a);
     }
     DPE_LAUNCH_CHECK(m);
@@ -709,18 +710,15 @@ int launch_conv(dpe_model *m, int it, const float *r, int Bc, int C, const float
             if (C * CV_FG <= 384 && smem2 <= 48 * 1024) {
                 k_conv_dense2<384, 4><<<Bc * (emb / CV_FG), C * CV_FG, smem2, s>>>(N, C, 3, emb, hm, pw, x, ldx, p.d_in);
             } else {
-                static size_t attr2 = 0;
-                if (smem2 > 48 * 1024 && smem2 > attr2) {
-                    DPE_CUDA(cudaFuncSetAttribute(k_conv_dense2<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                    attr2 = smem2;
-                }
+                if (int e = opt_in_smem(m, KID_CONV2_BIG, k_conv_dense2<1024, 1>)) return e;
                 k_conv_dense2<1024, 1><<<Bc * (emb / CV_FG), C * CV_FG, smem2, s>>>(N, C, 3, emb, hm, pw, x, ldx, p.d_in);
             }
         } else {
             int NP = (N + 3) & ~3;
             if ((NP & 7) == 0) NP += 4;
             size_t smem = ((size_t)N * CV_FG * NP + (size_t)N * CV_CB * CV_FG) * sizeof(float);
-            if (smem > 48 * 1024) DPE_CUDA(cudaFuncSetAttribute(k_conv_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem > DPE_SMEM_OPTIN) return set_error(DPE_ERR_UNSUPPORTED, "conv: %zu bytes of shared memory", smem);
+            if (int e = opt_in_smem(m, KID_CONV1, k_conv_dense)) return e;
             int n_cb = (C + CV_CB - 1) / CV_CB;
             k_conv_dense<<<Bc * (emb / CV_FG) * n_cb, CV_FG * CV_CB, smem, s>>>(N, C, 3, emb, hm, pw, x, ldx, p.d_in);
         }
@@ -772,6 +770,35 @@ __global__ void k_him(const float *__restrict__ emb_tab, const float *__restrict
     float acc = 0.f;
     for (int k = 0; k < F; ++k) acc = fmaf(h[k], W[k * dE + f], acc);
     him[idx] = tanh_f32(acc + b[f]);
+}
+
+// Device-side set_geometry: R / Z already live on the GPU (MCMCState.R, .Z); copies them, converts Z to float (clamped to the
+// embedding vocabulary, a flag records a violation) and sums the ion-ion repulsion in the host routine's order (same float32 bits).
+__global__ void k_geometry_from_device(const float *__restrict__ R, const int32_t *__restrict__ Z, int I, int z_min, int z_max,
+                                       float *__restrict__ R_out, float *__restrict__ Zf, float *__restrict__ eii, int32_t *__restrict__ flag) {
+    for (int t = threadIdx.x; t < 3 * I; t += blockDim.x) R_out[t] = R[t];
+    for (int t = threadIdx.x; t < I; t += blockDim.x) {
+        int z = Z[t];
+        if (z < z_min || z > z_max) { atomicExch(flag, 1); z = min(max(z, z_min), z_max); }
+        Zf[t] = (float)z;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float e = 0.f;
+        for (int a = 0; a < I; ++a)
+            for (int b = a + 1; b < I; ++b) {
+                const float dx = R[a * 3] - R[b * 3], dy = R[a * 3 + 1] - R[b * 3 + 1], dz = R[a * 3 + 2] - R[b * 3 + 2];
+                e = __fadd_rn(e, __fdiv_rn(__fmul_rn(Zf[a], Zf[b]), __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)))));
+            }
+        eii[0] = e;
+    }
+}
+
+int launch_geometry_from_device(dpe_model *m, const float *R_dev, const int32_t *Z_dev, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    k_geometry_from_device<<<1, 128, 0, s>>>(R_dev, Z_dev, d.n_ion, d.z_min, d.z_max, m->R_dev, m->Z_dev, m->eii_dev, m->geom_flag_dev);
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
 }
 
 int launch_prepare_geometry(dpe_model *m, cudaStream_t s) {

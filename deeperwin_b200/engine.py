@@ -55,7 +55,6 @@ class Engine:
         d.use_taos = int(bool(use_taos))
         self.use_taos = bool(use_taos)
         self.n_dets, self.d_last = n_dets, list(n_hidden_one_el)[n_iterations - 1]
-        self._tao_sig = None
         self._tao_keep = None
         self.dims = d
         self.n_el, self.n_up, self.n_ion = n_el, n_up, n_ion
@@ -71,10 +70,11 @@ class Engine:
             check(self.lib.dpe_param_leaf(self.handle, i, C.byref(off), C.byref(size), C.byref(rows), C.byref(cols)), "dpe_param_leaf")
             self.leaf_shapes.append((off.value, size.value, rows.value, cols.value))
         self._flat = torch.empty(self.n_params, dtype=torch.float32, device=self.device)
-        self._param_sig = None
-        self._geom_sig = None
+        self._flat_views = [self._flat[off:off + size] for off, size, _, _ in self.leaf_shapes]
+        self._geom_keep = None
         self._ws: Optional[torch.Tensor] = None
-        self.workspace_cap = int(workspace_gb * 2 ** 30)
+        self._ws_need: Dict[Tuple[int, int], int] = {}
+        self._workspace_cap = int(workspace_gb * 2 ** 30)
         if os.environ.get("DPE_GEMM_PATH", "") != "":       # 0 = FP32 SIMT GEMM, 1 = tcgen05 3xTF32 GEMM
             self.set_gemm_path(int(os.environ["DPE_GEMM_PATH"]))
 
@@ -87,36 +87,63 @@ class Engine:
             pass
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def workspace_cap(self) -> int:
+        return self._workspace_cap
+
+    @workspace_cap.setter
+    def workspace_cap(self, nbytes: int):
+        self._workspace_cap = int(nbytes)
+        self._ws_need.clear()
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def set_params(self, params: Dict[str, Dict[str, torch.Tensor]]):
-        sig = tuple((params[m][k].data_ptr(), params[m][k]._version) for m, k in self.leaves)
-        if sig == self._param_sig:
-            return
+        """`params` of log_psi_sqr(params, ...).  The weights are uploaded on EVERY call (one multi-tensor copy into the flat
+        vector + the library's re-split, a few MB device-to-device): freshness is never inferred from tensor identity, so in-place
+        updates through `.data`, raw-pointer writes by an optimiser kernel or a re-allocated tensor at the same address are all seen."""
         with torch.cuda.device(self.device):
+            srcs = []
             for (mod, name), (off, size, rows, cols) in zip(self.leaves, self.leaf_shapes):
                 t = params[mod][name]
                 if t.numel() != size:
                     raise ValueError(f"parameter {mod}/{name} has {t.numel()} values, expected {size} ({rows}x{cols})")
-                self._flat[off:off + size].copy_(t.reshape(-1).to(torch.float32), non_blocking=True)
+                if t.device != self.device or t.dtype != torch.float32:
+                    t = t.to(device=self.device, dtype=torch.float32)
+                srcs.append(t.detach().reshape(-1))
+            torch._foreach_copy_(self._flat_views, srcs)
             check(self.lib.dpe_model_set_params(self.handle, _ptr(self._flat), self.n_params, self._stream()), "dpe_model_set_params")
-        self._param_sig = sig
 
     def set_geometry(self, R, Z):
+        """`R, Z` of log_psi_sqr(params, n_up, n_dn, r, R, Z, fixed_params).  CUDA tensors (MCMCState.R / .Z) are handed to the
+        library as device pointers -- no host copy, no synchronisation; host arrays go through the library's pinned staging ring."""
+        if isinstance(R, torch.Tensor) and R.is_cuda:
+            Rd = R.detach().to(device=self.device, dtype=torch.float32)
+            Zd = (Z.detach() if isinstance(Z, torch.Tensor) else torch.as_tensor(np.asarray(Z))).to(device=self.device, dtype=torch.int32)
+            if Rd.ndim == 3:      # tiled over a device/batch axis by the caller: all copies are equal
+                Rd, Zd = Rd[0], Zd[0]
+            if tuple(Rd.shape) != (self.n_ion, 3) or tuple(Zd.shape) != (self.n_ion,):
+                raise ValueError(f"R/Z shapes {tuple(Rd.shape)}/{tuple(Zd.shape)} do not match n_ion={self.n_ion}")
+            Rd, Zd = Rd.contiguous(), Zd.contiguous()
+            with torch.cuda.device(self.device):
+                check(self.lib.dpe_model_set_geometry_dev(self.handle, _ptr(Rd), _ptr(Zd), self._stream()), "dpe_model_set_geometry_dev")
+            self._geom_keep = (Rd, Zd)       # the copy kernel runs asynchronously on the stream
+            return
         Rn = np.ascontiguousarray(np.asarray(R.detach().cpu() if isinstance(R, torch.Tensor) else R, dtype=np.float32))
         Zn = np.ascontiguousarray(np.asarray(Z.detach().cpu() if isinstance(Z, torch.Tensor) else Z).astype(np.int32))
-        if Rn.ndim == 3:      # tiled over a device/batch axis by the caller: all copies are equal
+        if Rn.ndim == 3:
             Rn, Zn = Rn[0], Zn[0]
-        sig = (Rn.tobytes(), Zn.tobytes())
-        if sig == self._geom_sig:
-            return
         if Rn.shape != (self.n_ion, 3) or Zn.shape != (self.n_ion,):
             raise ValueError(f"R/Z shapes {Rn.shape}/{Zn.shape} do not match n_ion={self.n_ion}")
         with torch.cuda.device(self.device):
             check(self.lib.dpe_model_set_geometry(self.handle, Rn.ctypes.data_as(C.POINTER(C.c_float)),
                                                   Zn.ctypes.data_as(C.POINTER(C.c_int32)), self._stream()), "dpe_model_set_geometry")
-        self._geom_sig = sig
+
+    def geometry_status(self):
+        """Raises if a device-side set_geometry ever saw a nuclear charge outside the embedding vocabulary (synchronises)."""
+        with torch.cuda.device(self.device):
+            check(self.lib.dpe_model_geometry_status(self.handle, self._stream()), "dpe_model_geometry_status")
 
     def set_tao_cache(self, cache: Optional[Dict]):
         """fixed_params["cache"]["taos"] of the reference (wavefunction.py:164-209, orbital_net.py:84-95):
@@ -126,10 +153,7 @@ class Engine:
         if not cache or "backflows" not in cache or "exponents" not in cache:
             raise NotImplementedError('this model evaluates transferable atomic orbitals from fixed_params["cache"]["taos"] '
                                       "(backflows, exponents); the geometry-only nets that fill the cache are not part of the hot path")
-        bfs, exs = list(cache["backflows"]), list(cache["exponents"])
-        sig = tuple((t.data_ptr(), t._version) for t in bfs + exs)
-        if sig == self._tao_sig:
-            return
+        bfs, exs = list(cache["backflows"]), list(cache["exponents"])     # re-packed on every call, like the weights (set_params)
         n_dn = self.n_el - self.n_up
         dev = []
         for t, n_orb, tail in ((bfs[0], self.n_up, (self.n_dets, self.d_last)), (bfs[1], n_dn, (self.n_dets, self.d_last)),
@@ -142,13 +166,15 @@ class Engine:
             check(self.lib.dpe_model_set_tao_cache(self.handle, _ptr(dev[0]), _ptr(dev[1]), _ptr(dev[2]), _ptr(dev[3]), self._stream()),
                   "dpe_model_set_tao_cache")
         self._tao_keep = dev       # the pack kernel runs asynchronously on the stream
-        self._tao_sig = sig
 
     def workspace(self, n_walkers: int, mode: int) -> torch.Tensor:
-        need = min(self.lib.dpe_workspace_bytes(self.handle, n_walkers, mode), self.workspace_cap)
-        free, _ = torch.cuda.mem_get_info(self.device)
+        key = (n_walkers, mode)
+        need = self._ws_need.get(key)
+        if need is None:
+            need = self._ws_need[key] = min(self.lib.dpe_workspace_bytes(self.handle, n_walkers, mode), self.workspace_cap)
         have = 0 if self._ws is None else self._ws.numel()
-        if have < need:
+        if have < need:            # grow only: the device is queried for free memory when (and only when) a larger buffer is needed
+            free, _ = torch.cuda.mem_get_info(self.device)
             need = min(need, have + int(free * 0.9))
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -220,6 +246,10 @@ class Engine:
 
     def set_gemm_path(self, path: int):
         check(self.lib.dpe_set_gemm_path(self.handle, path), "dpe_set_gemm_path")
+
+    def set_det_path(self, generic: bool = False, simt: bool = False):
+        """Test knob (dpe_set_det_path): generic block-per-matrix determinant kernel also for n_el <= 16 / CUDA-core tangent stage."""
+        check(self.lib.dpe_set_det_path(self.handle, int(generic) | (int(simt) << 1)), "dpe_set_det_path")
 
     GEMM_CLASSES = {0: "k_gemm_simt<128,128,8,8>", 1: "k_gemm_simt<128,64,8,4>", 2: "k_gemm_simt<256,32,8,4>", 3: "k_gemm_tc_3xtf32",
                     4: "k_gemm_tc2_3xtf32"}

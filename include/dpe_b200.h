@@ -99,8 +99,16 @@ int dpe_param_leaf(const dpe_model *m, int32_t leaf, int64_t *offset, int64_t *s
  * memory) and rebuilds the derived kernel-side layouts. */
 int dpe_model_set_params(dpe_model *m, const float *params_dev, int64_t n, void *stream);
 
-/* `R, Z` of log_psi_sqr(params, n_up, n_dn, r, R, Z, fixed_params): host arrays R[n_ion*3], Z[n_ion]. */
+/* `R, Z` of log_psi_sqr(params, n_up, n_dn, r, R, Z, fixed_params): host arrays R[n_ion*3], Z[n_ion].
+ * The arrays are staged through pinned memory owned by the handle: the call does not synchronise the stream. */
 int dpe_model_set_geometry(dpe_model *m, const float *R_host, const int32_t *Z_host, void *stream);
+
+/* The same with R / Z already on the device (MCMCState.R float32[n_ion,3], MCMCState.Z int32[n_ion], mcmc.py:23-24): no host
+ * round trip at all -- the weight-sharing loop switches geometry every optimisation step (variational_optimization.py:356-387).
+ * Z outside [z_min, z_max] cannot be reported synchronously: it is clamped and latched; dpe_model_geometry_status (which
+ * synchronises) returns DPE_ERR_ARG if that ever happened. */
+int dpe_model_set_geometry_dev(dpe_model *m, const float *R_dev, const int32_t *Z_dev, void *stream);
+int dpe_model_geometry_status(dpe_model *m, void *stream);
 
 /* `fixed_params["cache"]["taos"]` of log_psi_sqr(...) for models built with use_taos = 1 (orbital_net.py:84-95,
  * model/wavefunction.py:164-209): the geometry-only outputs of TAOBackflow / TAOExponents, device arrays,
@@ -188,6 +196,11 @@ int dpe_debug_gemm(dpe_model *m, int32_t path, const float *a_dev, int32_t lda, 
                    int32_t M, int32_t N, int32_t K, int32_t seg_len, int32_t a_seg_stride, int32_t a_seg_off, int32_t c_seg_stride,
                    int32_t c_seg_off, int32_t c_col_off, void *stream);
 int dpe_get_gemm_path(const dpe_model *m);
+/* Which kernels the determinant stage (model/wavefunction.py:63-83) uses -- test knob, every combination computes the same
+ * quantities: bit 0 = the generic block-per-matrix kernel also for n_el <= 16 (default there: one warp per matrix),
+ * bit 1 = tangent / Laplacian traces on CUDA cores instead of the tcgen05 trace kernel. Default 0. */
+int dpe_set_det_path(dpe_model *m, int32_t flags);
+int dpe_get_det_path(const dpe_model *m);
 /* Live kernel timing for bench.py's roofline: while enabled, every dense-layer GEMM launch is bracketed by
  * CUDA events on the launching stream. dpe_profile_collect synchronises and returns, for GEMM kernel class
  * `klass` (0: SIMT 128x128, 1: SIMT 128x64, 2: SIMT 256x32, 3: tcgen05 3xTF32), the summed device time (ms), the

@@ -511,8 +511,11 @@ def forward_laplacian(params, d: ModelDims, r, R, Z, return_intermediates=False,
     lap = 2 * F_lap
     e_kin = -0.5 * (0.5 * lap + 0.25 * (grad * grad).sum(-1))
     e_pot = potential_energy(r, R, Z)
+    # conditioning of the walker: every determinant enters through its inverse (error amplification cond_2(A_d)) and the signed sum
+    # over determinants amplifies by sum|q_d| / |sum q_d|  ->  cond_eff = sum_d |q_d| cond(A_d) / |sum_d q_d|
+    cond_eff = (q.abs() * torch.linalg.cond(A0.double())).sum(-1) / psi.abs().double().clamp_min(1e-300)
     out = dict(logpsi2=logpsi2, phase=torch.where(psi < 0, torch.full_like(psi, math.pi), torch.zeros_like(psi)), grad=grad, lap=lap,
-               E_kin=e_kin, E_pot=e_pot, E_loc=e_kin + e_pot, sign_d=sign, logdet_d=logdet)
+               E_kin=e_kin, E_pot=e_pot, E_loc=e_kin + e_pot, sign_d=sign, logdet_d=logdet, cond=cond_eff)
     if return_intermediates:
         inter.update(mo=mo, g_d=g_d, lap_d=lap_d)
         out["inter"] = inter

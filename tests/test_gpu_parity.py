@@ -3,11 +3,10 @@ against the fp64 oracle on identical walker positions and weights.
 
 Tolerances (BASELINE.json north_star): log psi^2 1e-5 relative, E_loc 1e-4 relative, fp32 kernel vs fp64 oracle;
 sign / phase exact; RNG keys, bits, thresholds, accept masks, ages, step_nr bit-exact.
-The stated tolerances are asserted on the MEDIAN walker.  The Slater matrices of a random-init network are
-ill-conditioned for a few walkers (cond up to 1e5), where ANY fp32 evaluation -- including the reference's own
-fp32 path -- deviates from the fp64 truth by more than that (tools/parity_stats.py: the CUDA path and the fp32
-CPU restatement have the same error distribution); the worst walker is therefore held to 4x the worst error of
-the fp32 CPU oracle on the same batch (8x for the single worst walker, 3x for the 90th percentile)."""
+The acceptance rule for the floating-point outputs is oracle/parity_rule.py: walkers whose Slater matrices are
+well conditioned (cond_eff < 1e3) must meet the stated tolerance outright; every other walker is held to 2x the
+error the fp32 CPU restatement makes at the same conditioning (never below the stated tolerance).  The burnt-in
+case additionally asserts the stated tolerances on the 99th percentile of |psi|^2-distributed walkers."""
 import ctypes as C
 from pathlib import Path
 
@@ -39,9 +38,34 @@ def make(name, B, seed=3, bias_scale=0.1, envelope_jitter=0.5, small=False, devi
     return phys, d, p32, p64, R, r, eng
 
 
+def check_against_oracle(ref, f32, lp, e_loc, aux, phase, what):
+    """log psi^2, sign, E_pot, E_loc, gradient of the CUDA path vs the fp64 oracle `ref` under the parity rule; `f32` is the
+    fp32 CPU restatement on the same inputs (the fp32 floor)."""
+    from oracle import parity_rule
+    lp, e_loc = lp.double().cpu(), e_loc.double().cpu()
+    cond = ref["cond"]
+    rel_lp = (lp - ref["logpsi2"]).abs() / ref["logpsi2"].abs()
+    floor_lp = (f32["logpsi2"].double() - ref["logpsi2"]).abs() / ref["logpsi2"].abs()
+    parity_rule.check(rel_lp, floor_lp, cond, 1e-5, f"{what} log psi^2")
+    assert torch.equal(phase.cpu() > 1.0, ref["phase"] > 1.0)            # sign exact (phase is 0 or pi)
+    assert set(phase.cpu().unique().tolist()) <= {0.0, float(np.float32(np.pi))}
+    if aux is not None:
+        # the forward-only pass (Metropolis step) and the value channel of the Laplacian pass are the same arithmetic
+        assert torch.allclose(aux["log_psi_sqr"].cpu(), lp.float(), rtol=2e-6, atol=0)
+        assert (aux["E_pot"].double().cpu() - ref["E_pot"]).abs().max() / ref["E_pot"].abs().max() < 1e-6
+        gerr = (aux["grad"].double().cpu() - ref["grad"]).abs().amax(-1) / ref["grad"].abs().amax(-1)
+        gfloor = (f32["grad"].double() - ref["grad"]).abs().amax(-1) / ref["grad"].abs().amax(-1)
+        parity_rule.check(gerr, gfloor, cond, 1e-4, f"{what} grad log psi^2")
+    scale = ref["E_loc"].abs().clamp_min(1.0)
+    err = (e_loc - ref["E_loc"]).abs() / scale
+    floor = (f32["E_loc"].double() - ref["E_loc"]).abs() / scale
+    parity_rule.check(err, floor, cond, 1e-4, f"{what} E_loc")
+    return rel_lp, err
+
+
 # B / N atoms: odd electron counts -- the tensor-core determinant stage then runs with shifted TMA boxes ((det * N) mod 4 != 0)
 # and the odd-N minor pairing; ("B", small): n_dets * N = 15 is not a TMA-legal stride, the stage falls back to CUDA cores
-@pytest.mark.parametrize("name,small,B", [("LiH", True, 32), ("LiH", False, 32), ("N2", False, 24), ("HChain10", False, 8),
+@pytest.mark.parametrize("name,small,B", [("LiH", True, 32), ("LiH", False, 32), ("N2", False, 48), ("HChain10", False, 8),
                                           ("B", False, 16), ("N", False, 12), ("B", True, 16)])
 def test_logpsi_and_eloc_match_oracle(name, small, B):
     from oracle import model as om
@@ -50,29 +74,59 @@ def test_logpsi_and_eloc_match_oracle(name, small, B):
     f32 = om.forward_laplacian(p32, d, r, R, phys.Z)                       # fp32 CPU restatement: the error floor of fp32
     e_loc, aux = eng.local_energy(r.cuda(), with_aux=True)
     phase, lp = eng.log_psi_sqr(r.cuda())
-    lp, e_loc = lp.double().cpu(), e_loc.double().cpu()
-    # log psi^2: 1e-5 relative on the median walker, worst walker <= max(1e-5, 4 x worst fp32-CPU error)
-    rel_lp = (lp - ref["logpsi2"]).abs() / ref["logpsi2"].abs()
-    floor_lp = (f32["logpsi2"].double() - ref["logpsi2"]).abs() / ref["logpsi2"].abs()
-    assert rel_lp.median() < 1e-5, rel_lp.median()
-    assert rel_lp.quantile(0.9) <= max(1e-5, 3 * floor_lp.quantile(0.9).item()), (rel_lp.quantile(0.9), floor_lp.quantile(0.9))
-    assert rel_lp.max() <= max(1e-5, 8 * floor_lp.max().item()), (rel_lp.max(), floor_lp.max())
-    # the forward-only pass (Metropolis step) and the value channel of the Laplacian pass are the same arithmetic
-    assert torch.allclose(aux["log_psi_sqr"].cpu(), lp.float(), rtol=2e-6, atol=0)
-    assert torch.equal(phase.cpu() > 1.0, ref["phase"] > 1.0)            # sign exact (phase is 0 or pi)
-    assert set(phase.cpu().unique().tolist()) <= {0.0, float(np.float32(np.pi))}
-    assert (aux["E_pot"].double().cpu() - ref["E_pot"]).abs().max() / ref["E_pot"].abs().max() < 1e-6
-    # E_loc: 1e-4 relative on the median walker, worst walker <= max(1e-4, 4 x worst fp32-CPU error)
+    check_against_oracle(ref, f32, lp, e_loc, aux, phase, f"{name}{' small' if small else ''}")
+
+
+# Systems with more than 16 electrons run kernels nothing above touches: the block-per-matrix FP64 factorisation k_det<64> /
+# k_det<128,false>, the tensor-core trace kernel with NP = 32 / 48, k_conv_dense2's multi-block electron loop, and -- when
+# 3N + 2 > 48 (benzene: 128 channels) -- the dense layers WITHOUT the fused tanh-rule epilogue (plain GEMM + k_act + k_envelope).
+# Every path variant must reproduce the oracle: gemm 1 = tcgen05 3xTF32 / 0 = FP32 SIMT GEMMs; det "tc" = tensor-core trace
+# kernel, "simt" = CUDA-core tangent stage (k_det<64,true>), "generic" = block-per-matrix kernel also where n_el <= 16.
+@pytest.mark.parametrize("name,B,gemm,det", [("Benzene", 4, 1, "tc"), ("Benzene", 4, 1, "simt"), ("Benzene", 3, 0, "tc"),
+                                             ("Allene_TinyMol", 8, 1, "tc"), ("Allene_TinyMol", 8, 1, "simt"), ("Allene_TinyMol", 5, 0, "tc"),
+                                             ("Ethene", 8, 1, "tc"), ("Ethene", 8, 1, "generic"), ("N2", 16, 1, "generic"),
+                                             ("N2", 16, 1, "generic+simt"), ("N2", 16, 1, "simt"), ("LiH", 16, 0, "generic+simt")])
+def test_large_systems_and_every_kernel_path_match_oracle(name, B, gemm, det):
+    from oracle import model as om
+    phys, d, p32, p64, R, r, eng = make(name, B)
+    if gemm == 1 and eng.lib.dpe_get_gemm_path(eng.handle) != 1:
+        pytest.skip("tensor-core path unavailable")
+    eng.set_gemm_path(gemm)
+    eng.set_det_path(generic="generic" in det, simt="simt" in det)
+    assert eng.lib.dpe_get_det_path(eng.handle) == int("generic" in det) | (int("simt" in det) << 1)
+    ref = om.forward_laplacian(p64, d, r.double(), R.double(), phys.Z)
+    f32 = om.forward_laplacian(p32, d, r, R, phys.Z)
+    e_loc, aux = eng.local_energy(r.cuda(), with_aux=True)
+    phase, lp = eng.log_psi_sqr(r.cuda())
+    check_against_oracle(ref, f32, lp, e_loc, aux, phase, f"{name} gemm={gemm} det={det}")
+
+
+def test_burnt_in_walkers_hold_the_stated_tolerances_at_p99():
+    """Walkers distributed as |psi|^2 (1000 Metropolis steps, the reference's burn-in length, configuration.py:1041) keep away
+    from the nodes, where the signed sum over determinants cancels: for them the stated tolerances hold at the 99th percentile
+    against the fp32 floor's own 99th percentile, and the parity rule holds walker by walker."""
+    import deeperwin_b200 as dpe
+    from oracle import model as om
+    cfg = dpe.Configuration(physical=dict(name="N2"))
+    phys = cfg.physical
+    f, _, _, params, fixed = dpe.build_log_psi_squared(cfg.model, phys, None, None, rng_seed=11, device="cuda:0")
+    st = dpe.MCMCState.initialize_around_nuclei(192, phys, "exponential", "el_ion_mapping", dpe.PRNGKey(5), device="cuda:0")
+    st = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=1000)).run_inter_steps(f, st, params, 7, 7, fixed)
+    d = om.ModelDims(n_el=14, n_up=7, n_ion=2, Z_max=7)
+    p32 = {m: {k: v.cpu() for k, v in l.items()} for m, l in params.items()}
+    p64 = om.cast_params(p32, torch.float64)
+    r, R = st.r.cpu(), st.R.cpu()
+    ref = om.forward_laplacian(p64, d, r.double(), R.double(), phys.Z)
+    f32 = om.forward_laplacian(p32, d, r, R, phys.Z)
+    e_loc, aux = f.engine.local_energy(st.r, with_aux=True)
+    phase, lp = f.engine.log_psi_sqr(st.r)
+    rel_lp, err = check_against_oracle(ref, f32, lp, e_loc, aux, phase, "N2 burnt in")
     scale = ref["E_loc"].abs().clamp_min(1.0)
-    err = (e_loc - ref["E_loc"]).abs() / scale
     floor = (f32["E_loc"].double() - ref["E_loc"]).abs() / scale
-    assert err.median() < 1e-4, err.median()
-    assert err.quantile(0.9) <= max(1e-4, 3 * floor.quantile(0.9).item()), (err.quantile(0.9), floor.quantile(0.9))
-    assert err.max() <= max(1e-4, 8 * floor.max().item()), (err.max(), floor.max())
-    gerr = (aux["grad"].double().cpu() - ref["grad"]).abs().amax(-1) / ref["grad"].abs().amax(-1)
-    gfloor = (f32["grad"].double() - ref["grad"]).abs().amax(-1) / ref["grad"].abs().amax(-1)
-    assert gerr.median() < 1e-4, gerr.median()
-    assert gerr.max() <= max(1e-4, 8 * gfloor.max().item()), (gerr.max(), gfloor.max())
+    floor_lp = (f32["logpsi2"].double() - ref["logpsi2"]).abs() / ref["logpsi2"].abs()
+    assert rel_lp.quantile(0.99) <= max(1e-5, 2 * floor_lp.quantile(0.99).item()), (rel_lp.quantile(0.99), floor_lp.quantile(0.99))
+    assert err.quantile(0.99) <= max(1e-4, 2 * floor.quantile(0.99).item()), (err.quantile(0.99), floor.quantile(0.99))
+    assert rel_lp.median() < 1e-5 and err.median() < 1e-4
 
 
 @pytest.mark.parametrize("name,B,nd", [("LiH", 32, 4), ("N2", 16, 4), ("B", 16, 3)])
@@ -90,20 +144,7 @@ def test_tao_orbitals_match_oracle(name, B, nd):
     f32 = om.forward_laplacian(p32, d, r, R, phys.Z, tao=tao32)
     e_loc, aux = eng.local_energy(r.cuda(), with_aux=True)
     phase, lp = eng.log_psi_sqr(r.cuda())
-    lp, e_loc = lp.double().cpu(), e_loc.double().cpu()
-    rel_lp = (lp - ref["logpsi2"]).abs() / ref["logpsi2"].abs()
-    floor_lp = (f32["logpsi2"].double() - ref["logpsi2"]).abs() / ref["logpsi2"].abs()
-    assert rel_lp.median() < 1e-5, rel_lp.median()
-    assert rel_lp.max() <= max(1e-5, 8 * floor_lp.max().item()), (rel_lp.max(), floor_lp.max())
-    assert torch.allclose(aux["log_psi_sqr"].cpu(), lp.float(), rtol=2e-6, atol=0)
-    assert torch.equal(phase.cpu() > 1.0, ref["phase"] > 1.0)
-    scale = ref["E_loc"].abs().clamp_min(1.0)
-    err = (e_loc - ref["E_loc"]).abs() / scale
-    floor = (f32["E_loc"].double() - ref["E_loc"]).abs() / scale
-    assert err.median() < 1e-4, err.median()
-    assert err.max() <= max(1e-4, 8 * floor.max().item()), (err.max(), floor.max())
-    gerr = (aux["grad"].double().cpu() - ref["grad"]).abs().amax(-1) / ref["grad"].abs().amax(-1)
-    assert gerr.median() < 1e-4, gerr.median()
+    check_against_oracle(ref, f32, lp, e_loc, aux, phase, f"{name} TAO")
 
 
 def test_tao_model_through_the_reference_callables():
@@ -148,15 +189,19 @@ def test_golden_fixtures(name):
     tao32 = om.cast_tao_cache(om.make_tao_cache(d, seed=int(g["seed"])), torch.float32) if d.use_taos else None
     if tao32:
         eng.set_tao_cache({k: [t.cuda() for t in v] for k, v in tao32.items()})
+    from oracle import parity_rule
     e, aux = eng.local_energy(torch.from_numpy(g["r"]).cuda(), with_aux=True)
     rel_lp = np.abs(aux["log_psi_sqr"].cpu().numpy() - g["logpsi2"]) / np.abs(g["logpsi2"])
     rel_e = np.abs(e.cpu().numpy() - g["E_loc"]) / np.maximum(np.abs(g["E_loc"]), 1.0)
     # fp32 CPU restatement on the same fixture = what any fp32 evaluation loses to the conditioning of these walkers
     f32 = om.forward_laplacian(p32, d, torch.from_numpy(g["r"]), torch.from_numpy(g["R"]), g["Z"].tolist(), tao=tao32)
+    p64 = om.cast_params(p32, torch.float64)
+    tao64 = om.cast_tao_cache(tao32, torch.float64) if tao32 else None
+    cond = om.forward_laplacian(p64, d, torch.from_numpy(g["r"]).double(), torch.from_numpy(g["R"]).double(), g["Z"].tolist(), tao=tao64)["cond"]
     fl_lp = np.abs(f32["logpsi2"].numpy() - g["logpsi2"]) / np.abs(g["logpsi2"])
     fl_e = np.abs(f32["E_loc"].numpy() - g["E_loc"]) / np.maximum(np.abs(g["E_loc"]), 1.0)
-    assert np.median(rel_lp) < 1e-5 and rel_lp.max() <= max(1e-5, 8 * fl_lp.max()), (rel_lp, fl_lp)
-    assert np.median(rel_e) < 1e-4 and rel_e.max() <= max(1e-4, 8 * fl_e.max()), (rel_e, fl_e)
+    parity_rule.check(rel_lp, fl_lp, cond, 1e-5, f"golden {name} log psi^2")
+    parity_rule.check(rel_e, fl_e, cond, 1e-4, f"golden {name} E_loc")
 
 
 def test_analytic_helium_like():
