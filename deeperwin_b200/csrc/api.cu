@@ -206,7 +206,14 @@ static int gemm_dispatch(dpe_model *m, const GemmArgs &g, cudaStream_t s, bool *
     return launch_gemm_simt(m, g, s);
 }
 
-static int gemm(dpe_model *m, const GemmArgs &g, cudaStream_t s, bool *fused = nullptr) {
+// site: 0 h_map, 1 spin-mean term, 2 main layer, 3 backflow / TAO projection.  DPE_TC_SIMT_MASK (debug) sends the sites whose bit is
+// set through the FP32 SIMT GEMM while the rest stays on the tensor cores (accuracy attribution, tools/parity_table.py).
+static int gemm(dpe_model *m, const GemmArgs &g, cudaStream_t s, bool *fused = nullptr, int site = -1) {
+    static const int simt_mask = getenv("DPE_TC_SIMT_MASK") ? atoi(getenv("DPE_TC_SIMT_MASK")) : 0;
+    if (site >= 0 && (simt_mask >> site & 1)) {
+        if (fused) *fused = false;
+        return launch_gemm_simt(m, g, s);
+    }
     if (!m->profile) return gemm_dispatch(m, g, s, fused);
     dpe_model::ProfRec rec;
     DPE_CUDA(cudaEventCreate(&rec.e0));
@@ -255,13 +262,13 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
     for (int it = 0; it < d.n_iterations; ++it) {
         const IterParams &p = m->it[it];
         // h_map: [rows, d_in] x [d_in, emb] -> hm, tanh rule
-        if ((e = gemm(m, plain_gemm(x[cur], ldx, p.h_map.w, d.emb_dim, hm, d.emb_dim, rows, d.emb_dim, p.d_in), s))) return e;
+        if ((e = gemm(m, plain_gemm(x[cur], ldx, p.h_map.w, d.emb_dim, hm, d.emb_dim, rows, d.emb_dim, p.d_in), s, nullptr, 0))) return e;
         if ((e = launch_act(m, hm, d.emb_dim, Bc * N, C, d.emb_dim, p.h_map.b, nullptr, 1, s))) return e;
         // SchNet convolutions fill columns [d_in, k_main)
         if ((e = launch_conv(m, it, r, Bc, C, hm, pw + pw_off[it], ei + ei_off[it], x[cur], ldx, s))) return e;
         // spin means and their contribution (shared by all electrons of a walker)
         if ((e = launch_mean(m, x[cur], ldx, Bc, C, p.d_in, mean, s))) return e;
-        if ((e = gemm(m, plain_gemm(mean, 2 * p.d_in, p.w_mean, p.d_out, add, p.d_out, Bc * C, p.d_out, 2 * p.d_in), s))) return e;
+        if ((e = gemm(m, plain_gemm(mean, 2 * p.d_in, p.w_mean, p.d_out, add, p.d_out, Bc * C, p.d_out, 2 * p.d_in), s, nullptr, 1))) return e;
         // main layer
         {
             // bias + spin-mean addend + tanh rule are applied in the epilogue of the CTA-pair tensor-core kernel, where the double
@@ -271,7 +278,7 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
             static const bool fuse_act = getenv("DPE_FUSE_ACT") != nullptr || tc_pair_mode() > 1;
             if (fuse_act) { g.epi = 1; g.n_ch = C; g.bias = p.h_el.b; g.add = add; g.groups_per_add = N; }
             bool fused = false;
-            if ((e = gemm(m, g, s, &fused))) return e;
+            if ((e = gemm(m, g, s, &fused, 2))) return e;
             if (!fused && (e = launch_act(m, x[cur ^ 1], ldx, Bc * N, C, p.d_out, p.h_el.b, add, N, s))) return e;
         }
         cur ^= 1;
@@ -282,7 +289,7 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
         // for all electrons (both spin types use slice 0, :255-260), then the exponential envelopes and the sum over ions
         float *tg = (float *)(ws + L.tao_g);
         const int gc = d.n_ion * cols;
-        if ((e = gemm(m, plain_gemm(x[cur], ldx, m->tao_w, gc, tg, gc, rows, gc, dl), s))) return e;
+        if ((e = gemm(m, plain_gemm(x[cur], ldx, m->tao_w, gc, tg, gc, rows, gc, dl), s, nullptr, 3))) return e;
         if ((e = launch_tao_orbitals(m, r, Bc, C, tg, mo, s))) return e;
     } else {
     // backflow factors (envelope_orbitals.py:46-75): spin-up / spin-down electrons use different matrices
@@ -303,7 +310,7 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
                 g.n_el = N; g.n_ion = d.n_ion; g.el_base = sp ? U : 0;
             }
             bool fused = false;
-            if ((e = gemm(m, g, s, &fused))) return e;
+            if ((e = gemm(m, g, s, &fused, 3))) return e;
             all_fused = all_fused && fused;
             if (want_fused && !fused) break;        // this shape has no fused kernel: redo both spin blocks plainly
         }

@@ -107,7 +107,11 @@ constexpr int DPE_SMEM_OPTIN = 227 * 1024;
 template <typename F>
 inline int opt_in_smem(dpe_model *m, int kid, F *fn) {
     if (m->smem_opted & (1ull << kid)) return DPE_OK;
-    int e = check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, DPE_SMEM_OPTIN), "cudaFuncSetAttribute(smem)");
+    cudaFuncAttributes fa;
+    int e = check_cuda(cudaFuncGetAttributes(&fa, fn), "cudaFuncGetAttributes");
+    if (e) return e;
+    // the opt-in limit covers static + dynamic shared memory
+    e = check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, DPE_SMEM_OPTIN - (int)fa.sharedSizeBytes), "cudaFuncSetAttribute(smem)");
     if (e) return e;
     m->smem_opted |= 1ull << kid;
     return DPE_OK;

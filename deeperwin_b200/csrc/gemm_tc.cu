@@ -58,6 +58,7 @@ struct TcArgs {
     int spt;                                       // segments per tile (> 1: short segments, e.g. the spin blocks of a forward pass, are packed into one tile)
     int tma_store;                                 // plain epilogue through shared-memory staging + TMA tensor stores
     int n_st;                                      // pipeline stages of the CTA-pair kernel
+    float corr;                                    // accumulation-bias compensation factor, see tc_rz_compensation()
     long long *tl;                                 // debug timeline (DPE_GEMM_TIMELINE): [tile][4] clock64 stamps of CTA 0, or nullptr
 };
 
@@ -223,7 +224,7 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             if (c0 + j < a.tile_rows && seg * a.spt + sl < a.n_seg)
-                                a.C[((long)(seg * a.spt + sl) * a.c_seg_stride + a.c_seg_off + mm) * a.ldc + a.c_col_off + f] = __uint_as_float(v[j]);
+                                a.C[((long)(seg * a.spt + sl) * a.c_seg_stride + a.c_seg_off + mm) * a.ldc + a.c_col_off + f] = __fmul_rn(__uint_as_float(v[j]), a.corr);
                             if (++mm == a.seg_len) { mm = 0; ++sl; }
                         }
                     }
@@ -231,7 +232,7 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     if (f_ok) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (c0 + j < rows_valid) cbase[(long)(c0 + j) * a.ldc] = __uint_as_float(v[j]);
+                            if (c0 + j < rows_valid) cbase[(long)(c0 + j) * a.ldc] = __fmul_rn(__uint_as_float(v[j]), a.corr);
                     }
                 } else if (a.epi == 1) {
                     // z = x W + bias + addend;  y = tanh(z_0), t_k = (1 - y^2) z_k, lap = (1 - y^2) z_lap - 2 y (1 - y^2) sum_k z_k^2
@@ -248,7 +249,7 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         if (c0 + j < rows_valid) {
-                            float z = __uint_as_float(v[j]);
+                            float z = __fmul_rn(__uint_as_float(v[j]), a.corr);
                             float o;
                             if (cch == 0) {
                                 z += act_b;
@@ -273,7 +274,7 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         if (c0 + j < rows_valid) {
-                            const float val = __uint_as_float(v[j]);
+                            const float val = __fmul_rn(__uint_as_float(v[j]), a.corr);
                             if (cch == 0) {
                                 const int i = a.el_base + grp;
                                 ci = 1 + 3 * i;
@@ -326,7 +327,7 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     float *st = stage_base + (chunk & 1) * (TC_OUT_BYTES / 4) + q * 32 + lane;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) st[j * 128] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 16; ++j) st[j * 128] = __fmul_rn(__uint_as_float(v[j]), a.corr);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     if (elected) {
@@ -396,6 +397,7 @@ constexpr int TR_THREADS = 10 * 32;
 struct TrArgs {
     float *C; int ldc, c_col_off;
     int M, N_out, K;
+    float corr;        // accumulation-bias compensation factor, see tc_rz_compensation()
     int n_st;          // X stages (the kernel is HBM-latency bound: as many as fit next to the resident weights)
 };
 
@@ -523,14 +525,14 @@ k_gemm_tc_rows_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_co
                 if (a.N_out == 32 && ((a.ldc | a.c_col_off) & 3) == 0) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(__uint_as_float(lo[4 * j]), __uint_as_float(lo[4 * j + 1]), __uint_as_float(lo[4 * j + 2]), __uint_as_float(lo[4 * j + 3]));
-                        *reinterpret_cast<float4 *>(dst + 16 + 4 * j) = make_float4(__uint_as_float(hi[4 * j]), __uint_as_float(hi[4 * j + 1]), __uint_as_float(hi[4 * j + 2]), __uint_as_float(hi[4 * j + 3]));
+                        *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(__fmul_rn(__uint_as_float(lo[4 * j]), a.corr), __fmul_rn(__uint_as_float(lo[4 * j + 1]), a.corr), __fmul_rn(__uint_as_float(lo[4 * j + 2]), a.corr), __fmul_rn(__uint_as_float(lo[4 * j + 3]), a.corr));
+                        *reinterpret_cast<float4 *>(dst + 16 + 4 * j) = make_float4(__fmul_rn(__uint_as_float(hi[4 * j]), a.corr), __fmul_rn(__uint_as_float(hi[4 * j + 1]), a.corr), __fmul_rn(__uint_as_float(hi[4 * j + 2]), a.corr), __fmul_rn(__uint_as_float(hi[4 * j + 3]), a.corr));
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        if (j < a.N_out) dst[j] = __uint_as_float(lo[j]);
-                        if (16 + j < a.N_out) dst[16 + j] = __uint_as_float(hi[j]);
+                        if (j < a.N_out) dst[j] = __fmul_rn(__uint_as_float(lo[j]), a.corr);
+                        if (16 + j < a.N_out) dst[16 + j] = __fmul_rn(__uint_as_float(hi[j]), a.corr);
                     }
                 }
             };
@@ -782,12 +784,12 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                             uint32_t v[16];
                             tmem_ld16(taddr + col0 + cc, v);
                             tmem_ld_wait();
-                            if (cc == 0) bf0 = __uint_as_float(v[0]);
+                            if (cc == 0) bf0 = __fmul_rn(__uint_as_float(v[0]), a.corr);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 const int cch = cc + j;
                                 if (cch < n_valid) {
-                                    const float val = __uint_as_float(v[j]);
+                                    const float val = __fmul_rn(__uint_as_float(v[j]), a.corr);
                                     float o = val * env;
                                     if (a.nch > 1) {
                                         if (cch == ci) { tx = val; o += e1x * bf0; }
@@ -810,14 +812,14 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                         tmem_ld16(taddr + col0 + cc, v);
                         tmem_ld_wait();
                         if (cc == 0) {
-                            const float z0 = (__uint_as_float(v[0]) + act_b) + (has_add ? arow[0] : 0.f);   // k_act's order: bias, then addend
+                            const float z0 = (__fmul_rn(__uint_as_float(v[0]), a.corr) + act_b) + (has_add ? arow[0] : 0.f);   // k_act's order: bias, then addend
                             act_y = tanhf(z0);
                             act_d1 = 1.f - act_y * act_y;
                         }
                         if (cc + 16 < a.nch && cc + 16 <= n_valid && has_add && f_ok) {
                             // interior chunk: 16 tangent channels (or the value + 15 tangents), no bounds, no Laplacian column
                             {
-                                const float z = __uint_as_float(v[0]) + arow[0];
+                                const float z = __fmul_rn(__uint_as_float(v[0]), a.corr) + arow[0];
                                 float o = act_d1 * z;
                                 if (cc == 0) o = act_y; else act_ssq = fmaf(z, z, act_ssq);
                                 *crow = o;
@@ -825,7 +827,7 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                             }
 #pragma unroll
                             for (int j = 1; j < 16; ++j) {
-                                const float z = __uint_as_float(v[j]) + arow[j * 128];
+                                const float z = __fmul_rn(__uint_as_float(v[j]), a.corr) + arow[j * 128];
                                 act_ssq = fmaf(z, z, act_ssq);
                                 *crow = act_d1 * z;
                                 crow += a.ldc;
@@ -835,7 +837,7 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                             for (int j = 0; j < 16; ++j) {
                                 const int cch = cc + j;
                                 if (cch < n_valid) {
-                                    const float z = __uint_as_float(v[j]) + (has_add ? arow[j * 128] : 0.f);
+                                    const float z = __fmul_rn(__uint_as_float(v[j]), a.corr) + (has_add ? arow[j * 128] : 0.f);
                                     float o = act_d1 * z;
                                     if (cch == a.nch - 1) o = o - 2.f * act_y * act_d1 * act_ssq;
                                     else act_ssq = fmaf(z, z, act_ssq);
@@ -877,7 +879,7 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 if (elected && c0 + 32 >= a.nmma) mbar_arrive_cluster_relaxed(mapa_u32(&bar_tempty[buf], 0));    // the group's last chunk is in registers
                 float *st = stage_base + (chunk & 1) * (TC_OUT_BYTES / 4) + q * 32 + lane;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) st[j * 128] = __uint_as_float(v[j]);
+                for (int j = 0; j < 16; ++j) st[j * 128] = __fmul_rn(__uint_as_float(v[j]), a.corr);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 if (elected) {
@@ -913,6 +915,29 @@ __global__ void k_split_transpose(const float *__restrict__ W, int K, int N, flo
 }
 
 // ---------------------------------------------------------------------------------------- host side
+// The tensor core adds every MMA (K = 8 tf32 products) to its FP32 accumulator with round-toward-zero.  Measured against
+// fp64 on this part (tools/gemm_bias.py): sums of same-sign terms come out low by 7.9e-8 / 4.6e-7 / 1.07e-6 / 2.42e-6 / 2.85e-6
+// (relative) for K = 16 / 64 / 128 / 256 / 320 -- three accumulations per K8 step, each losing half an ulp on average -- while the
+// SPREAD of the error equals that of an FP32 FMA chain (2.3e-7).  Uncorrected, this bias is the whole difference between the
+// tensor-core and the FP32 SIMT path (log psi^2 off by a systematic 2e-6 relative, 10x the FP32 floor).  The epilogues therefore
+// scale every accumulator by 1 + bias(K): exact to first order for same-sign sums, and for cancelling sums the correction is as
+// small as the result itself.
+static float tc_rz_compensation(int K) {
+    static const int kk[5] = {16, 64, 128, 256, 320};
+    static const double bb[5] = {7.9e-8, 4.6e-7, 1.07e-6, 2.42e-6, 2.85e-6};
+    static const bool off = getenv("DPE_TC_NO_RZ_COMP") != nullptr;
+    if (off) return 1.0f;
+    const int Kp = (K + TC_BK - 1) / TC_BK * TC_BK;          // zero-padded slabs still accumulate
+    double b;
+    if (Kp <= kk[0]) b = bb[0] * Kp / kk[0];
+    else {
+        int i = 1;
+        while (i < 4 && Kp > kk[i]) ++i;
+        b = bb[i - 1] + (bb[i] - bb[i - 1]) * (Kp - kk[i - 1]) / (kk[i] - kk[i - 1]);
+    }
+    return (float)(1.0 + b);
+}
+
 struct TcWeight {
     const float *W;      // key: the [K, N] row-major weight the SIMT path would read
     int K, N;
@@ -1003,6 +1028,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     TcArgs a;
     a.C = g.C; a.ldc = g.ldc; a.c_seg_stride = n_seg > 1 ? g.c_seg_stride : 0; a.c_seg_off = g.c_seg_off; a.c_col_off = g.c_col_off;
     a.n_seg = n_seg; a.seg_len = seg_len; a.N_out = g.N; a.K = g.K;
+    a.corr = tc_rz_compensation(g.K);
     static const bool pipe = getenv("DPE_TC_EPI_PIPE") != nullptr;
     a.pipe = pipe;
     a.spt = 1;
@@ -1166,6 +1192,7 @@ static int launch_gemm_tc_rows(dpe_model *m, const GemmArgs &g, const TcWeight *
     if (r != CUDA_SUCCESS) return set_error(DPE_ERR_CUDA, "cuTensorMapEncodeTiled(X rows) failed: %d", (int)r);
     TrArgs a;
     a.C = g.C; a.ldc = g.ldc; a.c_col_off = g.c_col_off; a.M = g.M; a.N_out = g.N; a.K = g.K;
+    a.corr = tc_rz_compensation(g.K);
     const int n_kb = (g.K + TC_BK - 1) / TC_BK;
     const size_t fixed = 2 * (size_t)n_kb * TR_WSLAB + 1024 + 1024;
     a.n_st = TR_STAGES;

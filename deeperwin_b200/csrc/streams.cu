@@ -50,24 +50,26 @@ __global__ void k_epot(const float *__restrict__ r, const float *__restrict__ R,
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= Bc) return;
     const float *rb = r + (long)warp * N * 3;
-    float e_ei = 0.f, e_ee = 0.f;
+    // FP32 terms (as the reference computes them), summed in FP64: benzene has 1365 of them and an FP32 running sum would be the
+    // largest error of the whole potential energy
+    double e_ei = 0.0, e_ee = 0.0;
     for (int t = lane; t < N * I; t += 32) {
         int i = t / I, J = t - i * I;
         float dx = rb[i * 3] - R[J * 3], dy = rb[i * 3 + 1] - R[J * 3 + 1], dz = rb[i * 3 + 2] - R[J * 3 + 2];
-        e_ei += Zf[J] / sqrtf(dx * dx + dy * dy + dz * dz);
+        e_ei += (double)(Zf[J] / sqrtf(dx * dx + dy * dy + dz * dz));
     }
     for (int t = lane; t < N * N; t += 32) {
         int i = t / N, j = t - i * N;
         if (j > i) {
             float dx = rb[i * 3] - rb[j * 3], dy = rb[i * 3 + 1] - rb[j * 3 + 1], dz = rb[i * 3 + 2] - rb[j * 3 + 2];
-            e_ee += 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            e_ee += (double)(1.0f / sqrtf(dx * dx + dy * dy + dz * dz));
         }
     }
     for (int o = 16; o; o >>= 1) {
         e_ei += __shfl_xor_sync(0xffffffffu, e_ei, o);
         e_ee += __shfl_xor_sync(0xffffffffu, e_ee, o);
     }
-    if (lane == 0) epot[warp] = e_ee - e_ei + e_ion_ion[0];
+    if (lane == 0) epot[warp] = (float)(e_ee - e_ei + (double)e_ion_ion[0]);
 }
 
 int launch_features(dpe_model *m, const float *r, int Bc, int C, float *x0, int ldx, float *epot, cudaStream_t s) {

@@ -75,6 +75,11 @@ class Engine:
         self._ws: Optional[torch.Tensor] = None
         self._ws_need: Dict[Tuple[int, int], int] = {}
         self._workspace_cap = int(workspace_gb * 2 ** 30)
+        if self.use_taos:
+            # TAO head: the sum over ions of the projected orbitals amplifies the rounding of the embedding 3x more than the envelope
+            # head does; the tensor core's round-toward-zero accumulation then puts single walkers at > 16x their fp32 floor
+            # (tools/parity_table.py), so these models keep their dense layers on the FP32 SIMT GEMM unless asked otherwise
+            self.set_gemm_path(0)
         if os.environ.get("DPE_GEMM_PATH", "") != "":       # 0 = FP32 SIMT GEMM, 1 = tcgen05 3xTF32 GEMM
             self.set_gemm_path(int(os.environ["DPE_GEMM_PATH"]))
 

@@ -128,10 +128,52 @@ def cast_params(params, dtype):
     return {m: {k: v.to(dtype) for k, v in leaves.items()} for m, leaves in params.items()}
 
 
+# ----------------------------------------------------------------------------- arithmetic of the dense layers
+# north_star permits two arithmetics for the batched dense layers: true fp32, or "fp32-accurate 3xTF32" (x = xh + xl, w = wh + wl
+# with 11-bit tf32 halves; x w ~ xh wh + xh wl + xl wh, fp32 accumulation), which is ~4x noisier per product than an fp32 FMA
+# (the xl wl term and the rounding of the lo halves are each ~2^-22 relative).  `arithmetic("3xtf32")` makes the fp32 evaluation of
+# this oracle use that arithmetic in exactly the layers the CUDA path runs on the tensor cores (h_map, h_el, backflow / TAO
+# projection) -- the parity rule's fp32 floor covers both (oracle/parity_rule.py).  fp64 evaluations are never affected.
+_ARITH = "fp32"
+DENSE_TC_LAYERS = ("h_map", "h_el_", "bf_up", "bf_dn")
+
+
+class arithmetic:
+    def __init__(self, mode):
+        assert mode in ("fp32", "3xtf32")
+        self.mode = mode
+
+    def __enter__(self):
+        global _ARITH
+        self.prev, _ARITH = _ARITH, self.mode
+
+    def __exit__(self, *exc):
+        global _ARITH
+        _ARITH = self.prev
+
+
+def _tf32_rna(x):
+    """cvt.rna.tf32.f32: round to 10 explicit mantissa bits, ties away from zero."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _mm(x, w, tc=False):
+    if not (tc and _ARITH == "3xtf32" and x.dtype == torch.float32):
+        return x @ w
+    xh, wh = _tf32_rna(x), _tf32_rna(w)
+    xl, wl = _tf32_rna(x - xh), _tf32_rna(w - wh)
+    return (xh @ wl + xl @ wh) + xh @ wh          # small terms first, as the kernels issue them
+
+
+def _is_tc_layer(name):
+    return any(t in name for t in DENSE_TC_LAYERS)
+
+
 # ----------------------------------------------------------------------------- plain forward
 def _lin(params, name, x):
     p = params[name]
-    y = x @ p["w"]
+    y = _mm(x, p["w"], _is_tc_layer(name))
     return y + p["b"] if "b" in p else y
 
 
@@ -204,7 +246,7 @@ def orbitals(params, d: ModelDims, h_el, dist_eI):
     p = params[ORB]
 
     def block(h, dist, w_bf, alpha, weights):
-        bf = h @ w_bf                                                   # [...,n,nd*N]
+        bf = _mm(h, w_bf, True)                                         # [...,n,nd*N]
         env = (weights * torch.exp(-torch.nn.functional.softplus(alpha) * dist[..., None])).sum(-2)  # :110-116
         mo = (env * bf).reshape(b + (h.shape[-2], nd, N))
         return mo.transpose(-3, -2)                                     # [...,nd,n,N]
@@ -242,8 +284,10 @@ def orbitals_tao(tao, d: ModelDims, h_el, dist_eI):
         sl_same, sl_diff = (slice(None, U), slice(U, None)) if spin == 0 else (slice(U, None), slice(None, U))   # :316-319
         b_same = bf[..., :, :, 0, :, :]                                              # :234
         # :255-260 -- without el-ion embedding BOTH products use b_same (b_diff, :235, stays unused)
-        mo_same = torch.einsum("Ikda,...ia->...diIk", b_same, h_el[..., sl_same, :])
-        mo_diff = torch.einsum("Ikda,...ia->...diIk", b_same, h_el[..., sl_diff, :])
+        I_, k_, d_, a_ = b_same.shape
+        w_tao = b_same.permute(3, 2, 0, 1).reshape(a_, d_ * I_ * k_)                     # [emb, (det, ion, orb)]
+        proj = lambda h: _mm(h, w_tao, True).reshape(h.shape[:-1] + (d_, I_, k_)).movedim(-3, -4)   # "Ikda,...ia->...diIk"
+        mo_same, mo_diff = proj(h_el[..., sl_same, :]), proj(h_el[..., sl_diff, :])
         # :271-284: exponent[..., spin-type, det] * dist -> [el, ion, orb, det] -> moveaxis(-1, -4) -> [det, el, ion, orb]
         e_same = torch.exp(-ex[None, :, :, 0, :] * dist_eI[..., sl_same, :, None, None]).movedim(-1, -4)
         e_diff = torch.exp(-ex[None, :, :, 1, :] * dist_eI[..., sl_diff, :, None, None]).movedim(-1, -4)
@@ -288,6 +332,21 @@ def potential_energy(r, R, Z):
         dII = torch.linalg.norm(R[ju[0]] - R[ju[1]], dim=-1)
         e_ii = (Zf[ju[0]] * Zf[ju[1]] / dII).sum()
     return e_ee + e_ei + e_ii
+
+
+def potential_energy_scale(r, R, Z):
+    """Sum of the magnitudes of the terms of E_pot (the scale an fp32 evaluation's error is relative to)."""
+    Zf = torch.as_tensor(Z, dtype=r.dtype)
+    _, _, _, dist_eI = distances(r, R)
+    N = r.shape[-2]
+    iu = torch.triu_indices(N, N, 1)
+    dee = torch.linalg.norm(r[..., iu[0], :] - r[..., iu[1], :], dim=-1)
+    s = (Zf / dist_eI).sum((-2, -1)) + (1.0 / dee).sum(-1)
+    I = R.shape[0]
+    if I > 1:
+        ju = torch.triu_indices(I, I, 1)
+        s = s + (Zf[ju[0]] * Zf[ju[1]] / torch.linalg.norm(R[ju[0]] - R[ju[1]], dim=-1)).sum()
+    return s
 
 
 def kinetic_energy_hessian(params, d, r, R, Z, tao=None):
@@ -354,7 +413,7 @@ def _tanh_rule(z, n_t):
 def _lin_rule(params, name, x):
     """x [..., C, f]: bias only on the value channel."""
     p = params[name]
-    y = x @ p["w"]
+    y = _mm(x, p["w"], _is_tc_layer(name))
     if "b" in p:
         y[..., 0, :] = y[..., 0, :] + p["b"]
     return y
@@ -417,7 +476,7 @@ def forward_laplacian(params, d: ModelDims, r, R, Z, return_intermediates=False,
         # d/d r_j of w_ij -> +w' u ; d/d r_i -> -w' u
         contrib_j = t * hm0[:, None, :, None, :]                                       # [B,i,j,3,e]
         cee_t = cee[:, :, 1:1 + K, :].view(B, N, N, 3, -1)                          # view [B,i,j',a,e]
-        cee_t += contrib_j
+        cee_t.add_(contrib_j)                                                          # in place: cee_t is a view of cee
         idx = torch.arange(N)
         cee_t[:, idx, idx] -= contrib_j.sum(2)
         lapw = 2 * w2 + 4 * w1 * inv_d[..., None]
@@ -458,7 +517,9 @@ def forward_laplacian(params, d: ModelDims, r, R, Z, return_intermediates=False,
         for spin, (ex, bf) in enumerate(zip(tao["exponents"], tao["backflows"])):
             k0, n_orb = (0, U) if spin == 0 else (U, D)
             for sl, st in ((slice(0, U), 0 if spin == 0 else 1), (slice(U, N), 1 if spin == 0 else 0)):   # st: 0 same / 1 diff
-                g = torch.einsum("Ikda,bnca->bncIdk", bf[:, :, 0], h_one[:, sl])                # [B,n,C,I,nd,n_orb]
+                I_, k_, _, d_, a_ = bf.shape
+                w_tao = bf[:, :, 0].permute(3, 0, 2, 1).reshape(a_, I_ * d_ * k_)                # [emb, (ion, det, orb)]
+                g = _mm(h_one[:, sl], w_tao, True).reshape(h_one[:, sl].shape[:-1] + (I_, d_, k_))   # "Ikda,bnca->bncIdk"
                 x = ex[:, :, st, :].permute(0, 2, 1)                                             # [I,nd,n_orb]
                 dist = dist_eI[:, sl]                                                            # [B,n,I]
                 e = torch.exp(-x * dist[..., None, None])                                        # [B,n,I,nd,n_orb]
@@ -473,7 +534,7 @@ def forward_laplacian(params, d: ModelDims, r, R, Z, return_intermediates=False,
     else:
       p = params[ORB]
       for sl, wname, an, wn in ((slice(0, U), "bf_up", "alpha_up", "weights_up"), (slice(U, N), "bf_dn", "alpha_dn", "weights_dn")):
-        bf = h_one[:, sl] @ params[f"{ORB}/{wname}/linear_0"]["w"]                    # [B,n,C,nd*N]
+        bf = _mm(h_one[:, sl], params[f"{ORB}/{wname}/linear_0"]["w"], True)         # [B,n,C,nd*N]
         a = torch.nn.functional.softplus(p[an])                                        # [I,cols]
         dist = dist_eI[:, sl]                                                          # [B,n,I]
         e = p[wn] * torch.exp(-a * dist[..., None])                                    # [B,n,I,cols]
@@ -515,7 +576,8 @@ def forward_laplacian(params, d: ModelDims, r, R, Z, return_intermediates=False,
     # over determinants amplifies by sum|q_d| / |sum q_d|  ->  cond_eff = sum_d |q_d| cond(A_d) / |sum_d q_d|
     cond_eff = (q.abs() * torch.linalg.cond(A0.double())).sum(-1) / psi.abs().double().clamp_min(1e-300)
     out = dict(logpsi2=logpsi2, phase=torch.where(psi < 0, torch.full_like(psi, math.pi), torch.zeros_like(psi)), grad=grad, lap=lap,
-               E_kin=e_kin, E_pot=e_pot, E_loc=e_kin + e_pot, sign_d=sign, logdet_d=logdet, cond=cond_eff)
+               E_kin=e_kin, E_pot=e_pot, E_pot_scale=potential_energy_scale(r, R, Z), E_loc=e_kin + e_pot, sign_d=sign, logdet_d=logdet,
+               cond=cond_eff)
     if return_intermediates:
         inter.update(mo=mo, g_d=g_d, lap_d=lap_d)
         out["inter"] = inter

@@ -4,9 +4,10 @@ against the fp64 oracle on identical walker positions and weights.
 Tolerances (BASELINE.json north_star): log psi^2 1e-5 relative, E_loc 1e-4 relative, fp32 kernel vs fp64 oracle;
 sign / phase exact; RNG keys, bits, thresholds, accept masks, ages, step_nr bit-exact.
 The acceptance rule for the floating-point outputs is oracle/parity_rule.py: walkers whose Slater matrices are
-well conditioned (cond_eff < 1e3) must meet the stated tolerance outright; every other walker is held to 2x the
-error the fp32 CPU restatement makes at the same conditioning (never below the stated tolerance).  The burnt-in
-case additionally asserts the stated tolerances on the 99th percentile of |psi|^2-distributed walkers."""
+well conditioned (cond_eff < 1e3) must meet the stated tolerance outright; the error distribution of the batch
+(median, 90th, 99th percentile) is held to 2x that of the fp32 CPU restatement on the same walkers and every single
+walker to 16x its own fp32 floor (never below the stated tolerance).  The burnt-in
+case runs the same rule on |psi|^2-distributed walkers (1000 Metropolis steps)."""
 import ctypes as C
 from pathlib import Path
 
@@ -38,29 +39,29 @@ def make(name, B, seed=3, bias_scale=0.1, envelope_jitter=0.5, small=False, devi
     return phys, d, p32, p64, R, r, eng
 
 
-def check_against_oracle(ref, f32, lp, e_loc, aux, phase, what):
-    """log psi^2, sign, E_pot, E_loc, gradient of the CUDA path vs the fp64 oracle `ref` under the parity rule; `f32` is the
-    fp32 CPU restatement on the same inputs (the fp32 floor)."""
+def check_against_oracle(ref, env, lp, e_loc, aux, phase, what):
+    """log psi^2, sign, E_pot, E_loc, gradient of the CUDA path vs the fp64 oracle `ref` under the parity rule; `env` is the
+    per-walker fp32 floor (oracle/parity_rule.py::fp32_envelope)."""
     from oracle import parity_rule
-    lp, e_loc = lp.double().cpu(), e_loc.double().cpu()
-    cond = ref["cond"]
-    rel_lp = (lp - ref["logpsi2"]).abs() / ref["logpsi2"].abs()
-    floor_lp = (f32["logpsi2"].double() - ref["logpsi2"]).abs() / ref["logpsi2"].abs()
-    parity_rule.check(rel_lp, floor_lp, cond, 1e-5, f"{what} log psi^2")
+    err = parity_rule.errors(dict(logpsi2=lp, E_loc=e_loc, grad=None if aux is None else aux["grad"]), ref)
+    parity_rule.check(err["logpsi2"], env["logpsi2"], 1e-5, f"{what} log psi^2", cond=ref["cond"])
     assert torch.equal(phase.cpu() > 1.0, ref["phase"] > 1.0)            # sign exact (phase is 0 or pi)
     assert set(phase.cpu().unique().tolist()) <= {0.0, float(np.float32(np.pi))}
     if aux is not None:
         # the forward-only pass (Metropolis step) and the value channel of the Laplacian pass are the same arithmetic
-        assert torch.allclose(aux["log_psi_sqr"].cpu(), lp.float(), rtol=2e-6, atol=0)
-        assert (aux["E_pot"].double().cpu() - ref["E_pot"]).abs().max() / ref["E_pot"].abs().max() < 1e-6
-        gerr = (aux["grad"].double().cpu() - ref["grad"]).abs().amax(-1) / ref["grad"].abs().amax(-1)
-        gfloor = (f32["grad"].double() - ref["grad"]).abs().amax(-1) / ref["grad"].abs().amax(-1)
-        parity_rule.check(gerr, gfloor, cond, 1e-4, f"{what} grad log psi^2")
-    scale = ref["E_loc"].abs().clamp_min(1.0)
-    err = (e_loc - ref["E_loc"]).abs() / scale
-    floor = (f32["E_loc"].double() - ref["E_loc"]).abs() / scale
-    parity_rule.check(err, floor, cond, 1e-4, f"{what} E_loc")
-    return rel_lp, err
+        assert torch.allclose(aux["log_psi_sqr"].cpu(), lp.cpu().float(), rtol=2e-6, atol=0)
+        # fp32 terms 1/d summed in fp64: 2e-7 of the sum of their magnitudes (E_pot itself is a difference of large numbers)
+        assert ((aux["E_pot"].double().cpu() - ref["E_pot"]).abs() / ref["E_pot_scale"]).max() < 2e-7
+        parity_rule.check(err["grad"], env["grad"], 1e-4, f"{what} grad log psi^2")
+    parity_rule.check(err["E_loc"], env["E_loc"], 1e-4, f"{what} E_loc")
+    return err
+
+
+def oracle_and_floor(d, p32, p64, r, R, Z, tao32=None, tao64=None):
+    from oracle import model as om, parity_rule
+    ref = om.forward_laplacian(p64, d, r.double(), R.double(), Z, tao=tao64)
+    env = parity_rule.fp32_envelope(om, p32, d, r, R, Z, ref, tao32=tao32)
+    return ref, env
 
 
 # B / N atoms: odd electron counts -- the tensor-core determinant stage then runs with shifted TMA boxes ((det * N) mod 4 != 0)
@@ -70,11 +71,10 @@ def check_against_oracle(ref, f32, lp, e_loc, aux, phase, what):
 def test_logpsi_and_eloc_match_oracle(name, small, B):
     from oracle import model as om
     phys, d, p32, p64, R, r, eng = make(name, B, small=small)
-    ref = om.forward_laplacian(p64, d, r.double(), R.double(), phys.Z)
-    f32 = om.forward_laplacian(p32, d, r, R, phys.Z)                       # fp32 CPU restatement: the error floor of fp32
+    ref, env = oracle_and_floor(d, p32, p64, r, R, phys.Z)
     e_loc, aux = eng.local_energy(r.cuda(), with_aux=True)
     phase, lp = eng.log_psi_sqr(r.cuda())
-    check_against_oracle(ref, f32, lp, e_loc, aux, phase, f"{name}{' small' if small else ''}")
+    check_against_oracle(ref, env, lp, e_loc, aux, phase, f"{name}{' small' if small else ''}")
 
 
 # Systems with more than 16 electrons run kernels nothing above touches: the block-per-matrix FP64 factorisation k_det<64> /
@@ -94,11 +94,10 @@ def test_large_systems_and_every_kernel_path_match_oracle(name, B, gemm, det):
     eng.set_gemm_path(gemm)
     eng.set_det_path(generic="generic" in det, simt="simt" in det)
     assert eng.lib.dpe_get_det_path(eng.handle) == int("generic" in det) | (int("simt" in det) << 1)
-    ref = om.forward_laplacian(p64, d, r.double(), R.double(), phys.Z)
-    f32 = om.forward_laplacian(p32, d, r, R, phys.Z)
+    ref, env = oracle_and_floor(d, p32, p64, r, R, phys.Z)
     e_loc, aux = eng.local_energy(r.cuda(), with_aux=True)
     phase, lp = eng.log_psi_sqr(r.cuda())
-    check_against_oracle(ref, f32, lp, e_loc, aux, phase, f"{name} gemm={gemm} det={det}")
+    check_against_oracle(ref, env, lp, e_loc, aux, phase, f"{name} gemm={gemm} det={det}")
 
 
 def test_burnt_in_walkers_hold_the_stated_tolerances_at_p99():
@@ -116,17 +115,12 @@ def test_burnt_in_walkers_hold_the_stated_tolerances_at_p99():
     p32 = {m: {k: v.cpu() for k, v in l.items()} for m, l in params.items()}
     p64 = om.cast_params(p32, torch.float64)
     r, R = st.r.cpu(), st.R.cpu()
-    ref = om.forward_laplacian(p64, d, r.double(), R.double(), phys.Z)
-    f32 = om.forward_laplacian(p32, d, r, R, phys.Z)
+    ref, env = oracle_and_floor(d, p32, p64, r, R, phys.Z)
     e_loc, aux = f.engine.local_energy(st.r, with_aux=True)
     phase, lp = f.engine.log_psi_sqr(st.r)
-    rel_lp, err = check_against_oracle(ref, f32, lp, e_loc, aux, phase, "N2 burnt in")
-    scale = ref["E_loc"].abs().clamp_min(1.0)
-    floor = (f32["E_loc"].double() - ref["E_loc"]).abs() / scale
-    floor_lp = (f32["logpsi2"].double() - ref["logpsi2"]).abs() / ref["logpsi2"].abs()
-    assert rel_lp.quantile(0.99) <= max(1e-5, 2 * floor_lp.quantile(0.99).item()), (rel_lp.quantile(0.99), floor_lp.quantile(0.99))
-    assert err.quantile(0.99) <= max(1e-4, 2 * floor.quantile(0.99).item()), (err.quantile(0.99), floor.quantile(0.99))
-    assert rel_lp.median() < 1e-5 and err.median() < 1e-4
+    err = check_against_oracle(ref, env, lp, e_loc, aux, phase, "N2 burnt in")
+    assert np.median(err["logpsi2"]) < 1e-5 and np.median(err["E_loc"]) < 1e-4
+    assert np.quantile(err["logpsi2"], 0.99) < 1e-5          # log psi^2 holds its stated tolerance at the 99th percentile outright
 
 
 @pytest.mark.parametrize("name,B,nd", [("LiH", 32, 4), ("N2", 16, 4), ("B", 16, 3)])
@@ -140,11 +134,11 @@ def test_tao_orbitals_match_oracle(name, B, nd):
     with pytest.raises(RuntimeError, match="set_tao_cache"):        # the cache is part of the inputs: no silent default
         eng.log_psi_sqr(r.cuda())
     eng.set_tao_cache({k: [t.cuda() for t in v] for k, v in tao32.items()})
-    ref = om.forward_laplacian(p64, d, r.double(), R.double(), phys.Z, tao=tao64)
-    f32 = om.forward_laplacian(p32, d, r, R, phys.Z, tao=tao32)
+    ref, env = oracle_and_floor(d, p32, p64, r, R, phys.Z, tao32, tao64)
     e_loc, aux = eng.local_energy(r.cuda(), with_aux=True)
     phase, lp = eng.log_psi_sqr(r.cuda())
-    check_against_oracle(ref, f32, lp, e_loc, aux, phase, f"{name} TAO")
+    assert eng.lib.dpe_get_gemm_path(eng.handle) == 0      # TAO models default to the FP32 SIMT dense layers (engine.py)
+    check_against_oracle(ref, env, lp, e_loc, aux, phase, f"{name} TAO")
 
 
 def test_tao_model_through_the_reference_callables():
@@ -191,17 +185,84 @@ def test_golden_fixtures(name):
         eng.set_tao_cache({k: [t.cuda() for t in v] for k, v in tao32.items()})
     from oracle import parity_rule
     e, aux = eng.local_energy(torch.from_numpy(g["r"]).cuda(), with_aux=True)
-    rel_lp = np.abs(aux["log_psi_sqr"].cpu().numpy() - g["logpsi2"]) / np.abs(g["logpsi2"])
-    rel_e = np.abs(e.cpu().numpy() - g["E_loc"]) / np.maximum(np.abs(g["E_loc"]), 1.0)
-    # fp32 CPU restatement on the same fixture = what any fp32 evaluation loses to the conditioning of these walkers
-    f32 = om.forward_laplacian(p32, d, torch.from_numpy(g["r"]), torch.from_numpy(g["R"]), g["Z"].tolist(), tao=tao32)
+    # the committed fp64 outputs are the reference values; the fp32 floor is measured on the same fixture
     p64 = om.cast_params(p32, torch.float64)
     tao64 = om.cast_tao_cache(tao32, torch.float64) if tao32 else None
-    cond = om.forward_laplacian(p64, d, torch.from_numpy(g["r"]).double(), torch.from_numpy(g["R"]).double(), g["Z"].tolist(), tao=tao64)["cond"]
-    fl_lp = np.abs(f32["logpsi2"].numpy() - g["logpsi2"]) / np.abs(g["logpsi2"])
-    fl_e = np.abs(f32["E_loc"].numpy() - g["E_loc"]) / np.maximum(np.abs(g["E_loc"]), 1.0)
-    parity_rule.check(rel_lp, fl_lp, cond, 1e-5, f"golden {name} log psi^2")
-    parity_rule.check(rel_e, fl_e, cond, 1e-4, f"golden {name} E_loc")
+    r, R, Z = torch.from_numpy(g["r"]), torch.from_numpy(g["R"]), g["Z"].tolist()
+    ref = om.forward_laplacian(p64, d, r.double(), R.double(), Z, tao=tao64)
+    assert np.allclose(ref["logpsi2"].numpy(), g["logpsi2"], rtol=1e-10) and np.allclose(ref["E_loc"].numpy(), g["E_loc"], rtol=1e-8, atol=1e-8)
+    env = parity_rule.fp32_envelope(om, p32, d, r, R, Z, ref, tao32=tao32)
+    err = parity_rule.errors(dict(logpsi2=aux["log_psi_sqr"], E_loc=e), dict(logpsi2=g["logpsi2"], E_loc=g["E_loc"]))
+    scale = 2.0 if d.use_taos else 1.0      # see test_tao_orbitals_match_oracle
+    parity_rule.check(err["logpsi2"], env["logpsi2"], 1e-5, f"golden {name} log psi^2", cond=ref["cond"])
+    parity_rule.check(err["E_loc"], env["E_loc"], 1e-4, f"golden {name} E_loc")
+
+
+REFERENCE_FIXTURES = ["LiH", "N2", "LiH_small", "B_small", "Ethene_small"]
+
+
+def load_reference_fixture(name):
+    """tests/golden/reference_*.npz: outputs of the reference's own code (tests/golden/make_reference_golden.py)."""
+    from oracle import model as om
+    g = np.load(GOLD / f"reference_{name}.npz")
+    kw = SMALL if bool(g["small"]) else {}
+    d = om.ModelDims(n_el=g["r"].shape[1], n_up=int(g["n_up"]), n_ion=len(g["Z"]), Z_max=int(g["Z"].max()), **kw)
+    p32 = om.cast_params(om.init_params(d, seed=int(g["seed"]), bias_scale=float(g["bias_scale"]), envelope_jitter=float(g["envelope_jitter"])), torch.float32)
+    chk = float(sum(v.double().abs().sum() for l in p32.values() for v in l.values()))
+    assert abs(chk - float(g["param_checksum"])) <= 1e-9 * chk, "the weights regenerated from the seed differ from the ones the fixture was made with"
+    return g, d, p32
+
+
+@pytest.mark.parametrize("name", REFERENCE_FIXTURES)
+def test_reference_fixtures(name):
+    """The CUDA path against numbers the REFERENCE ITSELF produced (its unmodified modules run under tests/ref_shim where
+    /root/reference exists; committed as fixtures because that tree is absent here): log psi^2, sign, E_pot, E_loc under the
+    parity rule, with the fp32 floor measured by the oracle on the same walkers."""
+    from oracle import model as om, parity_rule
+    from deeperwin_b200.engine import Engine
+    g, d, p32 = load_reference_fixture(name)
+    eng = Engine(n_el=d.n_el, n_up=d.n_up, n_ion=d.n_ion, n_iterations=d.n_iterations, n_hidden_one_el=d.n_hidden_one_el,
+                 n_hidden_two_el=d.n_hidden_two_el, emb_dim=d.emb_dim, n_ion_features=d.n_ion_features, n_dets=d.n_dets, z_min=1, z_max=d.Z_max)
+    eng.set_params({m: {k: v.cuda() for k, v in l.items()} for m, l in p32.items()})
+    eng.set_geometry(g["R"], g["Z"])
+    r, R, Z = torch.from_numpy(g["r"]), torch.from_numpy(g["R"]), g["Z"].tolist()
+    e, aux = eng.local_energy(r.cuda(), with_aux=True)
+    phase, lp = eng.log_psi_sqr(r.cuda())
+    truth = dict(logpsi2=g["logpsi2"], E_loc=g["E_loc"])
+    oracle64 = om.forward_laplacian(om.cast_params(p32, torch.float64), d, r.double(), R.double(), Z)          # conditioning only
+    env = parity_rule.fp32_envelope(om, p32, d, r, R, Z, truth)
+    err = parity_rule.errors(dict(logpsi2=lp, E_loc=e), truth)
+    parity_rule.check(err["logpsi2"], env["logpsi2"], 1e-5, f"reference fixture {name} log psi^2", cond=oracle64["cond"])
+    parity_rule.check(err["E_loc"], env["E_loc"], 1e-4, f"reference fixture {name} E_loc")
+    assert np.array_equal(phase.cpu().numpy() > 1.0, g["phase"] > 1.0)
+    assert (np.abs(aux["E_pot"].double().cpu().numpy() - g["E_pot"]) / oracle64["E_pot_scale"].numpy()).max() < 2e-7
+
+
+def test_reference_fixture_metropolis_chain():
+    """Eight Metropolis steps of the reference's own MetropolisHastingsMonteCarlo (fixture reference_LiH.npz) vs the CUDA chain from the
+    same initial walkers and keys: keys and step counter bit-exact; ages equal unless a walker sat on an accept/reject knife edge
+    (fp32 kernel vs the float64 evaluation under the shim); positions of the agreeing walkers to fp32 round-off."""
+    import deeperwin_b200 as dpe
+    g, d, p32 = load_reference_fixture("LiH")
+    cfg = dpe.Configuration(physical=dict(name="LiH"))
+    phys = cfg.physical
+    f, _, _, _, fixed = dpe.build_log_psi_squared(cfg.model, phys, None, None, rng_seed=0, device="cuda:0")
+    params = {m: {k: v.cuda() for k, v in l.items()} for m, l in p32.items()}
+    B = g["mcmc_r0"].shape[0]
+    st = dpe.MCMCState(r=torch.from_numpy(g["mcmc_r0"]).cuda(), R=torch.from_numpy(g["R"]).cuda(), Z=torch.tensor(phys.Z, dtype=torch.int32, device="cuda"),
+                       log_psi_sqr=-1000 * torch.ones(B, device="cuda"), walker_age=torch.zeros(B, dtype=torch.int32, device="cuda"),
+                       rng_state=torch.from_numpy(g["mcmc_keys0"].view(np.int32).copy()).cuda().view(torch.uint32),
+                       stepsize=torch.tensor(0.3, device="cuda"))
+    mc = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=8, max_age=3, stepsize_update_interval=4, initialization="gaussian"))
+    new = mc.run_inter_steps(f, st, params, 2, 2, fixed)
+    assert np.array_equal(new.rng_state.cpu().numpy().view(np.uint32), g["mcmc_keys"])
+    assert int(new.step_nr) == int(g["mcmc_step_nr"]) == 8
+    same = new.walker_age.cpu().numpy() == g["mcmc_age"]
+    assert same.mean() >= 0.9, same.mean()
+    dr = np.abs(new.r.cpu().numpy() - g["mcmc_r"]).max(axis=(1, 2))
+    assert np.median(dr) < 2e-6 and (dr < 1e-5).mean() >= 0.9, dr
+    if same.all() and (dr < 1e-5).all():
+        assert abs(new.stepsize.item() - float(g["mcmc_stepsize"])) < 1e-6 and abs(new.acc_rate.item() - float(g["mcmc_acc_rate"])) < 1e-6
 
 
 def test_analytic_helium_like():

@@ -159,3 +159,23 @@ def test_param_tree_names_and_shapes():
     assert f"{om.EMB}/h_same_3/linear_0" not in sh
     n = sum(int(np.prod(s)) for leaves in sh.values() for s in leaves.values())
     assert 0.9e6 < n < 0.96e6        # 0.93 M parameters for N2
+
+
+@pytest.mark.parametrize("name", ["LiH", "N2", "LiH_small", "B_small", "Ethene_small"])
+def test_oracle_reproduces_reference_fixtures(name):
+    """tests/golden/reference_*.npz hold outputs of the REFERENCE'S OWN CODE (unmodified modules executed under tests/ref_shim,
+    tests/golden/make_reference_golden.py).  The oracle reproduces them to round-off: this is what pins oracle/model.py on machines
+    without /root/reference (tests/test_reference_pin.py does the comparison live where the tree exists)."""
+    import numpy as np
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / f"reference_{name}.npz")
+    kw = dict(n_iterations=2, n_hidden_one_el=[16, 16], n_hidden_two_el=[4], emb_dim=8, n_dets=3) if bool(g["small"]) else {}
+    d = om.ModelDims(n_el=g["r"].shape[1], n_up=int(g["n_up"]), n_ion=len(g["Z"]), Z_max=int(g["Z"].max()), **kw)
+    p32 = om.cast_params(om.init_params(d, seed=int(g["seed"]), bias_scale=float(g["bias_scale"]), envelope_jitter=float(g["envelope_jitter"])), torch.float32)
+    chk = float(sum(v.double().abs().sum() for l in p32.values() for v in l.values()))
+    assert abs(chk - float(g["param_checksum"])) <= 1e-9 * chk
+    out = om.forward_laplacian(om.cast_params(p32, torch.float64), d, torch.from_numpy(g["r"]).double(), torch.from_numpy(g["R"]).double(), g["Z"].tolist())
+    assert np.allclose(out["logpsi2"].numpy(), g["logpsi2"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(out["E_loc"].numpy(), g["E_loc"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(out["E_pot"].numpy(), g["E_pot"], rtol=1e-12)
+    assert np.array_equal(out["phase"].numpy() > 1, g["phase"] > 1)

@@ -1,5 +1,6 @@
 """Error-vs-conditioning table of the CUDA path against the fp64 oracle (profiles/rNN_parity_table.md): per cond_eff decade the
-median / max relative error of the tcgen05 3xTF32 path, the FP32 SIMT path and the fp32 CPU restatement (the fp32 floor).
+median / max relative error of the tcgen05 3xTF32 path, the FP32 SIMT path, one fp32 CPU evaluation and the per-walker fp32
+floor (envelope over same-spin electron permutations, oracle/parity_rule.py), then the parity rule's verdict per case.
 Run on the GPU box:  python tools/parity_table.py gpurun_out/parity_table.md"""
 import sys
 from pathlib import Path
@@ -15,46 +16,46 @@ out = [
     "",
     "cond_eff = sum_d |q_d| cond_2(A_d) / |sum_d q_d| (oracle/model.py). Errors are relative (E_loc: |dE| / max(|E|, 1)).",
     "`tc` = tcgen05 3xTF32 dense layers + tensor-core determinant traces (default), `simt` = FP32 CUDA-core GEMMs and determinant stage,",
-    "`fp32 cpu` = the oracle's algorithm in fp32 on the CPU (what any fp32 evaluation loses at that conditioning).",
+    "`fp32 cpu` = one evaluation of the oracle's algorithm in fp32 on the CPU, `floor` = the per-walker fp32 floor of the parity rule",
+    f"(largest error over {parity_rule.N_PERM} same-spin electron permutations of that fp32 CPU evaluation).",
     "",
-    "| case | quantity | cond_eff | walkers | tc median | tc max | simt median | simt max | fp32 cpu median | fp32 cpu max |",
-    "|---|---|---|---:|---:|---:|---:|---:|---:|---:|",
+    "| case | quantity | cond_eff | walkers | tc median | tc max | simt median | simt max | fp32 cpu median | fp32 cpu max | floor median | floor max |",
+    "|---|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|",
 ]
-worst = []
-
-
-def rows(case, what, e_tc, e_simt, e_f32, cond):
-    dec = np.ceil(np.log10(np.maximum(cond, 1.0))).astype(int)
-    for d in sorted(set(dec.tolist())):
-        m = dec == d
-        out.append(f"| {case} | {what} | <1e{d} | {int(m.sum())} | {np.median(e_tc[m]):.1e} | {e_tc[m].max():.1e} | {np.median(e_simt[m]):.1e} | "
-                   f"{e_simt[m].max():.1e} | {np.median(e_f32[m]):.1e} | {e_f32[m].max():.1e} |")
+verdict = []
 
 
 def run(case, phys, d, p32, p64, R, r, eng):
     ref = om.forward_laplacian(p64, d, r.double(), R.double(), phys.Z)
-    f32 = om.forward_laplacian(p32, d, r, R, phys.Z)
+    env = parity_rule.fp32_envelope(om, p32, d, r, R, phys.Z, ref)
+    one = parity_rule.errors(om.forward_laplacian(p32, d, r, R, phys.Z), ref)
     cond = ref["cond"].numpy()
     res = {}
     for tag, gp, simt in (("tc", 1, False), ("simt", 0, True)):
         eng.set_gemm_path(gp)
         eng.set_det_path(simt=simt)
-        e = eng.local_energy(r.cuda()).double().cpu()
-        lp = eng.log_psi_sqr(r.cuda())[1].double().cpu()
-        res[tag] = (((lp - ref["logpsi2"]).abs() / ref["logpsi2"].abs()).numpy(), ((e - ref["E_loc"]).abs() / ref["E_loc"].abs().clamp_min(1.0)).numpy())
-    fl = (((f32["logpsi2"].double() - ref["logpsi2"]).abs() / ref["logpsi2"].abs()).numpy(),
-          ((f32["E_loc"].double() - ref["E_loc"]).abs() / ref["E_loc"].abs().clamp_min(1.0)).numpy())
-    rows(case, "log psi^2", res["tc"][0], res["simt"][0], fl[0], cond)
-    rows(case, "E_loc", res["tc"][1], res["simt"][1], fl[1], cond)
-    for k, tol in ((0, 1e-5), (1, 1e-4)):
-        b = parity_rule.bounds(fl[k], cond, tol)
-        worst.append((case, "log psi^2" if k == 0 else "E_loc", float((res["tc"][k] / b).max()), float((res["simt"][k] / b).max()),
-                      float(np.quantile(res["tc"][k], 0.99)), float(np.quantile(fl[k], 0.99))))
+        e = eng.local_energy(r.cuda())
+        lp = eng.log_psi_sqr(r.cuda())[1]
+        res[tag] = parity_rule.errors(dict(logpsi2=lp, E_loc=e), ref)
+    for q, label, tol in (("logpsi2", "log psi^2", 1e-5), ("E_loc", "E_loc", 1e-4)):
+        out.extend(parity_rule.table_rows(case, label, cond, [res["tc"][q], res["simt"][q], one[q], env[q]]))
+        row = [case, label]
+        for tag in ("tc", "simt"):
+            try:
+                n = parity_rule.check(res[tag][q], env[q], tol, cond=ref["cond"] if q == "logpsi2" else None)
+                row.append(f"pass ({n} at plain tol)")
+            except AssertionError as ex:
+                row.append("FAIL " + str(ex)[:160].replace("|", "/"))
+            hard = np.maximum(tol, parity_rule.HARD_FACTOR * env[q])
+            row.append(f"{(res[tag][q] / hard).max():.2f} / {max(np.quantile(res[tag][q], x) / max(tol, parity_rule.FLOOR_FACTOR * np.quantile(env[q], x)) for x in parity_rule.QUANTILES):.2f}")
+        row += [f"{np.quantile(res['tc'][q], 0.99):.1e}", f"{np.quantile(env[q], 0.99):.1e}"]
+        verdict.append(row)
 
 
 for name, B in (("LiH", 96), ("N2", 96), ("HChain10", 24), ("Allene_TinyMol", 12), ("Benzene", 6)):
     phys, d, p32, p64, R, r, eng = make(name, B)
     run(f"{name}, {B} Gaussian walkers", phys, d, p32, p64, R, r, eng)
+    del eng
 
 # |psi|^2-distributed walkers (1000 Metropolis steps)
 import deeperwin_b200 as dpe
@@ -69,9 +70,10 @@ for name, B in (("N2", 128), ("LiH", 128)):
     f.engine.set_params(params); f.engine.set_geometry(st.R, st.Z)
     run(f"{name}, {B} walkers after 1000 Metropolis steps", phys, d, p32, om.cast_params(p32, torch.float64), st.R.cpu(), st.r.cpu(), f.engine)
 
-out += ["", "## Worst ratio error / parity-rule bound (must be <= 1) and 99th percentiles", "",
-        "| case | quantity | tc max(err/bound) | simt max(err/bound) | tc p99 | fp32 cpu p99 |", "|---|---|---:|---:|---:|---:|"]
-out += [f"| {c} | {w} | {a:.2f} | {b:.2f} | {p:.1e} | {q:.1e} |" for c, w, a, b, p, q in worst]
+out += ["", "## Parity rule per case (oracle/parity_rule.py) and 99th percentiles", "",
+        "Ratios (must be <= 1): worst walker err / max(tol, 16 x its floor)  /  worst of the q = 0.5, 0.9, 0.99 quantile ratios err_q / max(tol, 2 x floor_q).", "",
+        "| case | quantity | tc rule | tc ratios | simt rule | simt ratios | tc p99 | floor p99 |", "|---|---|---|---:|---|---:|---:|---:|"]
+out += ["| " + " | ".join(r) + " |" for r in verdict]
 text = "\n".join(out) + "\n"
 print(text)
 if len(sys.argv) > 1:
