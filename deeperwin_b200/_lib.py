@@ -22,6 +22,12 @@ class DpeMcmcConfig(C.Structure):
                 ("min_stepsize_scale", C.c_float), ("max_stepsize_scale", C.c_float), ("proposal", C.c_int32)]
 
 
+class DpeXlaDescriptor(C.Structure):
+    """include/dpe_b200.h dpe_xla_descriptor: the `opaque` of the XLA custom calls."""
+    _fields_ = [("model", C.c_uint64), ("workspace_bytes", C.c_uint64), ("n_walkers", C.c_int32), ("n_steps", C.c_int32),
+                ("recompute_log_psi", C.c_int32), ("run_controller", C.c_int32), ("mcmc", DpeMcmcConfig)]
+
+
 class DpeMcmcState(C.Structure):
     _fields_ = [("r_dev", C.c_void_p), ("log_psi_sqr_dev", C.c_void_p), ("walker_age_dev", C.c_void_p),
                 ("rng_state_dev", C.c_void_p), ("stepsize_dev", C.c_void_p), ("step_nr_dev", C.c_void_p),
@@ -52,6 +58,10 @@ SIGNATURES = {
     "dpe_energy_moments2": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
     "dpe_energy_median": (C.c_int, [_P, C.c_int32, _P, _P]),
     "dpe_energy_width": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P]),
+    "dpe_xla_log_psi_sqr": (None, [_P, C.POINTER(_P), C.c_char_p, C.c_size_t]),
+    "dpe_xla_local_energy": (None, [_P, C.POINTER(_P), C.c_char_p, C.c_size_t]),
+    "dpe_xla_mcmc_steps": (None, [_P, C.POINTER(_P), C.c_char_p, C.c_size_t]),
+    "dpe_xla_last_status": (C.c_int, []),
     "dpe_threefry_mcmc_randoms": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "dpe_threefry_bits": (C.c_int, [C.POINTER(C.c_uint32), C.c_int32, _P, _P]),
     "dpe_threefry_normal": (C.c_int, [C.POINTER(C.c_uint32), C.c_int32, _P, _P]),

@@ -174,6 +174,31 @@ int dpe_energy_moments2(const float *e_loc_dev, const float *e_clipped_dev, int3
 int dpe_energy_median(const float *e_dev, int32_t n, float *out_dev, void *stream);
 int dpe_energy_width(const float *e_dev, int32_t n, const float *center_dev, int32_t metric, float *out_dev, void *stream);
 
+/* ---- XLA custom-call entry points (keeping JAX as the host) ------------------------------------------
+ * Legacy GPU custom-call ABI of the reference's pinned jaxlib (jax 0.4.23): void fn(cudaStream_t, void **buffers, const char
+ * *opaque, size_t opaque_len) with `buffers` = operands then results (device pointers).  They replace the three switch points
+ * of the reference: log_psi_sqr (model/wavefunction.py:293), get_local_energy (hamiltonian.py:280-289) and the pmapped
+ * _run_mcmc_steps (mcmc.py:325-327, 389-406).  `opaque` is one dpe_xla_descriptor, serialised by the Python binding.
+ *   dpe_xla_log_psi_sqr : operands r, workspace                      results phase, log_psi_sqr
+ *   dpe_xla_local_energy: operands r, workspace                      results e_loc
+ *   dpe_xla_mcmc_steps  : operands r, log_psi_sqr, walker_age, rng_state, stepsize, step_nr, acc_rate, workspace
+ *                         results  the same seven MCMCState fields after n_steps, accept_counts[n_steps]
+ * The legacy ABI has no return value: a failure fills the results with NaN and is latched; dpe_xla_last_status() returns and
+ * clears it (0 if every custom call since the last query succeeded), dpe_last_error() holds the message. */
+typedef struct dpe_xla_descriptor {
+    uint64_t model;            /* dpe_model* of dpe_model_create, as an integer */
+    uint64_t workspace_bytes;  /* size of the workspace operand */
+    int32_t n_walkers;
+    int32_t n_steps;           /* mcmc_steps only */
+    int32_t recompute_log_psi; /* mcmc_steps only: mcmc.py:396 */
+    int32_t run_controller;    /* mcmc_steps only: 1 on a single device, 0 when the caller psum-s accept_counts first */
+    dpe_mcmc_config mcmc;      /* mcmc_steps only */
+} dpe_xla_descriptor;
+void dpe_xla_log_psi_sqr(void *stream, void **buffers, const char *opaque, size_t opaque_len);
+void dpe_xla_local_energy(void *stream, void **buffers, const char *opaque, size_t opaque_len);
+void dpe_xla_mcmc_steps(void *stream, void **buffers, const char *opaque, size_t opaque_len);
+int dpe_xla_last_status(void);
+
 /* ---- test hooks (jax.random restated; oracle/threefry.py) ------------------------------------ */
 /* keys[B,2] -> new_keys[B,2], noise[B,n,3]=normal(sub,[n,3]), thr[B]=uniform(sub,()), as one Metropolis
  * step consumes them (mcmc.py:178-179, 360-361). */

@@ -14,6 +14,7 @@ its worst walker).
 
 Rule (`check`), each clause can fail:
   Q  distribution: for q in 0.5, 0.9, 0.99:  quantile_q(err) <= max(tol, FLOOR_FACTOR x quantile_q(floor))      FLOOR_FACTOR = 2
+     (a quantile is judged when at least one walker lies above it: q = 0.99 needs 100 walkers, q = 0.9 ten)
      -- the batch as a whole is at most 2x the fp32 floor, and its median meets the stated tolerance whenever fp32 does
   A  every walker:  err <= max(tol, HARD_FACTOR x floor of that walker)                                        HARD_FACTOR = 16
      (so a walker whose fp32 floor is below tol / 16 must meet the stated tolerance outright).  The per-walker factor is wide
@@ -46,7 +47,7 @@ def errors(out, ref):
     e = {"logpsi2": _np(out["logpsi2"]) - _np(ref["logpsi2"]), "E_loc": _np(out["E_loc"]) - _np(ref["E_loc"])}
     res = {"logpsi2": np.abs(e["logpsi2"]) / np.abs(_np(ref["logpsi2"])),
            "E_loc": np.abs(e["E_loc"]) / np.maximum(np.abs(_np(ref["E_loc"])), 1.0)}
-    if out.get("grad") is not None:
+    if out.get("grad") is not None and ref.get("grad") is not None:
         g, gr = _np(out["grad"]), _np(ref["grad"])
         res["grad"] = np.abs(g - gr).max(-1) / np.abs(gr).max(-1)
     return res
@@ -82,6 +83,8 @@ def check(err, floor, tol, what="", cond=None):
         return ", ".join(f"walker {i}: err {err[i]:.2e} (fp32 floor {floor[i]:.2e}" + (f", cond {_np(cond)[i]:.1e})" if cond is not None else ")") for i in idx[:6])
 
     for q in QUANTILES:
+        if len(err) * (1.0 - q) < 1.0:          # too few walkers for this quantile to be more than the single worst walker (clause A)
+            continue
         eq, fq = np.quantile(err, q), np.quantile(floor, q)
         if not eq <= max(tol, FLOOR_FACTOR * fq):
             msgs.append(f"Q: quantile {q:g} of the error {eq:.2e} > max(tol, {FLOOR_FACTOR:g} x {fq:.2e})")
