@@ -203,7 +203,11 @@ class Workload:
         if args.gemm_path >= 0:
             self.engine.set_gemm_path(args.gemm_path)
         self.get_local_energy = dpe.build_local_energy(self.log_psi_sqr, forward_lap=True)
-        self.total_energy = dpe.build_total_energy(self.get_local_energy, cfg.optimization.clipping)
+        # N > 1: the E statistics and their two scalar NCCL all-reduces run on a side stream (they are rendezvous points of all ranks;
+        # the next Metropolis step proceeds underneath), and the accept counts are all-reduced only where the step-size controller
+        # needs them (every stepsize_update_interval steps, mcmc.plan_segments) instead of after every step
+        self.stats_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+        self.total_energy = dpe.build_total_energy(self.get_local_energy, cfg.optimization.clipping, stats_stream=self.stats_stream)
         # synthetic walkers: r0 = R[el_ion_mapping] + N(0,1) (mcmc.py:64-67), threefry seed 1234, then burn-in
         full = dpe.MCMCState.initialize_around_nuclei(walkers * world, phys, "gaussian", "el_ion_mapping", dpe.PRNGKey(1234), device=dev)
         state = full.split_across_devices()
@@ -220,18 +224,37 @@ class Workload:
         self.st = DpeMcmcState(self.r.data_ptr(), self.lp.data_ptr(), self.age.data_ptr(), self.keys.data_ptr(), self.ss.data_ptr(),
                                self.sn.data_ptr(), self.ar.data_ptr())
         self.counts = torch.zeros(32, dtype=torch.int32, device=dev)
+        self.pending = torch.zeros(4096, dtype=torch.int32, device=dev)      # accept counts not yet seen by the controller (N > 1)
+        self.n_pending = 0
+        self.step_host = int(self.sn.item())
         self.R_, self.Z_ = state.R[0], state.Z[0]
         self.aux = None
         torch.cuda.synchronize()
 
+    def flush_counts(self):
+        """All-reduces the accept counts gathered since the last step-size boundary and replays the controller over them
+        (mcmc.py:367-377 from integer counts: the same acc_rate EMA and step size as a per-step pmean)."""
+        import torch.distributed as dist
+        if self.n_pending:
+            seg = self.pending[:self.n_pending]
+            dist.all_reduce(seg)
+            self.engine.mcmc_controller(self.st, seg, self.n_pending, self.B * self.world, self.mc._cfg)
+            self.n_pending = 0
+
     def device_step(self, n_mcmc=1):
         """n_mcmc Metropolis steps + one forward-Laplacian E_loc + statistics, state resident in HBM."""
-        import torch.distributed as dist
-        counts = self.counts[:n_mcmc]
-        self.engine.mcmc_steps(self.st, self.B, n_mcmc, self.mc._cfg, False, self.world == 1, counts)
-        if self.world > 1:
-            dist.all_reduce(counts)
-            self.engine.mcmc_controller(self.st, counts, n_mcmc, self.B * self.world, self.mc._cfg)
+        if self.world == 1:
+            self.engine.mcmc_steps(self.st, self.B, n_mcmc, self.mc._cfg, False, True, self.counts[:n_mcmc])
+        else:
+            from deeperwin_b200.mcmc import plan_segments
+            for seg in plan_segments(self.step_host, n_mcmc, self.mc._cfg.stepsize_update_interval):
+                if self.n_pending + seg > self.pending.numel():
+                    self.flush_counts()
+                self.engine.mcmc_steps(self.st, self.B, seg, self.mc._cfg, False, False, self.pending[self.n_pending:self.n_pending + seg])
+                self.n_pending += seg
+                self.step_host += seg
+                if self.step_host % self.mc._cfg.stepsize_update_interval == 0:
+                    self.flush_counts()
         loss, (self.clip_state, self.aux) = self.total_energy(self.params, self.clip_state, self.spin, (self.r, self.R_, self.Z_, self.fixed))
         return loss
 
@@ -262,6 +285,9 @@ class Workload:
             flush.zero_()                                   # L2 flush between timed iterations (not timed)
             ev[k][0].record()
             self.device_step(n_mcmc)
+            if k == steps - 1 and self.world > 1:
+                self.flush_counts()                                  # nothing is left outside the timed region
+                torch.cuda.current_stream().wait_stream(self.stats_stream)
             ev[k][1].record()
         torch.cuda.synchronize()
         if self.world > 1:
@@ -301,7 +327,8 @@ class Workload:
                 "algorithmic_flops_per_launch": prof["flops"] / max(prof["count"], 1),
                 "frac_of_fp32_simt_peak": ach / fp32_peak, "fp32_simt_peak": fp32_peak,
                 "share_of_eloc_time": prof["class_ms"] / prof["total_ms"],
-                "eloc_pass_ms": prof["total_ms"],
+                "eloc_pass_ms": prof["total_ms"], "eloc_stages_ms": prof.get("stages_ms"),
+                "forward_stages_ms": {k: round(v[0], 4) for k, v in engine.profile_stages(lambda: engine.log_psi_sqr(self.r)).items()},
                 "eloc_pass_frac": None if flop_eval is None else B * flop_eval / (prof["total_ms"] * 1e-3) / 1e12 / tensor_peak}
 
 

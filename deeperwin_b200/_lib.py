@@ -8,6 +8,8 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libdpe_b200.so"
 DPE_MAX_ITER = 8
 MODE_FORWARD, MODE_LAPLACIAN = 0, 1
+STAGE_NAMES = ("features", "el_ion_stream", "pair_stream", "h_map", "schnet_conv", "spin_mean", "mean_term_gemm", "main_layer",
+               "orbitals", "det_factor", "det_trace", "combine", "mcmc")
 
 
 class DpeDims(C.Structure):
@@ -74,6 +76,7 @@ SIGNATURES = {
     "dpe_profile_enable": (C.c_int, [_P, C.c_int32]),
     "dpe_profile_collect": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "dpe_profile_launches": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_int32)]),
+    "dpe_profile_stages": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "dpe_launch_count": (C.c_int64, [_P]),
 }
 

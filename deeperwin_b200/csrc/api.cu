@@ -222,6 +222,7 @@ static int gemm(dpe_model *m, const GemmArgs &g, cudaStream_t s, bool *fused = n
     int e = gemm_dispatch(m, g, s, fused);
     DPE_CUDA(cudaEventRecord(rec.e1, s));
     rec.klass = m->last_gemm_class;
+    rec.stage = -1;
     rec.flops = 2.0 * (double)g.M * (double)g.N * (double)g.K;
     m->prof->push_back(rec);
     return e;
@@ -255,22 +256,29 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
     const int ldx = L.ldx;
     const int rows = Bc * N * C;
     int e;
-    if ((e = launch_features(m, r, Bc, C, x[0], ldx, C > 1 ? epot : nullptr, s))) return e;
-    if ((e = launch_eion_stream(m, r, Bc, CE, ei, ei_off, s))) return e;
-    if ((e = launch_pair_stream(m, r, Bc, C > 1 ? 3 : 1, pw, pw_off, s))) return e;
+    { StageTimer t(m, ST_FEATURES, s); if ((e = launch_features(m, r, Bc, C, x[0], ldx, C > 1 ? epot : nullptr, s))) return e; }
+    { StageTimer t(m, ST_EION, s); if ((e = launch_eion_stream(m, r, Bc, CE, ei, ei_off, s))) return e; }
+    { StageTimer t(m, ST_PAIR, s); if ((e = launch_pair_stream(m, r, Bc, C > 1 ? 3 : 1, pw, pw_off, s))) return e; }
     int cur = 0;
     for (int it = 0; it < d.n_iterations; ++it) {
         const IterParams &p = m->it[it];
         // h_map: [rows, d_in] x [d_in, emb] -> hm, tanh rule
-        if ((e = gemm(m, plain_gemm(x[cur], ldx, p.h_map.w, d.emb_dim, hm, d.emb_dim, rows, d.emb_dim, p.d_in), s, nullptr, 0))) return e;
-        if ((e = launch_act(m, hm, d.emb_dim, Bc * N, C, d.emb_dim, p.h_map.b, nullptr, 1, s))) return e;
+        {
+            StageTimer t(m, ST_HMAP, s);
+            if ((e = gemm(m, plain_gemm(x[cur], ldx, p.h_map.w, d.emb_dim, hm, d.emb_dim, rows, d.emb_dim, p.d_in), s, nullptr, 0))) return e;
+            if ((e = launch_act(m, hm, d.emb_dim, Bc * N, C, d.emb_dim, p.h_map.b, nullptr, 1, s))) return e;
+        }
         // SchNet convolutions fill columns [d_in, k_main)
-        if ((e = launch_conv(m, it, r, Bc, C, hm, pw + pw_off[it], ei + ei_off[it], x[cur], ldx, s))) return e;
+        { StageTimer t(m, ST_CONV, s); if ((e = launch_conv(m, it, r, Bc, C, hm, pw + pw_off[it], ei + ei_off[it], x[cur], ldx, s))) return e; }
         // spin means and their contribution (shared by all electrons of a walker)
-        if ((e = launch_mean(m, x[cur], ldx, Bc, C, p.d_in, mean, s))) return e;
-        if ((e = gemm(m, plain_gemm(mean, 2 * p.d_in, p.w_mean, p.d_out, add, p.d_out, Bc * C, p.d_out, 2 * p.d_in), s, nullptr, 1))) return e;
+        { StageTimer t(m, ST_MEAN, s); if ((e = launch_mean(m, x[cur], ldx, Bc, C, p.d_in, mean, s))) return e; }
+        {
+            StageTimer t(m, ST_MEAN_GEMM, s);
+            if ((e = gemm(m, plain_gemm(mean, 2 * p.d_in, p.w_mean, p.d_out, add, p.d_out, Bc * C, p.d_out, 2 * p.d_in), s, nullptr, 1))) return e;
+        }
         // main layer
         {
+            StageTimer t(m, ST_MAIN, s);
             // bias + spin-mean addend + tanh rule are applied in the epilogue of the CTA-pair tensor-core kernel, where the double
             // buffered accumulators let it run under the next tile's MMAs (gemm_tc.cu); every other kernel leaves `fused`
             // false and k_act does it as a separate HBM-bound pass.
@@ -284,6 +292,8 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
         cur ^= 1;
     }
     const int cols = d.n_dets * N, dl = d.n_hidden_one_el[d.n_iterations - 1];
+    {
+    StageTimer t_orb(m, ST_ORBITALS, s);
     if (d.use_taos) {
         // transferable atomic orbitals (transferable_atomic_orbitals.py:287-349): one GEMM against the cached backflow matrix
         // for all electrons (both spin types use slice 0, :255-260), then the exponential envelopes and the sum over ions
@@ -320,8 +330,9 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
     }
     if (!env_fused && (e = launch_envelope(m, r, Bc, C, mo, s))) return e;
     }
+    }
     if ((e = launch_det(m, Bc, C, mo, det, C > 1 ? (float *)(ws + L.ainv) : nullptr, s))) return e;
-    if ((e = launch_combine(m, Bc, C, det, epot, phase, logpsi2, grad, ekin, eloc, epot_out, s))) return e;
+    { StageTimer t(m, ST_COMBINE, s); if ((e = launch_combine(m, Bc, C, det, epot, phase, logpsi2, grad, ekin, eloc, epot_out, s))) return e; }
     return DPE_OK;
 }
 
@@ -661,6 +672,22 @@ int dpe_profile_launches(dpe_model *m, int32_t klass, double *ms_arr, double *fl
         ms_arr[*n] = t; flops_arr[*n] = r.flops; ++*n;
     }
     return DPE_OK;
+}
+
+int dpe_profile_stages(dpe_model *m, double *ms_arr, int64_t *count_arr, int32_t cap) {
+    if (!m || !ms_arr || !count_arr || cap < ST_COUNT) return set_error(DPE_ERR_ARG, "profile_stages: need room for %d stages", (int)ST_COUNT);
+    DPE_CUDA(cudaDeviceSynchronize());
+    for (int k = 0; k < cap; ++k) { ms_arr[k] = 0.0; count_arr[k] = 0; }
+    std::vector<dpe_model::ProfRec> keep;
+    for (auto &r : *m->prof) {
+        if (r.stage < 0) { keep.push_back(r); continue; }
+        float t = 0.f;
+        DPE_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms_arr[r.stage] += t; count_arr[r.stage] += 1;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    m->prof->swap(keep);
+    return ST_COUNT;
 }
 
 int64_t dpe_launch_count(const dpe_model *m) { return m ? m->launches : 0; }

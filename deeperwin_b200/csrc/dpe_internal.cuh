@@ -84,7 +84,7 @@ struct dpe_model {
     int gemm_path;
     int64_t launches;
     bool profile;
-    struct ProfRec { cudaEvent_t e0, e1; int klass; double flops; };
+    struct ProfRec { cudaEvent_t e0, e1; int klass; double flops; int stage; };
     std::vector<ProfRec> *prof;
     int last_gemm_class;
     void *tc;      // dpe::TcState (gemm_tc.cu): tf32-split transposed weights + their TMA descriptors
@@ -116,6 +116,22 @@ inline int opt_in_smem(dpe_model *m, int kid, F *fn) {
     m->smem_opted |= 1ull << kid;
     return DPE_OK;
 }
+
+// Stage timing (bench.py / tools): while dpe_profile_enable is on, every launch group of run_chunk is bracketed by CUDA events on the
+// launching stream.  Stage ids are the indices of DPE_STAGE_NAMES (include/dpe_b200.h).
+enum Stage { ST_FEATURES = 0, ST_EION, ST_PAIR, ST_HMAP, ST_CONV, ST_MEAN, ST_MEAN_GEMM, ST_MAIN, ST_ORBITALS, ST_DET_FACTOR, ST_DET_TRACE,
+             ST_COMBINE, ST_MCMC, ST_COUNT };
+struct StageTimer {
+    dpe_model *m; cudaStream_t s; dpe_model::ProfRec rec; bool on;
+    StageTimer(dpe_model *m_, int stage, cudaStream_t s_) : m(m_), s(s_), on(m_->profile) {
+        if (!on) return;
+        rec.klass = -1; rec.flops = 0.0; rec.stage = stage;
+        on = cudaEventCreate(&rec.e0) == cudaSuccess && cudaEventCreate(&rec.e1) == cudaSuccess && cudaEventRecord(rec.e0, s) == cudaSuccess;
+    }
+    ~StageTimer() {
+        if (on && cudaEventRecord(rec.e1, s) == cudaSuccess) m->prof->push_back(rec);
+    }
+};
 
 // gemm_simt.cu
 int launch_gemm_simt(dpe_model *m, const GemmArgs &g, cudaStream_t s);

@@ -631,6 +631,8 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *
     aug_bytes = (aug_bytes + 15) & ~(size_t)15;
     size_t smem = aug_bytes + ((lap ? (size_t)N * nq : 0) + 16) * sizeof(float) + 10 * sizeof(double);
     int blocks = Bc * d.n_dets;
+    {
+    StageTimer t_factor(m, ST_DET_FACTOR, s);
     if (N <= 16 && !force_generic) {
         const size_t per_warp = ((size_t)N * 32 + ((lap && !tc) ? ((size_t)N * 16 + 2 * ((size_t)N * 16 + 16) + 2 * 272 + 8) / 2 + 2 : 0)) * sizeof(double);
         const long n_mat = (long)blocks;
@@ -651,7 +653,9 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *
         else k_det<128, false><<<blocks, 128, smem, s>>>(N, C, d.n_dets, mo, det, nullptr, nullptr, NP);
     }
     DPE_LAUNCH_CHECK(m);
+    }
     if (tc) {
+        StageTimer t_trace(m, ST_DET_TRACE, s);
         int e = launch_det_trace_tc(m, Bc, C, mo, ah, al, NP, det, s);
         if (e == DPE_ERR_UNSUPPORTED) {      // shape outside the tensor-core kernel: redo the whole stage on CUDA cores
             if (N <= 16 && !force_generic) {

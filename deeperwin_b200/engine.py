@@ -259,6 +259,25 @@ class Engine:
     GEMM_CLASSES = {0: "k_gemm_simt<128,128,8,8>", 1: "k_gemm_simt<128,64,8,4>", 2: "k_gemm_simt<256,32,8,4>", 3: "k_gemm_tc_3xtf32",
                     4: "k_gemm_tc2_3xtf32"}
 
+    def profile_stages(self, fn):
+        """Runs fn() once with per-stage CUDA-event timing (dpe_profile_stages): {stage: (ms, timed launch groups)}."""
+        from ._lib import STAGE_NAMES
+        fn()
+        torch.cuda.synchronize(self.device)
+        check(self.lib.dpe_profile_enable(self.handle, 1), "dpe_profile_enable")
+        fn()
+        torch.cuda.synchronize(self.device)
+        check(self.lib.dpe_profile_enable(self.handle, 0), "dpe_profile_enable")
+        n = len(STAGE_NAMES)
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        rc = self.lib.dpe_profile_stages(self.handle, ms, cnt, n)
+        if rc < 0:
+            check(rc, "dpe_profile_stages")
+        for klass in self.GEMM_CLASSES:            # drop the per-GEMM records of the same pass
+            a, b, c = C.c_double(), C.c_int64(), C.c_double()
+            self.lib.dpe_profile_collect(self.handle, klass, C.byref(a), C.byref(b), C.byref(c))
+        return {STAGE_NAMES[i]: (ms[i], cnt[i]) for i in range(n) if cnt[i]}
+
     def profile_gemms(self, fn):
         """Runs fn() once with per-launch CUDA-event timing of the dense-layer GEMMs (bench.py roofline).
         Returns the kernel class with the largest summed time."""
@@ -273,6 +292,11 @@ class Engine:
         fn()
         torch.cuda.synchronize(self.device)
         check(self.lib.dpe_profile_enable(self.handle, 0), "dpe_profile_enable")
+        from ._lib import STAGE_NAMES
+        n_st = len(STAGE_NAMES)
+        st_ms, st_cnt = (C.c_double * n_st)(), (C.c_int64 * n_st)()
+        self.lib.dpe_profile_stages(self.handle, st_ms, st_cnt, n_st)
+        stages = {STAGE_NAMES[i]: round(st_ms[i], 4) for i in range(n_st) if st_cnt[i]}
         best = None
         launches = {}
         for klass, name in self.GEMM_CLASSES.items():
@@ -293,4 +317,5 @@ class Engine:
             fmax = max(f for _, f in per)
             top = [(t, f) for t, f in per if f >= 0.999 * fmax]
             best.update(ms=sum(t for t, _ in top), count=len(top), flops=sum(f for _, f in top))
+            best["stages_ms"] = stages
         return best

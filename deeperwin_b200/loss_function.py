@@ -18,10 +18,15 @@ def init_clipping_state(is_complex=False, device="cuda"):
     return torch.tensor(0.0, dtype=torch.float32, device=device), torch.tensor(1e12, dtype=torch.float32, device=device)
 
 
-def build_total_energy(get_local_energy, clipping_config: ClippingConfig):
+def build_total_energy(get_local_energy, clipping_config: ClippingConfig, stats_stream: "torch.cuda.Stream | None" = None):
     """Returns total_energy(params, clipping_state, spin_state, batch) -> (loss, (clipping_state, aux)) with the
     aux keys of loss_function.py:100-107.  All clipping variants of the reference: tanh / hard window (:44-59), centre
-    mean / median, width std / mae (:19-30), window from the previous step or from the current energies (:62-72)."""
+    mean / median, width std / mae (:19-30), window from the previous step or from the current energies (:62-72).
+
+    `stats_stream` (optional, multi-GPU): the reductions and their NCCL all-reduces are issued on that side stream, ordered after
+    the E_loc pass by an event.  The scalar all-reduces are device-side rendezvous points of all ranks; on the compute stream each
+    of them makes every GPU wait for the slowest one, on a side stream the next Metropolis steps run underneath.  The caller
+    synchronises `stats_stream` (or waits on it) before reading the returned scalars."""
     clip_mode = {"tanh": 0, "hard": 1}[clipping_config.name]
     lib = _lib.load()
     p = lambda t: C.c_void_p(t.data_ptr())
@@ -55,6 +60,16 @@ def build_total_energy(get_local_energy, clipping_config: ClippingConfig):
     def total_energy(params, state, spin_state, batch):
         r, R, Z, fixed_params = batch
         E_loc = get_local_energy(params, spin_state, r, R, Z, fixed_params).reshape(-1).contiguous()
+        if stats_stream is None:
+            return _statistics(E_loc, state)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(E_loc.device))
+        E_loc.record_stream(stats_stream)
+        with torch.cuda.stream(stats_stream):
+            stats_stream.wait_event(done)
+            return _statistics(E_loc, state)
+
+    def _statistics(E_loc, state):
         dev = E_loc.device
         n = E_loc.numel()
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)

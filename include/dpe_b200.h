@@ -234,6 +234,12 @@ int dpe_profile_enable(dpe_model *m, int32_t on);
 int dpe_profile_collect(dpe_model *m, int32_t klass, double *ms, int64_t *count, double *flops);
 /* Same, but per launch: fills ms_arr / flops_arr (capacity cap) in launch order and sets *n; does not clear the records. */
 int dpe_profile_launches(dpe_model *m, int32_t klass, double *ms_arr, double *flops_arr, int32_t cap, int32_t *n);
+/* While profiling is enabled every launch group of a pass is also timed per STAGE; dpe_profile_stages synchronises, fills
+ * ms_arr / count_arr (capacity cap >= the number of stages) with the summed device time and the number of timed groups per
+ * stage, clears those records and returns the number of stages (negative dpe_status on error).  Stage order: */
+#define DPE_STAGE_NAMES "features", "el_ion_stream", "pair_stream", "h_map", "schnet_conv", "spin_mean", "mean_term_gemm", "main_layer", \
+                        "orbitals", "det_factor", "det_trace", "combine", "mcmc"
+int dpe_profile_stages(dpe_model *m, double *ms_arr, int64_t *count_arr, int32_t cap);
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t dpe_launch_count(const dpe_model *m);
 

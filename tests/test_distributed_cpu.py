@@ -58,6 +58,39 @@ def _worker(rank, world, port, ret):
         c_ref = np.float32(np.mean([np.float32(np.median(c)) for c in clipped]))
         out["med_center_ref"] = float(c_ref)
         out["med_width_ref"] = float(3.0 * np.mean([np.mean(np.abs(c - c_ref)) for c in clipped]))
+        # deferred accept-count all-reduce (mcmc.plan_segments): each rank runs its shard of an oracle chain without a controller,
+        # the counts are all-reduced per segment and the scalar tail of make_mcmc_step (mcmc.py:367-377) is replayed from them;
+        # the result must equal the chain on the union of the walkers with the per-step pmean of the reference
+        from deeperwin_b200.mcmc import plan_segments
+        from oracle import threefry
+        Bt, Ne, n_steps, interval = 16, 2, 13, 4
+        keys = threefry.split(threefry.prng_key(5), Bt)
+        r0 = rng.normal(0, 1, (Bt, Ne, 3)).astype(np.float32)
+        func = lambda rr: (-2.0 * np.linalg.norm(rr, axis=-1).sum(-1)).astype(np.float32)          # log psi^2 of a product of 1s orbitals
+        mk = lambda sl: omc.OracleMCMCState(r=r0[sl].copy(), R=np.zeros((1, 3), np.float32), Z=np.array([2]), log_psi_sqr=func(r0[sl]),
+                                            walker_age=np.zeros(len(r0[sl]), np.int32), rng_state=keys[sl].copy(), stepsize=np.float32(0.5))
+        union = mk(slice(None))
+        for _ in range(n_steps):
+            union = omc.make_mcmc_step(func, union, max_age=3, stepsize_update_interval=interval)
+        shard = mk(slice(rank * 8, (rank + 1) * 8))
+        ss, ar, sn = np.float32(0.5), np.float32(0.0), 0
+        for seg in plan_segments(0, n_steps, interval):
+            counts = []
+            for _ in range(seg):
+                shard.stepsize = ss                                              # replicated scalar: changes only at segment boundaries
+                shard, mask = omc.make_mcmc_step(func, shard, max_age=3, stepsize_update_interval=10 ** 9, return_mask=True)
+                counts.append(int(mask.sum()))
+            tot = utils.psum(torch.tensor(counts, dtype=torch.int32)).numpy()
+            for c in tot:                                                        # dpe_mcmc_controller (csrc/mcmc.cu k_controller)
+                rate = np.float32(c) / np.float32(Bt)
+                sn += 1
+                ar_new = np.float32(np.float32(0.9) * ar + np.float32(0.1) * rate)
+                if sn % interval == 0:
+                    ss = np.float32(ss / np.float32(1.05)) if ar < np.float32(0.5) else np.float32(ss * np.float32(1.05))
+                    ss = np.float32(np.clip(ss, np.float32(0.01), np.float32(1.0)))
+                ar = ar_new
+        out["chain_r_equal"] = bool(np.array_equal(shard.r, union.r[rank * 8:(rank + 1) * 8]))
+        out["chain_scalars"] = (float(ss), float(ar), sn, float(union.stepsize), float(union.acc_rate), union.step_nr)
         ret[rank] = out
     finally:
         dist.destroy_process_group()
@@ -75,3 +108,6 @@ def test_gloo_world_size_2():
         assert o["flat"] == [[0.5] * 3, [1.0] * 4]
         assert abs(o["E_mean"] - o["E_ref_mean"]) < 1e-5 and abs(o["E_var"] - o["E_ref_var"]) < 1e-4
         assert abs(o["med_center"] - o["med_center_ref"]) < 1e-5 and abs(o["med_width"] - o["med_width_ref"]) < 1e-4
+        assert o["chain_r_equal"]
+        ss, ar, sn, uss, uar, usn = o["chain_scalars"]
+        assert ss == uss and sn == usn and abs(ar - uar) < 1e-7
