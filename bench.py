@@ -274,7 +274,12 @@ class Workload:
             a0.record(); self.device_step(n_mcmc); a1.record()
             torch.cuda.synchronize()
             extra.append(a0.elapsed_time(a1)); best = min(best, extra[-1])
-            if len(extra) >= 3 and all(t <= 1.03 * best for t in extra[-3:]):
+            settled = len(extra) >= 3 and all(t <= 1.03 * best for t in extra[-3:])
+            if self.world > 1:                      # every rank must run the same number of steps (the steps contain collectives)
+                flag = torch.tensor([0 if settled else 1], dtype=torch.int32, device=self.dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                settled = int(flag.item()) == 0
+            if settled:
                 break
         if self.world > 1:
             dist.barrier()

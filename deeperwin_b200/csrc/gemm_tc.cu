@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 #include "dpe_internal.cuh"
 #include "tc_common.cuh"
@@ -59,6 +60,8 @@ struct TcArgs {
     int tma_store;                                 // plain epilogue through shared-memory staging + TMA tensor stores
     int n_st;                                      // pipeline stages of the CTA-pair kernel
     float corr;                                    // accumulation-bias compensation factor, see tc_rz_compensation()
+    int seg_split;                                 // fused epilogues: channel segments per (walker, electron) group (work items per group)
+    int add_smem;                                  // epi 1: the addend rows of a tile are TMA-prefetched into shared memory (else read from global)
     long long *tl;                                 // debug timeline (DPE_GEMM_TIMELINE): [tile][4] clock64 stamps of CTA 0, or nullptr
 };
 
@@ -591,7 +594,7 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint64_t *bar_aempty = bar_afull + 2;           // [2] ... and has been consumed
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_aempty + 2);
     uint8_t *out_stage = smem + n_st * T2_STAGE_BYTES + 1024;                      // plain epilogue: TMA-store staging
-    float *addbuf = reinterpret_cast<float *>(smem + n_st * T2_STAGE_BYTES + 1024); // fused epilogue: [2 tiles][2 walkers][nch][128 features]
+    float *addbuf = reinterpret_cast<float *>(smem + n_st * T2_STAGE_BYTES + 1024); // fused epilogue: [2 tiles][2 walkers][nch][128 features] addend rows (add_smem), then the partial sums of the channel segments
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -627,7 +630,7 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 const int ft = (int)(t % a.n_ft);
                 const long rest = t / a.n_ft;
                 const int rt = (int)(rest % a.n_rt), seg = (int)(rest / a.n_rt);
-                if (FUSED && a.add) {
+                if (FUSED && a.add && a.add_smem) {
                     // addends of this tile: one box of nch rows x 128 features per walker the tile touches (at most two)
                     const int slot = tcount & 1, m0 = rt * a.tile_rows;
                     const int rows_valid = min(a.tile_rows, a.seg_len - m0);
@@ -724,14 +727,24 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         uint32_t tph0 = 0, tph1 = 0;
         int buf = 0, chunk = 0, tcount = 0;
         if constexpr (FUSED) {
-            // Fused dense-layer epilogue (mlp.py:45-69 under the forward Laplacian; what k_act does in a separate pass):
-            //   z = x W + bias + addend;  y = tanh(z_0), t_k = (1 - y^2) z_k, lap = (1 - y^2) z_lap - 2 y (1 - y^2) sum_k z_k^2.
-            // With the accumulators double buffered it runs under the next tile's MMAs.  One thread = one output feature and one
-            // (walker, electron) group of nch rows at a time: the tanh state of a group lives in registers.  The walk over a
-            // group is a dependent chain (~180 clocks per row for a lone warp), so each TMEM lane quarter gets four warps that
-            // take the groups of a tile round robin; results go straight to global memory (coalesced 128 B per warp and row).
+            // Fused dense-layer epilogues (what k_act / k_envelope do in separate HBM passes); with the accumulators double buffered they
+            // run under the next tile's MMAs.
+            //   epi 1 (mlp.py:45-69 under the forward Laplacian):  z = x W + bias + addend;  y = tanh(z_0), t_k = (1 - y^2) z_k,
+            //          lap = (1 - y^2) z_lap - 2 y (1 - y^2) sum_k z_k^2
+            //   epi 2 (envelope_orbitals.py:96-127): mo = env (x) bf with the product rule
+            // One thread = one output feature.  The rows of a tile are whole (walker, electron) groups of nch channels; a WORK ITEM is one
+            // of a.seg_split channel segments of one group, and the four warps of a TMEM lane quarter take the items of a tile round
+            // robin (a walk over rows is a dependent chain of ~180 clocks per row for a lone warp).  Splitting groups into segments keeps
+            // all four warps busy when a tile holds few groups (benzene: 2 groups of 128 channels; N2: 5 groups of 44).  The only
+            // state that crosses segments is sum_k z_k^2 of epi 1: the segments park their partial sums in shared memory and, after a
+            // barrier of the quarter's four warps, the Laplacian rows are finished.  The spin-mean addend rows are read straight from
+            // global memory (L2-resident: one walker's block serves all its electrons), fetched a chunk ahead of the dependent chain.
             const int k4 = (warp - 6) >> 2;                            // which of the four warps of this lane quarter
             const bool has_add = a.add != nullptr;
+            const int S = a.seg_split, seg_ch = (a.nch + S - 1) / S;
+            const bool add_smem = has_add && a.add_smem;
+            float *ssq_s = addbuf + (a.add_smem ? (size_t)4 * a.nch * 128 : 0);      // [group][segment][128 features] partial sums (S > 1 only)
+            const long astride = add_smem ? 128 : a.N_out;
             for (long t = pair; t < n_tiles; t += n_pairs, ++tcount) {
                 const int ft = (int)(t % a.n_ft);
                 const long rest = t / a.n_ft;
@@ -741,35 +754,41 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 const int n_grp = (rows_valid + a.nch - 1) / a.nch;
                 const int f = ft * TC_FEAT + (int)rank * 128 + q * 32 + lane;
                 const bool f_ok = f < a.N_out;
+                const int fc = f_ok ? f : 0;                               // clamped feature for loads that every lane issues
                 const float act_b = (f_ok && a.bias) ? a.bias[f] : 0.f;
                 float *cbase = a.C + ((long)seg * a.c_seg_stride + a.c_seg_off + m0) * a.ldc + a.c_col_off + f;
                 const long agrp = ((long)seg * a.seg_len + m0) / a.nch;    // global (walker, electron) group of column 0
                 const int e0 = (int)(agrp % a.gpa);                        // its electron index within the walker
                 const int slot = tcount & 1;
-                if (a.add) mbar_wait(&bar_afull[slot], ((uint32_t)tcount >> 1) & 1u);
+                if (add_smem) mbar_wait(&bar_afull[slot], ((uint32_t)tcount >> 1) & 1u);
                 mbar_wait(&bar_tfull[buf], buf ? tph1 : tph0);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
-                for (int gi = k4; gi < n_grp; gi += 4) {
-                    // the 16-column TMEM loads start at the group's first row, so the channel of register j of chunk c is 16 c + j:
-                    // the value column is (0, 0), everything else is a tangent except channel nch - 1 (the Laplacian)
+                const int n_items = n_grp * S;
+                auto addend_rows = [&](int gi) -> const float * {
+                    if (!has_add) return nullptr;
+                    if (add_smem) return addbuf + ((size_t)(slot * 2 + (e0 + gi) / a.gpa) * a.nch) * 128 + q * 32 + lane;
+                    return a.add + (((agrp + gi) / a.gpa) * a.nch) * (long)a.N_out + fc;
+                };
+                for (int item = k4; item < n_items; item += 4) {
+                    const int gi = item / S, sg = item - gi * S;
                     const int col0 = gi * a.nch;
                     const int n_valid = min(a.nch, rows_valid - col0);         // rows of this group inside the segment (all of them, normally)
+                    const int c_lo = sg * seg_ch, c_hi = min(n_valid, c_lo + seg_ch);
                     if (a.epi == 2) {
-                        // envelope multiply of the backflow GEMM (envelope_orbitals.py:96-127) with the product rule -- what k_envelope does
-                        // in a separate in-place pass.  env = sum_J w_J exp(-alpha_J |r_i - R_J|) for this (electron, orbital column); only
-                        // the electron's own three tangent channels and the Laplacian channel get extra terms.
+                        // env = sum_J w_J exp(-alpha_J |r_i - R_J|) for this (electron, orbital column); only the electron's own three tangent
+                        // channels and the Laplacian channel get extra terms
                         const int i = a.el_base + m0 / a.nch + gi;
                         const int ci = 1 + 3 * i;
                         float env = 0.f, e1x = 0.f, e1y = 0.f, e1z = 0.f, el = 0.f;
-                        if (f_ok) {
+                        {
                             const float *ri = a.r + ((long)seg * a.n_el + i) * 3;
                             const float rx = ri[0], ry = ri[1], rz = ri[2];
                             for (int J = 0; J < a.n_ion; ++J) {
                                 const float dx = rx - a.R[J * 3], dy = ry - a.R[J * 3 + 1], dz = rz - a.R[J * 3 + 2];
                                 const float d = sqrtf(dx * dx + dy * dy + dz * dz);
-                                const float al = a.spa[(long)J * a.N_out + f];
-                                const float e = __fmul_rn(a.envw[(long)J * a.N_out + f], expf(-al * d));
+                                const float al = a.spa[(long)J * a.N_out + fc];
+                                const float e = __fmul_rn(a.envw[(long)J * a.N_out + fc], expf(-al * d));
                                 env = __fadd_rn(env, e);
                                 if (a.nch > 1) {
                                     const float inv = 1.f / d, ge = -al * e * inv;
@@ -778,83 +797,144 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                                 }
                             }
                         }
-                        float bf0 = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
-                        float *crow = cbase + (long)col0 * a.ldc;
-                        for (int cc = 0; cc < a.nch; cc += 16) {
+                        // every row is val * env; the electron's own three tangent rows and the Laplacian row get their product-rule terms in
+                        // a second, four-row patch, which keeps the walk over the rows free of per-row case distinctions
+                        float *crow = cbase + (long)(col0 + c_lo) * a.ldc;
+                        int cc = c_lo;
+                        for (; cc + 16 <= c_hi; cc += 16) {
                             uint32_t v[16];
                             tmem_ld16(taddr + col0 + cc, v);
                             tmem_ld_wait();
-                            if (cc == 0) bf0 = __fmul_rn(__uint_as_float(v[0]), a.corr);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                const int cch = cc + j;
-                                if (cch < n_valid) {
-                                    const float val = __fmul_rn(__uint_as_float(v[j]), a.corr);
-                                    float o = val * env;
-                                    if (a.nch > 1) {
-                                        if (cch == ci) { tx = val; o += e1x * bf0; }
-                                        else if (cch == ci + 1) { ty = val; o += e1y * bf0; }
-                                        else if (cch == ci + 2) { tz = val; o += e1z * bf0; }
-                                        else if (cch == a.nch - 1) o += el * bf0 + 2.f * (e1x * tx + e1y * ty + e1z * tz);
-                                    }
-                                    if (f_ok) *crow = o;
-                                }
+                                if (f_ok) *crow = __fmul_rn(__uint_as_float(v[j]), a.corr) * env;      // same roundings as plain store + k_envelope
                                 crow += a.ldc;
+                            }
+                        }
+                        if (cc < c_hi) {
+                            uint32_t v[16];
+                            tmem_ld16_clipped(taddr, col0 + cc, v);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (cc + j < c_hi && f_ok) *crow = __fmul_rn(__uint_as_float(v[j]), a.corr) * env;
+                                crow += a.ldc;
+                            }
+                        }
+                        if (a.nch > 1) {                                       // (TMEM loads are warp-wide: only the stores are predicated)
+                            const float bf0 = __fmul_rn(tmem_ld1(taddr + col0), a.corr);
+                            float t3[3] = {0.f, 0.f, 0.f};
+                            const float e1[3] = {e1x, e1y, e1z};
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                const int ch = ci + k;
+                                const bool mine = ch >= c_lo && ch < c_hi;
+                                if (mine || c_hi == a.nch) t3[k] = __fmul_rn(tmem_ld1(taddr + col0 + ch), a.corr);
+                                if (mine && f_ok) cbase[(long)(col0 + ch) * a.ldc] = t3[k] * env + e1[k] * bf0;
+                            }
+                            if (c_hi == a.nch) {
+                                const float vl = __fmul_rn(tmem_ld1(taddr + col0 + a.nch - 1), a.corr);
+                                if (f_ok) cbase[(long)(col0 + a.nch - 1) * a.ldc] = vl * env + (el * bf0 + 2.f * (e1x * t3[0] + e1y * t3[1] + e1z * t3[2]));
                             }
                         }
                         continue;
                     }
-                    const float *arow = addbuf + ((size_t)(slot * 2 + (e0 + gi) / a.gpa) * a.nch) * 128 + q * 32 + lane;
-                    float *crow = cbase + (long)col0 * a.ldc;
-                    float act_y = 0.f, act_d1 = 0.f, act_ssq = 0.f;
-                    for (int cc = 0; cc < a.nch; cc += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(taddr + col0 + cc, v);
-                        tmem_ld_wait();
-                        if (cc == 0) {
-                            const float z0 = (__fmul_rn(__uint_as_float(v[0]), a.corr) + act_b) + (has_add ? arow[0] : 0.f);   // k_act's order: bias, then addend
+                    // ---- epi 1: 16-column TMEM chunks aligned to the segment start; channel 0 is the value, nch - 1 the Laplacian.
+                    // The addends of a chunk are fetched into registers ahead of the dependent chain; the shared-memory variant has a
+                    // compile-time row stride (immediate offsets), the global one walks a pointer.
+                    auto run_item = [&](auto smem_tag) {
+                        constexpr bool SM = decltype(smem_tag)::value;
+                        const float *arow = addend_rows(gi);
+                        const long gstride = a.N_out;
+                        float act_y = 0.f, act_d1 = 0.f, act_ssq = 0.f;
+                        if (sg > 0) {                                           // later segments fetch the value column themselves
+                            const float z0 = (__fmul_rn(tmem_ld1(taddr + col0), a.corr) + act_b) + (has_add ? arow[0] : 0.f);
                             act_y = tanhf(z0);
                             act_d1 = 1.f - act_y * act_y;
                         }
-                        if (cc + 16 < a.nch && cc + 16 <= n_valid && has_add && f_ok) {
-                            // interior chunk: 16 tangent channels (or the value + 15 tangents), no bounds, no Laplacian column
-                            {
-                                const float z = __fmul_rn(__uint_as_float(v[0]), a.corr) + arow[0];
-                                float o = act_d1 * z;
-                                if (cc == 0) o = act_y; else act_ssq = fmaf(z, z, act_ssq);
-                                *crow = o;
-                                crow += a.ldc;
-                            }
+                        float *crow = cbase + (long)(col0 + c_lo) * a.ldc;
+                        if (has_add) arow += SM ? (long)c_lo * 128 : (long)c_lo * gstride;
+                        for (int cc = c_lo; cc < c_hi; cc += 16) {
+                            uint32_t v[16];
+                            const bool full = cc + 16 <= c_hi;
+                            if (full) tmem_ld16(taddr + col0 + cc, v);
+                            // addends: shared memory -> read in place (immediate offsets); global memory -> registers, ahead of the chain
+                            float adg[SM ? 1 : 16];
+                            if constexpr (!SM) {
 #pragma unroll
-                            for (int j = 1; j < 16; ++j) {
-                                const float z = __fmul_rn(__uint_as_float(v[j]), a.corr) + arow[j * 128];
-                                act_ssq = fmaf(z, z, act_ssq);
-                                *crow = act_d1 * z;
-                                crow += a.ldc;
+                                for (int j = 0; j < 16; ++j) adg[j] = (has_add && (full || cc + j < c_hi)) ? arow[j * gstride] : 0.f;
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const int cch = cc + j;
-                                if (cch < n_valid) {
-                                    const float z = __fmul_rn(__uint_as_float(v[j]), a.corr) + (has_add ? arow[j * 128] : 0.f);
+                            auto ad_at = [&](int j) -> float {
+                                if constexpr (SM) return arow[j * 128];
+                                else return adg[j];
+                            };
+#define ad_(j) ad_at(j)
+                            if (full) tmem_ld_wait();
+                            else tmem_ld16_clipped(taddr, col0 + cc, v);
+                            if (cc == 0) {
+                                const float z0 = (__fmul_rn(__uint_as_float(v[0]), a.corr) + act_b) + ad_(0);   // k_act's order: bias, then addend
+                                act_y = tanhf(z0);
+                                act_d1 = 1.f - act_y * act_y;
+                            }
+                            if (full && cc + 16 < a.nch && f_ok) {
+                                // interior chunk: 16 tangent channels (or the value + 15 tangents), no bounds, no Laplacian column
+                                {
+                                    const float z = __fmul_rn(__uint_as_float(v[0]), a.corr) + ad_(0);
                                     float o = act_d1 * z;
-                                    if (cch == a.nch - 1) o = o - 2.f * act_y * act_d1 * act_ssq;
-                                    else act_ssq = fmaf(z, z, act_ssq);
-                                    if (j == 0 && cc == 0) { o = act_y; act_ssq = 0.f; }
-                                    if (f_ok) *crow = o;
+                                    if (cc == 0) o = act_y; else act_ssq = fmaf(z, z, act_ssq);
+                                    *crow = o;
+                                    crow += a.ldc;
                                 }
-                                crow += a.ldc;
+#pragma unroll
+                                for (int j = 1; j < 16; ++j) {
+                                    const float z = __fmul_rn(__uint_as_float(v[j]), a.corr) + ad_(j);
+                                    act_ssq = fmaf(z, z, act_ssq);
+                                    *crow = act_d1 * z;
+                                    crow += a.ldc;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const int cch = cc + j;
+                                    if (cch < c_hi) {
+                                        const float z = __fmul_rn(__uint_as_float(v[j]), a.corr) + ad_(j);
+                                        float o = act_d1 * z;
+                                        bool store = f_ok;
+                                        if (cch == a.nch - 1) { o = o - 2.f * act_y * act_d1 * act_ssq; store = store && S == 1; }
+                                        else act_ssq = fmaf(z, z, act_ssq);
+                                        if (cch == 0) { o = act_y; act_ssq = 0.f; }
+                                        if (store) *crow = o;
+                                    }
+                                    crow += a.ldc;
+                                }
                             }
+                            if (has_add) arow += SM ? 16 * 128 : 16 * gstride;
+#undef ad_
                         }
-                        arow += 16 * 128;
+                        if (S > 1) ssq_s[(gi * S + sg) * 128 + q * 32 + lane] = act_ssq;
+                    };
+                    if (add_smem) run_item(std::true_type{}); else run_item(std::false_type{});
+                }
+                if (S > 1 && a.epi == 1) {
+                    // Laplacian rows: the partial sums of all segments of a group are complete after the quarter's barrier
+                    asm volatile("bar.sync %0, 128;" ::"r"(8 + q) : "memory");
+                    for (int gi = k4; gi < n_grp; gi += 4) {
+                        const int col0 = gi * a.nch;
+                        if (rows_valid - col0 < a.nch) continue;            // ragged last group of a segment: it has no Laplacian row here
+                        const float *arow = addend_rows(gi);
+                        const float z0 = (__fmul_rn(tmem_ld1(taddr + col0), a.corr) + act_b) + (has_add ? arow[0] : 0.f);
+                        const float y = tanhf(z0), d1 = 1.f - y * y;
+                        float ssq = 0.f;
+                        for (int sg = 0; sg < S; ++sg) ssq += ssq_s[(gi * S + sg) * 128 + q * 32 + lane];
+                        const float zl = __fmul_rn(tmem_ld1(taddr + col0 + a.nch - 1), a.corr) + (has_add ? arow[(long)(a.nch - 1) * astride] : 0.f);
+                        if (f_ok) cbase[(long)(col0 + a.nch - 1) * a.ldc] = d1 * zl - 2.f * y * d1 * ssq;
                     }
+                    asm volatile("bar.sync %0, 128;" ::"r"(8 + q) : "memory");      // the partial sums may be overwritten by the next tile
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive_cluster_relaxed(mapa_u32(&bar_tempty[buf], 0));      // this warp's share of the accumulator is drained
-                    if (a.add) mbar_arrive(&bar_aempty[slot]);
+                    if (add_smem) mbar_arrive(&bar_aempty[slot]);
                 }
                 if (buf) tph1 ^= 1; else tph0 ^= 1;
                 buf ^= 1;
@@ -1106,16 +1186,22 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     size_t smem2 = T2_SMEM_BYTES;
     a.n_st = T2_PLAIN_STAGES;
     CUtensorMap map_add = map_x;
-    if (pair_ok && a.epi == 1) {
-        // fused tanh-rule epilogue: addend tiles ([2 tiles][2 walkers][nch][128 features]) live in shared memory;
-        // a tile must not touch more than two walkers
+    a.seg_split = 1;
+    a.add_smem = 0;
+    if (pair_ok && a.epi) {
+        // fused epilogues: work items = channel segments of the (walker, electron) groups of a tile, four warps per TMEM lane quarter
         const int gpt = a.tile_rows / a.nch;
+        static const int seg_env = getenv("DPE_TC_SEG_SPLIT") ? atoi(getenv("DPE_TC_SEG_SPLIT")) : 0;
+        a.seg_split = seg_env > 0 ? seg_env : (gpt <= 1 ? 4 : (gpt <= 2 ? 2 : 1));
+        if (a.nch < 8 * a.seg_split) a.seg_split = 1;
+        if (a.nch < 8) pair_ok = false;             // forward-only passes (one channel per group): plain GEMM + the separate activation pass
+        size_t part_bytes = a.epi == 1 && a.seg_split > 1 ? (size_t)gpt * a.seg_split * 512 : 0;
+        // epi 1: the addend rows of a tile ([2 tiles][2 walkers][nch][128 features]) are TMA-prefetched into shared memory when a tile
+        // touches at most two walkers and four K-stages still fit next to them (loads from global memory inside the dependent
+        // epilogue chain cost the N2 layers 55 %); larger channel counts (3N + 2 > 48) read them from global memory
+        static const bool no_add_smem = getenv("DPE_TC_ADD_GLOBAL") != nullptr;
         const size_t add_bytes = (size_t)4 * a.nch * 512;
-        a.n_st = T2_STAGES;
-        while (a.n_st > 3 && (size_t)a.n_st * T2_STAGE_BYTES + 1024 + add_bytes + 1024 > 227 * 1024) --a.n_st;
-        smem2 = (size_t)a.n_st * T2_STAGE_BYTES + 1024 + add_bytes + 1024;
-        if (gpt > a.gpa || smem2 > 227 * 1024 || (g.N & 3) || use_pair < 2) pair_ok = false;
-        if (pair_ok && g.add) {
+        if (a.epi == 1 && g.add && !no_add_smem && gpt <= a.gpa && 4 * (size_t)T2_STAGE_BYTES + 1024 + add_bytes + part_bytes + 1024 <= 227 * 1024) {
             const long n_walkers = ((long)n_seg * seg_len / a.nch) / a.gpa;
             cuuint64_t adims[2] = {(cuuint64_t)g.N, (cuuint64_t)(n_walkers * a.nch)};
             cuuint64_t astr[1] = {(cuuint64_t)g.N * sizeof(float)};
@@ -1124,15 +1210,12 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
             CUresult ra = enc(&map_add, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(g.add), adims, astr, abox, aes,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (ra != CUDA_SUCCESS) pair_ok = false;
+            if (ra == CUDA_SUCCESS) { a.add_smem = 1; part_bytes += add_bytes; }
         }
-    }
-    if (pair_ok && a.epi == 2) {
         a.n_st = T2_STAGES;
-        smem2 = (size_t)a.n_st * T2_STAGE_BYTES + 1024 + 1024;
-        // each lane quarter has four epilogue warps that take one (walker, electron) group each: with fewer than four groups per
-        // tile (3N+2 > 64) half of them idle and the walk over 100+ rows outlasts the MMAs (benzene: 44 ms fused vs 25 ms unfused)
-        if (use_pair < 2 || a.tile_rows / a.nch < 4) pair_ok = false;
+        while (a.n_st > 3 && (size_t)a.n_st * T2_STAGE_BYTES + 1024 + part_bytes + 1024 > 227 * 1024) --a.n_st;
+        smem2 = (size_t)a.n_st * T2_STAGE_BYTES + 1024 + part_bytes + 1024;
+        if (smem2 > 227 * 1024 || (g.N & 3) || use_pair < 2) pair_ok = false;
     }
     // the fused epilogues are only worth running where they overlap the MMAs (double-buffered accumulators of the pair kernel)
     static const bool force_act = getenv("DPE_FUSE_ACT") != nullptr, force_env = getenv("DPE_FUSE_ENVELOPE") != nullptr;

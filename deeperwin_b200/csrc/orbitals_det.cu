@@ -615,6 +615,54 @@ __global__ void __launch_bounds__(128, (LAP && !FACTOR) ? 4 : 8) k_det_warp(int 
     }
 }
 
+// Forward-only determinants of small systems (N <= 16; the Metropolis step): the LU sweep needs N <= 16 columns, so a warp carries TWO
+// matrices, one per half-warp (columns 0-15 / 16-31 of the same [N][32] FP64 tile; all shuffles stay inside a half).  Same arithmetic
+// as k_det_warp<false>, twice the matrices per latency-bound sweep.
+__global__ void __launch_bounds__(128, 8) k_det_fwd_half(int N, int n_det, long n_mat, const float *__restrict__ mo, float *__restrict__ det) {
+    extern __shared__ double smd[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, half = lane >> 4, q = lane & 15;
+    const long bd = (blockIdx.x * 4L + wib) * 2 + half;
+    const bool valid = bd < n_mat;
+    double *aug = smd + (size_t)wib * N * 32 + half * 16;          // this half's columns: aug[i * 32 + q]
+    const long bb = valid ? bd : 0;
+    const long b = bb / n_det;
+    const int dt = (int)(bb - b * n_det);
+    const int cols = n_det * N;
+    const float *mob = mo + b * (long)N * cols + (long)dt * N;     // C = 1: element (i, o) = mob[i * cols + o]
+    for (int i = 0; i < N; ++i)
+        aug[i * 32 + q] = (q < N && valid) ? (double)mob[(long)i * cols + q] : (q == i ? 1.0 : 0.0);
+    __syncwarp();
+    double logdet = 0.0;
+    float sign = 1.f;
+    for (int p = 0; p < N; ++p) {
+        float best = (q >= p && q < N) ? fabsf((float)aug[q * 32 + p]) : -1.f;
+        int bi = q;
+        for (int o = 8; o; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (bi != p) {
+            double t = aug[p * 32 + q];
+            aug[p * 32 + q] = aug[bi * 32 + q];
+            aug[bi * 32 + q] = t;
+            sign = -sign;
+        }
+        __syncwarp();
+        const double piv = aug[p * 32 + p];
+        logdet += log(fabs(piv));
+        if (piv < 0.0) sign = -sign;
+        __syncwarp();
+        const double rowp = aug[p * 32 + q] / piv;
+        for (int i = p + 1; i < N; ++i) {
+            const double fct = aug[i * 32 + p];
+            if (q > p && q < N) aug[i * 32 + q] = fma(-fct, rowp, aug[i * 32 + q]);
+        }
+        __syncwarp();
+    }
+    if (q == 0 && valid) { det[bd * 2] = (float)logdet; det[bd * 2 + 1] = sign; }
+}
+
 int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *ainv, cudaStream_t s) {
     const dpe_dims &d = m->dims;
     const int N = d.n_el;
@@ -638,7 +686,11 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *
         const long n_mat = (long)blocks;
         if (lap && tc) k_det_warp<true, true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, ah, al, NP);
         else if (lap) k_det_warp<true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, ah, al, NP);
-        else k_det_warp<false><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, nullptr, nullptr, NP);
+        else {
+            static const bool one_per_warp = getenv("DPE_DET_FWD_SINGLE") != nullptr;      // debug: one matrix per warp
+            if (one_per_warp) k_det_warp<false><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, nullptr, nullptr, NP);
+            else k_det_fwd_half<<<(int)((n_mat + 7) / 8), 128, 4 * (size_t)N * 32 * sizeof(double), s>>>(N, d.n_dets, n_mat, mo, det);
+        }
     } else {
         // 64 threads: one 8 x 8 tile of P per thread (N <= 64 -> at most 64 tiles) and one column of mo per thread
         if (smem > DPE_SMEM_OPTIN) return set_error(DPE_ERR_UNSUPPORTED, "det: %zu bytes of shared memory", smem);

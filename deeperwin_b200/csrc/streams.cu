@@ -363,6 +363,132 @@ __global__ void __launch_bounds__(256) k_pair_stream(PairArgs a) {
     }
 }
 
+// Forward-only pair stream (the Metropolis step): one warp carries P unordered pairs of the SAME spin class through all iterations at
+// once, so every LDS.128 of layer weights feeds 4 P FMAs instead of 4 (the single-pair version is bound by those loads).
+template <int P>
+__device__ __forceinline__ void pair_dense_multi(const float *__restrict__ W4, int din, int dout, const float *__restrict__ xs, float (&z)[P], int lane) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) z[p] = 0.f;
+    const bool act = lane < dout;
+    if (din == 1) {
+        const float w = act ? W4[lane * 4] : 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) z[p] = xs[p * 32] * w;
+        return;
+    }
+    const int nk4 = din >> 2;
+    for (int k4 = 0; k4 < nk4; ++k4) {
+        const float4 w = act ? *reinterpret_cast<const float4 *>(W4 + (k4 * dout + lane) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float4 xv = *reinterpret_cast<const float4 *>(xs + p * 32 + k4 * 4);
+            z[p] = fmaf(xv.x, w.x, z[p]); z[p] = fmaf(xv.y, w.y, z[p]); z[p] = fmaf(xv.z, w.z, z[p]); z[p] = fmaf(xv.w, w.w, z[p]);
+        }
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(256) k_pair_stream_fwd(PairArgs a, int n_walkers) {
+    extern __shared__ __align__(16) float smem[];
+    int base[DPE_MAX_ITER], blk[DPE_MAX_ITER];
+    int off = 0;
+    for (int it = 0; it < a.n_iter; ++it) {
+        base[it] = off;
+        const int kp = a.dP[it] == 1 ? 4 : a.dP[it];
+        blk[it] = kp * a.emb + a.emb + ((it + 1 < a.n_iter) ? kp * a.dP[it + 1] + a.dP[it + 1] : 0);
+        off += 2 * blk[it];
+    }
+    float *xs_all = smem + off;                                        // [8 warps][P][32]
+    int *pair_tab = reinterpret_cast<int *>(xs_all + 8 * P * 32);      // same-spin pairs first, then different-spin pairs; (i << 8) | j
+    auto stage = [&](float *dst, const float *src, int din, int dout) {
+        const int kp = din == 1 ? 4 : din;
+        for (int t = threadIdx.x; t < kp * dout; t += blockDim.x) {
+            int k4 = t / (dout * 4), rem = t - k4 * dout * 4, n = rem >> 2, kk = rem & 3, k = k4 * 4 + kk;
+            dst[t] = k < din ? src[k * dout + n] : 0.f;
+        }
+    };
+    for (int it = 0; it < a.n_iter; ++it)
+        for (int sd = 0; sd < 2; ++sd) {
+            float *dst = smem + base[it] + sd * blk[it];
+            const int kp = a.dP[it] == 1 ? 4 : a.dP[it];
+            stage(dst, a.ww[it][sd], a.dP[it], a.emb);
+            for (int t = threadIdx.x; t < a.emb; t += blockDim.x) dst[kp * a.emb + t] = a.wb[it][sd][t];
+            if (it + 1 < a.n_iter) {
+                stage(dst + kp * a.emb + a.emb, a.hw[it][sd], a.dP[it], a.dP[it + 1]);
+                for (int t = threadIdx.x; t < a.dP[it + 1]; t += blockDim.x) dst[kp * a.emb + a.emb + kp * a.dP[it + 1] + t] = a.hb[it][sd][t];
+            }
+        }
+    const int N = a.N, U = a.U, D = N - U;
+    const int n_same = U * (U + 1) / 2 + D * (D + 1) / 2, n_diff = U * D;
+    if (threadIdx.x == 0) {                                             // tiny table, built by one thread
+        int ps = 0, pd = n_same;
+        for (int i = 0; i < N; ++i)
+            for (int j = i; j < N; ++j) {
+                if ((i < U) == (j < U)) pair_tab[ps++] = (i << 8) | j;
+                else pair_tab[pd++] = (i << 8) | j;
+            }
+    }
+    __syncthreads();
+    const int gs = (n_same + P - 1) / P, gd = (n_diff + P - 1) / P, n_groups = gs + gd;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float *xs = xs_all + wib * P * 32;
+    const long n_units = (long)n_walkers * n_groups;
+    for (long u = blockIdx.x * 8L + wib; u < n_units; u += gridDim.x * 8L) {
+        const long b = u / n_groups;
+        const int g = (int)(u - b * n_groups);
+        const int sd = g >= gs ? 1 : 0;
+        const int first = sd ? n_same + (g - gs) * P : g * P;
+        const int cnt = min(P, (sd ? n_same + n_diff : n_same) - first);
+        int pi[P], pj[P];
+        float x[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int pk = pair_tab[first + min(p, cnt - 1)];            // padding slots repeat the last pair and are not stored
+            pi[p] = pk >> 8; pj[p] = pk & 255;
+            const float *ri = a.r + (b * N + pi[p]) * 3, *rj = a.r + (b * N + pj[p]) * 3;
+            const float dx = rj[0] - ri[0], dy = rj[1] - ri[1], dz = rj[2] - ri[2];
+            const float d = (pi[p] == pj[p]) ? 0.f : sqrtf(dx * dx + dy * dy + dz * dz);
+            x[p] = lane == 0 ? d : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < DPE_MAX_ITER; ++it) {
+            if (it < a.n_iter) {
+                __syncwarp();
+#pragma unroll
+                for (int p = 0; p < P; ++p) xs[p * 32 + lane] = x[p];
+                __syncwarp();
+                const float *blkp = smem + base[it] + sd * blk[it];
+                const int kp = a.dP[it] == 1 ? 4 : a.dP[it];
+                float z[P];
+                pair_dense_multi<P>(blkp, a.dP[it], a.emb, xs, z, lane);
+                if (lane < a.emb) {
+                    const float bias = blkp[kp * a.emb + lane];
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        if (p < cnt) {
+                            const float w = tanh_f32(z[p] + bias);
+                            a.out[it][((b * N + pi[p]) * N + pj[p]) * (long)a.emb + lane] = w;
+                            if (pi[p] != pj[p]) a.out[it][((b * N + pj[p]) * N + pi[p]) * (long)a.emb + lane] = w;
+                        }
+                    }
+                }
+                if (it + 1 < a.n_iter) {
+                    const float *hwp = blkp + kp * a.emb + a.emb;
+                    const int dn = a.dP[it + 1];
+                    pair_dense_multi<P>(hwp, a.dP[it], dn, xs, z, lane);
+                    const float bias = lane < dn ? hwp[kp * dn + lane] : 0.f;
+                    const bool res = a.dP[it] == dn;
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const float y = lane < dn ? tanh_f32(z[p] + bias) : 0.f;
+                        x[p] = res ? (x[p] + y) * 0.70710678118654752f : y;
+                    }
+                }
+            }
+        }
+    }
+}
+
 int launch_pair_stream(dpe_model *m, const float *r, int Bc, int CP, float *pw_base, const size_t *pw_off, cudaStream_t s) {
     const dpe_dims &d = m->dims;
     PairArgs a;
@@ -386,8 +512,18 @@ int launch_pair_stream(dpe_model *m, const float *r, int Bc, int CP, float *pw_b
     long blocks = ((long)Bc * (d.n_el * (d.n_el + 1) / 2) + 7) / 8;
     if (blocks > 148 * 4) blocks = 148 * 4;
     int e;
-    if (CP == 1) {
-        if ((e = opt_in_smem(m, KID_PAIR1, k_pair_stream<1>))) return e;
+    static const bool single_pair_fwd = getenv("DPE_PAIR_FWD_SINGLE") != nullptr;     // debug: the one-pair-per-warp forward kernel
+    if (CP == 1 && !single_pair_fwd) {
+        constexpr int P = 4;
+        const int U = d.n_up, D = d.n_el - U;
+        const int n_groups = (U * (U + 1) / 2 + D * (D + 1) / 2 + P - 1) / P + (U * D + P - 1) / P;
+        size_t smem_f = (fl - (size_t)8 * CP * 32 + (size_t)8 * P * 32) * sizeof(float);
+        long blocks_f = ((long)Bc * n_groups + 7) / 8;
+        if (blocks_f > 148 * 4) blocks_f = 148 * 4;
+        if ((e = opt_in_smem(m, KID_PAIR1, k_pair_stream_fwd<P>))) return e;
+        k_pair_stream_fwd<P><<<(int)blocks_f, 256, smem_f, s>>>(a, Bc);
+    } else if (CP == 1) {
+        if ((e = opt_in_smem(m, KID_MCMC_FUSED, k_pair_stream<1>))) return e;
         k_pair_stream<1><<<(int)blocks, 256, smem, s>>>(a);
     } else {
         if ((e = opt_in_smem(m, KID_PAIR3, k_pair_stream<3>))) return e;
@@ -624,6 +760,123 @@ __global__ void __launch_bounds__(MAXT, MINB) k_conv_dense2(int N, int C, int CP
     }
 }
 
+// Third version: the sparse product-rule terms (what k_conv_special adds in a second read-modify-write pass) are folded into the dense
+// kernel, so conv_ee / conv_eI are written exactly once.  Block = (walker, 8 features), thread = (channel c, feature f) as in
+// k_conv_dense2.  A prologue run by the first N x 8 threads computes, per electron i and feature, the sums over j that only the
+// own-electron tangent channels and the Laplacian channel need,
+//     s_a[i]  = sum_{j != i} w'_ij u_ij,a hm0_j
+//     lap[i]  = sum_{j != i} (2 w''_ij + 4 w'_ij / d_ij) hm0_j + 2 w'_ij u_ij . (d hm_j / d r_j - d hm_j / d r_i)
+// from the hm slab that is resident in shared memory anyway; every other tangent channel (electron e != i, axis a) gets its single
+// term w'_ie u_ie,a hm0_e in the thread that owns the channel.  The thread also expands the 5-channel el-ion convolution into its
+// channel of conv_eI.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_conv_fused(int N, int C, int emb, int dE, const float *__restrict__ r, const float *__restrict__ hm,
+                                                     const float *__restrict__ pw, const float *__restrict__ ei, float *__restrict__ x, int ldx,
+                                                     int col_ee) {
+    extern __shared__ __align__(16) float sm[];
+    float *A_s = sm;                               // [j][f][NP]  (one block of <= 16 electrons i at a time)
+    float *B_s = A_s + N * CV_FG * CV2_NP;         // [j][c][f]
+    float *W1_s = B_s + N * C * CV_FG;             // [i][j][f]  w'
+    float *W2_s = W1_s + N * N * CV_FG;            // [i][j][f]  w''
+    float4 *U_s = reinterpret_cast<float4 *>(W2_s + N * N * CV_FG);    // [i][j] (u_x, u_y, u_z, 1/d) of r_j - r_i
+    float *S_s = reinterpret_cast<float *>(U_s + N * N);               // [i][a][f]
+    float *L_s = S_s + N * 3 * CV_FG;              // [i][f]
+    const int n_fg = emb / CV_FG;
+    const int fg = blockIdx.x % n_fg;
+    const long b = blockIdx.x / n_fg;
+    const int f0 = fg * CV_FG;
+    const int tid = threadIdx.x, f = tid & (CV_FG - 1), c = tid >> 3;       // blockDim.x = 8 * C
+    for (int j = 0; j < N; ++j)
+        B_s[(j * C + c) * CV_FG + f] = hm[((b * N + j) * (long)C + c) * emb + f0 + f];
+    for (int t = tid; t < N * N * CV_FG; t += blockDim.x) {              // f fastest: 8 threads share one 32-byte sector of pw
+        const int ff = t & (CV_FG - 1), ij = t >> 3;
+        const float *p1 = pw + (b * N * N + ij) * 3L * emb + emb + f0 + ff;
+        W1_s[t] = p1[0];
+        W2_s[t] = p1[emb];
+    }
+    for (int t = tid; t < N * N; t += blockDim.x) {
+        const int i = t / N, j = t - i * N;
+        const float *rb = r + b * N * 3;
+        const float dx = rb[3 * j] - rb[3 * i], dy = rb[3 * j + 1] - rb[3 * i + 1], dz = rb[3 * j + 2] - rb[3 * i + 2];
+        const float inv = i == j ? 0.f : 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+        U_s[t] = make_float4(dx * inv, dy * inv, dz * inv, inv);
+    }
+    __syncthreads();
+    if (tid < N * CV_FG) {                          // prologue: thread = (electron i, feature f)
+        const int i = tid >> 3;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, lap = 0.f;
+        for (int j = 0; j < N; ++j) {
+            const float4 u = U_s[i * N + j];         // all zero for j == i: every term below vanishes
+            const float w1 = W1_s[(i * N + j) * CV_FG + f], w2 = j == i ? 0.f : W2_s[(i * N + j) * CV_FG + f];
+            const float *hj = B_s + (j * C) * CV_FG + f;
+            const float h0 = hj[0];
+            const float *hjj = hj + (1 + 3 * j) * CV_FG, *hji = hj + (1 + 3 * i) * CV_FG;
+            const float cross = u.x * (hjj[0] - hji[0]) + u.y * (hjj[CV_FG] - hji[CV_FG]) + u.z * (hjj[2 * CV_FG] - hji[2 * CV_FG]);
+            const float t = w1 * h0;
+            s0 = fmaf(t, u.x, s0); s1 = fmaf(t, u.y, s1); s2 = fmaf(t, u.z, s2);
+            lap += (2.f * w2 + 4.f * w1 * u.w) * h0 + 2.f * w1 * cross;
+        }
+        S_s[(i * 3 + 0) * CV_FG + f] = s0; S_s[(i * 3 + 1) * CV_FG + f] = s1; S_s[(i * 3 + 2) * CV_FG + f] = s2;
+        L_s[i * CV_FG + f] = lap;
+    }
+    const bool tangent = c >= 1 && c < C - 1;
+    const int e = tangent ? (c - 1) / 3 : 0, ax = tangent ? (c - 1) - 3 * e : 0;
+    const float h0e = B_s[(e * C) * CV_FG + f];
+    for (int i0 = 0; i0 < N; i0 += 16) {
+        const int ni = min(16, N - i0);
+        __syncthreads();                           // previous i block consumed; first time: prologue tables complete
+        for (int t = tid; t < N * CV2_NP * CV_FG; t += blockDim.x) {      // ff fastest: 8 threads share one 32-byte sector of pw
+            const int ff = t & (CV_FG - 1), ji = t >> 3, i = ji % CV2_NP, j = ji / CV2_NP;
+            A_s[(j * CV_FG + ff) * CV2_NP + i] = i < ni ? pw[(((b * N + i0 + i) * N) + j) * 3L * emb + f0 + ff] : 0.f;
+        }
+        __syncthreads();
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+        const float *ap = A_s + f * CV2_NP;
+        const float *bp = B_s + c * CV_FG + f;
+        for (int j = 0; j < N; ++j) {
+            const float h = bp[j * C * CV_FG];
+            const float4 w0 = *reinterpret_cast<const float4 *>(ap + j * CV_FG * CV2_NP);
+            const float4 w1 = *reinterpret_cast<const float4 *>(ap + j * CV_FG * CV2_NP + 4);
+            const float4 w2 = *reinterpret_cast<const float4 *>(ap + j * CV_FG * CV2_NP + 8);
+            const float4 w3 = *reinterpret_cast<const float4 *>(ap + j * CV_FG * CV2_NP + 12);
+            acc[0] = fmaf(w0.x, h, acc[0]); acc[1] = fmaf(w0.y, h, acc[1]); acc[2] = fmaf(w0.z, h, acc[2]); acc[3] = fmaf(w0.w, h, acc[3]);
+            acc[4] = fmaf(w1.x, h, acc[4]); acc[5] = fmaf(w1.y, h, acc[5]); acc[6] = fmaf(w1.z, h, acc[6]); acc[7] = fmaf(w1.w, h, acc[7]);
+            acc[8] = fmaf(w2.x, h, acc[8]); acc[9] = fmaf(w2.y, h, acc[9]); acc[10] = fmaf(w2.z, h, acc[10]); acc[11] = fmaf(w2.w, h, acc[11]);
+            acc[12] = fmaf(w3.x, h, acc[12]); acc[13] = fmaf(w3.y, h, acc[13]); acc[14] = fmaf(w3.z, h, acc[14]); acc[15] = fmaf(w3.w, h, acc[15]);
+        }
+        float *xp = x + (((b * N + i0) * (long)C) + c) * ldx + col_ee + f0 + f;
+        const long xstride = (long)C * ldx;
+        const bool do_ei = f0 + f < dE;
+        const float *eip = ei + ((b * N + i0) * 5L) * dE + f0 + f;                        // [i][5][dE]
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < ni) {
+                const int ig = i0 + i;
+                float v = acc[i];
+                if (tangent) {
+                    if (e == ig) {
+                        v -= S_s[(ig * 3 + ax) * CV_FG + f];
+                    } else {
+                        const float4 u = U_s[ig * N + e];
+                        v += (W1_s[(ig * N + e) * CV_FG + f] * h0e) * (ax == 0 ? u.x : (ax == 1 ? u.y : u.z));
+                    }
+                } else if (c == C - 1) {
+                    v += L_s[ig * CV_FG + f];
+                }
+                xp[i * xstride] = v;
+                if (do_ei) {        // conv_eI: the 5-channel el-ion convolution expanded into the C channels of electron i
+                    float w = 0.f;
+                    if (c == 0) w = eip[(long)i * 5 * dE];
+                    else if (c == C - 1) w = eip[(long)i * 5 * dE + 4 * dE];
+                    else if (e == ig) w = eip[(long)i * 5 * dE + (1 + ax) * dE];
+                    xp[i * xstride + emb] = w;
+                }
+            }
+    }
+}
+
 // Sparse part of the product rule (w depends on r_i, r_j only) and the expansion of conv_eI: one thread per (walker, i, f).
 //   d/dr_j  (j != i):  + w'_ij u_ij hm_j          d/dr_i:  - sum_j w'_ij u_ij hm_j
 //   Laplacian:  sum_j [ (2 w''_ij + 4 w'_ij / d_ij) hm_j + 2 w'_ij u_ij . (d hm_j/d r_j - d hm_j/d r_i) ]
@@ -706,6 +959,21 @@ int launch_conv(dpe_model *m, int it, const float *r, int Bc, int C, const float
     } else {
         if (emb % CV_FG) return set_error(DPE_ERR_UNSUPPORTED, "conv: emb_dim=%d must be a multiple of %d", emb, CV_FG);
         static const bool old_dense = getenv("DPE_CONV_V1") != nullptr;
+        static const bool split_conv = getenv("DPE_CONV_SPLIT") != nullptr;       // debug: dense + sparse kernels instead of the fused one
+        const size_t smem3 = ((size_t)N * CV_FG * CV2_NP + (size_t)N * C * CV_FG + (size_t)2 * N * N * CV_FG + (size_t)4 * N * N + (size_t)N * 4 * CV_FG) * sizeof(float);
+        // conv_eI has dE <= emb features (validate_dims), so the emb / 8 feature groups of a walker cover it
+        if (!old_dense && !split_conv && C * CV_FG <= 1024 && smem3 <= (size_t)DPE_SMEM_OPTIN - 1024 && p.dE <= emb) {
+            static const int minb = getenv("DPE_CONV_MINB") ? atoi(getenv("DPE_CONV_MINB")) : 4;
+            if (C * CV_FG <= 384 && smem3 <= 48 * 1024) {
+                if (minb == 3) k_conv_fused<384, 3><<<Bc * (emb / CV_FG), C * CV_FG, smem3, s>>>(N, C, emb, p.dE, r, hm, pw, ei, x, ldx, p.d_in);
+                else k_conv_fused<384, 4><<<Bc * (emb / CV_FG), C * CV_FG, smem3, s>>>(N, C, emb, p.dE, r, hm, pw, ei, x, ldx, p.d_in);
+            } else {
+                if (int e = opt_in_smem(m, KID_GRAD_A, k_conv_fused<1024, 1>)) return e;
+                k_conv_fused<1024, 1><<<Bc * (emb / CV_FG), C * CV_FG, smem3, s>>>(N, C, emb, p.dE, r, hm, pw, ei, x, ldx, p.d_in);
+            }
+            DPE_LAUNCH_CHECK(m);
+            return DPE_OK;
+        }
         const size_t smem2 = ((size_t)N * CV_FG * CV2_NP + (size_t)N * C * CV_FG) * sizeof(float);
         if (!old_dense && C * CV_FG <= 1024 && smem2 <= 200 * 1024) {
             // small systems: 384-thread blocks at 3 blocks per SM (the kernel is latency bound: occupancy matters more than registers)

@@ -109,6 +109,25 @@ static __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[1
                  : "r"(taddr) : "memory");
 }
 static __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one accumulator column of this thread's lane (load + wait)
+static __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return __uint_as_float(v);
+}
+
+// 16 columns starting at `col` of a 256-column accumulator at `tbase`: one x16 load, or single-column loads where the chunk would
+// run past the accumulator (the columns past it read as 0).  Warp-uniform.
+static __device__ __forceinline__ void tmem_ld16_clipped(uint32_t tbase, int col, uint32_t (&v)[16]) {
+    if (col + 16 <= 256) {
+        tmem_ld16(tbase + col, v);
+        tmem_ld_wait();
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = col + j < 256 ? __float_as_uint(tmem_ld1(tbase + col + j)) : 0u;
+    }
+}
 
 // K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 64-byte rows, 8-row atoms.
 static __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {

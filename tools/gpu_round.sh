@@ -1,10 +1,10 @@
-set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-TAG=${TAG:-r02e}
-timeout 1500 python -m pytest tests -m gpu -q --tb=line 2>&1 | grep -E "AssertionError|Error|passed|failed" | cut -c1-900 > gpurun_out/${TAG}_pytest.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
-cat gpurun_out/${TAG}_pytest.log
-tail -2 gpurun_out/${TAG}_smoke.log
-tail -c 400 gpurun_out/${TAG}_bench.err
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_properties.py tests/test_gpu_multigeometry.py -m gpu -q --tb=line 2>&1 | grep -E "AssertionError|Error|passed|failed" | cut -c1-600
+for v in "" "DPE_TC_ADD_GLOBAL=1" "DPE_TC_SEG_SPLIT=2"; do
+  env $v timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-cadence 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']; s=d['secondary']; r2=s['roofline']
+print('VARIANT [$v]', 'ms/step', round(d['ms_per_step'],3), 'eloc', round(r['eloc_pass_ms'],3), 'frac', round(r['frac'],3), round(r['class_frac'],3), 'main', r['eloc_stages_ms']['main_layer'], 'orb', r['eloc_stages_ms']['orbitals'])
+print('   benzene ms/step', round(s['ms_per_step'],2), 'evals/s', round(s['value'],1), 'stages', r2['eloc_stages_ms'])"
+done
