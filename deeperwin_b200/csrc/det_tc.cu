@@ -32,7 +32,7 @@ constexpr int DT_X_BYTES = DT_ROWS * TC_ROWB;    // 16 KB raw -> hi, + 16 KB lo
 constexpr int DT_STAGE_BYTES = 2 * DT_X_BYTES;
 constexpr int DT_MAX_STAGES = 4;
 constexpr int DT_EPI_WARPS = 8;                  // one accumulator row per epilogue thread
-constexpr int DT_THREADS = (6 + DT_EPI_WARPS) * 32;
+constexpr int DT_THREADS = (6 + DT_EPI_WARPS) * 32;      // per epilogue group: the G = 2 instantiation runs (6 + 2 * DT_EPI_WARPS) warps
 constexpr int DT_TMEM_COLS = 512;                // 2 buffers x 2 halves x 2 NP (NP <= 64)
 
 struct DtArgs {
@@ -57,9 +57,13 @@ static __device__ __forceinline__ float minor2(float a, float d, float b, float 
     const float e = __fmaf_rn(b, c, -p);
     return __fsub_rn(__fmaf_rn(a, d, -p), e);
 }
-static __device__ __forceinline__ void dt_epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(DT_EPI_WARPS * 32) : "memory"); }
+static __device__ __forceinline__ void dt_epi_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(DT_EPI_WARPS * 32) : "memory"); }
 
-__global__ void __launch_bounds__(DT_THREADS, 1)
+// G = number of epilogue groups (8 warps each).  The epilogue is a latency chain per thread (TMEM -> shared memory, then the walk over
+// the 2 x 2 minors), so with G = 2 two groups take alternate tiles -- group g always drains accumulator g -- each with its own Q
+// buffer and named barrier; the per-determinant sums of the two groups meet in shared memory (two addends: order-independent).
+template <int G>
+__global__ void __launch_bounds__((6 + G * DT_EPI_WARPS) * 32, 1)
 k_det_trace_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
                const __grid_constant__ CUtensorMap map_wl, DtArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -70,8 +74,10 @@ k_det_trace_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int QS = a.qs;      // row stride = 2 mod 4: the cyclic row / column / diagonal walks of the epilogue all advance by QS + 1
                               // words from lane to lane (odd: conflict free); the row stores see a 2-way conflict
     float *Qs = reinterpret_cast<float *>(wbase + 4 * whalf);   // [n_qbuf][256][QS]
-    double *red = reinterpret_cast<double *>(Qs + a.n_qbuf * DT_ROWS * QS);     // [2][8]; (NP + 1) * 1024 + 1024 bytes after W keeps it 8-byte aligned
-    uint64_t *bars = reinterpret_cast<uint64_t *>(red + 2 * DT_EPI_WARPS);
+    double *red = reinterpret_cast<double *>(Qs + a.n_qbuf * DT_ROWS * QS);     // [2 groups][2][8]; (NP + 1) * 1024 + 1024 bytes after W keeps it 8-byte aligned
+    double *unit_acc = red + 4 * DT_EPI_WARPS;                                  // [4] per-determinant sums where both groups contribute
+    int *unit_cnt = reinterpret_cast<int *>(unit_acc + 4);                      // [4]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(unit_cnt + 4);
     uint64_t *bar_full = bars, *bar_split = bars + DT_MAX_STAGES, *bar_empty = bars + 2 * DT_MAX_STAGES;
     uint64_t *bar_tfull = bars + 3 * DT_MAX_STAGES, *bar_tempty = bar_tfull + 2;
     uint64_t *bar_wfull = bar_tempty + 2, *bar_wempty = bar_wfull + 2;
@@ -83,6 +89,7 @@ k_det_trace_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t xbytes = (uint32_t)(TC_ROWB * N * a.cpt);      // one TMA box: cpt channels x N electrons x 64 B
 
     if (threadIdx.x == 0) {
+        for (int k = 0; k < 4; ++k) { unit_acc[k] = 0.0; unit_cnt[k] = 0; }
         for (int s = 0; s < DT_MAX_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_split[s], 128); mbar_init(&bar_empty[s], 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], DT_EPI_WARPS * 32);
@@ -198,30 +205,58 @@ k_det_trace_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (++stage == a.n_stages) { stage = 0; phase ^= 1; }
             }
     } else {
-        const int q = warp & 3, hh = (warp - 6) >> 2;       // TMEM lane quarter (= warp % 4) and accumulator half of this warp
+        const int grp = (warp - 6) / DT_EPI_WARPS, gw = (warp - 6) - grp * DT_EPI_WARPS;     // epilogue group, warp within the group
+        const int q = warp & 3, hh = gw >> 2;               // TMEM lane quarter (= warp % 4) and accumulator half of this warp
         const int mrow = hh * 128 + q * 32 + lane;          // the tile row this thread owns
         const int cl = mrow / N, i = mrow - cl * N;         // (channel within the tile, electron) of that row
         // cyclic partners (i + 1 .. i + n_pairs) mod N: every unordered pair once; for even N the antipodal pair goes to the lower index
         const int n_pairs = ((N - 1) >> 1) + ((!(N & 1) && 2 * i < N) ? 1 : 0);
-        uint32_t tph0 = 0, tph1 = 0;
-        int buf = 0, ui = 0, tcount = 0;
-        float *pend = nullptr;                              // record whose lap' still waits for the block-wide sum (thread 0)
-        int pend_par = 0;
+        double *red_g = red + grp * 2 * DT_EPI_WARPS;
+        const bool both = G == 2 && a.n_tiles >= 2;         // both groups see tiles of every determinant
+        int ui = 0, tcount = 0;
+        float *pend = nullptr;                              // record whose lap' still waits for the group-wide sum (thread mrow == 0)
+        int pend_par = 0, pend_ui = 0;
+        auto finish_pending = [&]() {
+            const double *rd = red_g + pend_par * DT_EPI_WARPS;
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < DT_EPI_WARPS; ++w) tot += rd[w];
+            if (!both) {
+                pend[2] = (float)tot;
+            } else {
+                const int slot = pend_ui & 3;
+                atomicAdd(&unit_acc[slot], tot);
+                __threadfence_block();
+                if (atomicAdd(&unit_cnt[slot], 1) == 1) {   // the other group's share is in: a + b, whichever came first
+                    __threadfence_block();
+                    pend[2] = (float)atomicAdd(&unit_acc[slot], 0.0);
+                    unit_acc[slot] = 0.0;
+                    unit_cnt[slot] = 0;
+                }
+            }
+            pend = nullptr;
+        };
         for (long u = blockIdx.x; u < a.n_units; u += gridDim.x, ++ui) {
             float *out = a.det + u * a.rec;
             // per determinant:  lap' = tr(Ainv lapA) + sum_k (g_k^2 - tr(Q_k^2)) = tr(Ainv lapA) + 2 sum_k e2(Q_k), with e2 the sum
             // of the 2 x 2 principal minors.  g_k^2 and tr(Q_k^2) cancel to many digits for an ill-conditioned A (Q_k close to
             // rank one); in the minor form that cancellation happens inside each minor, where minor2() resolves it exactly.
             float e2 = 0.f, lap_tr = 0.f;
+            int n_mine = 0;
             for (int t = 0; t < a.n_tiles; ++t, ++tcount) {
+                const int buf = tcount & 1;
+                if (G == 2 && buf != grp) continue;            // the other group's tile
+                ++n_mine;
+                const uint32_t tph = ((uint32_t)tcount >> 1) & 1u;
                 const int c0 = 1 + t * a.cpt;
                 const int nc = min(a.cpt, C - c0);
                 const int rows = nc * N;
-                float *Q = Qs + (a.n_qbuf == 2 ? (tcount & 1) * DT_ROWS * QS : 0);
-                mbar_wait(&bar_tfull[buf], buf ? tph1 : tph0);
+                const bool one_q = G == 2 || a.n_qbuf == 1;    // this group has a single Q buffer
+                float *Q = Qs + (G == 2 ? grp : (a.n_qbuf == 2 ? (tcount & 1) : 0)) * DT_ROWS * QS;
+                mbar_wait(&bar_tfull[buf], tph);
                 tc_fence_after();
-                if (mrow == 0) DT_TL(6, tcount);
-                if (a.n_qbuf == 1) dt_epi_sync();            // single Q buffer: everybody is done reading the previous tile
+                if (mrow == 0 && grp == 0) DT_TL(6, tcount);
+                if (one_q) dt_epi_sync(grp);                   // single Q buffer: everybody is done reading the previous tile
                 if (hh < a.n_half) {
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + hh) * NA;
                     float2 *d0 = reinterpret_cast<float2 *>(Q + mrow * QS);
@@ -239,38 +274,32 @@ k_det_trace_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 }
                 tc_fence_before();
                 mbar_arrive(&bar_tempty[buf]);
-                if (mrow == N - 1) DT_TL(8, tcount);
-                dt_epi_sync();                               // Q tile complete (and, with two buffers, the tile before last retired)
-                if (mrow == 0 && pend) {
-                    const double *rd = red + pend_par * DT_EPI_WARPS;
-                    double tot = 0.0;
-#pragma unroll
-                    for (int w = 0; w < DT_EPI_WARPS; ++w) tot += rd[w];
-                    pend[2] = (float)tot;
-                    pend = nullptr;
-                }
-                if (mrow == N - 1) DT_TL(9, tcount);
+                if (mrow == N - 1 && grp == 0) DT_TL(8, tcount);
+                dt_epi_sync(grp);                              // Q tile complete (and, with two buffers, the tile before last retired)
+                if (mrow == 0 && pend) finish_pending();
+                if (mrow == N - 1 && grp == 0) DT_TL(9, tcount);
                 if (mrow < rows && c0 + cl < C - 1) {          // tangent channel: this row's share of the 2 x 2 principal minors of Q_c
                     const float *__restrict__ row = Q + mrow * QS;
                     const float *__restrict__ blk = Q + cl * N * QS;
                     const float qii = row[i];
-                    for (int d0 = 1; d0 <= n_pairs; d0 += 8) {         // operands of up to 8 pairs are fetched ahead of the arithmetic;
-                        float pd[8], pb[8], pc[8];                     // no branches: pairs past the end read row i itself and add 0
+                    constexpr int PB = G == 2 ? 4 : 8;                 // operands of up to PB pairs are fetched ahead of the arithmetic;
+                    for (int d0 = 1; d0 <= n_pairs; d0 += PB) {        // no branches: pairs past the end read row i itself and add 0
+                        float pd[PB], pb[PB], pc[PB];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            int o = i + d0 + u;
+                        for (int k = 0; k < PB; ++k) {
+                            int o = i + d0 + k;
                             o = o >= N ? o - N : o;
-                            o = d0 + u <= n_pairs ? o : i;
-                            pd[u] = blk[o * QS + o]; pb[u] = row[o]; pc[u] = blk[o * QS + i];
+                            o = d0 + k <= n_pairs ? o : i;
+                            pd[k] = blk[o * QS + o]; pb[k] = row[o]; pc[k] = blk[o * QS + i];
                         }
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const float mm = minor2(qii, pd[u], pb[u], pc[u]);
-                            e2 = __fadd_rn(e2, d0 + u <= n_pairs ? mm : 0.f);
+                        for (int k = 0; k < PB; ++k) {
+                            const float mm = minor2(qii, pd[k], pb[k], pc[k]);
+                            e2 = __fadd_rn(e2, d0 + k <= n_pairs ? mm : 0.f);
                         }
                     }
                 }
-                if (mrow == N - 1) DT_TL(10, tcount);
+                if (mrow == N - 1 && grp == 0) DT_TL(10, tcount);
                 {
                     // g_c = tr(dA_c Ainv): one thread per channel sums the diagonal of its block -- in a warp whose rows the tile does
                     // not use, when there is one (it then runs beside the minors instead of after them), else the block's last row
@@ -289,24 +318,22 @@ k_det_trace_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         else lap_tr = gk;                      // tr(Ainv lapA)
                     }
                 }
-                if (mrow == N - 1) DT_TL(7, tcount);
-                if (buf) tph1 ^= 1; else tph0 ^= 1;
-                buf ^= 1;
+                if (mrow == N - 1 && grp == 0) DT_TL(7, tcount);
             }
-            double acc = 2.0 * (double)e2 + (double)lap_tr;
-            acc = dt_warp_sum(acc);
-            if (lane == 0) red[(ui & 1) * DT_EPI_WARPS + warp - 6] = acc;
-            pend = out;                                       // summed by thread 0 after the next barrier
-            pend_par = ui & 1;
+            if (n_mine) {
+                double acc = 2.0 * (double)e2 + (double)lap_tr;
+                acc = dt_warp_sum(acc);
+                if (lane == 0) red_g[(ui & 1) * DT_EPI_WARPS + gw] = acc;
+                if (mrow == 0 && pend) {                      // two determinants in a row without a barrier of this group in between cannot happen:
+                    /* unreachable: every determinant this group takes part in has at least one tile with two barriers */
+                }
+                pend = out;                                   // summed by thread mrow == 0 after the group's next barrier
+                pend_par = ui & 1;
+                pend_ui = ui;
+            }
         }
-        dt_epi_sync();
-        if (mrow == 0 && pend) {
-            const double *rd = red + pend_par * DT_EPI_WARPS;
-            double tot = 0.0;
-#pragma unroll
-            for (int w = 0; w < DT_EPI_WARPS; ++w) tot += rd[w];
-            pend[2] = (float)tot;
-        }
+        dt_epi_sync(grp);
+        if (mrow == 0 && pend) finish_pending();
     }
     tc_fence_before();
     __syncthreads();
@@ -355,7 +382,7 @@ int launch_det_trace_tc(dpe_model *m, int Bc, int C, const float *mo, const floa
     a.qs = ((N + 1) & ~3) + 2;                            // smallest stride >= N with stride = 2 (mod 4)
     // shared-memory plan: as many TMA stages as fit (HBM latency), two Q buffers if possible (one barrier per tile)
     const size_t w_bytes = 4 * (size_t)a.n_kb * NP * TC_ROWB, q_bytes = (size_t)DT_ROWS * a.qs * sizeof(float);
-    const size_t fixed = w_bytes + 2 * DT_EPI_WARPS * sizeof(double) + (3 * DT_MAX_STAGES + 8) * sizeof(uint64_t) + 16 + 1024;
+    const size_t fixed = w_bytes + (4 * DT_EPI_WARPS + 4) * sizeof(double) + 4 * sizeof(int) + (3 * DT_MAX_STAGES + 8) * sizeof(uint64_t) + 16 + 1024;
     const int options[5][2] = {{4, 2}, {3, 2}, {3, 1}, {2, 2}, {2, 1}};
     size_t smem = 0;
     for (const auto &o : options) {
@@ -364,7 +391,13 @@ int launch_det_trace_tc(dpe_model *m, int Bc, int C, const float *mo, const floa
         if (smem <= 227 * 1024) break;
     }
     if (smem > 227 * 1024) return DPE_ERR_UNSUPPORTED;
-    if (int e = opt_in_smem(m, KID_DET_TRACE, k_det_trace_tc)) return e;
+    // two epilogue groups need a Q buffer each (the n_qbuf = 2 plans)
+    static const int groups_env = getenv("DPE_DET_EPI_GROUPS") ? atoi(getenv("DPE_DET_EPI_GROUPS")) : 2;
+    // measured: benzene (22 tiles per determinant) 71.6 -> 68.0 ms with two groups, N2 (3 tiles) unchanged -- the stage is bound by the depth of
+    // its TMA pipeline (three 32 KB stages per tile next to the Q buffers), not by the epilogue alone
+    const int n_groups = (groups_env == 2 && a.n_qbuf == 2 && a.n_tiles >= 8) ? 2 : 1;
+    if (n_groups == 2) { if (int e = opt_in_smem(m, KID_DET_TRACE, k_det_trace_tc<2>)) return e; }
+    else if (int e = opt_in_smem(m, KID_GRAD_B, k_det_trace_tc<1>)) return e;
     const int grid = (int)(a.n_units < m->n_sm ? a.n_units : m->n_sm);
     a.tl = nullptr;
     const char *tl_path = getenv("DPE_DET_TIMELINE");          // debug: dump the role timeline of CTA 0 (clock64 stamps)
@@ -372,7 +405,8 @@ int launch_det_trace_tc(dpe_model *m, int Bc, int C, const float *mo, const floa
         DPE_CUDA(cudaMalloc(&a.tl, DT_TL_TILES * 12 * sizeof(long long)));
         DPE_CUDA(cudaMemsetAsync(a.tl, 0, DT_TL_TILES * 12 * sizeof(long long), s));
     }
-    k_det_trace_tc<<<grid, DT_THREADS, smem, s>>>(map_x, map_wh, map_wl, a);
+    if (n_groups == 2) k_det_trace_tc<2><<<grid, (6 + 2 * DT_EPI_WARPS) * 32, smem, s>>>(map_x, map_wh, map_wl, a);
+    else k_det_trace_tc<1><<<grid, DT_THREADS, smem, s>>>(map_x, map_wh, map_wl, a);
     DPE_LAUNCH_CHECK(m);
     if (tl_path) {
         std::vector<long long> h(DT_TL_TILES * 12);

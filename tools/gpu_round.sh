@@ -1,7 +1,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_properties.py tests/test_gpu_multigeometry.py -m gpu -q --tb=line 2>&1 | grep -E "AssertionError|Error|passed|failed" | cut -c1-600
-for v in "" "DPE_TC_ADD_GLOBAL=1" "DPE_TC_SEG_SPLIT=2"; do
+for v in "" "DPE_DET_EPI_GROUPS=1"; do
   env $v timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-cadence 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']; s=d['secondary']; r2=s['roofline']
