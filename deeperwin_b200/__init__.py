@@ -11,8 +11,9 @@ from .configuration import (ClippingConfig, Configuration, MCMCConfigEvaluation,
 from .hamiltonian import build_local_energy
 from .loss_function import build_total_energy, init_clipping_state
 from .mcmc import MCMCState, MetropolisHastingsMonteCarlo, PRNGKey
+from .optimization import build_value_and_grad_func
 from .wavefunction import build_log_psi_squared
 
 __all__ = ["Configuration", "PhysicalConfig", "ModelConfigDeepErwin4", "MCMCConfigOptimization", "MCMCConfigEvaluation",
            "ClippingConfig", "build_log_psi_squared", "build_local_energy", "build_total_energy", "init_clipping_state",
-           "MCMCState", "MetropolisHastingsMonteCarlo", "PRNGKey"]
+           "MCMCState", "MetropolisHastingsMonteCarlo", "PRNGKey", "build_value_and_grad_func"]

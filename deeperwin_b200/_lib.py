@@ -60,6 +60,11 @@ SIGNATURES = {
     "dpe_energy_moments2": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
     "dpe_energy_median": (C.c_int, [_P, C.c_int32, _P, _P]),
     "dpe_energy_width": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P]),
+    "dpe_kfac_layer_count": (C.c_int32, [_P]),
+    "dpe_kfac_floats": (C.c_int64, [_P]),
+    "dpe_kfac_layer": (C.c_int, [_P, C.c_int32, C.c_char_p, C.c_int32] + [C.POINTER(C.c_int32)] * 4 + [C.POINTER(C.c_int64)] * 2),
+    "dpe_gradient_workspace_bytes": (C.c_size_t, [_P, C.c_int32]),
+    "dpe_param_gradient": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "dpe_xla_log_psi_sqr": (None, [_P, C.POINTER(_P), C.c_char_p, C.c_size_t]),
     "dpe_xla_local_energy": (None, [_P, C.POINTER(_P), C.c_char_p, C.c_size_t]),
     "dpe_xla_mcmc_steps": (None, [_P, C.POINTER(_P), C.c_char_p, C.c_size_t]),

@@ -237,6 +237,20 @@ static GemmArgs plain_gemm(const float *A, int lda, const float *W, int ldw, flo
     return g;
 }
 
+// Dense layers for the other translation units (grad.cu): C = A W through the model's GEMM path (tensor cores where the weight is registered)
+int dense_gemm(dpe_model *m, const float *A, int lda, const float *W, float *Cc, int ldc, int M, int N, int K, cudaStream_t s) {
+    return gemm(m, plain_gemm(A, lda, W, N, Cc, ldc, M, N, K), s);
+}
+// ... on the row segment [seg_off, seg_off + seg_len) of every block of seg_stride rows (the spin block of a walker)
+int dense_gemm_seg(dpe_model *m, const float *A, int lda, const float *W, float *Cc, int ldc, int M, int N, int K, int seg_len, int seg_stride, int seg_off,
+                   cudaStream_t s) {
+    GemmArgs g = plain_gemm(A, lda, W, N, Cc, ldc, M, N, K);
+    g.a_seg_len = g.c_seg_len = seg_len;
+    g.a_seg_stride = g.c_seg_stride = seg_stride;
+    g.a_seg_off = g.c_seg_off = seg_off;
+    return gemm(m, g, s);
+}
+
 // One chunk of Bc walkers through the whole network. C = 1 (forward) or 3N+2 (forward Laplacian).
 static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, const WsLayout &L, float *phase, float *logpsi2,
                      float *grad, float *ekin, float *eloc, float *epot_out, cudaStream_t s) {

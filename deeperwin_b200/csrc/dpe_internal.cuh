@@ -177,6 +177,11 @@ int launch_det_trace_tc(dpe_model *m, int Bc, int C, const float *mo, const floa
 int launch_combine(dpe_model *m, int Bc, int C, const float *det, const float *epot, float *phase, float *logpsi2,
                    float *grad, float *ekin, float *eloc, float *epot_out, cudaStream_t s);
 
+// api.cu: dense layers for grad.cu
+int dense_gemm(dpe_model *m, const float *A, int lda, const float *W, float *Cc, int ldc, int M, int N, int K, cudaStream_t s);
+int dense_gemm_seg(dpe_model *m, const float *A, int lda, const float *W, float *Cc, int ldc, int M, int N, int K, int seg_len, int seg_stride, int seg_off,
+                   cudaStream_t s);
+
 // mcmc.cu
 int launch_propose(const dpe_mcmc_state *st, int B, int n_el, int proposal, int step_offset, float *r_prop, float *thr, uint32_t *new_keys, cudaStream_t s);
 int launch_accept(const dpe_mcmc_state *st, int B, int n_el, const float *r_prop, const float *lp_prop, const float *thr,

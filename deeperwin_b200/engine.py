@@ -223,6 +223,42 @@ class Engine:
                                               E_kin=ekin.reshape(batch), E_pot=epot.reshape(batch))
         return e_loc.reshape(batch)
 
+    # ------------------------------------------------------------------ optimisation step
+    def kfac_layers(self):
+        """[(haiku module, din, dout, has_bias, rows_per_walker, a_offset, g_offset)] of the dense layers (dpe_kfac_layer)."""
+        if getattr(self, "_kfac_layers", None) is None:
+            out = []
+            for i in range(self.lib.dpe_kfac_layer_count(self.handle)):
+                name = C.create_string_buffer(128)
+                v = [C.c_int32() for _ in range(4)]
+                o = [C.c_int64() for _ in range(2)]
+                check(self.lib.dpe_kfac_layer(self.handle, i, name, 128, *[C.byref(x) for x in v], *[C.byref(x) for x in o]), "dpe_kfac_layer")
+                out.append((name.value.decode(), v[0].value, v[1].value, v[2].value, v[3].value, o[0].value, o[1].value))
+            self._kfac_layers = out
+        return self._kfac_layers
+
+    def param_gradient(self, r: torch.Tensor, cotangent: Optional[torch.Tensor], with_kfac: bool = False, out: Optional[torch.Tensor] = None):
+        """Backward pass of log psi^2 (dpe_param_gradient).  Returns (flat, log_psi_sqr): `flat` = [gradient (n_params) | KFAC factors] in ONE
+        buffer, so that a multi-GPU caller reduces both with a single all-reduce."""
+        r = self._r(r).reshape(-1, self.n_el, 3)
+        B = r.shape[0]
+        n_k = int(self.lib.dpe_kfac_floats(self.handle)) if with_kfac else 0
+        n_g = self.n_params if cotangent is not None else 0
+        if out is None:
+            out = torch.empty(n_g + n_k, dtype=torch.float32, device=self.device)
+        lp = torch.empty(B, dtype=torch.float32, device=self.device)
+        cot = None if cotangent is None else cotangent.to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+        need = min(self.lib.dpe_gradient_workspace_bytes(self.handle, B), self.workspace_cap)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        grad_ptr = _ptr(out) if n_g else None
+        kfac_ptr = C.c_void_p(out.data_ptr() + 4 * n_g) if n_k else None
+        with torch.cuda.device(self.device):
+            check(self.lib.dpe_param_gradient(self.handle, _ptr(r), B, _ptr(cot), grad_ptr, kfac_ptr, _ptr(lp), _ptr(self._ws), self._ws.numel(),
+                                              self._stream()), "dpe_param_gradient")
+        return out, lp
+
     def mcmc_steps(self, state_struct: DpeMcmcState, n_walkers: int, n_steps: int, cfg: DpeMcmcConfig, recompute: bool,
                    run_controller: bool, counts: torch.Tensor):
         ws = self.workspace(n_walkers, MODE_FORWARD)

@@ -174,6 +174,26 @@ int dpe_energy_moments2(const float *e_loc_dev, const float *e_clipped_dev, int3
 int dpe_energy_median(const float *e_dev, int32_t n, float *out_dev, void *stream);
 int dpe_energy_width(const float *e_dev, int32_t n, const float *center_dev, int32_t metric, float *out_dev, void *stream);
 
+/* ---- optimisation step: parameter gradient and KFAC statistics --------------------------------
+ * dpe_param_gradient is the backward pass of log psi^2 on the value channel.
+ *   grad_dev[n_params] (canonical leaf order, may be NULL) = sum_b cotangent_dev[b] * d log_psi_sqr_b / d params: with
+ *     cotangent_b = (E_clipped_b - mean E_clipped) / B it is the gradient of total_energy (optimization/loss_function.py:143-154);
+ *   kfac_dev[dpe_kfac_floats] (may be NULL) receives, per dense layer, the Kronecker factors of kfac_jax's dense blocks with the
+ *     repeated-dense folding (custom_kfac_jax/kfac_jax/_src/curvature_blocks.py:1594-1624, curvature_tags_and_blocks.py:41-64) for the
+ *     loss registered in loss_function.py:148-150 (normal predictive distribution on 1/2 log psi^2, variance 1/2, fisher_exact):
+ *        A[(din + bias)^2] = [x, 1]^T [x, 1] / B',  G[dout^2] = dy^T dy / B',  dy = (1 / sqrt 2) d log psi^2 / dy,  B' = n_walkers * rows_per_walker.
+ *     The layers, their shapes and offsets: dpe_kfac_layer_count / dpe_kfac_layer (name = the haiku module of the layer);
+ *   log_psi_sqr_dev[B] (may be NULL) receives log psi^2 of the same pass.
+ * Both outputs are sums / means over THIS device's walkers: with several GPUs the caller all-reduces the two buffers (one flat
+ * all-reduce, optimizers.py:133, kfac optimizer.py:1151).  Batches larger than the workspace are processed in chunks. */
+int32_t dpe_kfac_layer_count(const dpe_model *m);
+int64_t dpe_kfac_floats(const dpe_model *m);
+int dpe_kfac_layer(const dpe_model *m, int32_t index, char *name, int32_t name_len, int32_t *din, int32_t *dout, int32_t *has_bias,
+                   int32_t *rows_per_walker, int64_t *a_offset, int64_t *g_offset);
+size_t dpe_gradient_workspace_bytes(const dpe_model *m, int32_t n_walkers);
+int dpe_param_gradient(dpe_model *m, const float *r_dev, int32_t n_walkers, const float *cotangent_dev, float *grad_dev, float *kfac_dev,
+                       float *log_psi_sqr_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* ---- XLA custom-call entry points (keeping JAX as the host) ------------------------------------------
  * Legacy GPU custom-call ABI of the reference's pinned jaxlib (jax 0.4.23): void fn(cudaStream_t, void **buffers, const char
  * *opaque, size_t opaque_len) with `buffers` = operands then results (device pointers).  They replace the three switch points

@@ -1,0 +1,88 @@
+"""Parameter gradient and KFAC statistics (dpe_param_gradient) against the fp64 oracle (oracle/gradient.py, itself pinned to the
+reference's jax.value_and_grad(total_energy) in tests/test_reference_pin.py).  Tolerance per leaf / factor: 1e-4 of its largest
+entry, or 16x (oracle/parity_rule.HARD_FACTOR) the error of the SAME oracle run in fp32 on the CPU where that is larger (randomly placed walkers include
+near-singular determinants whose backward pass amplifies fp32 round-off for any fp32 implementation; the factor covers the
+GPU's FMA chains, measured at ~3x the CPU BLAS round-off in profiles/r02_parity_table.md, and the different summation order).  Structural mistakes show up as O(1) errors."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+from test_gpu_parity import SMALL, make  # noqa: E402
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("name,small,B", [("LiH", True, 24), ("LiH", False, 16), ("B", True, 12), ("N2", False, 6), ("HChain6", True, 8)])
+def test_gradient_and_kfac_match_oracle(name, small, B):
+    from oracle import gradient as og
+    phys, d, p32, p64, R, r, eng = make(name, B, small=small)
+    g = torch.Generator().manual_seed(5)
+    cot = (torch.randn(B, generator=g) / B).float()
+    flat, lp = eng.param_gradient(r.cuda(), cot.cuda(), with_kfac=True)
+    ref = og.param_gradient(p64, d, r.double(), R.double(), phys.Z, cot.double())
+    ref32 = og.param_gradient(p32, d, r, R, phys.Z, cot)
+    floor = max(_rel(ref32[mod][leaf], ref[mod][leaf]) for mod, leaf in eng.leaves)
+    for (mod, leaf), (off, size, rows, cols) in zip(eng.leaves, eng.leaf_shapes):
+        got = flat[off:off + size].reshape(ref[mod][leaf].shape)
+        err = _rel(got, ref[mod][leaf])
+        assert err < max(1e-4, 16 * floor), (mod, leaf, err, floor)
+    fac = og.kfac_factors(p64, d, r.double(), R.double(), phys.Z)
+    fac32 = og.kfac_factors(p32, d, r, R, phys.Z)
+    floor_g = max(_rel(fac32[k][1], fac[k][1]) for k in fac)
+    kf = flat[eng.n_params:]
+    layers = eng.kfac_layers()
+    assert {l[0] for l in layers} == set(fac)
+    for lname, din, dout, hb, rpw, a_off, g_off in layers:
+        A_ref, G_ref, rpw_ref = fac[lname]
+        assert rpw == rpw_ref, lname
+        A = kf[a_off:a_off + (din + hb) ** 2].reshape(din + hb, din + hb)
+        G = kf[g_off:g_off + dout * dout].reshape(dout, dout)
+        assert _rel(A, A_ref) < 1e-5, (lname, "A", _rel(A, A_ref))
+        assert _rel(G, G_ref) < max(1e-4, 16 * floor_g), (lname, "G", _rel(G, G_ref), floor_g)
+    # the same pass returns log psi^2
+    assert torch.allclose(lp, eng.log_psi_sqr(r.cuda())[1], rtol=2e-6, atol=0)
+
+
+def test_chunked_gradient_equals_single_pass_and_public_api():
+    """A workspace smaller than the batch -> chunks with accumulation; build_value_and_grad_func mirrors loss_function.py:75-154."""
+    import deeperwin_b200 as dpe
+    from oracle import gradient as og, model as om
+    cfg = dpe.Configuration(physical=dict(name="LiH"))
+    phys = cfg.physical
+    f, _, _, params, fixed = dpe.build_log_psi_squared(cfg.model, phys, None, None, rng_seed=2, device="cuda:0")
+    eng = f.engine
+    st = dpe.MCMCState.initialize_around_nuclei(96, phys, "gaussian", "el_ion_mapping", dpe.PRNGKey(1), device="cuda:0")
+    st = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=10, initialization="gaussian")).run_inter_steps(f, st, params, 2, 2, fixed)
+    cot = torch.randn(96, device="cuda") / 96
+    eng.set_params(params); eng.set_geometry(st.R, st.Z)
+    full, _ = eng.param_gradient(st.r, cot, with_kfac=True)
+    cap = eng.workspace_cap
+    try:
+        eng.workspace_cap = int(eng.lib.dpe_gradient_workspace_bytes(eng.handle, 40))          # chunks of 40, 40, 16 walkers
+        eng._ws = None
+        chunked, _ = eng.param_gradient(st.r, cot, with_kfac=True)
+    finally:
+        eng.workspace_cap = cap
+        eng._ws = None
+    scale = full.abs().max()
+    assert float((full - chunked).abs().max() / scale) < 2e-6          # chunk sums are re-associated: equal to fp32 round-off
+    # public API: value_and_grad
+    gle = dpe.build_local_energy(f, forward_lap=True)
+    vag = dpe.build_value_and_grad_func(f, gle, dpe.ClippingConfig(), with_kfac_statistics=True)
+    (loss, (cs, aux)), grads = vag(params, dpe.init_clipping_state(), (2, 2), st.build_batch(fixed))
+    d = om.ModelDims(n_el=4, n_up=2, n_ion=2, Z_max=3)
+    p64 = {m: {k: v.double().cpu() for k, v in l.items()} for m, l in params.items()}
+    args = (d, st.r.double().cpu(), st.R.double().cpu(), phys.Z, aux["E_loc_clipped"].double().cpu())
+    ref = og.loss_gradient_from_energies(p64, *args)
+    p32 = {m: {k: v.float().cpu() for k, v in l.items()} for m, l in params.items()}
+    ref32 = og.loss_gradient_from_energies(p32, args[0], st.r.cpu(), st.R.cpu(), phys.Z, aux["E_loc_clipped"].cpu())
+    floor = max(_rel(ref32[m][k], v) for m, l in ref.items() for k, v in l.items())
+    for m, leaves in ref.items():
+        for k, v in leaves.items():
+            assert grads[m][k].shape == params[m][k].shape
+            assert _rel(grads[m][k], v) < max(1e-4, 16 * floor), (m, k, _rel(grads[m][k], v), floor)
+    assert abs(float(loss) - float(aux["E_mean_clipped"])) == 0.0 and "kfac" in aux and len(aux["kfac"]) == 32

@@ -220,3 +220,24 @@ def test_config_defaults_match(ref):
         for k, v in db.items():
             if k in da:
                 assert da[k] == v, (type(b).__name__, k, da[k], v)
+
+
+def test_parameter_gradient(ref):
+    """The gradient of the reference's own total_energy (optimization/loss_function.py:89-154: jax.value_and_grad of the function
+    with the custom jvp) equals the oracle's backward pass of sum_b (E_c - mean E_c)_b / B * log psi^2_b."""
+    from oracle import gradient as og
+    phys, d, p, R, Z, r = system("LiH", 6, **SMALL)
+    _, _, log_psi_sqr = build_reference_model(ref, 3, **small_model_kw())
+    E = torch.tensor([-7.9, -8.3, -8.1, -7.5, -9.0, -8.2], dtype=torch.float64)
+    cc = ref.cfg.ClippingConfig(name="hard", center="mean", width_metric="std", from_previous_step=True, clip_by=5.0)
+    vag = ref.loss.build_value_and_grad_func(log_psi_sqr, lambda params, spin, *batch: E, cc)
+    state = (torch.tensor(-8.0, dtype=torch.float64), torch.tensor(100.0, dtype=torch.float64))       # wide window: nothing is clipped
+    (loss, (st, stats)), grads = vag(p, state, (phys.n_up, phys.n_dn), (r, R, Z, {}))
+    mine = og.loss_gradient_from_energies(p, d, r, R, phys.Z, E)
+    n = 0
+    for m, leaves in mine.items():
+        for k, g in leaves.items():
+            gr = grads[m][k]
+            assert torch.allclose(g, gr, rtol=1e-9, atol=1e-12), (m, k, (g - gr).abs().max())
+            n += 1
+    assert n == sum(len(v) for v in p.values()) and abs(float(loss) - float(E.mean())) < 1e-12
