@@ -258,6 +258,44 @@ class Workload:
         loss, (self.clip_state, self.aux) = self.total_energy(self.params, self.clip_state, self.spin, (self.r, self.R_, self.Z_, self.fixed))
         return loss
 
+    def optimisation_epoch(self, n_mcmc=20):
+        """One epoch of the reference's optimisation loop without the optimiser's control flow: n_mcmc Metropolis steps, E_loc + clipped
+        statistics, then the parameter gradient and the KFAC factors of every dense layer in one backward pass (+ one flat all-reduce)."""
+        import torch.distributed as dist
+        self.device_step(n_mcmc)
+        diff = self.aux["E_loc_clipped"] - self.aux["E_mean_clipped"]
+        cot = self.torch.nan_to_num(diff, nan=0.0) / diff.numel()
+        if getattr(self, "grad_flat", None) is None:
+            self.grad_flat = self.torch.empty(self.engine.n_params + int(self.engine.lib.dpe_kfac_floats(self.engine.handle)),
+                                              dtype=self.torch.float32, device=self.dev)
+        self.engine.param_gradient(self.r, cot, with_kfac=True, out=self.grad_flat)
+        if self.world > 1:
+            dist.all_reduce(self.grad_flat)
+            self.grad_flat /= self.world
+        return self.grad_flat
+
+    def timed_epochs(self, reps, n_mcmc, flush):
+        torch = self.torch
+        self.optimisation_epoch(n_mcmc)
+        torch.cuda.synchronize()
+        launches0 = self.engine.launch_count()
+        ms = []
+        for _ in range(reps):
+            flush.zero_()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(); self.optimisation_epoch(n_mcmc)
+            if self.world > 1:
+                self.flush_counts()
+                torch.cuda.current_stream().wait_stream(self.stats_stream)
+            a1.record()
+            torch.cuda.synchronize()
+            ms.append(a0.elapsed_time(a1))
+        t = torch.tensor([sum(ms)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / reps, (self.engine.launch_count() - launches0) // reps
+
     def timed(self, steps, warmup, flush, n_mcmc=1, settle=True):
         """W warm-up steps (+ a bounded settle loop), then exactly `steps` steps timed with CUDA events, L2 flushed (untimed)
         between them; returns (device ms summed over the steps = max over ranks, per-step ms of this rank, launches, wall window)."""
@@ -370,6 +408,13 @@ def run_ours(args):
         cadence = {"n_inter_steps": n_inter, "value": B * world * 3 / (c_ms * 1e-3), "unit": UNIT, "ms_per_epoch": c_ms / 3,
                    "metropolis_ms_per_step": (c_ms / 3 - dev_ms / args.steps) / (n_inter - 1), "gpu_launches": c_launches,
                    "what": "20 Metropolis steps + 1 forward-Laplacian E_loc + statistics per epoch (configuration.py:1039); evals/s = walkers / epoch time"}
+
+        if w.engine.lib.dpe_kfac_layer_count(w.engine.handle) > 0:
+            o_ms, o_launches = w.timed_epochs(3, n_inter, flush)
+            cadence["optimisation_epoch"] = {
+                "ms_per_epoch": o_ms, "value": B * world / (o_ms * 1e-3), "unit": UNIT, "gradient_and_kfac_ms": o_ms - c_ms / 3, "gpu_launches": o_launches,
+                "what": "the epoch above + the parameter gradient of the clipped-energy loss and the KFAC factors (A, G) of every dense layer "
+                        "(one backward pass, dpe_param_gradient; one flat all-reduce when N > 1); the optimiser's own update is outside the hot path"}
 
     # ---- end-to-end through the public Python API with host buffers ---------------------------------
     e2e = None

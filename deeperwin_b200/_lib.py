@@ -60,6 +60,8 @@ SIGNATURES = {
     "dpe_energy_moments2": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
     "dpe_energy_median": (C.c_int, [_P, C.c_int32, _P, _P]),
     "dpe_energy_width": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P]),
+    "dpe_set_mcmc_graph": (C.c_int, [_P, C.c_int32]),
+    "dpe_get_mcmc_graph": (C.c_int, [_P]),
     "dpe_kfac_layer_count": (C.c_int32, [_P]),
     "dpe_kfac_floats": (C.c_int64, [_P]),
     "dpe_kfac_layer": (C.c_int, [_P, C.c_int32, C.c_char_p, C.c_int32] + [C.POINTER(C.c_int32)] * 4 + [C.POINTER(C.c_int64)] * 2),

@@ -431,6 +431,7 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
         else for (int sp = 0; sp < 2 && !e; ++sp) e = tc_register_weight(m, m->bf_w[sp], dl, cols);
         if (e) { tc_destroy(m); cudaGetLastError(); }      // no tensor-core path: dense layers stay on the FP32 SIMT GEMM
         m->gemm_path = m->tc ? 1 : 0;
+        { const char *g = getenv("DPE_MCMC_GRAPH"); m->mcmc_graph_mode = (g && g[0] == '0') ? 0 : 1; }
     }
     *out = m;
     return DPE_OK;
@@ -445,6 +446,7 @@ void dpe_model_destroy(dpe_model *m) {
         if (m->geom_ev[k]) cudaEventDestroy(m->geom_ev[k]);
     cudaFree(m->tao_w); cudaFree(m->tao_ex[0]);
     tc_destroy(m);
+    mcmc_graphs_destroy(m);
     if (m->prof) {
         for (auto &r : *m->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
         delete m->prof;
@@ -567,19 +569,31 @@ int dpe_local_energy(dpe_model *m, const float *r_dev, int32_t n_walkers, float 
                        grad_dev, e_kin_dev, e_loc_dev, e_pot_dev, (cudaStream_t)stream);
 }
 
-int dpe_mcmc_steps(dpe_model *m, const dpe_mcmc_state *st, int32_t B, int32_t n_steps, const dpe_mcmc_config *cfg,
-                   int32_t recompute_log_psi, int32_t run_controller, int32_t *accept_counts_dev, void *workspace_dev,
-                   size_t workspace_bytes, void *stream) {
-    if (!m || !st || !cfg || !workspace_dev || B <= 0 || n_steps < 0) return set_error(DPE_ERR_ARG, "mcmc_steps: bad argument");
-    if (!st->r_dev || !st->log_psi_sqr_dev || !st->walker_age_dev || !st->rng_state_dev || !st->stepsize_dev || !st->step_nr_dev || !st->acc_rate_dev)
-        return set_error(DPE_ERR_ARG, "mcmc_steps: state has null fields");
-    if (n_steps > 0 && !accept_counts_dev) return set_error(DPE_ERR_ARG, "mcmc_steps: accept_counts_dev is null");
-    if (cfg->proposal < 0 || cfg->proposal > 2) return set_error(DPE_ERR_UNSUPPORTED, "mcmc_steps: proposal %d (0 normal, 1 cauchy, 2 normal_one_el)", cfg->proposal);
-    cudaStream_t s = (cudaStream_t)stream;
+// ---- Metropolis steps ------------------------------------------------------------------------------------------------------------
+// One step = propose, network forward pass (~110 small launches), accept (+ controller).  A call that REPEATS an earlier call exactly
+// (same state / count / workspace pointers, sizes, config and kernel-path settings -- the inter-step loop of a run) is replayed from a CUDA
+// graph captured on its second occurrence: every launch argument is then identical by construction (the step number, step size and RNG keys
+// live in device memory), and the per-launch CPU + front-end cost disappears.  First occurrences and non-repeating calls launch eagerly.
+}  // extern "C"
+namespace dpe {
+struct McmcKey {
+    dpe_mcmc_state st; dpe_mcmc_config cfg;
+    int32_t B, n_steps, recompute, run_controller, gemm_path, det_flags;
+    void *counts, *ws; size_t ws_bytes;
+};
+struct McmcGraph { McmcKey key; cudaGraphExec_t exec; int64_t launches; uint64_t used; };
+struct McmcGraphCache { std::vector<McmcKey> seen; std::vector<McmcGraph> graphs; uint64_t tick = 0; };      // `seen`: the last few eager calls
+void mcmc_graphs_destroy(dpe_model *m) {
+    if (!m->mcmc_graphs) return;
+    for (auto &g : m->mcmc_graphs->graphs) cudaGraphExecDestroy(g.exec);
+    delete m->mcmc_graphs;
+    m->mcmc_graphs = nullptr;
+}
+
+static int mcmc_steps_eager(dpe_model *m, const dpe_mcmc_state *st, int32_t B, int32_t n_steps, const dpe_mcmc_config *cfg, int32_t recompute_log_psi,
+                            int32_t run_controller, int32_t *accept_counts_dev, char *ws, size_t workspace_bytes, cudaStream_t s) {
     WsLayout L;
     plan_mcmc(m->dims, B, L);
-    if (workspace_bytes <= L.total_mcmc) return set_error(DPE_ERR_WORKSPACE, "workspace too small for the Metropolis scratch");
-    char *ws = (char *)workspace_dev;
     float *r_prop = (float *)(ws + L.r_prop), *lp_prop = (float *)(ws + L.lp_prop), *thr = (float *)(ws + L.thr);
     uint32_t *new_keys = (uint32_t *)(ws + L.new_keys);
     char *ws_net = ws + L.total_mcmc;
@@ -602,6 +616,86 @@ int dpe_mcmc_steps(dpe_model *m, const dpe_mcmc_state *st, int32_t B, int32_t n_
     }
     return DPE_OK;
 }
+}  // namespace dpe
+extern "C" {
+
+int dpe_mcmc_steps(dpe_model *m, const dpe_mcmc_state *st, int32_t B, int32_t n_steps, const dpe_mcmc_config *cfg,
+                   int32_t recompute_log_psi, int32_t run_controller, int32_t *accept_counts_dev, void *workspace_dev,
+                   size_t workspace_bytes, void *stream) {
+    if (!m || !st || !cfg || !workspace_dev || B <= 0 || n_steps < 0) return set_error(DPE_ERR_ARG, "mcmc_steps: bad argument");
+    if (!st->r_dev || !st->log_psi_sqr_dev || !st->walker_age_dev || !st->rng_state_dev || !st->stepsize_dev || !st->step_nr_dev || !st->acc_rate_dev)
+        return set_error(DPE_ERR_ARG, "mcmc_steps: state has null fields");
+    if (n_steps > 0 && !accept_counts_dev) return set_error(DPE_ERR_ARG, "mcmc_steps: accept_counts_dev is null");
+    if (cfg->proposal < 0 || cfg->proposal > 2) return set_error(DPE_ERR_UNSUPPORTED, "mcmc_steps: proposal %d (0 normal, 1 cauchy, 2 normal_one_el)", cfg->proposal);
+    cudaStream_t s = (cudaStream_t)stream;
+    WsLayout L;
+    plan_mcmc(m->dims, B, L);
+    if (workspace_bytes <= L.total_mcmc) return set_error(DPE_ERR_WORKSPACE, "workspace too small for the Metropolis scratch");
+    char *ws = (char *)workspace_dev;
+    const bool try_graph = m->mcmc_graph_mode == 1 && !m->profile && n_steps > 0;
+    if (!try_graph) return mcmc_steps_eager(m, st, B, n_steps, cfg, recompute_log_psi, run_controller, accept_counts_dev, ws, workspace_bytes, s);
+
+    McmcKey key;
+    memset(&key, 0, sizeof(key));
+    key.st = *st; key.cfg = *cfg; key.B = B; key.n_steps = n_steps; key.recompute = recompute_log_psi; key.run_controller = run_controller;
+    key.gemm_path = m->gemm_path; key.det_flags = m->det_flags; key.counts = accept_counts_dev; key.ws = ws; key.ws_bytes = workspace_bytes;
+    if (!m->mcmc_graphs) m->mcmc_graphs = new McmcGraphCache();
+    McmcGraphCache &gc = *m->mcmc_graphs;
+    for (auto &g : gc.graphs)
+        if (!memcmp(&g.key, &key, sizeof(key))) {
+            DPE_CUDA(cudaGraphLaunch(g.exec, s));
+            g.used = ++gc.tick;
+            m->launches += g.launches;
+            return DPE_OK;
+        }
+    bool repeat = false;
+    for (size_t k = 0; k < gc.seen.size() && !repeat; ++k)
+        if (!memcmp(&gc.seen[k], &key, sizeof(key))) { repeat = true; gc.seen.erase(gc.seen.begin() + k); }
+    if (!repeat) {
+        if (gc.seen.size() >= 8) gc.seen.erase(gc.seen.begin());
+        gc.seen.push_back(key);
+    }
+    if (!repeat) return mcmc_steps_eager(m, st, B, n_steps, cfg, recompute_log_psi, run_controller, accept_counts_dev, ws, workspace_bytes, s);
+
+    // second occurrence: capture.  Any failure ends the capture, clears the error and runs the call eagerly.
+    const int64_t launches0 = m->launches;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        const int e = mcmc_steps_eager(m, st, B, n_steps, cfg, recompute_log_psi, run_controller, accept_counts_dev, ws, workspace_bytes, s);
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        ok = e == DPE_OK && ce == cudaSuccess && graph != nullptr;
+    }
+    const int64_t captured = m->launches - launches0;
+    m->launches = launches0;
+    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+        cudaGetLastError();
+        m->mcmc_graph_mode = 0;                    // do not try again on this model
+        return mcmc_steps_eager(m, st, B, n_steps, cfg, recompute_log_psi, run_controller, accept_counts_dev, ws, workspace_bytes, s);
+    }
+    if (gc.graphs.size() >= 8) {                   // bounded cache: drop the least recently used
+        size_t lru = 0;
+        for (size_t k = 1; k < gc.graphs.size(); ++k)
+            if (gc.graphs[k].used < gc.graphs[lru].used) lru = k;
+        cudaGraphExecDestroy(gc.graphs[lru].exec);
+        gc.graphs.erase(gc.graphs.begin() + lru);
+    }
+    gc.graphs.push_back(McmcGraph{key, exec, captured, ++gc.tick});
+    DPE_CUDA(cudaGraphLaunch(exec, s));
+    m->launches += captured;
+    return DPE_OK;
+}
+
+int dpe_set_mcmc_graph(dpe_model *m, int32_t mode) {
+    if (!m || (mode != 0 && mode != 1)) return set_error(DPE_ERR_ARG, "set_mcmc_graph: mode must be 0 (eager) or 1 (graph replay of repeated calls)");
+    m->mcmc_graph_mode = mode;
+    if (!mode) mcmc_graphs_destroy(m);
+    return DPE_OK;
+}
+int dpe_get_mcmc_graph(const dpe_model *m) { return m ? m->mcmc_graph_mode : -1; }
 
 int64_t dpe_debug_ws_offset(const dpe_model *m, int32_t n_walkers, int32_t mode, const char *name) {
     if (!m || !name || n_walkers <= 0) return -1;

@@ -53,6 +53,7 @@ struct WsLayout {
     int ldx;       // row stride (floats) of the X buffers
 };
 
+struct McmcGraphCache;
 }  // namespace dpe
 
 struct dpe_model {
@@ -83,6 +84,8 @@ struct dpe_model {
     bool params_set, geom_set;
     int gemm_path;
     int64_t launches;
+    dpe::McmcGraphCache *mcmc_graphs;           // captured Metropolis step sequences (api.cu), nullptr until first use
+    int mcmc_graph_mode;                          // dpe_set_mcmc_graph: 0 eager launches, 1 replay a captured CUDA graph when a call repeats
     bool profile;
     struct ProfRec { cudaEvent_t e0, e1; int klass; double flops; int stage; };
     std::vector<ProfRec> *prof;
@@ -92,6 +95,7 @@ struct dpe_model {
 };
 
 namespace dpe {
+void mcmc_graphs_destroy(dpe_model *m);
 
 int set_error(int code, const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);

@@ -142,6 +142,81 @@ __global__ void __launch_bounds__(256) k_atb(AtbArgs a) {
         }
 }
 
+// The same product for NARROW operands (Ma, Nb <= 32: every pair / el-ion / ion layer): HBM-bound, ~(Ma + Nb) * 4 bytes and Mt * Nb FMAs per row.
+// No shared-memory staging: each warp streams its own rows, every lane owns a 4 x 8 patch of the 32 x 32 product (+ its share of the ones row) and
+// reads its 4 + 8 operands straight from the row (all lanes of a warp hit the same one or two 128-byte lines: broadcast loads).  The eight warps of
+// a block are combined in shared memory in a fixed order.
+__global__ void __launch_bounds__(256) k_atb_narrow(AtbArgs a) {
+    __shared__ float red[8][33 * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m0 = (lane >> 2) * 4, n0 = (lane & 3) * 8;
+    const int Mt = a.Ma + a.ones;
+    const long r_begin = blockIdx.x * a.rows_per_split, r_end = min(a.rows, r_begin + a.rows_per_split);
+    const bool vecA = a.Ma == 32 && (a.lda & 3) == 0 && ((size_t)a.A & 15) == 0;
+    const bool vecB = a.Nb == 32 && (a.ldb & 3) == 0 && ((size_t)a.B & 15) == 0;
+    const unsigned NN = (unsigned)(a.N * a.N);
+    const float one_w = (lane >> 2) == 0 ? 1.f : 0.f;          // the ones row is accumulated by the lanes of the first patch row
+    float acc[4][8] = {}, acc1[8] = {};
+    constexpr int UNR = 4;
+    for (long rb = r_begin + warp; rb < r_end; rb += 8 * UNR) {
+        float av[UNR][4], bv[UNR][8], w[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const long r = rb + 8 * u;
+            bool ok = r < r_end;
+            if (ok && a.sel >= 0) {
+                const unsigned pidx = (unsigned)((unsigned long long)r % NN), i = pidx / (unsigned)a.N, j = pidx - i * (unsigned)a.N;
+                ok = ((((int)i < a.U) == ((int)j < a.U)) ? 0 : 1) == a.sel;
+            }
+            w[u] = ok ? (a.wts ? a.wts[r / a.rpw] : 1.f) : 0.f;
+            const long pr = ok ? map_row(a.rm, r) : -1;
+            if (pr >= 0 && vecA) {
+                const float4 t = *reinterpret_cast<const float4 *>(a.A + pr * a.lda + m0);
+                av[u][0] = t.x; av[u][1] = t.y; av[u][2] = t.z; av[u][3] = t.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) av[u][k] = (pr >= 0 && m0 + k < a.Ma) ? a.A[pr * a.lda + m0 + k] : 0.f;
+            }
+            if (pr >= 0 && vecB) {
+                const float4 t0 = *reinterpret_cast<const float4 *>(a.B + pr * a.ldb + n0), t1 = *reinterpret_cast<const float4 *>(a.B + pr * a.ldb + n0 + 4);
+                bv[u][0] = t0.x; bv[u][1] = t0.y; bv[u][2] = t0.z; bv[u][3] = t0.w; bv[u][4] = t1.x; bv[u][5] = t1.y; bv[u][6] = t1.z; bv[u][7] = t1.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) bv[u][k] = (pr >= 0 && n0 + k < a.Nb) ? a.B[pr * a.ldb + n0 + k] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float x = av[u][k] * w[u];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) acc[k][v] = fmaf(x, bv[u][v], acc[k][v]);
+            }
+            const float x1 = w[u] * one_w;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) acc1[v] = fmaf(x1, bv[u][v], acc1[v]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+            if (m0 + k < a.Ma && n0 + v < a.Nb) red[warp][(m0 + k) * a.Nb + n0 + v] = acc[k][v];
+    if (a.ones && (lane >> 2) == 0)
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+            if (n0 + v < a.Nb) red[warp][a.Ma * a.Nb + n0 + v] = acc1[v];
+    __syncthreads();
+    float *P = a.part + (size_t)blockIdx.x * Mt * a.Nb;
+    for (int t = threadIdx.x; t < Mt * a.Nb; t += 256) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) sacc += red[wv][t];
+        P[t] = sacc;
+    }
+}
+
 // C[m, n] (ldc) = (accumulate ? C : 0) + scale * sum_split P[split][m, n]      (fixed summation order: deterministic)
 __global__ void k_atb_reduce(const float *__restrict__ part, int n_split, int Mt, int Nb, float *__restrict__ C, long ldc, float scale, int accumulate) {
     const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -171,6 +246,19 @@ static int atb(GradCtx &g, float *out, long ldc, const float *A, long lda, int M
     a.sel = sel; a.N = d.n_el; a.U = d.n_up; a.rm = rm;
     const int Mt = Ma + a.ones;
     const size_t per = (size_t)Mt * Nb;
+    if (Ma <= 32 && Nb <= 32) {                                   // narrow operands: the streaming kernel
+        long n_blocks = std::min<long>((rows + 255) / 256, 148L * 6);
+        while (n_blocks > 1 && per * n_blocks > g.part_floats) n_blocks = (n_blocks + 1) / 2;
+        if (per * n_blocks > g.part_floats) return set_error(DPE_ERR_WORKSPACE, "gradient workspace too small for a %d x %d product", Mt, Nb);
+        a.n_split = (int)n_blocks;
+        a.rows_per_split = (rows + n_blocks - 1) / n_blocks;
+        a.part = g.part;
+        k_atb_narrow<<<(unsigned)n_blocks, 256, 0, g.s>>>(a);
+        DPE_LAUNCH_CHECK(g.m);
+        k_atb_reduce<<<(int)((per + 255) / 256), 256, 0, g.s>>>(g.part, a.n_split, Mt, Nb, out, ldc, scale, g.accumulate ? 1 : 0);
+        DPE_LAUNCH_CHECK(g.m);
+        return DPE_OK;
+    }
     const long tiles = (long)((Mt + 63) / 64) * ((Nb + 63) / 64);
     // every block walks its rows serially, 16 at a time: split the rows until ~8 blocks per SM are in flight, but keep >= 256 rows per block
     int n_split = (int)((rows + 255) / 256);
@@ -912,7 +1000,7 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
                 if (grad && (e = atb(g, grad + leaf_off(hl.w), dn, fp(L.px[it]), p.dP, p.dP, true, fp(L.dzh[it]), dn, dn, P2, N * N, cot, 1.f, sd))) return e;
                 if (kfac) {
                     const KfacLayer &k = kl[kbase[it] + 5 + sd];
-                    if ((e = atb(g, kfac + k.a_off, p.dP + 1, fp(L.px[it]), p.dP, p.dP, true, fp(L.px[it]), p.dP, p.dP, P2, N * N, nullptr, 1.f, sd))) return e;
+                    // the A factor equals that of w_same / w_diff (same input rows): copied at the end (dpe_param_gradient)
                     if ((e = atb(g, kfac + k.g_off, dn, fp(L.dzh[it]), dn, dn, false, fp(L.dzh[it]), dn, dn, P2, N * N, nullptr, 0.5f, sd))) return e;
                 }
             }
@@ -1028,6 +1116,14 @@ int dpe_param_gradient(dpe_model *m, const float *r_dev, int32_t n_walkers, cons
         if (e) return e;
     }
     if (kfac_dev) {
+        for (int it = 0, base = 1; it < d.n_iterations; ++it) {           // h_same / h_diff see the rows w_same / w_diff see: one A factor serves both
+            if (it + 1 < d.n_iterations)
+                for (int sd = 0; sd < 2; ++sd) {
+                    const KfacLayer &src = kl[base + sd], &dst = kl[base + 5 + sd];
+                    if (int e = check_cuda(cudaMemcpyAsync(kfac_dev + dst.a_off, kfac_dev + src.a_off, sizeof(float) * (src.din + 1) * (src.din + 1), cudaMemcpyDeviceToDevice, s), __func__)) return e;
+                }
+            base += it + 1 < d.n_iterations ? 8 : 5;
+        }
         for (int k = 0; k < n_layers; ++k) {
             const KfacLayer &l = kl[k];
             const float rows = (float)((double)n_walkers * l.rows_per_walker);

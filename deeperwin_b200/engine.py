@@ -259,6 +259,10 @@ class Engine:
                                               self._stream()), "dpe_param_gradient")
         return out, lp
 
+    def set_mcmc_graph(self, on: bool):
+        """Replay repeated mcmc_steps calls from a captured CUDA graph (default) or launch every kernel eagerly."""
+        check(self.lib.dpe_set_mcmc_graph(self.handle, 1 if on else 0), "dpe_set_mcmc_graph")
+
     def mcmc_steps(self, state_struct: DpeMcmcState, n_walkers: int, n_steps: int, cfg: DpeMcmcConfig, recompute: bool,
                    run_controller: bool, counts: torch.Tensor):
         ws = self.workspace(n_walkers, MODE_FORWARD)

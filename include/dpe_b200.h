@@ -174,6 +174,11 @@ int dpe_energy_moments2(const float *e_loc_dev, const float *e_clipped_dev, int3
 int dpe_energy_median(const float *e_dev, int32_t n, float *out_dev, void *stream);
 int dpe_energy_width(const float *e_dev, int32_t n, const float *center_dev, int32_t metric, float *out_dev, void *stream);
 
+/* Repeated dpe_mcmc_steps calls (identical pointers, sizes, config) are replayed from a CUDA graph captured on the second occurrence; mode 0 keeps
+ * every call on plain launches (also: environment DPE_MCMC_GRAPH=0).  Results are identical either way (same kernels, same order). */
+int dpe_set_mcmc_graph(dpe_model *m, int32_t mode);
+int dpe_get_mcmc_graph(const dpe_model *m);
+
 /* ---- optimisation step: parameter gradient and KFAC statistics --------------------------------
  * dpe_param_gradient is the backward pass of log psi^2 on the value channel.
  *   grad_dev[n_params] (canonical leaf order, may be NULL) = sum_b cotangent_dev[b] * d log_psi_sqr_b / d params: with
