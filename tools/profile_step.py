@@ -1,0 +1,28 @@
+"""The three passes of an optimisation epoch, once each after a warm-up, for ncu captures (N2 x 4096 walkers by default):
+one Metropolis step (plain launches), one forward-Laplacian E_loc pass, one gradient + KFAC backward pass."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+import deeperwin_b200 as dpe
+
+mol = sys.argv[1] if len(sys.argv) > 1 else "N2"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+what = sys.argv[3] if len(sys.argv) > 3 else "mcmc,eloc,grad"
+cfg = dpe.Configuration(physical=dict(name=mol))
+phys = cfg.physical
+f, _, _, params, fixed = dpe.build_log_psi_squared(cfg.model, phys, None, None, rng_seed=1234, device="cuda:0")
+f.engine.set_mcmc_graph(False)
+st = dpe.MCMCState.initialize_around_nuclei(B, phys, "gaussian", "el_ion_mapping", dpe.PRNGKey(1234), device="cuda:0")
+mc = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=1, initialization="gaussian"))
+gle = dpe.build_local_energy(f, forward_lap=True)
+cot = torch.randn(B, device="cuda") / B
+for rep in range(2):                       # rep 0 warms up (smem opt-ins, TMA descriptors), rep 1 is the one to read
+    if "mcmc" in what:
+        st = mc.run_inter_steps(f, st, params, phys.n_up, phys.n_dn, fixed)
+    if "eloc" in what:
+        e = gle(params, (phys.n_up, phys.n_dn), st.r, st.R, st.Z, fixed)
+    if "grad" in what:
+        f.engine.param_gradient(st.r, cot, with_kfac=True)
+    torch.cuda.synchronize()
+print("done")
