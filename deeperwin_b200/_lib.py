@@ -21,7 +21,8 @@ class DpeDims(C.Structure):
 
 class DpeMcmcConfig(C.Structure):
     _fields_ = [("max_age", C.c_int32), ("stepsize_update_interval", C.c_int32), ("target_acceptance_rate", C.c_float),
-                ("min_stepsize_scale", C.c_float), ("max_stepsize_scale", C.c_float), ("proposal", C.c_int32)]
+                ("min_stepsize_scale", C.c_float), ("max_stepsize_scale", C.c_float), ("proposal", C.c_int32),
+                ("r_min", C.c_float), ("r_max", C.c_float), ("langevin_scale", C.c_float)]
 
 
 class DpeXlaDescriptor(C.Structure):

@@ -249,6 +249,19 @@ class MCMCSimpleProposalConfig(ConfigBaseclass):
     name: Literal["normal", "cauchy", "normal_one_el"] = "normal"     # configuration.py:952-953
 
 
+class MCMCLangevinProposalConfig(ConfigBaseclass):
+    name: Literal["langevin"] = "langevin"                            # configuration.py:956-963
+    langevin_scale: float = 1.0
+    r_min: float = 0.2
+    r_max: float = 2.0
+
+
+class LocalStepsizeProposalConfig(ConfigBaseclass):
+    name: Literal["local", "local_one_el"] = "local"                  # configuration.py:966-975
+    r_min: float = 0.1
+    r_max: float = 1
+
+
 class MCMCConfig(ConfigBaseclass):
     n_inter_steps: int
     n_burn_in: int
@@ -260,7 +273,7 @@ class MCMCConfig(ConfigBaseclass):
     target_acceptance_rate: float = 0.5
     min_stepsize_scale: float = 1e-2
     max_stepsize_scale: float = 1.0
-    proposal: MCMCSimpleProposalConfig = MCMCSimpleProposalConfig()
+    proposal: Union[MCMCSimpleProposalConfig, MCMCLangevinProposalConfig, LocalStepsizeProposalConfig] = MCMCSimpleProposalConfig()
     p_spin_swap: float = 0.0
     p_spin_flip: float = 0.0
 

@@ -173,6 +173,7 @@ static void plan_mcmc(const dpe_dims &d, int B, WsLayout &L) {
     L.lp_prop = take((size_t)B * sizeof(float));
     L.thr = take((size_t)B * sizeof(float));
     L.new_keys = take((size_t)B * 2 * sizeof(uint32_t));
+    L.log_q = take((size_t)B * sizeof(float));
     L.total_mcmc = off;
 }
 
@@ -596,6 +597,7 @@ static int mcmc_steps_eager(dpe_model *m, const dpe_mcmc_state *st, int32_t B, i
     plan_mcmc(m->dims, B, L);
     float *r_prop = (float *)(ws + L.r_prop), *lp_prop = (float *)(ws + L.lp_prop), *thr = (float *)(ws + L.thr);
     uint32_t *new_keys = (uint32_t *)(ws + L.new_keys);
+    float *log_q = cfg->proposal >= 3 ? (float *)(ws + L.log_q) : nullptr;
     char *ws_net = ws + L.total_mcmc;
     size_t ws_net_bytes = workspace_bytes - L.total_mcmc;
     int e;
@@ -604,10 +606,10 @@ static int mcmc_steps_eager(dpe_model *m, const dpe_mcmc_state *st, int32_t B, i
     if (n_steps > 0) DPE_CUDA(cudaMemsetAsync(accept_counts_dev, 0, (size_t)n_steps * sizeof(int32_t), s));
     for (int t = 0; t < n_steps; ++t) {
         // without the in-call controller step_nr is advanced afterwards (dpe_mcmc_controller): offset the moved electron by t
-        if ((e = launch_propose(st, B, m->dims.n_el, cfg->proposal, run_controller ? 0 : t, r_prop, thr, new_keys, s))) return e;
+        if ((e = launch_propose(m, st, B, *cfg, run_controller ? 0 : t, r_prop, thr, new_keys, log_q, s))) return e;
         m->launches++;
         if ((e = run_batched(m, r_prop, B, 1, ws_net, ws_net_bytes, nullptr, lp_prop, nullptr, nullptr, nullptr, nullptr, s))) return e;
-        if ((e = launch_accept(st, B, m->dims.n_el, r_prop, lp_prop, thr, new_keys, cfg->max_age, nullptr, accept_counts_dev + t, s))) return e;
+        if ((e = launch_accept(st, B, m->dims.n_el, r_prop, lp_prop, thr, new_keys, log_q, cfg->max_age, nullptr, accept_counts_dev + t, s))) return e;
         m->launches++;
         if (run_controller) {
             if ((e = launch_controller(st, accept_counts_dev + t, 1, B, *cfg, s))) return e;
@@ -626,7 +628,9 @@ int dpe_mcmc_steps(dpe_model *m, const dpe_mcmc_state *st, int32_t B, int32_t n_
     if (!st->r_dev || !st->log_psi_sqr_dev || !st->walker_age_dev || !st->rng_state_dev || !st->stepsize_dev || !st->step_nr_dev || !st->acc_rate_dev)
         return set_error(DPE_ERR_ARG, "mcmc_steps: state has null fields");
     if (n_steps > 0 && !accept_counts_dev) return set_error(DPE_ERR_ARG, "mcmc_steps: accept_counts_dev is null");
-    if (cfg->proposal < 0 || cfg->proposal > 2) return set_error(DPE_ERR_UNSUPPORTED, "mcmc_steps: proposal %d (0 normal, 1 cauchy, 2 normal_one_el)", cfg->proposal);
+    if (cfg->proposal < 0 || cfg->proposal > 5) return set_error(DPE_ERR_UNSUPPORTED, "mcmc_steps: proposal %d (0 normal, 1 cauchy, 2 normal_one_el, 3 local, 4 local_one_el, 5 langevin)", cfg->proposal);
+    if (cfg->proposal >= 3 && !(cfg->r_min > 0.f && cfg->r_max >= cfg->r_min)) return set_error(DPE_ERR_ARG, "mcmc_steps: local proposals need 0 < r_min <= r_max");
+    if (cfg->proposal >= 3 && !m->geom_set) return set_error(DPE_ERR_STATE, "mcmc_steps: set_geometry must be called first");
     cudaStream_t s = (cudaStream_t)stream;
     WsLayout L;
     plan_mcmc(m->dims, B, L);

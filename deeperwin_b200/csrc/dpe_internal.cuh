@@ -49,7 +49,7 @@ struct WsLayout {
     size_t ei_it[DPE_MAX_ITER];   // offsets (bytes) of the per-iteration el-ion convolution blocks
     size_t pw_it[DPE_MAX_ITER];
     // per-call (full batch) scratch for the Metropolis step
-    size_t r_prop, lp_prop, thr, new_keys, mask, ctrl, total_mcmc;
+    size_t r_prop, lp_prop, thr, new_keys, log_q, mask, ctrl, total_mcmc;
     int ldx;       // row stride (floats) of the X buffers
 };
 
@@ -187,9 +187,10 @@ int dense_gemm_seg(dpe_model *m, const float *A, int lda, const float *W, float 
                    cudaStream_t s);
 
 // mcmc.cu
-int launch_propose(const dpe_mcmc_state *st, int B, int n_el, int proposal, int step_offset, float *r_prop, float *thr, uint32_t *new_keys, cudaStream_t s);
+int launch_propose(const dpe_model *m, const dpe_mcmc_state *st, int B, const dpe_mcmc_config &cfg, int step_offset, float *r_prop, float *thr, uint32_t *new_keys,
+                   float *log_q, cudaStream_t s);
 int launch_accept(const dpe_mcmc_state *st, int B, int n_el, const float *r_prop, const float *lp_prop, const float *thr,
-                  const uint32_t *new_keys, int max_age, int32_t *mask, int32_t *count, cudaStream_t s);
+                  const uint32_t *new_keys, const float *log_q, int max_age, int32_t *mask, int32_t *count, cudaStream_t s);
 int launch_controller(const dpe_mcmc_state *st, const int32_t *counts, int n_steps, int64_t n_total,
                       const dpe_mcmc_config &cfg, cudaStream_t s);
 

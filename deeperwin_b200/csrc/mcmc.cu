@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(256) k_propose_one_el(const float *__restrict_
         if (el == moved) {
             uint32_t x0 = (k == 1) ? 1u : 0u, x1 = (k == 1) ? 0u : 2u;
             threefry2x32(sub[0], sub[1], x0, x1);
-            v = __fadd_rn(v, __fmul_rn(bits_to_normal(k == 2 ? x1 : x0), stepsize[0]));
+            const float nz = bits_to_normal(k == 2 ? x1 : x0);
+            v = stepsize ? __fadd_rn(v, __fmul_rn(nz, stepsize[0])) : nz;        // stepsize == nullptr: the raw noise (local_one_el)
         }
         if (e == 0) {
             uint32_t t0 = 0u, t1 = 0u;
@@ -151,25 +152,138 @@ __global__ void __launch_bounds__(256) k_propose(const float *__restrict__ r, co
     }
 }
 
-int launch_propose(const dpe_mcmc_state *st, int B, int n_el, int proposal, int step_offset, float *r_prop, float *thr, uint32_t *new_keys, cudaStream_t s) {
-    int n = 3 * n_el, h = (n + 1) / 2;
-    if (proposal == 2) {
+// ---- proposals with a position-dependent step size (mcmc.py:204-284) -----------------------------------------------------------
+// s(r_i) = stepsize * clip(min_J |r_i - R_J|, r_min, r_max);  langevin adds the drift g(r_i) = -scale sum_J Z_J (r_i - R_J) / |r_i - R_J| times s^2.
+// The arithmetic follows the reference expression by expression in float32 without FMA contraction (positions must not depend on it).
+struct LocalStep { float s, g[3]; };
+__device__ __forceinline__ LocalStep local_step(const float *ri, const float *__restrict__ R, const float *__restrict__ Z, int n_ion, float stepsize,
+                                                float r_min, float r_max, float scale, bool langevin) {
+    float dmin = 3.4e38f, gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int J = 0; J < n_ion; ++J) {
+        const float dx = __fsub_rn(ri[0], R[3 * J]), dy = __fsub_rn(ri[1], R[3 * J + 1]), dz = __fsub_rn(ri[2], R[3 * J + 2]);
+        const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+        dmin = fminf(dmin, d);
+        if (langevin) {                              // sum over ions of diff * Z / dist
+            gx = __fadd_rn(gx, __fdiv_rn(__fmul_rn(dx, Z[J]), d));
+            gy = __fadd_rn(gy, __fdiv_rn(__fmul_rn(dy, Z[J]), d));
+            gz = __fadd_rn(gz, __fdiv_rn(__fmul_rn(dz, Z[J]), d));
+        }
+    }
+    LocalStep o;
+    o.s = __fmul_rn(stepsize, fminf(fmaxf(dmin, r_min), r_max));
+    o.g[0] = __fmul_rn(-scale, gx); o.g[1] = __fmul_rn(-scale, gy); o.g[2] = __fmul_rn(-scale, gz);
+    return o;
+}
+
+// log q(r | r') - log q(r' | r) of one electron: 3 (log s - log s') + (d_fwd / s^2 - d_rev / s'^2) / 2
+__device__ __forceinline__ float log_q_term(float s, float s_new, float d_fwd, float d_rev) {
+    const float a = __fmul_rn(3.f, __fsub_rn(logf(s), logf(s_new)));
+    const float b = __fmul_rn(0.5f, __fsub_rn(__fdiv_rn(d_fwd, __fmul_rn(s, s)), __fdiv_rn(d_rev, __fmul_rn(s_new, s_new))));
+    return __fadd_rn(a, b);
+}
+
+// "local" / "langevin": r_prop holds the raw noise of k_propose on entry, the proposed positions on exit.  One warp per walker (lanes over
+// electrons), the per-electron log_q terms are summed in a fixed order.
+__global__ void __launch_bounds__(256) k_local_finish(const float *__restrict__ r, const float *__restrict__ R, const float *__restrict__ Z, int n_ion,
+                                                       const float *__restrict__ stepsize, int B, int n_el, float r_min, float r_max, float scale,
+                                                       int langevin, float *__restrict__ r_prop, float *__restrict__ log_q) {
+    const int lane = threadIdx.x & 31;
+    const long b = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    const float ss = stepsize[0];
+    float lq = 0.f;
+    for (int i0 = 0; i0 < n_el; i0 += 32) {           // every lane walks the same number of rounds (shuffles below)
+        const int i = i0 + lane;
+        float term = 0.f;
+        if (i < n_el) {
+            const float *ri = r + (b * n_el + i) * 3;
+            float *rp = r_prop + (b * n_el + i) * 3;
+            const LocalStep o = local_step(ri, R, Z, n_ion, ss, r_min, r_max, scale, langevin);
+            float rn[3], drift[3];
+            for (int k = 0; k < 3; ++k) {
+                drift[k] = langevin ? __fmul_rn(o.g[k], __fmul_rn(o.s, o.s)) : 0.f;
+                rn[k] = __fadd_rn(ri[k], __fmul_rn(rp[k], o.s));
+                if (langevin) rn[k] = __fadd_rn(rn[k], drift[k]);
+            }
+            const LocalStep n = local_step(rn, R, Z, n_ion, ss, r_min, r_max, scale, langevin);
+            float d_fwd = 0.f, d_rev = 0.f;
+            for (int k = 0; k < 3; ++k) {
+                const float f = langevin ? __fsub_rn(__fsub_rn(rn[k], ri[k]), drift[k]) : __fsub_rn(rn[k], ri[k]);
+                d_fwd = __fadd_rn(d_fwd, __fmul_rn(f, f));
+                if (langevin) {
+                    const float v = __fsub_rn(__fsub_rn(ri[k], rn[k]), __fmul_rn(n.g[k], __fmul_rn(n.s, n.s)));
+                    d_rev = __fadd_rn(d_rev, __fmul_rn(v, v));
+                }
+                rp[k] = rn[k];
+            }
+            if (!langevin) d_rev = d_fwd;                 // local: 0.5 dist_sqr (1 / s^2 - 1 / s'^2)
+            term = log_q_term(o.s, n.s, d_fwd, d_rev);
+        }
+        for (int off = 16; off; off >>= 1) term += __shfl_xor_sync(0xffffffffu, term, off);
+        lq += term;
+    }
+    if (lane == 0) log_q[b] = lq;
+}
+
+// "local_one_el" (mcmc.py:231-253): k_propose_one_el has moved electron step_nr % n_el by noise * stepsize; rescale that move to the local
+// step size of the electron and form its log_q_ratio.  One thread per walker.
+__global__ void __launch_bounds__(256) k_local_one_el_finish(const float *__restrict__ r, const float *__restrict__ R, int n_ion,
+                                                              const float *__restrict__ stepsize, const int32_t *__restrict__ step_nr, int step_offset,
+                                                              int B, int n_el, float r_min, float r_max, float *__restrict__ r_prop,
+                                                              float *__restrict__ log_q) {
+    const long b = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int i = (step_nr[0] + step_offset) % n_el;
+    const float *ri = r + (b * n_el + i) * 3;
+    float *rp = r_prop + (b * n_el + i) * 3;                 // holds the raw noise (k_propose_one_el was run with stepsize = nullptr -> noise only)
+    const float ss = stepsize[0];
+    const LocalStep o = local_step(ri, R, nullptr, n_ion, ss, r_min, r_max, 0.f, false);
+    float rn[3], d = 0.f;
+    for (int k = 0; k < 3; ++k) rn[k] = __fadd_rn(ri[k], __fmul_rn(rp[k], o.s));
+    const LocalStep n = local_step(rn, R, nullptr, n_ion, ss, r_min, r_max, 0.f, false);
+    for (int k = 0; k < 3; ++k) {
+        const float f = __fsub_rn(rn[k], ri[k]);
+        d = __fadd_rn(d, __fmul_rn(f, f));
+        rp[k] = rn[k];
+    }
+    log_q[b] = log_q_term(o.s, n.s, d, d);
+}
+
+int launch_propose(const dpe_model *m, const dpe_mcmc_state *st, int B, const dpe_mcmc_config &cfg, int step_offset, float *r_prop, float *thr,
+                   uint32_t *new_keys, float *log_q, cudaStream_t s) {
+    const int n_el = m->dims.n_el, n = 3 * n_el, h = (n + 1) / 2, proposal = cfg.proposal;
+    if (proposal == 2 || proposal == 4) {
         long total = (long)B * n;
-        k_propose_one_el<<<(int)((total + 255) / 256), 256, 0, s>>>(st->r_dev, st->rng_state_dev, st->stepsize_dev, st->step_nr_dev, step_offset,
-                                                                    B, n_el, r_prop, thr, new_keys);
-        return check_cuda(cudaGetLastError(), "k_propose_one_el");
+        // proposal 4: raw noise for the moved electron (unit step), positions copied for the others
+        k_propose_one_el<<<(int)((total + 255) / 256), 256, 0, s>>>(st->r_dev, st->rng_state_dev, proposal == 2 ? st->stepsize_dev : nullptr, st->step_nr_dev,
+                                                                    step_offset, B, n_el, r_prop, thr, new_keys);
+        if (int e = check_cuda(cudaGetLastError(), "k_propose_one_el")) return e;
+        if (proposal == 4) {
+            k_local_one_el_finish<<<(B + 255) / 256, 256, 0, s>>>(st->r_dev, m->R_dev, m->dims.n_ion, st->stepsize_dev, st->step_nr_dev, step_offset, B, n_el,
+                                                                  cfg.r_min, cfg.r_max, r_prop, log_q);
+            return check_cuda(cudaGetLastError(), "k_local_one_el_finish");
+        }
+        return DPE_OK;
     }
     long total = (long)B * h;
-    k_propose<<<(int)((total + 255) / 256), 256, 0, s>>>(st->r_dev, st->rng_state_dev, st->stepsize_dev, B, n, r_prop, nullptr,
+    const bool local = proposal == 3 || proposal == 5;
+    // local / langevin: k_propose leaves the raw noise in r_prop, k_local_finish turns it into positions and log_q_ratio
+    k_propose<<<(int)((total + 255) / 256), 256, 0, s>>>(st->r_dev, st->rng_state_dev, st->stepsize_dev, B, n, local ? nullptr : r_prop, local ? r_prop : nullptr,
                                                          thr, new_keys, proposal == 1);
-    return check_cuda(cudaGetLastError(), "k_propose");
+    if (int e = check_cuda(cudaGetLastError(), "k_propose")) return e;
+    if (local) {
+        k_local_finish<<<(int)(((long)B * 32 + 255) / 256), 256, 0, s>>>(st->r_dev, m->R_dev, m->Z_dev, m->dims.n_ion, st->stepsize_dev, B, n_el, cfg.r_min,
+                                                                        cfg.r_max, cfg.langevin_scale, proposal == 5, r_prop, log_q);
+        return check_cuda(cudaGetLastError(), "k_local_finish");
+    }
+    return DPE_OK;
 }
 
 // accept/reject (mcmc.py:358-366): one thread per walker decides, then the block copies positions.
 __global__ void __launch_bounds__(256) k_accept(float *__restrict__ r, float *__restrict__ lp, int32_t *__restrict__ age,
                                                  uint32_t *__restrict__ keys, const float *__restrict__ r_prop,
                                                  const float *__restrict__ lp_prop, const float *__restrict__ thr,
-                                                 const uint32_t *__restrict__ new_keys, int B, int n, int max_age,
+                                                 const uint32_t *__restrict__ new_keys, const float *__restrict__ log_q, int B, int n, int max_age,
                                                  int32_t *__restrict__ mask, int32_t *__restrict__ count) {
     __shared__ int s_acc[256];
     __shared__ int s_cnt;
@@ -180,7 +294,7 @@ __global__ void __launch_bounds__(256) k_accept(float *__restrict__ r, float *__
     int acc = 0;
     if (b < B) {
         float lo = lp[b], ln = lp_prop[b];
-        float p_acc = expf(ln - lo);                      // log_q_ratio = 0 for the normal proposal
+        float p_acc = log_q ? expf(__fadd_rn(__fsub_rn(ln, lo), log_q[b])) : expf(ln - lo);      // mcmc.py:359; log_q_ratio = 0 for proposals 0-2
         int a = age[b];
         acc = (p_acc > thr[b]) || (a >= max_age);
         age[b] = acc ? 0 : a + 1;
@@ -201,9 +315,9 @@ __global__ void __launch_bounds__(256) k_accept(float *__restrict__ r, float *__
 }
 
 int launch_accept(const dpe_mcmc_state *st, int B, int n_el, const float *r_prop, const float *lp_prop, const float *thr,
-                  const uint32_t *new_keys, int max_age, int32_t *mask, int32_t *count, cudaStream_t s) {
+                  const uint32_t *new_keys, const float *log_q, int max_age, int32_t *mask, int32_t *count, cudaStream_t s) {
     k_accept<<<(B + 255) / 256, 256, 0, s>>>(st->r_dev, st->log_psi_sqr_dev, st->walker_age_dev, st->rng_state_dev, r_prop,
-                                             lp_prop, thr, new_keys, B, 3 * n_el, max_age, mask, count);
+                                             lp_prop, thr, new_keys, log_q, B, 3 * n_el, max_age, mask, count);
     return check_cuda(cudaGetLastError(), "k_accept");
 }
 

@@ -270,12 +270,15 @@ class MetropolisHastingsMonteCarlo:
 
     def __init__(self, mcmc_config: MCMCConfig):
         self.config = mcmc_config
-        proposals = {"normal": 0, "cauchy": 1, "normal_one_el": 2}       # mcmc.py:330-343; all three have log_q_ratio = 0
-        if self.config.proposal.name not in proposals:
+        # mcmc.py:330-343; 0-2 have log_q_ratio = 0, 3-5 carry it into the acceptance probability
+        proposals = {"normal": 0, "cauchy": 1, "normal_one_el": 2, "local": 3, "local_one_el": 4, "langevin": 5}
+        prop = self.config.proposal
+        if prop.name not in proposals:
             raise NotImplementedError("Unknown MCMC proposal type")   # mcmc.py:343
         self._cfg = DpeMcmcConfig(int(mcmc_config.max_age), int(mcmc_config.stepsize_update_interval),
                                   float(mcmc_config.target_acceptance_rate), float(mcmc_config.min_stepsize_scale),
-                                  float(mcmc_config.max_stepsize_scale), proposals[self.config.proposal.name])
+                                  float(mcmc_config.max_stepsize_scale), proposals[prop.name],
+                                  float(getattr(prop, "r_min", 0.0)), float(getattr(prop, "r_max", 0.0)), float(getattr(prop, "langevin_scale", 0.0)))
         self.last_accept_counts: Optional[torch.Tensor] = None
 
     def _run_mcmc_steps(self, func, state: MCMCState, params, n_up, n_dn, fixed_params, n_steps) -> MCMCState:

@@ -58,8 +58,14 @@ typedef struct dpe_mcmc_config {
     float target_acceptance_rate;
     float min_stepsize_scale;
     float max_stepsize_scale;
-    int32_t proposal;        /* MCMCSimpleProposalConfig.name (configuration.py:952-953): 0 "normal" (mcmc.py:175-180),
-                                1 "cauchy" (:196-201), 2 "normal_one_el" (:183-193: electron step_nr % n_el moves); log_q_ratio = 0 */
+    int32_t proposal;        /* proposal.name (configuration.py:952-975, mcmc.py:330-343): 0 "normal" (mcmc.py:175-180), 1 "cauchy" (:196-201),
+                                2 "normal_one_el" (:183-193: electron step_nr % n_el moves) -- log_q_ratio = 0;
+                                3 "local" (:212-228), 4 "local_one_el" (:231-253): step size x clip(distance to the closest nucleus, r_min, r_max);
+                                5 "langevin" (:205-209, 256-284): local step size + drift -langevin_scale sum_J Z_J (r - R_J) / |r - R_J|;
+                                3-5 carry their log_q_ratio into the acceptance probability (mcmc.py:359) */
+    float r_min;             /* proposals 3-5 (LocalStepsizeProposalConfig / MCMCLangevinProposalConfig) */
+    float r_max;
+    float langevin_scale;    /* proposal 5 */
 } dpe_mcmc_config;
 
 /* Device-resident walker state: the batch-axis fields of MCMCState (mcmc.py:20-33, 149-151). */

@@ -129,22 +129,66 @@ def initialize_around_nuclei(n_walkers, R, Z, el_ion_mapping, seed, init_method=
         rng_state=threefry.split(rng, n_walkers))
 
 
+def _el_ion(r, R):
+    """utils/utils.py get_el_ion_distance_matrix: diff[b, i, J] = r_i - R_J, dist = |diff| (float32)."""
+    diff = (r[:, :, None, :] - R[None, None, :, :]).astype(f32)
+    return diff, np.sqrt(np.sum(diff * diff, axis=-1, dtype=f32)).astype(f32)
+
+
 def make_mcmc_step(func: Callable[[np.ndarray], np.ndarray], state: OracleMCMCState, *, max_age=20,
                    stepsize_update_interval=100, target_acceptance_rate=0.5, min_stepsize_scale=1e-2,
-                   max_stepsize_scale=1.0, allreduce_mean=lambda x: x, return_mask=False, proposal="normal"):
-    """mcmc.py:345-387 with the `normal` proposal (mcmc.py:175-180).
+                   max_stepsize_scale=1.0, allreduce_mean=lambda x: x, return_mask=False, proposal="normal", proposal_kw=None):
+    """mcmc.py:345-387 with every proposal of mcmc.py:175-284 (`proposal_kw`: r_min, r_max, langevin_scale of the local / langevin ones).
     func(r[B,N,3] f32) -> log_psi_sqr[B] f32."""
     B, N, _ = state.r.shape
+    proposal_kw = proposal_kw or {}
     new_keys, noise, thr = threefry.mcmc_step_randoms(state.rng_state, N, proposal)   # same subkey for noise and threshold
+    log_q_ratio = np.zeros(B, f32)
+    ss = f32(state.stepsize)
     if proposal == "normal_one_el":          # mcmc.py:183-193: only electron step_nr % n_el moves
         r_new = state.r.copy()
         idx = int(state.step_nr) % N
-        r_new[:, idx, :] = (state.r[:, idx, :] + noise * f32(state.stepsize)).astype(f32)
-    else:                                    # normal (mcmc.py:175-180) / cauchy (:196-201); log_q_ratio = 0 for all three
-        r_new = (state.r + noise * f32(state.stepsize)).astype(f32)
+        r_new[:, idx, :] = (state.r[:, idx, :] + noise * ss).astype(f32)
+    elif proposal in ("local", "local_one_el"):     # mcmc.py:212-253: step size proportional to the distance to the closest nucleus
+        r_min, r_max = f32(proposal_kw.get("r_min", 0.1)), f32(proposal_kw.get("r_max", 1.0))
+        closest = lambda rr: np.min(_el_ion(rr, state.R)[1], axis=-1)
+        if proposal == "local":
+            s = (ss * np.clip(closest(state.r), r_min, r_max)).astype(f32)                       # [B, N]
+            r_new = (state.r + noise * s[..., None]).astype(f32)
+            s_new = (ss * np.clip(closest(r_new), r_min, r_max)).astype(f32)
+            dist_sqr = np.sum((r_new - state.r) ** 2, axis=-1, dtype=f32)
+            lq = f32(3) * (np.log(s) - np.log(s_new)) + f32(0.5) * dist_sqr * (f32(1) / s ** 2 - f32(1) / s_new ** 2)
+            log_q_ratio = np.sum(lq, axis=-1, dtype=f32)
+        else:
+            idx = int(state.step_nr) % N
+            s = (ss * np.clip(closest(state.r)[:, idx], r_min, r_max)).astype(f32)               # [B]
+            r_new = state.r.copy()
+            r_new[:, idx, :] = (state.r[:, idx, :] + noise * s[:, None]).astype(f32)
+            s_new = (ss * np.clip(closest(r_new)[:, idx], r_min, r_max)).astype(f32)
+            dist_sqr = np.sum((r_new[:, idx, :] - state.r[:, idx, :]) ** 2, axis=-1, dtype=f32)
+            log_q_ratio = (f32(3) * (np.log(s) - np.log(s_new)) + f32(0.5) * dist_sqr * (f32(1) / s ** 2 - f32(1) / s_new ** 2)).astype(f32)
+    elif proposal == "langevin":             # mcmc.py:205-209, 256-284: local step size + drift towards the nuclei
+        scale = f32(proposal_kw.get("langevin_scale", 1.0))
+        r_min, r_max = f32(proposal_kw.get("r_min", 0.2)), f32(proposal_kw.get("r_max", 2.0))
+
+        def step_and_bias(rr):
+            diff, dist = _el_ion(rr, state.R)
+            g = (-scale * np.sum(diff * state.Z.astype(f32)[:, None] / dist[..., None], axis=-2, dtype=f32)).astype(f32)   # [B, N, 3]
+            return (ss * np.clip(np.min(dist, axis=-1, keepdims=True), r_min, r_max)).astype(f32), g                     # [B, N, 1]
+
+        s, g = step_and_bias(state.r)
+        r_new = (state.r + noise * s + g * s ** 2).astype(f32)
+        s_new, g_new = step_and_bias(r_new)
+        d_fwd = np.sum((r_new - state.r - g * s ** 2) ** 2, axis=-1, dtype=f32)
+        d_rev = np.sum((state.r - r_new - g_new * s_new ** 2) ** 2, axis=-1, dtype=f32)
+        s1, s1n = s[..., 0], s_new[..., 0]
+        lq = f32(3) * (np.log(s1) - np.log(s1n)) + f32(0.5) * (d_fwd / s1 ** 2 - d_rev / s1n ** 2)
+        log_q_ratio = np.sum(lq, axis=-1, dtype=f32)
+    else:                                    # normal (mcmc.py:175-180) / cauchy (:196-201); log_q_ratio = 0
+        r_new = (state.r + noise * ss).astype(f32)
     lp_new = np.asarray(func(r_new), f32)
     with np.errstate(over="ignore"):
-        p_accept = np.exp((lp_new - state.log_psi_sqr).astype(f32)).astype(f32)
+        p_accept = np.exp(((lp_new - state.log_psi_sqr).astype(f32) + log_q_ratio).astype(f32)).astype(f32)
     do_accept = (p_accept > thr) | (state.walker_age >= max_age)
     age = np.where(do_accept, 0, state.walker_age + 1).astype(np.int32)
     lp = np.where(do_accept, lp_new, state.log_psi_sqr).astype(f32)

@@ -117,12 +117,13 @@ def mcmc_step_randoms(keys, n_el, proposal="normal"):
 
     keys: uint32[B, 2].  Returns (new_keys[B,2], noise[B,n_el,3] f32, thr[B] f32).
     `split(key)` -> (new_key, sub); noise = normal(sub,[n_el,3]); thr = uniform(sub,()) -- the SAME subkey.
-    proposal "cauchy" (mcmc.py:196-201): cauchy noise of the same shape; "normal_one_el" (mcmc.py:183-193): noise[B, 3] only.
+    proposal "cauchy" (mcmc.py:196-201): cauchy noise of the same shape; "normal_one_el" (mcmc.py:183-193) and
+    "local_one_el" (:231-253): noise[B, 3] only; "local" (:212-228) and "langevin" (:256-284): normal noise of the full shape.
     """
     keys = np.asarray(keys, dtype=np.uint32)
     B = keys.shape[0]
     new_keys = np.empty((B, 2), np.uint32)
-    shape = (3,) if proposal == "normal_one_el" else (n_el, 3)
+    shape = (3,) if proposal in ("normal_one_el", "local_one_el") else (n_el, 3)
     noise = np.empty((B,) + shape, np.float32)
     thr = np.empty((B,), np.float32)
     for b in range(B):

@@ -334,7 +334,7 @@ def _broadcast_axes(axes, tree):
 def vmap(fun, in_axes=0, out_axes=0, axis_name=None, **_):
     """jax.vmap as a Python loop: slices every mapped leaf, calls `fun`, stacks the results."""
     @functools.wraps(fun)
-    def mapped(*args):
+    def mapped(*args, **kwargs):                   # keyword arguments are broadcast (jax maps them over axis 0; the reference passes configs only)
         axes_per_arg = in_axes if isinstance(in_axes, (tuple, list)) and len(in_axes) == len(args) and not _is_dataclass_instance(in_axes) else [in_axes] * len(args)
         flat, rebuilds, leaf_axes = [], [], []
         for a, ax in zip(args, axes_per_arg):
@@ -353,7 +353,7 @@ def vmap(fun, in_axes=0, out_axes=0, axis_name=None, **_):
         outs = []
         for i in range(n):
             call_args = [rb([_index_axis(l, ax, i) for l, ax in zip(leaves, axs)]) for leaves, axs, rb in zip(flat, leaf_axes, rebuilds)]
-            outs.append(fun(*call_args))
+            outs.append(fun(*call_args, **kwargs))
         out_leaves0, out_rb = tree_flatten(outs[0])
         o_axes = _broadcast_axes(out_axes, outs[0]) if not (isinstance(out_axes, (tuple, list)) and isinstance(outs[0], tuple) and len(out_axes) == len(outs[0])) else \
             [ax for spec, val in zip(out_axes, outs[0]) for ax in _broadcast_axes(spec, val)]

@@ -50,7 +50,7 @@ def test_xla_descriptor_layout_and_refusal(built_library):
     opaque is refused before anything touches the device."""
     from deeperwin_b200 import _lib
     lib = _lib.load()
-    assert ctypes.sizeof(_lib.DpeXlaDescriptor) == 8 + 8 + 4 * 4 + ctypes.sizeof(_lib.DpeMcmcConfig) == 56
+    assert ctypes.sizeof(_lib.DpeMcmcConfig) == 36 and ctypes.sizeof(_lib.DpeXlaDescriptor) == 72        # 8 + 8 + 4 * 4 + 36, padded to a multiple of 8
     assert _lib.DpeXlaDescriptor.model.offset == 0 and _lib.DpeXlaDescriptor.n_walkers.offset == 16 and _lib.DpeXlaDescriptor.mcmc.offset == 32
     lib.dpe_xla_local_energy(None, None, b"abc", 3)
     assert lib.dpe_xla_last_status() == -1 and b"opaque" in lib.dpe_last_error()
@@ -138,7 +138,10 @@ def test_configuration_mirror(tmp_path):
     with pytest.raises(NotImplementedError):              # options the CUDA path does not implement raise loudly
         dpe.Configuration(model=dict(embedding=dict(use_h_two_same_diff=False)))
     with pytest.raises(Exception):
-        dpe.Configuration(optimization=dict(mcmc=dict(proposal=dict(name="langevin"))))       # not among the simple proposals
+        dpe.Configuration(optimization=dict(mcmc=dict(proposal=dict(name="hmc"))))            # not a proposal of the reference
+    lang = dpe.Configuration(optimization=dict(mcmc=dict(proposal=dict(name="langevin", langevin_scale=0.5)))).optimization.mcmc.proposal
+    assert (lang.name, lang.langevin_scale, lang.r_min, lang.r_max) == ("langevin", 0.5, 0.2, 2.0)         # configuration.py:956-963
+    assert dpe.Configuration(optimization=dict(mcmc=dict(proposal=dict(name="local_one_el")))).optimization.mcmc.proposal.r_max == 1
     assert dpe.Configuration(optimization=dict(mcmc=dict(proposal=dict(name="cauchy")))).optimization.mcmc.proposal.name == "cauchy"
     p = tmp_path / "config.yml"
     cfg.save(p)

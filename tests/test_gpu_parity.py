@@ -466,11 +466,15 @@ def test_exponential_initialisation_matches_oracle(name):
     assert st2.r.shape == (cfg.optimization.mcmc.n_walkers, phys.n_electrons, 3) and torch.isfinite(st2.r).all()
 
 
-@pytest.mark.parametrize("proposal", ["normal_one_el", "cauchy"])
+PROPOSAL_KW = {"local": dict(r_min=0.15, r_max=0.9), "local_one_el": dict(r_min=0.15, r_max=0.9), "langevin": dict(langevin_scale=0.7, r_min=0.25, r_max=1.5)}
+
+
+@pytest.mark.parametrize("proposal", ["normal_one_el", "cauchy", "local", "local_one_el", "langevin"])
 def test_proposal_variants_match_oracle_chain(proposal):
-    """mcmc.py:183-201 through the public MetropolisHastingsMonteCarlo: keys and ages bit-exact, positions to float tolerance
+    """mcmc.py:183-284 through the public MetropolisHastingsMonteCarlo: keys and ages bit-exact, positions to float tolerance
     (normal_one_el: electron step_nr % n_el moves, jax's halves layout of normal(sub, [3]); cauchy: tan(pi (u - 1/2)), where
-    tanf vs XLA's tan may differ in the last bits)."""
+    tanf vs XLA's tan may differ in the last bits; local / local_one_el / langevin: position-dependent step size, drift and the
+    log_q_ratio in the acceptance probability)."""
     import deeperwin_b200 as dpe
     from oracle import mcmc as omc, model as om
     _, phys, f, params, fixed, state = _mcmc_setup(B=32)
@@ -480,15 +484,18 @@ def test_proposal_variants_match_oracle_chain(proposal):
     func = lambda r: om.log_psi_sqr(p64, d, torch.from_numpy(r).double(), R64, phys.Z)[1].float().numpy()
     st = omc.OracleMCMCState(r=state.r.cpu().numpy(), R=state.R.cpu().numpy(), Z=np.array(phys.Z), log_psi_sqr=state.log_psi_sqr.cpu().numpy(),
                              walker_age=state.walker_age.cpu().numpy(), rng_state=state.rng_state.cpu().numpy().view(np.uint32))
-    n_steps = 9 if proposal == "normal_one_el" else 4
-    ref = omc.run_mcmc_steps(func, st, n_steps, max_age=20, stepsize_update_interval=5, proposal=proposal)
-    cfg = dpe.MCMCConfigOptimization(n_inter_steps=n_steps, stepsize_update_interval=5, initialization="gaussian", proposal=dict(name=proposal))
+    one_el = proposal.endswith("one_el")
+    n_steps = 9 if one_el else (4 if proposal == "cauchy" else 7)
+    pkw = PROPOSAL_KW.get(proposal, {})
+    ref = omc.run_mcmc_steps(func, st, n_steps, max_age=20, stepsize_update_interval=5, proposal=proposal, proposal_kw=pkw)
+    cfg = dpe.MCMCConfigOptimization(n_inter_steps=n_steps, stepsize_update_interval=5, initialization="gaussian", proposal=dict(name=proposal, **pkw))
     new = dpe.MetropolisHastingsMonteCarlo(cfg).run_inter_steps(f, state, params, phys.n_up, phys.n_dn, fixed)
     assert np.array_equal(new.rng_state.cpu().numpy().view(np.uint32), ref.rng_state)
     assert int(new.step_nr) == ref.step_nr == n_steps
     same_age = new.walker_age.cpu().numpy() == ref.walker_age
-    assert same_age.mean() >= (1.0 if proposal == "normal_one_el" else 0.9)        # cauchy: a knife-edge walker may flip
+    assert same_age.mean() >= (1.0 if proposal == "normal_one_el" else 0.9)        # a knife-edge walker may flip
     dr = np.abs(new.r.cpu().numpy() - ref.r).max(axis=(1, 2))
-    assert dr[same_age].max() < (1e-5 if proposal == "normal_one_el" else 1e-3)
+    assert dr[same_age].max() < (1e-3 if proposal == "cauchy" else 1e-5)
+    assert abs(float(new.stepsize) - float(ref.stepsize)) < 1e-6
     with pytest.raises(Exception):
-        dpe.MCMCConfigOptimization(proposal=dict(name="langevin"))
+        dpe.MCMCConfigOptimization(proposal=dict(name="hmc"))

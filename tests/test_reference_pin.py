@@ -122,7 +122,7 @@ def _ref_mcmc_config(ref, **kw):
     return ref.cfg.MCMCConfigOptimization(**kw)
 
 
-@pytest.mark.parametrize("proposal,n_steps", [("normal", 12), ("normal_one_el", 9), ("cauchy", 4)])
+@pytest.mark.parametrize("proposal,n_steps", [("normal", 12), ("normal_one_el", 9), ("cauchy", 4), ("local", 8), ("local_one_el", 9), ("langevin", 8)])
 def test_metropolis_chain(ref, proposal, n_steps):
     """MetropolisHastingsMonteCarlo._run_mcmc_steps of the reference (mcmc.py:345-406) against the oracle chain on the same
     log psi^2 function: keys, ages and step counters bit-exact, positions / step size / acceptance rate to float32 round-off
@@ -133,8 +133,9 @@ def test_metropolis_chain(ref, proposal, n_steps):
     B = 16
     st0 = omc.initialize_around_nuclei(B, phys.R, phys.Z, phys.el_ion_mapping, 1234, "gaussian", n_up=phys.n_up)
     func = lambda rr: om.log_psi_sqr(p, d, torch.from_numpy(rr).double(), R, phys.Z)[1].float().numpy()
-    oracle_state = omc.run_mcmc_steps(func, st0, n_steps, max_age=3, stepsize_update_interval=5, proposal=proposal)
-    cfg = _ref_mcmc_config(ref, n_inter_steps=n_steps, max_age=3, stepsize_update_interval=5, proposal=dict(name=proposal))
+    pkw = {"local": dict(r_min=0.15, r_max=0.9), "local_one_el": dict(r_min=0.15, r_max=0.9), "langevin": dict(langevin_scale=0.7, r_min=0.25, r_max=1.5)}.get(proposal, {})
+    oracle_state = omc.run_mcmc_steps(func, st0, n_steps, max_age=3, stepsize_update_interval=5, proposal=proposal, proposal_kw=pkw)
+    cfg = _ref_mcmc_config(ref, n_inter_steps=n_steps, max_age=3, stepsize_update_interval=5, proposal=dict(name=proposal, **pkw))
     mc = ref.mcmc.MetropolisHastingsMonteCarlo(cfg)
     state = ref.mcmc.MCMCState(r=torch.from_numpy(st0.r).double(), R=R, Z=Z, log_psi_sqr=torch.from_numpy(st0.log_psi_sqr).double(),
                                walker_age=torch.from_numpy(st0.walker_age).long(), rng_state=st0.rng_state.copy())
