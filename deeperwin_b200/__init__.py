@@ -6,6 +6,7 @@
 
 Importing the package does not load the CUDA library; the first call that needs it raises if it is missing
 (there is no CPU fallback)."""
+from .checkpoints import RunData, load_run, save_run
 from .configuration import (ClippingConfig, Configuration, MCMCConfigEvaluation, MCMCConfigOptimization,
                             ModelConfigDeepErwin4, PhysicalConfig)
 from .hamiltonian import build_local_energy
@@ -16,4 +17,4 @@ from .wavefunction import build_log_psi_squared
 
 __all__ = ["Configuration", "PhysicalConfig", "ModelConfigDeepErwin4", "MCMCConfigOptimization", "MCMCConfigEvaluation",
            "ClippingConfig", "build_log_psi_squared", "build_local_energy", "build_total_energy", "init_clipping_state",
-           "MCMCState", "MetropolisHastingsMonteCarlo", "PRNGKey", "build_value_and_grad_func"]
+           "MCMCState", "MetropolisHastingsMonteCarlo", "PRNGKey", "build_value_and_grad_func", "RunData", "load_run", "save_run"]

@@ -499,3 +499,26 @@ def test_proposal_variants_match_oracle_chain(proposal):
     assert abs(float(new.stepsize) - float(ref.stepsize)) < 1e-6
     with pytest.raises(Exception):
         dpe.MCMCConfigOptimization(proposal=dict(name="hmc"))
+
+
+def test_resume_from_a_reference_checkpoint():
+    """tests/golden/reference_chkpt.zip was written by the reference's save_run: load it, continue the Metropolis chain and evaluate E_loc."""
+    import deeperwin_b200 as dpe
+    from deeperwin_b200 import checkpoints as chk
+    from oracle import model as om
+    data = dpe.load_run(GOLD / "reference_chkpt.zip", device="cuda:0")
+    cfg = dpe.Configuration(physical=dict(name="LiH"),
+                            model=dict(embedding=dict(n_iterations=2, n_hidden_one_el=[16, 16], n_hidden_two_el=[4], n_hidden_el_ions=[4], emb_dim=8),
+                                       orbitals=dict(n_determinants=3)))
+    f, _, _, init, fixed = dpe.build_log_psi_squared(cfg.model, cfg.physical, None, None, rng_seed=0, device="cuda:0")
+    params = chk.params_to_torch(data.params, "cuda:0")
+    assert {m: set(l) for m, l in params.items()} == {m: set(l) for m, l in init.items()}
+    st = data.mcmc_state
+    d = om.ModelDims(n_el=4, n_up=2, n_ion=2, Z_max=3, **SMALL)
+    p64 = {m: {k: torch.from_numpy(np.asarray(v)).double() for k, v in l.items()} for m, l in data.params.items()}
+    ref = om.forward_laplacian(p64, d, st.r.double().cpu(), st.R.double().cpu(), cfg.physical.Z)
+    e = dpe.build_local_energy(f, forward_lap=True)(params, (2, 2), st.r, st.R, st.Z, fixed)
+    assert np.median(np.abs(e.cpu().numpy() - ref["E_loc"].numpy()) / np.maximum(np.abs(ref["E_loc"].numpy()), 1)) < 1e-4
+    mc = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=3, initialization="gaussian"))
+    new = mc.run_inter_steps(f, st, params, 2, 2, fixed)
+    assert int(new.step_nr) == 123 and torch.isfinite(new.log_psi_sqr).all() and new.r.shape == st.r.shape

@@ -242,3 +242,28 @@ def test_parameter_gradient(ref):
             assert torch.allclose(g, gr, rtol=1e-9, atol=1e-12), (m, k, (g - gr).abs().max())
             n += 1
     assert n == sum(len(v) for v in p.values()) and abs(float(loss) - float(E.mean())) < 1e-12
+
+
+def test_reference_load_run_reads_a_checkpoint_written_here(ref, tmp_path):
+    """deeperwin_b200.save_run -> the reference's own load_run (checkpoints.py:69-93): mcmc_state.pkl comes back as the reference's
+    MCMCState dataclass, params / clipping state / metadata unchanged.  (No config.yml: the reference parses it with ruamel.yaml, absent here.)"""
+    import deeperwin.checkpoints as rchk
+    import deeperwin_b200 as dpe
+    from deeperwin_b200.mcmc import MCMCState
+    g = torch.Generator().manual_seed(3)
+    st = MCMCState(r=torch.randn(6, 4, 3, generator=g), R=torch.randn(2, 3, generator=g), Z=torch.tensor([3, 1], dtype=torch.int32),
+                   log_psi_sqr=torch.randn(6, generator=g), walker_age=torch.arange(6, dtype=torch.int32),
+                   rng_state=torch.arange(12, dtype=torch.int32).reshape(6, 2).view(torch.uint32), stepsize=torch.tensor(0.2),
+                   step_nr=torch.tensor(40, dtype=torch.int32), acc_rate=torch.tensor(0.5))
+    params = {"wf/~/input/h_ion": {"embeddings": torch.randn(3, 32, generator=g)}, "wf/x/linear_0": {"w": torch.randn(4, 5, generator=g), "b": torch.zeros(5)}}
+    fn = tmp_path / "chkpt.zip"
+    dpe.save_run(fn, dpe.RunData(params=params, mcmc_state=st, clipping_state=(torch.tensor(-8.0), 0.5), metadata=dict(n_epochs=40),
+                                 history=[dict(opt_epoch=0, opt_E_mean=-7.5)], summary=dict(E_mean=-8.0)))
+    data = rchk.load_run(str(fn))
+    assert type(data.mcmc_state) is ref.mcmc.MCMCState
+    assert np.array_equal(data.mcmc_state.r, st.r.numpy()) and data.mcmc_state.r.dtype == np.float32
+    assert np.array_equal(data.mcmc_state.rng_state, st.rng_state.view(torch.int32).numpy().view(np.uint32)) and data.mcmc_state.rng_state.dtype == np.uint32
+    assert np.array_equal(data.mcmc_state.walker_age, np.arange(6)) and float(data.mcmc_state.stepsize) == pytest.approx(0.2) and int(data.mcmc_state.step_nr) == 40
+    assert data.mcmc_state.build_batch({})[1].shape == (2, 3)                            # the reference's own method on the loaded object
+    assert set(data.params) == set(params) and np.array_equal(data.params["wf/x/linear_0"]["w"], params["wf/x/linear_0"]["w"].numpy())
+    assert tuple(float(x) for x in data.clipping_state) == (-8.0, 0.5) and data.metadata == dict(n_epochs=40)
