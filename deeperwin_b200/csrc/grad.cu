@@ -142,6 +142,83 @@ __global__ void __launch_bounds__(256) k_atb(AtbArgs a) {
         }
 }
 
+// WIDE operands (both sides > 64 columns: the 256-wide layers, the h_el factor, the orbital layers): 128 x 128 tile per block, 8 x 8 outputs per
+// thread (two 4-wide groups 64 apart on each side, so the float4 shared-memory reads of a quarter warp are contiguous), 16 rows per step, the next
+// step's rows prefetched into registers while the current one is multiplied (one barrier per step).  FP32 CUDA cores: ~4 LDS.128 per 64 FMA.
+__global__ void __launch_bounds__(256, 2) k_atb_wide(AtbArgs a) {
+    __shared__ __align__(16) float As[2][16][128], Bs[2][16][128];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int Mt = a.Ma + a.ones;
+    const int n_nb = (a.Nb + 127) / 128;
+    const int m0 = (blockIdx.x / n_nb) * 128, n0 = (blockIdx.x % n_nb) * 128;
+    const long r_begin = blockIdx.y * a.rows_per_split, r_end = min(a.rows, r_begin + a.rows_per_split);
+    const bool vecA = (a.lda & 3) == 0 && ((size_t)a.A & 15) == 0, vecB = (a.ldb & 3) == 0 && ((size_t)a.B & 15) == 0;
+    const int lrow = tid >> 5, lc = (tid & 31) * 4;              // loader: rows lrow and lrow + 8 of the step, columns lc .. lc + 3
+    float acc[8][8] = {};
+    float4 ra[2], rb[2];
+    auto fetch = [&](long rc) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const long r = rc + lrow + 8 * q;
+            ra[q] = make_float4(0.f, 0.f, 0.f, 0.f); rb[q] = ra[q];
+            if (r < r_end) {
+                const unsigned r32 = (unsigned)r;
+                const float w = a.wts ? a.wts[r32 / (unsigned)a.rpw] : 1.f;
+                const long pr = a.rm.seg_len ? (long)(r32 / (unsigned)a.rm.seg_len) * a.rm.seg_stride + a.rm.seg_off + r32 % (unsigned)a.rm.seg_len : r;
+                const int mc = m0 + lc, nc = n0 + lc;
+                float va[4], vb[4];
+                if (vecA && mc + 3 < a.Ma) { const float4 t = *reinterpret_cast<const float4 *>(a.A + pr * a.lda + mc); va[0] = t.x; va[1] = t.y; va[2] = t.z; va[3] = t.w; }
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) va[k] = mc + k < a.Ma ? a.A[pr * a.lda + mc + k] : (mc + k < Mt ? 1.f : 0.f);
+                }
+                if (vecB && nc + 3 < a.Nb) { const float4 t = *reinterpret_cast<const float4 *>(a.B + pr * a.ldb + nc); vb[0] = t.x; vb[1] = t.y; vb[2] = t.z; vb[3] = t.w; }
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) vb[k] = nc + k < a.Nb ? a.B[pr * a.ldb + nc + k] : 0.f;
+                }
+                ra[q] = make_float4(va[0] * w, va[1] * w, va[2] * w, va[3] * w);
+                rb[q] = make_float4(vb[0], vb[1], vb[2], vb[3]);
+            }
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            *reinterpret_cast<float4 *>(&As[buf][lrow + 8 * q][lc]) = ra[q];
+            *reinterpret_cast<float4 *>(&Bs[buf][lrow + 8 * q][lc]) = rb[q];
+        }
+    };
+    fetch(r_begin);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (long rc = r_begin; rc < r_end; rc += 16, buf ^= 1) {
+        const bool more = rc + 16 < r_end;
+        if (more) fetch(rc + 16);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 4]), a1 = *reinterpret_cast<const float4 *>(&As[buf][k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]), b1 = *reinterpret_cast<const float4 *>(&Bs[buf][k][64 + tx * 4]);
+            const float x[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, y[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) acc[u][v] = fmaf(x[u], y[v], acc[u][v]);
+        }
+        if (more) stash(buf ^ 1);
+        __syncthreads();
+    }
+    float *P = a.part + (size_t)blockIdx.y * Mt * a.Nb;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const int mm = m0 + (u < 4 ? ty * 4 + u : 64 + ty * 4 + u - 4), nn = n0 + (v < 4 ? tx * 4 + v : 64 + tx * 4 + v - 4);
+            if (mm < Mt && nn < a.Nb) P[(size_t)mm * a.Nb + nn] = acc[u][v];
+        }
+}
+
 // The same product for NARROW operands (Ma, Nb <= 32: every pair / el-ion / ion layer): HBM-bound, ~(Ma + Nb) * 4 bytes and Mt * Nb FMAs per row.
 // No shared-memory staging: each warp streams its own rows, every lane owns a 4 x 8 patch of the 32 x 32 product (+ its share of the ones row) and
 // reads its 4 + 8 operands straight from the row (all lanes of a warp hit the same one or two 128-byte lines: broadcast loads).  The eight warps of
@@ -164,12 +241,13 @@ __global__ void __launch_bounds__(256) k_atb_narrow(AtbArgs a) {
         for (int u = 0; u < UNR; ++u) {
             const long r = rb + 8 * u;
             bool ok = r < r_end;
+            const unsigned r32 = (unsigned)r;                      // the launcher guarantees rows < 2^31: 32-bit divisions (the 64-bit ones cost more than the FMAs)
             if (ok && a.sel >= 0) {
-                const unsigned pidx = (unsigned)((unsigned long long)r % NN), i = pidx / (unsigned)a.N, j = pidx - i * (unsigned)a.N;
+                const unsigned pidx = r32 % NN, i = pidx / (unsigned)a.N, j = pidx - i * (unsigned)a.N;
                 ok = ((((int)i < a.U) == ((int)j < a.U)) ? 0 : 1) == a.sel;
             }
-            w[u] = ok ? (a.wts ? a.wts[r / a.rpw] : 1.f) : 0.f;
-            const long pr = ok ? map_row(a.rm, r) : -1;
+            w[u] = ok ? (a.wts ? a.wts[r32 / (unsigned)a.rpw] : 1.f) : 0.f;
+            const long pr = !ok ? -1 : (a.rm.seg_len ? (long)(r32 / (unsigned)a.rm.seg_len) * a.rm.seg_stride + a.rm.seg_off + r32 % (unsigned)a.rm.seg_len : r);
             if (pr >= 0 && vecA) {
                 const float4 t = *reinterpret_cast<const float4 *>(a.A + pr * a.lda + m0);
                 av[u][0] = t.x; av[u][1] = t.y; av[u][2] = t.z; av[u][3] = t.w;
@@ -218,14 +296,25 @@ __global__ void __launch_bounds__(256) k_atb_narrow(AtbArgs a) {
 }
 
 // C[m, n] (ldc) = (accumulate ? C : 0) + scale * sum_split P[split][m, n]      (fixed summation order: deterministic)
-__global__ void k_atb_reduce(const float *__restrict__ part, int n_split, int Mt, int Nb, float *__restrict__ C, long ldc, float scale, int accumulate) {
-    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (idx >= (long)Mt * Nb) return;
-    const int mm = (int)(idx / Nb), nn = (int)(idx - (long)mm * Nb);
+// A block reduces 32 outputs: warp g sums the partials g, g + 8, ... of its 32 outputs, then the eight sub-sums are added in order.
+__global__ void __launch_bounds__(256) k_atb_reduce(const float *__restrict__ part, int n_split, int Mt, int Nb, float *__restrict__ C, long ldc, float scale,
+                                                     int accumulate) {
+    __shared__ float sub[8][32];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const long idx = blockIdx.x * 32L + lane, per = (long)Mt * Nb;
     float s = 0.f;
-    for (int k = 0; k < n_split; ++k) s += part[(size_t)k * Mt * Nb + idx];
-    float *c = C + (long)mm * ldc + nn;
-    *c = (accumulate ? *c : 0.f) + scale * s;
+    if (idx < per)
+        for (int k = g; k < n_split; k += 8) s += part[(size_t)k * per + idx];
+    sub[g][lane] = s;
+    __syncthreads();
+    if (g == 0 && idx < per) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sub[k][lane];
+        const int mm = (int)(idx / Nb), nn = (int)(idx - (long)mm * Nb);
+        float *c = C + (long)mm * ldc + nn;
+        *c = (accumulate ? *c : 0.f) + scale * t;
+    }
 }
 
 struct GradCtx {
@@ -246,8 +335,8 @@ static int atb(GradCtx &g, float *out, long ldc, const float *A, long lda, int M
     a.sel = sel; a.N = d.n_el; a.U = d.n_up; a.rm = rm;
     const int Mt = Ma + a.ones;
     const size_t per = (size_t)Mt * Nb;
-    if (Ma <= 32 && Nb <= 32) {                                   // narrow operands: the streaming kernel
-        long n_blocks = std::min<long>((rows + 255) / 256, 148L * 6);
+    if (Ma <= 32 && Nb <= 32 && rows < (1L << 31)) {               // narrow operands: the streaming kernel
+        long n_blocks = std::min<long>((rows + 255) / 256, 148L * 4);
         while (n_blocks > 1 && per * n_blocks > g.part_floats) n_blocks = (n_blocks + 1) / 2;
         if (per * n_blocks > g.part_floats) return set_error(DPE_ERR_WORKSPACE, "gradient workspace too small for a %d x %d product", Mt, Nb);
         a.n_split = (int)n_blocks;
@@ -255,7 +344,22 @@ static int atb(GradCtx &g, float *out, long ldc, const float *A, long lda, int M
         a.part = g.part;
         k_atb_narrow<<<(unsigned)n_blocks, 256, 0, g.s>>>(a);
         DPE_LAUNCH_CHECK(g.m);
-        k_atb_reduce<<<(int)((per + 255) / 256), 256, 0, g.s>>>(g.part, a.n_split, Mt, Nb, out, ldc, scale, g.accumulate ? 1 : 0);
+        k_atb_reduce<<<(int)((per + 31) / 32), 256, 0, g.s>>>(g.part, a.n_split, Mt, Nb, out, ldc, scale, g.accumulate ? 1 : 0);
+        DPE_LAUNCH_CHECK(g.m);
+        return DPE_OK;
+    }
+    if (Mt > 64 && Nb > 64 && rows < (1L << 31) && sel < 0) {       // wide operands: 128 x 128 tiles
+        const long tiles = (long)((Mt + 127) / 128) * ((Nb + 127) / 128);
+        int n_split = (int)((rows + 255) / 256);
+        while (n_split > 1 && tiles * n_split > 148L * 4) n_split = (n_split + 1) / 2;      // two blocks per SM, two waves
+        while (n_split > 1 && per * n_split > g.part_floats) n_split = (n_split + 1) / 2;
+        if (per * n_split > g.part_floats) return set_error(DPE_ERR_WORKSPACE, "gradient workspace too small for a %d x %d product", Mt, Nb);
+        a.n_split = n_split;
+        a.rows_per_split = ((rows + n_split - 1) / n_split + 15) / 16 * 16;
+        a.part = g.part;
+        k_atb_wide<<<dim3((unsigned)tiles, (unsigned)n_split), 256, 0, g.s>>>(a);
+        DPE_LAUNCH_CHECK(g.m);
+        k_atb_reduce<<<(int)((per + 31) / 32), 256, 0, g.s>>>(g.part, n_split, Mt, Nb, out, ldc, scale, g.accumulate ? 1 : 0);
         DPE_LAUNCH_CHECK(g.m);
         return DPE_OK;
     }
@@ -271,7 +375,7 @@ static int atb(GradCtx &g, float *out, long ldc, const float *A, long lda, int M
     dim3 grid((unsigned)tiles, (unsigned)n_split);
     k_atb<<<grid, 256, 0, g.s>>>(a);
     DPE_LAUNCH_CHECK(g.m);
-    k_atb_reduce<<<(int)((per + 255) / 256), 256, 0, g.s>>>(g.part, n_split, Mt, Nb, out, ldc, scale, g.accumulate ? 1 : 0);
+    k_atb_reduce<<<(int)((per + 31) / 32), 256, 0, g.s>>>(g.part, n_split, Mt, Nb, out, ldc, scale, g.accumulate ? 1 : 0);
     DPE_LAUNCH_CHECK(g.m);
     return DPE_OK;
 }
