@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--secondary", default="Benzene", help="molecule of the secondary block ('' to skip)")
     ap.add_argument("--secondary-steps", type=int, default=3)
     ap.add_argument("--no-cadence", action="store_true")
+    ap.add_argument("--no-weight-sharing", action="store_true")
     return ap.parse_args()
 
 
@@ -479,6 +480,10 @@ def run_ours(args):
                      "algorithmic_tflops": None if flop2 is None else v2 * flop2 / 1e12,
                      "E_mean": float(w2.aux["E_mean"]), "acc_rate": float(w2.ar.item())}
         del w2
+    # ---- weight sharing (BASELINE.json configs[2]): one set of weights, 16 H10 geometries, ONE geometry per optimisation step ------
+    shared = None
+    if not args.no_weight_sharing:
+        shared = weight_sharing_block(torch, world, dev, flush)
     if sampler:
         sampler.stop()
     if rank != 0:
@@ -497,12 +502,63 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "algorithmic_tflops": None if flop_eval is None else value * flop_eval / 1e12,
             "step_frac_of_tensor_peak": None if flop_eval is None else value / world * flop_eval / 1e12 / (pk["bf16_tflops"] / 6.0),
-            "cadence": cadence, "secondary": secondary,
+            "cadence": cadence, "secondary": secondary, "weight_sharing": shared,
             "E_mean": E_mean, "acc_rate": acc_rate, "step_ms": [round(t, 2) for t in step_ms],
             "extra_warmup_steps": n_settle}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def weight_sharing_block(torch, world, dev, flush, n_geom=16, walkers=512, n_inter=20):
+    """configs[2]: H10 chains at 16 bond lengths sharing one set of weights (variational_optimization.py:356-387 optimises ONE geometry per
+    step, all GPUs sharing its walkers).  A step = switch geometry (device-side, no host round trip) + n_inter Metropolis steps + E_loc +
+    clipped statistics + parameter gradient and KFAC factors (+ their flat all-reduce), through the public callables; one round = 16 steps."""
+    import numpy as np
+    import deeperwin_b200 as dpe
+    n_at = 10
+    mapping = list(range(0, n_at, 2)) + list(range(1, n_at, 2))
+    phys = [dpe.PhysicalConfig(name=f"HChain{n_at}_{a:.3f}", R=[[float(a) * k, 0.0, 0.0] for k in range(n_at)], Z=[1] * n_at, n_electrons=n_at,
+                               n_up=n_at // 2, el_ion_mapping=mapping) for a in np.linspace(1.2, 3.6, n_geom)]
+    cfg = dpe.Configuration(physical=phys[0].model_dump())
+    f, _, _, params, fixed = dpe.build_log_psi_squared(cfg.model, phys[0], None, None, rng_seed=11, device=dev)
+    gle = dpe.build_local_energy(f, forward_lap=True)
+    vag = dpe.build_value_and_grad_func(f, gle, dpe.ClippingConfig(), with_kfac_statistics=True)
+    mc = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=n_inter, initialization="gaussian"))
+    rank = int(os.environ.get("RANK", 0))
+    states = [dpe.MCMCState.initialize_around_nuclei(walkers, p, "gaussian", "el_ion_mapping", dpe.PRNGKey(100 * rank + g), device=dev)
+              for g, p in enumerate(phys)]
+    clip = [dpe.init_clipping_state() for _ in phys]
+    spin = (n_at // 2, n_at // 2)
+
+    def one_round():
+        e = []
+        for g in range(n_geom):
+            states[g] = mc.run_inter_steps(f, states[g], params, spin[0], spin[1], fixed)
+            (loss, (clip[g], aux)), grads = vag(params, clip[g], spin, states[g].build_batch(fixed))
+            e.append(loss)
+        return e
+
+    for _ in range(3):                       # warm-up: burn-in of every geometry; graphs of the repeating Metropolis calls are captured
+        one_round()
+    torch.cuda.synchronize()
+    launches0 = f.engine.launch_count()
+    flush.zero_()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    e = one_round()
+    a1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    return {"value": walkers * world * n_geom / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / n_geom, "steps": n_geom, "n_geometries": n_geom,
+            "walkers_per_gpu_per_geometry": walkers, "n_inter_steps": n_inter, "gpu_launches": f.engine.launch_count() - launches0,
+            "E_mean_first_last": [float(e[0]), float(e[-1])],
+            "what": "H10 chain, 16 bond lengths, one shared set of weights; step = geometry switch + 20 Metropolis steps + forward-Laplacian E_loc + "
+                    "statistics + gradient and KFAC factors (one flat all-reduce when N > 1); evals/s = walkers x geometries / time of one round"}
 
 
 def main():

@@ -583,10 +583,11 @@ struct McmcKey {
     void *counts, *ws; size_t ws_bytes;
 };
 struct McmcGraph { McmcKey key; cudaGraphExec_t exec; int64_t launches; uint64_t used; };
-struct McmcGraphCache { std::vector<McmcKey> seen; std::vector<McmcGraph> graphs; uint64_t tick = 0; };      // `seen`: the last few eager calls
+struct McmcGraphCache { std::vector<McmcKey> seen; std::vector<McmcGraph> graphs; uint64_t tick = 0; cudaStream_t capture_stream = nullptr; };      // `seen`: the last few eager calls
 void mcmc_graphs_destroy(dpe_model *m) {
     if (!m->mcmc_graphs) return;
     for (auto &g : m->mcmc_graphs->graphs) cudaGraphExecDestroy(g.exec);
+    if (m->mcmc_graphs->capture_stream) cudaStreamDestroy(m->mcmc_graphs->capture_stream);
     delete m->mcmc_graphs;
     m->mcmc_graphs = nullptr;
 }
@@ -656,7 +657,7 @@ int dpe_mcmc_steps(dpe_model *m, const dpe_mcmc_state *st, int32_t B, int32_t n_
     for (size_t k = 0; k < gc.seen.size() && !repeat; ++k)
         if (!memcmp(&gc.seen[k], &key, sizeof(key))) { repeat = true; gc.seen.erase(gc.seen.begin() + k); }
     if (!repeat) {
-        if (gc.seen.size() >= 8) gc.seen.erase(gc.seen.begin());
+        if (gc.seen.size() >= 64) gc.seen.erase(gc.seen.begin());
         gc.seen.push_back(key);
     }
     if (!repeat) return mcmc_steps_eager(m, st, B, n_steps, cfg, recompute_log_psi, run_controller, accept_counts_dev, ws, workspace_bytes, s);
@@ -665,10 +666,12 @@ int dpe_mcmc_steps(dpe_model *m, const dpe_mcmc_state *st, int32_t B, int32_t n_
     const int64_t launches0 = m->launches;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    // captured on a private stream (the caller's may be the legacy default stream, which cannot be captured); the graph is launched on the caller's
+    if (!gc.capture_stream && cudaStreamCreateWithFlags(&gc.capture_stream, cudaStreamNonBlocking) != cudaSuccess) gc.capture_stream = nullptr;
+    bool ok = gc.capture_stream && cudaStreamBeginCapture(gc.capture_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
-        const int e = mcmc_steps_eager(m, st, B, n_steps, cfg, recompute_log_psi, run_controller, accept_counts_dev, ws, workspace_bytes, s);
-        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        const int e = mcmc_steps_eager(m, st, B, n_steps, cfg, recompute_log_psi, run_controller, accept_counts_dev, ws, workspace_bytes, gc.capture_stream);
+        const cudaError_t ce = cudaStreamEndCapture(gc.capture_stream, &graph);
         ok = e == DPE_OK && ce == cudaSuccess && graph != nullptr;
     }
     const int64_t captured = m->launches - launches0;
@@ -680,7 +683,7 @@ int dpe_mcmc_steps(dpe_model *m, const dpe_mcmc_state *st, int32_t B, int32_t n_
         m->mcmc_graph_mode = 0;                    // do not try again on this model
         return mcmc_steps_eager(m, st, B, n_steps, cfg, recompute_log_psi, run_controller, accept_counts_dev, ws, workspace_bytes, s);
     }
-    if (gc.graphs.size() >= 8) {                   // bounded cache: drop the least recently used
+    if (gc.graphs.size() >= 48) {                  // bounded cache (a weight-sharing run keeps two state buffers per geometry): drop the least recently used
         size_t lru = 0;
         for (size_t k = 1; k < gc.graphs.size(); ++k)
             if (gc.graphs[k].used < gc.graphs[lru].used) lru = k;

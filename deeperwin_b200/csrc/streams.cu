@@ -801,6 +801,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k_conv_fused(int N, int C, int emb
         const float inv = i == j ? 0.f : 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
         U_s[t] = make_float4(dx * inv, dy * inv, dz * inv, inv);
     }
+    // the w slab of the first block of electrons does not depend on the prologue: fetch it in the same global-load phase
+    auto load_w = [&](int i0, int ni) {
+        for (int t = tid; t < N * CV2_NP * CV_FG; t += blockDim.x) {      // ff fastest: 8 threads share one 32-byte sector of pw
+            const int ff = t & (CV_FG - 1), ji = t >> 3, i = ji % CV2_NP, j = ji / CV2_NP;
+            A_s[(j * CV_FG + ff) * CV2_NP + i] = i < ni ? pw[(((b * N + i0 + i) * N) + j) * 3L * emb + f0 + ff] : 0.f;
+        }
+    };
+    load_w(0, min(16, N));
     __syncthreads();
     if (tid < N * CV_FG) {                          // prologue: thread = (electron i, feature f)
         const int i = tid >> 3;
@@ -825,11 +833,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_conv_fused(int N, int C, int emb
     for (int i0 = 0; i0 < N; i0 += 16) {
         const int ni = min(16, N - i0);
         __syncthreads();                           // previous i block consumed; first time: prologue tables complete
-        for (int t = tid; t < N * CV2_NP * CV_FG; t += blockDim.x) {      // ff fastest: 8 threads share one 32-byte sector of pw
-            const int ff = t & (CV_FG - 1), ji = t >> 3, i = ji % CV2_NP, j = ji / CV2_NP;
-            A_s[(j * CV_FG + ff) * CV2_NP + i] = i < ni ? pw[(((b * N + i0 + i) * N) + j) * 3L * emb + f0 + ff] : 0.f;
+        if (i0 > 0) {
+            load_w(i0, ni);
+            __syncthreads();
         }
-        __syncthreads();
         float acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.f;

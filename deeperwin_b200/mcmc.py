@@ -280,6 +280,7 @@ class MetropolisHastingsMonteCarlo:
                                   float(mcmc_config.max_stepsize_scale), proposals[prop.name],
                                   float(getattr(prop, "r_min", 0.0)), float(getattr(prop, "r_max", 0.0)), float(getattr(prop, "langevin_scale", 0.0)))
         self.last_accept_counts: Optional[torch.Tensor] = None
+        self._work = {}            # persistent step buffers per (walker shape, device, n_steps)
 
     def _run_mcmc_steps(self, func, state: MCMCState, params, n_up, n_dn, fixed_params, n_steps) -> MCMCState:
         """mcmc.py:389-406. `func` must be the log_psi_sqr callable of build_log_psi_squared."""
@@ -291,18 +292,24 @@ class MetropolisHastingsMonteCarlo:
         engine.set_params(params)
         engine.set_geometry(sq(state.R), sq(state.Z))
         engine.set_tao_cache(((fixed_params or {}).get("cache") or {}).get("taos"))
-        # functional update: inputs are never mutated (SURVEY.md 8b conventions)
-        r = sq(state.r).to(torch.float32).contiguous().clone()
-        lp = sq(state.log_psi_sqr).to(torch.float32).contiguous().clone()
-        age = sq(state.walker_age).to(torch.int32).contiguous().clone()
-        keys = sq(state.rng_state).contiguous().clone()
-        stepsize = sq(state.stepsize).to(torch.float32).reshape(1).clone()
-        step_nr = sq(state.step_nr).to(torch.int32).reshape(1).clone()
-        acc_rate = sq(state.acc_rate).to(torch.float32).reshape(1).clone()
+        # functional update: inputs are never mutated (SURVEY.md 8b conventions).  The steps run on PERSISTENT work buffers of this object
+        # (copy in, advance in place, copy out): the library sees the same pointers on every call of a run, so its CUDA-graph replay
+        # of repeated calls (dpe_mcmc_steps) applies to the public API as well, whatever the allocator does with the state tensors.
+        src = [sq(state.r).to(torch.float32), sq(state.log_psi_sqr).to(torch.float32), sq(state.walker_age).to(torch.int32),
+               sq(state.rng_state).contiguous().view(torch.int32), sq(state.stepsize).to(torch.float32).reshape(1), sq(state.step_nr).to(torch.int32).reshape(1),
+               sq(state.acc_rate).to(torch.float32).reshape(1)]
+        wkey = (tuple(src[0].shape), src[0].device, max(n_steps, 1))
+        work = self._work.get(wkey)
+        if work is None:
+            if len(self._work) >= 4:
+                self._work.pop(next(iter(self._work)))
+            work = self._work[wkey] = [torch.empty_like(t, memory_format=torch.contiguous_format) for t in src] + \
+                                      [torch.zeros(max(n_steps, 1), dtype=torch.int32, device=src[0].device)]
+        torch._foreach_copy_(work[:7], src)
+        r, lp, age, keys, stepsize, step_nr, acc_rate, counts = work
         B = r.shape[0]
         st = DpeMcmcState(r.data_ptr(), lp.data_ptr(), age.data_ptr(), keys.data_ptr(), stepsize.data_ptr(), step_nr.data_ptr(),
                           acc_rate.data_ptr())
-        counts = torch.zeros(max(n_steps, 1), dtype=torch.int32, device=r.device)
         ws_n = utils.world_size()
         step_host = state._step_nr_host
         if ws_n == 1:
@@ -319,6 +326,10 @@ class MetropolisHastingsMonteCarlo:
                 torch.distributed.all_reduce(seg_counts)     # acceptance rate: pmean(mean(do_accept)), mcmc.py:367
                 engine.mcmc_controller(st, seg_counts, seg, B * ws_n, self._cfg)
                 done += seg
+        out = [torch.empty_like(t) for t in work]
+        torch._foreach_copy_(out, work)
+        r, lp, age, keys, stepsize, step_nr, acc_rate, counts = out
+        keys = keys.view(torch.uint32)
         self.last_accept_counts = counts[:n_steps]
         known = state._step_nr_host if state._step_nr_host is not None else step_host
         un = (lambda x: x[None]) if split_axis else (lambda x: x)

@@ -51,6 +51,7 @@ def test_in_place_state_replays_and_counts_launches():
 
     a, la = run(False)
     b, lb = run(True)
+    assert eng.lib.dpe_get_mcmc_graph(eng.handle) == 1            # the capture succeeded (a failure switches the model back to plain launches)
     assert la == lb and len(set(la)) == 1 and la[0] > 100
     for x, y in zip(a, b):
         assert torch.equal(x, y)
