@@ -66,9 +66,39 @@ __global__ void __launch_bounds__(256) k_envelope(const float *__restrict__ r, c
     }
 }
 
+// Forward pass (one channel): one block per (walker, electron) row, the el-ion distances once per block, no index divisions.
+// Same arithmetic and summation order as k_envelope.
+__global__ void __launch_bounds__(128) k_envelope_fwd(const float *__restrict__ r, const float *__restrict__ R, int N, int U, int I, int cols,
+                                                       const float *__restrict__ spa_up, const float *__restrict__ spa_dn,
+                                                       const float *__restrict__ w_up, const float *__restrict__ w_dn, float *__restrict__ mo) {
+    __shared__ float dist[64];
+    const long bi = blockIdx.x;
+    const int i = (int)(bi % N);
+    if (threadIdx.x < I) {
+        const float *ri = r + bi * 3;
+        const int J = threadIdx.x;
+        const float dx = ri[0] - R[J * 3], dy = ri[1] - R[J * 3 + 1], dz = ri[2] - R[J * 3 + 2];
+        dist[J] = sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+    __syncthreads();
+    const float *spa = i < U ? spa_up : spa_dn;
+    const float *wt = i < U ? w_up : w_dn;
+    float *p = mo + bi * (long)cols;
+    for (int col = threadIdx.x; col < cols; col += blockDim.x) {
+        float env = 0.f;
+        for (int J = 0; J < I; ++J) env = __fadd_rn(env, __fmul_rn(wt[J * cols + col], expf(-spa[J * cols + col] * dist[J])));
+        p[col] *= env;
+    }
+}
+
 int launch_envelope(dpe_model *m, const float *r, int Bc, int C, float *mo, cudaStream_t s) {
     const dpe_dims &d = m->dims;
     int cols = d.n_dets * d.n_el;
+    if (C == 1 && d.n_ion <= 64) {
+        k_envelope_fwd<<<Bc * d.n_el, 128, 0, s>>>(r, m->R_dev, d.n_el, d.n_up, d.n_ion, cols, m->sp_alpha[0], m->sp_alpha[1], m->env_w[0], m->env_w[1], mo);
+        DPE_LAUNCH_CHECK(m);
+        return DPE_OK;
+    }
     long total = (long)Bc * d.n_el * cols;
     long blocks = (total + 255) / 256;
     if (blocks > 148L * 32) blocks = 148L * 32;
