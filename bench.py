@@ -526,16 +526,24 @@ def weight_sharing_block(torch, world, dev, flush, n_geom=16, walkers=512, n_int
     vag = dpe.build_value_and_grad_func(f, gle, dpe.ClippingConfig(), with_kfac_statistics=True)
     mc = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=n_inter, initialization="gaussian"))
     rank = int(os.environ.get("RANK", 0))
-    states = [dpe.MCMCState.initialize_around_nuclei(walkers, p, "gaussian", "el_ion_mapping", dpe.PRNGKey(100 * rank + g), device=dev)
-              for g, p in enumerate(phys)]
-    clip = [dpe.init_clipping_state() for _ in phys]
     spin = (n_at // 2, n_at // 2)
+    geoms = [dpe.GeometryDataStore(idx=g, physical_config=p, spin_state=spin, fixed_params=fixed, clipping_state=dpe.init_clipping_state(),
+                                   mcmc_state=dpe.MCMCState.initialize_around_nuclei(walkers, p, "gaussian", "el_ion_mapping", dpe.PRNGKey(100 * rank + g), device=dev))
+             for g, p in enumerate(phys)]
+    ema = {m: {k: v.clone() for k, v in l.items()} for m, l in params.items()}
+    flat_p = [t for l in params.values() for t in l.values()]
+    state = {"params": params, "epoch": 0}
+
+    def sgd(p, grads, aux, lr=1e-4):          # stands in for the optimiser's update (KFAC preconditioning is outside the hot path): one multi-tensor kernel
+        torch._foreach_add_(flat_p, [grads[m][k] for m, l in p.items() for k in l], alpha=-lr)
+        return p
 
     def one_round():
         e = []
-        for g in range(n_geom):
-            states[g] = mc.run_inter_steps(f, states[g], params, spin[0], spin[1], fixed)
-            (loss, (clip[g], aux)), grads = vag(params, clip[g], spin, states[g].build_batch(fixed))
+        for _ in range(n_geom):
+            state["params"], idx, loss = dpe.shared_optimization_step(state["epoch"], geoms, f, vag, mc, state["params"], sgd, scheduling_method="round_robin",
+                                                                      permutation=list(range(n_geom)), ema_params=ema)
+            state["epoch"] += 1
             e.append(loss)
         return e
 
@@ -557,8 +565,9 @@ def weight_sharing_block(torch, world, dev, flush, n_geom=16, walkers=512, n_int
     return {"value": walkers * world * n_geom / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / n_geom, "steps": n_geom, "n_geometries": n_geom,
             "walkers_per_gpu_per_geometry": walkers, "n_inter_steps": n_inter, "gpu_launches": f.engine.launch_count() - launches0,
             "E_mean_first_last": [float(e[0]), float(e[-1])],
-            "what": "H10 chain, 16 bond lengths, one shared set of weights; step = geometry switch + 20 Metropolis steps + forward-Laplacian E_loc + "
-                    "statistics + gradient and KFAC factors (one flat all-reduce when N > 1); evals/s = walkers x geometries / time of one round"}
+            "what": "H10 chain, 16 bond lengths, one shared set of weights, round-robin schedule (shared_optimization_step); step = geometry switch + "
+                    "20 Metropolis steps + forward-Laplacian E_loc + statistics + gradient and KFAC factors (one flat all-reduce when N > 1) + an SGD "
+                    "parameter update + EMA; evals/s = walkers x geometries / time of one round"}
 
 
 def main():

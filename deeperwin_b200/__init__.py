@@ -13,8 +13,10 @@ from .hamiltonian import build_local_energy
 from .loss_function import build_total_energy, init_clipping_state
 from .mcmc import MCMCState, MetropolisHastingsMonteCarlo, PRNGKey
 from .optimization import build_value_and_grad_func
+from .shared_optimization import GeometryDataStore, get_next_geometry_index, shared_optimization_step, update_ema_params
 from .wavefunction import build_log_psi_squared
 
 __all__ = ["Configuration", "PhysicalConfig", "ModelConfigDeepErwin4", "MCMCConfigOptimization", "MCMCConfigEvaluation",
            "ClippingConfig", "build_log_psi_squared", "build_local_energy", "build_total_energy", "init_clipping_state",
-           "MCMCState", "MetropolisHastingsMonteCarlo", "PRNGKey", "build_value_and_grad_func", "RunData", "load_run", "save_run"]
+           "MCMCState", "MetropolisHastingsMonteCarlo", "PRNGKey", "build_value_and_grad_func", "RunData", "load_run", "save_run",
+           "GeometryDataStore", "get_next_geometry_index", "shared_optimization_step", "update_ema_params"]

@@ -59,3 +59,48 @@ def test_tensor_core_and_simt_paths_agree(name):
     eng.set_gemm_path(1)
     assert ((lp1 - lp0).abs() / lp0.abs()).median() < 5e-6
     assert ((e1 - e0).abs() / e0.abs().clamp_min(1.0)).median() < 3e-4
+
+
+def test_shared_optimization_loop_over_geometries():
+    """shared_optimization_step (variational_optimization.py:354-400): scheduler, Metropolis inter-steps of the chosen geometry, loss + gradient
+    on its walkers, the caller's update, EMA of the parameters, per-geometry bookkeeping."""
+    import deeperwin_b200 as dpe
+    n_at = 6
+    phys = [dpe.PhysicalConfig(name=f"HChain{n_at}_{a:.2f}", R=[[a * k, 0.0, 0.0] for k in range(n_at)], Z=[1] * n_at,
+                               n_electrons=n_at, n_up=n_at // 2, el_ion_mapping=[0, 2, 4, 1, 3, 5]) for a in np.linspace(1.6, 2.6, 3)]
+    cfg = dpe.Configuration(physical=phys[0].model_dump())
+    f, _, _, params, fixed = dpe.build_log_psi_squared(cfg.model, phys[0], None, None, rng_seed=3, device="cuda:0")
+    gle = dpe.build_local_energy(f, forward_lap=True)
+    vag = dpe.build_value_and_grad_func(f, gle, dpe.ClippingConfig())
+    mc = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=3, initialization="gaussian"))
+    geoms = [dpe.GeometryDataStore(idx=g, physical_config=p, spin_state=(3, 3), fixed_params=fixed, clipping_state=dpe.init_clipping_state(),
+                                   mcmc_state=dpe.MCMCState.initialize_around_nuclei(32, p, "gaussian", "el_ion_mapping", dpe.PRNGKey(g), device="cuda:0"))
+             for g, p in enumerate(phys)]
+    ema = {m: {k: v.clone() for k, v in l.items()} for m, l in params.items()}
+    p0 = {m: {k: v.clone() for k, v in l.items()} for m, l in params.items()}
+    seen_grads = []
+
+    def update(p, grads, aux):
+        seen_grads.append(grads)
+        return {m: {k: v - 1e-3 * grads[m][k] for k, v in l.items()} for m, l in p.items()}
+
+    order = []
+    for epoch in range(9):
+        method = "round_robin" if epoch < 6 else "stddev"
+        params, idx, loss = dpe.shared_optimization_step(epoch, geoms, f, vag, mc, params, update, scheduling_method=method, n_initial_round_robin_per_geom=2,
+                                                         permutation=[2, 0, 1], ema_params=ema, params_ema_factor=0.9)
+        order.append(idx)
+        assert torch.isfinite(loss)
+    assert order[:6] == [2, 0, 1, 2, 0, 1]
+    stds = [float(torch.sqrt(g.current_metrics["E_var"])) for g in geoms]
+    assert all(g.n_opt_epochs >= 2 for g in geoms) and sum(g.n_opt_epochs for g in geoms) == 9
+    assert int(geoms[order[-1]].mcmc_state.step_nr) == 3 * geoms[order[-1]].n_opt_epochs and geoms[order[-1]].last_epoch_optimized == 8
+    # EMA: 0.9 ema + 0.1 params after every step, started from the initial parameters
+    k = ("wf/~/input/h_ion", "embeddings")
+    e = p0[k[0]][k[1]].clone()
+    cur = p0[k[0]][k[1]].clone()
+    for gr in seen_grads:
+        cur = cur - 1e-3 * gr[k[0]][k[1]]
+        e = 0.9 * e + 0.1 * cur
+    assert torch.allclose(ema[k[0]][k[1]], e, rtol=1e-5, atol=1e-7)
+    assert len(stds) == 3 and all(np.isfinite(stds))

@@ -267,3 +267,25 @@ def test_reference_load_run_reads_a_checkpoint_written_here(ref, tmp_path):
     assert data.mcmc_state.build_batch({})[1].shape == (2, 3)                            # the reference's own method on the loaded object
     assert set(data.params) == set(params) and np.array_equal(data.params["wf/x/linear_0"]["w"], params["wf/x/linear_0"]["w"].numpy())
     assert tuple(float(x) for x in data.clipping_state) == (-8.0, 0.5) and data.metadata == dict(n_epochs=40)
+
+
+def test_geometry_scheduler_matches_the_reference(ref):
+    from types import SimpleNamespace
+    """get_next_geometry_index (utils/utils.py:704-748) of the reference vs deeperwin_b200.shared_optimization on the same records, for
+    every deterministic branch: round robin (with the permutation the shared loop always passes), the max-age override, stddev."""
+    import deeperwin_b200 as dpe
+    rng = np.random.default_rng(0)
+    n = 6
+    for trial in range(40):
+        stores_ref, stores = [], []
+        for k in range(n):
+            kw = dict(last_epoch_optimized=int(rng.integers(0, 60)), weight=1.0 / n)
+            a, b = SimpleNamespace(**kw, current_metrics={"E_var": float(rng.uniform(0.1, 2.0))}), dpe.GeometryDataStore(**kw)
+            b.current_metrics = dict(a.current_metrics)
+            stores_ref.append(a); stores.append(b)
+        perm = list(rng.permutation(n))
+        n_epoch = int(rng.integers(0, 90))
+        for method, max_age, n_rr in (("round_robin", None, 10), ("stddev", None, 2), ("stddev", 12, 0), ("stddev", 500, 0)):
+            want = int(ref.utils.get_next_geometry_index(n_epoch, stores_ref, method, max_age, n_rr, perm))
+            got = dpe.get_next_geometry_index(n_epoch, stores, method, max_age, n_rr, perm)
+            assert got == want, (trial, method, max_age, n_rr, n_epoch)
