@@ -1,0 +1,29 @@
+"""A small pass through every kernel family for compute-sanitizer (memcheck / racecheck): E_loc + forward on LiH / N2 / ethene (N > 16 path),
+Metropolis steps with every proposal, gradient + KFAC pass, TAO head, XLA shim is covered by its own test."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+import deeperwin_b200 as dpe
+
+small = dict(embedding=dict(n_iterations=2, n_hidden_one_el=[16, 16], n_hidden_two_el=[4], n_hidden_el_ions=[4], emb_dim=8), orbitals=dict(n_determinants=3))
+for mol, B, model_kw in (("LiH", 8, {}), ("N2", 6, {}), ("Ethene", 3, small), ("Benzene", 2, small)):
+    cfg = dpe.Configuration(physical=dict(name=mol), model=model_kw)
+    phys = cfg.physical
+    f, _, _, params, fixed = dpe.build_log_psi_squared(cfg.model, phys, None, None, rng_seed=1, device="cuda:0")
+    gle = dpe.build_local_energy(f, forward_lap=True)
+    st = dpe.MCMCState.initialize_around_nuclei(B, phys, "exponential", "el_ion_mapping", dpe.PRNGKey(3), device="cuda:0")
+    for prop in ("normal", "cauchy", "normal_one_el", "local", "local_one_el", "langevin"):
+        mc = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=2, proposal=dict(name=prop)))
+        for _ in range(3):                                   # third call replays the captured graph
+            st = mc.run_inter_steps(f, st, params, phys.n_up, phys.n_dn, fixed)
+    e = gle(params, (phys.n_up, phys.n_dn), *st.build_batch(fixed))
+    vag = dpe.build_value_and_grad_func(f, gle, dpe.ClippingConfig(), with_kfac_statistics=True)
+    (loss, (cs, aux)), grads = vag(params, dpe.init_clipping_state(), (phys.n_up, phys.n_dn), st.build_batch(fixed))
+    for path in (0, 1):
+        f.engine.set_gemm_path(path) if path == 0 or f.engine.lib.dpe_get_gemm_path(f.engine.handle) == 0 else None
+        f.engine.local_energy(st.r)
+    f.engine.set_gemm_path(1)
+    torch.cuda.synchronize()
+    print(mol, "E_mean", float(e.mean()), "loss", float(loss), "finite grads", all(torch.isfinite(v).all() for l in grads.values() for v in l.values()))
+print("done")
