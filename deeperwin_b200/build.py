@@ -10,7 +10,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libdpe_b200.so"
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "det_tc.cu", "streams.cu", "orbitals_det.cu", "mcmc.cu", "xla_shim.cu", "grad.cu"]
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "det_tc.cu", "streams.cu", "orbitals_det.cu", "mcmc.cu", "xla_shim.cu", "grad.cu", "pair_tc.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -106,7 +106,7 @@ int check_cuda(cudaError_t e, const char *what);
 // context, and a model lives on one device): always to the full 227 KB, so that two models with different needs cannot undercut
 // each other.
 enum KernelId { KID_PAIR1 = 0, KID_PAIR3, KID_CONV2_BIG, KID_CONV1, KID_DET64, KID_DET64F, KID_DET128, KID_GEMM_TC, KID_GEMM_TC2F,
-                KID_GEMM_TC2P, KID_GEMM_ROWS, KID_DET_TRACE, KID_MCMC_FUSED, KID_GRAD_A, KID_GRAD_B, KID_COUNT };
+                KID_GEMM_TC2P, KID_GEMM_ROWS, KID_DET_TRACE, KID_MCMC_FUSED, KID_GRAD_A, KID_GRAD_B, KID_PAIR_TC, KID_COUNT };
 constexpr int DPE_SMEM_OPTIN = 227 * 1024;
 template <typename F>
 inline int opt_in_smem(dpe_model *m, int kid, F *fn) {
@@ -187,6 +187,8 @@ int dense_gemm_seg(dpe_model *m, const float *A, int lda, const float *W, float 
                    cudaStream_t s);
 
 // mcmc.cu
+int launch_pair_stream_tc(dpe_model *m, const float *r, int Bc, float *pw_base, const size_t *pw_off, cudaStream_t s);
+float tc_rz_comp(int K);
 int launch_propose(const dpe_model *m, const dpe_mcmc_state *st, int B, const dpe_mcmc_config &cfg, int step_offset, float *r_prop, float *thr, uint32_t *new_keys,
                    float *log_q, cudaStream_t s);
 int launch_accept(const dpe_mcmc_state *st, int B, int n_el, const float *r_prop, const float *lp_prop, const float *thr,

@@ -1018,6 +1018,8 @@ static float tc_rz_compensation(int K) {
     return (float)(1.0 + b);
 }
 
+float tc_rz_comp(int K) { return tc_rz_compensation(K); }
+
 struct TcWeight {
     const float *W;      // key: the [K, N] row-major weight the SIMT path would read
     int K, N;

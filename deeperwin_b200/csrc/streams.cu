@@ -514,6 +514,11 @@ int launch_pair_stream(dpe_model *m, const float *r, int Bc, int CP, float *pw_b
     int e;
     static const bool single_pair_fwd = getenv("DPE_PAIR_FWD_SINGLE") != nullptr;     // debug: the one-pair-per-warp forward kernel
     if (CP == 1 && !single_pair_fwd) {
+        // forward pass: the tensor-core pair stream (pair_tc.cu) when the layers have its 1 -> 32 -> 32 shape and the tensor-core path is on
+        e = launch_pair_stream_tc(m, r, Bc, pw_base, pw_off, s);
+        if (e != DPE_ERR_UNSUPPORTED) return e;
+    }
+    if (CP == 1 && !single_pair_fwd) {
         constexpr int P = 4;
         const int U = d.n_up, D = d.n_el - U;
         const int n_groups = (U * (U + 1) / 2 + D * (D + 1) / 2 + P - 1) / P + (U * D + P - 1) / P;

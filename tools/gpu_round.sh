@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
-mkdir -p gpurun_out
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_paths.py > gpurun_out/memcheck.log 2>&1; echo "memcheck exit $?"; grep -E "ERROR SUMMARY|Invalid|done|E_mean" gpurun_out/memcheck.log | head -20
-timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_paths.py > gpurun_out/racecheck.log 2>&1; echo "racecheck exit $?"; grep -E "RACECHECK SUMMARY|hazard|done" gpurun_out/racecheck.log | head -20
+timeout 1500 python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -12 | cut -c1-500
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -2
