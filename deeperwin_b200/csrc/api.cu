@@ -280,8 +280,11 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
         // h_map: [rows, d_in] x [d_in, emb] -> hm, tanh rule
         {
             StageTimer t(m, ST_HMAP, s);
-            if ((e = gemm(m, plain_gemm(x[cur], ldx, p.h_map.w, d.emb_dim, hm, d.emb_dim, rows, d.emb_dim, p.d_in), s, nullptr, 0))) return e;
-            if ((e = launch_act(m, hm, d.emb_dim, Bc * N, C, d.emb_dim, p.h_map.b, nullptr, 1, s))) return e;
+            GemmArgs gh = plain_gemm(x[cur], ldx, p.h_map.w, d.emb_dim, hm, d.emb_dim, rows, d.emb_dim, p.d_in);
+            bool fused_h = false;
+            if (C == 1) { gh.epi = 1; gh.n_ch = 1; gh.bias = p.h_map.b; gh.add = nullptr; gh.groups_per_add = 1; }    // forward pass: tanh in the rows-GEMM epilogue
+            if ((e = gemm(m, gh, s, &fused_h, 0))) return e;
+            if (!fused_h && (e = launch_act(m, hm, d.emb_dim, Bc * N, C, d.emb_dim, p.h_map.b, nullptr, 1, s))) return e;
         }
         // SchNet convolutions fill columns [d_in, k_main)
         { StageTimer t(m, ST_CONV, s); if ((e = launch_conv(m, it, r, Bc, C, hm, pw + pw_off[it], ei + ei_off[it], x[cur], ldx, s))) return e; }

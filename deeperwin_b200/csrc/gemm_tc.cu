@@ -402,6 +402,7 @@ struct TrArgs {
     int M, N_out, K;
     float corr;        // accumulation-bias compensation factor, see tc_rz_compensation()
     int n_st;          // X stages (the kernel is HBM-latency bound: as many as fit next to the resident weights)
+    const float *bias; // forward pass: y = tanh(x W + bias) in the epilogue (nullptr: plain store)
 };
 
 __global__ void __launch_bounds__(TR_THREADS, 1)
@@ -525,18 +526,23 @@ k_gemm_tc_rows_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_co
             auto store_row = [&](long row, const uint32_t (&lo)[16], const uint32_t (&hi)[16]) {
                 if (row >= a.M) return;
                 float *dst = a.C + row * a.ldc + a.c_col_off;
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    o[j] = __fmul_rn(__uint_as_float(lo[j]), a.corr);
+                    o[16 + j] = __fmul_rn(__uint_as_float(hi[j]), a.corr);
+                }
+                if (a.bias) {                              // forward pass: bias + tanh here instead of a separate pass over the output
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = j < a.N_out ? tanhf(o[j] + a.bias[j]) : 0.f;
+                }
                 if (a.N_out == 32 && ((a.ldc | a.c_col_off) & 3) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(__fmul_rn(__uint_as_float(lo[4 * j]), a.corr), __fmul_rn(__uint_as_float(lo[4 * j + 1]), a.corr), __fmul_rn(__uint_as_float(lo[4 * j + 2]), a.corr), __fmul_rn(__uint_as_float(lo[4 * j + 3]), a.corr));
-                        *reinterpret_cast<float4 *>(dst + 16 + 4 * j) = make_float4(__fmul_rn(__uint_as_float(hi[4 * j]), a.corr), __fmul_rn(__uint_as_float(hi[4 * j + 1]), a.corr), __fmul_rn(__uint_as_float(hi[4 * j + 2]), a.corr), __fmul_rn(__uint_as_float(hi[4 * j + 3]), a.corr));
-                    }
+                    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (j < a.N_out) dst[j] = __fmul_rn(__uint_as_float(lo[j]), a.corr);
-                        if (16 + j < a.N_out) dst[16 + j] = __fmul_rn(__uint_as_float(hi[j]), a.corr);
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (j < a.N_out) dst[j] = o[j];
                 }
             };
             const long r0 = t * TR_ROWS + q * 32 + lane;
@@ -1264,7 +1270,10 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
 
 static int launch_gemm_tc_rows(dpe_model *m, const GemmArgs &g, const TcWeight *w, cudaStream_t s) {
     if (g.a_seg_len < g.M || g.c_seg_len < g.M || g.a_seg_off || g.c_seg_off) return DPE_ERR_UNSUPPORTED;   // plain rows only
-    if (g.K > TR_MAX_KB * TC_BK || g.epi) return DPE_ERR_UNSUPPORTED;
+    // forward pass (one channel per row group, no addend): bias + tanh in the epilogue.  (The same fusion in the wide kernels' staging epilogue
+    // was measured slower than the separate k_act pass: 256 tanh per epilogue thread and tile are exposed behind ~10 k clocks of MMAs.)
+    const bool act_fwd = g.epi == 1 && g.n_ch == 1 && !g.add && g.bias;
+    if (g.K > TR_MAX_KB * TC_BK || (g.epi && !act_fwd)) return DPE_ERR_UNSUPPORTED;
     EncodeTiledFn enc = get_encode();
     if (!enc) return DPE_ERR_UNSUPPORTED;
     CUtensorMap map_x;
@@ -1278,6 +1287,7 @@ static int launch_gemm_tc_rows(dpe_model *m, const GemmArgs &g, const TcWeight *
     TrArgs a;
     a.C = g.C; a.ldc = g.ldc; a.c_col_off = g.c_col_off; a.M = g.M; a.N_out = g.N; a.K = g.K;
     a.corr = tc_rz_compensation(g.K);
+    a.bias = act_fwd ? g.bias : nullptr;
     const int n_kb = (g.K + TC_BK - 1) / TC_BK;
     const size_t fixed = 2 * (size_t)n_kb * TR_WSLAB + 1024 + 1024;
     a.n_st = TR_STAGES;
