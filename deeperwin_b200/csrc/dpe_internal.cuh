@@ -95,6 +95,25 @@ struct dpe_model {
 };
 
 namespace dpe {
+#ifdef __CUDACC__
+// log|det| = sum_p log|pivot_p| without a double-precision log per pivot (the FP64 pipe issues one warp instruction every other clock and
+// log costs ~50 of them: 14 logs were 8x the elimination itself): the pivots are multiplied into a mantissa in [1, 2) with the binary exponent
+// tracked separately, one log at the end.
+struct LogDetAcc {
+    double mant = 1.0;
+    int ex = 0;
+    __device__ __forceinline__ void mul(double piv) {
+        mant *= fabs(piv);
+        const long long bits = __double_as_longlong(mant);
+        const int e = (int)((bits >> 52) & 0x7ff);
+        if (e != 0 && e != 0x7ff) {                    // zero / denormal / inf / nan: leave as is, the final log reports it
+            ex += e - 1023;
+            mant = __longlong_as_double((bits & ~(0x7ffLL << 52)) | (1023LL << 52));
+        }
+    }
+    __device__ __forceinline__ double value() const { return log(mant) + (double)ex * 0.69314718055994530942; }
+};
+#endif
 void mcmc_graphs_destroy(dpe_model *m);
 
 int set_error(int code, const char *fmt, ...);

@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(64) k_det_inverse(int N, int n_det, const floa
         aug[i * S + o] = o < N ? (double)mob[(long)i * cols + o] : (o - N == i ? 1.0 : 0.0);
     }
     __syncthreads();
-    double logdet = 0.0;
+    LogDetAcc logdet;
     float sign = 1.f;
     for (int p = 0; p < N; ++p) {
         if (tid < 32) {
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(64) k_det_inverse(int N, int n_det, const floa
             __syncthreads();
         }
         const double piv = aug[p * S + p];
-        logdet += log(fabs(piv));
+        logdet.mul(piv);
         if (piv < 0.0) sign = -sign;
         const double inv = 1.0 / piv;
         __syncthreads();
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(64) k_det_inverse(int N, int n_det, const floa
         }
         __syncthreads();
     }
-    if (tid == 0) { det[bd * 2] = (float)logdet; det[bd * 2 + 1] = sign; }
+    if (tid == 0) { det[bd * 2] = (float)logdet.value(); det[bd * 2 + 1] = sign; }
     for (int e = tid; e < N * N; e += 64) {
         const int q = e / N, i = e - q * N;
         ainv[bd * (long)N * N + e] = (float)aug[q * S + N + i];          // Ainv[q][i]

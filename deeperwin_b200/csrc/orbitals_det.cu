@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(T, FACTOR ? 12 : (T == 64 ? 6 : 3)) k_det(int 
         aug[i * S + o] = o < N ? (double)mob[((long)i * C) * cols + o] : ((o - N == i) ? 1.0 : 0.0);
     }
     __syncthreads();
-    double logdet = 0.0;
+    LogDetAcc logdet;
     float sign = 1.f;
     for (int p = 0; p < N; ++p) {
         // pivot search (first maximum, as LAPACK's idamax)
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(T, FACTOR ? 12 : (T == 64 ? 6 : 3)) k_det(int 
             __syncthreads();
         }
         const double piv = aug[p * S + p];
-        logdet += log(fabs(piv));
+        logdet.mul(piv);
         if (piv < 0.0) sign = -sign;
         const double inv = 1.0 / piv;
         __syncthreads();
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(T, FACTOR ? 12 : (T == 64 ? 6 : 3)) k_det(int 
         }
     }
     float *out = det + bd * (long)(LAP ? K + 3 : 2);
-    if (tid == 0) { out[0] = (float)logdet; out[1] = sign; }
+    if (tid == 0) { out[0] = (float)logdet.value(); out[1] = sign; }
     if (!LAP) return;
 
     if (FACTOR || ainv_hi) {     // factor-only mode: the tensor-core trace kernel (det_tc.cu) consumes AinvT[i][sh + q] = Ainv[q][i], tf32-split, zero padded
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(128, (LAP && !FACTOR) ? 4 : 8) k_det_warp(int 
         aug[i * 32 + lane] = v;
     }
     __syncwarp();
-    double logdet = 0.0;
+    LogDetAcc logdet;
     float sign = 1.f;
     for (int p = 0; p < N; ++p) {
         float best = (lane >= p && lane < N) ? fabsf((float)aug[lane * 32 + p]) : -1.f;
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(128, (LAP && !FACTOR) ? 4 : 8) k_det_warp(int 
             __syncwarp();
         }
         const double piv = aug[p * 32 + p];
-        logdet += log(fabs(piv));
+        logdet.mul(piv);
         if (piv < 0.0) sign = -sign;
         __syncwarp();
         if (LAP) {
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(128, (LAP && !FACTOR) ? 4 : 8) k_det_warp(int 
         __syncwarp();
     }
     float *out = det + bd * (long)(LAP ? K + 3 : 2);
-    if (lane == 0) { out[0] = (float)logdet; out[1] = sign; }
+    if (lane == 0) { out[0] = (float)logdet.value(); out[1] = sign; }
     if (!LAP) return;
 
     if (FACTOR || ainv_hi) {     // factor-only mode (see k_det)
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(128, 8) k_det_fwd_half(int N, int n_det, long 
     for (int i = 0; i < N; ++i)
         aug[i * 32 + q] = (q < N && valid) ? (double)mob[(long)i * cols + q] : (q == i ? 1.0 : 0.0);
     __syncwarp();
-    double logdet = 0.0;
+    LogDetAcc logdet;
     float sign = 1.f;
     for (int p = 0; p < N; ++p) {
         float best = (q >= p && q < N) ? fabsf((float)aug[q * 32 + p]) : -1.f;
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(128, 8) k_det_fwd_half(int N, int n_det, long 
         }
         __syncwarp();
         const double piv = aug[p * 32 + p];
-        logdet += log(fabs(piv));
+        logdet.mul(piv);
         if (piv < 0.0) sign = -sign;
         __syncwarp();
         const double rowp = aug[p * 32 + q] / piv;
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(128, 8) k_det_fwd_half(int N, int n_det, long 
         }
         __syncwarp();
     }
-    if (q == 0 && valid) { det[bd * 2] = (float)logdet; det[bd * 2 + 1] = sign; }
+    if (q == 0 && valid) { det[bd * 2] = (float)logdet.value(); det[bd * 2 + 1] = sign; }
 }
 
 int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *ainv, cudaStream_t s) {
