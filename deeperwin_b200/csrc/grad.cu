@@ -1066,12 +1066,8 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
             a.dzw[it] = fp(L.dzw[it]); a.px[it] = fp(L.px[it]); a.dzh[it] = fp(L.dzh[it]);
         }
         const size_t sm_pair = (size_t)nit * 4 * WMAT * sizeof(float), sm_eion = (size_t)nit * WMAT * sizeof(float);
-        static bool opted = false;
-        if (!opted) {
-            cudaFuncSetAttribute(k_bw_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DPE_MAX_ITER * 4 * WMAT * sizeof(float)));
-            cudaFuncSetAttribute(k_bw_eion, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DPE_MAX_ITER * WMAT * sizeof(float)));
-            opted = true;
-        }
+        if ((e = opt_in_smem(m, KID_BW_PAIR, k_bw_pair))) return e;       // per model / device, as every other kernel with more than 48 KB
+        if ((e = opt_in_smem(m, KID_BW_EION, k_bw_eion))) return e;
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u << 10) / sm_pair));
         k_bw_pair<<<(unsigned)std::min<long>((P2 * 32 + 255) / 256, 148L * per_sm), 256, sm_pair, s>>>(a);
         DPE_LAUNCH_CHECK(m);

@@ -263,19 +263,23 @@ __global__ void __launch_bounds__(T, FACTOR ? 12 : (T == 64 ? 6 : 3)) k_det(int 
                                                                   float *__restrict__ ainv_hi, float *__restrict__ ainv_lo, int NP) {
     // The factorisation runs in FP64 (O(N^3) against the O(3N * N^3) FP32 tangent stage).
     extern __shared__ double smd[];
-    const int W = LAP ? 2 * N : N;       // augmented width
+    // Gauss-Jordan IN PLACE: the identity half of [A | I] is never stored (half the FP64 work and shared memory of the augmented form);
+    // row interchanges are recorded and undone as column interchanges of the inverse, in reverse order, through the index map cidx.
+    const int W = N;
     const int S = W + 1;                 // padded row stride
     const int NQ = (N + 7) & ~7;         // rows padded to 8 floats (float4 loads), zero filled
     double *aug = smd;                   // [N][S]; after the sweep the same memory holds dA[2][N][NQ] and the tile exchange buffer
     size_t aug_b = (size_t)N * S * sizeof(double);                // must match launch_det
     {
         const size_t nbt = NQ >> 3, alias_b = (2 * (size_t)N * NQ + nbt * nbt * 64) * sizeof(float);
-        if (LAP && alias_b > aug_b) aug_b = alias_b;
+        if (LAP && !FACTOR && alias_b > aug_b) aug_b = alias_b;  // (the factor-only instantiation has no tangent stage: no alias, no AinvT)
         aug_b = (aug_b + 15) & ~(size_t)15;
     }
     float *AinvT = reinterpret_cast<float *>(reinterpret_cast<char *>(smd) + aug_b);   // [N][NQ]  AinvT[i][pos(o)] = Ainv[o][i]
-    float *red = AinvT + (LAP ? N * NQ : 0);                      // 8 floats
+    float *red = AinvT + (LAP && !FACTOR ? N * NQ : 0);           // 8 floats
     double *redd = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(red + 8) + 7) & ~uintptr_t(7));   // 8 doubles
+    double *colp = redd + 8;                                      // [N] pivot column of the current step
+    int *perm = reinterpret_cast<int *>(colp + N);                // [N] row exchanged with row p at step p; afterwards cidx
     __shared__ int piv_row;
     const int tid = threadIdx.x;
     const long bd = blockIdx.x;
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(T, FACTOR ? 12 : (T == 64 ? 6 : 3)) k_det(int 
 
     for (int e = tid; e < N * W; e += T) {
         int i = e / W, o = e - i * W;
-        aug[i * S + o] = o < N ? (double)mob[((long)i * C) * cols + o] : ((o - N == i) ? 1.0 : 0.0);
+        aug[i * S + o] = (double)mob[((long)i * C) * cols + o];
     }
     __syncthreads();
     LogDetAcc logdet;
@@ -322,14 +326,22 @@ __global__ void __launch_bounds__(T, FACTOR ? 12 : (T == 64 ? 6 : 3)) k_det(int 
         const double inv = 1.0 / piv;
         __syncthreads();
         if (LAP) {
-            // Gauss-Jordan: scale the pivot row, eliminate the column from every other row (thread = column, no divisions)
-            for (int o = tid; o < W; o += T) aug[p * S + o] *= inv;
+            // in-place Gauss-Jordan step: stash column p, scale the pivot row (its own entry becomes 1 / pivot), eliminate the column from
+            // every other row (thread = column, no divisions); column p itself receives -a_ip / pivot
+            if (tid == 0) perm[p] = pr;
+            for (int i = tid; i < N; i += T) colp[i] = aug[i * S + p];
             __syncthreads();
-            for (int o = tid; o < W; o += T) {
-                if (o == p) continue;
-                const double rp = aug[p * S + o];
-                for (int i = 0; i < N; ++i)
-                    if (i != p) aug[i * S + o] = fma(-aug[i * S + p], rp, aug[i * S + o]);
+            for (int o = tid; o < N; o += T) aug[p * S + o] = o == p ? inv : aug[p * S + o] * inv;
+            __syncthreads();
+            for (int o = tid; o < N; o += T) {
+                if (o == p) {
+                    for (int i = 0; i < N; ++i)
+                        if (i != p) aug[i * S + p] = -colp[i] * inv;
+                } else {
+                    const double rp = aug[p * S + o];
+                    for (int i = 0; i < N; ++i)
+                        if (i != p) aug[i * S + o] = fma(-colp[i], rp, aug[i * S + o]);
+                }
             }
             __syncthreads();
         } else {
@@ -343,13 +355,23 @@ __global__ void __launch_bounds__(T, FACTOR ? 12 : (T == 64 ? 6 : 3)) k_det(int 
     float *out = det + bd * (long)(LAP ? K + 3 : 2);
     if (tid == 0) { out[0] = (float)logdet.value(); out[1] = sign; }
     if (!LAP) return;
+    // Ainv = M P_{N-1} ... P_0 (M: the in-place result for the row-interchanged matrix): column i of Ainv is column cidx[i] of M
+    if (tid == 0) {
+        int *cidx = perm;                          // built in place from a local copy of the interchange list
+        int pv[64];
+        for (int k = 0; k < N; ++k) pv[k] = perm[k];
+        for (int k = 0; k < N; ++k) cidx[k] = k;
+        for (int pp = N - 1; pp >= 0; --pp) { const int t = cidx[pp]; cidx[pp] = cidx[pv[pp]]; cidx[pv[pp]] = t; }
+    }
+    __syncthreads();
+    const int *cidx = perm;
 
     if (FACTOR || ainv_hi) {     // factor-only mode: the tensor-core trace kernel (det_tc.cu) consumes AinvT[i][sh + q] = Ainv[q][i], tf32-split, zero padded
         float *oh = ainv_hi + bd * (long)NP * NP, *ol = ainv_lo + bd * (long)NP * NP;
         const int sh = (dt * N) & 3;     // the TMA box starts at the 16-byte aligned column below det * N
         for (int e = tid; e < NP * NP; e += T) {
             const int i = e / NP, q = e - i * NP - sh;
-            const float v = (i < N && q >= 0 && q < N) ? (float)aug[q * S + N + i] : 0.f;
+            const float v = (i < N && q >= 0 && q < N) ? (float)aug[q * S + cidx[i]] : 0.f;
             const float hi = det_rna_tf32(v);
             oh[e] = hi;
             ol[e] = det_rna_tf32(v - hi);
@@ -366,7 +388,7 @@ __global__ void __launch_bounds__(T, FACTOR ? 12 : (T == 64 ? 6 : 3)) k_det(int 
     __syncthreads();
     for (int e = tid; e < N * N; e += T) {
         int i = e / N, o = e - i * N;
-        AinvT[i * NPAD + pos(o)] = (float)aug[o * S + N + i];
+        AinvT[i * NPAD + pos(o)] = (float)aug[o * S + cidx[i]];
     }
     __syncthreads();                       // aug is dead from here on: its memory becomes dA[2] (double buffer) and Tx
     float *dAb = reinterpret_cast<float *>(aug);           // [2][N][NPAD]
@@ -703,11 +725,11 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *
     const bool tc = lap && ainv && NP <= 64 && m->gemm_path == 1 && !force_simt;
     float *ah = tc ? ainv : nullptr, *al = tc ? ainv + (size_t)Bc * d.n_dets * NP * NP : nullptr;
     const size_t nq = (N + 7) & ~7, nb = nq / 8;
-    size_t aug_bytes = (size_t)N * ((lap ? 2 * N : N) + 1) * sizeof(double);
+    size_t aug_bytes = (size_t)N * (N + 1) * sizeof(double);                      // in-place Gauss-Jordan: no identity half
     const size_t alias_bytes = (2 * (size_t)N * nq + nb * nb * 64) * sizeof(float);
     if (lap && aug_bytes < alias_bytes) aug_bytes = alias_bytes;
     aug_bytes = (aug_bytes + 15) & ~(size_t)15;
-    size_t smem = aug_bytes + ((lap ? (size_t)N * nq : 0) + 16) * sizeof(float) + 10 * sizeof(double);
+    size_t smem = aug_bytes + ((lap ? (size_t)N * nq : 0) + 16) * sizeof(float) + 10 * sizeof(double) + (size_t)N * (sizeof(double) + sizeof(int)) + 16;
     int blocks = Bc * d.n_dets;
     {
     StageTimer t_factor(m, ST_DET_FACTOR, s);
@@ -730,7 +752,10 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *
             if ((e = opt_in_smem(m, KID_DET64F, k_det<64, true, true>))) return e;
             if ((e = opt_in_smem(m, KID_DET128, k_det<128, false>))) return e;
         }
-        if (lap && tc) k_det<64, true, true><<<blocks, 64, smem, s>>>(N, C, d.n_dets, mo, det, ah, al, NP);
+        // factor-only: just the N x (N + 1) FP64 matrix, the pivot column and the interchange list
+        const size_t smem_f = (((size_t)N * (N + 1) * sizeof(double) + 15) & ~(size_t)15) + 16 * sizeof(float) + 10 * sizeof(double) +
+                              (size_t)N * (sizeof(double) + sizeof(int)) + 16;
+        if (lap && tc) k_det<64, true, true><<<blocks, 64, smem_f, s>>>(N, C, d.n_dets, mo, det, ah, al, NP);
         else if (lap) k_det<64, true><<<blocks, 64, smem, s>>>(N, C, d.n_dets, mo, det, ah, al, NP);
         else k_det<128, false><<<blocks, 128, smem, s>>>(N, C, d.n_dets, mo, det, nullptr, nullptr, NP);
     }
