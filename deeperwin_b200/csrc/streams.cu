@@ -16,31 +16,33 @@ __device__ __forceinline__ float tanh_f32(float x) { return tanhf(x); }
 // ------------------------------------------------------------------------------------------------
 // features: h_one^0 = reshape([dist_eI, diff_eI]) with tangents, plus E_pot
 // ------------------------------------------------------------------------------------------------
-__global__ void k_features(const float *__restrict__ r, const float *__restrict__ R, int Bc, int N, int I, int C,
-                           float *__restrict__ x0, int ldx) {
-    const int d0 = 4 * I;
-    const long total = (long)Bc * N * C * d0;
-    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        int col = idx % d0;
-        long row = idx / d0;            // (b*N + i)*C + c
-        int c = row % C;
-        long bi = row / C;
-        int i = bi % N;
-        int J = col >> 2, q = col & 3;
+// One block per (walker, electron): the el-ion distances and differences once per block, then the C x 4I entries of the electron's rows with
+// 32-bit index arithmetic (the first version spent ~100 instructions of 64-bit divisions per 4-byte store).
+__global__ void __launch_bounds__(128) k_features(const float *__restrict__ r, const float *__restrict__ R, int N, int I, int C,
+                                                   float *__restrict__ x0, int ldx) {
+    extern __shared__ float fs[];                  // [I][4]: d, dx, dy, dz
+    const long bi = blockIdx.x;                    // b * N + i
+    const int i = (int)(bi % N);
+    for (int J = threadIdx.x; J < I; J += blockDim.x) {
         const float *ri = r + bi * 3;
-        float dx = ri[0] - R[J * 3 + 0], dy = ri[1] - R[J * 3 + 1], dz = ri[2] - R[J * 3 + 2];
-        float d = sqrtf(dx * dx + dy * dy + dz * dz);
-        float diff[3] = {dx, dy, dz};
+        const float dx = ri[0] - R[J * 3 + 0], dy = ri[1] - R[J * 3 + 1], dz = ri[2] - R[J * 3 + 2];
+        fs[J * 4] = sqrtf(dx * dx + dy * dy + dz * dz);
+        fs[J * 4 + 1] = dx; fs[J * 4 + 2] = dy; fs[J * 4 + 3] = dz;
+    }
+    __syncthreads();
+    const int d0 = 4 * I, own = 1 + 3 * i;
+    float *xb = x0 + bi * (long)C * ldx;
+    for (int t = threadIdx.x; t < C * d0; t += blockDim.x) {
+        const int c = t / d0, col = t - c * d0, J = col >> 2, q = col & 3;
+        const float d = fs[J * 4];
         float v = 0.f;
-        if (c == 0) {
-            v = (q == 0) ? d : diff[q - 1];
-        } else if (c == C - 1) {
-            v = (q == 0) ? 2.0f / d : 0.f;
-        } else {
-            int k = c - 1, e = k / 3, a = k - 3 * e;
-            if (e == i) v = (q == 0) ? diff[a] / d : ((q - 1 == a) ? 1.f : 0.f);
+        if (c == 0) v = fs[J * 4 + q];                                  // (d, dx, dy, dz)
+        else if (c == C - 1) v = q == 0 ? 2.0f / d : 0.f;               // Laplacian of |r - R|
+        else if (c >= own && c < own + 3) {                              // tangent of this electron's own coordinate a
+            const int a = c - own;
+            v = q == 0 ? fs[J * 4 + 1 + a] / d : (q - 1 == a ? 1.f : 0.f);
         }
-        x0[row * ldx + col] = v;
+        xb[(long)c * ldx + col] = v;
     }
 }
 
@@ -74,9 +76,7 @@ __global__ void k_epot(const float *__restrict__ r, const float *__restrict__ R,
 
 int launch_features(dpe_model *m, const float *r, int Bc, int C, float *x0, int ldx, float *epot, cudaStream_t s) {
     const dpe_dims &d = m->dims;
-    long total = (long)Bc * d.n_el * C * 4 * d.n_ion;
-    int blocks = (int)((total + 255) / 256 < 148L * 64 ? (total + 255) / 256 : 148L * 64);
-    k_features<<<blocks, 256, 0, s>>>(r, m->R_dev, Bc, d.n_el, d.n_ion, C, x0, ldx);
+    k_features<<<Bc * d.n_el, 128, (size_t)d.n_ion * 4 * sizeof(float), s>>>(r, m->R_dev, d.n_el, d.n_ion, C, x0, ldx);
     DPE_LAUNCH_CHECK(m);
     if (epot) {
         k_epot<<<(Bc * 32 + 255) / 256, 256, 0, s>>>(r, m->R_dev, m->Z_dev, Bc, d.n_el, d.n_ion, m->eii_dev, epot);
