@@ -382,18 +382,24 @@ static int atb(GradCtx &g, float *out, long ldc, const float *A, long lda, int M
 
 // ------------------------------------------------------------------------------------------------ determinants: inverse
 // FP64 Gauss-Jordan with partial pivoting, one block per (walker, determinant): Ainv [N, N] (FP32), log|det|, sign.
-__global__ void __launch_bounds__(64) k_det_inverse(int N, int n_det, const float *__restrict__ mo, float *__restrict__ det, float *__restrict__ ainv) {
-    extern __shared__ double aug[];          // [N][2N + 1]
+template <int T>
+__global__ void __launch_bounds__(T) k_det_inverse(int N, int n_det, const float *__restrict__ mo, float *__restrict__ det, float *__restrict__ ainv) {
+    // in place (no identity half), row interchanges undone as column interchanges in reverse order -- as k_det in orbitals_det.cu.
+    // T = 32 (N <= 32): one warp per matrix, warp-level synchronisation only.
+    extern __shared__ double aug[];          // [N][N + 1], then colp[N], then perm[N]
     __shared__ int piv_row;
-    const int W = 2 * N, S = W + 1, tid = threadIdx.x;
+    const int S = N + 1, tid = threadIdx.x;
+    double *colp = aug + N * S;
+    int *perm = reinterpret_cast<int *>(colp + N);
+    auto sync = [] { if (T == 32) __syncwarp(); else __syncthreads(); };
     const long bd = blockIdx.x, b = bd / n_det;
     const int dt = (int)(bd - b * n_det), cols = n_det * N;
     const float *mob = mo + b * (long)N * cols + (long)dt * N;
-    for (int e = tid; e < N * W; e += 64) {
-        const int i = e / W, o = e - i * W;
-        aug[i * S + o] = o < N ? (double)mob[(long)i * cols + o] : (o - N == i ? 1.0 : 0.0);
+    for (int e = tid; e < N * N; e += T) {
+        const int i = e / N, o = e - i * N;
+        aug[i * S + o] = (double)mob[(long)i * cols + o];
     }
-    __syncthreads();
+    sync();
     LogDetAcc logdet;
     float sign = 1.f;
     for (int p = 0; p < N; ++p) {
@@ -405,34 +411,46 @@ __global__ void __launch_bounds__(64) k_det_inverse(int N, int n_det, const floa
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
-            if (tid == 0) piv_row = bi;
+            if (tid == 0) { piv_row = bi; perm[p] = bi; }
         }
-        __syncthreads();
+        sync();
         const int pr = piv_row;
         if (pr != p) {
-            for (int o = tid; o < W; o += 64) { const double t = aug[p * S + o]; aug[p * S + o] = aug[pr * S + o]; aug[pr * S + o] = t; }
+            for (int o = tid; o < N; o += T) { const double t = aug[p * S + o]; aug[p * S + o] = aug[pr * S + o]; aug[pr * S + o] = t; }
             sign = -sign;
-            __syncthreads();
+            sync();
         }
         const double piv = aug[p * S + p];
         logdet.mul(piv);
         if (piv < 0.0) sign = -sign;
         const double inv = 1.0 / piv;
-        __syncthreads();
-        for (int o = tid; o < W; o += 64) aug[p * S + o] *= inv;
-        __syncthreads();
-        for (int o = tid; o < W; o += 64) {
-            if (o == p) continue;
-            const double rp = aug[p * S + o];
-            for (int i = 0; i < N; ++i)
-                if (i != p) aug[i * S + o] = fma(-aug[i * S + p], rp, aug[i * S + o]);
+        for (int i = tid; i < N; i += T) colp[i] = aug[i * S + p];
+        sync();
+        for (int o = tid; o < N; o += T) aug[p * S + o] = o == p ? inv : aug[p * S + o] * inv;
+        sync();
+        for (int o = tid; o < N; o += T) {
+            if (o == p) {
+                for (int i = 0; i < N; ++i)
+                    if (i != p) aug[i * S + p] = -colp[i] * inv;
+            } else {
+                const double rp = aug[p * S + o];
+                for (int i = 0; i < N; ++i)
+                    if (i != p) aug[i * S + o] = fma(-colp[i], rp, aug[i * S + o]);
+            }
         }
-        __syncthreads();
+        sync();
     }
-    if (tid == 0) { det[bd * 2] = (float)logdet.value(); det[bd * 2 + 1] = sign; }
-    for (int e = tid; e < N * N; e += 64) {
+    if (tid == 0) {
+        det[bd * 2] = (float)logdet.value(); det[bd * 2 + 1] = sign;
+        int pv[64];
+        for (int k = 0; k < N; ++k) pv[k] = perm[k];
+        for (int k = 0; k < N; ++k) perm[k] = k;
+        for (int pp = N - 1; pp >= 0; --pp) { const int t = perm[pp]; perm[pp] = perm[pv[pp]]; perm[pv[pp]] = t; }      // perm becomes the column index map
+    }
+    sync();
+    for (int e = tid; e < N * N; e += T) {
         const int q = e / N, i = e - q * N;
-        ainv[bd * (long)N * N + e] = (float)aug[q * S + N + i];          // Ainv[q][i]
+        ainv[bd * (long)N * N + e] = (float)aug[q * S + perm[i]];          // Ainv[q][i]
     }
 }
 
@@ -960,7 +978,11 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
         if ((e = dense_gemm_seg(m, h_last, ldx, m->bf_w[sp], bf, cols, Bc * (sp ? D : U), cols, dl, sp ? D : U, N, sp ? U : 0, s))) return e;
     DPE_CUDA(cudaMemcpyAsync(mo, bf, (size_t)R1 * cols * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if ((e = launch_envelope(m, r, Bc, 1, mo, s))) return e;
-    k_det_inverse<<<Bc * d.n_dets, 64, (size_t)N * (2 * N + 1) * sizeof(double), s>>>(N, d.n_dets, mo, fp(L.det), fp(L.ainv));
+    {
+        const size_t sm_inv = ((size_t)N * (N + 1) + N) * sizeof(double) + (size_t)N * sizeof(int) + 8;
+        if (N <= 32) k_det_inverse<32><<<Bc * d.n_dets, 32, sm_inv, s>>>(N, d.n_dets, mo, fp(L.det), fp(L.ainv));
+        else k_det_inverse<64><<<Bc * d.n_dets, 64, sm_inv, s>>>(N, d.n_dets, mo, fp(L.det), fp(L.ainv));
+    }
     DPE_LAUNCH_CHECK(m);
     k_bw_combine<<<(Bc * 32 + 127) / 128, 128, 0, s>>>(Bc, d.n_dets, fp(L.det), fp(L.coef), logpsi2);
     DPE_LAUNCH_CHECK(m);

@@ -1,6 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_properties.py tests/test_gpu_gradient.py -m gpu -q --tb=short -x 2>&1 | tail -6 | cut -c1-400
-timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-cadence --no-weight-sharing 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); s=d['secondary']
-print('N2 ms/step', round(d['ms_per_step'],3)); print('benzene', s['value'], s['ms_per_step'], s['roofline']['eloc_stages_ms'])"
+timeout 900 python -m pytest tests/test_gpu_gradient.py -m gpu -q --tb=short 2>&1 | tail -5 | cut -c1-400
+timeout 600 python tools/_grad_time.py 2>&1 | tail -4
