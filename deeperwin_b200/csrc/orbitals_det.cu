@@ -715,6 +715,79 @@ __global__ void __launch_bounds__(128, 8) k_det_fwd_half(int N, int n_det, long 
     if (q == 0 && valid) { det[bd * 2] = (float)logdet.value(); det[bd * 2 + 1] = sign; }
 }
 
+// Factor-only stage of the Laplacian pass for N <= 16 (what k_det_warp<true, true> did with one matrix per warp and the augmented [A | I]):
+// TWO matrices per warp (16 lanes each, lane = column) and Gauss-Jordan IN PLACE, so every lane works on a live column; the inverse leaves as
+// the tf32-split, zero-padded, column-shifted AinvT tile the tensor-core trace kernel consumes (see k_det).
+__global__ void __launch_bounds__(128, 8) k_det_factor_half(int N, int C, int n_det, long n_mat, const float *__restrict__ mo, float *__restrict__ det,
+                                                             float *__restrict__ ainv_hi, float *__restrict__ ainv_lo, int NP) {
+    extern __shared__ double smd[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, half = lane >> 4, q = lane & 15;
+    const long bd = (blockIdx.x * 4L + wib) * 2 + half;
+    const bool valid = bd < n_mat;
+    double *warp_base = smd + (size_t)wib * (N * 32 + 32 + 16);
+    double *aug = warp_base + half * 16;                           // this half's columns: aug[i * 32 + q]
+    double *colp = warp_base + N * 32 + half * 16;                 // [16] pivot column of the current step
+    int *cidx = reinterpret_cast<int *>(warp_base + N * 32 + 32) + half * 16;      // [16] interchange list, then the column index map
+    const long bb = valid ? bd : 0;
+    const long b = bb / n_det;
+    const int dt = (int)(bb - b * n_det);
+    const int cols = n_det * N, K = C - 2;
+    const float *mob = mo + b * (long)N * C * cols + (long)dt * N;   // element (i, c, o): mob[(i*C + c)*cols + o]
+    for (int i = 0; i < N; ++i)
+        aug[i * 32 + q] = (q < N && valid) ? (double)mob[((long)i * C) * cols + q] : (q == i ? 1.0 : 0.0);
+    __syncwarp();
+    LogDetAcc logdet;
+    float sign = 1.f;
+    for (int p = 0; p < N; ++p) {
+        float best = (q >= p && q < N) ? fabsf((float)aug[q * 32 + p]) : -1.f;
+        int bi = q;
+        for (int o = 8; o; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (q == 0) cidx[p] = bi;
+        if (bi != p) {
+            double t = aug[p * 32 + q];
+            aug[p * 32 + q] = aug[bi * 32 + q];
+            aug[bi * 32 + q] = t;
+            sign = -sign;
+        }
+        __syncwarp();
+        const double piv = aug[p * 32 + p];
+        logdet.mul(piv);
+        if (piv < 0.0) sign = -sign;
+        const double inv = 1.0 / piv;
+        colp[q] = q < N ? aug[q * 32 + p] : 0.0;                   // column p before it is overwritten
+        __syncwarp();
+        const double rp = q == p ? inv : aug[p * 32 + q] * inv;
+        if (q < N) aug[p * 32 + q] = rp;
+        for (int i = 0; i < N; ++i) {
+            if (i == p || q >= N) continue;
+            aug[i * 32 + q] = q == p ? -colp[i] * inv : fma(-colp[i], rp, aug[i * 32 + q]);
+        }
+        __syncwarp();
+    }
+    if (q == 0) {
+        if (valid) { float *out = det + bd * (long)(K + 3); out[0] = (float)logdet.value(); out[1] = sign; }
+        int pv[16];
+        for (int k = 0; k < N; ++k) pv[k] = cidx[k];
+        for (int k = 0; k < N; ++k) cidx[k] = k;
+        for (int pp = N - 1; pp >= 0; --pp) { const int t = cidx[pp]; cidx[pp] = cidx[pv[pp]]; cidx[pv[pp]] = t; }
+    }
+    __syncwarp();
+    if (!valid) return;
+    float *oh = ainv_hi + bd * (long)NP * NP, *ol = ainv_lo + bd * (long)NP * NP;
+    const int sh = (dt * N) & 3;             // the TMA box starts at the 16-byte aligned column below det * N
+    for (int e = q; e < NP * NP; e += 16) {
+        const int i = e / NP, qq = e - i * NP - sh;
+        const float v = (i < N && qq >= 0 && qq < N) ? (float)aug[qq * 32 + cidx[i]] : 0.f;
+        const float hi = det_rna_tf32(v);
+        oh[e] = hi;
+        ol[e] = det_rna_tf32(v - hi);
+    }
+}
+
 int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *ainv, cudaStream_t s) {
     const dpe_dims &d = m->dims;
     const int N = d.n_el;
@@ -736,7 +809,10 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *
     if (N <= 16 && !force_generic) {
         const size_t per_warp = ((size_t)N * 32 + ((lap && !tc) ? ((size_t)N * 16 + 2 * ((size_t)N * 16 + 16) + 2 * 272 + 8) / 2 + 2 : 0)) * sizeof(double);
         const long n_mat = (long)blocks;
-        if (lap && tc) k_det_warp<true, true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, ah, al, NP);
+        static const bool factor_single = getenv("DPE_DET_FACTOR_SINGLE") != nullptr;       // debug: one matrix per warp, augmented form
+        if (lap && tc && !factor_single)
+            k_det_factor_half<<<(int)((n_mat + 7) / 8), 128, 4 * ((size_t)N * 32 + 32 + 16) * sizeof(double), s>>>(N, C, d.n_dets, n_mat, mo, det, ah, al, NP);
+        else if (lap && tc) k_det_warp<true, true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, ah, al, NP);
         else if (lap) k_det_warp<true><<<(int)((n_mat + 3) / 4), 128, 4 * per_warp + 32, s>>>(N, C, d.n_dets, n_mat, mo, det, ah, al, NP);
         else {
             static const bool one_per_warp = getenv("DPE_DET_FWD_SINGLE") != nullptr;      // debug: one matrix per warp
