@@ -1,3 +1,4 @@
+"""Times dpe_param_gradient (gradient only / gradient + KFAC factors) on N2 x 4096 and benzene x 1024 walkers."""
 import sys, time, torch
 sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 from test_gpu_parity import make
