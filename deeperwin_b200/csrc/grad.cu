@@ -610,12 +610,14 @@ __global__ void __launch_bounds__(256) k_bw_gather(int N, int U, int d_in, int e
 // One warp per ORDERED pair (i, j); lane = feature.  Recomputes the chain x^0 = d_ij, x^{it+1} = res(tanh(x^it W_h + b), x^it) and
 // w^it = tanh(x^it W_w + b), then walks back with the cotangents dzw^it of the w layers (k_bw_conv):
 //   dx^it = dzw^it W_w^T + dzh^it W_h^T + (residual ? dx^{it+1} / sqrt 2 : 0),   dzh^it = dx^{it+1} (res ? 1/sqrt 2 : 1) (1 - t^2)
-// Outputs for the products: px[it] = x^it (layer input), dzh[it].
+// Outputs for the products: px[it] = x^it (layer input), dzh[it] and a copy of dzw[it], all three with the rows ordered class-major
+// ([walker][same-spin pair] then [walker][different-spin pair]): every product of a w_same / w_diff / h_same / h_diff layer then streams a
+// contiguous row range instead of filtering every second row away.
 struct PairBwArgs {
     const float *r;
     const float *ww[DPE_MAX_ITER][2], *wb[DPE_MAX_ITER][2], *hw[DPE_MAX_ITER][2], *hb[DPE_MAX_ITER][2];
     const float *dzw[DPE_MAX_ITER];
-    float *px[DPE_MAX_ITER], *dzh[DPE_MAX_ITER];
+    float *px[DPE_MAX_ITER], *dzh[DPE_MAX_ITER], *dzw_cm[DPE_MAX_ITER];     // written CLASS-MAJOR: [same-spin pairs of all walkers | different-spin pairs]
     int dP[DPE_MAX_ITER];
     int n_iter, N, U, emb;
     long n_pairs;
@@ -657,6 +659,10 @@ __global__ void __launch_bounds__(256) k_bw_pair(PairBwArgs a) {
     const long b = p / ((long)N * N);
     const int ij = (int)(p - b * N * N), i = ij / N, j = ij - i * N;
     const int sd = ((i < a.U) == (j < a.U)) ? 0 : 1;
+    const int U = a.U, D = N - U, n_same = U * U + D * D, n_diff = 2 * U * D;
+    const long n_walkers = a.n_pairs / ((long)N * N);
+    const long pc = sd == 0 ? b * n_same + (i < U ? i * U + j : U * U + (i - U) * D + (j - U))
+                            : n_walkers * n_same + b * n_diff + (i < U ? i * D + (j - U) : U * D + (i - U) * U + j);       // class-major row
     const float *ri = a.r + (b * N + i) * 3, *rj = a.r + (b * N + j) * 3;
     const float dx0 = rj[0] - ri[0], dy0 = rj[1] - ri[1], dz0 = rj[2] - ri[2];
     const float dist = i == j ? 0.f : sqrtf(dx0 * dx0 + dy0 * dy0 + dz0 * dz0);
@@ -665,7 +671,7 @@ __global__ void __launch_bounds__(256) k_bw_pair(PairBwArgs a) {
 #pragma unroll
     for (int it = 0; it < DPE_MAX_ITER; ++it) {
         if (it < a.n_iter) {
-            if (lane < a.dP[it]) a.px[it][p * a.dP[it] + lane] = x[it];
+            if (lane < a.dP[it]) a.px[it][pc * a.dP[it] + lane] = x[it];
             if (it + 1 < a.n_iter) {
                 const int dn = a.dP[it + 1];
                 const float z = warp_matvec(wsm + ((it * 2 + sd) * 2 + 1) * WMAT, a.dP[it], dn, x[it], lane) + (lane < dn ? a.hb[it][sd][lane] : 0.f);
@@ -679,12 +685,13 @@ __global__ void __launch_bounds__(256) k_bw_pair(PairBwArgs a) {
     for (int it = DPE_MAX_ITER - 1; it >= 0; --it) {
         if (it < a.n_iter) {
             const float dzw = lane < a.emb ? a.dzw[it][p * a.emb + lane] : 0.f;
+            if (lane < a.emb) a.dzw_cm[it][pc * a.emb + lane] = dzw;
             float dxc = warp_matvec_t(wsm + ((it * 2 + sd) * 2) * WMAT, a.dP[it], a.emb, dzw, lane);
             if (it + 1 < a.n_iter) {
                 const int dn = a.dP[it + 1];
                 const bool res = a.dP[it] == dn;
                 const float dzh = dxn * (res ? 0.70710678118654752f : 1.f) * (1.f - t[it] * t[it]);
-                if (lane < dn) a.dzh[it][p * dn + lane] = dzh;
+                if (lane < dn) a.dzh[it][pc * dn + lane] = dzh;
                 dxc += warp_matvec_t(wsm + ((it * 2 + sd) * 2 + 1) * WMAT, a.dP[it], dn, dzh, lane);
                 if (res) dxc += dxn * 0.70710678118654752f;
             }
@@ -784,7 +791,7 @@ __global__ void __launch_bounds__(256) k_bw_him(int N, int I, int dE, int F, con
 struct GradLayout {
     size_t x[DPE_MAX_ITER + 1], hm[DPE_MAX_ITER], mean[DPE_MAX_ITER], pw[DPE_MAX_ITER], ei[DPE_MAX_ITER];
     size_t add, bf, mo, det, ainv, coef, dbf, dy, dz, dx, sumdz, dmean, dzhm, dhmap, sumx;
-    size_t dzw[DPE_MAX_ITER], px[DPE_MAX_ITER], dzh[DPE_MAX_ITER], dcei[DPE_MAX_ITER], ex[DPE_MAX_ITER], dze[DPE_MAX_ITER], pei[DPE_MAX_ITER],
+    size_t dzw[DPE_MAX_ITER], dzw_cm[DPE_MAX_ITER], px[DPE_MAX_ITER], dzh[DPE_MAX_ITER], dcei[DPE_MAX_ITER], ex[DPE_MAX_ITER], dze[DPE_MAX_ITER], pei[DPE_MAX_ITER],
         dzhim[DPE_MAX_ITER];
     size_t xion, onehot, dhion, part, env_part, scr;
     size_t part_floats, total;
@@ -817,6 +824,7 @@ static void grad_plan(const dpe_dims &d, int Bc, GradLayout &L) {
         L.pw[it] = take(P2 * d.emb_dim);
         L.ei[it] = take(R1 * d_eion_in(d, it));
         L.dzw[it] = take(P2 * d.emb_dim);
+        L.dzw_cm[it] = take(P2 * d.emb_dim);
         L.px[it] = take(P2 * d_pair_in(d, it));
         L.dzh[it] = take(it + 1 < nit ? P2 * d_pair_in(d, it + 1) : 0);
         L.dcei[it] = take(R1 * d_eion_in(d, it));
@@ -1085,7 +1093,7 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
             a.dP[it] = p.dP;
             a.ww[it][0] = p.w_same.w; a.wb[it][0] = p.w_same.b; a.ww[it][1] = p.w_diff.w; a.wb[it][1] = p.w_diff.b;
             a.hw[it][0] = p.h_same.w; a.hb[it][0] = p.h_same.b; a.hw[it][1] = p.h_diff.w; a.hb[it][1] = p.h_diff.b;
-            a.dzw[it] = fp(L.dzw[it]); a.px[it] = fp(L.px[it]); a.dzh[it] = fp(L.dzh[it]);
+            a.dzw[it] = fp(L.dzw[it]); a.dzw_cm[it] = fp(L.dzw_cm[it]); a.px[it] = fp(L.px[it]); a.dzh[it] = fp(L.dzh[it]);
         }
         const size_t sm_pair = (size_t)nit * 4 * WMAT * sizeof(float), sm_eion = (size_t)nit * WMAT * sizeof(float);
         if ((e = opt_in_smem(m, KID_BW_PAIR, k_bw_pair))) return e;       // per model / device, as every other kernel with more than 48 KB
@@ -1106,24 +1114,27 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
     float *dhion = fp(L.dhion);
     for (int it = 0; it < nit; ++it) {
         const IterParams &p = m->it[it];
-        const int rpw_same = U * U + D * D, rpw_diff = 2 * U * D;
-        (void)rpw_same; (void)rpw_diff;
         for (int sd = 0; sd < 2; ++sd) {
             const Dense &wl = sd ? p.w_diff : p.w_same, &hl = sd ? p.h_diff : p.h_same;
-            // rows = ordered pairs; the class filter picks same / different spin; the per-walker cotangent index is row / N^2
-            if (grad && (e = atb(g, grad + leaf_off(wl.w), emb, fp(L.px[it]), p.dP, p.dP, true, fp(L.dzw[it]), emb, emb, P2, N * N, cot, 1.f, sd))) return e;
+            // class-major rows (k_bw_pair): the rows of this spin class are one contiguous range; rows per walker = pairs of the class
+            const int rpw = sd ? 2 * U * D : U * U + D * D;
+            const long row0 = sd ? (long)Bc * (U * U + D * D) : 0, rows_c = (long)Bc * rpw;
+            if (rows_c == 0) continue;
+            const float *px = fp(L.px[it]) + row0 * p.dP, *dzw = fp(L.dzw_cm[it]) + row0 * emb;
+            if (grad && (e = atb(g, grad + leaf_off(wl.w), emb, px, p.dP, p.dP, true, dzw, emb, emb, rows_c, rpw, cot, 1.f))) return e;
             if (kfac) {
                 const KfacLayer &k = kl[kbase[it] + sd];
-                if ((e = atb(g, kfac + k.a_off, p.dP + 1, fp(L.px[it]), p.dP, p.dP, true, fp(L.px[it]), p.dP, p.dP, P2, N * N, nullptr, 1.f, sd))) return e;
-                if ((e = atb(g, kfac + k.g_off, emb, fp(L.dzw[it]), emb, emb, false, fp(L.dzw[it]), emb, emb, P2, N * N, nullptr, 0.5f, sd))) return e;
+                if ((e = atb(g, kfac + k.a_off, p.dP + 1, px, p.dP, p.dP, true, px, p.dP, p.dP, rows_c, rpw, nullptr, 1.f))) return e;
+                if ((e = atb(g, kfac + k.g_off, emb, dzw, emb, emb, false, dzw, emb, emb, rows_c, rpw, nullptr, 0.5f))) return e;
             }
             if (it + 1 < nit) {
                 const int dn = m->it[it + 1].dP;
-                if (grad && (e = atb(g, grad + leaf_off(hl.w), dn, fp(L.px[it]), p.dP, p.dP, true, fp(L.dzh[it]), dn, dn, P2, N * N, cot, 1.f, sd))) return e;
+                const float *dzh = fp(L.dzh[it]) + row0 * dn;
+                if (grad && (e = atb(g, grad + leaf_off(hl.w), dn, px, p.dP, p.dP, true, dzh, dn, dn, rows_c, rpw, cot, 1.f))) return e;
                 if (kfac) {
                     const KfacLayer &k = kl[kbase[it] + 5 + sd];
                     // the A factor equals that of w_same / w_diff (same input rows): copied at the end (dpe_param_gradient)
-                    if ((e = atb(g, kfac + k.g_off, dn, fp(L.dzh[it]), dn, dn, false, fp(L.dzh[it]), dn, dn, P2, N * N, nullptr, 0.5f, sd))) return e;
+                    if ((e = atb(g, kfac + k.g_off, dn, dzh, dn, dn, false, dzh, dn, dn, rows_c, rpw, nullptr, 0.5f))) return e;
                 }
             }
         }

@@ -1,6 +1,4 @@
 # scratch runner for gpurun calls during development: edit, then  gpurun -- 'bash tools/gpu_round.sh'
 cd $GRAFT_REPO_ROOT
-mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -5
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -1
-timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -2 gpurun_out/bench_final.err
+timeout 900 python -m pytest tests/test_gpu_gradient.py -m gpu -q --tb=short 2>&1 | tail -5 | cut -c1-400
+timeout 600 python tools/grad_timing.py 2>&1 | tail -4
