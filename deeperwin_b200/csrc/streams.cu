@@ -551,11 +551,13 @@ __global__ void __launch_bounds__(256) k_act(float *__restrict__ z, int ld, long
     constexpr int UB = 8;
     const int w4 = width >> 2;
     const long total = n_groups * w4;
+    const bool small = total < (1L << 31);         // 32-bit index arithmetic (the forward pass does one float4 per thread: 64-bit divisions would dominate)
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const long g = idx / w4;
+        const long g = small ? (long)((unsigned)idx / (unsigned)w4) : idx / w4;
         const int f = (int)(idx - g * w4) << 2;
         float *zp = z + g * C * ld + f;
-        const float *ap = add ? add + (g / groups_per_add) * C * width + f : nullptr;
+        const long ga = small ? (long)((unsigned)g / (unsigned)groups_per_add) : g / groups_per_add;
+        const float *ap = add ? add + ga * C * width + f : nullptr;
         float4 z0 = *reinterpret_cast<const float4 *>(zp);
         if (bias) { float4 b = *reinterpret_cast<const float4 *>(bias + f); z0.x += b.x; z0.y += b.y; z0.z += b.z; z0.w += b.w; }
         if (ap) { float4 a = *reinterpret_cast<const float4 *>(ap); z0.x += a.x; z0.y += a.y; z0.z += a.z; z0.w += a.w; }
