@@ -534,6 +534,30 @@ __global__ void __launch_bounds__(128) k_bw_orbitals(int Bc, int N, int U, int I
     }
 }
 
+// Transferable-atomic-orbital head (orbitals_det.cu: k_tao_orbitals), backward of the value channel:
+//   mo[b, i, col] = sum_J g[b, i, J, col] exp(-x_s[J, col] |r_i - R_J|)   =>   dg[b, i, J, col] = dmo[b, i, col] exp(-x_s[J, col] |r_i - R_J|),
+//   dmo[b, i, (d, q)] = coef[b, d] Ainv_d[q, i].   g is overwritten by dg.  (The backflow matrix and the exponents come from the geometry cache:
+//   their cotangents belong to the geometry-only nets, which are outside this library.)
+__global__ void __launch_bounds__(256) k_bw_tao(long total, int N, int U, int I, int n_det, const float *__restrict__ r, const float *__restrict__ R,
+                                                const float *__restrict__ coef, const float *__restrict__ ainv, const float *__restrict__ ex_same,
+                                                const float *__restrict__ ex_diff, float *__restrict__ g) {
+    const int cols = n_det * N;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int col = (int)(idx % cols);
+        const long bi = idx / cols;
+        const long b = bi / N;
+        const int i = (int)(bi - b * N), dt = col / N, q = col - dt * N;
+        const float dmo = coef[b * n_det + dt] * ainv[(b * n_det + dt) * N * N + (long)q * N + i];
+        const float *ex = ((i < U) == (q < U)) ? ex_same : ex_diff;
+        const float *ri = r + bi * 3;
+        float *gp = g + bi * (long)I * cols + col;
+        for (int J = 0; J < I; ++J) {
+            const float dx = ri[0] - R[J * 3], dy = ri[1] - R[J * 3 + 1], dz = ri[2] - R[J * 3 + 2];
+            gp[(long)J * cols] = dmo * expf(-ex[(long)J * cols + col] * sqrtf(dx * dx + dy * dy + dz * dz));
+        }
+    }
+}
+
 // leaf[J, col] (+)= sum_split part[split][spin][which][J][col]
 __global__ void k_bw_env_reduce(const float *__restrict__ part, int n_split, int I, int cols, int sp, int which, float *__restrict__ out, int accumulate) {
     const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -834,7 +858,8 @@ static void grad_plan(const dpe_dims &d, int Bc, GradLayout &L) {
         L.dzhim[it] = take((size_t)Bc * I * d_eion_in(d, it));
     }
     L.add = take((size_t)Bc * max_dout);
-    L.bf = take(R1 * cols); L.mo = take(R1 * cols); L.dbf = take(R1 * cols);
+    L.bf = take(d.use_taos ? R1 * I * cols : R1 * cols);       // TAO models: the per-ion orbital pre-factors g[b, i, J, col], overwritten by their cotangents
+    L.mo = take(R1 * cols); L.dbf = take(d.use_taos ? 0 : R1 * cols);
     L.det = take((size_t)Bc * d.n_dets * 2);
     L.ainv = take((size_t)Bc * d.n_dets * N * N);
     L.coef = take((size_t)Bc * d.n_dets);
@@ -893,6 +918,7 @@ static int kfac_layers(const dpe_model *m, KfacLayer *out) {
             add("wf/fermi_net_embedding/h_el_ion_%d/linear_0", it, dE, d.n_hidden_two_el[it], 1, N * I);
         }
     }
+    if (d.use_taos) return n;          // the TAO head has no dense layer of its own (backflows come from the geometry cache)
     const int dl = d.n_hidden_one_el[d.n_iterations - 1], cols = d.n_dets * N;
     add("wf/~/orbitals/envelope_orbitals/bf_up/linear_0", 0, dl, cols, 0, U);
     add("wf/~/orbitals/envelope_orbitals/bf_dn/linear_0", 0, dl, cols, 0, D);
@@ -982,10 +1008,16 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
     }
     const int dl = d.n_hidden_one_el[nit - 1];
     float *h_last = fp(L.x[nit]), *bf = fp(L.bf), *mo = fp(L.mo);
-    for (int sp = 0; sp < 2; ++sp)
-        if ((e = dense_gemm_seg(m, h_last, ldx, m->bf_w[sp], bf, cols, Bc * (sp ? D : U), cols, dl, sp ? D : U, N, sp ? U : 0, s))) return e;
-    DPE_CUDA(cudaMemcpyAsync(mo, bf, (size_t)R1 * cols * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    if ((e = launch_envelope(m, r, Bc, 1, mo, s))) return e;
+    if (d.use_taos) {
+        // one projection against the cached backflow matrix for all electrons, then the exponential envelopes and the sum over ions
+        if ((e = dense_gemm(m, h_last, ldx, m->tao_w, bf, I * cols, (int)R1, I * cols, dl, s))) return e;
+        if ((e = launch_tao_orbitals(m, r, Bc, 1, bf, mo, s))) return e;
+    } else {
+        for (int sp = 0; sp < 2; ++sp)
+            if ((e = dense_gemm_seg(m, h_last, ldx, m->bf_w[sp], bf, cols, Bc * (sp ? D : U), cols, dl, sp ? D : U, N, sp ? U : 0, s))) return e;
+        DPE_CUDA(cudaMemcpyAsync(mo, bf, (size_t)R1 * cols * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if ((e = launch_envelope(m, r, Bc, 1, mo, s))) return e;
+    }
     {
         const size_t sm_inv = ((size_t)N * (N + 1) + N) * sizeof(double) + (size_t)N * sizeof(int) + 8;
         if (N <= 32) k_det_inverse<32><<<Bc * d.n_dets, 32, sm_inv, s>>>(N, d.n_dets, mo, fp(L.det), fp(L.ainv));
@@ -996,6 +1028,17 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
     DPE_LAUNCH_CHECK(m);
 
     // ---------------- backward: orbitals
+    int kbase[DPE_MAX_ITER], kidx_bf = 1;
+    for (int it = 0; it < nit; ++it) { kbase[it] = kidx_bf; kidx_bf += (it + 1 < nit) ? 8 : 5; }
+    float *dy = fp(L.dy);
+    if (d.use_taos) {
+        const long total = R1 * cols;
+        k_bw_tao<<<(int)std::min<long>((total + 255) / 256, 148L * 32), 256, 0, s>>>(total, N, U, I, d.n_dets, r, m->R_dev, fp(L.coef), fp(L.ainv), m->tao_ex[0],
+                                                                                   m->tao_ex[1], bf);
+        DPE_LAUNCH_CHECK(m);
+        // dh[b, i, :] = dg[b, i, :] @ W_tao^T
+        if ((e = gemm_nt(m, bf, (long)I * cols, m->tao_w, (long)I * cols, dy, ldx, R1, dl, I * cols, false, s))) return e;
+    } else {
     {
         dim3 grid((cols + 127) / 128, L.env_splits);
         k_bw_orbitals<<<grid, 128, 0, s>>>(Bc, N, U, I, d.n_dets, r, m->R_dev, fp(L.coef), fp(L.ainv), bf, m->sp_alpha[0], m->sp_alpha[1], m->alpha[0],
@@ -1011,9 +1054,7 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
             }
         }
     }
-    int kbase[DPE_MAX_ITER], kidx_bf = 1;
-    for (int it = 0; it < nit; ++it) { kbase[it] = kidx_bf; kidx_bf += (it + 1 < nit) ? 8 : 5; }
-    float *dy = fp(L.dy), *dbf = fp(L.dbf);
+    float *dbf = fp(L.dbf);
     for (int sp = 0; sp < 2; ++sp) {
         const int ns = sp ? D : U;
         const RowMap rm{ns, N, sp ? U : 0};             // the spin block of every walker
@@ -1026,6 +1067,7 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
             if ((e = atb(g, kfac + k.a_off, dl, h_last, ldx, dl, false, h_last, ldx, dl, rows, ns, nullptr, 1.f, -1, rm))) return e;
             if ((e = atb(g, kfac + k.g_off, cols, dbf, cols, cols, false, dbf, cols, cols, rows, ns, nullptr, 0.5f, -1, rm))) return e;
         }
+    }
     }
 
     // ---------------- backward: embedding iterations
@@ -1178,13 +1220,13 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
 extern "C" {
 
 int32_t dpe_kfac_layer_count(const dpe_model *m) {
-    if (!m || m->dims.use_taos) return 0;
+    if (!m) return 0;
     KfacLayer kl[8 * DPE_MAX_ITER + 4];
     return kfac_layers(m, kl);
 }
 
 int64_t dpe_kfac_floats(const dpe_model *m) {
-    if (!m || m->dims.use_taos) return 0;
+    if (!m) return 0;
     KfacLayer kl[8 * DPE_MAX_ITER + 4];
     const int n = kfac_layers(m, kl);
     return kl[n - 1].g_off + (int64_t)kl[n - 1].dout * kl[n - 1].dout;
@@ -1218,7 +1260,7 @@ int dpe_param_gradient(dpe_model *m, const float *r_dev, int32_t n_walkers, cons
                        float *log_psi_sqr_dev, void *workspace_dev, size_t workspace_bytes, void *stream) {
     if (!m || !r_dev || !workspace_dev || n_walkers <= 0 || (!grad_dev && !kfac_dev)) return set_error(DPE_ERR_ARG, "param_gradient: bad argument");
     if (grad_dev && !cotangent_dev) return set_error(DPE_ERR_ARG, "param_gradient: the gradient needs the per-walker cotangents");
-    if (m->dims.use_taos) return set_error(DPE_ERR_UNSUPPORTED, "param_gradient: transferable-atomic-orbital models are not implemented (their parameters live in the geometry nets)");
+    if (m->dims.use_taos && !m->tao_set) return set_error(DPE_ERR_STATE, "param_gradient: set_tao_cache must be called first");
     if (!m->params_set || !m->geom_set) return set_error(DPE_ERR_STATE, "set_params and set_geometry must be called first");
     const dpe_dims &d = m->dims;
     if (d.emb_dim > 32 || d.n_ion_features > 32) return set_error(DPE_ERR_UNSUPPORTED, "param_gradient: pair / ion layers wider than 32");

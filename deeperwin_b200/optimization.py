@@ -44,6 +44,7 @@ def build_value_and_grad_func(log_psi_sqr_func, get_local_energy, clipping_confi
         cot = torch.nan_to_num(diff, nan=0.0) / diff.numel()
         engine.set_params(params)
         engine.set_geometry(R, Z)
+        engine.set_tao_cache(((fixed_params or {}).get("cache") or {}).get("taos"))      # TAO models: gradient of the embedding, cache held fixed
         flat, _ = engine.param_gradient(r, cot, with_kfac=with_kfac_statistics)
         if utils.world_size() > 1:                                                  # one flat all-reduce for gradient + KFAC factors
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)

@@ -195,6 +195,8 @@ int dpe_get_mcmc_graph(const dpe_model *m);
  *        A[(din + bias)^2] = [x, 1]^T [x, 1] / B',  G[dout^2] = dy^T dy / B',  dy = (1 / sqrt 2) d log psi^2 / dy,  B' = n_walkers * rows_per_walker.
  *     The layers, their shapes and offsets: dpe_kfac_layer_count / dpe_kfac_layer (name = the haiku module of the layer);
  *   log_psi_sqr_dev[B] (may be NULL) receives log psi^2 of the same pass.
+ * TAO models (use_taos): the gradient covers the embedding leaves (the flat vector has no orbital leaves), the factor list has no orbital layers, and
+ * the geometry cache of dpe_model_set_tao_cache is held fixed (its cotangents belong to the geometry-only nets, outside this library).
  * Both outputs are sums / means over THIS device's walkers: with several GPUs the caller all-reduces the two buffers (one flat
  * all-reduce, optimizers.py:133, kfac optimizer.py:1151).  Batches larger than the workspace are processed in chunks. */
 int32_t dpe_kfac_layer_count(const dpe_model *m);

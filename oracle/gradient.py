@@ -32,18 +32,19 @@ def _leaf_params(params):
     return {m: {k: v.clone().requires_grad_(True) for k, v in l.items()} for m, l in params.items()}
 
 
-def param_gradient(params, d: om.ModelDims, r, R, Z, cotangent) -> Dict[str, Dict[str, torch.Tensor]]:
-    """d/d params of sum_b cotangent_b * log psi^2_b  (loss_function.py:143-154 with cotangent = (E_c - mean E_c) / B)."""
+def param_gradient(params, d: om.ModelDims, r, R, Z, cotangent, tao=None) -> Dict[str, Dict[str, torch.Tensor]]:
+    """d/d params of sum_b cotangent_b * log psi^2_b  (loss_function.py:143-154 with cotangent = (E_c - mean E_c) / B).
+    TAO models (`tao` = the geometry cache): the gradient with respect to the embedding parameters; the cache is held fixed."""
     p = _leaf_params(params)
-    lp = om.log_psi_sqr(p, d, r, R, Z)[1]
+    lp = om.log_psi_sqr(p, d, r, R, Z, tao)[1]
     (lp * torch.as_tensor(cotangent, dtype=lp.dtype)).sum().backward()
     return {m: {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in l.items()} for m, l in p.items()}
 
 
-def loss_gradient_from_energies(params, d, r, R, Z, E_clipped):
+def loss_gradient_from_energies(params, d, r, R, Z, E_clipped, tao=None):
     """The full gradient of total_energy for given clipped local energies (loss_function.py:143-154)."""
     E = torch.as_tensor(E_clipped, dtype=torch.float64)
-    return param_gradient(params, d, r, R, Z, (E - E.mean()) / E.numel())
+    return param_gradient(params, d, r, R, Z, (E - E.mean()) / E.numel(), tao)
 
 
 class _Recorder:
@@ -61,7 +62,7 @@ class _Recorder:
         return y
 
 
-def kfac_factors(params, d: om.ModelDims, r, R, Z):
+def kfac_factors(params, d: om.ModelDims, r, R, Z, tao=None):
     """{layer: (A, G, rows_per_walker)} of every dense layer of the dpe4 model, and the per-walker forward pass they come from."""
     rec = _Recorder()
     p = _leaf_params(params)
@@ -75,7 +76,7 @@ def kfac_factors(params, d: om.ModelDims, r, R, Z):
         onehot_b = onehot[None].expand(B, -1, -1)
         h_ion_b = onehot_b @ emb_tab                                                                                        # [B, I, F]
         h_ion_b.retain_grad()
-        lp = _log_psi_sqr_tiled(p, d, r, R, h_ion_b)
+        lp = _log_psi_sqr_tiled(p, d, r, R, h_ion_b, tao)
     finally:
         om._lin = saved
     (lp.sum() / math.sqrt(2.0)).backward()
@@ -94,7 +95,7 @@ def kfac_factors(params, d: om.ModelDims, r, R, Z):
     return out
 
 
-def _log_psi_sqr_tiled(params, d, r, R, h_ion_b):
+def _log_psi_sqr_tiled(params, d, r, R, h_ion_b, tao=None):
     """oracle.model.embedding / orbitals / sum_of_determinants with per-walker ion features h_ion_b [B, I, F]."""
     U, D, N = d.n_up, d.n_dn, d.n_el
     b = r.shape[:-2]
@@ -125,6 +126,8 @@ def _log_psi_sqr_tiled(params, d, r, R, h_ion_b):
         same = om._res(torch.tanh(om._lin(params, f"{EMB}/h_same_{it}/linear_0", same)), same)
         diff = om._res(torch.tanh(om._lin(params, f"{EMB}/h_diff_{it}/linear_0", diff)), diff)
         h_eI = om._res(torch.tanh(om._lin(params, f"{EMB}/h_el_ion_{it}/linear_0", h_eI)), h_eI)
+    if d.use_taos:
+        return om.sum_of_determinants(om.orbitals_tao(tao, d, h_one, dist_eI))[1]
     ORB = om.ORB
     p = params[ORB]
     nd = d.n_dets

@@ -86,3 +86,36 @@ def test_chunked_gradient_equals_single_pass_and_public_api():
             assert grads[m][k].shape == params[m][k].shape
             assert _rel(grads[m][k], v) < max(1e-4, 16 * floor), (m, k, _rel(grads[m][k], v), floor)
     assert abs(float(loss) - float(aux["E_mean_clipped"])) == 0.0 and "kfac" in aux and len(aux["kfac"]) == 32
+
+
+@pytest.mark.parametrize("name,B,nd", [("LiH", 16, 4), ("N2", 6, 4), ("B", 10, 3)])
+def test_tao_models_gradient_of_the_embedding_and_kfac(name, B, nd):
+    """TAO orbital head (geometry cache held fixed): gradient with respect to the embedding parameters and the Kronecker factors of the
+    embedding layers, against the fp64 oracle (autograd through oracle.model.orbitals_tao)."""
+    from oracle import gradient as og, model as om
+    phys, d, p32, p64, R, r, eng = make(name, B, n_dets=nd, use_taos=True)
+    tao32 = om.cast_tao_cache(om.make_tao_cache(d, seed=9), torch.float32)
+    tao64 = om.cast_tao_cache(tao32, torch.float64)
+    eng.set_tao_cache({k: [t.cuda() for t in v] for k, v in tao32.items()})
+    g = torch.Generator().manual_seed(6)
+    cot = (torch.randn(B, generator=g) / B).float()
+    flat, lp = eng.param_gradient(r.cuda(), cot.cuda(), with_kfac=True)
+    ref = og.param_gradient(p64, d, r.double(), R.double(), phys.Z, cot.double(), tao64)
+    ref32 = og.param_gradient(p32, d, r, R, phys.Z, cot, tao32)
+    assert all(not m.startswith("wf/~/orbitals") for m, _ in eng.leaves)          # no per-walker orbital parameters in a TAO model
+    floor = max(_rel(ref32[mod][leaf], ref[mod][leaf]) for mod, leaf in eng.leaves)
+    for (mod, leaf), (off, size, rows, cols) in zip(eng.leaves, eng.leaf_shapes):
+        err = _rel(flat[off:off + size].reshape(ref[mod][leaf].shape), ref[mod][leaf])
+        assert err < max(1e-4, 16 * floor), (mod, leaf, err, floor)
+    fac = og.kfac_factors(p64, d, r.double(), R.double(), phys.Z, tao64)
+    fac32 = og.kfac_factors(p32, d, r, R, phys.Z, tao32)
+    floor_g = max(_rel(fac32[k][1], fac[k][1]) for k in fac)
+    kf = flat[eng.n_params:]
+    layers = eng.kfac_layers()
+    assert {l[0] for l in layers} == set(fac) and not any("orbitals" in l[0] for l in layers)
+    for lname, din, dout, hb, rpw, a_off, g_off in layers:
+        A = kf[a_off:a_off + (din + hb) ** 2].reshape(din + hb, din + hb)
+        G = kf[g_off:g_off + dout * dout].reshape(dout, dout)
+        assert _rel(A, fac[lname][0]) < 1e-5, (lname, "A")
+        assert _rel(G, fac[lname][1]) < max(1e-4, 16 * floor_g), (lname, "G", _rel(G, fac[lname][1]), floor_g)
+    assert torch.allclose(lp, eng.log_psi_sqr(r.cuda())[1], rtol=2e-6, atol=0)

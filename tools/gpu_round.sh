@@ -1,4 +1,3 @@
 # scratch runner for gpurun calls during development: edit, then  gpurun -- 'bash tools/gpu_round.sh'
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_properties.py -m gpu -q --tb=short -x 2>&1 | tail -4 | cut -c1-400
-timeout 600 python tools/mcmc_timing.py N2 4096 2>&1 | grep "n_inter=20 graph=True" | tail -1
+timeout 900 python -m pytest tests/test_gpu_gradient.py -m gpu -q --tb=short 2>&1 | tail -15 | cut -c1-500
