@@ -16,6 +16,17 @@ __device__ __forceinline__ float tanh_f32(float x) { return tanhf(x); }
 // ------------------------------------------------------------------------------------------------
 // features: h_one^0 = reshape([dist_eI, diff_eI]) with tangents, plus E_pot
 // ------------------------------------------------------------------------------------------------
+// Forward pass (one channel): a handful of values per electron row, one thread per value.
+__global__ void k_features_fwd(const float *__restrict__ r, const float *__restrict__ R, int n_rows, int I, float *__restrict__ x0, int ldx) {
+    const int d0 = 4 * I;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * d0) return;
+    const int row = idx / d0, col = idx - row * d0, J = col >> 2, q = col & 3;
+    const float *ri = r + (long)row * 3;
+    const float dx = ri[0] - R[J * 3 + 0], dy = ri[1] - R[J * 3 + 1], dz = ri[2] - R[J * 3 + 2];
+    x0[(long)row * ldx + col] = q == 0 ? sqrtf(dx * dx + dy * dy + dz * dz) : (q == 1 ? dx : (q == 2 ? dy : dz));
+}
+
 // One block per (walker, electron): the el-ion distances and differences once per block, then the C x 4I entries of the electron's rows with
 // 32-bit index arithmetic (the first version spent ~100 instructions of 64-bit divisions per 4-byte store).
 __global__ void __launch_bounds__(128) k_features(const float *__restrict__ r, const float *__restrict__ R, int N, int I, int C,
@@ -76,7 +87,12 @@ __global__ void k_epot(const float *__restrict__ r, const float *__restrict__ R,
 
 int launch_features(dpe_model *m, const float *r, int Bc, int C, float *x0, int ldx, float *epot, cudaStream_t s) {
     const dpe_dims &d = m->dims;
-    k_features<<<Bc * d.n_el, 128, (size_t)d.n_ion * 4 * sizeof(float), s>>>(r, m->R_dev, d.n_el, d.n_ion, C, x0, ldx);
+    if (C == 1 && (long)Bc * d.n_el * 4 * d.n_ion < (1L << 31)) {
+        const int n = Bc * d.n_el * 4 * d.n_ion;
+        k_features_fwd<<<(n + 255) / 256, 256, 0, s>>>(r, m->R_dev, Bc * d.n_el, d.n_ion, x0, ldx);
+    } else {
+        k_features<<<Bc * d.n_el, 128, (size_t)d.n_ion * 4 * sizeof(float), s>>>(r, m->R_dev, d.n_el, d.n_ion, C, x0, ldx);
+    }
     DPE_LAUNCH_CHECK(m);
     if (epot) {
         k_epot<<<(Bc * 32 + 255) / 256, 256, 0, s>>>(r, m->R_dev, m->Z_dev, Bc, d.n_el, d.n_ion, m->eii_dev, epot);
@@ -551,13 +567,11 @@ __global__ void __launch_bounds__(256) k_act(float *__restrict__ z, int ld, long
     constexpr int UB = 8;
     const int w4 = width >> 2;
     const long total = n_groups * w4;
-    const bool small = total < (1L << 31);         // 32-bit index arithmetic (the forward pass does one float4 per thread: 64-bit divisions would dominate)
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const long g = small ? (long)((unsigned)idx / (unsigned)w4) : idx / w4;
+        const long g = idx / w4;
         const int f = (int)(idx - g * w4) << 2;
         float *zp = z + g * C * ld + f;
-        const long ga = small ? (long)((unsigned)g / (unsigned)groups_per_add) : g / groups_per_add;
-        const float *ap = add ? add + ga * C * width + f : nullptr;
+        const float *ap = add ? add + (g / groups_per_add) * C * width + f : nullptr;
         float4 z0 = *reinterpret_cast<const float4 *>(zp);
         if (bias) { float4 b = *reinterpret_cast<const float4 *>(bias + f); z0.x += b.x; z0.y += b.y; z0.z += b.z; z0.w += b.w; }
         if (ap) { float4 a = *reinterpret_cast<const float4 *>(ap); z0.x += a.x; z0.y += a.y; z0.z += a.z; z0.w += a.w; }
