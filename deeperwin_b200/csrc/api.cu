@@ -275,6 +275,7 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
     { StageTimer t(m, ST_EION, s); if ((e = launch_eion_stream(m, r, Bc, CE, ei, ei_off, s))) return e; }
     { StageTimer t(m, ST_PAIR, s); if ((e = launch_pair_stream(m, r, Bc, C > 1 ? 3 : 1, pw, pw_off, s))) return e; }
     int cur = 0;
+    bool mean_ready = false;          // the spin means of x[cur] were already formed by the previous iteration's activation kernel (forward pass)
     for (int it = 0; it < d.n_iterations; ++it) {
         const IterParams &p = m->it[it];
         // h_map: [rows, d_in] x [d_in, emb] -> hm, tanh rule
@@ -289,7 +290,8 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
         // SchNet convolutions fill columns [d_in, k_main)
         { StageTimer t(m, ST_CONV, s); if ((e = launch_conv(m, it, r, Bc, C, hm, pw + pw_off[it], ei + ei_off[it], x[cur], ldx, s))) return e; }
         // spin means and their contribution (shared by all electrons of a walker)
-        { StageTimer t(m, ST_MEAN, s); if ((e = launch_mean(m, x[cur], ldx, Bc, C, p.d_in, mean, s))) return e; }
+        if (!mean_ready) { StageTimer t(m, ST_MEAN, s); if ((e = launch_mean(m, x[cur], ldx, Bc, C, p.d_in, mean, s))) return e; }
+        mean_ready = false;
         {
             StageTimer t(m, ST_MEAN_GEMM, s);
             if ((e = gemm(m, plain_gemm(mean, 2 * p.d_in, p.w_mean, p.d_out, add, p.d_out, Bc * C, p.d_out, 2 * p.d_in), s, nullptr, 1))) return e;
@@ -305,7 +307,15 @@ static int run_chunk(dpe_model *m, const float *r, int Bc, int C, char *ws, cons
             if (fuse_act) { g.epi = 1; g.n_ch = C; g.bias = p.h_el.b; g.add = add; g.groups_per_add = N; }
             bool fused = false;
             if ((e = gemm(m, g, s, &fused, 2))) return e;
-            if (!fused && (e = launch_act(m, x[cur ^ 1], ldx, Bc * N, C, p.d_out, p.h_el.b, add, N, s))) return e;
+            if (!fused) {
+                // forward pass: the activation kernel also leaves the spin means of its output for the next iteration (no second pass over it)
+                static const bool no_act_mean = getenv("DPE_NO_ACT_MEAN") != nullptr;
+                if (C == 1 && !no_act_mean) {
+                    const bool next = it + 1 < d.n_iterations && m->it[it + 1].d_in == p.d_out;
+                    if ((e = launch_act_mean_fwd(m, x[cur ^ 1], ldx, Bc, p.d_out, p.h_el.b, add, next ? mean : nullptr, s))) return e;
+                    mean_ready = next;
+                } else if ((e = launch_act(m, x[cur ^ 1], ldx, Bc * N, C, p.d_out, p.h_el.b, add, N, s))) return e;
+            }
         }
         cur ^= 1;
     }

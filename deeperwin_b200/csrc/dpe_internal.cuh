@@ -171,6 +171,7 @@ int launch_pair_stream(dpe_model *m, const float *r, int Bc, int CP, float *pw_b
 int launch_act(dpe_model *m, float *z, int ld, int n_groups, int C, int width, const float *bias, const float *add,
                int groups_per_add, cudaStream_t s);
 int launch_mean(dpe_model *m, const float *x, int ldx, int Bc, int C, int d_in, float *mean, cudaStream_t s);
+int launch_act_mean_fwd(dpe_model *m, float *z, int ld, int Bc, int width, const float *bias, const float *add, float *mean, cudaStream_t s);
 int launch_conv(dpe_model *m, int it, const float *r, int Bc, int C, const float *hm, const float *pw, const float *ei,
                 float *x, int ldx, cudaStream_t s);
 int launch_prepare_params(dpe_model *m, cudaStream_t s);

@@ -608,6 +608,43 @@ __global__ void __launch_bounds__(256) k_act(float *__restrict__ z, int ld, long
     }
 }
 
+// Forward pass (one channel): bias + spin-mean addend + tanh of a main-layer output, in place, one block per walker -- and, from the same registers,
+// the spin means of the RESULT, which the next iteration would otherwise form with a second pass over it (k_mean).  Same summation order and
+// arithmetic as k_act + k_mean: the results are bit-identical to the two-kernel sequence.
+__global__ void __launch_bounds__(256) k_act_mean_fwd(float *__restrict__ z, int ld, int N, int U, int width, const float *__restrict__ bias,
+                                                       const float *__restrict__ add, float *__restrict__ mean) {
+    const long b = blockIdx.x;
+    constexpr int CH = 16;
+    for (int f = threadIdx.x; f < width; f += blockDim.x) {
+        const float bia = bias ? bias[f] : 0.f, ad = add ? add[b * width + f] : 0.f;
+        float up = 0.f, dn = 0.f;
+        float *zp = z + b * N * (long)ld + f;
+        for (int i0 = 0; i0 < N; i0 += CH) {
+            float v[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k)
+                if (i0 + k < N) v[k] = zp[(long)(i0 + k) * ld];
+#pragma unroll
+            for (int k = 0; k < CH; ++k)
+                if (i0 + k < N) {
+                    const float y = tanh_f32((v[k] + bia) + ad);
+                    zp[(long)(i0 + k) * ld] = y;
+                    if (i0 + k < U) up += y; else dn += y;
+                }
+        }
+        if (mean) {
+            mean[b * 2 * width + f] = up / (float)U;
+            mean[b * 2 * width + width + f] = dn / (float)(N - U);
+        }
+    }
+}
+
+int launch_act_mean_fwd(dpe_model *m, float *z, int ld, int Bc, int width, const float *bias, const float *add, float *mean, cudaStream_t s) {
+    k_act_mean_fwd<<<Bc, 256, 0, s>>>(z, ld, m->dims.n_el, m->dims.n_up, width, bias, add, mean);
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
 int launch_act(dpe_model *m, float *z, int ld, int n_groups, int C, int width, const float *bias, const float *add,
                int groups_per_add, cudaStream_t s) {
     if ((width & 3) || (ld & 3)) return set_error(DPE_ERR_UNSUPPORTED, "act: width=%d / ld=%d must be multiples of 4", width, ld);
