@@ -241,6 +241,16 @@ __device__ __forceinline__ float det_rna_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// Pivot search of a 16-lane half warp in ONE redux instruction: key = [28 high bits of |a| as an ordered integer | 15 - row], so the maximum key is
+// the largest magnitude (ties and near-ties within 2^-20: the lower row, any of them is an equally good pivot).  Lanes outside [p, N) pass key 0
+// ... except that row p itself must win when the whole column is zero: its key is at least 15 - p + 1 > 0 only if p < 15; a singular matrix gives
+// log 0 = -inf either way.
+__device__ __forceinline__ int half_warp_pivot(float mag, int q, bool candidate, int half) {
+    const unsigned key = candidate ? ((__float_as_uint(mag) & 0xfffffff0u) | (unsigned)(15 - q)) : 0u;
+    const unsigned best = __reduce_max_sync(half ? 0xffff0000u : 0x0000ffffu, key);
+    return 15 - (int)(best & 15u);
+}
+
 template <int T>
 __device__ __forceinline__ void group_sync() {
     if (T == 32) __syncwarp(); else __syncthreads();
@@ -687,13 +697,8 @@ __global__ void __launch_bounds__(128, 8) k_det_fwd_half(int N, int n_det, long 
     LogDetAcc logdet;
     float sign = 1.f;
     for (int p = 0; p < N; ++p) {
-        float best = (q >= p && q < N) ? fabsf((float)aug[q * 32 + p]) : -1.f;
-        int bi = q;
-        for (int o = 8; o; o >>= 1) {
-            float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
+        int bi = half_warp_pivot(fabsf((float)aug[q * 32 + p]), q, q >= p && q < N, half);
+        if (bi < p || bi >= N) bi = p;                               // all-zero column: keep the row (the determinant is zero anyway)
         if (bi != p) {
             double t = aug[p * 32 + q];
             aug[p * 32 + q] = aug[bi * 32 + q];
@@ -705,7 +710,7 @@ __global__ void __launch_bounds__(128, 8) k_det_fwd_half(int N, int n_det, long 
         logdet.mul(piv);
         if (piv < 0.0) sign = -sign;
         __syncwarp();
-        const double rowp = aug[p * 32 + q] / piv;
+        const double rowp = aug[p * 32 + q] * (1.0 / piv);           // one reciprocal, not a division per element
         for (int i = p + 1; i < N; ++i) {
             const double fct = aug[i * 32 + p];
             if (q > p && q < N) aug[i * 32 + q] = fma(-fct, rowp, aug[i * 32 + q]);
@@ -739,13 +744,8 @@ __global__ void __launch_bounds__(128, 8) k_det_factor_half(int N, int C, int n_
     LogDetAcc logdet;
     float sign = 1.f;
     for (int p = 0; p < N; ++p) {
-        float best = (q >= p && q < N) ? fabsf((float)aug[q * 32 + p]) : -1.f;
-        int bi = q;
-        for (int o = 8; o; o >>= 1) {
-            float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
+        int bi = half_warp_pivot(fabsf((float)aug[q * 32 + p]), q, q >= p && q < N, half);
+        if (bi < p || bi >= N) bi = p;                               // all-zero column: keep the row (the determinant is zero anyway)
         if (q == 0) cidx[p] = bi;
         if (bi != p) {
             double t = aug[p * 32 + q];
