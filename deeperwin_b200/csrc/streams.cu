@@ -132,124 +132,6 @@ __device__ __forceinline__ void warp_dense_tanh(const float *__restrict__ W, con
     }
 }
 
-struct SmallNet {         // shared-memory offsets (floats) of the per-iteration tiny layers
-    int w_off[DPE_MAX_ITER][4], b_off[DPE_MAX_ITER][4];
-    int din[DPE_MAX_ITER], dout_w[DPE_MAX_ITER], dout_h[DPE_MAX_ITER];
-    int n_iter, total;
-};
-
-// ------------------------------------------------------------------------------------------------
-// el-ion stream: h_eI^it for all iterations + conv_eI^it[b,i,:] = sum_J h_eI^it[b,i,J,:] * him^it[J,:]
-// ------------------------------------------------------------------------------------------------
-struct EionArgs {
-    const float *r, *R;
-    const float *w[DPE_MAX_ITER], *b[DPE_MAX_ITER], *him[DPE_MAX_ITER];
-    float *out[DPE_MAX_ITER];
-    int dE[DPE_MAX_ITER];
-    int n_iter, N, I, n_rows;  // n_rows = Bc*N
-};
-
-template <int CH>
-__global__ void __launch_bounds__(256) k_eion_stream(EionArgs a) {
-    extern __shared__ float smem[];
-    // stage the (n_iter-1) layer weights: [din*dout] + [dout]
-    int off = 0;
-    int w_off[DPE_MAX_ITER], b_off[DPE_MAX_ITER];
-    for (int it = 0; it + 1 < a.n_iter; ++it) {
-        w_off[it] = off; off += a.dE[it] * a.dE[it + 1];
-        b_off[it] = off; off += a.dE[it + 1];
-    }
-    for (int it = 0; it + 1 < a.n_iter; ++it) {
-        int nw = a.dE[it] * a.dE[it + 1];
-        for (int t = threadIdx.x; t < nw; t += blockDim.x) smem[w_off[it] + t] = a.w[it][t];
-        for (int t = threadIdx.x; t < a.dE[it + 1]; t += blockDim.x) smem[b_off[it] + t] = a.b[it][t];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
-    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < a.n_rows; row += gridDim.x * warps_per_block) {
-        const float *ri = a.r + (long)row * 3;
-        float rx = ri[0], ry = ri[1], rz = ri[2];
-        float acc[DPE_MAX_ITER][CH];
-#pragma unroll
-        for (int it = 0; it < DPE_MAX_ITER; ++it)
-#pragma unroll
-            for (int c = 0; c < CH; ++c) acc[it][c] = 0.f;
-        for (int J = 0; J < a.I; ++J) {
-            float dx = rx - a.R[J * 3], dy = ry - a.R[J * 3 + 1], dz = rz - a.R[J * 3 + 2];
-            float d = sqrtf(dx * dx + dy * dy + dz * dz);
-            float x[CH];
-            {   // features [d, dx, dy, dz] on lanes 0..3
-                float diff = lane == 1 ? dx : (lane == 2 ? dy : dz);
-                x[0] = lane == 0 ? d : (lane < 4 ? diff : 0.f);
-                if (CH > 1) {
-                    float inv = 1.f / d;
-                    float u[3] = {dx * inv, dy * inv, dz * inv};
-#pragma unroll
-                    for (int c = 1; c < CH - 1; ++c) x[c] = lane == 0 ? u[c - 1] : ((lane == c) ? 1.f : 0.f);
-                    x[CH - 1] = lane == 0 ? 2.f * inv : 0.f;
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < DPE_MAX_ITER; ++it) {
-                if (it < a.n_iter) {
-                    float hm = lane < a.dE[it] ? a.him[it][J * a.dE[it] + lane] : 0.f;
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) acc[it][c] = fmaf(x[c], hm, acc[it][c]);
-                    if (it + 1 < a.n_iter) {
-                        float y[CH];
-                        warp_dense_tanh<CH>(smem + w_off[it], smem + b_off[it], a.dE[it], a.dE[it + 1], x, y, lane);
-                        const bool res = a.dE[it] == a.dE[it + 1];     // mlp.py:13-16
-#pragma unroll
-                        for (int c = 0; c < CH; ++c) x[c] = res ? (x[c] + y[c]) * 0.70710678118654752f : y[c];
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < DPE_MAX_ITER; ++it) {
-            if (it < a.n_iter && lane < a.dE[it]) {
-#pragma unroll
-                for (int c = 0; c < CH; ++c) a.out[it][((long)row * CH + c) * a.dE[it] + lane] = acc[it][c];
-            }
-        }
-    }
-}
-
-int launch_eion_stream(dpe_model *m, const float *r, int Bc, int CE, float *ei_base, const size_t *ei_off, cudaStream_t s) {
-    const dpe_dims &d = m->dims;
-    EionArgs a;
-    a.r = r; a.R = m->R_dev; a.n_iter = d.n_iterations; a.N = d.n_el; a.I = d.n_ion; a.n_rows = Bc * d.n_el;
-    size_t smem = 0;
-    for (int it = 0; it < d.n_iterations; ++it) {
-        a.dE[it] = m->it[it].dE;
-        a.him[it] = m->it[it].him;
-        a.out[it] = ei_base + ei_off[it];
-        a.w[it] = m->it[it].h_el_ion.w;
-        a.b[it] = m->it[it].h_el_ion.b;
-        if (it + 1 < d.n_iterations) smem += ((size_t)m->it[it].dE * m->it[it + 1].dE + m->it[it + 1].dE) * sizeof(float);
-    }
-    int blocks = (a.n_rows + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    if (CE == 1) k_eion_stream<1><<<blocks, 256, smem, s>>>(a);
-    else k_eion_stream<5><<<blocks, 256, smem, s>>>(a);
-    DPE_LAUNCH_CHECK(m);
-    return DPE_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// pair stream: w^it[b,i,j,:] (value, d/dd, d2/dd2) for every iteration, one warp per pair
-// ------------------------------------------------------------------------------------------------
-struct PairArgs {
-    const float *r;
-    const float *ww[DPE_MAX_ITER][2], *wb[DPE_MAX_ITER][2];   // w_same / w_diff
-    const float *hw[DPE_MAX_ITER][2], *hb[DPE_MAX_ITER][2];   // h_same / h_diff
-    float *out[DPE_MAX_ITER];
-    int dP[DPE_MAX_ITER];
-    int n_iter, N, U, emb;
-    long n_pairs;  // Bc*N*N
-};
-
 // Tiny dense layer for one pair held by a warp: lane = output feature, the input vector x[c][0:din] sits in a
 // per-warp shared buffer (float4 broadcast reads), weights are staged as [k/4][n][4] (one LDS.128 per 4 k).
 template <int CH>
@@ -288,6 +170,137 @@ __device__ __forceinline__ void pair_dense_tanh(const float *__restrict__ W4, co
         y[CH - 1] = act ? d1 * z[CH - 1] - 2.f * t * d1 * ssq : 0.f;
     }
 }
+
+struct SmallNet {         // shared-memory offsets (floats) of the per-iteration tiny layers
+    int w_off[DPE_MAX_ITER][4], b_off[DPE_MAX_ITER][4];
+    int din[DPE_MAX_ITER], dout_w[DPE_MAX_ITER], dout_h[DPE_MAX_ITER];
+    int n_iter, total;
+};
+
+// ------------------------------------------------------------------------------------------------
+// el-ion stream: h_eI^it for all iterations + conv_eI^it[b,i,:] = sum_J h_eI^it[b,i,J,:] * him^it[J,:]
+// ------------------------------------------------------------------------------------------------
+struct EionArgs {
+    const float *r, *R;
+    const float *w[DPE_MAX_ITER], *b[DPE_MAX_ITER], *him[DPE_MAX_ITER];
+    float *out[DPE_MAX_ITER];
+    int dE[DPE_MAX_ITER];
+    int n_iter, N, I, n_rows;  // n_rows = Bc*N
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_eion_stream(EionArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    // stage the (n_iter-1) layer weights as [k/4][n][4] (+ bias): one LDS.128 feeds four k of a lane's output, and the layer input sits in a per-warp
+    // shared buffer read with broadcast LDS.128 (pair_dense_tanh) -- the shuffle-per-k version was bound by the SM's one shuffle per clock
+    int off = 0;
+    int w_off[DPE_MAX_ITER], b_off[DPE_MAX_ITER];
+    for (int it = 0; it + 1 < a.n_iter; ++it) {
+        const int kp = (a.dE[it] + 3) & ~3;
+        w_off[it] = off; off += kp * a.dE[it + 1];
+        b_off[it] = off; off += (a.dE[it + 1] + 3) & ~3;
+    }
+    float *xs_all = smem + off;                  // [8 warps][CH][32]
+    for (int it = 0; it + 1 < a.n_iter; ++it) {
+        const int din = a.dE[it], dout = a.dE[it + 1], kp = (din + 3) & ~3;
+        for (int t = threadIdx.x; t < kp * dout; t += blockDim.x) {
+            const int k4 = t / (dout * 4), rem = t - k4 * dout * 4, n = rem >> 2, kk = rem & 3, k = k4 * 4 + kk;
+            smem[w_off[it] + t] = k < din ? a.w[it][k * dout + n] : 0.f;
+        }
+        for (int t = threadIdx.x; t < dout; t += blockDim.x) smem[b_off[it] + t] = a.b[it][t];
+    }
+    for (int t = threadIdx.x; t < 8 * CH * 32; t += blockDim.x) xs_all[t] = 0.f;
+    __syncthreads();
+    float *xs = xs_all + (threadIdx.x >> 5) * CH * 32;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < a.n_rows; row += gridDim.x * warps_per_block) {
+        const float *ri = a.r + (long)row * 3;
+        float rx = ri[0], ry = ri[1], rz = ri[2];
+        float acc[DPE_MAX_ITER][CH];
+#pragma unroll
+        for (int it = 0; it < DPE_MAX_ITER; ++it)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) acc[it][c] = 0.f;
+        for (int J = 0; J < a.I; ++J) {
+            float dx = rx - a.R[J * 3], dy = ry - a.R[J * 3 + 1], dz = rz - a.R[J * 3 + 2];
+            float d = sqrtf(dx * dx + dy * dy + dz * dz);
+            float x[CH];
+            {   // features [d, dx, dy, dz] on lanes 0..3
+                float diff = lane == 1 ? dx : (lane == 2 ? dy : dz);
+                x[0] = lane == 0 ? d : (lane < 4 ? diff : 0.f);
+                if (CH > 1) {
+                    float inv = 1.f / d;
+                    float u[3] = {dx * inv, dy * inv, dz * inv};
+#pragma unroll
+                    for (int c = 1; c < CH - 1; ++c) x[c] = lane == 0 ? u[c - 1] : ((lane == c) ? 1.f : 0.f);
+                    x[CH - 1] = lane == 0 ? 2.f * inv : 0.f;
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < DPE_MAX_ITER; ++it) {
+                if (it < a.n_iter) {
+                    float hm = lane < a.dE[it] ? a.him[it][J * a.dE[it] + lane] : 0.f;
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) acc[it][c] = fmaf(x[c], hm, acc[it][c]);
+                    if (it + 1 < a.n_iter) {
+                        float y[CH];
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) xs[c * 32 + lane] = x[c];
+                        __syncwarp();
+                        pair_dense_tanh<CH>(smem + w_off[it], smem + b_off[it], (a.dE[it] + 3) & ~3, a.dE[it + 1], xs, y, lane);
+                        const bool res = a.dE[it] == a.dE[it + 1];     // mlp.py:13-16
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) x[c] = res ? (x[c] + y[c]) * 0.70710678118654752f : y[c];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < DPE_MAX_ITER; ++it) {
+            if (it < a.n_iter && lane < a.dE[it]) {
+#pragma unroll
+                for (int c = 0; c < CH; ++c) a.out[it][((long)row * CH + c) * a.dE[it] + lane] = acc[it][c];
+            }
+        }
+    }
+}
+
+int launch_eion_stream(dpe_model *m, const float *r, int Bc, int CE, float *ei_base, const size_t *ei_off, cudaStream_t s) {
+    const dpe_dims &d = m->dims;
+    EionArgs a;
+    a.r = r; a.R = m->R_dev; a.n_iter = d.n_iterations; a.N = d.n_el; a.I = d.n_ion; a.n_rows = Bc * d.n_el;
+    size_t smem = 0;
+    for (int it = 0; it < d.n_iterations; ++it) {
+        a.dE[it] = m->it[it].dE;
+        a.him[it] = m->it[it].him;
+        a.out[it] = ei_base + ei_off[it];
+        a.w[it] = m->it[it].h_el_ion.w;
+        a.b[it] = m->it[it].h_el_ion.b;
+        if (it + 1 < d.n_iterations) smem += ((size_t)((m->it[it].dE + 3) & ~3) * m->it[it + 1].dE + ((m->it[it + 1].dE + 3) & ~3)) * sizeof(float);
+    }
+    smem += (size_t)8 * CE * 32 * sizeof(float);          // per-warp layer-input buffers
+    int blocks = (a.n_rows + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (CE == 1) k_eion_stream<1><<<blocks, 256, smem, s>>>(a);
+    else k_eion_stream<5><<<blocks, 256, smem, s>>>(a);
+    DPE_LAUNCH_CHECK(m);
+    return DPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair stream: w^it[b,i,j,:] (value, d/dd, d2/dd2) for every iteration, one warp per pair
+// ------------------------------------------------------------------------------------------------
+struct PairArgs {
+    const float *r;
+    const float *ww[DPE_MAX_ITER][2], *wb[DPE_MAX_ITER][2];   // w_same / w_diff
+    const float *hw[DPE_MAX_ITER][2], *hb[DPE_MAX_ITER][2];   // h_same / h_diff
+    float *out[DPE_MAX_ITER];
+    int dP[DPE_MAX_ITER];
+    int n_iter, N, U, emb;
+    long n_pairs;  // Bc*N*N
+};
 
 // One warp per UNORDERED electron pair (i <= j): w(i,j) = w(j,i) because both orderings see the same distance and the
 // same (same-spin / different-spin) weights (ferminet_embedding.py:197-205: diff = concat(ud, du) through one MLP).
