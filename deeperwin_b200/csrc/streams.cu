@@ -102,36 +102,6 @@ int launch_features(dpe_model *m, const float *r, int Bc, int C, float *x0, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// warp-wide tiny dense layer: lane = output feature; x[c] holds input feature `lane` of channel c
-// ------------------------------------------------------------------------------------------------
-template <int CH>
-__device__ __forceinline__ void warp_dense_tanh(const float *__restrict__ W, const float *__restrict__ bias, int din,
-                                                int dout, const float (&x)[CH], float (&y)[CH], int lane) {
-    float z[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) z[c] = 0.f;
-    const bool act = lane < dout;
-    for (int k = 0; k < din; ++k) {
-        float w = act ? W[k * dout + lane] : 0.f;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) z[c] = fmaf(__shfl_sync(0xffffffffu, x[c], k), w, z[c]);
-    }
-    if (act) z[0] += bias[lane];
-    // tanh rule: channels 1..CH-2 tangents, CH-1 Laplacian (CH == 1: value only)
-    float t = tanh_f32(z[0]);
-    float d1 = 1.f - t * t;
-    y[0] = act ? t : 0.f;
-    if (CH > 1) {
-        float ssq = 0.f;
-#pragma unroll
-        for (int c = 1; c < CH - 1; ++c) {
-            ssq = fmaf(z[c], z[c], ssq);
-            y[c] = act ? d1 * z[c] : 0.f;
-        }
-        y[CH - 1] = act ? d1 * z[CH - 1] - 2.f * t * d1 * ssq : 0.f;
-    }
-}
-
 // Tiny dense layer for one pair held by a warp: lane = output feature, the input vector x[c][0:din] sits in a
 // per-warp shared buffer (float4 broadcast reads), weights are staged as [k/4][n][4] (one LDS.128 per 4 k).
 template <int CH>
