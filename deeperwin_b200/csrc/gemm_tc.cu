@@ -1144,6 +1144,13 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
         const int tiles_min = (seg_len + 255) / 256;
         a.nmma = (((seg_len + tiles_min - 1) / tiles_min) + 15) / 16 * 16;
         if (a.nmma > 256) a.nmma = 256;
+        // few rows (the spin-mean term of a forward pass: one row per walker): narrower row tiles until about half the SMs have one -- the
+        // tile's MMAs, not the weight loads, are what a lone CTA waits for (per-element arithmetic does not depend on the tile shape)
+        static const bool no_small_tiles = getenv("DPE_TC_NO_SMALL_TILES") != nullptr;
+        if (n_seg == 1 && !no_small_tiles) {
+            const long n_ft0 = (g.N + TC_FEAT - 1) / TC_FEAT;
+            while (a.nmma > 32 && ((seg_len + a.nmma - 1) / a.nmma) * n_ft0 * 2 <= m->n_sm) a.nmma = (a.nmma / 2 + 15) / 16 * 16;
+        }
         a.tile_rows = a.nmma;
         a.n_rt = (seg_len + a.nmma - 1) / a.nmma;
     }
