@@ -584,7 +584,7 @@ int dpe_local_energy(dpe_model *m, const float *r_dev, int32_t n_walkers, float 
 }
 
 // ---- Metropolis steps ------------------------------------------------------------------------------------------------------------
-// One step = propose, network forward pass (~110 small launches), accept (+ controller).  A call that REPEATS an earlier call exactly
+// One step = propose, network forward pass (~30 small launches), accept (+ controller).  A call that REPEATS an earlier call exactly
 // (same state / count / workspace pointers, sizes, config and kernel-path settings -- the inter-step loop of a run) is replayed from a CUDA
 // graph captured on its second occurrence: every launch argument is then identical by construction (the step number, step size and RNG keys
 // live in device memory), and the per-launch CPU + front-end cost disappears.  First occurrences and non-repeating calls launch eagerly.

@@ -1,8 +1,8 @@
 # scratch runner for gpurun calls during development: edit, then  gpurun -- 'bash tools/gpu_round.sh'
 cd $GRAFT_REPO_ROOT
-mkdir -p gpurun_out/r02
-O=gpurun_out/r02
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc_rows -s 5 -c 2 -o $O/rows -f python tools/profile_step.py N2 4096 eloc > /dev/null 2>&1
-ncu -i $O/rows.ncu-rep --page raw --csv > $O/rows.raw.csv 2>/dev/null
-ncu -i $O/rows.ncu-rep --page source --csv --print-source sass --launch-skip 1 --launch-count 1 > $O/rows.sass.csv 2>/dev/null
-rm -f $O/rows.ncu-rep
+mkdir -p gpurun_out
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -2 gpurun_out/bench_final.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/bench_final.json').read().strip().splitlines()[-1]); r=d['roofline']
+print(d['value'], d['ms_per_step'], r['frac'], r['frac_sustained'], r['peak'], r['peak_sustained'], sorted(d.keys()))"
