@@ -26,4 +26,23 @@ for mol, B, model_kw in (("LiH", 8, {}), ("N2", 6, {}), ("Ethene", 3, small), ("
     f.engine.set_gemm_path(1)
     torch.cuda.synchronize()
     print(mol, "E_mean", float(e.mean()), "loss", float(loss), "finite grads", all(torch.isfinite(v).all() for l in grads.values() for v in l.values()))
+# TAO orbital head (geometry cache = random stand-ins of the right shapes): forward, E_loc, gradient of the embedding
+import math
+cfg = dpe.Configuration(physical=dict(name="LiH"), model=dict(orbitals=dict(envelope_orbitals=None, transferable_atomic_orbitals=dict(name="taos"), n_determinants=4)))
+phys = cfg.physical
+f, _, _, params, fixed = dpe.build_log_psi_squared(cfg.model, phys, None, None, rng_seed=1, device="cuda:0")
+emb = cfg.model.embedding.n_hidden_one_el[-1]
+g = torch.Generator().manual_seed(3)
+tao = {"backflows": [(torch.randn(len(phys.Z), n, 2, 4, emb, generator=g) / math.sqrt(emb)).cuda() for n in (phys.n_up, phys.n_dn)],
+       "exponents": [(0.5 + torch.rand(len(phys.Z), n, 2, 4, generator=g)).cuda() for n in (phys.n_up, phys.n_dn)]}
+fixed = dict(fixed or {}, cache=dict(taos=tao))
+st = dpe.MCMCState.initialize_around_nuclei(8, phys, "gaussian", "el_ion_mapping", dpe.PRNGKey(3), device="cuda:0")
+mc = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=2))
+for _ in range(3):
+    st = mc.run_inter_steps(f, st, params, phys.n_up, phys.n_dn, fixed)
+gle = dpe.build_local_energy(f, forward_lap=True)
+vag = dpe.build_value_and_grad_func(f, gle, dpe.ClippingConfig(), with_kfac_statistics=True)
+(loss, _), grads = vag(params, dpe.init_clipping_state(), (phys.n_up, phys.n_dn), st.build_batch(fixed))
+torch.cuda.synchronize()
+print("LiH TAO loss", float(loss), "finite grads", all(torch.isfinite(v).all() for l in grads.values() for v in l.values()))
 print("done")
