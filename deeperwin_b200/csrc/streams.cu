@@ -767,14 +767,20 @@ __global__ void __launch_bounds__(MAXT, MINB) k_conv_dense2(int N, int C, int CP
     const long b = blockIdx.x / n_fg;
     const int f0 = fg * CV_FG;
     const int tid = threadIdx.x, f = tid & (CV_FG - 1), c = tid >> 3;       // blockDim.x = 8 * C
-    for (int j = 0; j < N; ++j)
-        B_s[(j * C + c) * CV_FG + f] = hm[((b * N + j) * (long)C + c) * emb + f0 + f];
+    static_assert(CV_FG == 8, "the float4 staging below assumes 8 features per block");
+    for (int t = tid; t < N * C * 2; t += blockDim.x) {                   // 16-byte staging loads (two float4 per row of 8 features)
+        const int row = t >> 1, hq = (t & 1) * 4;                           // row = j * C + c
+        *reinterpret_cast<float4 *>(B_s + row * CV_FG + hq) = *reinterpret_cast<const float4 *>(hm + (b * N * C + row) * (long)emb + f0 + hq);
+    }
     for (int i0 = 0; i0 < N; i0 += 16) {
         const int ni = min(16, N - i0);
         __syncthreads();                           // previous i block consumed (and, first time, nothing)
-        for (int t = tid; t < N * CV2_NP * CV_FG; t += blockDim.x) {      // ff fastest: 8 threads share one 32-byte sector of pw
-            const int ff = t & (CV_FG - 1), ji = t >> 3, i = ji % CV2_NP, j = ji / CV2_NP;
-            A_s[(j * CV_FG + ff) * CV2_NP + i] = i < ni ? pw[(((b * N + i0 + i) * N) + j) * (long)CP * emb + f0 + ff] : 0.f;
+        for (int t = tid; t < N * CV2_NP * 2; t += blockDim.x) {           // one float4 of w per thread, transposed into A_s[j][f][i]
+            const int hq = (t & 1) * 4, i = (t >> 1) % CV2_NP, j = (t >> 1) / CV2_NP;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < ni) v = *reinterpret_cast<const float4 *>(pw + (((b * N + i0 + i) * N) + j) * (long)CP * emb + f0 + hq);
+            float *dst = A_s + (j * CV_FG + hq) * CV2_NP + i;
+            dst[0] = v.x; dst[CV2_NP] = v.y; dst[2 * CV2_NP] = v.z; dst[3 * CV2_NP] = v.w;
         }
         __syncthreads();
         float acc[16];
