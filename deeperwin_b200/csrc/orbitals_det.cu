@@ -833,7 +833,14 @@ int launch_det(dpe_model *m, int Bc, int C, const float *mo, float *det, float *
                               (size_t)N * (sizeof(double) + sizeof(int)) + 16;
         if (lap && tc) k_det<64, true, true><<<blocks, 64, smem_f, s>>>(N, C, d.n_dets, mo, det, ah, al, NP);
         else if (lap) k_det<64, true><<<blocks, 64, smem, s>>>(N, C, d.n_dets, mo, det, ah, al, NP);
-        else k_det<128, false><<<blocks, 128, smem, s>>>(N, C, d.n_dets, mo, det, nullptr, nullptr, NP);
+        else {
+            // forward pass: at most N - 1 <= 63 columns are live per pivot -- two warps per matrix, and only the N x (N + 1) matrix in shared memory
+            static const bool wide_fwd = getenv("DPE_DET_FWD_128") != nullptr;
+            const size_t smem_fw = (((size_t)N * (N + 1) * sizeof(double) + 15) & ~(size_t)15) + 16 * sizeof(float) + 10 * sizeof(double) +
+                                   (size_t)N * (sizeof(double) + sizeof(int)) + 16;
+            if (wide_fwd) k_det<128, false><<<blocks, 128, smem, s>>>(N, C, d.n_dets, mo, det, nullptr, nullptr, NP);
+            else k_det<64, false><<<blocks, 64, smem_fw, s>>>(N, C, d.n_dets, mo, det, nullptr, nullptr, NP);
+        }
     }
     DPE_LAUNCH_CHECK(m);
     }
