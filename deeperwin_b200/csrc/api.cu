@@ -242,6 +242,20 @@ static GemmArgs plain_gemm(const float *A, int lda, const float *W, int ldw, flo
 int dense_gemm(dpe_model *m, const float *A, int lda, const float *W, float *Cc, int ldc, int M, int N, int K, cudaStream_t s) {
     return gemm(m, plain_gemm(A, lda, W, N, Cc, ldc, M, N, K), s);
 }
+// C = A W^T with the layer's own weight W [N, K] (registered with tr): the backward data products of the gradient pass
+int dense_gemm_t(dpe_model *m, const float *A, int lda, const float *W, float *Cc, int ldc, int M, int N, int K, int seg_len, int seg_stride, int seg_off,
+                 cudaStream_t s) {
+    static const bool off = getenv("DPE_GEMM_NT_TC") && atoi(getenv("DPE_GEMM_NT_TC")) == 0;
+    if (off || m->gemm_path != 1) return DPE_ERR_UNSUPPORTED;
+    GemmArgs g = plain_gemm(A, lda, W, K, Cc, ldc, M, N, K);
+    g.w_tr = 1;
+    if (seg_len > 0) {
+        g.a_seg_len = g.c_seg_len = seg_len;
+        g.a_seg_stride = g.c_seg_stride = seg_stride;
+        g.a_seg_off = g.c_seg_off = seg_off;
+    }
+    return launch_gemm_tc(m, g, s);
+}
 // ... on the row segment [seg_off, seg_off + seg_len) of every block of seg_stride rows (the spin block of a walker)
 int dense_gemm_seg(dpe_model *m, const float *A, int lda, const float *W, float *Cc, int ldc, int M, int N, int K, int seg_len, int seg_stride, int seg_off,
                    cudaStream_t s) {
@@ -439,10 +453,14 @@ int dpe_model_create(const dpe_dims *dims, dpe_model **out) {
             e = tc_register_weight(m, m->it[it].w_main, m->it[it].k_main, m->it[it].d_out);
             if (!e) e = tc_register_weight(m, m->it[it].w_mean, 2 * m->it[it].d_in, m->it[it].d_out);
             if (!e && m->it[it].d_in <= 320) e = tc_register_weight(m, m->it[it].h_map.w, m->it[it].d_in, dims->emb_dim);
+            if (!e) e = tc_register_weight(m, m->it[it].w_main, m->it[it].d_out, m->it[it].k_main, true);       // gradient pass: dx = dz W^T
         }
         const int cols = dims->n_dets * dims->n_el, dl = dims->n_hidden_one_el[dims->n_iterations - 1];
         if (dims->use_taos) { if (!e) e = tc_register_weight(m, m->tao_w, dl, dims->n_ion * cols); }
-        else for (int sp = 0; sp < 2 && !e; ++sp) e = tc_register_weight(m, m->bf_w[sp], dl, cols);
+        else for (int sp = 0; sp < 2 && !e; ++sp) {
+            e = tc_register_weight(m, m->bf_w[sp], dl, cols);
+            if (!e) e = tc_register_weight(m, m->bf_w[sp], cols, dl, true);
+        }
         if (e) { tc_destroy(m); cudaGetLastError(); }      // no tensor-core path: dense layers stay on the FP32 SIMT GEMM
         m->gemm_path = m->tc ? 1 : 0;
         { const char *g = getenv("DPE_MCMC_GRAPH"); m->mcmc_graph_mode = (g && g[0] == '0') ? 0 : 1; }

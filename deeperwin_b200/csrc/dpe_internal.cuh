@@ -31,6 +31,7 @@ struct GemmArgs {
     const float *A; int lda;
     int a_seg_len, a_seg_stride, a_seg_off;   // row m -> (m / seg_len) * seg_stride + seg_off + m % seg_len
     const float *W; int ldw;                  // [K, N] row-major
+    int w_tr = 0;                             // 1: W is stored [N, K] row-major (C = A W^T with a layer's own weight: backward data products, tensor-core path only)
     float *C; int ldc;
     int c_seg_len, c_seg_stride, c_seg_off, c_col_off;
     int M, N, K;
@@ -160,7 +161,7 @@ struct StageTimer {
 int launch_gemm_simt(dpe_model *m, const GemmArgs &g, cudaStream_t s);
 // gemm_tc.cu (tcgen05 3xTF32); returns DPE_ERR_UNSUPPORTED when the shape does not fit, caller falls back to SIMT
 int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s);
-int tc_register_weight(dpe_model *m, const float *W, int K, int N);   // W: [K, N] row-major, device
+int tc_register_weight(dpe_model *m, const float *W, int K, int N, bool tr = false);   // W: [K, N] row-major, device (tr: stored [N, K], used as W^T)
 int tc_refresh_weights(dpe_model *m, cudaStream_t s);                  // re-split after a parameter update
 void tc_destroy(dpe_model *m);
 
@@ -203,12 +204,17 @@ int launch_combine(dpe_model *m, int Bc, int C, const float *det, const float *e
 
 // api.cu: dense layers for grad.cu
 int dense_gemm(dpe_model *m, const float *A, int lda, const float *W, float *Cc, int ldc, int M, int N, int K, cudaStream_t s);
+// C = A W^T for a weight registered with tr (tensor cores only: DPE_ERR_UNSUPPORTED otherwise, the caller keeps its own kernel)
+int dense_gemm_t(dpe_model *m, const float *A, int lda, const float *W, float *Cc, int ldc, int M, int N, int K, int seg_len, int seg_stride, int seg_off,
+                 cudaStream_t s);
 int dense_gemm_seg(dpe_model *m, const float *A, int lda, const float *W, float *Cc, int ldc, int M, int N, int K, int seg_len, int seg_stride, int seg_off,
                    cudaStream_t s);
 
 // mcmc.cu
 int launch_pair_stream_tc(dpe_model *m, const float *r, int Bc, float *pw_base, const size_t *pw_off, cudaStream_t s);
 float tc_rz_comp(int K);
+// gemm_tc.cu: split-K  At Bt^T  products of the gradient / KFAC pass on the CTA-pair tensor-core kernel (grad.cu prepares the transposed operands)
+int launch_atb_tc(dpe_model *m, const float *At, float *Bt_hi, float *Bt_lo, long Rp, int Kc, int Mt, int Nb, float *part, cudaStream_t s);
 int launch_propose(const dpe_model *m, const dpe_mcmc_state *st, int B, const dpe_mcmc_config &cfg, int step_offset, float *r_prop, float *thr, uint32_t *new_keys,
                    float *log_q, cudaStream_t s);
 int launch_accept(const dpe_mcmc_state *st, int B, int n_el, const float *r_prop, const float *lp_prop, const float *thr,

@@ -62,6 +62,7 @@ struct TcArgs {
     float corr;                                    // accumulation-bias compensation factor, see tc_rz_compensation()
     int seg_split;                                 // fused epilogues: channel segments per (walker, electron) group (work items per group)
     int add_smem;                                  // epi 1: the addend rows of a tile are TMA-prefetched into shared memory (else read from global)
+    int w_seg_k;                                   // K offset of the W maps per segment (split-K products: a segment is a K chunk), else 0
     long long *tl;                                 // debug timeline (DPE_GEMM_TIMELINE): [tile][4] clock64 stamps of CTA 0, or nullptr
 };
 
@@ -119,8 +120,8 @@ k_gemm_tc_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     uint8_t *st = smem + stage * TC_STAGE_BYTES;
                     mbar_expect_tx(&bar_full[stage], tx);
-                    tma_load_2d(st, &map_wh, &bar_full[stage], kb * TC_BK, ft * TC_FEAT);
-                    tma_load_2d(st + TC_W_BYTES, &map_wl, &bar_full[stage], kb * TC_BK, ft * TC_FEAT);
+                    tma_load_2d(st, &map_wh, &bar_full[stage], kb * TC_BK + seg * a.w_seg_k, ft * TC_FEAT);
+                    tma_load_2d(st + TC_W_BYTES, &map_wl, &bar_full[stage], kb * TC_BK + seg * a.w_seg_k, ft * TC_FEAT);
                     tma_load_3d(st + 2 * TC_W_BYTES, &map_x, &bar_full[stage], kb * TC_BK, a.spt > 1 ? 0 : rt * a.tile_rows, seg * a.spt);
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -653,8 +654,8 @@ k_gemm_tc2_3xtf32(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     uint8_t *st = smem + stage * T2_STAGE_BYTES;
                     mbar_expect_tx(&bar_full[stage], tx);
-                    tma_load_2d(st, &map_wh, &bar_full[stage], kb * TC_BK, ft * TC_FEAT + (int)rank * 128);
-                    tma_load_2d(st + T2_W_BYTES, &map_wl, &bar_full[stage], kb * TC_BK, ft * TC_FEAT + (int)rank * 128);
+                    tma_load_2d(st, &map_wh, &bar_full[stage], kb * TC_BK + seg * a.w_seg_k, ft * TC_FEAT + (int)rank * 128);
+                    tma_load_2d(st + T2_W_BYTES, &map_wl, &bar_full[stage], kb * TC_BK + seg * a.w_seg_k, ft * TC_FEAT + (int)rank * 128);
                     tma_load_3d(st + 2 * T2_W_BYTES, &map_x, &bar_full[stage], kb * TC_BK, rt * a.tile_rows + (int)rank * half_rows, seg);
                     if (++stage == n_st) { stage = 0; phase ^= 1; }
                 }
@@ -1000,6 +1001,15 @@ __global__ void k_split_transpose(const float *__restrict__ W, int K, int N, flo
     lo[idx] = rna_tf32(w - h);
 }
 
+// W[N][K] as stored -> tf32-rounded halves in the same layout (weights used transposed)
+__global__ void k_split_plain(const float *__restrict__ W, long n, float *__restrict__ hi, float *__restrict__ lo) {
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const float w = W[idx], h = rna_tf32(w);
+    hi[idx] = h;
+    lo[idx] = rna_tf32(w - h);
+}
+
 // ---------------------------------------------------------------------------------------- host side
 // The tensor core adds every MMA (K = 8 tf32 products) to its FP32 accumulator with round-toward-zero.  Measured against
 // fp64 on this part (tools/gemm_bias.py): sums of same-sign terms come out low by 7.9e-8 / 4.6e-7 / 1.07e-6 / 2.42e-6 / 2.85e-6
@@ -1033,6 +1043,7 @@ struct TcWeight {
     CUtensorMap map_hi, map_lo;
     CUtensorMap map_hi128, map_lo128;   // 128-row boxes for the CTA-pair kernel
     bool fresh;
+    bool tr;             // W is stored [N, K]: the halves are a plain split (backward data products  C = A W^T)
 };
 
 struct TcState {
@@ -1055,23 +1066,26 @@ static int encode_w(CUtensorMap *map, float *ptr, int N, int K, int box_rows) {
     return DPE_OK;
 }
 
-int tc_register_weight(dpe_model *m, const float *W, int K, int N) {
+int tc_register_weight(dpe_model *m, const float *W, int K, int N, bool tr) {
     if (!m->tc) m->tc = new TcState();
     TcState *st = static_cast<TcState *>(m->tc);
     for (auto &c : st->weights)
-        if (c.W == W && c.K == K && c.N == N) { c.fresh = false; return DPE_OK; }     // already registered (dpe_debug_gemm re-registers)
+        if (c.W == W && c.K == K && c.N == N && c.tr == tr) { c.fresh = false; return DPE_OK; }     // already registered (dpe_debug_gemm re-registers)
+    if (tr && (K & 3)) return DPE_OK;       // optional use: a row pitch TMA cannot address leaves that product on the FP32 cores (the lookup finds nothing)
     TcWeight w;
-    w.W = W; w.K = K; w.N = N; w.fresh = false;
+    w.W = W; w.K = K; w.N = N; w.fresh = false; w.tr = tr;
+    w.hi = w.lo = nullptr;
     DPE_CUDA(cudaMalloc(&w.hi, (size_t)K * N * sizeof(float)));
-    DPE_CUDA(cudaMalloc(&w.lo, (size_t)K * N * sizeof(float)));
+    if (cudaMalloc(&w.lo, (size_t)K * N * sizeof(float)) != cudaSuccess) { cudaFree(w.hi); return set_error(DPE_ERR_CUDA, "cudaMalloc of a split weight failed"); }
     int e;
     const int box_rows = N <= TR_N ? TR_N : TC_FEAT;      // narrow layers use the rows kernel (Wt resident in shared memory)
-    if ((e = encode_w(&w.map_hi, w.hi, N, K, box_rows))) return e;
-    if ((e = encode_w(&w.map_lo, w.lo, N, K, box_rows))) return e;
-    if (N > TR_N) {
-        if ((e = encode_w(&w.map_hi128, w.hi, N, K, 128))) return e;
-        if ((e = encode_w(&w.map_lo128, w.lo, N, K, 128))) return e;
+    e = encode_w(&w.map_hi, w.hi, N, K, box_rows);
+    if (!e) e = encode_w(&w.map_lo, w.lo, N, K, box_rows);
+    if (!e && N > TR_N) {
+        e = encode_w(&w.map_hi128, w.hi, N, K, 128);
+        if (!e) e = encode_w(&w.map_lo128, w.lo, N, K, 128);
     }
+    if (e) { cudaFree(w.hi); cudaFree(w.lo); return e; }
     st->weights.push_back(w);
     return DPE_OK;
 }
@@ -1081,7 +1095,8 @@ int tc_refresh_weights(dpe_model *m, cudaStream_t s) {
     TcState *st = static_cast<TcState *>(m->tc);
     for (auto &w : st->weights) {
         long n = (long)w.K * w.N;
-        k_split_transpose<<<(int)((n + 255) / 256), 256, 0, s>>>(w.W, w.K, w.N, w.hi, w.lo);
+        if (w.tr) k_split_plain<<<(int)((n + 255) / 256), 256, 0, s>>>(w.W, n, w.hi, w.lo);
+        else k_split_transpose<<<(int)((n + 255) / 256), 256, 0, s>>>(w.W, w.K, w.N, w.hi, w.lo);
         DPE_LAUNCH_CHECK(m);
         w.fresh = true;
     }
@@ -1101,9 +1116,9 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     TcState *st = static_cast<TcState *>(m->tc);
     const TcWeight *w = nullptr;
     for (auto &c : st->weights)
-        if (c.W == g.W && c.K == g.K && c.N == g.N && c.fresh) { w = &c; break; }
+        if (c.W == g.W && c.K == g.K && c.N == g.N && c.tr == (g.w_tr != 0) && c.fresh) { w = &c; break; }
     if (!w) return DPE_ERR_UNSUPPORTED;
-    if ((g.K & 3) || (g.lda & 3) || (reinterpret_cast<size_t>(g.A) & 15) || g.ldw != g.N) return DPE_ERR_UNSUPPORTED;
+    if ((g.K & 3) || (g.lda & 3) || (reinterpret_cast<size_t>(g.A) & 15) || g.ldw != (g.w_tr ? g.K : g.N)) return DPE_ERR_UNSUPPORTED;
     if (g.N <= TR_N) return launch_gemm_tc_rows(m, g, w, s);
     // A and C must use the same segmentation (true for every caller in api.cu)
     if (g.a_seg_len != g.c_seg_len) return DPE_ERR_UNSUPPORTED;
@@ -1120,6 +1135,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
     static const bool pipe = getenv("DPE_TC_EPI_PIPE") != nullptr;
     a.pipe = pipe;
     a.spt = 1;
+    a.w_seg_k = 0;
     a.epi = g.epi; a.nch = g.epi ? g.n_ch : 1;
     a.r = g.r; a.R = g.R; a.spa = g.spa; a.envw = g.envw; a.n_el = g.n_el; a.n_ion = g.n_ion; a.el_base = g.el_base;
     a.bias = g.bias; a.add = g.add; a.gpa = g.groups_per_add > 0 ? g.groups_per_add : 1;
@@ -1272,6 +1288,60 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
             fclose(f);
         }
     }
+    return DPE_OK;
+}
+
+// Split-K product of the gradient / KFAC pass (grad.cu) on the CTA-pair kernel:
+//   P[s][m, n] = sum_{k < Kc} At[m, s Kc + k] Bt[n, s Kc + k]        s < S = Rp / Kc
+// At [S][Mt][Kc] FP32 (chunk-major; the reduction index -- walker x electron rows -- contiguous; split in shared memory like every X operand),
+// Bt_hi / Bt_lo [Nb][Rp] tf32 halves (the role the layer weights play in a forward product).  A "segment" of the kernel is one K chunk: the
+// X map walks chunks along its third dimension, the W maps get the chunk's K offset (w_seg_k), and segment s stores into P[s].
+// The caller sums the S partial products in a fixed order (k_atb_reduce).
+int launch_atb_tc(dpe_model *m, const float *At, float *Bt_hi, float *Bt_lo, long Rp, int Kc, int Mt, int Nb, float *part, cudaStream_t s) {
+    static const bool off = getenv("DPE_ATB_TC") && atoi(getenv("DPE_ATB_TC")) == 0;
+    if (off || m->gemm_path != 1 || tc_pair_mode() < 1) return DPE_ERR_UNSUPPORTED;
+    if ((Nb & 3) || (Kc % TC_BK) || Rp % Kc || (reinterpret_cast<size_t>(At) & 15) || (reinterpret_cast<size_t>(part) & 15)) return DPE_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return DPE_ERR_UNSUPPORTED;
+    const int S = (int)(Rp / Kc);
+    TcArgs a = {};
+    a.C = part; a.ldc = Nb; a.c_seg_stride = Mt; a.c_seg_off = 0; a.c_col_off = 0;
+    a.n_seg = S; a.seg_len = Mt; a.N_out = Nb; a.K = Kc;
+    a.corr = tc_rz_compensation(Kc);
+    a.spt = 1; a.w_seg_k = Kc; a.epi = 0; a.nch = 1; a.gpa = 1; a.seg_split = 1; a.n_st = T2_PLAIN_STAGES; a.tma_store = 1;
+    const int tiles_min = (Mt + 255) / 256;
+    a.nmma = (((Mt + tiles_min - 1) / tiles_min) + 31) / 32 * 32;     // each CTA of the pair loads half of the MMA N rows
+    if (a.nmma > 256) a.nmma = 256;
+    a.tile_rows = a.nmma;
+    a.n_rt = (Mt + a.nmma - 1) / a.nmma;
+    a.n_ft = (Nb + TC_FEAT - 1) / TC_FEAT;
+
+    CUtensorMap map_x, map_c, map_h, map_l;
+    cuuint32_t es[3] = {1, 1, 1};
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)Kc, (cuuint64_t)Mt, (cuuint64_t)S};
+        cuuint64_t strides[2] = {(cuuint64_t)Kc * sizeof(float), (cuuint64_t)Mt * Kc * sizeof(float)};      // chunk-major: At[s][m][k]
+        cuuint32_t box[3] = {TC_BK, (cuuint32_t)(a.nmma / 2), 1};
+        CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(At), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return set_error(DPE_ERR_CUDA, "cuTensorMapEncodeTiled(At) failed: %d", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)Nb, (cuuint64_t)Mt, (cuuint64_t)S};
+        cuuint64_t strides[2] = {(cuuint64_t)Nb * sizeof(float), (cuuint64_t)Mt * Nb * sizeof(float)};
+        cuuint32_t box[3] = {128, TC_OUT_ROWS, 1};
+        CUresult r = enc(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, part, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return set_error(DPE_ERR_CUDA, "cuTensorMapEncodeTiled(P) failed: %d", (int)r);
+    }
+    if (Rp >= (1L << 31)) return DPE_ERR_UNSUPPORTED;
+    if (int e = encode_w(&map_h, Bt_hi, Nb, (int)Rp, 128)) return e;
+    if (int e = encode_w(&map_l, Bt_lo, Nb, (int)Rp, 128)) return e;
+    if (int e = opt_in_smem(m, KID_GEMM_TC2P, k_gemm_tc2_3xtf32<false>)) return e;
+    const long n_tiles = (long)S * a.n_rt * a.n_ft;
+    const long pairs = n_tiles < m->n_sm / 2 ? n_tiles : m->n_sm / 2;
+    k_gemm_tc2_3xtf32<false><<<(int)pairs * 2, TC_THREADS, T2_SMEM_BYTES, s>>>(map_x, map_h, map_l, map_c, map_x, a);
+    DPE_LAUNCH_CHECK(m);
     return DPE_OK;
 }
 

@@ -66,6 +66,11 @@ __global__ void __launch_bounds__(256) k_gemm_nt(const float *__restrict__ A, lo
 static int gemm_nt(dpe_model *m, const float *A, long lda, const float *W, long ldw, float *C, long ldc, long R, int K, int Nn, bool acc, cudaStream_t s,
                    RowMap rm = RowMap{0, 0, 0}) {
     if (R <= 0 || K <= 0 || Nn <= 0) return DPE_OK;
+    if (!acc && ldw == Nn && R >= 1024 && R < (1L << 31) && lda < (1L << 31) && ldc < (1L << 31)) {
+        // the layer's own weight read transposed, on the tensor cores (registered with tr in dpe_model_create); other shapes: FP32 cores
+        const int e = dense_gemm_t(m, A, (int)lda, W, C, (int)ldc, (int)R, K, Nn, rm.seg_len, rm.seg_stride, rm.seg_off, s);
+        if (e != DPE_ERR_UNSUPPORTED) return e;
+    }
     dim3 grid((K + 63) / 64, (unsigned)((R + 63) / 64));
     k_gemm_nt<<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, (int)R, K, Nn, acc ? 1 : 0, rm);
     DPE_LAUNCH_CHECK(m);
@@ -317,12 +322,55 @@ __global__ void __launch_bounds__(256) k_atb_reduce(const float *__restrict__ pa
     }
 }
 
+// Operands of a WIDE product for the tensor-core path (launch_atb_tc, gemm_tc.cu): the reduction index r (walker x electron rows) becomes the
+// contiguous one, through a 32 x 32 shared-memory transpose (coalesced on both sides).
+//   mode 0:  At[s][m][k] = wrow(r) * Aaug[r, m],  r = s Kc + k   (FP32, chunk-major; the kernel splits it into tf32 halves in shared memory)
+//   mode 1:  Bt_hi / Bt_lo[n][r] = tf32 halves of B[r, n]
+// rows r >= rows (padding up to Rp = S Kc) are written as zeros.
+__device__ __forceinline__ float to_tf32(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+__global__ void __launch_bounds__(256) k_atb_prep(const float *__restrict__ src, long ld, int ncols, int ones, long rows, long Rp, int Kc, int rpw,
+                                                  const float *__restrict__ wts, RowMap rm, int mode, float *__restrict__ o0, float *__restrict__ o1) {
+    __shared__ float tile[32][33];
+    const long r0 = blockIdx.x * 32L;
+    const int c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nc = ncols + ones;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int rr = ty + 8 * q, c = c0 + tx;
+        const long r = r0 + rr;
+        float v = 0.f;
+        if (r < rows && c < nc) {
+            const unsigned r32 = (unsigned)r;
+            const long pr = rm.seg_len ? (long)(r32 / (unsigned)rm.seg_len) * rm.seg_stride + rm.seg_off + r32 % (unsigned)rm.seg_len : r;
+            v = c < ncols ? src[pr * ld + c] : 1.f;
+            if (wts) v *= wts[r32 / (unsigned)rpw];
+        }
+        tile[rr][tx] = v;
+    }
+    __syncthreads();
+    const long r = r0 + tx;
+    const long sc = r / Kc;
+    const int k = (int)(r - sc * Kc);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int cc = ty + 8 * q, c = c0 + cc;
+        if (c >= nc) continue;
+        const float v = tile[tx][cc];
+        if (mode == 0) o0[((size_t)sc * nc + c) * Kc + k] = v;
+        else {
+            const float h = to_tf32(v);
+            o0[(size_t)c * Rp + r] = h;
+            o1[(size_t)c * Rp + r] = to_tf32(v - h);
+        }
+    }
+}
+
 struct GradCtx {
     dpe_model *m;
     cudaStream_t s;
     float *part; size_t part_floats;      // scratch of the split products
     const float *cot;                     // per-walker cotangents c_b of this chunk (gradient), or nullptr
     bool accumulate;                      // add to the outputs (second and later chunks)
+    float *tcs; size_t tcs_floats;        // transposed operands of the wide products on the tensor-core path
 };
 
 // out[Ma + ones, Nb] (ldc) (+)= scale * Aaug^T diag(w) B
@@ -347,6 +395,37 @@ static int atb(GradCtx &g, float *out, long ldc, const float *A, long lda, int M
         k_atb_reduce<<<(int)((per + 31) / 32), 256, 0, g.s>>>(g.part, a.n_split, Mt, Nb, out, ldc, scale, g.accumulate ? 1 : 0);
         DPE_LAUNCH_CHECK(g.m);
         return DPE_OK;
+    }
+    static const bool atb_tc_off = getenv("DPE_ATB_TC") && atoi(getenv("DPE_ATB_TC")) == 0;
+    if (Mt > 64 && Nb > 64 && rows >= 1024 && rows < (1L << 31) && sel < 0 && !(Nb & 3) && g.tcs && g.m->gemm_path == 1 && tc_pair_mode() >= 1 && !atb_tc_off) {
+        // wide operands on the tensor cores: split-K over chunks of Kc rows, 3xTF32 (FP32-accurate) on the CTA-pair dense-layer kernel.
+        // (Short products stay on the FP32 cores: the accumulation-bias compensation assumes full chunks, and there is nothing to gain.)
+        // Kc balances waves of (256 feature x <= 256 row) tiles over the 74 CTA pairs against the size of the partial products.
+        const int tiles_min = (Mt + 255) / 256, nmma = (((Mt + tiles_min - 1) / tiles_min) + 31) / 32 * 32;
+        const long tpc = (long)((Mt + nmma - 1) / nmma) * ((Nb + 255) / 256);
+        int Kc = 0; double best = 0.0;
+        for (int kc = 256; kc <= 2048; kc *= 2) {
+            const long S = (rows + kc - 1) / kc;
+            if (per * (size_t)S > g.part_floats || (size_t)(Mt + 2 * Nb) * (size_t)(S * kc) > g.tcs_floats) continue;
+            const long waves = (S * tpc + 73) / 74;
+            const double cost = (double)waves * (kc * 120.0 + 25000.0) + (double)S * per * 8.0 / 6.0e12 * 1.9e9 / 1.0;     // clocks: MMA waves + partial write / read
+            if (!Kc || cost < best) { Kc = kc; best = cost; }
+        }
+        if (Kc) {
+            const long S = (rows + Kc - 1) / Kc, Rp = S * Kc;
+            float *At = g.tcs, *Bh = At + (size_t)Mt * Rp, *Bl = Bh + (size_t)Nb * Rp;
+            k_atb_prep<<<dim3((unsigned)(Rp / 32), (unsigned)((Mt + 31) / 32)), 256, 0, g.s>>>(A, lda, Ma, a.ones, rows, Rp, Kc, rpw, wts, rm, 0, At, nullptr);
+            DPE_LAUNCH_CHECK(g.m);
+            k_atb_prep<<<dim3((unsigned)(Rp / 32), (unsigned)((Nb + 31) / 32)), 256, 0, g.s>>>(B, ldb, Nb, 0, rows, Rp, Kc, 1, nullptr, rm, 1, Bh, Bl);
+            DPE_LAUNCH_CHECK(g.m);
+            const int e = launch_atb_tc(g.m, At, Bh, Bl, Rp, Kc, Mt, Nb, g.part, g.s);
+            if (e == DPE_OK) {
+                k_atb_reduce<<<(int)((per + 31) / 32), 256, 0, g.s>>>(g.part, (int)S, Mt, Nb, out, ldc, scale, g.accumulate ? 1 : 0);
+                DPE_LAUNCH_CHECK(g.m);
+                return DPE_OK;
+            }
+            if (e != DPE_ERR_UNSUPPORTED) return e;
+        }
     }
     if (Mt > 64 && Nb > 64 && rows < (1L << 31) && sel < 0) {       // wide operands: 128 x 128 tiles
         const long tiles = (long)((Mt + 127) / 128) * ((Nb + 127) / 128);
@@ -817,8 +896,8 @@ struct GradLayout {
     size_t add, bf, mo, det, ainv, coef, dbf, dy, dz, dx, sumdz, dmean, dzhm, dhmap, sumx;
     size_t dzw[DPE_MAX_ITER], dzw_cm[DPE_MAX_ITER], px[DPE_MAX_ITER], dzh[DPE_MAX_ITER], dcei[DPE_MAX_ITER], ex[DPE_MAX_ITER], dze[DPE_MAX_ITER], pei[DPE_MAX_ITER],
         dzhim[DPE_MAX_ITER];
-    size_t xion, onehot, dhion, part, env_part, scr;
-    size_t part_floats, total;
+    size_t xion, onehot, dhion, part, env_part, scr, tcs;
+    size_t part_floats, tcs_floats, total;
     int ldx, env_splits, walkers_per_split;
 };
 
@@ -872,8 +951,16 @@ static void grad_plan(const dpe_dims &d, int Bc, GradLayout &L) {
     size_t biggest = (size_t)(max_k + 1) * (max_k + 1);
     if ((size_t)cols * cols > biggest) biggest = (size_t)cols * cols;
     if ((size_t)(max_k + 1) * 2 * max_din > biggest) biggest = (size_t)(max_k + 1) * 2 * max_din;
-    L.part_floats = biggest * 32;
+    L.part_floats = biggest * 64;
     L.part = take(L.part_floats);
+    // transposed operands of the widest product on the tensor-core path: At [Mt][Rp] + Bt_hi, Bt_lo [Nb][Rp], rows padded to the K chunk
+    {
+        size_t wmax = (size_t)max_k + 1;
+        if ((size_t)cols > wmax) wmax = cols;
+        if ((size_t)max_dout > wmax) wmax = max_dout;
+        L.tcs_floats = 3 * wmax * (R1 + 2048);
+        L.tcs = take(L.tcs_floats);
+    }
     L.walkers_per_split = 64;
     L.env_splits = (Bc + L.walkers_per_split - 1) / L.walkers_per_split;
     L.env_part = take((size_t)L.env_splits * 2 * 2 * I * cols);
@@ -984,7 +1071,7 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
     const int ldx = L.ldx;
     auto fp = [&](size_t off) { return reinterpret_cast<float *>(ws + off); };
     int e;
-    GradCtx g{m, s, fp(L.part), L.part_floats, cot, accumulate};
+    GradCtx g{m, s, fp(L.part), L.part_floats, cot, accumulate, fp(L.tcs), L.tcs_floats};
     auto leaf_off = [&](const float *p) { return (size_t)(p - m->params); };
 
     // ---------------- forward pass on the value channel, every intermediate kept

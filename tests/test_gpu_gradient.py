@@ -16,7 +16,8 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("name,small,B", [("LiH", True, 24), ("LiH", False, 16), ("B", True, 12), ("N2", False, 6), ("HChain6", True, 8)])
+@pytest.mark.parametrize("name,small,B", [("LiH", True, 24), ("LiH", False, 16), ("B", True, 12), ("N2", False, 6), ("HChain6", True, 8),
+                                          ("N2", False, 160)])          # >= 1024 (walker, electron) rows: the wide products run on the tensor cores
 def test_gradient_and_kfac_match_oracle(name, small, B):
     from oracle import gradient as og
     phys, d, p32, p64, R, r, eng = make(name, B, small=small)
