@@ -126,7 +126,7 @@ int check_cuda(cudaError_t e, const char *what);
 // context, and a model lives on one device): always to the full 227 KB, so that two models with different needs cannot undercut
 // each other.
 enum KernelId { KID_PAIR1 = 0, KID_PAIR3, KID_CONV2_BIG, KID_CONV1, KID_DET64, KID_DET64F, KID_DET128, KID_GEMM_TC, KID_GEMM_TC2F,
-                KID_GEMM_TC2P, KID_GEMM_ROWS, KID_DET_TRACE, KID_MCMC_FUSED, KID_GRAD_A, KID_GRAD_B, KID_PAIR_TC, KID_BW_PAIR, KID_BW_EION, KID_COUNT };
+                KID_GEMM_TC2P, KID_GEMM_ROWS, KID_DET_TRACE, KID_MCMC_FUSED, KID_GRAD_A, KID_GRAD_B, KID_PAIR_TC, KID_BW_PAIR, KID_BW_EION, KID_BW_PAIR_ROWS, KID_COUNT };
 constexpr int DPE_SMEM_OPTIN = 227 * 1024;
 template <typename F>
 inline int opt_in_smem(dpe_model *m, int kid, F *fn) {

@@ -804,6 +804,127 @@ __global__ void __launch_bounds__(256) k_bw_pair(PairBwArgs a) {
     }
 }
 
+// The same backward for the default widths (pair features 1 -> 32 -> 32 -> ..., 32 convolution features): ONE THREAD per ordered pair.  The warp-per-pair
+// kernel above spends its time in the MIO pipe (32 SHFL + 32 LDS per 32 x 32 product and pair); with a row per thread the operand vector lives in
+// registers and every lane of a warp reads the SAME weight row, so a product costs 8 broadcast LDS.128 per pair and the kernel is FMA / HBM bound.
+// The layer inputs x^it go to global memory on the way forward (they are outputs anyway) and are read back on the way down; the tanh output of a
+// residual layer is recovered as t = sqrt2 x^{it+1} - x^it.
+constexpr int PBR_THREADS = 128;
+__device__ __forceinline__ void st_row32(float *dst, const float (&v)[32]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) reinterpret_cast<float4 *>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+// acc[k] += sum_n v[n] W[k, n] for the four n of one float4 of v   (W row-major [32][32] in shared memory, all lanes read the same address)
+__device__ __forceinline__ void acc_wt4(float (&acc)[32], const float *W, int n4, const float4 v) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const float4 w = *reinterpret_cast<const float4 *>(W + k * 32 + n4 * 4);
+        acc[k] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[k]))));
+    }
+}
+__global__ void __launch_bounds__(PBR_THREADS) k_bw_pair_rows(PairBwArgs a) {
+    extern __shared__ __align__(16) float wsm[];      // [it][class][w | h][32 x 32], then the h biases [it][class][32]
+    const int nit = a.n_iter;
+    float *bsm = wsm + nit * 4 * 1024;
+    for (int t = threadIdx.x; t < nit * 4 * 1024; t += blockDim.x) {
+        const int e = t & 1023, wh = (t >> 10) & 1, c = (t >> 11) & 1, it = t >> 12, k = e >> 5, n = e & 31;
+        float v = 0.f;
+        if (wh == 0) { if (k < a.dP[it]) v = a.ww[it][c][k * 32 + n]; }
+        else if (it + 1 < nit && k < a.dP[it]) v = a.hw[it][c][k * 32 + n];
+        wsm[t] = v;
+    }
+    for (int t = threadIdx.x; t < nit * 64; t += blockDim.x) {
+        const int n = t & 31, c = (t >> 5) & 1, it = t >> 6;
+        bsm[t] = it + 1 < nit ? a.hb[it][c][n] : 0.f;
+    }
+    __syncthreads();
+    const int N = a.N, U = a.U, D = N - U, n_same = U * U + D * D, n_diff = 2 * U * D;
+    const long n_walkers = a.n_pairs / ((long)N * N);
+    constexpr float RS2 = 0.70710678118654752f, S2 = 1.41421356237309505f;
+    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < a.n_pairs; p += (long)gridDim.x * blockDim.x) {
+        const long b = p / ((long)N * N);
+        const int ij = (int)(p - b * N * N), i = ij / N, j = ij - i * N;
+        const int sd = ((i < U) == (j < U)) ? 0 : 1;
+        const long pc = sd == 0 ? b * n_same + (i < U ? i * U + j : U * U + (i - U) * D + (j - U))
+                                : n_walkers * n_same + b * n_diff + (i < U ? i * D + (j - U) : U * D + (i - U) * U + j);       // class-major row
+        const float *ri = a.r + (b * N + i) * 3, *rj = a.r + (b * N + j) * 3;
+        const float dx0 = rj[0] - ri[0], dy0 = rj[1] - ri[1], dz0 = rj[2] - ri[2];
+        const float dist = i == j ? 0.f : sqrtf(dx0 * dx0 + dy0 * dy0 + dz0 * dz0);
+        // ---- forward: x^1 = tanh(d W_h^0 + b), x^{it+1} = (x^it + tanh(x^it W_h^it + b)) / sqrt2; every x^it is stored (class-major)
+        a.px[0][pc] = dist;
+        float x[32];
+        {
+            const float *W = wsm + (sd * 2 + 1) * 1024, *bb = bsm + sd * 32;
+#pragma unroll
+            for (int n = 0; n < 32; ++n) x[n] = tanhf(fmaf(dist, W[n], bb[n]));
+        }
+        st_row32(a.px[1] + pc * 32, x);
+        for (int it = 1; it + 1 < nit; ++it) {
+            const float *W = wsm + ((it * 2 + sd) * 2 + 1) * 1024, *bb = bsm + (it * 2 + sd) * 32;
+            float z[32];
+#pragma unroll
+            for (int n = 0; n < 32; ++n) z[n] = bb[n];
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 w = *reinterpret_cast<const float4 *>(W + k * 32 + q * 4);
+                    z[4 * q] = fmaf(x[k], w.x, z[4 * q]); z[4 * q + 1] = fmaf(x[k], w.y, z[4 * q + 1]);
+                    z[4 * q + 2] = fmaf(x[k], w.z, z[4 * q + 2]); z[4 * q + 3] = fmaf(x[k], w.w, z[4 * q + 3]);
+                }
+#pragma unroll
+            for (int n = 0; n < 32; ++n) x[n] = (x[n] + tanhf(z[n])) * RS2;
+            st_row32(a.px[it + 1] + pc * 32, x);
+        }
+        // ---- backward: dx^it = dzw^it W_w^T + dzh^it W_h^T + dx^{it+1} / sqrt2,  dzh^it = dx^{it+1} / sqrt2 (1 - t^2)
+        float dxn[32];
+#pragma unroll
+        for (int n = 0; n < 32; ++n) dxn[n] = 0.f;
+        for (int it = nit - 1; it >= 1; --it) {
+            float dxc[32];
+            const bool has_h = it + 1 < nit;
+#pragma unroll
+            for (int n = 0; n < 32; ++n) dxc[n] = has_h ? dxn[n] * RS2 : 0.f;
+            const float *Ww = wsm + ((it * 2 + sd) * 2) * 1024, *Wh = Ww + 1024;
+            const float4 *gz = reinterpret_cast<const float4 *>(a.dzw[it] + p * 32);
+            float4 *gcm = reinterpret_cast<float4 *>(a.dzw_cm[it] + pc * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 v = gz[q];
+                gcm[q] = v;
+                acc_wt4(dxc, Ww, q, v);
+            }
+            if (has_h) {
+                const float4 *x0 = reinterpret_cast<const float4 *>(a.px[it] + pc * 32), *x1 = reinterpret_cast<const float4 *>(a.px[it + 1] + pc * 32);
+                float4 *gh = reinterpret_cast<float4 *>(a.dzh[it] + pc * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 u0 = x0[q], u1 = x1[q];
+                    const float t0 = fmaf(S2, u1.x, -u0.x), t1 = fmaf(S2, u1.y, -u0.y), t2 = fmaf(S2, u1.z, -u0.z), t3 = fmaf(S2, u1.w, -u0.w);
+                    const float4 v = make_float4(dxn[4 * q] * RS2 * (1.f - t0 * t0), dxn[4 * q + 1] * RS2 * (1.f - t1 * t1),
+                                                 dxn[4 * q + 2] * RS2 * (1.f - t2 * t2), dxn[4 * q + 3] * RS2 * (1.f - t3 * t3));
+                    gh[q] = v;
+                    acc_wt4(dxc, Wh, q, v);
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < 32; ++n) dxn[n] = dxc[n];
+        }
+        {   // it = 0: one input feature (the distance), nothing upstream: only the cotangents of the two layers' pre-activations
+            const float4 *gz = reinterpret_cast<const float4 *>(a.dzw[0] + p * 32);
+            float4 *gcm = reinterpret_cast<float4 *>(a.dzw_cm[0] + pc * 32), *gh = reinterpret_cast<float4 *>(a.dzh[0] + pc * 32);
+            const float4 *x1 = reinterpret_cast<const float4 *>(a.px[1] + pc * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                gcm[q] = gz[q];
+                const float4 t = x1[q];
+                gh[q] = make_float4(dxn[4 * q] * (1.f - t.x * t.x), dxn[4 * q + 1] * (1.f - t.y * t.y), dxn[4 * q + 2] * (1.f - t.z * t.z),
+                                    dxn[4 * q + 3] * (1.f - t.w * t.w));
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ el-ion stream backward
 // One warp per (walker, electron, ion): chain h^0 = [d, dx, dy, dz], h^{it+1} = res(tanh(h^it W + b), h^it);  conv_eI^it[i] = sum_J h^it[i, J] him^it[J].
 //   cotangent of h^it from the convolution: dcei^it[b, i] * him^it[J];  pei^it[b, i, J] = h^it * dcei^it  (cotangent of him^it before the sum over i)
@@ -1227,8 +1348,18 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
         const size_t sm_pair = (size_t)nit * 4 * WMAT * sizeof(float), sm_eion = (size_t)nit * WMAT * sizeof(float);
         if ((e = opt_in_smem(m, KID_BW_PAIR, k_bw_pair))) return e;       // per model / device, as every other kernel with more than 48 KB
         if ((e = opt_in_smem(m, KID_BW_EION, k_bw_eion))) return e;
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u << 10) / sm_pair));
-        k_bw_pair<<<(unsigned)std::min<long>((P2 * 32 + 255) / 256, 148L * per_sm), 256, sm_pair, s>>>(a);
+        static const bool rows_off = getenv("DPE_BW_PAIR_ROWS") && atoi(getenv("DPE_BW_PAIR_ROWS")) == 0;
+        bool rows_ok = !rows_off && emb == 32 && nit >= 2 && a.dP[0] == 1;
+        for (int it = 1; it < nit; ++it) rows_ok = rows_ok && a.dP[it] == 32;
+        if (rows_ok) {                // default widths: one thread per pair, operands in registers
+            const size_t sm_rows = ((size_t)nit * 4 * 1024 + (size_t)nit * 64) * sizeof(float);
+            if ((e = opt_in_smem(m, KID_BW_PAIR_ROWS, k_bw_pair_rows))) return e;
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220u << 10) / (sm_rows + 1024)));
+            k_bw_pair_rows<<<(unsigned)std::min<long>((P2 + PBR_THREADS - 1) / PBR_THREADS, 148L * per_sm), PBR_THREADS, sm_rows, s>>>(a);
+        } else {
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u << 10) / sm_pair));
+            k_bw_pair<<<(unsigned)std::min<long>((P2 * 32 + 255) / 256, 148L * per_sm), 256, sm_pair, s>>>(a);
+        }
         DPE_LAUNCH_CHECK(m);
         EionBwArgs b;
         b.r = r; b.R = m->R_dev; b.n_iter = nit; b.N = N; b.I = I; b.n_rows = R3;
