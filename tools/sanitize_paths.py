@@ -1,5 +1,5 @@
 """A small pass through every kernel family for compute-sanitizer (memcheck / racecheck): E_loc + forward on LiH / N2 / ethene (N > 16 path),
-Metropolis steps with every proposal, gradient + KFAC pass, TAO head, XLA shim is covered by its own test."""
+Metropolis steps with every proposal, gradient + KFAC pass (small batches: FP32-core products; 160 walkers: tensor-core products), TAO head, XLA shim is covered by its own test."""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -45,4 +45,14 @@ vag = dpe.build_value_and_grad_func(f, gle, dpe.ClippingConfig(), with_kfac_stat
 (loss, _), grads = vag(params, dpe.init_clipping_state(), (phys.n_up, phys.n_dn), st.build_batch(fixed))
 torch.cuda.synchronize()
 print("LiH TAO loss", float(loss), "finite grads", all(torch.isfinite(v).all() for l in grads.values() for v in l.values()))
+# >= 1024 (walker, electron) rows: the wide gradient / KFAC products and dx = dz W^T on the tensor cores (k_atb_prep, launch_atb_tc, dense_gemm_t),
+# the thread-per-pair backward of the pair stream (k_bw_pair_rows)
+cfg = dpe.Configuration(physical=dict(name="N2"))
+phys = cfg.physical
+f, _, _, params, fixed = dpe.build_log_psi_squared(cfg.model, phys, None, None, rng_seed=1, device="cuda:0")
+st = dpe.MCMCState.initialize_around_nuclei(160, phys, "gaussian", "el_ion_mapping", dpe.PRNGKey(3), device="cuda:0")
+f.engine.set_params(params); f.engine.set_geometry(st.R, st.Z)
+flat, lp = f.engine.param_gradient(st.r, torch.full((160,), 1.0 / 160, device="cuda"), with_kfac=True)
+torch.cuda.synchronize()
+print("N2 x 160 gradient + KFAC finite", bool(torch.isfinite(flat).all()))
 print("done")
