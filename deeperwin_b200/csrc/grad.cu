@@ -554,11 +554,12 @@ __global__ void k_bw_combine(int Bc, int n_det, const float *__restrict__ det, f
 //   dmo = coef[b, det] Ainv[b, det][orb][i];  env and its parameter derivatives recomputed;  dbf = dmo env;  denv = dmo bf
 //   d weights[J, col] += c_b denv exp(-a d);  d alpha[J, col] += c_b denv w exp(-a d) (-d) sigmoid(alpha)
 // partial sums per split: part[split][spin][2][I][cols]
-__global__ void __launch_bounds__(128) k_bw_orbitals(int Bc, int N, int U, int I, int n_det, const float *__restrict__ r, const float *__restrict__ R,
-                                                     const float *__restrict__ coef, const float *__restrict__ ainv, const float *__restrict__ bf,
-                                                     const float *__restrict__ spa_up, const float *__restrict__ spa_dn, const float *__restrict__ alpha_up,
-                                                     const float *__restrict__ alpha_dn, const float *__restrict__ w_up, const float *__restrict__ w_dn,
-                                                     const float *__restrict__ cot, float *__restrict__ dbf, float *__restrict__ part, int walkers_per_split) {
+__global__ void __launch_bounds__(64) k_bw_orbitals(int Bc, int N, int U, int I, int n_det, const float *__restrict__ r, const float *__restrict__ R,
+                                                    const float *__restrict__ coef, const float *__restrict__ ainv, const float *__restrict__ bf,
+                                                    const float *__restrict__ spa_up, const float *__restrict__ spa_dn, const float *__restrict__ alpha_up,
+                                                    const float *__restrict__ alpha_dn, const float *__restrict__ w_up, const float *__restrict__ w_dn,
+                                                    const float *__restrict__ cot, float *__restrict__ dbf, float *__restrict__ part, int walkers_per_split) {
+    // thread = orbital column, block row = a few walkers (the launcher sizes the split so that ~8 blocks per SM exist even for small batches)
     const int cols = n_det * N;
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= cols) return;
@@ -570,9 +571,14 @@ __global__ void __launch_bounds__(128) k_bw_orbitals(int Bc, int N, int U, int I
         const int i_lo = sp ? U : 0, i_hi = sp ? N : U;
         for (int J0 = 0; J0 < I; J0 += MAXI) {
             const int nJ = min(MAXI, I - J0);
-            float gw[MAXI], ga[MAXI];
+            const bool one_block = I <= MAXI;                 // all ions in this block: the envelope itself comes out of the same loop
+            float gw[MAXI], ga[MAXI], sa[MAXI], sw[MAXI];
 #pragma unroll
-            for (int k = 0; k < MAXI; ++k) { gw[k] = 0.f; ga[k] = 0.f; }
+            for (int k = 0; k < MAXI; ++k) {
+                gw[k] = 0.f; ga[k] = 0.f;
+                sa[k] = k < nJ ? spa[(long)(J0 + k) * cols + col] : 0.f;
+                sw[k] = k < nJ ? wt[(long)(J0 + k) * cols + col] : 0.f;
+            }
             for (int b = b0; b < b1; ++b) {
                 const float cb = cot ? cot[b] : 1.f;
                 const float cf = coef[(long)b * n_det + dt];
@@ -580,11 +586,12 @@ __global__ void __launch_bounds__(128) k_bw_orbitals(int Bc, int N, int U, int I
                     const long row = (long)b * N + i;
                     const float dmo = cf * ainv[((long)b * n_det + dt) * N * N + (long)q * N + i];
                     const float *ri = r + row * 3;
+                    const float rx = ri[0], ry = ri[1], rz = ri[2];
                     float env = 0.f;
                     const float denv = dmo * bf[row * cols + col];
-                    if (J0 == 0) {
+                    if (J0 == 0 && !one_block) {
                         for (int J = 0; J < I; ++J) {
-                            const float dx = ri[0] - R[J * 3], dy = ri[1] - R[J * 3 + 1], dz = ri[2] - R[J * 3 + 2];
+                            const float dx = rx - R[J * 3], dy = ry - R[J * 3 + 1], dz = rz - R[J * 3 + 2];
                             env += wt[(long)J * cols + col] * expf(-spa[(long)J * cols + col] * sqrtf(dx * dx + dy * dy + dz * dz));
                         }
                         dbf[row * cols + col] = dmo * env;
@@ -593,12 +600,14 @@ __global__ void __launch_bounds__(128) k_bw_orbitals(int Bc, int N, int U, int I
                     for (int k = 0; k < MAXI; ++k)
                         if (k < nJ) {
                             const int J = J0 + k;
-                            const float dx = ri[0] - R[J * 3], dy = ri[1] - R[J * 3 + 1], dz = ri[2] - R[J * 3 + 2];
+                            const float dx = rx - R[J * 3], dy = ry - R[J * 3 + 1], dz = rz - R[J * 3 + 2];
                             const float dd = sqrtf(dx * dx + dy * dy + dz * dz);
-                            const float e = expf(-spa[(long)J * cols + col] * dd);
+                            const float e = expf(-sa[k] * dd);
+                            env = fmaf(sw[k], e, env);
                             gw[k] = fmaf(cb * denv, e, gw[k]);
-                            ga[k] = fmaf(cb * denv, -dd * wt[(long)J * cols + col] * e, ga[k]);
+                            ga[k] = fmaf(cb * denv, -dd * sw[k] * e, ga[k]);
                         }
+                    if (one_block) dbf[row * cols + col] = dmo * env;
                 }
             }
             for (int k = 0; k < nJ; ++k) {
@@ -638,12 +647,23 @@ __global__ void __launch_bounds__(256) k_bw_tao(long total, int N, int U, int I,
 }
 
 // leaf[J, col] (+)= sum_split part[split][spin][which][J][col]
-__global__ void k_bw_env_reduce(const float *__restrict__ part, int n_split, int I, int cols, int sp, int which, float *__restrict__ out, int accumulate) {
-    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (idx >= (long)I * cols) return;
+__global__ void __launch_bounds__(256) k_bw_env_reduce(const float *__restrict__ part, int n_split, int I, int cols, int sp, int which, float *__restrict__ out,
+                                                       int accumulate) {
+    // a block reduces 32 outputs: warp g sums the splits g, g + 8, ..., then the eight sub-sums are added in order (deterministic)
+    __shared__ float sub[8][32];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const long idx = blockIdx.x * 32L + lane, n = (long)I * cols;
     float s = 0.f;
-    for (int k = 0; k < n_split; ++k) s += part[((((size_t)k * 2 + sp) * 2 + which) * I) * cols + idx];
-    out[idx] = (accumulate ? out[idx] : 0.f) + s;
+    if (idx < n)
+        for (int k = g; k < n_split; k += 8) s += part[((((size_t)k * 2 + sp) * 2 + which) * I) * cols + idx];
+    sub[g][lane] = s;
+    __syncthreads();
+    if (g == 0 && idx < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sub[k][lane];
+        out[idx] = (accumulate ? out[idx] : 0.f) + t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ dense layers backward (elementwise parts)
@@ -1082,7 +1102,11 @@ static void grad_plan(const dpe_dims &d, int Bc, GradLayout &L) {
         L.tcs_floats = 3 * wmax * (R1 + 2048);
         L.tcs = take(L.tcs_floats);
     }
-    L.walkers_per_split = 64;
+    {   // k_bw_orbitals: thread = orbital column, block row = walkers_per_split walkers; ~8 blocks of 64 threads per SM also for small batches
+        const long col_blocks = (cols + 63) / 64;
+        long wps = (long)Bc * col_blocks / (148L * 8);
+        L.walkers_per_split = (int)std::max<long>(1, std::min<long>(64, wps));
+    }
     L.env_splits = (Bc + L.walkers_per_split - 1) / L.walkers_per_split;
     L.env_part = take((size_t)L.env_splits * 2 * 2 * I * cols);
     L.scr = take((size_t)2 * (max_k + 1) * (max_k + 1) + (size_t)(max_k + 1) * 2 * max_din + (size_t)4 * max_din * max_din);
@@ -1248,16 +1272,16 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
         if ((e = gemm_nt(m, bf, (long)I * cols, m->tao_w, (long)I * cols, dy, ldx, R1, dl, I * cols, false, s))) return e;
     } else {
     {
-        dim3 grid((cols + 127) / 128, L.env_splits);
-        k_bw_orbitals<<<grid, 128, 0, s>>>(Bc, N, U, I, d.n_dets, r, m->R_dev, fp(L.coef), fp(L.ainv), bf, m->sp_alpha[0], m->sp_alpha[1], m->alpha[0],
+        dim3 grid((cols + 63) / 64, L.env_splits);
+        k_bw_orbitals<<<grid, 64, 0, s>>>(Bc, N, U, I, d.n_dets, r, m->R_dev, fp(L.coef), fp(L.ainv), bf, m->sp_alpha[0], m->sp_alpha[1], m->alpha[0],
                                            m->alpha[1], m->env_w[0], m->env_w[1], cot, fp(L.dbf), fp(L.env_part), L.walkers_per_split);
         DPE_LAUNCH_CHECK(m);
         if (grad) {
             const long n = (long)I * cols;
             for (int sp = 0; sp < 2; ++sp) {
-                k_bw_env_reduce<<<(int)((n + 255) / 256), 256, 0, s>>>(fp(L.env_part), L.env_splits, I, cols, sp, 0, grad + leaf_off(m->env_w[sp]), accumulate);
+                k_bw_env_reduce<<<(int)((n + 31) / 32), 256, 0, s>>>(fp(L.env_part), L.env_splits, I, cols, sp, 0, grad + leaf_off(m->env_w[sp]), accumulate);
                 DPE_LAUNCH_CHECK(m);
-                k_bw_env_reduce<<<(int)((n + 255) / 256), 256, 0, s>>>(fp(L.env_part), L.env_splits, I, cols, sp, 1, grad + leaf_off(m->alpha[sp]), accumulate);
+                k_bw_env_reduce<<<(int)((n + 31) / 32), 256, 0, s>>>(fp(L.env_part), L.env_splits, I, cols, sp, 1, grad + leaf_off(m->alpha[sp]), accumulate);
                 DPE_LAUNCH_CHECK(m);
             }
         }
