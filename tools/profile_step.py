@@ -17,6 +17,7 @@ st = dpe.MCMCState.initialize_around_nuclei(B, phys, "gaussian", "el_ion_mapping
 mc = dpe.MetropolisHastingsMonteCarlo(dpe.MCMCConfigOptimization(n_inter_steps=1, initialization="gaussian"))
 gle = dpe.build_local_energy(f, forward_lap=True)
 cot = torch.randn(B, device="cuda") / B
+f.engine.set_params(params); f.engine.set_geometry(st.R, st.Z)          # (the callables do this themselves; a gradient-only run needs it)
 for rep in range(2):                       # rep 0 warms up (smem opt-ins, TMA descriptors), rep 1 is the one to read
     if "mcmc" in what:
         st = mc.run_inter_steps(f, st, params, phys.n_up, phys.n_dn, fixed)
