@@ -533,6 +533,86 @@ __global__ void __launch_bounds__(T) k_det_inverse(int N, int n_det, const float
     }
 }
 
+// The same inverse with ONE ROW PER THREAD held in registers (N <= NP <= 64; T = 32 or 64 threads per matrix, four matrices per block for T = 32).
+// The shared-memory form above moves ~1.2 MB through shared memory per 42 x 42 matrix (every element read and written once per pivot); here a
+// pivot step costs one warp-wide max (REDUX on a magnitude | row key), one row written to shared memory by its owner and N broadcast LDS.64 by the
+// others.  Rows are never exchanged: column p takes its pivot from the not-yet-used thread t_p with the largest |a[p]|, which is the row-swapped
+// algorithm with logical row p living in thread t_p; at the end  Ainv[p][t_k] = a_{t_p}[k]  and the sign carries the parity of k -> t_k.
+template <int NP, int T>
+__global__ void __launch_bounds__(T == 32 ? 128 : 64) k_det_inverse_rows(int N, int n_det, long n_mat, const float *__restrict__ mo, float *__restrict__ det,
+                                                                          float *__restrict__ ainv) {
+    constexpr int MPB = T == 32 ? 4 : 1;
+    __shared__ double rowp[MPB][NP], pv[MPB][NP];
+    __shared__ unsigned wkey[MPB][2];
+    __shared__ int tk[MPB][NP];
+    const int sub = threadIdx.x / T, t = threadIdx.x % T;
+    const long bd = blockIdx.x * (long)MPB + sub;
+    if (bd >= n_mat) return;                              // whole warps (T = 32) or the whole block (T = 64)
+    auto sync = [] { if (T == 32) __syncwarp(); else __syncthreads(); };
+    const long b = bd / n_det;
+    const int dt = (int)(bd - b * n_det), cols = n_det * N;
+    const float *mob = mo + b * (long)N * cols + (long)dt * N;
+    double a[NP];
+#pragma unroll
+    for (int o = 0; o < NP; ++o) a[o] = (t < N && o < N) ? (double)mob[(long)t * cols + o] : 0.0;
+    bool used = t >= N;
+    int my_p = -1;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        if (p < N) {
+            // key: [31] row still free, [30:6] exponent and 14 leading mantissa bits of |a[p]| (FP64), [5:0] 63 - row (ties go to the lowest row)
+            const unsigned key = used ? 0u : (0x80000000u | ((unsigned)__double2hiint(fabs(a[p])) & 0x7fffffc0u) | (unsigned)(63 - t));
+            unsigned best = __reduce_max_sync(0xffffffffu, key);
+            if (T == 64) {
+                if ((threadIdx.x & 31) == 0) wkey[sub][threadIdx.x >> 5] = best;
+                __syncthreads();
+                best = max(wkey[sub][0], wkey[sub][1]);
+            }
+            const int tp = 63 - (int)(best & 63u);
+            if (t == tp) {
+                const double piv = a[p], inv = 1.0 / piv;
+#pragma unroll
+                for (int o = 0; o < NP; ++o)
+                    if (o < N) { a[o] = o == p ? inv : a[o] * inv; rowp[sub][o] = a[o]; }
+                pv[sub][p] = piv;
+                tk[sub][p] = t;
+                used = true;
+                my_p = p;
+            }
+            sync();
+            if (t != tp) {
+                const double f = a[p];
+#pragma unroll
+                for (int o = 0; o < NP; ++o)
+                    if (o < N) a[o] = o == p ? -f * rowp[sub][p] : fma(-f, rowp[sub][o], a[o]);
+            }
+            sync();                                       // the next pivot row overwrites rowp (and wkey)
+        }
+    }
+    if (my_p >= 0) {
+        float *out = ainv + bd * (long)N * N + (long)my_p * N;
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+            if (k < N) out[tk[sub][k]] = (float)a[k];
+    }
+    if (t == 0) {
+        LogDetAcc logdet;
+        float sign = 1.f;
+        unsigned long long seen = 0ull;
+        for (int k = 0; k < N; ++k) {
+            const double piv = pv[sub][k];
+            logdet.mul(piv);
+            if (piv < 0.0) sign = -sign;
+            if (!((seen >> k) & 1ull)) {                  // cycle of the permutation k -> t_k: a cycle of length L contributes (-1)^(L - 1)
+                int j = k, len = 0;
+                while (!((seen >> j) & 1ull)) { seen |= 1ull << j; j = tk[sub][j]; ++len; }
+                if (!(len & 1)) sign = -sign;
+            }
+        }
+        det[bd * 2] = (float)logdet.value(); det[bd * 2 + 1] = sign;
+    }
+}
+
 // coef[b, d] = d log psi^2 / d log|det_d| = 2 rho w_d   (wavefunction.py:77-83; the shift is the constant max)
 __global__ void k_bw_combine(int Bc, int n_det, const float *__restrict__ det, float *__restrict__ coef, float *__restrict__ logpsi2) {
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -1252,7 +1332,15 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
     }
     {
         const size_t sm_inv = ((size_t)N * (N + 1) + N) * sizeof(double) + (size_t)N * sizeof(int) + 8;
-        if (N <= 32) k_det_inverse<32><<<Bc * d.n_dets, 32, sm_inv, s>>>(N, d.n_dets, mo, fp(L.det), fp(L.ainv));
+        static const bool inv_rows_off = getenv("DPE_DET_INV_ROWS") && atoi(getenv("DPE_DET_INV_ROWS")) == 0;
+        const long n_mat = (long)Bc * d.n_dets;
+        if (!inv_rows_off && N <= 64) {                   // one row per thread, in registers
+            const unsigned g4 = (unsigned)((n_mat + 3) / 4);
+            if (N <= 16) k_det_inverse_rows<16, 32><<<g4, 128, 0, s>>>(N, d.n_dets, n_mat, mo, fp(L.det), fp(L.ainv));
+            else if (N <= 32) k_det_inverse_rows<32, 32><<<g4, 128, 0, s>>>(N, d.n_dets, n_mat, mo, fp(L.det), fp(L.ainv));
+            else if (N <= 48) k_det_inverse_rows<48, 64><<<(unsigned)n_mat, 64, 0, s>>>(N, d.n_dets, n_mat, mo, fp(L.det), fp(L.ainv));
+            else k_det_inverse_rows<64, 64><<<(unsigned)n_mat, 64, 0, s>>>(N, d.n_dets, n_mat, mo, fp(L.det), fp(L.ainv));
+        } else if (N <= 32) k_det_inverse<32><<<Bc * d.n_dets, 32, sm_inv, s>>>(N, d.n_dets, mo, fp(L.det), fp(L.ainv));
         else k_det_inverse<64><<<Bc * d.n_dets, 64, sm_inv, s>>>(N, d.n_dets, mo, fp(L.det), fp(L.ainv));
     }
     DPE_LAUNCH_CHECK(m);

@@ -16,11 +16,22 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
+def _h_chain(n):
+    import deeperwin_b200 as dpe
+    return dpe.PhysicalConfig(name=f"HChain{n}", R=[[1.8 * k, 0.0, 0.0] for k in range(n)], Z=[1] * n, n_electrons=n, n_up=n // 2,
+                              el_ion_mapping=list(range(0, n, 2)) + list(range(1, n, 2)))
+
+
 @pytest.mark.parametrize("name,small,B", [("LiH", True, 24), ("LiH", False, 16), ("B", True, 12), ("N2", False, 6), ("HChain6", True, 8),
-                                          ("N2", False, 160)])          # >= 1024 (walker, electron) rows: the wide products run on the tensor cores
+                                          ("N2", False, 160),           # >= 1024 (walker, electron) rows: the wide products run on the tensor cores
+                                          ("Allene_TinyMol", True, 4),  # 22 electrons: inverse kernel with 32 register rows
+                                          ("Benzene", True, 3),         # 42 electrons: two warps per matrix, 48 register rows
+                                          ("HChain20", True, 3),        # 20 ions: more than one ion block in the envelope backward
+                                          ("HChain50", True, 2)])       # 50 electrons: 64 register rows
 def test_gradient_and_kfac_match_oracle(name, small, B):
     from oracle import gradient as og
-    phys, d, p32, p64, R, r, eng = make(name, B, small=small)
+    custom = _h_chain(int(name[6:])) if name.startswith("HChain") and name != "HChain6" else None
+    phys, d, p32, p64, R, r, eng = make(name, B, small=small, phys=custom)
     g = torch.Generator().manual_seed(5)
     cot = (torch.randn(B, generator=g) / B).float()
     flat, lp = eng.param_gradient(r.cuda(), cot.cuda(), with_kfac=True)

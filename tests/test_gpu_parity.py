@@ -20,11 +20,11 @@ GOLD = Path(__file__).parent / "golden"
 SMALL = dict(n_iterations=2, n_hidden_one_el=[16, 16], n_hidden_two_el=[4], emb_dim=8, n_dets=3)
 
 
-def make(name, B, seed=3, bias_scale=0.1, envelope_jitter=0.5, small=False, device="cuda:0", **dims_kw):
+def make(name, B, seed=3, bias_scale=0.1, envelope_jitter=0.5, small=False, device="cuda:0", phys=None, **dims_kw):
     import deeperwin_b200 as dpe
     from deeperwin_b200.engine import Engine
     from oracle import model as om
-    phys = dpe.PhysicalConfig(name=name)
+    phys = phys or dpe.PhysicalConfig(name=name)
     d = om.ModelDims(n_el=phys.n_electrons, n_up=phys.n_up, n_ion=len(phys.Z), Z_max=max(phys.Z), **{**(SMALL if small else {}), **dims_kw})
     p32 = om.cast_params(om.init_params(d, seed=seed, bias_scale=bias_scale, envelope_jitter=envelope_jitter), torch.float32)
     p64 = om.cast_params(p32, torch.float64)
