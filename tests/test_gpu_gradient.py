@@ -131,3 +131,39 @@ def test_tao_models_gradient_of_the_embedding_and_kfac(name, B, nd):
         assert _rel(A, fac[lname][0]) < 1e-5, (lname, "A")
         assert _rel(G, fac[lname][1]) < max(1e-4, 16 * floor_g), (lname, "G", _rel(G, fac[lname][1]), floor_g)
     assert torch.allclose(lp, eng.log_psi_sqr(r.cuda())[1], rtol=2e-6, atol=0)
+
+
+_PRODUCTS_SCRIPT = """
+import sys, numpy as np, torch
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+from test_gpu_parity import make
+phys, d, p32, p64, R, r, eng = make("N2", 160)
+cot = (torch.randn(160, generator=torch.Generator().manual_seed(5)) / 160).float()
+flat, lp = eng.param_gradient(r.cuda(), cot.cuda(), with_kfac=True)
+np.save(sys.argv[1], flat.cpu().numpy())
+"""
+
+
+def test_tensor_core_products_of_the_gradient_pass_match_the_fp32_core_products(tmp_path):
+    """The gradient + KFAC pass of N2 x 160 walkers with its wide products and dx = dz W^T on tcgen05 (default) against the same pass in a fresh
+    process with DPE_ATB_TC=0 DPE_GEMM_NT_TC=0 (the switches are read once per process): identical inputs up to those products, so the
+    difference is their own 3xTF32 rounding, propagated through the linear backward chain -- far below the oracle tolerance."""
+    import os, subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    out = {}
+    for tag, env in (("tc", {}), ("fp32", {"DPE_ATB_TC": "0", "DPE_GEMM_NT_TC": "0"})):
+        f = tmp_path / f"{tag}.npy"
+        subprocess.run([sys.executable, "-c", _PRODUCTS_SCRIPT, str(f)], cwd=root, env={**os.environ, **env}, check=True, timeout=600)
+        out[tag] = torch.from_numpy(np.load(f))
+    phys, d, p32, p64, R, r, eng = make("N2", 4)
+    worst = 0.0
+    for (mod, leaf), (off, size, rows, cols) in zip(eng.leaves, eng.leaf_shapes):
+        worst = max(worst, _rel(out["tc"][off:off + size], out["fp32"][off:off + size]))
+    kf = slice(eng.n_params, None)
+    for lname, din, dout, hb, rpw, a_off, g_off in eng.kfac_layers():
+        for o, n in ((a_off, (din + hb) ** 2), (g_off, dout * dout)):
+            worst = max(worst, _rel(out["tc"][kf][o:o + n], out["fp32"][kf][o:o + n]))
+    assert not torch.equal(out["tc"], out["fp32"])          # the switch did change the path
+    print("tensor-core vs FP32-core products, worst relative difference of a leaf / factor:", worst)
+    assert worst < 1e-4, worst          # measured 3.6e-5 (leaves whose terms cancel: both paths carry fp32 round-off of the summands, in different orders)
