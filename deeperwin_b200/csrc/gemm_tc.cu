@@ -1300,7 +1300,7 @@ int launch_gemm_tc(dpe_model *m, const GemmArgs &g, cudaStream_t s) {
 int launch_atb_tc(dpe_model *m, const float *At, float *Bt_hi, float *Bt_lo, long Rp, int Kc, int Mt, int Nb, float *part, cudaStream_t s) {
     static const bool off = getenv("DPE_ATB_TC") && atoi(getenv("DPE_ATB_TC")) == 0;
     if (off || m->gemm_path != 1 || tc_pair_mode() < 1) return DPE_ERR_UNSUPPORTED;
-    if ((Nb & 3) || (Kc % TC_BK) || Rp % Kc || (reinterpret_cast<size_t>(At) & 15) || (reinterpret_cast<size_t>(part) & 15)) return DPE_ERR_UNSUPPORTED;
+    if ((Nb & 3) || (Kc % TC_BK) || Rp % Kc || Rp >= (1L << 31) || (reinterpret_cast<size_t>(At) & 15) || (reinterpret_cast<size_t>(part) & 15)) return DPE_ERR_UNSUPPORTED;
     EncodeTiledFn enc = get_encode();
     if (!enc) return DPE_ERR_UNSUPPORTED;
     const int S = (int)(Rp / Kc);
@@ -1334,7 +1334,6 @@ int launch_atb_tc(dpe_model *m, const float *At, float *Bt_hi, float *Bt_lo, lon
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return set_error(DPE_ERR_CUDA, "cuTensorMapEncodeTiled(P) failed: %d", (int)r);
     }
-    if (Rp >= (1L << 31)) return DPE_ERR_UNSUPPORTED;
     if (int e = encode_w(&map_h, Bt_hi, Nb, (int)Rp, 128)) return e;
     if (int e = encode_w(&map_l, Bt_lo, Nb, (int)Rp, 128)) return e;
     if (int e = opt_in_smem(m, KID_GEMM_TC2P, k_gemm_tc2_3xtf32<false>)) return e;

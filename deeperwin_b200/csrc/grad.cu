@@ -300,6 +300,95 @@ __global__ void __launch_bounds__(256) k_atb_narrow(AtbArgs a) {
     }
 }
 
+// Second form of the narrow product: the per-row bookkeeping (row decode, walker weight, addresses) of k_atb_narrow costs more instructions than
+// its 32 FMAs per lane, and the kernel is issue bound (ncu: 125-157 warp instructions per row, issue active 55-67 % at 25 % occupancy).  Here a
+// HALF-warp takes a row and every lane an 8 x 8 patch: one pass of the loop body serves two rows, so the overhead per row halves while the loads in
+// flight (2 rows x UNR) and the FMA count per row stay the same.  ONES / WTS are compile-time (the G factors need neither).
+template <bool ONES, bool WTS>
+__global__ void __launch_bounds__(256, 2) k_atb_narrow2(AtbArgs a) {
+    __shared__ float red[8][33 * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, hw = lane >> 4, l16 = lane & 15;
+    const int m0 = (l16 >> 2) * 8, n0 = (l16 & 3) * 8;
+    const int Mt = a.Ma + (ONES ? 1 : 0);
+    const long r_begin = blockIdx.x * a.rows_per_split, r_end = min(a.rows, r_begin + a.rows_per_split);
+    const bool vecA = a.Ma == 32 && (a.lda & 3) == 0 && ((size_t)a.A & 15) == 0;
+    const bool vecB = a.Nb == 32 && (a.ldb & 3) == 0 && ((size_t)a.B & 15) == 0;
+    const unsigned NN = (unsigned)(a.N * a.N);
+    const bool first_m = (l16 >> 2) == 0;                  // these lanes also accumulate the ones row
+    float acc[8][8] = {}, acc1[8] = {};
+    constexpr int UNR = 2;
+    for (long rb = r_begin + warp * 2 + hw; rb < r_end; rb += 16 * UNR) {
+        float av[UNR][8], bv[UNR][8], w[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const long r = rb + 16 * u;
+            bool ok = r < r_end;
+            const unsigned r32 = (unsigned)r;
+            if (ok && a.sel >= 0) {
+                const unsigned pidx = r32 % NN, i = pidx / (unsigned)a.N, j = pidx - i * (unsigned)a.N;
+                ok = ((((int)i < a.U) == ((int)j < a.U)) ? 0 : 1) == a.sel;
+            }
+            w[u] = ok ? (WTS ? a.wts[r32 / (unsigned)a.rpw] : 1.f) : 0.f;
+            const long pr = !ok ? -1 : (a.rm.seg_len ? (long)(r32 / (unsigned)a.rm.seg_len) * a.rm.seg_stride + a.rm.seg_off + r32 % (unsigned)a.rm.seg_len : r);
+            if (pr >= 0 && vecA) {
+                const float4 t0 = *reinterpret_cast<const float4 *>(a.A + pr * a.lda + m0), t1 = *reinterpret_cast<const float4 *>(a.A + pr * a.lda + m0 + 4);
+                av[u][0] = t0.x; av[u][1] = t0.y; av[u][2] = t0.z; av[u][3] = t0.w; av[u][4] = t1.x; av[u][5] = t1.y; av[u][6] = t1.z; av[u][7] = t1.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) av[u][k] = (pr >= 0 && m0 + k < a.Ma) ? a.A[pr * a.lda + m0 + k] : 0.f;
+            }
+            if (pr >= 0 && vecB) {
+                const float4 t0 = *reinterpret_cast<const float4 *>(a.B + pr * a.ldb + n0), t1 = *reinterpret_cast<const float4 *>(a.B + pr * a.ldb + n0 + 4);
+                bv[u][0] = t0.x; bv[u][1] = t0.y; bv[u][2] = t0.z; bv[u][3] = t0.w; bv[u][4] = t1.x; bv[u][5] = t1.y; bv[u][6] = t1.z; bv[u][7] = t1.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) bv[u][k] = (pr >= 0 && n0 + k < a.Nb) ? a.B[pr * a.ldb + n0 + k] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float x = WTS ? av[u][k] * w[u] : av[u][k];          // (rows that do not count were loaded as zeros)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) acc[k][v] = fmaf(x, bv[u][v], acc[k][v]);
+            }
+            if (ONES) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) acc1[v] = fmaf(w[u], bv[u][v], acc1[v]);
+            }
+        }
+    }
+    // the two rows of a pass: half-warp 1 is added to half-warp 0 (fixed order)
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[k][v] += __shfl_down_sync(0xffffffffu, acc[k][v], 16);
+    if (ONES) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc1[v] += __shfl_down_sync(0xffffffffu, acc1[v], 16);
+    }
+    if (hw == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+                if (m0 + k < a.Ma && n0 + v < a.Nb) red[warp][(m0 + k) * a.Nb + n0 + v] = acc[k][v];
+        if (ONES && first_m)
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+                if (n0 + v < a.Nb) red[warp][a.Ma * a.Nb + n0 + v] = acc1[v];
+    }
+    __syncthreads();
+    float *P = a.part + (size_t)blockIdx.x * Mt * a.Nb;
+    for (int t = threadIdx.x; t < Mt * a.Nb; t += 256) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) sacc += red[wv][t];
+        P[t] = sacc;
+    }
+}
+
 // C[m, n] (ldc) = (accumulate ? C : 0) + scale * sum_split P[split][m, n]      (fixed summation order: deterministic)
 // A block reduces 32 outputs: warp g sums the partials g, g + 8, ... of its 32 outputs, then the eight sub-sums are added in order.
 __global__ void __launch_bounds__(256) k_atb_reduce(const float *__restrict__ part, int n_split, int Mt, int Nb, float *__restrict__ C, long ldc, float scale,
@@ -390,7 +479,12 @@ static int atb(GradCtx &g, float *out, long ldc, const float *A, long lda, int M
         a.n_split = (int)n_blocks;
         a.rows_per_split = (rows + n_blocks - 1) / n_blocks;
         a.part = g.part;
-        k_atb_narrow<<<(unsigned)n_blocks, 256, 0, g.s>>>(a);
+        static const bool narrow_v1 = getenv("DPE_ATB_NARROW_V1") != nullptr;
+        if (narrow_v1) k_atb_narrow<<<(unsigned)n_blocks, 256, 0, g.s>>>(a);
+        else if (a.ones && a.wts) k_atb_narrow2<true, true><<<(unsigned)n_blocks, 256, 0, g.s>>>(a);
+        else if (a.ones) k_atb_narrow2<true, false><<<(unsigned)n_blocks, 256, 0, g.s>>>(a);
+        else if (a.wts) k_atb_narrow2<false, true><<<(unsigned)n_blocks, 256, 0, g.s>>>(a);
+        else k_atb_narrow2<false, false><<<(unsigned)n_blocks, 256, 0, g.s>>>(a);
         DPE_LAUNCH_CHECK(g.m);
         k_atb_reduce<<<(int)((per + 31) / 32), 256, 0, g.s>>>(g.part, a.n_split, Mt, Nb, out, ldc, scale, g.accumulate ? 1 : 0);
         DPE_LAUNCH_CHECK(g.m);
@@ -400,14 +494,14 @@ static int atb(GradCtx &g, float *out, long ldc, const float *A, long lda, int M
     if (Mt > 64 && Nb > 64 && rows >= 1024 && rows < (1L << 31) && sel < 0 && !(Nb & 3) && g.tcs && g.m->gemm_path == 1 && tc_pair_mode() >= 1 && !atb_tc_off) {
         // wide operands on the tensor cores: split-K over chunks of Kc rows, 3xTF32 (FP32-accurate) on the CTA-pair dense-layer kernel.
         // (Short products stay on the FP32 cores: the accumulation-bias compensation assumes full chunks, and there is nothing to gain.)
-        // Kc balances waves of (256 feature x <= 256 row) tiles over the 74 CTA pairs against the size of the partial products.
+        // Kc balances waves of (256 feature x <= 256 row) tiles over the CTA pairs (74 on a B200) against the size of the partial products.
         const int tiles_min = (Mt + 255) / 256, nmma = (((Mt + tiles_min - 1) / tiles_min) + 31) / 32 * 32;
         const long tpc = (long)((Mt + nmma - 1) / nmma) * ((Nb + 255) / 256);
         int Kc = 0; double best = 0.0;
         for (int kc = 256; kc <= 2048; kc *= 2) {
             const long S = (rows + kc - 1) / kc;
             if (per * (size_t)S > g.part_floats || (size_t)(Mt + 2 * Nb) * (size_t)(S * kc) > g.tcs_floats) continue;
-            const long waves = (S * tpc + 73) / 74;
+            const long n_pairs = std::max(1, g.m->n_sm / 2), waves = (S * tpc + n_pairs - 1) / n_pairs;
             const double cost = (double)waves * (kc * 120.0 + 25000.0) + (double)S * per * 8.0 / 6.0e12 * 1.9e9 / 1.0;     // clocks: MMA waves + partial write / read
             if (!Kc || cost < best) { Kc = kc; best = cost; }
         }
