@@ -1003,7 +1003,7 @@ __global__ void __launch_bounds__(256) k_bw_pair(PairBwArgs a) {
 // registers and every lane of a warp reads the SAME weight row, so a product costs 8 broadcast LDS.128 per pair and the kernel is FMA / HBM bound.
 // The layer inputs x^it go to global memory on the way forward (they are outputs anyway) and are read back on the way down; the tanh output of a
 // residual layer is recovered as t = sqrt2 x^{it+1} - x^it.
-constexpr int PBR_THREADS = 128;
+constexpr int PBR_THREADS = 384;          // one block per SM: one copy of the weights (64 KB), the rest of the 256 KB stays L1 for the row-per-thread global accesses
 __device__ __forceinline__ void st_row32(float *dst, const float (&v)[32]) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) reinterpret_cast<float4 *>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -1560,7 +1560,7 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
         if (rows_ok) {                // default widths: one thread per pair, operands in registers
             const size_t sm_rows = ((size_t)nit * 4 * 1024 + (size_t)nit * 64) * sizeof(float);
             if ((e = opt_in_smem(m, KID_BW_PAIR_ROWS, k_bw_pair_rows))) return e;
-            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220u << 10) / (sm_rows + 1024)));
+            const int per_sm = 1;
             k_bw_pair_rows<<<(unsigned)std::min<long>((P2 + PBR_THREADS - 1) / PBR_THREADS, 148L * per_sm), PBR_THREADS, sm_rows, s>>>(a);
         } else {
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u << 10) / sm_pair));
