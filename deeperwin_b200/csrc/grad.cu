@@ -1035,12 +1035,25 @@ __global__ void __launch_bounds__(PBR_THREADS) k_bw_pair_rows(PairBwArgs a) {
     const int N = a.N, U = a.U, D = N - U, n_same = U * U + D * D, n_diff = 2 * U * D;
     const long n_walkers = a.n_pairs / ((long)N * N);
     constexpr float RS2 = 0.70710678118654752f, S2 = 1.41421356237309505f;
-    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < a.n_pairs; p += (long)gridDim.x * blockDim.x) {
-        const long b = p / ((long)N * N);
-        const int ij = (int)(p - b * N * N), i = ij / N, j = ij - i * N;
-        const int sd = ((i < U) == (j < U)) ? 0 : 1;
-        const long pc = sd == 0 ? b * n_same + (i < U ? i * U + j : U * U + (i - U) * D + (j - U))
-                                : n_walkers * n_same + b * n_diff + (i < U ? i * D + (j - U) : U * D + (i - U) * U + j);       // class-major row
+    // threads walk the pairs in CLASS-MAJOR order (the order of px / dzh / dzw_cm): all lanes of a warp but one boundary warp use the same
+    // weight matrices, so the weight rows are true broadcasts (in pair order every warp mixes the two spin classes: two wavefronts per LDS)
+    const long n_same_rows = n_walkers * n_same;
+    for (long pc = blockIdx.x * (long)blockDim.x + threadIdx.x; pc < a.n_pairs; pc += (long)gridDim.x * blockDim.x) {
+        const int sd = pc < n_same_rows ? 0 : 1;
+        long b; int i, j;
+        if (sd == 0) {
+            b = pc / n_same;
+            const int k = (int)(pc - b * n_same);
+            if (k < U * U) { i = k / U; j = k - i * U; }
+            else { const int k2 = k - U * U; i = U + k2 / D; j = U + (k2 - (i - U) * D); }
+        } else {
+            const long q = pc - n_same_rows;
+            b = q / n_diff;
+            const int k = (int)(q - b * n_diff);
+            if (k < U * D) { i = k / D; j = U + (k - i * D); }
+            else { const int k2 = k - U * D; i = U + k2 / U; j = k2 - (i - U) * U; }
+        }
+        const long p = (b * N + i) * N + j;                  // row of dzw (pair order)
         const float *ri = a.r + (b * N + i) * 3, *rj = a.r + (b * N + j) * 3;
         const float dx0 = rj[0] - ri[0], dy0 = rj[1] - ri[1], dz0 = rj[2] - ri[2];
         const float dist = i == j ? 0.f : sqrtf(dx0 * dx0 + dy0 * dy0 + dz0 * dz0);
