@@ -473,7 +473,8 @@ static int atb(GradCtx &g, float *out, long ldc, const float *A, long lda, int M
     const int Mt = Ma + a.ones;
     const size_t per = (size_t)Mt * Nb;
     if (Ma <= 32 && Nb <= 32 && rows < (1L << 31)) {               // narrow operands: the streaming kernel
-        long n_blocks = std::min<long>((rows + 255) / 256, 148L * 4);
+        // two blocks are resident per SM (registers): one wave, and half the partial products of the earlier two-wave grid to reduce
+        long n_blocks = std::min<long>((rows + 255) / 256, 148L * 2);
         while (n_blocks > 1 && per * n_blocks > g.part_floats) n_blocks = (n_blocks + 1) / 2;
         if (per * n_blocks > g.part_floats) return set_error(DPE_ERR_WORKSPACE, "gradient workspace too small for a %d x %d product", Mt, Nb);
         a.n_split = (int)n_blocks;
