@@ -1381,17 +1381,30 @@ __global__ void k_symmetrize_xx(int km, const float *__restrict__ XX, float coun
     out[idx] = q < km ? XX[(long)p * km + q] : (p < km ? XX[(long)km * km + p] : count);
 }
 
-// completes the A factor of a biased layer whose [x | 1]^T x block ((din + 1) x din, row stride din + 1) has been accumulated: the ones column is the
-// transpose of the ones row, the corner the row count
-__global__ void k_complete_ones(float *__restrict__ A, int din, float rows) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x, T = din + 1;
-    if (p > din) return;
-    A[(long)p * T + din] = p < din ? A[(long)din * T + p] : rows;
+// (completion of the A factor of a biased layer whose [x | 1]^T x block ((din + 1) x din, row stride din + 1) has been accumulated: the ones column is the
+// transpose of the ones row, the corner the row count -- k_kfac_complete below)
+// The end of the KFAC pass for ALL layers in two launches (it was one k_complete_ones and two scaling launches per layer, ~90 launches of a few
+// microseconds each): the table travels as a kernel argument.
+constexpr int KFIN_MAX = 8 * DPE_MAX_ITER + 4;
+struct KfacFinTab {
+    int n;
+    long long a_off[KFIN_MAX], g_off[KFIN_MAX];
+    int din[KFIN_MAX], nA[KFIN_MAX], nG[KFIN_MAX], ones[KFIN_MAX];      // nA = (din + bias)^2, nG = dout^2; ones: complete the ones column first
+    float rows[KFIN_MAX];
+};
+__global__ void __launch_bounds__(128) k_kfac_complete(float *__restrict__ kfac, const __grid_constant__ KfacFinTab t) {
+    const int k = blockIdx.x;
+    if (!t.ones[k]) return;
+    const int din = t.din[k], T = din + 1;
+    float *A = kfac + t.a_off[k];
+    for (int p = threadIdx.x; p <= din; p += blockDim.x) A[(long)p * T + din] = p < din ? A[(long)din * T + p] : t.rows[k];
 }
-
-__global__ void k_scale(float *p, long n, float s) {
-    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (i < n) p[i] *= s;
+__global__ void __launch_bounds__(256) k_kfac_scale(float *__restrict__ kfac, const __grid_constant__ KfacFinTab t) {
+    const int k = blockIdx.y >> 1, g = blockIdx.y & 1;
+    float *p = kfac + (g ? t.g_off[k] : t.a_off[k]);
+    const int n = g ? t.nG[k] : t.nA[k];
+    const float s = 1.f / t.rows[k];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] *= s;
 }
 
 // ------------------------------------------------------------------------------------------------ one chunk: forward (kept) + backward
@@ -1737,20 +1750,22 @@ int dpe_param_gradient(dpe_model *m, const float *r_dev, int32_t n_walkers, cons
                 }
             base += it + 1 < d.n_iterations ? 8 : 5;
         }
+        KfacFinTab tab;
+        tab.n = n_layers;
+        int n_max = 1;
         for (int k = 0; k < n_layers; ++k) {
             const KfacLayer &l = kl[k];
-            const float rows = (float)((double)n_walkers * l.rows_per_walker);
             const bool is_hel = strstr(l.name, "/h_el_") != nullptr && strstr(l.name, "/h_el_ion_") == nullptr;          // assembled with its ones row and column already
-            if (l.has_bias && !is_hel) {
-                k_complete_ones<<<(l.din + 1 + 127) / 128, 128, 0, s>>>(kfac_dev + l.a_off, l.din, rows);
-                DPE_LAUNCH_CHECK(m);
-            }
-            const long nA = (long)(l.din + l.has_bias) * (l.din + l.has_bias), nG = (long)l.dout * l.dout;
-            k_scale<<<(int)((nA + 255) / 256), 256, 0, s>>>(kfac_dev + l.a_off, nA, 1.f / rows);
-            DPE_LAUNCH_CHECK(m);
-            k_scale<<<(int)((nG + 255) / 256), 256, 0, s>>>(kfac_dev + l.g_off, nG, 1.f / rows);
-            DPE_LAUNCH_CHECK(m);
+            tab.a_off[k] = l.a_off; tab.g_off[k] = l.g_off; tab.din[k] = l.din;
+            tab.nA[k] = (l.din + l.has_bias) * (l.din + l.has_bias); tab.nG[k] = l.dout * l.dout;
+            tab.ones[k] = (l.has_bias && !is_hel) ? 1 : 0;
+            tab.rows[k] = (float)((double)n_walkers * l.rows_per_walker);
+            n_max = std::max(n_max, std::max(tab.nA[k], tab.nG[k]));
         }
+        k_kfac_complete<<<n_layers, 128, 0, s>>>(kfac_dev, tab);
+        DPE_LAUNCH_CHECK(m);
+        k_kfac_scale<<<dim3((unsigned)std::min(32, (n_max + 2047) / 2048), (unsigned)(2 * n_layers)), 256, 0, s>>>(kfac_dev, tab);
+        DPE_LAUNCH_CHECK(m);
     }
     return DPE_OK;
 }
