@@ -419,36 +419,43 @@ __global__ void __launch_bounds__(256) k_atb_reduce(const float *__restrict__ pa
 __device__ __forceinline__ float to_tf32(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
 __global__ void __launch_bounds__(256) k_atb_prep(const float *__restrict__ src, long ld, int ncols, int ones, long rows, long Rp, int Kc, int rpw,
                                                   const float *__restrict__ wts, RowMap rm, int mode, float *__restrict__ o0, float *__restrict__ o1) {
+    // (ncu on the first version: issue-bound, ~250 warp instructions per 32 x 32 tile, most of them 64-bit divisions of the row decode done by every
+    // thread: the per-row work -- physical row, walker weight -- is done once per row by the first warp, and the indices are 32-bit)
     __shared__ float tile[32][33];
-    const long r0 = blockIdx.x * 32L;
+    __shared__ long poff[32];          // element offset of the row in src, or -1
+    __shared__ float wrow[32];
+    const unsigned r0 = blockIdx.x * 32u;                    // rows < 2^31 (launcher)
     const int c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nc = ncols + ones;
+    if (threadIdx.x < 32) {
+        const unsigned r = r0 + threadIdx.x;
+        const bool ok = r < (unsigned)rows;
+        const long pr = !ok ? -1 : (rm.seg_len ? (long)(r / (unsigned)rm.seg_len) * rm.seg_stride + rm.seg_off + r % (unsigned)rm.seg_len : (long)r);
+        poff[threadIdx.x] = ok ? pr * ld : -1;
+        wrow[threadIdx.x] = ok ? (wts ? wts[r / (unsigned)rpw] : 1.f) : 0.f;
+    }
+    __syncthreads();
+    const int c = c0 + tx;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int rr = ty + 8 * q, c = c0 + tx;
-        const long r = r0 + rr;
+        const int rr = ty + 8 * q;
+        const long po = poff[rr];
         float v = 0.f;
-        if (r < rows && c < nc) {
-            const unsigned r32 = (unsigned)r;
-            const long pr = rm.seg_len ? (long)(r32 / (unsigned)rm.seg_len) * rm.seg_stride + rm.seg_off + r32 % (unsigned)rm.seg_len : r;
-            v = c < ncols ? src[pr * ld + c] : 1.f;
-            if (wts) v *= wts[r32 / (unsigned)rpw];
-        }
+        if (po >= 0 && c < nc) v = (c < ncols ? src[po + c] : 1.f) * wrow[rr];
         tile[rr][tx] = v;
     }
     __syncthreads();
-    const long r = r0 + tx;
-    const long sc = r / Kc;
-    const int k = (int)(r - sc * Kc);
+    const unsigned r = r0 + tx, sc = r / (unsigned)Kc, k = r - sc * (unsigned)Kc;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int cc = ty + 8 * q, c = c0 + cc;
-        if (c >= nc) continue;
+        const int cc = ty + 8 * q, co = c0 + cc;
+        if (co >= nc) continue;
         const float v = tile[tx][cc];
-        if (mode == 0) o0[((size_t)sc * nc + c) * Kc + k] = v;
+        if (mode == 0) o0[((size_t)sc * nc + co) * Kc + k] = v;
         else {
             const float h = to_tf32(v);
-            o0[(size_t)c * Rp + r] = h;
-            o1[(size_t)c * Rp + r] = to_tf32(v - h);
+            const size_t o = (size_t)co * Rp + r;
+            o0[o] = h;
+            o1[o] = to_tf32(v - h);
         }
     }
 }
@@ -729,6 +736,7 @@ __global__ void k_bw_combine(int Bc, int n_det, const float *__restrict__ det, f
 //   dmo = coef[b, det] Ainv[b, det][orb][i];  env and its parameter derivatives recomputed;  dbf = dmo env;  denv = dmo bf
 //   d weights[J, col] += c_b denv exp(-a d);  d alpha[J, col] += c_b denv w exp(-a d) (-d) sigmoid(alpha)
 // partial sums per split: part[split][spin][2][I][cols]
+template <int MAXI>          // ions per register block (4 / 8 / 16): four arrays of MAXI floats per thread decide the occupancy of this latency-bound kernel
 __global__ void __launch_bounds__(64) k_bw_orbitals(int Bc, int N, int U, int I, int n_det, const float *__restrict__ r, const float *__restrict__ R,
                                                     const float *__restrict__ coef, const float *__restrict__ ainv, const float *__restrict__ bf,
                                                     const float *__restrict__ spa_up, const float *__restrict__ spa_dn, const float *__restrict__ alpha_up,
@@ -740,7 +748,6 @@ __global__ void __launch_bounds__(64) k_bw_orbitals(int Bc, int N, int U, int I,
     if (col >= cols) return;
     const int dt = col / N, q = col - dt * N;
     const int b0 = blockIdx.y * walkers_per_split, b1 = min(Bc, b0 + walkers_per_split);
-    constexpr int MAXI = 16;
     for (int sp = 0; sp < 2; ++sp) {
         const float *spa = sp ? spa_dn : spa_up, *al = sp ? alpha_dn : alpha_up, *wt = sp ? w_dn : w_up;
         const int i_lo = sp ? U : 0, i_hi = sp ? N : U;
@@ -1482,7 +1489,11 @@ static int grad_chunk(dpe_model *m, const float *r, int Bc, const float *cot, fl
     } else {
     {
         dim3 grid((cols + 63) / 64, L.env_splits);
-        k_bw_orbitals<<<grid, 64, 0, s>>>(Bc, N, U, I, d.n_dets, r, m->R_dev, fp(L.coef), fp(L.ainv), bf, m->sp_alpha[0], m->sp_alpha[1], m->alpha[0],
+        if (I <= 4) k_bw_orbitals<4><<<grid, 64, 0, s>>>(Bc, N, U, I, d.n_dets, r, m->R_dev, fp(L.coef), fp(L.ainv), bf, m->sp_alpha[0], m->sp_alpha[1], m->alpha[0],
+                                           m->alpha[1], m->env_w[0], m->env_w[1], cot, fp(L.dbf), fp(L.env_part), L.walkers_per_split);
+        else if (I <= 8) k_bw_orbitals<8><<<grid, 64, 0, s>>>(Bc, N, U, I, d.n_dets, r, m->R_dev, fp(L.coef), fp(L.ainv), bf, m->sp_alpha[0], m->sp_alpha[1], m->alpha[0],
+                                           m->alpha[1], m->env_w[0], m->env_w[1], cot, fp(L.dbf), fp(L.env_part), L.walkers_per_split);
+        else k_bw_orbitals<16><<<grid, 64, 0, s>>>(Bc, N, U, I, d.n_dets, r, m->R_dev, fp(L.coef), fp(L.ainv), bf, m->sp_alpha[0], m->sp_alpha[1], m->alpha[0],
                                            m->alpha[1], m->env_w[0], m->env_w[1], cot, fp(L.dbf), fp(L.env_part), L.walkers_per_split);
         DPE_LAUNCH_CHECK(m);
         if (grad) {
