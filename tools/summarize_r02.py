@@ -68,7 +68,7 @@ def metrics():
     lines = ["# Round 2: `ncu --set full` key metrics\n",
              "Command per kernel: `ncu --set full --clock-control none --import-source on -k regex:<kernel> -s <skip> -c <n> -o <rep> python tools/profile_step.py N2 4096 <passes>`,",
              "then `ncu -i <rep> --page raw --csv`.  N2 x 4096 walkers, one B200, second repetition of each pass.  One row per captured launch.\n"]
-    for f in ("gemm_main", "conv", "det_trace", "mean", "pair_fwd", "det_factor", "fwd_kernels", "grad_atb", "grad_pair"):
+    for f in ("gemm_main", "conv", "det_trace", "mean", "pair_fwd", "det_factor", "fwd_kernels", "grad_atb", "grad_pair", "grad_new_a", "grad_new_b"):
         p = SRC / f"{f}.raw.csv"
         if not p.exists() or p.stat().st_size < 1000:
             continue
