@@ -198,7 +198,9 @@ int dpe_get_mcmc_graph(const dpe_model *m);
  * TAO models (use_taos): the gradient covers the embedding leaves (the flat vector has no orbital leaves), the factor list has no orbital layers, and
  * the geometry cache of dpe_model_set_tao_cache is held fixed (its cotangents belong to the geometry-only nets, outside this library).
  * Both outputs are sums / means over THIS device's walkers: with several GPUs the caller all-reduces the two buffers (one flat
- * all-reduce, optimizers.py:133, kfac optimizer.py:1151).  Batches larger than the workspace are processed in chunks. */
+ * all-reduce, optimizers.py:133, kfac optimizer.py:1151).  The workspace (dpe_gradient_workspace_bytes) holds the saved activations of a
+ * chunk of walkers, the split-K partial products and the transposed operands of the tensor-core products (N2 x 4096 walkers: 3.4 GB);
+ * batches larger than the workspace handed in are processed in chunks that accumulate. */
 int32_t dpe_kfac_layer_count(const dpe_model *m);
 int64_t dpe_kfac_floats(const dpe_model *m);
 int dpe_kfac_layer(const dpe_model *m, int32_t index, char *name, int32_t name_len, int32_t *din, int32_t *dout, int32_t *has_bias,
